@@ -1,0 +1,19 @@
+# Builds the C-ABI library (sm_100a only) and the oracle's C twin.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
+SRC := $(wildcard avsr_tf1_b200/csrc/*.cu)
+OBJ := $(SRC:.cu=.o)
+LIB := avsr_tf1_b200/lib/libavsr_b200.so
+
+all: $(LIB)
+
+%.o: %.cu avsr_tf1_b200/csrc/common.cuh include/avsr_b200.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJ)
+	mkdir -p avsr_tf1_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)
+
+clean:
+	rm -f $(OBJ) $(LIB)

@@ -1,0 +1,102 @@
+"""ctypes binding of the C ABI in include/avsr_b200.h (libavsr_b200.so).
+
+There is no CPU fallback: if the shared library is missing, importing any op
+raises.  Build it with ``make`` (or ``python -c 'import __graft_entry__ as g; g.build()'``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libavsr_b200.so')
+
+c_float_p = C.POINTER(C.c_float)
+c_int_p = C.POINTER(C.c_int)
+
+
+class AvsrAttnMech(C.Structure):
+    _fields_ = [
+        ('kind', C.c_int), ('Tm', C.c_int), ('Dm', C.c_int), ('A', C.c_int),
+        ('values', C.c_void_p), ('keys', C.c_void_p), ('mem_len', C.c_void_p),
+        ('Wl', C.c_void_p), ('Wq', C.c_void_p), ('v', C.c_void_p), ('g', C.c_void_p), ('bias', C.c_void_p),
+        ('align', C.c_void_p), ('hc', C.c_void_p), ('pq', C.c_void_p),
+        ('dkeys', C.c_void_p), ('dvalues', C.c_void_p), ('dWl', C.c_void_p), ('dWq', C.c_void_p),
+        ('dv', C.c_void_p), ('dg', C.c_void_p), ('dbias', C.c_void_p), ('dpq', C.c_void_p),
+    ]
+
+
+class AvsrRnnSeq(C.Structure):
+    _fields_ = [
+        ('T', C.c_int), ('B', C.c_int), ('H', C.c_int), ('n_mech', C.c_int), ('output_attention', C.c_int),
+        ('len', C.c_void_p), ('gates', C.c_void_p), ('Wrec', C.c_void_p), ('c0', C.c_void_p),
+        ('S', C.c_void_p), ('craw', C.c_void_p), ('out', C.c_void_p), ('cT', C.c_void_p), ('hT', C.c_void_p),
+        ('mech', AvsrAttnMech * 2),
+        ('dout', C.c_void_p), ('dcT', C.c_void_p), ('dhT', C.c_void_p), ('dZ', C.c_void_p), ('dA', C.c_void_p),
+        ('dWrec', C.c_void_p), ('dc0', C.c_void_p), ('dh0', C.c_void_p), ('work', C.c_void_p),
+    ]
+
+
+ATTN_KINDS = {'luong': 0, 'scaled_luong': 1, 'bahdanau': 2, 'normed_bahdanau': 3}
+
+_P, _I, _L, _F, _D = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+
+# name -> (restype, argtypes).  Must list every symbol include/avsr_b200.h declares
+# (tests/test_abi.py checks both directions).
+PROTOTYPES = {
+    'avsr_last_error': (C.c_char_p, []),
+    'avsr_version': (_I, []),
+    'avsr_launch_count': (C.c_ulonglong, []),
+    'avsr_set_tensor_cores': (_I, [_I]),
+    'avsr_gemm': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _P]),
+    'avsr_colsum': (_I, [_P, _P, _I, _I, _I, _P]),
+    'avsr_bn_stats': (_I, [_P, _P, _L, _I, _P]),
+    'avsr_bn_apply_train': (_I, [_P, _P, _L, _I, _P, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
+    'avsr_bn_apply_eval': (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _F, _P]),
+    'avsr_bn_bwd_stats': (_I, [_P, _P, _P, _L, _I, _P]),
+    'avsr_bn_bwd_apply': (_I, [_P, _P, _P, _L, _I, _P, _D, _P, _P, _P, _P, _P]),
+    'avsr_reverse_sequence': (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    'avsr_transpose01': (_I, [_P, _P, _P, _I, _I, _I]),
+    'avsr_rnn_work_floats': (C.c_size_t, [_I, _I, _I, _I, _I]),
+    'avsr_rnn_seq_fwd': (_I, [_P, C.POINTER(AvsrRnnSeq)]),
+    'avsr_rnn_seq_bwd': (_I, [_P, C.POINTER(AvsrRnnSeq)]),
+    'avsr_normed_v_fwd': (_I, [_P, _P, _P, _I, _P]),
+    'avsr_normed_v_bwd': (_I, [_P, _P, _P, _P, _I, _P, _P]),
+    'avsr_embedding_fwd': (_I, [_P, _P, _I, _I, _P, _L, _P]),
+    'avsr_embedding_bwd': (_I, [_P, _P, _P, _L, _I, _I, _P]),
+    'avsr_seq_loss': (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _F, _P, _P]),
+    'avsr_sumsq': (_I, [_P, _P, _L, _P]),
+    'avsr_axpy': (_I, [_P, _F, _P, _P, _L]),
+    'avsr_adam_clip_step': (_I, [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F]),
+    'avsr_greedy_pick': (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    'avsr_beam_step': (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
+    'avsr_gather_rows': (_I, [_P, _P, _P, _L, _I, _P]),
+}
+
+_lib = None
+
+
+class AvsrError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libavsr_b200.so (once).  Raises if it has not been built - by design."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AvsrError(f'{LIB_PATH} not found: build the CUDA library first (make). '
+                        'There is deliberately no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise AvsrError(load().avsr_last_error().decode('utf-8', 'replace'))

@@ -1,0 +1,107 @@
+// Shared helpers for the avsr_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace avsr {
+
+// ---- error reporting across the C ABI (no exceptions) ----------------------
+void set_error(const char* fmt, ...);
+extern unsigned long long g_launch_count;  // kernels launched by this library
+
+#define AVSR_CHECK_CUDA(expr)                                                          \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      ::avsr::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+#define AVSR_REQUIRE(cond, ...)                                                        \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      ::avsr::set_error(__VA_ARGS__);                                                  \
+      return 2;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+// launch + count + check (no sync)
+#define AVSR_LAUNCH(kernel, grid, block, smem, stream, ...)                            \
+  do {                                                                                 \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                        \
+    ++::avsr::g_launch_count;                                                          \
+    AVSR_CHECK_CUDA(cudaGetLastError());                                               \
+  } while (0)
+
+#define AVSR_TRY(expr)                                                                 \
+  do {                                                                                 \
+    int _r = (expr);                                                                   \
+    if (_r != 0) return _r;                                                            \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers ---------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// tanh via exp: accurate to ~1e-7 relative (tanh.approx is only ~5e-4)
+__device__ __forceinline__ float tanhf_acc(float x) {
+  float ax = fabsf(x);
+  float e = __expf(-2.0f * ax);
+  float r = (1.0f - e) / (1.0f + e);
+  return copysignf(r, x);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide reductions for blockDim.x <= 1024 (multiple of 32); `sh` has >= 33 floats
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? sh[lane] : 0.0f;
+    t = warp_sum(t);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? sh[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+// ---- internal entry points shared between translation units ------------------
+// C[M,N](ldc) = beta*C + op(A)*op(B) (+bias[N]); beta in {0,1}.  op(A) is MxK:
+// transA==0 -> A stored [M,K] row-major with leading dim lda; transA==1 -> stored [K,M].
+int gemm(cudaStream_t st, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
+         int ldb, float* C, int ldc, float beta, const float* bias);
+// exact fp32 CUDA-core implementation (gemm_simt.cu)
+int gemm_simt(cudaStream_t st, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
+              int ldb, float* C, int ldc, float beta, const float* bias);
+
+}  // namespace avsr

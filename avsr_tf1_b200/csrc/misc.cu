@@ -1,0 +1,509 @@
+// Memory-bound helpers of the hot path: input batch-norm, reverse_sequence,
+// embedding, masked sequence loss, global-norm / clip / Adam, decode helpers.
+#include <float.h>
+
+#include "../../include/avsr_b200.h"
+#include "common.cuh"
+
+namespace avsr {
+
+// ---- column statistics: out[f] += sum_r a[r,f]; out[F+f] += sum_r a[r,f]*b[r,f] (b==null -> a*a)
+__global__ void colstats_kernel(const float* __restrict__ a, const float* __restrict__ b, long long rows, int F,
+                                int rows_per_block, float* __restrict__ out) {
+  __shared__ float s0[8][33], s1[8][33];
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float p0 = 0.f, p1 = 0.f;
+  if (f < F) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      float x = a[r * F + f];
+      float y = b ? b[r * F + f] : x;
+      p0 += x;
+      p1 = fmaf(x, y, p1);
+    }
+  }
+  s0[threadIdx.y][threadIdx.x] = p0;
+  s1[threadIdx.y][threadIdx.x] = p1;
+  __syncthreads();
+  if (threadIdx.y == 0 && f < F) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      p0 += s0[k][threadIdx.x];
+      p1 += s1[k][threadIdx.x];
+    }
+    atomicAdd(out + f, p0);
+    atomicAdd(out + F + f, p1);
+  }
+}
+
+static int colstats(cudaStream_t st, const float* a, const float* b, long long rows, int F, float* out) {
+  if (rows <= 0) return 0;
+  int rpb = 256;
+  dim3 grid(cdiv(F, 32), cdiv(rows, rpb));
+  AVSR_LAUNCH(colstats_kernel, grid, dim3(32, 8), 0, st, a, b, rows, F, rpb, out);
+  return 0;
+}
+
+__global__ void colsum_kernel(const float* __restrict__ a, long long rows, int N, int ld, int rows_per_block,
+                              float* __restrict__ out) {
+  __shared__ float s0[8][33];
+  const int f = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float p0 = 0.f;
+  if (f < N)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) p0 += a[r * ld + f];
+  s0[threadIdx.y][threadIdx.x] = p0;
+  __syncthreads();
+  if (threadIdx.y == 0 && f < N) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) p0 += s0[k][threadIdx.x];
+    atomicAdd(out + f, p0);
+  }
+}
+
+__global__ void bn_apply_train_kernel(const float* __restrict__ x, long long n, int F, const float* __restrict__ sums,
+                                      float inv_count, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float eps, float momentum,
+                                      float* __restrict__ y, float* __restrict__ xhat, float* __restrict__ invstd,
+                                      float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int f = (int)(i % F);
+  float mean = sums[f] * inv_count;
+  float var = fmaxf(sums[F + f] * inv_count - mean * mean, 0.0f);
+  float is = rsqrtf(var + eps);
+  float xh = (x[i] - mean) * is;
+  xhat[i] = xh;
+  y[i] = fmaf(xh, gamma[f], beta[f]);
+  if (i < F) {  // first row: per-feature side outputs
+    invstd[f] = is;
+    if (moving_mean) moving_mean[f] = moving_mean[f] * momentum + mean * (1.0f - momentum);
+    if (moving_var) moving_var[f] = moving_var[f] * momentum + var * (1.0f - momentum);
+  }
+}
+
+__global__ void bn_apply_eval_kernel(const float* __restrict__ x, long long n, int F, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, const float* __restrict__ mm,
+                                     const float* __restrict__ mv, float eps, float* __restrict__ y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int f = (int)(i % F);
+  y[i] = fmaf((x[i] - mm[f]) * rsqrtf(mv[f] + eps), gamma[f], beta[f]);
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ xhat, long long n, int F,
+                                    const float* __restrict__ sums2, float inv_count,
+                                    const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                    float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int f = (int)(i % F);
+  float sdy = sums2[f], sdyx = sums2[F + f];
+  dx[i] = gamma[f] * invstd[f] * (dy[i] - sdy * inv_count - xhat[i] * sdyx * inv_count);
+  if (i < F) {
+    if (dgamma) dgamma[f] += sdyx;
+    if (dbeta) dbeta[f] += sdy;
+  }
+}
+
+__global__ void reverse_sequence_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int B, int F,
+                                        const int* __restrict__ len) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)T * B * F;
+  if (i >= n) return;
+  int f = (int)(i % F);
+  long long tb = i / F;
+  int b = (int)(tb % B), t = (int)(tb / B);
+  int L = min(len[b], T);
+  int ts = t < L ? L - 1 - t : t;
+  y[i] = x[((long long)ts * B + b) * F + f];
+}
+
+__global__ void transpose01_kernel(const float* __restrict__ x, float* __restrict__ y, int d0, int d1, int F) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)d0 * d1 * F;
+  if (i >= n) return;
+  int f = (int)(i % F);
+  long long r = i / F;  // output row = j*d0 + k  (j in d1, k in d0)
+  int k = (int)(r % d0), j = (int)(r / d0);
+  y[i] = x[((long long)k * d1 + j) * F + f];
+}
+
+__global__ void embedding_fwd_kernel(const float* __restrict__ table, int V, int E, const int* __restrict__ ids,
+                                     long long n, float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * E) return;
+  long long r = i / E;
+  int e = (int)(i - r * E);
+  int id = ids[r];
+  out[i] = (id >= 0 && id < V) ? table[(size_t)id * E + e] : 0.0f;
+}
+
+// deterministic: one block per vocabulary row scans all ids
+__global__ void embedding_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ ids, long long n, int E,
+                                     float* __restrict__ dtable) {
+  const int v = blockIdx.x;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    float acc = 0.0f;
+    for (long long r = 0; r < n; ++r)
+      if (ids[r] == v) acc += dout[r * E + e];
+    dtable[(size_t)v * E + e] += acc;
+  }
+}
+
+// one warp per (t,b) row
+__global__ void seq_loss_kernel(const float* __restrict__ logits, int T, int B, int V, const int* __restrict__ labels,
+                                int ldl, const int* __restrict__ labels_len, float inv_denom,
+                                float* __restrict__ loss_sum, float* __restrict__ dlogits) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= T * B) return;
+  const int t = warp / B, b = warp - t * B;
+  const float* z = logits + (size_t)warp * V;
+  float* dz = dlogits + (size_t)warp * V;
+  if (t >= labels_len[b]) {
+    for (int v = lane; v < V; v += 32) dz[v] = 0.0f;
+    return;
+  }
+  float mx = -INFINITY;
+  for (int v = lane; v < V; v += 32) mx = fmaxf(mx, z[v]);
+  mx = warp_max(mx);
+  float s = 0.0f;
+  for (int v = lane; v < V; v += 32) s += expf(z[v] - mx);
+  s = warp_sum(s);
+  const float lse = logf(s) + mx;
+  const int y = labels[(size_t)b * ldl + t];
+  for (int v = lane; v < V; v += 32) {
+    float p = expf(z[v] - lse);
+    dz[v] = (p - (v == y ? 1.0f : 0.0f)) * inv_denom;
+  }
+  if (lane == 0) atomicAdd(loss_sum, lse - z[y]);
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float red[33];
+  float acc = 0.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc = fmaf(x[i], x[i], acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+__global__ void axpy_kernel(float a, const float* __restrict__ x, float* __restrict__ y, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaf(a, x[i], y[i]);
+}
+
+__global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, const float* __restrict__ sumsq, float clip,
+                                 float lr_t, float b1, float b2, float eps) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float scale = 1.0f;
+  if (clip > 0.0f) {
+    float norm = sqrtf(sumsq[0]);
+    scale = clip / fmaxf(norm, clip);  // tf.clip_by_global_norm
+  }
+  float gi = g[i] * scale;
+  float mi = b1 * m[i] + (1.0f - b1) * gi;
+  float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr_t * mi / (sqrtf(vi) + eps);  // TF-Adam: epsilon outside the sqrt
+}
+
+__global__ void normed_v_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, int A,
+                                    float* __restrict__ veff) {
+  __shared__ float red[33];
+  float acc = 0.0f;
+  for (int u = threadIdx.x; u < A; u += blockDim.x) acc = fmaf(v[u], v[u], acc);
+  acc = block_sum(acc, red);
+  float s = g[0] * rsqrtf(acc);
+  for (int u = threadIdx.x; u < A; u += blockDim.x) veff[u] = v[u] * s;
+}
+
+__global__ void normed_v_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                    const float* __restrict__ dveff, int A, float* __restrict__ dv,
+                                    float* __restrict__ dg) {
+  __shared__ float red[33];
+  float n2 = 0.0f, dot = 0.0f;
+  for (int u = threadIdx.x; u < A; u += blockDim.x) {
+    n2 = fmaf(v[u], v[u], n2);
+    dot = fmaf(dveff[u], v[u], dot);
+  }
+  n2 = block_sum(n2, red);
+  dot = block_sum(dot, red);
+  float inv = rsqrtf(n2);
+  float dvhat = dot * inv;  // dveff . vhat
+  if (threadIdx.x == 0) dg[0] += dvhat;
+  for (int u = threadIdx.x; u < A; u += blockDim.x) dv[u] += g[0] * inv * (dveff[u] - dvhat * v[u] * inv);
+}
+
+// ---- decoding helpers -----------------------------------------------------------
+__global__ void greedy_pick_kernel(const float* __restrict__ logits, int B, int V, int eos, int* __restrict__ finished,
+                                   int* __restrict__ sample_out, int* __restrict__ next_ids) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* z = logits + (size_t)b * V;
+  int best = 0;
+  float bv = z[0];
+  for (int v = 1; v < V; ++v)
+    if (z[v] > bv) {
+      bv = z[v];
+      best = v;
+    }
+  int fin = finished[b];
+  sample_out[b] = fin ? 0 : best;  // impute_finished zeroes finished rows
+  next_ids[b] = best;
+  finished[b] = fin | (best == eos);
+}
+
+// one CTA per utterance; W*V candidates
+__global__ void beam_step_kernel(const float* __restrict__ logits, int W, int V, int eos, float lpw,
+                                 float* __restrict__ log_probs, int* __restrict__ finished, int* __restrict__ lengths,
+                                 int* __restrict__ word_out, int* __restrict__ parent_out,
+                                 float* __restrict__ score_out) {
+  extern __shared__ float sm[];
+  const int N = W * V;
+  float* score = sm;           // N
+  float* total = score + N;    // N
+  float* lp_old = total + N;   // W
+  int* fin_old = (int*)(lp_old + W);
+  int* len_old = fin_old + W;
+  int* taken = len_old + W;    // N
+  __shared__ float rv[32];
+  __shared__ int ri[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int w = tid; w < W; w += blockDim.x) {
+    lp_old[w] = log_probs[b * W + w];
+    fin_old[w] = finished[b * W + w];
+    len_old[w] = lengths[b * W + w];
+  }
+  __syncthreads();
+  for (int w = warp; w < W; w += nw) {
+    const float* z = logits + ((size_t)b * W + w) * V;
+    float mx = -INFINITY;
+    for (int v = lane; v < V; v += 32) mx = fmaxf(mx, z[v]);
+    mx = warp_max(mx);
+    float s = 0.0f;
+    for (int v = lane; v < V; v += 32) s += expf(z[v] - mx);
+    s = warp_sum(s);
+    const float ls = logf(s);
+    for (int v = lane; v < V; v += 32) {
+      float lsm = (z[v] - mx) - ls;
+      if (fin_old[w]) lsm = (v == eos) ? 0.0f : -FLT_MAX;
+      float tot = lp_old[w] + lsm;
+      int nl = len_old[w] + ((!fin_old[w] && v != eos) ? 1 : 0);
+      float pen = lpw == 0.0f ? 1.0f : powf((5.0f + (float)nl) / 6.0f, lpw);
+      total[w * V + v] = tot;
+      score[w * V + v] = tot / pen;
+      taken[w * V + v] = 0;
+    }
+  }
+  __syncthreads();
+  for (int k = 0; k < W; ++k) {
+    // argmax with lowest-index tie-break (tf.nn.top_k)
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < N; i += blockDim.x) {
+      if (taken[i]) continue;
+      float s = score[i];
+      if (bi == 0x7fffffff || s > bv) {
+        bv = s;
+        bi = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      rv[warp] = bv;
+      ri[warp] = bi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w2 = 1; w2 < nw; ++w2) {
+        float ov = rv[w2];
+        int oi = ri[w2];
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > bv || (ov == bv && oi < bi))) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      taken[bi] = 1;
+      int word = bi % V, parent = bi / V;
+      int pf = fin_old[parent];
+      word_out[b * W + k] = word;
+      parent_out[b * W + k] = parent;
+      score_out[b * W + k] = bv;
+      log_probs[b * W + k] = total[bi];
+      lengths[b * W + k] = len_old[parent] + (pf ? 0 : 1);
+      finished[b * W + k] = pf | (word == eos);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, long long n, int F,
+                                   float* __restrict__ dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * F) return;
+  long long r = i / F;
+  int f = (int)(i - r * F);
+  dst[i] = src[(size_t)idx[r] * F + f];
+}
+
+}  // namespace avsr
+
+// ================================================================================
+// C ABI
+// ================================================================================
+using namespace avsr;
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" {
+
+int avsr_colsum(avsr_stream_t s, const float* X, int M, int N, int ldx, float* out) {
+  if (M <= 0 || N <= 0) return 0;
+  int rpb = 256;
+  dim3 grid(cdiv(N, 32), cdiv(M, rpb));
+  AVSR_LAUNCH(colsum_kernel, grid, dim3(32, 8), 0, ST(s), X, (long long)M, N, ldx, rpb, out);
+  return 0;
+}
+
+int avsr_bn_stats(avsr_stream_t s, const float* x, long long rows, int F, float* sums) {
+  return colstats(ST(s), x, nullptr, rows, F, sums);
+}
+
+int avsr_bn_apply_train(avsr_stream_t s, const float* x, long long rows, int F, const float* sums, double count,
+                        const float* gamma, const float* beta, float eps, float momentum, float* y, float* xhat,
+                        float* invstd, float* moving_mean, float* moving_var) {
+  long long n = rows * F;
+  AVSR_REQUIRE(rows >= 1 && count >= 1.0, "bn: empty batch");
+  AVSR_LAUNCH(bn_apply_train_kernel, cdiv(n, 256), 256, 0, ST(s), x, n, F, sums, (float)(1.0 / count), gamma, beta,
+              eps, momentum, y, xhat, invstd, moving_mean, moving_var);
+  return 0;
+}
+
+int avsr_bn_apply_eval(avsr_stream_t s, const float* x, long long rows, int F, const float* gamma, const float* beta,
+                       const float* moving_mean, const float* moving_var, float eps, float* y) {
+  long long n = rows * F;
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(bn_apply_eval_kernel, cdiv(n, 256), 256, 0, ST(s), x, n, F, gamma, beta, moving_mean, moving_var, eps,
+              y);
+  return 0;
+}
+
+int avsr_bn_bwd_stats(avsr_stream_t s, const float* dy, const float* xhat, long long rows, int F, float* sums2) {
+  return colstats(ST(s), dy, xhat, rows, F, sums2);
+}
+
+int avsr_bn_bwd_apply(avsr_stream_t s, const float* dy, const float* xhat, long long rows, int F, const float* sums2,
+                      double count, const float* gamma, const float* invstd, float* dx, float* dgamma,
+                      float* dbeta) {
+  long long n = rows * F;
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(bn_bwd_apply_kernel, cdiv(n, 256), 256, 0, ST(s), dy, xhat, n, F, sums2, (float)(1.0 / count), gamma,
+              invstd, dx, dgamma, dbeta);
+  return 0;
+}
+
+int avsr_reverse_sequence(avsr_stream_t s, const float* x, float* y, int T, int B, int F, const int* len) {
+  long long n = (long long)T * B * F;
+  if (n <= 0) return 0;
+  AVSR_REQUIRE(x != y, "reverse_sequence cannot run in place");
+  AVSR_LAUNCH(reverse_sequence_kernel, cdiv(n, 256), 256, 0, ST(s), x, y, T, B, F, len);
+  return 0;
+}
+
+int avsr_transpose01(avsr_stream_t s, const float* x, float* y, int d0, int d1, int F) {
+  long long n = (long long)d0 * d1 * F;
+  if (n <= 0) return 0;
+  AVSR_REQUIRE(x != y, "transpose01 cannot run in place");
+  AVSR_LAUNCH(transpose01_kernel, cdiv(n, 256), 256, 0, ST(s), x, y, d0, d1, F);
+  return 0;
+}
+
+int avsr_embedding_fwd(avsr_stream_t s, const float* table, int V, int E, const int* ids, long long n, float* out) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(embedding_fwd_kernel, cdiv(n * E, 256), 256, 0, ST(s), table, V, E, ids, n, out);
+  return 0;
+}
+
+int avsr_embedding_bwd(avsr_stream_t s, const float* dout, const int* ids, long long n, int V, int E,
+                       float* dtable) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(embedding_bwd_kernel, V, 128, 0, ST(s), dout, ids, n, E, dtable);
+  return 0;
+}
+
+int avsr_seq_loss(avsr_stream_t s, const float* logits, int T, int B, int V, const int* labels, int ldl,
+                  const int* labels_len, float inv_denom, float* loss_sum, float* dlogits) {
+  if (T * B <= 0) return 0;
+  AVSR_LAUNCH(seq_loss_kernel, cdiv((long long)T * B * 32, 256), 256, 0, ST(s), logits, T, B, V, labels, ldl,
+              labels_len, inv_denom, loss_sum, dlogits);
+  return 0;
+}
+
+int avsr_sumsq(avsr_stream_t s, const float* x, long long n, float* out) {
+  if (n <= 0) return 0;
+  int grid = (int)min((long long)148 * 8, (long long)cdiv(n, 256));
+  AVSR_LAUNCH(sumsq_kernel, grid, 256, 0, ST(s), x, n, out);
+  return 0;
+}
+
+int avsr_axpy(avsr_stream_t s, float a, const float* x, float* y, long long n) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(axpy_kernel, cdiv(n, 256), 256, 0, ST(s), a, x, y, n);
+  return 0;
+}
+
+int avsr_adam_clip_step(avsr_stream_t s, float* params, const float* grads, float* m, float* v, long long n,
+                        const float* sumsq_dev, float clip_norm, float lr_t, float beta1, float beta2, float eps) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(adam_clip_kernel, cdiv(n, 256), 256, 0, ST(s), params, grads, m, v, n, sumsq_dev, clip_norm, lr_t,
+              beta1, beta2, eps);
+  return 0;
+}
+
+int avsr_normed_v_fwd(avsr_stream_t s, const float* v, const float* g, int A, float* veff) {
+  AVSR_LAUNCH(normed_v_fwd_kernel, 1, 256, 0, ST(s), v, g, A, veff);
+  return 0;
+}
+
+int avsr_normed_v_bwd(avsr_stream_t s, const float* v, const float* g, const float* dveff, int A, float* dv,
+                      float* dg) {
+  AVSR_LAUNCH(normed_v_bwd_kernel, 1, 256, 0, ST(s), v, g, dveff, A, dv, dg);
+  return 0;
+}
+
+int avsr_greedy_pick(avsr_stream_t s, const float* logits, int B, int V, int eos, int* finished, int* sample_out,
+                     int* next_ids) {
+  AVSR_LAUNCH(greedy_pick_kernel, cdiv(B, 128), 128, 0, ST(s), logits, B, V, eos, finished, sample_out, next_ids);
+  return 0;
+}
+
+int avsr_beam_step(avsr_stream_t s, const float* logits, int B, int W, int V, int eos, float length_penalty,
+                   float* log_probs, int* finished, int* lengths, int* word_out, int* parent_out, float* score_out) {
+  AVSR_REQUIRE(W >= 1 && W <= 32 && W <= V, "beam: width must be in [1, min(32, V)]");
+  size_t smem = (size_t)(3 * W * V + 3 * W) * sizeof(float);
+  AVSR_REQUIRE(smem <= 48 * 1024, "beam: W*V too large");
+  AVSR_LAUNCH(beam_step_kernel, B, 128, smem, ST(s), logits, W, V, eos, length_penalty, log_probs, finished, lengths,
+              word_out, parent_out, score_out);
+  return 0;
+}
+
+int avsr_gather_rows(avsr_stream_t s, const float* src, const int* idx, long long n, int F, float* dst) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(gather_rows_kernel, cdiv(n * F, 256), 256, 0, ST(s), src, idx, n, F, dst);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,490 @@
+// Recurrent sequence op: dynamic_rnn / dynamic_decode over LSTMCell, optionally
+// wrapped by an AttentionWrapper with 1-2 mechanisms.  See include/avsr_b200.h.
+//
+// Step structure (reference call sites: cells.py:14-18, attention.py:132-191,
+// encoder.py:265-290, decoder_unimodal.py:299-352, decoder_bimodal.py:227-277):
+//   rec    = [attention_{t-1} | h_{t-1}] @ Wrec                 (gemm)
+//   i,j,f,o= act(gates_t + rec); c,h update with length masking  (lstm_point_fwd)
+//   per mechanism: (pq = h @ Wq) ; score -> softmax -> context   (attn_fwd)
+//                  attention_m = [h | ctx] @ Wl                  (gemm)
+#include "../../include/avsr_b200.h"
+#include "common.cuh"
+
+namespace avsr {
+
+// --------------------------------------------------------------------------- //
+// LSTM pointwise
+// --------------------------------------------------------------------------- //
+struct HcDst {
+  float* p[2];
+  int ld[2];
+};
+
+__global__ void lstm_point_fwd_kernel(int t, int B, int H, float* __restrict__ gates_t, const float* __restrict__ rec,
+                                      const int* __restrict__ len, const float* __restrict__ c_prev,
+                                      const float* __restrict__ h_prev, int ldh_prev, float* __restrict__ c_next,
+                                      float* __restrict__ h_next, int ldh_next, float* __restrict__ craw_t,
+                                      float* __restrict__ out_t, HcDst hc) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  int b = idx / H, u = idx - b * H;
+  float cp = c_prev[idx];
+  float hp = h_prev[(size_t)b * ldh_prev + u];
+  float hn, cn;
+  if (t >= len[b]) {
+    hn = hp;
+    cn = cp;
+    craw_t[idx] = cp;
+    if (out_t) out_t[idx] = 0.0f;  // dynamic_rnn emits zeros past the sequence length
+  } else {
+    float* g = gates_t + (size_t)b * 4 * H;
+    const float* r = rec + (size_t)b * 4 * H;
+    float gi = sigmoidf_acc(g[u] + r[u]);
+    float gj = tanhf_acc(g[H + u] + r[H + u]);
+    float gf = sigmoidf_acc(g[2 * H + u] + r[2 * H + u] + 1.0f);  // forget_bias = 1.0
+    float go = sigmoidf_acc(g[3 * H + u] + r[3 * H + u]);
+    float cr = gf * cp + gi * gj;
+    cn = fminf(fmaxf(cr, -1.0f), 1.0f);  // cell_clip = 1.0 (cells.py:16)
+    hn = go * tanhf_acc(cn);
+    g[u] = gi;
+    g[H + u] = gj;
+    g[2 * H + u] = gf;
+    g[3 * H + u] = go;
+    craw_t[idx] = cr;
+    if (out_t) out_t[idx] = hn;
+  }
+  c_next[idx] = cn;
+  h_next[(size_t)b * ldh_next + u] = hn;
+  if (hc.p[0]) hc.p[0][(size_t)b * hc.ld[0] + u] = hn;
+  if (hc.p[1]) hc.p[1][(size_t)b * hc.ld[1] + u] = hn;
+}
+
+struct DhSrc {
+  const float* p[4];
+  int ld[4];
+};
+
+// grid over B*H.  dS_cur/dS_next rows are [datt(At) | dh(H)].
+__global__ void lstm_point_bwd_kernel(int t, int B, int H, int At, const float* __restrict__ gates_t,
+                                      const float* __restrict__ craw_t, const float* __restrict__ craw_prev,
+                                      const float* __restrict__ c0, const int* __restrict__ len,
+                                      const float* __restrict__ dout_h_t, const float* __restrict__ dS_cur,
+                                      const float* __restrict__ dc_cur, DhSrc extra, float* __restrict__ dZ_t,
+                                      float* __restrict__ dS_next, float* __restrict__ dc_next) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  int b = idx / H, u = idx - b * H;
+  int SW = At + H;
+  float dh_in = dS_cur[(size_t)b * SW + At + u];
+  float dc_in = dc_cur[idx];
+  float* dz = dZ_t + (size_t)b * 4 * H;
+  if (t >= len[b]) {
+    dz[u] = 0.f;
+    dz[H + u] = 0.f;
+    dz[2 * H + u] = 0.f;
+    dz[3 * H + u] = 0.f;
+    dS_next[(size_t)b * SW + At + u] = dh_in;
+    dc_next[idx] = dc_in;
+  } else {
+    float dh = dh_in + (dout_h_t ? dout_h_t[idx] : 0.0f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (extra.p[k]) dh += extra.p[k][(size_t)b * extra.ld[k] + u];
+    const float* g = gates_t + (size_t)b * 4 * H;
+    float gi = g[u], gj = g[H + u], gf = g[2 * H + u], go = g[3 * H + u];
+    float cr = craw_t[idx];
+    float c = fminf(fmaxf(cr, -1.0f), 1.0f);
+    float tc = tanhf_acc(c);
+    float cp = craw_prev ? fminf(fmaxf(craw_prev[idx], -1.0f), 1.0f) : (c0 ? c0[idx] : 0.0f);
+    float dct = dc_in + dh * go * (1.0f - tc * tc);
+    float dcr = (cr >= -1.0f && cr <= 1.0f) ? dct : 0.0f;
+    dz[u] = dcr * gj * gi * (1.0f - gi);
+    dz[H + u] = dcr * gi * (1.0f - gj * gj);
+    dz[2 * H + u] = dcr * cp * gf * (1.0f - gf);
+    dz[3 * H + u] = dh * tc * go * (1.0f - go);
+    dS_next[(size_t)b * SW + At + u] = 0.0f;
+    dc_next[idx] = dcr * gf;
+  }
+  // attention part of dS_next: zero (filled by the Wrec^T product afterwards)
+  for (int a = u; a < At; a += H) dS_next[(size_t)b * SW + a] = 0.0f;
+}
+
+// dA_t[b,:] = mask * (dS_cur.att + (oa ? dout_t : 0))
+__global__ void attn_bwd_prep_kernel(int t, int B, int At, int SW, const int* __restrict__ len,
+                                     const float* __restrict__ dS_cur, const float* __restrict__ dout_att_t,
+                                     float* __restrict__ dA_t) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * At) return;
+  int b = idx / At, a = idx - b * At;
+  float v = 0.0f;
+  if (t < len[b]) v = dS_cur[(size_t)b * SW + a] + (dout_att_t ? dout_att_t[idx] : 0.0f);
+  dA_t[idx] = v;
+}
+
+// out_t[b,:] = t < len[b] ? S_next[b, :At] : 0
+__global__ void emit_attention_kernel(int t, int B, int At, int SW, const int* __restrict__ len,
+                                      const float* __restrict__ S_next, float* __restrict__ out_t) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * At) return;
+  int b = idx / At, a = idx - b * At;
+  out_t[idx] = t < len[b] ? S_next[(size_t)b * SW + a] : 0.0f;
+}
+
+__global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows,
+                              int cols) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * cols) return;
+  size_t r = i / cols, c = i - r * cols;
+  dst[r * ldd + c] = src ? src[r * lds + c] : 0.0f;
+}
+
+// --------------------------------------------------------------------------- //
+// attention: score -> masked softmax -> context, one CTA per utterance
+// --------------------------------------------------------------------------- //
+constexpr int ATT_THREADS = 256;
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_fwd_kernel(int kind, int Tm, int B, int Dm, int A, const float* __restrict__ q, int ldq,
+                const float* __restrict__ keys, const float* __restrict__ values, const int* __restrict__ mem_len,
+                const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ bias,
+                float* __restrict__ align_t, float* __restrict__ ctx_out, int ldctx) {
+  extern __shared__ float sm[];
+  float* q_s = sm;            // A
+  float* v_s = q_s + A;       // A
+  float* sc = v_s + A;        // Tm
+  float* red = sc + Tm;       // 33
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = min(mem_len[b], Tm);
+  const bool luong = kind <= AVSR_ATTN_SCALED_LUONG;
+  for (int u = tid; u < A; u += ATT_THREADS) {
+    q_s[u] = q[(size_t)b * ldq + u] + ((!luong && bias) ? bias[u] : 0.0f);
+    v_s[u] = luong ? 0.0f : v[u];
+  }
+  __syncthreads();
+  const float gs = (kind == AVSR_ATTN_SCALED_LUONG) ? g[0] : 1.0f;
+  for (int tm = warp; tm < L; tm += ATT_THREADS / 32) {
+    const float* kr = keys + ((size_t)tm * B + b) * A;
+    float acc = 0.0f;
+    if (luong) {
+      for (int u = lane; u < A; u += 32) acc = fmaf(kr[u], q_s[u], acc);
+    } else {
+      for (int u = lane; u < A; u += 32) acc = fmaf(v_s[u], tanhf_acc(kr[u] + q_s[u]), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sc[tm] = gs * acc;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int tm = tid; tm < L; tm += ATT_THREADS) mx = fmaxf(mx, sc[tm]);
+  mx = block_max(mx, red);
+  float sum = 0.0f;
+  for (int tm = tid; tm < L; tm += ATT_THREADS) {
+    float e = __expf(sc[tm] - mx);
+    sc[tm] = e;
+    sum += e;
+  }
+  sum = block_sum(sum, red);
+  const float inv = L > 0 ? 1.0f / sum : 0.0f;
+  for (int tm = tid; tm < Tm; tm += ATT_THREADS) {
+    float a = tm < L ? sc[tm] * inv : 0.0f;
+    sc[tm] = a;
+    align_t[(size_t)b * Tm + tm] = a;
+  }
+  __syncthreads();
+  for (int d = tid; d < Dm; d += ATT_THREADS) {
+    const float* vp = values + (size_t)b * Dm + d;
+    const size_t stride = (size_t)B * Dm;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int tm = 0;
+    for (; tm + 3 < L; tm += 4) {
+      a0 = fmaf(sc[tm], vp[(size_t)tm * stride], a0);
+      a1 = fmaf(sc[tm + 1], vp[(size_t)(tm + 1) * stride], a1);
+      a2 = fmaf(sc[tm + 2], vp[(size_t)(tm + 2) * stride], a2);
+      a3 = fmaf(sc[tm + 3], vp[(size_t)(tm + 3) * stride], a3);
+    }
+    for (; tm < L; ++tm) a0 = fmaf(sc[tm], vp[(size_t)tm * stride], a0);
+    ctx_out[(size_t)b * ldctx + d] = (a0 + a1) + (a2 + a3);
+  }
+}
+
+// Backward of attn_fwd for one query step.  dctx [B,Dm](lddctx).  Writes dq_out [B,A]
+// (gradient wrt q: h for Luong, processed query for Bahdanau) and accumulates
+// dkeys, dvalues (context path only), dv, dg, dbias.
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_kernel(int kind, int t, const int* __restrict__ seq_len, int Tm, int B, int Dm, int A,
+                const float* __restrict__ q, int ldq, const float* __restrict__ keys,
+                const float* __restrict__ values, const int* __restrict__ mem_len, const float* __restrict__ v,
+                const float* __restrict__ g, const float* __restrict__ bias, const float* __restrict__ align_t,
+                const float* __restrict__ dctx, int lddctx, float* __restrict__ dq_out, int lddq,
+                float* __restrict__ dkeys, float* __restrict__ dvalues, float* __restrict__ dv,
+                float* __restrict__ dg, float* __restrict__ dbias) {
+  extern __shared__ float sm[];
+  float* q_s = sm;             // A
+  float* v_s = q_s + A;        // A
+  float* dctx_s = v_s + A;     // Dm
+  float* a_s = dctx_s + Dm;    // Tm
+  float* ds_s = a_s + Tm;      // Tm
+  float* raw_s = ds_s + Tm;    // Tm
+  float* red = raw_s + Tm;     // 33
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (t >= seq_len[b]) {  // masked step: no gradient flows
+    for (int u = tid; u < A; u += ATT_THREADS) dq_out[(size_t)b * lddq + u] = 0.0f;
+    return;
+  }
+  const int L = min(mem_len[b], Tm);
+  const bool luong = kind <= AVSR_ATTN_SCALED_LUONG;
+  for (int u = tid; u < A; u += ATT_THREADS) {
+    q_s[u] = q[(size_t)b * ldq + u] + ((!luong && bias) ? bias[u] : 0.0f);
+    v_s[u] = luong ? 0.0f : v[u];
+  }
+  for (int d = tid; d < Dm; d += ATT_THREADS) dctx_s[d] = dctx[(size_t)b * lddctx + d];
+  for (int tm = tid; tm < Tm; tm += ATT_THREADS) a_s[tm] = align_t[(size_t)b * Tm + tm];
+  __syncthreads();
+  for (int tm = warp; tm < L; tm += ATT_THREADS / 32) {
+    const size_t row = (size_t)tm * B + b;
+    const float* vr = values + row * Dm;
+    float* dvr = dvalues + row * Dm;
+    const float a = a_s[tm];
+    float acc = 0.0f;
+    for (int d = lane; d < Dm; d += 32) {
+      acc = fmaf(dctx_s[d], vr[d], acc);
+      dvr[d] += a * dctx_s[d];
+    }
+    acc = warp_sum(acc);
+    float raw = 0.0f;
+    if (kind == AVSR_ATTN_SCALED_LUONG) {
+      const float* kr = keys + row * A;
+      for (int u = lane; u < A; u += 32) raw = fmaf(kr[u], q_s[u], raw);
+      raw = warp_sum(raw);
+    }
+    if (lane == 0) {
+      ds_s[tm] = acc;
+      raw_s[tm] = raw;
+    }
+  }
+  __syncthreads();
+  float dot = 0.0f;
+  for (int tm = tid; tm < L; tm += ATT_THREADS) dot = fmaf(a_s[tm], ds_s[tm], dot);
+  dot = block_sum(dot, red);
+  float gsum = 0.0f;
+  const float gs = (kind == AVSR_ATTN_SCALED_LUONG) ? g[0] : 1.0f;
+  for (int tm = tid; tm < L; tm += ATT_THREADS) {
+    float ds = a_s[tm] * (ds_s[tm] - dot);
+    gsum = fmaf(ds, raw_s[tm], gsum);
+    ds_s[tm] = ds * gs;
+  }
+  if (kind == AVSR_ATTN_SCALED_LUONG) {
+    gsum = block_sum(gsum, red);
+    if (tid == 0) atomicAdd(dg, gsum);
+  }
+  __syncthreads();
+  for (int u = tid; u < A; u += ATT_THREADS) {
+    const size_t stride = (size_t)B * A;
+    const float* kp = keys + (size_t)b * A + u;
+    float* dkp = dkeys + (size_t)b * A + u;
+    float dq = 0.0f;
+    if (luong) {
+      const float qu = q_s[u];
+      for (int tm = 0; tm < L; ++tm) {
+        const float ds = ds_s[tm];
+        dq = fmaf(ds, kp[(size_t)tm * stride], dq);
+        dkp[(size_t)tm * stride] += ds * qu;
+      }
+    } else {
+      const float qu = q_s[u], vu = v_s[u];
+      float dvu = 0.0f;
+      for (int tm = 0; tm < L; ++tm) {
+        const float ds = ds_s[tm];
+        const float th = tanhf_acc(kp[(size_t)tm * stride] + qu);
+        const float dE = ds * vu * (1.0f - th * th);
+        dkp[(size_t)tm * stride] += dE;
+        dq += dE;
+        dvu = fmaf(ds, th, dvu);
+      }
+      atomicAdd(dv + u, dvu);
+      if (dbias) atomicAdd(dbias + u, dq);
+    }
+    dq_out[(size_t)b * lddq + u] = dq;
+  }
+}
+
+// --------------------------------------------------------------------------- //
+// host orchestration
+// --------------------------------------------------------------------------- //
+struct WorkLayout {
+  size_t rec, cbuf, dS, dcbuf, dHC, dq, total;
+};
+static WorkLayout work_layout(int B, int H, int At, int maxHD, int maxA) {
+  WorkLayout w;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
+  w.rec = take((size_t)B * 4 * H);
+  w.cbuf = take((size_t)2 * B * H);
+  w.dS = take((size_t)2 * B * (At + H));
+  w.dcbuf = take((size_t)2 * B * H);
+  w.dHC = take((size_t)2 * B * maxHD);
+  w.dq = take((size_t)2 * B * (maxA > H ? maxA : H));
+  w.total = o;
+  return w;
+}
+
+static int check_common(const AvsrRnnSeq* r, int* At_out, int* maxHD, int* maxA) {
+  AVSR_REQUIRE(r != nullptr, "rnn: null descriptor");
+  AVSR_REQUIRE(r->T >= 0 && r->B > 0 && r->H > 0, "rnn: bad dims T=%d B=%d H=%d", r->T, r->B, r->H);
+  AVSR_REQUIRE(r->n_mech >= 0 && r->n_mech <= 2, "rnn: n_mech must be 0..2");
+  int At = 0, hd = 0, ma = 0;
+  for (int k = 0; k < r->n_mech; ++k) {
+    const AvsrAttnMech& m = r->mech[k];
+    AVSR_REQUIRE(m.kind >= 0 && m.kind <= 3, "rnn: unknown attention mechanism %d", m.kind);
+    AVSR_REQUIRE(m.Tm > 0 && m.Dm > 0 && m.A > 0, "rnn: bad mechanism dims");
+    if (m.kind <= AVSR_ATTN_SCALED_LUONG)
+      AVSR_REQUIRE(m.A == r->H, "luong attention needs num_units == query depth (A=%d, H=%d)", m.A, r->H);
+    At += m.A;
+    hd = hd > r->H + m.Dm ? hd : r->H + m.Dm;
+    ma = ma > m.A ? ma : m.A;
+  }
+  *At_out = At;
+  *maxHD = hd;
+  *maxA = ma;
+  return 0;
+}
+
+static size_t attn_fwd_smem(const AvsrAttnMech& m) { return (size_t)(2 * m.A + m.Tm + 33) * sizeof(float); }
+static size_t attn_bwd_smem(const AvsrAttnMech& m) {
+  return (size_t)(2 * m.A + m.Dm + 3 * m.Tm + 33) * sizeof(float);
+}
+
+int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
+  int At, maxHD, maxA;
+  AVSR_TRY(check_common(r, &At, &maxHD, &maxA));
+  const int T = r->T, B = r->B, H = r->H, SW = At + H;
+  WorkLayout wl = work_layout(B, H, At, maxHD, maxA);
+  float* rec = r->work + wl.rec;
+  float* cbuf[2] = {r->work + wl.cbuf, r->work + wl.cbuf + (size_t)B * H};
+  const int pw_grid = cdiv((long long)B * H, 256);
+  AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->c0, H, cbuf[0], H, B, H);
+  int cur = 0;
+  for (int k = 0; k < r->n_mech; ++k) {
+    AVSR_REQUIRE(attn_fwd_smem(r->mech[k]) <= 200 * 1024, "attention: Tm too large for shared memory");
+    if (attn_fwd_smem(r->mech[k]) > 48 * 1024)
+      AVSR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  for (int t = 0; t < T; ++t) {
+    const float* S_t = r->S + (size_t)t * B * SW;
+    float* S_n = r->S + (size_t)(t + 1) * B * SW;
+    float* gates_t = r->gates + (size_t)t * B * 4 * H;
+    AVSR_TRY(gemm(st, 0, 0, B, 4 * H, SW, S_t, SW, r->Wrec, 4 * H, rec, 4 * H, 0.0f, nullptr));
+    HcDst hc = {{nullptr, nullptr}, {0, 0}};
+    for (int k = 0; k < r->n_mech; ++k) {
+      hc.p[k] = r->mech[k].hc + (size_t)t * B * (H + r->mech[k].Dm);
+      hc.ld[k] = H + r->mech[k].Dm;
+    }
+    float* out_h = (r->output_attention && r->n_mech > 0) ? nullptr : r->out + (size_t)t * B * H;
+    AVSR_LAUNCH(lstm_point_fwd_kernel, pw_grid, 256, 0, st, t, B, H, gates_t, rec, r->len, cbuf[cur], S_t + At, SW,
+                cbuf[cur ^ 1], S_n + At, SW, r->craw + (size_t)t * B * H, out_h, hc);
+    cur ^= 1;
+    int off = 0;
+    for (int k = 0; k < r->n_mech; ++k) {
+      const AvsrAttnMech& m = r->mech[k];
+      const bool luong = m.kind <= AVSR_ATTN_SCALED_LUONG;
+      const float* q = S_n + At;
+      int ldq = SW;
+      if (!luong) {
+        float* pq_t = m.pq + (size_t)t * B * m.A;
+        AVSR_TRY(gemm(st, 0, 0, B, m.A, H, S_n + At, SW, m.Wq, m.A, pq_t, m.A, 0.0f, nullptr));
+        q = pq_t;
+        ldq = m.A;
+      }
+      AVSR_LAUNCH(attn_fwd_kernel, B, ATT_THREADS, attn_fwd_smem(m), st, m.kind, m.Tm, B, m.Dm, m.A, q, ldq, m.keys,
+                  m.values, m.mem_len, m.v, m.g, m.bias, m.align + (size_t)t * B * m.Tm, hc.p[k] + H, hc.ld[k]);
+      AVSR_TRY(gemm(st, 0, 0, B, m.A, H + m.Dm, hc.p[k], hc.ld[k], m.Wl, m.A, S_n + off, SW, 0.0f, nullptr));
+      off += m.A;
+    }
+    if (r->output_attention && r->n_mech > 0)
+      AVSR_LAUNCH(emit_attention_kernel, cdiv((long long)B * At, 256), 256, 0, st, t, B, At, SW, r->len, S_n,
+                  r->out + (size_t)t * B * At);
+  }
+  if (r->cT) AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, cbuf[cur], H, r->cT, H, B, H);
+  if (r->hT) AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->S + (size_t)T * B * SW + At, SW, r->hT, H, B, H);
+  return 0;
+}
+
+int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
+  int At, maxHD, maxA;
+  AVSR_TRY(check_common(r, &At, &maxHD, &maxA));
+  const int T = r->T, B = r->B, H = r->H, SW = At + H;
+  const bool oa = r->output_attention && r->n_mech > 0;
+  WorkLayout wl = work_layout(B, H, At, maxHD, maxA);
+  float* dS[2] = {r->work + wl.dS, r->work + wl.dS + (size_t)B * SW};
+  float* dcb[2] = {r->work + wl.dcbuf, r->work + wl.dcbuf + (size_t)B * H};
+  float* dHC[2] = {r->work + wl.dHC, r->work + wl.dHC + (size_t)B * maxHD};
+  const int qw = maxA > H ? maxA : H;
+  float* dq[2] = {r->work + wl.dq, r->work + wl.dq + (size_t)B * qw};
+  const int pw_grid = cdiv((long long)B * H, 256);
+  AVSR_LAUNCH(copy2d_kernel, cdiv((long long)B * SW, 256), 256, 0, st, (const float*)nullptr, 0, dS[0], SW, B, SW);
+  AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->dhT, H, dS[0] + At, SW, B, H);
+  AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->dcT, H, dcb[0], H, B, H);
+  for (int k = 0; k < r->n_mech; ++k) {
+    AVSR_REQUIRE(attn_bwd_smem(r->mech[k]) <= 200 * 1024, "attention: Tm too large for shared memory");
+    if (attn_bwd_smem(r->mech[k]) > 48 * 1024)
+      AVSR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  int cur = 0;
+  for (int t = T - 1; t >= 0; --t) {
+    const float* S_n = r->S + (size_t)(t + 1) * B * SW;
+    float* dZ_t = r->dZ + (size_t)t * B * 4 * H;
+    DhSrc extra = {{nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}};
+    if (r->n_mech > 0) {
+      float* dA_t = r->dA + (size_t)t * B * At;
+      AVSR_LAUNCH(attn_bwd_prep_kernel, cdiv((long long)B * At, 256), 256, 0, st, t, B, At, SW, r->len, dS[cur],
+                  (oa && r->dout) ? r->dout + (size_t)t * B * At : nullptr, dA_t);
+      int off = 0;
+      for (int k = 0; k < r->n_mech; ++k) {
+        const AvsrAttnMech& m = r->mech[k];
+        const bool luong = m.kind <= AVSR_ATTN_SCALED_LUONG;
+        const int HD = H + m.Dm;
+        // d[h | ctx] = dA_m @ Wl^T
+        AVSR_TRY(gemm(st, 0, 1, B, HD, m.A, dA_t + off, At, m.Wl, m.A, dHC[k], HD, 0.0f, nullptr));
+        const float* q = luong ? S_n + At : m.pq + (size_t)t * B * m.A;
+        const int ldq = luong ? SW : m.A;
+        float* dq_out = luong ? dq[k] : m.dpq + (size_t)t * B * m.A;
+        AVSR_LAUNCH(attn_bwd_kernel, B, ATT_THREADS, attn_bwd_smem(m), st, m.kind, t, r->len, m.Tm, B, m.Dm, m.A, q,
+                    ldq, m.keys, m.values, m.mem_len, m.v, m.g, m.bias, m.align + (size_t)t * B * m.Tm,
+                    dHC[k] + H, HD, dq_out, m.A, m.dkeys, m.dvalues, m.dv, m.dg, m.dbias);
+        if (!luong) AVSR_TRY(gemm(st, 0, 1, B, H, m.A, dq_out, m.A, m.Wq, m.A, dq[k], H, 0.0f, nullptr));
+        extra.p[2 * k] = dHC[k];
+        extra.ld[2 * k] = HD;
+        extra.p[2 * k + 1] = dq[k];
+        extra.ld[2 * k + 1] = luong ? m.A : H;
+        off += m.A;
+      }
+    }
+    AVSR_LAUNCH(lstm_point_bwd_kernel, pw_grid, 256, 0, st, t, B, H, At, r->gates + (size_t)t * B * 4 * H,
+                r->craw + (size_t)t * B * H, t > 0 ? r->craw + (size_t)(t - 1) * B * H : nullptr, r->c0, r->len,
+                (oa || !r->dout) ? nullptr : r->dout + (size_t)t * B * H, dS[cur], dcb[cur], extra, dZ_t, dS[cur ^ 1],
+                dcb[cur ^ 1]);
+    // [datt_{t-1} | dh_{t-1}] += dZ_t @ Wrec^T
+    AVSR_TRY(gemm(st, 0, 1, B, SW, 4 * H, dZ_t, 4 * H, r->Wrec, 4 * H, dS[cur ^ 1], SW, 1.0f, nullptr));
+    cur ^= 1;
+  }
+  if (r->dh0) AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, dS[cur] + At, SW, r->dh0, H, B, H);
+  if (r->dc0) AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, dcb[cur], H, r->dc0, H, B, H);
+  if (T > 0) {
+    // dWrec += S[0:T]^T @ dZ
+    AVSR_TRY(gemm(st, 1, 0, SW, 4 * H, T * B, r->S, SW, r->dZ, 4 * H, r->dWrec, 4 * H, 1.0f, nullptr));
+    int off = 0;
+    for (int k = 0; k < r->n_mech; ++k) {
+      const AvsrAttnMech& m = r->mech[k];
+      const int HD = H + m.Dm;
+      AVSR_TRY(gemm(st, 1, 0, HD, m.A, T * B, m.hc, HD, r->dA + off, At, m.dWl, m.A, 1.0f, nullptr));
+      if (m.kind >= AVSR_ATTN_BAHDANAU)
+        AVSR_TRY(gemm(st, 1, 0, H, m.A, T * B, m.hc, HD, m.dpq, m.A, m.dWq, m.A, 1.0f, nullptr));
+      off += m.A;
+    }
+  }
+  return 0;
+}
+
+size_t rnn_work_floats(int B, int H, int At, int maxHD, int maxA) { return work_layout(B, H, At, maxHD, maxA).total; }
+
+}  // namespace avsr

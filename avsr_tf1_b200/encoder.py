@@ -1,0 +1,226 @@
+"""Encoders - drop-in for reference avsr/encoder.py (Seq2SeqEncoder :14-196,
+AttentiveEncoder :199-335), computing on B200 through libavsr_b200.so."""
+from __future__ import annotations
+
+import collections
+
+from . import ops
+from .attention import add_attention
+from .cells import build_rnn_layers
+from .layers import BatchNormInput, BuildContext, LSTMLayerOp
+
+
+class EncoderData(collections.namedtuple("EncoderData", ("outputs", "final_state"))):
+    pass
+
+
+def maybe_list(obj):
+    return obj if type(obj) in (list, tuple) else [obj, ]
+
+
+def _layer_prefixes(scope, n_layers, sub=''):
+    pre = f'{scope}/Encoder/' + (f'{sub}/' if sub else '')
+    if n_layers == 1:
+        return [pre + 'lstm_cell']
+    return [pre + f'multi_rnn_cell/cell_{k}/lstm_cell' for k in range(n_layers)]
+
+
+class Seq2SeqEncoder(object):
+    """Input BatchNorm -> stacked uni/bi-directional LSTM (encoder.py:14-196).
+
+    outputs [T,B,H] (Bi: [T,B,2H]); final_state = (c, h) of the LAST layer (Bi: the
+    Dense projections of encoder.py:124-141) - the only state the decoders read
+    (decoder_unimodal.py:144, decoder_bimodal.py:144-152)."""
+
+    def __init__(self, data, mode, hparams, num_units_per_layer, dropout_probability, ctx: BuildContext = None,
+                 scope='', feature_dim=None, **kwargs):
+        self._mode, self._hparams = mode, hparams
+        self._num_units_per_layer = tuple(num_units_per_layer)
+        self._scope, self._ctx = scope, ctx
+        self._F = int(feature_dim if feature_dim is not None else data.inputs.shape[-1])
+        if kwargs.get('regress_aus', False) and mode == 'train':
+            raise NotImplementedError('Action-Unit regression head (encoder.py:173-189) is row f-4, not built')
+        if hparams.instance_normalisation:
+            raise NotImplementedError('instance_normalisation is off in every reference config')
+        if hparams.input_dense_layers[0] > 0:
+            raise NotImplementedError('input_dense_layers is off in every reference config (avsr.py:38)')
+        self._bn = BatchNormInput(ctx, scope, self._F) if hparams.batch_normalisation is True else None
+        self._init_encoder()
+
+    def _init_encoder(self):
+        hp, ctx, scope = self._hparams, self._ctx, self._scope
+        units = self._num_units_per_layer
+        L = len(units)
+        self._units = units
+
+        def stack(sub):
+            cells = maybe_list(build_rnn_layers(
+                cell_type=hp.cell_type, num_units_per_layer=units, use_dropout=hp.use_dropout,
+                dropout_probability=self._dropout_probability_for(scope), mode=self._mode,
+                residual_connections=hp.residual_encoder if not sub else False,
+                highway_connections=hp.highway_encoder if not sub else False,
+                weight_sharing=hp.encoder_weight_sharing if not sub else False))
+            ops_, in_dim = [], self._F
+            for prefix, cell in zip(_layer_prefixes(scope, L, sub), cells):
+                ops_.append(LSTMLayerOp(ctx, prefix, in_dim, cell.num_units))
+                in_dim = cell.num_units
+            return ops_
+
+        if hp.encoder_type == 'unidirectional':
+            self._fw, self._bw = stack(''), None
+            self.output_dim = units[-1]
+        elif hp.encoder_type == 'bidirectional':
+            if hp.cell_type != 'lstm':
+                raise ValueError('BiRNN fusion strategy not implemented for this cell')
+            if L == 1:
+                raise ValueError('the reference cannot build a 1-layer bidirectional LSTM encoder '
+                                 '(encoder.py:125-133 indexes the state as a tuple of layers)')
+            self._fw, self._bw = stack('fw'), stack('bw')
+            dec = hp.decoder_units_per_layer[0]
+            self._proj = []
+            for i in range(2 * L):  # encoder.py:124-141: dense, dense_1, ... (c then h per layer)
+                name = f'{scope}/Encoder/dense' + ('' if i == 0 else f'_{i}') + '/kernel'
+                self._proj.append(ctx.declare(name, (2 * units[i // 2], dec), 'glorot'))
+            self.output_dim = 2 * units[-1]
+        else:
+            raise Exception('Allowed encoder types: `unidirectional`, `bidirectional`')
+
+    def _dropout_probability_for(self, scope):
+        hp = self._hparams
+        return hp.video_encoder_dropout_probability if scope == 'video' else hp.audio_encoder_dropout_probability
+
+    # ---- compute -------------------------------------------------------------
+    def forward(self, inputs, inputs_len):
+        """inputs [T,B,F] frame-major; returns EncoderData."""
+        train = self._mode == 'train'
+        ctx = self._ctx
+        self._lens = inputs_len
+        x = self._bn.forward(inputs, train) if self._bn is not None else inputs
+        cur = x
+        for op in self._fw:
+            cur = op.forward(cur, inputs_len)
+        if self._bw is None:
+            self._outputs = cur
+            self._final = self._fw[-1].final
+        else:
+            curb = ops.reverse_sequence(x, inputs_len)
+            for op in self._bw:
+                curb = op.forward(curb, inputs_len)
+            outb = ops.reverse_sequence(curb, inputs_len)
+            T, B, H = cur.shape
+            out = ops.empty(T, B, 2 * H)
+            out[:, :, :H].copy_(cur)
+            out[:, :, H:].copy_(outb)
+            self._outputs = out
+            cf, hf = self._fw[-1].final
+            cb, hb = self._bw[-1].final
+            self._cat_c = ops.empty(B, 2 * H)
+            self._cat_h = ops.empty(B, 2 * H)
+            self._cat_c[:, :H].copy_(cf); self._cat_c[:, H:].copy_(cb)
+            self._cat_h[:, :H].copy_(hf); self._cat_h[:, H:].copy_(hb)
+            dec = self._hparams.decoder_units_per_layer[0]
+            pc, ph = ops.empty(B, dec), ops.empty(B, dec)
+            ops.gemm(self._cat_c, ctx.p(self._proj[-2]), pc)
+            ops.gemm(self._cat_h, ctx.p(self._proj[-1]), ph)
+            self._final = (pc, ph)
+        return self.get_data()
+
+    def get_data(self):
+        return EncoderData(outputs=self._outputs, final_state=self._final)
+
+    def backward(self, doutputs, dfinal_state=None, need_dx=False):
+        """doutputs [T,B,out_dim] or None; dfinal_state = (dc, dh) wrt final_state or None."""
+        ctx = self._ctx
+        if self._bw is None:
+            d = doutputs if doutputs is not None else ops.zeros(*self._outputs.shape)
+            n = len(self._fw)
+            for i in range(n - 1, -1, -1):
+                need = (i > 0) or need_dx or self._bn is not None
+                d = self._fw[i].backward(d, dfinal_state if i == n - 1 else None, need_dx=need)
+            dx = d
+        else:
+            T, B, H2 = self._outputs.shape
+            H = H2 // 2
+            if doutputs is None:
+                doutputs = ops.zeros(T, B, H2)
+            dsf = dsb = None
+            if dfinal_state is not None:
+                dpc, dph = dfinal_state
+                ops.gemm(self._cat_c, dpc, ctx.g(self._proj[-2]), ta=True, beta=1.0)
+                ops.gemm(self._cat_h, dph, ctx.g(self._proj[-1]), ta=True, beta=1.0)
+                dcc, dch = ops.empty(B, H2), ops.empty(B, H2)
+                ops.gemm(dpc, ctx.p(self._proj[-2]), dcc, tb=True)
+                ops.gemm(dph, ctx.p(self._proj[-1]), dch, tb=True)
+                dsf = (dcc[:, :H].contiguous(), dch[:, :H].contiguous())
+                dsb = (dcc[:, H:].contiguous(), dch[:, H:].contiguous())
+            df = doutputs[:, :, :H].contiguous()
+            db = ops.reverse_sequence(doutputs[:, :, H:].contiguous(), self._lens)
+            n = len(self._fw)
+            for i in range(n - 1, -1, -1):
+                df = self._fw[i].backward(df, dsf if i == n - 1 else None, need_dx=True)
+                db = self._bw[i].backward(db, dsb if i == n - 1 else None, need_dx=True)
+            dxb = ops.reverse_sequence(db, self._lens)
+            ops.axpy(1.0, dxb, df)
+            dx = df
+        if self._bn is not None and dx is not None:
+            dx = self._bn.backward(dx)
+        return dx
+
+
+class AttentiveEncoder(Seq2SeqEncoder):
+    """AV-Align (encoder.py:199-335, https://arxiv.org/abs/1809.01728): the TOP audio layer is
+    an AttentionWrapper attending to the video encoder outputs (audio attends to video)."""
+
+    def __init__(self, data, mode, hparams, num_units_per_layer, attended_memory_depth, dropout_probability,
+                 ctx: BuildContext = None, scope='audio', feature_dim=None):
+        self._attended_memory_depth = int(attended_memory_depth)
+        super(AttentiveEncoder, self).__init__(data, mode, hparams, num_units_per_layer, dropout_probability,
+                                               ctx=ctx, scope=scope, feature_dim=feature_dim)
+
+    def _init_encoder(self):
+        hp, ctx, scope = self._hparams, self._ctx, self._scope
+        units = self._num_units_per_layer
+        L = len(units)
+        if hp.encoder_type != 'unidirectional':
+            raise Exception('AttentiveEncoder: only `unidirectional` is implemented (encoder.py:229)')
+        cells = maybe_list(build_rnn_layers(
+            cell_type=hp.cell_type, num_units_per_layer=units, use_dropout=hp.use_dropout,
+            dropout_probability=hp.audio_encoder_dropout_probability, mode=self._mode, as_list=True))
+        self._fw, in_dim = [], self._F
+        for k in range(L - 1):
+            self._fw.append(LSTMLayerOp(ctx, f'{scope}/Encoder/multi_rnn_cell/cell_{k}/lstm_cell', in_dim,
+                                        cells[k].num_units))
+            in_dim = cells[k].num_units
+        wrap = f'{scope}/Encoder/multi_rnn_cell/cell_{L - 1}/attention_wrapper' if L > 1 \
+            else f'{scope}/Encoder/attention_wrapper'
+        self._top = add_attention(cells[-1], attention_types=hp.attention_type[0], num_units=units[-1],
+                                  memory_depths=[self._attended_memory_depth], ctx=ctx, wrap_prefix=wrap,
+                                  mem_layer_names=[f'{scope}/Encoder/memory_layer/kernel'], in_dim=in_dim,
+                                  fusion_type='linear_fusion')
+        self._bw = None
+        self.output_dim = self._top.out_dim
+
+    def forward(self, inputs, inputs_len, attended_memory=None, attended_memory_length=None):
+        train = self._mode == 'train'
+        self._lens = inputs_len
+        x = self._bn.forward(inputs, train) if self._bn is not None else inputs
+        cur = x
+        for op in self._fw:
+            cur = op.forward(cur, inputs_len)
+        self._outputs = self._top.forward(cur, inputs_len, memories=[(attended_memory, attended_memory_length)])
+        self._final = self._top.final  # wrapper stripped: cell state only (encoder.py:314-330)
+        self.attention_alignment = self._top.bufs[0].align  # [T_audio, B, T_video]
+        self.attention_contexts = self._top.bufs[0].hc      # [T_audio, B, H + Dm]
+        return self.get_data()
+
+    def backward(self, doutputs, dfinal_state=None, need_dx=False):
+        """Returns (dx, dmemory) - dmemory is the gradient wrt the video encoder outputs."""
+        if doutputs is None:
+            doutputs = ops.zeros(*self._outputs.shape)
+        d, dmem, _ = self._top.backward(doutputs, dfinal_state, need_dx=True, want_init_grad=False)
+        for i in range(len(self._fw) - 1, -1, -1):
+            need = (i > 0) or need_dx or self._bn is not None
+            d = self._fw[i].backward(d, None, need_dx=need)
+        if self._bn is not None and d is not None:
+            d = self._bn.backward(d)
+        return d, dmem[0]

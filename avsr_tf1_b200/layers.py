@@ -1,0 +1,263 @@
+"""Compute blocks of the hot path, each with an explicit forward and backward
+(there is no autograd: every kernel is hand-written, see csrc/).  All sequences
+are frame-major [T, B, F] device tensors."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .params import ParamSpec
+
+BN_EPS = 1e-3  # tf.layers.batch_normalization defaults (encoder.py:45)
+BN_MOMENTUM = 0.99
+
+
+class BuildContext:
+    """Collects ParamSpecs while the model is being assembled, then owns the store."""
+
+    def __init__(self):
+        self.specs: List[ParamSpec] = []
+        self.store = None
+        self.world_size = 1
+        self.allreduce = None  # callable(tensor) -> None (in-place sum), set by Seq2SeqModel under DP
+
+    def declare(self, name, shape, init, trainable=True):
+        if any(s.name == name for s in self.specs):
+            raise Exception('duplicate variable ' + name)
+        self.specs.append(ParamSpec(name, tuple(int(x) for x in shape), init, trainable))
+        return name
+
+    def p(self, name):
+        return self.store.p(name)
+
+    def g(self, name):
+        return self.store.g(name)
+
+
+class BatchNormInput:
+    """tf.layers.batch_normalization(axis=-1) on the raw features (encoder.py:44-50):
+    batch statistics over every (b, t) position INCLUDING padding; momentum 0.99, eps 1e-3."""
+
+    def __init__(self, ctx: BuildContext, scope: str, F: int):
+        self.ctx, self.F = ctx, F
+        pre = f'{scope}/batch_normalization/'
+        self.gamma = ctx.declare(pre + 'gamma', (F,), 'ones')
+        self.beta = ctx.declare(pre + 'beta', (F,), 'zeros')
+        self.mm = ctx.declare(pre + 'moving_mean', (F,), 'zeros', trainable=False)
+        self.mv = ctx.declare(pre + 'moving_variance', (F,), 'ones', trainable=False)
+
+    def forward(self, x: torch.Tensor, train: bool) -> torch.Tensor:
+        ctx = self.ctx
+        T, B, F = x.shape
+        x2 = x.view(T * B, F)
+        y = torch.empty_like(x)
+        if not train:
+            ops.bn_apply_eval(x2, ctx.p(self.gamma), ctx.p(self.beta), ctx.p(self.mm), ctx.p(self.mv), BN_EPS, y)
+            return y
+        sums = ops.zeros(2 * F)
+        ops.bn_stats(x2, sums)
+        count = float(T * B)
+        if ctx.world_size > 1:  # exact large-batch statistics under data parallelism
+            ctx.allreduce(sums)
+            count *= ctx.world_size
+        self.xhat = torch.empty_like(x)
+        self.invstd = ops.empty(F)
+        self.count = count
+        ops.bn_apply_train(x2, sums, count, ctx.p(self.gamma), ctx.p(self.beta), BN_EPS, BN_MOMENTUM, y,
+                           self.xhat, self.invstd, ctx.p(self.mm), ctx.p(self.mv))
+        return y
+
+    def backward(self, dy: torch.Tensor) -> torch.Tensor:
+        ctx = self.ctx
+        T, B, F = dy.shape
+        dy2, xh2 = dy.view(T * B, F), self.xhat.view(T * B, F)
+        sums2 = ops.zeros(2 * F)
+        ops.bn_bwd_stats(dy2, xh2, sums2)
+        local = sums2
+        if ctx.world_size > 1:
+            local = sums2.clone()  # dgamma/dbeta stay local sums (the gradient all-reduce adds them up)
+            ctx.allreduce(sums2)
+        dx = torch.empty_like(dy)
+        ops.bn_bwd_apply(dy2, xh2, sums2, self.count, ctx.p(self.gamma), self.invstd, dx, None, None)
+        ops.axpy(1.0, local[F:], ctx.g(self.gamma))
+        ops.axpy(1.0, local[:F], ctx.g(self.beta))
+        return dx
+
+
+class LSTMLayerOp:
+    """One LSTMCell layer under dynamic_rnn (cells.py:14-18, encoder.py:80)."""
+
+    def __init__(self, ctx: BuildContext, prefix: str, in_dim: int, H: int):
+        self.ctx, self.I, self.H = ctx, in_dim, H
+        self.kernel = ctx.declare(prefix + '/kernel', (in_dim + H, 4 * H), 'lstm_kernel')
+        self.bias = ctx.declare(prefix + '/bias', (4 * H,), 'zeros')
+
+    def forward(self, x: torch.Tensor, lens: torch.Tensor):
+        T, B, I = x.shape
+        H = self.H
+        W, b = self.ctx.p(self.kernel), self.ctx.p(self.bias)
+        gates = ops.empty(T, B, 4 * H)
+        ops.gemm(x.view(T * B, I), W[:I], gates.view(T * B, 4 * H), bias=b)
+        self.x = x
+        self.rnn = ops.RnnSeq(T, B, H, lens, gates, W[I:])
+        out = self.rnn.forward()
+        self.final = (self.rnn.cT, self.rnn.hT)
+        return out
+
+    def backward(self, dout, dstate=None, need_dx=True):
+        T, B, I = self.x.shape
+        H = self.H
+        W = self.ctx.p(self.kernel)
+        gW, gb = self.ctx.g(self.kernel), self.ctx.g(self.bias)
+        dcT, dhT = dstate if dstate is not None else (None, None)
+        dZ = self.rnn.backward(dout, gW[I:], dcT=dcT, dhT=dhT)
+        dZ2 = dZ.view(T * B, 4 * H)
+        ops.gemm(self.x.view(T * B, I), dZ2, gW[:I], ta=True, beta=1.0)
+        ops.colsum(dZ2, gb)
+        dx = None
+        if need_dx:
+            dx = ops.empty(T, B, I)
+            ops.gemm(dZ2, W[:I], dx.view(T * B, I), tb=True)
+        self.rnn = None
+        return dx
+
+
+class MechDef:
+    """Static description of one attention mechanism (attention.py:5-88)."""
+
+    def __init__(self, ctx: BuildContext, kind: str, wrap_prefix: str, idx: int, mem_layer_name: str, H: int, Dm: int,
+                 A: int):
+        self.kind, self.H, self.Dm, self.A = kind, H, Dm, A
+        sfx = '' if idx == 0 else f'_{idx}'
+        fam = 'luong_attention' if 'luong' in kind else 'bahdanau_attention'
+        self.Wm = ctx.declare(mem_layer_name, (Dm, A), 'glorot')
+        self.Wq = self.v = self.g = self.b = None
+        if kind == 'scaled_luong':
+            self.g = ctx.declare(f'{wrap_prefix}/{fam}{sfx}/attention_g', (), 'ones')
+        if 'bahdanau' in kind:
+            self.Wq = ctx.declare(f'{wrap_prefix}/{fam}{sfx}/query_layer/kernel', (H, A), 'glorot')
+            self.v = ctx.declare(f'{wrap_prefix}/{fam}{sfx}/attention_v', (A,), 'glorot')
+        if kind == 'normed_bahdanau':
+            self.g = ctx.declare(f'{wrap_prefix}/{fam}{sfx}/attention_g', (), 'const:%r' % (1.0 / A) ** 0.5)
+            self.b = ctx.declare(f'{wrap_prefix}/{fam}{sfx}/attention_b', (A,), 'zeros')
+        self.Wl = ctx.declare(f'{wrap_prefix}/attention_layer{sfx}/kernel', (H + Dm, A), 'glorot')
+
+    @property
+    def output_attention(self):
+        return 'luong' in self.kind
+
+
+class AttnLSTMOp:
+    """AttentionWrapper(LSTMCell) under dynamic_rnn / dynamic_decode (attention.py:132-191)."""
+
+    def __init__(self, ctx: BuildContext, wrap_prefix: str, in_dim: int, H: int, mechs: Sequence[MechDef]):
+        self.ctx, self.Dx, self.H, self.mechs = ctx, in_dim, H, list(mechs)
+        self.At = sum(m.A for m in self.mechs)
+        self.kernel = ctx.declare(wrap_prefix + '/lstm_cell/kernel', (in_dim + self.At + H, 4 * H), 'lstm_kernel')
+        self.bias = ctx.declare(wrap_prefix + '/lstm_cell/bias', (4 * H,), 'zeros')
+        self.output_attention = self.mechs[-1].output_attention  # flag of the last mechanism created
+        self.out_dim = self.At if self.output_attention else H
+
+    def prepare_memories(self, memories: Sequence[Tuple[torch.Tensor, torch.Tensor]]):
+        """keys = memory_layer(values), once per batch (TF computes them at construction)."""
+        ctx = self.ctx
+        bufs = []
+        for md, (values, mem_len) in zip(self.mechs, memories):
+            Tm, B, Dm = values.shape
+            keys = ops.empty(Tm, B, md.A)
+            ops.gemm(values.view(Tm * B, Dm), ctx.p(md.Wm), keys.view(Tm * B, md.A))
+            v = ctx.p(md.v) if md.v else None
+            if md.kind == 'normed_bahdanau':
+                veff = ops.empty(md.A)
+                ops.normed_v_fwd(ctx.p(md.v), ctx.p(md.g), veff)
+                v = veff
+            bufs.append(ops.MechBuffers(md.kind, values, keys, mem_len, ctx.p(md.Wl),
+                                        Wq=ctx.p(md.Wq) if md.Wq else None, v=v,
+                                        g=ctx.p(md.g) if md.kind == 'scaled_luong' else None,
+                                        bias=ctx.p(md.b) if md.b else None))
+        return bufs
+
+    def forward(self, x, lens, memories=None, init=None, mech_bufs=None):
+        """x [T,B,Dx]; memories [(values [Tm,B,Dm], mem_len)]; init = (c0, h0) or None."""
+        T, B, Dx = x.shape
+        H = self.H
+        ctx = self.ctx
+        W, b = ctx.p(self.kernel), ctx.p(self.bias)
+        gates = ops.empty(T, B, 4 * H)
+        ops.gemm(x.view(T * B, Dx), W[:Dx], gates.view(T * B, 4 * H), bias=b)
+        self.x = x
+        self.bufs = mech_bufs if mech_bufs is not None else self.prepare_memories(memories)
+        c0, h0 = init if init is not None else (None, None)
+        self.rnn = ops.RnnSeq(T, B, H, lens, gates, W[Dx:], self.bufs, self.output_attention, c0=c0, h0=h0)
+        out = self.rnn.forward()
+        self.final = (self.rnn.cT, self.rnn.hT)
+        return out
+
+    def step(self, x1, active, mech_bufs, state):
+        """One decode step (inference).  x1 [1,B,Dx]; active [B] int32 (1 = run, 0 = carry state,
+        emit zeros: impute_finished); state = (c [B,H], S [B,At+H]).  Returns (out [B,O], new state)."""
+        _, B, Dx = x1.shape
+        H = self.H
+        W, b = self.ctx.p(self.kernel), self.ctx.p(self.bias)
+        gates = ops.empty(1, B, 4 * H)
+        ops.gemm(x1.view(B, Dx), W[:Dx], gates.view(B, 4 * H), bias=b)
+        c, S = state
+        rnn = ops.RnnSeq(1, B, H, active, gates, W[Dx:], mech_bufs, self.output_attention, c0=c, s0=S)
+        out = rnn.forward()
+        self.last_step = rnn
+        return out[0], (rnn.cT, rnn.S[1])
+
+    def initial_state(self, B, init=None):
+        S = ops.zeros(B, self.At + self.H)
+        if init is not None:
+            S[:, self.At:].copy_(init[1])
+            c = init[0].clone()
+        else:
+            c = ops.zeros(B, self.H)
+        return (c, S)
+
+    def backward(self, dout, dstate=None, need_dx=True, want_init_grad=True):
+        """Returns (dx, [dmemory per mechanism], (dc0, dh0))."""
+        ctx = self.ctx
+        T, B, Dx = self.x.shape
+        H = self.H
+        W = ctx.p(self.kernel)
+        gW, gb = ctx.g(self.kernel), ctx.g(self.bias)
+        dveff = {}
+        for k, (md, mb) in enumerate(zip(self.mechs, self.bufs)):
+            mb.dkeys = ops.zeros(mb.Tm, B, mb.A)
+            mb.dvalues = ops.zeros(mb.Tm, B, mb.Dm)
+            mb.dWl = ctx.g(md.Wl)
+            if md.Wq:
+                mb.dWq = ctx.g(md.Wq)
+                if md.kind == 'normed_bahdanau':
+                    dveff[k] = ops.zeros(mb.A)
+                    mb.dv = dveff[k]
+                    mb.dbias = ctx.g(md.b)
+                else:
+                    mb.dv = ctx.g(md.v)
+            if md.kind == 'scaled_luong':
+                mb.dg = ctx.g(md.g)
+        dcT, dhT = dstate if dstate is not None else (None, None)
+        dZ = self.rnn.backward(dout, gW[Dx:], dcT=dcT, dhT=dhT, want_init_grad=want_init_grad)
+        dZ2 = dZ.view(T * B, 4 * H)
+        ops.gemm(self.x.view(T * B, Dx), dZ2, gW[:Dx], ta=True, beta=1.0)
+        ops.colsum(dZ2, gb)
+        dx = None
+        if need_dx:
+            dx = ops.empty(T, B, Dx)
+            ops.gemm(dZ2, W[:Dx], dx.view(T * B, Dx), tb=True)
+        dmem = []
+        for k, (md, mb) in enumerate(zip(self.mechs, self.bufs)):
+            v2 = mb.values.view(mb.Tm * B, mb.Dm)
+            dk2 = mb.dkeys.view(mb.Tm * B, mb.A)
+            ops.gemm(v2, dk2, ctx.g(md.Wm), ta=True, beta=1.0)  # dWm
+            ops.gemm(dk2, ctx.p(md.Wm), mb.dvalues.view(mb.Tm * B, mb.Dm), tb=True, beta=1.0)
+            dmem.append(mb.dvalues)
+            if k in dveff:
+                ops.normed_v_bwd(ctx.p(md.v), ctx.p(md.g), dveff[k], ctx.g(md.v), ctx.g(md.g))
+        dinit = (self.rnn.dc0, self.rnn.dh0)
+        self.rnn = None
+        return dx, dmem, dinit

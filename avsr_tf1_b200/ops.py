@@ -1,0 +1,257 @@
+"""Thin Python wrappers over the C ABI.  torch tensors are used ONLY as device
+buffers (allocation, streams); every arithmetic kernel is in libavsr_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ATTN_KINDS, AvsrAttnMech, AvsrRnnSeq, check
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk_f32(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise _lib.AvsrError('expected a CUDA float32 tensor, got %s %s' % (t.device, t.dtype))
+
+
+def launch_count() -> int:
+    return int(_lib.load().avsr_launch_count())
+
+
+def set_tensor_cores(enable: bool) -> bool:
+    return bool(_lib.load().avsr_set_tensor_cores(1 if enable else 0))
+
+
+def empty(*shape, dtype=torch.float32):
+    return torch.empty(*shape, dtype=dtype, device='cuda')
+
+
+def zeros(*shape, dtype=torch.float32):
+    return torch.zeros(*shape, dtype=dtype, device='cuda')
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, ta=False, tb=False, beta=0.0, bias=None):
+    """out[M,N] = beta*out + op(A) op(B) (+bias).  2-D tensors, unit inner stride, any row stride."""
+    _chk_f32(A, B, out, bias)
+    assert A.dim() == 2 and B.dim() == 2 and out.dim() == 2
+    assert A.stride(1) == 1 and B.stride(1) == 1 and out.stride(1) == 1, 'inner stride must be 1'
+    M, K = (A.shape[1], A.shape[0]) if ta else A.shape
+    K2, N = (B.shape[1], B.shape[0]) if tb else B.shape
+    assert K == K2, f'gemm inner dims differ: {K} vs {K2}'
+    assert tuple(out.shape) == (M, N), f'gemm out shape {tuple(out.shape)} != {(M, N)}'
+    check(_lib.load().avsr_gemm(_stream(), int(ta), int(tb), M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(),
+                                B.stride(0), out.data_ptr(), out.stride(0), float(beta), _p(bias)))
+    return out
+
+
+def colsum(X: torch.Tensor, out: torch.Tensor):
+    """out[N] += column sums of X[M,N]."""
+    _chk_f32(X, out)
+    check(_lib.load().avsr_colsum(_stream(), X.data_ptr(), X.shape[0], X.shape[1], X.stride(0), out.data_ptr()))
+
+
+def bn_stats(x2d, sums):
+    check(_lib.load().avsr_bn_stats(_stream(), x2d.data_ptr(), x2d.shape[0], x2d.shape[1], sums.data_ptr()))
+
+
+def bn_apply_train(x2d, sums, count, gamma, beta, eps, momentum, y, xhat, invstd, mm, mv):
+    check(_lib.load().avsr_bn_apply_train(_stream(), x2d.data_ptr(), x2d.shape[0], x2d.shape[1], sums.data_ptr(),
+                                          float(count), gamma.data_ptr(), beta.data_ptr(), eps, momentum,
+                                          y.data_ptr(), xhat.data_ptr(), invstd.data_ptr(), _p(mm), _p(mv)))
+
+
+def bn_apply_eval(x2d, gamma, beta, mm, mv, eps, y):
+    check(_lib.load().avsr_bn_apply_eval(_stream(), x2d.data_ptr(), x2d.shape[0], x2d.shape[1], gamma.data_ptr(),
+                                         beta.data_ptr(), mm.data_ptr(), mv.data_ptr(), eps, y.data_ptr()))
+
+
+def bn_bwd_stats(dy2d, xhat2d, sums2):
+    check(_lib.load().avsr_bn_bwd_stats(_stream(), dy2d.data_ptr(), xhat2d.data_ptr(), dy2d.shape[0], dy2d.shape[1],
+                                        sums2.data_ptr()))
+
+
+def bn_bwd_apply(dy2d, xhat2d, sums2, count, gamma, invstd, dx, dgamma, dbeta):
+    check(_lib.load().avsr_bn_bwd_apply(_stream(), dy2d.data_ptr(), xhat2d.data_ptr(), dy2d.shape[0], dy2d.shape[1],
+                                        sums2.data_ptr(), float(count), gamma.data_ptr(), invstd.data_ptr(),
+                                        dx.data_ptr(), _p(dgamma), _p(dbeta)))
+
+
+def reverse_sequence(x: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+    """x [T,B,F] -> tf.reverse_sequence along time."""
+    T, B, F = x.shape
+    y = torch.empty_like(x)
+    check(_lib.load().avsr_reverse_sequence(_stream(), x.data_ptr(), y.data_ptr(), T, B, F, lens.data_ptr()))
+    return y
+
+
+def transpose01(x: torch.Tensor) -> torch.Tensor:
+    """[d0,d1,F] -> [d1,d0,F] (batch-major <-> frame-major)."""
+    x = x.contiguous()
+    d0, d1 = x.shape[0], x.shape[1]
+    F = int(x.numel() // max(1, d0 * d1))
+    y = torch.empty((d1, d0) + tuple(x.shape[2:]), dtype=x.dtype, device=x.device)
+    _chk_f32(x)
+    check(_lib.load().avsr_transpose01(_stream(), x.data_ptr(), y.data_ptr(), d0, d1, F))
+    return y
+
+
+def embedding_fwd(table, ids, out):
+    check(_lib.load().avsr_embedding_fwd(_stream(), table.data_ptr(), table.shape[0], table.shape[1], ids.data_ptr(),
+                                         ids.numel(), out.data_ptr()))
+
+
+def embedding_bwd(dout2d, ids, dtable):
+    check(_lib.load().avsr_embedding_bwd(_stream(), dout2d.data_ptr(), ids.data_ptr(), ids.numel(), dtable.shape[0],
+                                         dtable.shape[1], dtable.data_ptr()))
+
+
+def seq_loss(logits, labels, labels_len, inv_denom, loss_sum, dlogits):
+    T, B, V = logits.shape
+    check(_lib.load().avsr_seq_loss(_stream(), logits.data_ptr(), T, B, V, labels.data_ptr(), labels.stride(0),
+                                    labels_len.data_ptr(), float(inv_denom), loss_sum.data_ptr(), dlogits.data_ptr()))
+
+
+def sumsq(x, out):
+    check(_lib.load().avsr_sumsq(_stream(), x.data_ptr(), x.numel(), out.data_ptr()))
+
+
+def axpy(a, x, y):
+    check(_lib.load().avsr_axpy(_stream(), float(a), x.data_ptr(), y.data_ptr(), x.numel()))
+
+
+def adam_clip_step(params, grads, m, v, sumsq_dev, clip_norm, lr_t, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(_lib.load().avsr_adam_clip_step(_stream(), params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                          params.numel(), sumsq_dev.data_ptr(), float(clip_norm), float(lr_t),
+                                          beta1, beta2, eps))
+
+
+def normed_v_fwd(v, g, veff):
+    check(_lib.load().avsr_normed_v_fwd(_stream(), v.data_ptr(), g.data_ptr(), v.numel(), veff.data_ptr()))
+
+
+def normed_v_bwd(v, g, dveff, dv, dg):
+    check(_lib.load().avsr_normed_v_bwd(_stream(), v.data_ptr(), g.data_ptr(), dveff.data_ptr(), v.numel(),
+                                        dv.data_ptr(), dg.data_ptr()))
+
+
+def greedy_pick(logits, eos, finished, sample_out, next_ids):
+    B, V = logits.shape
+    check(_lib.load().avsr_greedy_pick(_stream(), logits.data_ptr(), B, V, eos, finished.data_ptr(),
+                                       sample_out.data_ptr(), next_ids.data_ptr()))
+
+
+def beam_step(logits, B, W, eos, lpw, log_probs, finished, lengths, word, parent, score):
+    V = logits.shape[1]
+    check(_lib.load().avsr_beam_step(_stream(), logits.data_ptr(), B, W, V, eos, float(lpw), log_probs.data_ptr(),
+                                     finished.data_ptr(), lengths.data_ptr(), word.data_ptr(), parent.data_ptr(),
+                                     score.data_ptr()))
+
+
+def gather_rows(src2d, idx, dst2d):
+    check(_lib.load().avsr_gather_rows(_stream(), src2d.data_ptr(), idx.data_ptr(), idx.numel(), src2d.shape[1],
+                                       dst2d.data_ptr()))
+
+
+# --------------------------------------------------------------------------- #
+# recurrent sequence op
+# --------------------------------------------------------------------------- #
+class MechBuffers:
+    """Device buffers of one attention mechanism for one sequence call."""
+
+    def __init__(self, kind: str, values, keys, mem_len, Wl, Wq=None, v=None, g=None, bias=None):
+        self.kind = kind
+        self.values, self.keys, self.mem_len = values, keys, mem_len
+        self.Wl, self.Wq, self.v, self.g, self.bias = Wl, Wq, v, g, bias
+        self.Tm, self.B, self.Dm = values.shape
+        self.A = keys.shape[2]
+        self.align = self.hc = self.pq = None
+        self.dkeys = self.dvalues = self.dWl = self.dWq = self.dv = self.dg = self.dbias = self.dpq = None
+
+    def fill(self, m: AvsrAttnMech):
+        m.kind = ATTN_KINDS[self.kind]
+        m.Tm, m.Dm, m.A = self.Tm, self.Dm, self.A
+        for k in ('values', 'keys', 'mem_len', 'Wl', 'Wq', 'v', 'g', 'bias', 'align', 'hc', 'pq', 'dkeys', 'dvalues',
+                  'dWl', 'dWq', 'dv', 'dg', 'dbias', 'dpq'):
+            setattr(m, k, _p(getattr(self, k)))
+
+
+class RnnSeq:
+    """One dynamic_rnn / dynamic_decode loop (see AvsrRnnSeq in include/avsr_b200.h)."""
+
+    def __init__(self, T, B, H, lens, gates, Wrec, mechs: Sequence[MechBuffers] = (), output_attention=False,
+                 c0=None, h0=None, s0=None):
+        self.T, self.B, self.H = T, B, H
+        self.lens, self.gates, self.Wrec, self.c0 = lens, gates, Wrec, c0
+        self.mechs = list(mechs)
+        self.oa = bool(output_attention) and len(self.mechs) > 0
+        self.At = sum(m.A for m in self.mechs)
+        SW = self.At + H
+        self.S = empty(T + 1, B, SW)
+        if s0 is not None:  # full state row [attention | h] (step-wise decoding)
+            self.S[0].copy_(s0)
+        else:
+            if self.At > 0:
+                self.S[0, :, :self.At].zero_()
+            if h0 is None:
+                self.S[0, :, self.At:].zero_()
+            else:
+                self.S[0, :, self.At:].copy_(h0)
+        self.craw = empty(T, B, H)
+        self.out = empty(T, B, self.At if self.oa else H)
+        self.cT = empty(B, H)
+        self.hT = empty(B, H)
+        for m in self.mechs:
+            m.align = empty(T, B, m.Tm)
+            m.hc = empty(T, B, H + m.Dm)
+            if 'bahdanau' in m.kind:
+                m.pq = empty(T, B, m.A)
+        maxHD = max([H + m.Dm for m in self.mechs], default=0)
+        maxA = max([m.A for m in self.mechs], default=0)
+        nwork = int(_lib.load().avsr_rnn_work_floats(B, H, self.At, maxHD, maxA))
+        self.work = empty(max(nwork, 4))
+        self.dZ = self.dA = None
+
+    def _desc(self, **bw) -> AvsrRnnSeq:
+        r = AvsrRnnSeq()
+        r.T, r.B, r.H, r.n_mech, r.output_attention = self.T, self.B, self.H, len(self.mechs), int(self.oa)
+        r.len, r.gates, r.Wrec, r.c0 = _p(self.lens), _p(self.gates), _p(self.Wrec), _p(self.c0)
+        r.S, r.craw, r.out, r.cT, r.hT = _p(self.S), _p(self.craw), _p(self.out), _p(self.cT), _p(self.hT)
+        for k, m in enumerate(self.mechs):
+            m.fill(r.mech[k])
+        r.work = _p(self.work)
+        for k, v in bw.items():
+            setattr(r, k, _p(v))
+        return r
+
+    def forward(self):
+        r = self._desc()
+        check(_lib.load().avsr_rnn_seq_fwd(_stream(), C.byref(r)))
+        return self.out
+
+    def backward(self, dout, dWrec, dcT=None, dhT=None, want_init_grad=False):
+        """Fills self.dZ [T,B,4H]; accumulates dWrec and the mechanism grads (set on the MechBuffers)."""
+        T, B, H = self.T, self.B, self.H
+        self.dZ = empty(T, B, 4 * H)
+        if self.At > 0:
+            self.dA = empty(T, B, self.At)
+        self.dc0 = empty(B, H) if want_init_grad else None
+        self.dh0 = empty(B, H) if want_init_grad else None
+        for m in self.mechs:
+            if 'bahdanau' in m.kind:
+                m.dpq = empty(T, B, m.A)
+        r = self._desc(dout=dout, dcT=dcT, dhT=dhT, dZ=self.dZ, dA=self.dA, dWrec=dWrec, dc0=self.dc0, dh0=self.dh0)
+        check(_lib.load().avsr_rnn_seq_bwd(_stream(), C.byref(r)))
+        return self.dZ

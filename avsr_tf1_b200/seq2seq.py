@@ -1,0 +1,335 @@
+"""Seq2SeqModel - drop-in for reference avsr/seq2seq.py (Seq2SeqModel :9-280).
+
+Same constructor, same attribute surface the reference caller (avsr/avsr.py)
+uses - ``train_op``, ``batch_loss``, ``global_norm``, ``global_step``, ``saver``,
+``_decoder.inference_predicted_ids`` - but eager: there is no TF graph/session.
+``data_sequences`` carries concrete batches (numpy or torch, batch-major like the
+reference) instead of tf.data iterator nodes; ``train_op()`` runs one optimiser
+step on the currently fed batch, ``feed()`` swaps the batch.
+
+Everything numeric runs in hand-written sm_100a CUDA (csrc/) through the C ABI of
+include/avsr_b200.h; torch supplies device buffers, streams and NCCL only."""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .decoder_bimodal import Seq2SeqBimodalDecoder
+from .decoder_unimodal import Seq2SeqUnimodalDecoder
+from .encoder import AttentiveEncoder, Seq2SeqEncoder
+from .layers import BuildContext
+from .params import ParamStore
+
+
+def _to_device(a, dtype):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        a = torch.from_numpy(np.ascontiguousarray(a))
+    if not a.is_cuda:
+        a = a.pin_memory() if not a.is_pinned() else a
+        a = a.to('cuda', non_blocking=True)
+    return a.to(dtype).contiguous()
+
+
+class Saver(object):
+    """tf.train.Saver stand-in (seq2seq.py:132-133): all global variables incl. Adam slots,
+    BN moving statistics and global_step, keyed by TF variable name, in one .npz file."""
+
+    def __init__(self, model):
+        self._model = model
+
+    def save(self, sess=None, save_path=None, global_step=None):
+        path = save_path if global_step is None else '%s-%d' % (save_path, global_step)
+        os.makedirs(os.path.dirname(os.path.abspath(path)) or '.', exist_ok=True)
+        st = self._model.store
+        blob = {'var/' + k: v for k, v in st.to_numpy('p').items()}
+        if st.m is not None:
+            blob.update({'adam_m/' + k: v for k, v in st.to_numpy('m').items()})
+            blob.update({'adam_v/' + k: v for k, v in st.to_numpy('v').items()})
+        blob['global_step'] = np.asarray(self._model._global_step, np.int64)
+        np.savez(path + '.npz', **blob)
+        return path
+
+    def restore(self, sess=None, save_path=None):
+        blob = np.load(save_path if save_path.endswith('.npz') else save_path + '.npz')
+        st = self._model.store
+        st.load_numpy({k[4:]: blob[k] for k in blob.files if k.startswith('var/')})
+        if st.m is not None and any(k.startswith('adam_m/') for k in blob.files):
+            for s in st.specs:
+                if s.trainable:
+                    st._view(st.m, s.name).copy_(torch.from_numpy(blob['adam_m/' + s.name]).reshape(
+                        st._view(st.m, s.name).shape))
+                    st._view(st.v, s.name).copy_(torch.from_numpy(blob['adam_v/' + s.name]).reshape(
+                        st._view(st.v, s.name).shape))
+        self._model._global_step = int(blob['global_step'])
+
+
+class Seq2SeqModel(object):
+    def __init__(self, data_sequences, mode, hparams, seed=2001, share_params_with=None, device='cuda'):
+        self._video_data = data_sequences[0]
+        self._audio_data = data_sequences[1]
+        self._mode = mode
+        self._hparams = hparams
+        if mode not in ('train', 'evaluate'):
+            raise ValueError('mode must be `train` or `evaluate`')
+        if hparams.cell_type != 'lstm':
+            raise Exception('cell type not supported: {}'.format(hparams.cell_type))
+        self._ctx = BuildContext()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self._ctx.world_size = torch.distributed.get_world_size()
+            self._ctx.allreduce = lambda t: torch.distributed.all_reduce(t)
+
+        self._make_encoders()
+        self._make_decoder()
+
+        if share_params_with is not None:
+            self.store = share_params_with.store
+        else:
+            # device='cpu' builds the variable table only (tests, checkpoint tools); compute needs CUDA
+            self.store = ParamStore(self._ctx.specs, device=device, with_optimizer=(mode == 'train'))
+            self.store.initialize(seed, vocab=len(hparams.unit_dict) - 1)
+        self._ctx.store = self.store
+        self._global_step = 0
+        self.batch_loss = None
+        self.global_norm = None
+        self.current_lr = None
+        if mode == 'train':
+            self._init_optimiser()
+        self._init_saver()
+        self._batch = None
+
+    # ---- construction (seq2seq.py:30-126) ---------------------------------------
+    def _make_encoders(self):
+        hp, ctx = self._hparams, self._ctx
+        if self._video_data is not None:
+            self._video_encoder = Seq2SeqEncoder(
+                data=self._video_data, mode=self._mode, hparams=hp,
+                num_units_per_layer=hp.encoder_units_per_layer[0],
+                dropout_probability=hp.video_encoder_dropout_probability, regress_aus=hp.regress_aus, ctx=ctx,
+                scope='video')
+        else:
+            self._video_encoder = None
+        if self._audio_data is not None:
+            if hp.architecture in ('unimodal', 'bimodal',):
+                self._audio_encoder = Seq2SeqEncoder(
+                    data=self._audio_data, mode=self._mode, hparams=hp,
+                    num_units_per_layer=hp.encoder_units_per_layer[1],
+                    dropout_probability=hp.audio_encoder_dropout_probability, ctx=ctx, scope='audio')
+            elif hp.architecture == 'av_align':
+                if self._video_encoder is None:
+                    raise Exception('av_align needs a video stream')
+                self._audio_encoder = AttentiveEncoder(
+                    data=self._audio_data, mode=self._mode, hparams=hp,
+                    num_units_per_layer=hp.encoder_units_per_layer[1],
+                    attended_memory_depth=self._video_encoder.output_dim,
+                    dropout_probability=hp.audio_encoder_dropout_probability, ctx=ctx, scope='audio')
+            else:
+                raise Exception('Unknown architecture')
+        else:
+            self._audio_encoder = None
+
+    def _state_depth(self, enc):
+        hp = self._hparams
+        if hp.encoder_type == 'bidirectional' and not isinstance(enc, AttentiveEncoder):
+            return hp.decoder_units_per_layer[0]
+        return enc._num_units_per_layer[-1]
+
+    def _make_decoder(self):
+        hp, ctx = self._hparams, self._ctx
+        if self._video_encoder is None and self._audio_encoder is None:
+            raise Exception('labels are None')
+        if hp.architecture in ('unimodal', 'av_align'):
+            enc = self._audio_encoder if self._audio_encoder is not None else self._video_encoder
+            self._decoder = Seq2SeqUnimodalDecoder([enc.output_dim], mode=self._mode, hparams=hp, ctx=ctx)
+        elif hp.architecture == 'bimodal':
+            if self._video_encoder is None or self._audio_encoder is None:
+                raise NotImplementedError('bimodal decoder with a missing modality (decoder_bimodal.py:127-142)')
+            self._decoder = Seq2SeqBimodalDecoder(
+                self._video_encoder.output_dim, self._audio_encoder.output_dim,
+                self._state_depth(self._video_encoder), self._state_depth(self._audio_encoder), mode=self._mode,
+                hparams=hp, ctx=ctx)
+        else:
+            raise Exception('Unknown architecture')
+
+    def _init_saver(self):
+        self.saver = Saver(self)
+
+    def _init_optimiser(self):
+        hp = self._hparams
+        if hp.loss_fun is not None:
+            raise ValueError('Unknown loss function {}'.format(hp.loss_fun)) if hp.loss_fun not in (
+                'focal_loss', 'mc_loss') else NotImplementedError('devel.py losses are self-described untested')
+        if hp.label_smoothing > 0.0:
+            raise NotImplementedError('label smoothing is off in every reference config')
+        if hp.optimiser != 'Adam':
+            raise Exception('Unsupported optimiser, try Adam') if hp.optimiser not in (
+                'Nadam', 'AdamW', 'Momentum') else NotImplementedError('only Adam is built on the B200 path')
+        if hp.lr_decay is not None:
+            raise NotImplementedError('cosine_restarts lr decay is not used by any shipped script')
+        self._l2_names = [n for n in self.store.names() if 'lstm_' in n and 'bias' not in n]  # seq2seq.py:283-290
+        self._loss_dev = torch.zeros(4, dtype=torch.float32, device=self.store.flat.device)
+
+    @property
+    def global_step(self):
+        return self._global_step
+
+    @property
+    def n_params(self):
+        return self.store.n_trainable
+
+    # ---- batches -------------------------------------------------------------------
+    def feed(self, data_sequences):
+        """Move one batch (batch-major, host or device) into frame-major device tensors."""
+        video, audio = data_sequences
+        b: Dict[str, object] = {}
+        ref = audio if audio is not None else video
+        for key, d in (('video', video), ('audio', audio)):
+            if d is None:
+                continue
+            x = _to_device(d.inputs, torch.float32)
+            if x.dim() > 3:  # raw lip crops [B,T,h,w,c] fed as flat features (video_processing='features')
+                x = x.reshape(x.shape[0], x.shape[1], -1)
+            b[key] = ops.transpose01(x)
+            b[key + '_len'] = _to_device(d.inputs_length, torch.int32)
+        if ref.labels is not None:
+            lab_len_host = ref.labels_length.cpu().numpy() if torch.is_tensor(ref.labels_length) \
+                else np.asarray(ref.labels_length)
+            T = int(lab_len_host.max())
+            labels = _to_device(ref.labels, torch.int32)
+            B = labels.shape[0]
+            go = torch.full((B, 1), self._decoder._GO_ID, dtype=torch.int32, device='cuda')
+            b['labels'] = labels
+            b['labels_len'] = _to_device(ref.labels_length, torch.int32)
+            b['dec_in_ids'] = torch.cat([go, labels], dim=1)[:, :T].t().contiguous()  # decoder_unimodal.py:61-68
+            b['T_dec'] = T
+            b['n_tokens'] = float(lab_len_host.sum())
+        self._batch = b
+        return b
+
+    # ---- forward ---------------------------------------------------------------------
+    def _encode(self, b):
+        enc = {}
+        if self._video_encoder is not None:
+            enc['video'] = self._video_encoder.forward(b['video'], b['video_len'])
+        if self._audio_encoder is not None:
+            if isinstance(self._audio_encoder, AttentiveEncoder):
+                enc['audio'] = self._audio_encoder.forward(b['audio'], b['audio_len'],
+                                                           attended_memory=enc['video'].outputs,
+                                                           attended_memory_length=b['video_len'])
+            else:
+                enc['audio'] = self._audio_encoder.forward(b['audio'], b['audio_len'])
+        return enc
+
+    def _decoder_inputs(self, b, enc):
+        if self._hparams.architecture == 'bimodal':
+            mems = [(enc['video'].outputs, b['video_len']), (enc['audio'].outputs, b['audio_len'])]
+            states = [enc['video'].final_state, enc['audio'].final_state]
+        else:
+            key = 'audio' if 'audio' in enc else 'video'
+            mems = [(enc[key].outputs, b[key + '_len'])]
+            states = [enc[key].final_state]
+        return mems, states
+
+    def encode(self, data_sequences=None):
+        """Parity probe: encoder outputs / final states (frame-major device tensors)."""
+        b = self.feed(data_sequences) if data_sequences is not None else self._batch
+        return self._encode(b)
+
+    def forward_backward(self):
+        """Forward + backward on the fed batch.  Leaves local gradient sums in store.grad and
+        the cross-entropy SUM (un-normalised over DP ranks handled via inv_denom) in _loss_dev[0]."""
+        b, ctx = self._batch, self._ctx
+        self.store.grad.zero_()
+        self._loss_dev.zero_()
+        n_tok = b['n_tokens']
+        if ctx.world_size > 1:  # exact large-batch loss denominator under data parallelism
+            t = torch.tensor([n_tok], dtype=torch.float64, device='cuda')
+            ctx.allreduce(t)
+            n_tok = float(t.item())
+        inv_denom = 1.0 / (n_tok + 1e-12)  # seq2seq.sequence_loss
+        enc = self._encode(b)
+        mems, states = self._decoder_inputs(b, enc)
+        self._decoder.forward_train(mems, states, b['dec_in_ids'], b['labels'], b['labels_len'], b['T_dec'],
+                                    inv_denom, self._loss_dev[0:1])
+        self._inv_denom = inv_denom
+        dmem, dstates = self._decoder.backward_train()
+        if self._hparams.architecture == 'bimodal':
+            self._audio_encoder.backward(dmem[1], dstates[1])
+            self._video_encoder.backward(dmem[0], dstates[0])
+        elif self._audio_encoder is not None:
+            if isinstance(self._audio_encoder, AttentiveEncoder):
+                _, dvid = self._audio_encoder.backward(dmem[0], dstates[0])
+                self._video_encoder.backward(dvid, None)
+            else:
+                self._audio_encoder.backward(dmem[0], dstates[0])
+                if self._video_encoder is not None:  # unimodal with both streams: video is unused by the loss
+                    pass
+        else:
+            self._video_encoder.backward(dmem[0], dstates[0])
+
+    def _lr_now(self):
+        hp = self._hparams
+        lr = hp.learning_rate
+        steps = hp.kwargs.get('warmup_steps', 750)
+        if steps:
+            lr *= min(1.0, (self._global_step + 1) / float(steps))  # seq2seq.py:275-280
+        return lr
+
+    def apply_gradients(self):
+        """all-reduce (DP) -> + L2 -> global norm -> clip + TF-Adam (seq2seq.py:175-178, 195-257)."""
+        hp, ctx, st = self._hparams, self._ctx, self.store
+        if ctx.world_size > 1:
+            ctx.allreduce(st.grad)
+            ctx.allreduce(self._loss_dev[0:1])
+        if hp.recurrent_l2_regularisation is not None:
+            for n in self._l2_names:
+                ops.axpy(hp.recurrent_l2_regularisation, st.p(n), st.g(n))
+                ops.sumsq(st.p(n), self._loss_dev[1:2])
+        ops.sumsq(st.grad, self._loss_dev[2:3])
+        lr = self._lr_now()
+        self.current_lr = lr
+        t = self._global_step + 1
+        lr_t = lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        clip = hp.max_gradient_norm if hp.clip_gradients is True else 0.0
+        ops.adam_clip_step(st.flat, st.grad, st.m, st.v, self._loss_dev[2:3], clip, lr_t, 0.9, 0.999, 1e-8)
+        self._global_step += 1
+
+    def fetch_scalars(self):
+        """Device -> host read of the step's results (what session.run returns, avsr.py:265-271)."""
+        hp = self._hparams
+        vals = self._loss_dev.cpu().numpy()
+        xent = float(vals[0]) * self._inv_denom  # sum(xent*w) / (sum(w) + 1e-12)
+        reg = 0.5 * (hp.recurrent_l2_regularisation or 0.0) * float(vals[1])
+        self.batch_loss = xent + reg
+        self.global_norm = math.sqrt(float(vals[2]))
+        return self.batch_loss, self.global_norm
+
+    def train_step(self, data_sequences=None, fetch=True):
+        if self._mode != 'train':
+            raise Exception('train_step needs mode == `train`')
+        if data_sequences is not None:
+            self.feed(data_sequences)
+        self.forward_backward()
+        self.apply_gradients()
+        if fetch:
+            return self.fetch_scalars()
+        return None
+
+    def train_op(self):
+        return self.train_step()
+
+    # ---- inference -------------------------------------------------------------------------
+    def predict(self, data_sequences=None):
+        """Runs the decoding algorithm of hparams (avsr.py:345): int32 ids [B, <=150]."""
+        b = self.feed(data_sequences) if data_sequences is not None else self._batch
+        enc = self._encode(b)
+        mems, states = self._decoder_inputs(b, enc)
+        if self._hparams.decoding_algorithm == 'greedy':
+            return self._decoder.decode_greedy(mems, states)
+        return self._decoder.decode_beam(mems, states)

@@ -1,0 +1,177 @@
+/* avsr_b200.h - C ABI of the B200-native AVSR seq2seq hot path.
+ *
+ * The reference (georgesterpu/avsr-tf1) is pure Python on TensorFlow 1.13 and has
+ * no FFI of its own; its hot path bottoms out in TF library calls.  Every entry
+ * point below therefore names the TF call site in the reference that it replaces
+ * (file:line into the reference tree).  The Python host in avsr_tf1_b200/ binds
+ * these with ctypes (avsr_tf1_b200/_lib.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host
+ *   - all floating point is fp32; lengths / ids are int32
+ *   - sequences are frame-major (time-major): [T, B, F], F contiguous
+ *   - `stream` is a cudaStream_t passed as void*
+ *   - return 0 on success; otherwise avsr_last_error() describes the failure
+ *   - no allocation, no synchronisation: calls only enqueue kernels on `stream`
+ *     (so a whole training step can be captured into one CUDA graph)
+ */
+#ifndef AVSR_B200_H_
+#define AVSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* avsr_stream_t;
+
+const char* avsr_last_error(void);
+int avsr_version(void);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+unsigned long long avsr_launch_count(void);
+/* 1 if the tcgen05 tensor-core GEMM path is enabled (default), 0 = exact fp32 CUDA cores */
+int avsr_set_tensor_cores(int enable);
+
+/* ---- dense products: tf.matmul / tf.layers.dense call sites ------------------
+ * (LSTMCell kernel product cells.py:14; memory_layer attention.py:26; my_dense
+ * decoder_unimodal.py:112; state projections encoder.py:134-137,
+ * decoder_bimodal.py:480-492; and their tf.gradients counterparts seq2seq.py:222)
+ * C[M,N](ldc) = beta*C + op(A) op(B) (+ bias[N]);  beta in {0,1}
+ * transA=0: A is [M,K] row-major (lda); transA=1: A is stored [K,M].  Same for B. */
+int avsr_gemm(avsr_stream_t stream, int transA, int transB, int M, int N, int K, const float* A, int lda,
+              const float* B, int ldb, float* C, int ldc, float beta, const float* bias);
+/* out[N] += column sums of X[M,N] (ldx)  (bias gradients) */
+int avsr_colsum(avsr_stream_t stream, const float* X, int M, int N, int ldx, float* out);
+
+/* ---- input batch normalisation: tf.layers.batch_normalization, encoder.py:44-50
+ * statistics over all rows (= B*T positions INCLUDING padding), per feature.
+ * Split in stats / apply so data-parallel ranks can all-reduce `sums` between. */
+int avsr_bn_stats(avsr_stream_t stream, const float* x, long long rows, int F, float* sums /*[2F]: sum, sumsq*/);
+int avsr_bn_apply_train(avsr_stream_t stream, const float* x, long long rows, int F, const float* sums,
+                        double count, const float* gamma, const float* beta, float eps, float momentum,
+                        float* y, float* xhat, float* invstd /*[F]*/, float* moving_mean, float* moving_var);
+int avsr_bn_apply_eval(avsr_stream_t stream, const float* x, long long rows, int F, const float* gamma,
+                       const float* beta, const float* moving_mean, const float* moving_var, float eps, float* y);
+/* backward: sums2 = [sum dy, sum dy*xhat] (all-reducible), then dx */
+int avsr_bn_bwd_stats(avsr_stream_t stream, const float* dy, const float* xhat, long long rows, int F,
+                      float* sums2 /*[2F]*/);
+int avsr_bn_bwd_apply(avsr_stream_t stream, const float* dy, const float* xhat, long long rows, int F,
+                      const float* sums2, double count, const float* gamma, const float* invstd, float* dx,
+                      float* dgamma, float* dbeta);
+
+/* ---- tf.reverse_sequence used by bidirectional_dynamic_rnn (encoder.py:110) --- */
+int avsr_reverse_sequence(avsr_stream_t stream, const float* x, float* y, int T, int B, int F, const int* len);
+
+/* boundary layout change: y[d1,d0,F] = x[d0,d1,F] (reference tensors are batch-major,
+ * device tensors frame-major) */
+int avsr_transpose01(avsr_stream_t stream, const float* x, float* y, int d0, int d1, int F);
+
+/* ---- recurrent sequence op --------------------------------------------------
+ * One call = one tf.nn.dynamic_rnn / seq2seq.dynamic_decode loop over an LSTMCell
+ * (cells.py:14-18: gate order i,j,f,o, forget bias 1, cell_clip 1), optionally
+ * wrapped in a seq2seq.AttentionWrapper with 1 or 2 mechanisms
+ * (attention.py:132-191; AV-Align encoder.py:265-290; LAS decoder
+ * decoder_unimodal.py:299-352; WLAS decoder decoder_bimodal.py:227-277).
+ * Length semantics of dynamic_rnn(sequence_length) / impute_finished: past
+ * len[b] the output row is 0 and the cell state is carried.                  */
+enum { AVSR_ATTN_LUONG = 0, AVSR_ATTN_SCALED_LUONG = 1, AVSR_ATTN_BAHDANAU = 2, AVSR_ATTN_NORMED_BAHDANAU = 3 };
+
+typedef struct AvsrAttnMech {
+  int kind, Tm, Dm, A;
+  const float* values;  /* [Tm,B,Dm] memory, zero past mem_len (encoder outputs already are) */
+  const float* keys;    /* [Tm,B,A]  = values @ memory_layer */
+  const int* mem_len;   /* [B] */
+  const float* Wl;      /* attention_layer kernel [(H+Dm), A] */
+  const float* Wq;      /* query_layer kernel [H,A]           (Bahdanau family) */
+  const float* v;       /* attention_v [A] (normed: the effective g*v/|v|) */
+  const float* g;       /* attention_g [1]                    (scaled Luong) */
+  const float* bias;    /* attention_b [A]                    (normed Bahdanau) */
+  /* saved by fwd for bwd (and exposed as parity probes) */
+  float* align;         /* [T,B,Tm] alignments                 */
+  float* hc;            /* [T,B,H+Dm] = [cell output | context] */
+  float* pq;            /* [T,B,A] processed query             (Bahdanau family) */
+  /* backward outputs (accumulated: caller zeroes them) */
+  float* dkeys;         /* [Tm,B,A]  */
+  float* dvalues;       /* [Tm,B,Dm] gradient through the context only */
+  float* dWl;           /* [(H+Dm),A] */
+  float* dWq;           /* [H,A] */
+  float* dv;            /* [A] wrt the effective v */
+  float* dg;            /* [1] */
+  float* dbias;         /* [A] */
+  float* dpq;           /* [T,B,A] scratch */
+} AvsrAttnMech;
+
+typedef struct AvsrRnnSeq {
+  int T, B, H, n_mech, output_attention;
+  const int* len;       /* [B] */
+  float* gates;         /* [T,B,4H] in: x_t @ Wx + bias; out: activations i,j,f,o */
+  const float* Wrec;    /* [(At+H),4H] rows of the cell kernel under the x rows: [attention ; h] */
+  const float* c0;      /* [B,H] initial cell state or NULL (zeros) */
+  float* S;             /* [(T+1),B,At+H] state rows [attention | h]; caller initialises S[0] */
+  float* craw;          /* [T,B,H] pre-clip cell values */
+  float* out;           /* [T,B,O], O = At if output_attention else H; zero past len */
+  float* cT;            /* [B,H] final (clipped) cell state, or NULL */
+  float* hT;            /* [B,H] final h, or NULL */
+  AvsrAttnMech mech[2];
+  /* backward */
+  const float* dout;    /* [T,B,O] */
+  const float* dcT;     /* [B,H] or NULL */
+  const float* dhT;     /* [B,H] or NULL */
+  float* dZ;            /* [T,B,4H] gradient wrt the gate pre-activations (overwritten) */
+  float* dA;            /* [T,B,At] scratch (gradient wrt attention vectors) */
+  float* dWrec;         /* [(At+H),4H] accumulated */
+  float* dc0;           /* [B,H] or NULL */
+  float* dh0;           /* [B,H] or NULL */
+  float* work;          /* scratch, >= avsr_rnn_work_floats() floats */
+} AvsrRnnSeq;
+
+/* At = sum of mechanism A; maxHD = max(H+Dm); maxA = max A (0,0,0 without attention) */
+size_t avsr_rnn_work_floats(int B, int H, int At, int maxHD, int maxA);
+int avsr_rnn_seq_fwd(avsr_stream_t stream, const AvsrRnnSeq* r);
+int avsr_rnn_seq_bwd(avsr_stream_t stream, const AvsrRnnSeq* r);
+
+/* effective v of normed Bahdanau and its backward (attention.py:34-42) */
+int avsr_normed_v_fwd(avsr_stream_t stream, const float* v, const float* g, int A, float* veff);
+int avsr_normed_v_bwd(avsr_stream_t stream, const float* v, const float* g, const float* dveff, int A, float* dv,
+                      float* dg);
+
+/* ---- embedding lookup and its gradient (decoder_unimodal.py:170) ------------- */
+int avsr_embedding_fwd(avsr_stream_t stream, const float* table, int V, int E, const int* ids, long long n,
+                       float* out);
+int avsr_embedding_bwd(avsr_stream_t stream, const float* dout, const int* ids, long long n, int V, int E,
+                       float* dtable);
+
+/* ---- seq2seq.sequence_loss with sequence_mask weights (seq2seq.py:142-171) ---
+ * logits [T,B,V] (rows past labels_len are treated as zero logits, impute_finished);
+ * labels [B,ldl] EOS-terminated.  loss_sum[0] += sum xent*w; dlogits = (softmax-onehot)*w*inv_denom */
+int avsr_seq_loss(avsr_stream_t stream, const float* logits, int T, int B, int V, const int* labels, int ldl,
+                  const int* labels_len, float inv_denom, float* loss_sum, float* dlogits);
+
+/* ---- optimiser (seq2seq.py:175-178, 195-257) --------------------------------- */
+/* out[0] += sum x^2 */
+int avsr_sumsq(avsr_stream_t stream, const float* x, long long n, float* out);
+/* y += a*x */
+int avsr_axpy(avsr_stream_t stream, float a, const float* x, float* y, long long n);
+/* clip_by_global_norm + TF-Adam in one pass over the flat buffers; sumsq_dev[0] is the
+ * squared global norm (device scalar); lr_t already contains the bias correction. */
+int avsr_adam_clip_step(avsr_stream_t stream, float* params, const float* grads, float* m, float* v, long long n,
+                        const float* sumsq_dev, float clip_norm, float lr_t, float beta1, float beta2,
+                        float eps);
+
+/* ---- inference helpers (decoder_unimodal.py:176-271) -------------------------- */
+/* greedy: ids[b] = argmax_v logits[b,:] (lowest index on ties) unless finished[b]; updates finished */
+int avsr_greedy_pick(avsr_stream_t stream, const float* logits, int B, int V, int eos, int* finished,
+                     int* sample_out /*[B] 0 if already finished*/, int* next_ids);
+/* one BeamSearchDecoder step: log_softmax, finished masking, length penalty, top-k */
+int avsr_beam_step(avsr_stream_t stream, const float* logits /*[B*W,V]*/, int B, int W, int V, int eos,
+                   float length_penalty, float* log_probs /*[B,W] in/out*/, int* finished /*[B,W] in/out*/,
+                   int* lengths /*[B,W] in/out*/, int* word_out, int* parent_out, float* score_out);
+/* dst[i,:] = src[idx[i],:] for rows of width F */
+int avsr_gather_rows(avsr_stream_t stream, const float* src, const int* idx, long long n, int F, float* dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVSR_B200_H_ */

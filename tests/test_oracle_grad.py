@@ -1,0 +1,63 @@
+"""Validates the oracle's analytic backward with central finite differences in fp64
+(the restatement must be validated by independent means)."""
+import numpy as np
+import pytest
+
+from avsr_tf1_b200.seq2seq import Seq2SeqModel
+from oracle.avsr_oracle import OracleModel
+from tests.helpers import cast_batch, config_hparams, oracle_hparams, synthetic_batch, to_data_sequences
+
+CASES = [
+    (1, {}),
+    (1, dict(attention_type=(('luong',), ('luong',)))),
+    (1, dict(attention_type=(('bahdanau',), ('normed_bahdanau',)))),
+    (2, {}),
+    (3, {}),
+    (4, {}),
+    (4, dict(attention_type=(('bahdanau',), ('bahdanau',)))),
+    (5, {}),
+    (5, dict(attention_type=(('bahdanau',), ('scaled_luong',)))),
+    (5, dict(batch_normalisation=False)),
+]
+
+
+def tiny_model(cfg, over, seed=7):
+    hp = config_hparams(cfg, units=6, embedding_size=5, **over)
+    batch = synthetic_batch(hp, B=3, Ta=7, Tv=5, Fa=4, Fv=3, L=4, ragged=True, seed=seed)
+    model = Seq2SeqModel(to_data_sequences(batch), 'train', hp, seed=11, device='cpu')
+    P = {k: v.astype(np.float64) for k, v in model.store.to_numpy('p').items()}
+    rng = np.random.default_rng(5)
+    for k in P:  # break symmetric / zero initial values so every path carries gradient
+        if k.endswith(('bias', 'beta', 'attention_b')):
+            P[k] = P[k] + 0.1 * rng.standard_normal(P[k].shape)
+        elif k.endswith('kernel') or k.endswith('attention_v') or k.endswith('embedding_matrix'):
+            P[k] = P[k] * 3.0
+    return hp, cast_batch(batch, np.float64), P, model
+
+
+@pytest.mark.parametrize('cfg,over', CASES)
+def test_backward_matches_finite_differences(cfg, over):
+    hp, batch, P, model = tiny_model(cfg, over)
+    om = OracleModel(oracle_hparams(hp), P)
+    loss, G, _ = om.loss_and_grads(batch)
+    assert np.isfinite(loss)
+    trainable = set(model.store.names())
+    assert set(G) == trainable
+    rng = np.random.default_rng(3)
+    eps = 1e-6
+    worst = 0.0
+    for name in sorted(trainable):
+        flat = P[name].reshape(-1)
+        for idx in rng.choice(flat.size, size=min(4, flat.size), replace=False):
+            old = flat[idx]
+            flat[idx] = old + eps
+            lp, _ = om.forward_train(batch)
+            flat[idx] = old - eps
+            lm, _ = om.forward_train(batch)
+            flat[idx] = old
+            fd = (lp - lm) / (2 * eps)
+            an = G[name].reshape(-1)[idx]
+            err = abs(fd - an) / max(1e-6, abs(fd) + abs(an))
+            worst = max(worst, err if max(abs(fd), abs(an)) > 1e-9 else 0.0)
+            assert abs(fd - an) <= 1e-6 + 2e-5 * max(abs(fd), abs(an)), (name, idx, fd, an)
+    assert worst < 1e-3
