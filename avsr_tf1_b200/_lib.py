@@ -64,10 +64,10 @@ PROTOTYPES = {
     'avsr_normed_v_bwd': (_I, [_P, _P, _P, _P, _I, _P, _P]),
     'avsr_embedding_fwd': (_I, [_P, _P, _I, _I, _P, _L, _P]),
     'avsr_embedding_bwd': (_I, [_P, _P, _P, _L, _I, _I, _P]),
-    'avsr_seq_loss': (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _F, _P, _P]),
+    'avsr_seq_loss': (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P]),
     'avsr_sumsq': (_I, [_P, _P, _L, _P]),
     'avsr_axpy': (_I, [_P, _F, _P, _P, _L]),
-    'avsr_adam_clip_step': (_I, [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F]),
+    'avsr_adam_clip_step': (_I, [_P, _P, _P, _P, _P, _L, _P, _F, _P, _F, _F, _F]),
     'avsr_greedy_pick': (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     'avsr_beam_step': (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     'avsr_gather_rows': (_I, [_P, _P, _P, _L, _I, _P]),

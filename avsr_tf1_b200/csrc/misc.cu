@@ -155,8 +155,9 @@ __global__ void embedding_bwd_kernel(const float* __restrict__ dout, const int* 
 
 // one warp per (t,b) row
 __global__ void seq_loss_kernel(const float* __restrict__ logits, int T, int B, int V, const int* __restrict__ labels,
-                                int ldl, const int* __restrict__ labels_len, float inv_denom,
+                                int ldl, const int* __restrict__ labels_len, const float* __restrict__ inv_denom_dev,
                                 float* __restrict__ loss_sum, float* __restrict__ dlogits) {
+  const float inv_denom = inv_denom_dev[0];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= T * B) return;
   const int t = warp / B, b = warp - t * B;
@@ -197,7 +198,8 @@ __global__ void axpy_kernel(float a, const float* __restrict__ x, float* __restr
 
 __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, long long n, const float* __restrict__ sumsq, float clip,
-                                 float lr_t, float b1, float b2, float eps) {
+                                 const float* __restrict__ lr_t_dev, float b1, float b2, float eps) {
+  const float lr_t = lr_t_dev[0];
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float scale = 1.0f;
@@ -445,7 +447,7 @@ int avsr_embedding_bwd(avsr_stream_t s, const float* dout, const int* ids, long 
 }
 
 int avsr_seq_loss(avsr_stream_t s, const float* logits, int T, int B, int V, const int* labels, int ldl,
-                  const int* labels_len, float inv_denom, float* loss_sum, float* dlogits) {
+                  const int* labels_len, const float* inv_denom, float* loss_sum, float* dlogits) {
   if (T * B <= 0) return 0;
   AVSR_LAUNCH(seq_loss_kernel, cdiv((long long)T * B * 32, 256), 256, 0, ST(s), logits, T, B, V, labels, ldl,
               labels_len, inv_denom, loss_sum, dlogits);
@@ -466,7 +468,7 @@ int avsr_axpy(avsr_stream_t s, float a, const float* x, float* y, long long n) {
 }
 
 int avsr_adam_clip_step(avsr_stream_t s, float* params, const float* grads, float* m, float* v, long long n,
-                        const float* sumsq_dev, float clip_norm, float lr_t, float beta1, float beta2, float eps) {
+                        const float* sumsq_dev, float clip_norm, const float* lr_t, float beta1, float beta2, float eps) {
   if (n <= 0) return 0;
   AVSR_LAUNCH(adam_clip_kernel, cdiv(n, 256), 256, 0, ST(s), params, grads, m, v, n, sumsq_dev, clip_norm, lr_t,
               beta1, beta2, eps);

@@ -118,10 +118,19 @@ def embedding_bwd(dout2d, ids, dtable):
                                          dtable.shape[1], dtable.data_ptr()))
 
 
+def _dev_scalar(x):
+    """float -> 1-element device tensor (tests / eager use); tensors pass through."""
+    if torch.is_tensor(x):
+        return x
+    return torch.tensor([float(x)], dtype=torch.float32, device='cuda')
+
+
 def seq_loss(logits, labels, labels_len, inv_denom, loss_sum, dlogits):
+    """inv_denom: device scalar tensor (or a float, copied to the device)."""
     T, B, V = logits.shape
+    inv = _dev_scalar(inv_denom)
     check(_lib.load().avsr_seq_loss(_stream(), logits.data_ptr(), T, B, V, labels.data_ptr(), labels.stride(0),
-                                    labels_len.data_ptr(), float(inv_denom), loss_sum.data_ptr(), dlogits.data_ptr()))
+                                    labels_len.data_ptr(), inv.data_ptr(), loss_sum.data_ptr(), dlogits.data_ptr()))
 
 
 def sumsq(x, out):
@@ -133,8 +142,10 @@ def axpy(a, x, y):
 
 
 def adam_clip_step(params, grads, m, v, sumsq_dev, clip_norm, lr_t, beta1=0.9, beta2=0.999, eps=1e-8):
+    """lr_t: device scalar tensor (or a float, copied to the device)."""
+    lr = _dev_scalar(lr_t)
     check(_lib.load().avsr_adam_clip_step(_stream(), params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                          params.numel(), sumsq_dev.data_ptr(), float(clip_norm), float(lr_t),
+                                          params.numel(), sumsq_dev.data_ptr(), float(clip_norm), lr.data_ptr(),
                                           beta1, beta2, eps))
 
 

@@ -26,17 +26,6 @@ from .layers import BuildContext
 from .params import ParamStore
 
 
-def _to_device(a, dtype):
-    if a is None:
-        return None
-    if isinstance(a, np.ndarray):
-        a = torch.from_numpy(np.ascontiguousarray(a))
-    if not a.is_cuda:
-        a = a.pin_memory() if not a.is_pinned() else a
-        a = a.to('cuda', non_blocking=True)
-    return a.to(dtype).contiguous()
-
-
 class Saver(object):
     """tf.train.Saver stand-in (seq2seq.py:132-133): all global variables incl. Adam slots,
     BN moving statistics and global_step, keyed by TF variable name, in one .npz file."""
@@ -103,6 +92,13 @@ class Seq2SeqModel(object):
             self._init_optimiser()
         self._init_saver()
         self._batch = None
+        self._in_sets, self._in, self._meta = {}, None, None
+        self._graphs = {}
+        self.use_cuda_graph = False  # opt-in: train_step replays one captured graph per batch shape
+        self.launches_last_step = 0
+        self.h2d_bytes = 0
+        if self.store.flat.is_cuda:
+            self._scal_dev = torch.zeros(2, dtype=torch.float32, device='cuda')
 
     # ---- construction (seq2seq.py:30-126) ---------------------------------------
     def _make_encoders(self):
@@ -184,31 +180,65 @@ class Seq2SeqModel(object):
         return self.store.n_trainable
 
     # ---- batches -------------------------------------------------------------------
+    def _as_tensor(self, a, dtype):
+        if isinstance(a, np.ndarray):
+            a = torch.from_numpy(np.ascontiguousarray(a))
+        return a if a.dtype == dtype else a.to(dtype)
+
     def feed(self, data_sequences):
-        """Move one batch (batch-major, host or device) into frame-major device tensors."""
+        """Copy one batch (batch-major like the reference; numpy / pinned host / device tensors) into
+        static device buffers.  The layout change to frame-major happens on the device (_prep)."""
         video, audio = data_sequences
-        b: Dict[str, object] = {}
         ref = audio if audio is not None else video
+        src = {}
         for key, d in (('video', video), ('audio', audio)):
             if d is None:
                 continue
-            x = _to_device(d.inputs, torch.float32)
+            x = self._as_tensor(d.inputs, torch.float32)
             if x.dim() > 3:  # raw lip crops [B,T,h,w,c] fed as flat features (video_processing='features')
                 x = x.reshape(x.shape[0], x.shape[1], -1)
-            b[key] = ops.transpose01(x)
-            b[key + '_len'] = _to_device(d.inputs_length, torch.int32)
+            src[key] = x
+            src[key + '_len'] = self._as_tensor(d.inputs_length, torch.int32)
+        meta = {}
         if ref.labels is not None:
-            lab_len_host = ref.labels_length.cpu().numpy() if torch.is_tensor(ref.labels_length) \
-                else np.asarray(ref.labels_length)
-            T = int(lab_len_host.max())
-            labels = _to_device(ref.labels, torch.int32)
-            B = labels.shape[0]
-            go = torch.full((B, 1), self._decoder._GO_ID, dtype=torch.int32, device='cuda')
+            ll = ref.labels_length
+            lab_len_host = ll.cpu().numpy() if torch.is_tensor(ll) else np.asarray(ll)
+            meta['T_dec'] = int(lab_len_host.max())
+            meta['n_tokens'] = float(lab_len_host.sum())
+            src['labels'] = self._as_tensor(ref.labels, torch.int32)
+            src['labels_len'] = self._as_tensor(ll, torch.int32)
+        key = tuple((k, tuple(v.shape)) for k, v in sorted(src.items())) + (meta.get('T_dec', 0),)
+        bufs = self._in_sets.get(key)
+        if bufs is None:
+            bufs = {k: torch.empty(v.shape, dtype=v.dtype, device='cuda') for k, v in src.items()}
+            self._in_sets[key] = bufs
+        nbytes = 0
+        for k, v in src.items():
+            bufs[k].copy_(v, non_blocking=True)
+            if not v.is_cuda:
+                nbytes += v.numel() * v.element_size()
+        self.h2d_bytes = nbytes
+        meta['key'] = key
+        self._in, self._meta = bufs, meta
+        self._batch = None
+        return meta
+
+    def _prep(self):
+        """Device-side batch preparation (capturable): batch-major -> frame-major, GO-prefixed ids."""
+        src, meta = self._in, self._meta
+        b: Dict[str, object] = {}
+        for key in ('video', 'audio'):
+            if key in src:
+                b[key] = ops.transpose01(src[key])
+                b[key + '_len'] = src[key + '_len']
+        if 'labels' in src:
+            T = meta['T_dec']
+            labels = src['labels']
+            go = torch.full((labels.shape[0], 1), self._decoder._GO_ID, dtype=torch.int32, device='cuda')
             b['labels'] = labels
-            b['labels_len'] = _to_device(ref.labels_length, torch.int32)
+            b['labels_len'] = src['labels_len']
             b['dec_in_ids'] = torch.cat([go, labels], dim=1)[:, :T].t().contiguous()  # decoder_unimodal.py:61-68
             b['T_dec'] = T
-            b['n_tokens'] = float(lab_len_host.sum())
         self._batch = b
         return b
 
@@ -238,26 +268,20 @@ class Seq2SeqModel(object):
 
     def encode(self, data_sequences=None):
         """Parity probe: encoder outputs / final states (frame-major device tensors)."""
-        b = self.feed(data_sequences) if data_sequences is not None else self._batch
-        return self._encode(b)
+        if data_sequences is not None:
+            self.feed(data_sequences)
+        return self._encode(self._prep())
 
     def forward_backward(self):
-        """Forward + backward on the fed batch.  Leaves local gradient sums in store.grad and
-        the cross-entropy SUM (un-normalised over DP ranks handled via inv_denom) in _loss_dev[0]."""
-        b, ctx = self._batch, self._ctx
+        """Forward + backward on the prepared batch.  Leaves the local gradient sums in store.grad and
+        the cross-entropy SUM in _loss_dev[0] (normalised by the device scalar inv_denom)."""
+        b = self._batch if self._batch is not None else self._prep()
         self.store.grad.zero_()
         self._loss_dev.zero_()
-        n_tok = b['n_tokens']
-        if ctx.world_size > 1:  # exact large-batch loss denominator under data parallelism
-            t = torch.tensor([n_tok], dtype=torch.float64, device='cuda')
-            ctx.allreduce(t)
-            n_tok = float(t.item())
-        inv_denom = 1.0 / (n_tok + 1e-12)  # seq2seq.sequence_loss
         enc = self._encode(b)
         mems, states = self._decoder_inputs(b, enc)
         self._decoder.forward_train(mems, states, b['dec_in_ids'], b['labels'], b['labels_len'], b['T_dec'],
-                                    inv_denom, self._loss_dev[0:1])
-        self._inv_denom = inv_denom
+                                    self._scal_dev[0:1], self._loss_dev[0:1])
         dmem, dstates = self._decoder.backward_train()
         if self._hparams.architecture == 'bimodal':
             self._audio_encoder.backward(dmem[1], dstates[1])
@@ -268,8 +292,6 @@ class Seq2SeqModel(object):
                 self._video_encoder.backward(dvid, None)
             else:
                 self._audio_encoder.backward(dmem[0], dstates[0])
-                if self._video_encoder is not None:  # unimodal with both streams: video is unused by the loss
-                    pass
         else:
             self._video_encoder.backward(dmem[0], dstates[0])
 
@@ -281,8 +303,9 @@ class Seq2SeqModel(object):
             lr *= min(1.0, (self._global_step + 1) / float(steps))  # seq2seq.py:275-280
         return lr
 
-    def apply_gradients(self):
-        """all-reduce (DP) -> + L2 -> global norm -> clip + TF-Adam (seq2seq.py:175-178, 195-257)."""
+    def finish_gradients(self):
+        """all-reduce (DP) -> + L2 on the LSTM kernels -> squared global norm
+        (seq2seq.py:175-178, 222, 246).  After this store.grad holds d(batch_loss)/d(theta)."""
         hp, ctx, st = self._hparams, self._ctx, self.store
         if ctx.world_size > 1:
             ctx.allreduce(st.grad)
@@ -292,13 +315,53 @@ class Seq2SeqModel(object):
                 ops.axpy(hp.recurrent_l2_regularisation, st.p(n), st.g(n))
                 ops.sumsq(st.p(n), self._loss_dev[1:2])
         ops.sumsq(st.grad, self._loss_dev[2:3])
+
+    def apply_gradients(self):
+        """clip_by_global_norm + TF-Adam (seq2seq.py:195-199, 245-257); lr_t is the device scalar
+        _scal_dev[1] written by _set_step_scalars (warm-up + bias correction, seq2seq.py:275-280)."""
+        hp, st = self._hparams, self.store
+        clip = hp.max_gradient_norm if hp.clip_gradients is True else 0.0
+        ops.adam_clip_step(st.flat, st.grad, st.m, st.v, self._loss_dev[2:3], clip, self._scal_dev[1:2], 0.9, 0.999,
+                           1e-8)
+
+    def _set_step_scalars(self):
+        """Host scalars of this step -> device (outside any captured graph)."""
+        ctx = self._ctx
+        n_tok = self._meta['n_tokens']
+        if ctx.world_size > 1:  # exact large-batch loss denominator under data parallelism
+            t = torch.tensor([n_tok], dtype=torch.float64, device='cuda')
+            ctx.allreduce(t)
+            n_tok = float(t.item())
+        self._inv_denom = 1.0 / (n_tok + 1e-12)  # seq2seq.sequence_loss
         lr = self._lr_now()
         self.current_lr = lr
         t = self._global_step + 1
-        lr_t = lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
-        clip = hp.max_gradient_norm if hp.clip_gradients is True else 0.0
-        ops.adam_clip_step(st.flat, st.grad, st.m, st.v, self._loss_dev[2:3], clip, lr_t, 0.9, 0.999, 1e-8)
-        self._global_step += 1
+        # pageable source: the driver stages it at call time, so the host may run ahead of the GPU safely
+        self._scal_dev.copy_(torch.tensor([self._inv_denom, lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)],
+                                          dtype=torch.float32))
+
+    def _step_body(self):
+        self._prep()
+        self.forward_backward()
+        self.finish_gradients()
+        self.apply_gradients()
+
+    def _capture(self, key):
+        """Capture one whole training step (thousands of launches) into a CUDA graph.  A throw-away eager
+        step warms every kernel first; parameters, Adam slots and BN statistics are restored after it."""
+        st = self.store
+        snap = [t.clone() for t in (st.flat, st.m, st.v)] + [v.clone() for v in st.state.values()]
+        n0 = ops.launch_count()
+        self._step_body()
+        torch.cuda.synchronize()
+        for dst, src in zip([st.flat, st.m, st.v] + list(st.state.values()), snap):
+            dst.copy_(src)
+        n1 = ops.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._step_body()
+        self._graphs[key] = (g, n1 - n0)
+        return self._graphs[key]
 
     def fetch_scalars(self):
         """Device -> host read of the step's results (what session.run returns, avsr.py:265-271)."""
@@ -315,8 +378,17 @@ class Seq2SeqModel(object):
             raise Exception('train_step needs mode == `train`')
         if data_sequences is not None:
             self.feed(data_sequences)
-        self.forward_backward()
-        self.apply_gradients()
+        self._set_step_scalars()
+        if self.use_cuda_graph:
+            key = self._meta['key']
+            g, n = self._graphs.get(key) or self._capture(key)
+            g.replay()
+            self.launches_last_step = n
+        else:
+            n0 = ops.launch_count()
+            self._step_body()
+            self.launches_last_step = ops.launch_count() - n0
+        self._global_step += 1
         if fetch:
             return self.fetch_scalars()
         return None
@@ -327,7 +399,9 @@ class Seq2SeqModel(object):
     # ---- inference -------------------------------------------------------------------------
     def predict(self, data_sequences=None):
         """Runs the decoding algorithm of hparams (avsr.py:345): int32 ids [B, <=150]."""
-        b = self.feed(data_sequences) if data_sequences is not None else self._batch
+        if data_sequences is not None:
+            self.feed(data_sequences)
+        b = self._prep()
         enc = self._encode(b)
         mems, states = self._decoder_inputs(b, enc)
         if self._hparams.decoding_algorithm == 'greedy':

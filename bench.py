@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark: AV-Align training throughput (utterances/s).
+
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on): AV-Align
+cross-modal fusion, 3x256 uni-LSTM video and audio encoders, 1x256 attention decoder,
+per-GPU batch 256, T_audio = 300 mel-80 frames, T_video = 75 lip crops of 36x36x3 (fed as
+flat 3888-d `features`, the only video entry the six hot-path files define; the ResNet
+front-end is SURVEY.md row f-3), 40-char targets + EOS.  One step = forward + backward +
+global-norm clip + Adam on one batch.
+
+  python bench.py --gpus N --steps K --warmup W          # our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference ...                   # the CPU restatement of the TF1 graph (oracle)
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = 'AV-Align train utterances/sec'
+UNIT = 'utterances/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='per-GPU batch (weak scaling)')
+    ap.add_argument('--video-input', default='crops3888', choices=['crops3888', 'features128'])
+    ap.add_argument('--attention', default='bahdanau', choices=['bahdanau', 'scaled_luong'])
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of one CUDA graph per step')
+    ap.add_argument('--no-tensor-cores', action='store_true')
+    ap.add_argument('--cpu-sample', type=int, default=8, help='utterances per CPU-baseline step')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def workload(args, B, seed):
+    from tests.helpers import config_hparams, synthetic_batch
+    hp = config_hparams(5, attention_type=((args.attention,), (args.attention,)))
+    Fv = 3888 if args.video_input == 'crops3888' else 128
+    batch = synthetic_batch(hp, B=B, Ta=300, Tv=75, Fa=80, Fv=Fv, L=40, ragged=False, seed=seed)
+    return hp, batch
+
+
+def config_dict(args, N):
+    return {
+        'workload': 'AV-Align (BASELINE.json configs[4]): 3x256 uni-LSTM video+audio encoders, cross-modal '
+                    f'{args.attention} attention in the top audio layer, 1x256 {args.attention} attention decoder',
+        'per_gpu_batch': args.batch, 'global_batch': args.batch * N, 'T_audio': 300, 'audio_features': 80,
+        'T_video': 75, 'video_features': 3888 if args.video_input == 'crops3888' else 128,
+        'video_input': '36x36x3 lip crops as flat features' if args.video_input == 'crops3888'
+        else '128-d visual features', 'label_len': 41, 'parallelism': f'dp{N}',
+        'dropout': 'off', 'scheduled_sampling': 'off (parity switches of SURVEY.md 8d; TF Philox streams are '
+                                                'not reproducible)',
+        'l2_flush': 'not needed: every step streams > 2 GB of activations through a 126 MB L2',
+    }
+
+
+# ------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (CPU restatement of the TF1 graph) on host cores
+# ------------------------------------------------------------------------------------
+def run_oracle(args, steps, warmup, sample):
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    from oracle import avsr_oracle as O
+    from tests.helpers import oracle_hparams, to_data_sequences
+    hp, batch = workload(args, sample, seed=0)
+    model = Seq2SeqModel(to_data_sequences(batch), 'train', hp, seed=2001, device='cpu')
+    P = model.store.to_numpy('p')
+    names = model.store.names()
+    om = O.OracleModel(oracle_hparams(hp), P)
+    m = {k: np.zeros_like(P[k]) for k in names}
+    v = {k: np.zeros_like(P[k]) for k in names}
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, G, _ = om.loss_and_grads(batch)
+        Pt = {k: P[k] for k in names}
+        O.clip_and_adam(Pt, G, m, v, s, hp.learning_rate, clip=hp.max_gradient_norm)
+        P.update(Pt)
+        times.append(time.perf_counter() - t0)
+    t = float(np.mean(times[warmup:]))
+    try:
+        import threadpoolctl
+        threads = max([p['num_threads'] for p in threadpoolctl.threadpool_info()] + [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    return dict(value=sample / t, sec_per_step=t, cores=int(threads), sample=sample, loss=float(loss))
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 12))
+    warmup = max(1, min(args.warmup, 2))
+    r = run_oracle(args, steps, warmup, args.cpu_sample)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warmup, 'ms_per_step': r['sec_per_step'] * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': config_dict(args, args.gpus),
+        'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                         'sample': f'{r["sample"]} utterances per step of the same workload (full sequence '
+                                   f'lengths), {steps} steps; NumPy/OpenBLAS restatement of the TF1 graph '
+                                   '(TensorFlow 1.13 cannot be installed here)'},
+        'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5)
+                for ln in out.stdout.strip().splitlines():
+                    self.rows.append([x.strip() for x in ln.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'),
+                                     r[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------
+# roofline of the dominant kernel class: the LSTM gate GEMMs (tensor-pipe bound)
+# ------------------------------------------------------------------------------------
+def gate_gemm_roofline(args, torch, ops):
+    """Times the big LSTM gate products of this workload in isolation with CUDA events on the launch
+    stream (distinct operand buffers per launch, > L2 in total).  FLOP = 2*M*N*K per product."""
+    B = args.batch
+    Fv = 3888 if args.video_input == 'crops3888' else 128
+    H = 256
+    shapes = []  # (ta, tb, M, N, K) forward x@Wx, dgrad dZ@Wx^T, wgrad x^T@dZ for every encoder layer
+    for T, I in ((75, Fv), (75, H), (75, H), (300, 80), (300, H), (300, H)):
+        M = T * B
+        shapes += [(0, 0, M, 4 * H, I), (0, 1, M, I, 4 * H), (1, 0, I, 4 * H, M)]
+    flops, ms = 0.0, 0.0
+    per = []
+    for ta, tb, M, N, K in shapes:
+        a = torch.randn((K, M) if ta else (M, K), device='cuda')
+        b = torch.randn((N, K) if tb else (K, N), device='cuda')
+        c = torch.empty(M, N, device='cuda')
+        for _ in range(2):
+            ops.gemm(a, b, c, ta=bool(ta), tb=bool(tb))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            ops.gemm(a, b, c, ta=bool(ta), tb=bool(tb))
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / reps
+        f = 2.0 * M * N * K
+        flops += f
+        ms += t
+        per.append({'shape': [int(ta), int(tb), M, N, K], 'ms': round(t, 4), 'tflops': round(f / t / 1e9, 2)})
+        del a, b, c
+    # TF32 cuBLAS peak, measured the way MEASURED_PEAKS.json measures bf16 (denominator only, not on the path)
+    n = 8192
+    x, y = torch.randn(n, n, device='cuda'), torch.randn(n, n, device='cuda')
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    best = 1e9
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    torch.backends.cuda.matmul.allow_tf32 = old
+    tf32_peak = 2.0 * n ** 3 / best / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    achieved = flops / ms / 1e9
+    return {'bound': 'tensor', 'achieved': round(achieved, 2), 'peak': round(tf32_peak, 1), 'unit': 'TFLOP/s',
+            'frac': round(achieved / tf32_peak, 4), 'traffic': None,
+            'kernel': 'LSTM gate GEMMs (x@Wx, dZ@Wx^T, x^T@dZ of the six encoder layers), timed in isolation',
+            'peak_source': 'TF32 torch.matmul 8192^3 measured in this run (operands are fp32/TF32, BASELINE.md '
+                           'section 2); bf16 peak of MEASURED_PEAKS.json = %s' % peaks.get('bf16_tflops'),
+            'gate_gemm_ms_per_step': round(ms, 3), 'per_shape': per}
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from avsr_tf1_b200 import ops
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    from tests.helpers import to_data_sequences
+
+    ops.set_tensor_cores(not args.no_tensor_cores)
+    hp, batch = workload(args, args.batch, seed=rank)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in batch.items()}
+    ds_host = to_data_sequences(pinned)
+    model = Seq2SeqModel(ds_host, 'train', hp, seed=2001)
+    model.use_cuda_graph = not args.no_graph
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing: inputs already in HBM ------------------------------------
+    model.feed(ds_host)
+    for _ in range(max(3, args.warmup)):
+        model.train_step(fetch=False)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        model.train_step(fetch=False)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = model.launches_last_step
+    loss, gnorm = model.fetch_scalars()
+
+    # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ---------------
+    for _ in range(2):
+        model.train_step(ds_host, fetch=True)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e2.record()
+    for _ in range(args.steps):
+        loss, gnorm = model.train_step(ds_host, fetch=True)
+    e3.record()
+    barrier()
+    e2e_wall = (time.perf_counter() - t_wall) * 1e3
+    e2e_ms = max_over_ranks(max(e2.elapsed_time(e3), 0.0))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    h2d = model.h2d_bytes
+    d2h = int(model._loss_dev.numel() * 4)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    value = args.batch * world / (ms_step / 1e3)
+    e2e_step = e2e_ms / args.steps
+    line = {
+        'metric': METRIC, 'value': round(value, 2), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(3, args.warmup), 'ms_per_step': round(ms_step, 4), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32' if args.no_tensor_cores else 'f32 storage/accumulate, tf32 tensor-core products',
+        'data': 'synthetic', 'config': config_dict(args, world),
+        'clocks': sampler.summary(),
+        'e2e': {'value': round(args.batch * world / (e2e_step / 1e3), 2), 'unit': UNIT, 'ms_per_step': round(e2e_step, 4),
+                'wall_ms_per_step': round(e2e_wall / args.steps, 4), 'h2d_bytes_per_step': int(h2d),
+                'd2h_bytes_per_step': d2h},
+        'gpu_launches': int(launches * args.steps),
+        'gpu_launches_per_step': int(launches),
+        'cuda_graph': bool(model.use_cuda_graph),
+        'loss': round(float(loss), 6), 'global_norm': round(float(gnorm), 6), 'n_params': int(model.n_params),
+    }
+    try:
+        line['roofline'] = gate_gemm_roofline(args, torch, ops)
+    except Exception as ex:  # keep the headline number even if the side measurement fails
+        line['roofline'] = {'error': repr(ex)}
+    if world == 1 and not args.skip_cpu_baseline:
+        r = run_oracle(args, steps=2, warmup=1, sample=args.cpu_sample)
+        line['cpu_baseline'] = {
+            'value': round(r['value'], 3), 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+            'sample': f'{r["sample"]} utterances per step of the same workload at full sequence lengths, 2 timed '
+                      'steps; NumPy/OpenBLAS restatement of the TF1 graph (oracle/)'}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

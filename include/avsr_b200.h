@@ -145,9 +145,10 @@ int avsr_embedding_bwd(avsr_stream_t stream, const float* dout, const int* ids, 
 
 /* ---- seq2seq.sequence_loss with sequence_mask weights (seq2seq.py:142-171) ---
  * logits [T,B,V] (rows past labels_len are treated as zero logits, impute_finished);
- * labels [B,ldl] EOS-terminated.  loss_sum[0] += sum xent*w; dlogits = (softmax-onehot)*w*inv_denom */
+ * labels [B,ldl] EOS-terminated.  loss_sum[0] += sum xent*w; dlogits = (softmax-onehot)*w*inv_denom.
+ * inv_denom_dev / lr_t_dev are DEVICE scalars so a captured CUDA graph can be replayed with new values. */
 int avsr_seq_loss(avsr_stream_t stream, const float* logits, int T, int B, int V, const int* labels, int ldl,
-                  const int* labels_len, float inv_denom, float* loss_sum, float* dlogits);
+                  const int* labels_len, const float* inv_denom_dev, float* loss_sum, float* dlogits);
 
 /* ---- optimiser (seq2seq.py:175-178, 195-257) --------------------------------- */
 /* out[0] += sum x^2 */
@@ -157,7 +158,7 @@ int avsr_axpy(avsr_stream_t stream, float a, const float* x, float* y, long long
 /* clip_by_global_norm + TF-Adam in one pass over the flat buffers; sumsq_dev[0] is the
  * squared global norm (device scalar); lr_t already contains the bias correction. */
 int avsr_adam_clip_step(avsr_stream_t stream, float* params, const float* grads, float* m, float* v, long long n,
-                        const float* sumsq_dev, float clip_norm, float lr_t, float beta1, float beta2,
+                        const float* sumsq_dev, float clip_norm, const float* lr_t_dev, float beta1, float beta2,
                         float eps);
 
 /* ---- inference helpers (decoder_unimodal.py:176-271) -------------------------- */

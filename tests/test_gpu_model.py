@@ -1,0 +1,237 @@
+"""GPU parity of the whole path behind the Seq2SeqModel boundary against the oracle, for
+the five BASELINE.json configurations (true layer widths, shortened sequences so the fp64
+oracle finishes in seconds) plus one full-length case.  Tolerance 1e-3 scaled error on
+encoder states / attention contexts / loss (north_star), 5e-3 on gradients."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import avsr_oracle as O
+from tests.helpers import cast_batch, config_hparams, oracle_hparams, synthetic_batch, to_data_sequences
+
+pytestmark = pytest.mark.gpu
+
+
+def close(got, want, rtol, what=''):
+    got = got.detach().cpu().numpy().astype(np.float64) if torch.is_tensor(got) else np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = max(1e-30, np.abs(want).max())
+    assert np.isfinite(got).all(), what + ': non-finite'
+    err = np.abs(got - want).max() / scale
+    assert err <= rtol, f'{what}: max scaled error {err:.3e} > {rtol:.1e}'
+    return err
+
+
+@pytest.fixture(params=[False, True], ids=['fp32', 'tf32'])
+def tensor_cores(request):
+    from avsr_tf1_b200 import ops
+    old = ops.set_tensor_cores(request.param)
+    yield request.param
+    ops.set_tensor_cores(old)
+
+
+def build(cfg, over, B, Ta, Tv, L, ragged=True, Fv=128):
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    hp = config_hparams(cfg, **over)
+    batch = synthetic_batch(hp, B=B, Ta=Ta, Tv=Tv, Fa=80, Fv=Fv, L=L, ragged=ragged)
+    ds = to_data_sequences(batch)
+    model = Seq2SeqModel(ds, 'train', hp, seed=2001)
+    return hp, batch, ds, model
+
+
+def oracle_for(hp, model, dtype=np.float64):
+    P = {k: v.astype(dtype) for k, v in model.store.to_numpy('p').items()}
+    return O.OracleModel(oracle_hparams(hp), P), P
+
+
+CASES = [
+    (1, {}), (2, {}), (3, {}), (4, {}), (5, {}),
+    (1, dict(attention_type=(('bahdanau',), ('bahdanau',)))),
+    (4, dict(attention_type=(('bahdanau',), ('bahdanau',)))),
+    (5, dict(attention_type=(('bahdanau',), ('bahdanau',)))),
+    (5, dict(attention_type=(('luong',), ('normed_bahdanau',)), batch_normalisation=False)),
+]
+
+
+@pytest.mark.parametrize('cfg,over', CASES)
+def test_loss_states_contexts_and_gradients(cfg, over, tensor_cores):
+    hp, batch, ds, model = build(cfg, over, B=4, Ta=40, Tv=12, L=8)
+    om, P = oracle_for(hp, model)
+    loss_ref, G_ref, rec = om.loss_and_grads(cast_batch(batch, np.float64))
+    model.feed(ds)
+    model._set_step_scalars()
+    model.forward_backward()
+    model.finish_gradients()
+    loss, gnorm = model.fetch_scalars()
+    rt = 1e-3
+    assert abs(loss - loss_ref) <= rt * abs(loss_ref), (loss, loss_ref)
+    # parity probes named by north_star: encoder outputs / final states / attention contexts
+    for key, enc in (('video', model._video_encoder), ('audio', model._audio_encoder)):
+        if enc is None or key not in rec['enc']:
+            continue
+        out_ref, (c_ref, h_ref) = rec['enc'][key]
+        d = enc.get_data()
+        close(d.outputs.transpose(0, 1), out_ref, rt, key + ' encoder outputs')
+        close(d.final_state[0], c_ref, rt, key + ' final c')
+        close(d.final_state[1], h_ref, rt, key + ' final h')
+    mask = torch.from_numpy(rec['mask']).to('cuda').float()[:, :, None]
+    H = model._decoder._H
+    for k, mb in enumerate(model._decoder._cell.bufs):
+        close(mb.hc.transpose(0, 1)[:, :, H:] * mask, rec['dec']['contexts'][k], rt, 'decoder contexts')
+    if hp.architecture == 'av_align':
+        amask = (np.arange(batch['audio'].shape[1])[None, :] < batch['audio_len'][:, None]).astype(np.float32)
+        amask = torch.from_numpy(amask).to('cuda')[:, :, None]
+        Ha = model._audio_encoder._num_units_per_layer[-1]
+        close(model._audio_encoder.attention_contexts.transpose(0, 1)[:, :, Ha:] * amask,
+              rec['audio/xmodal']['contexts'][0], rt, 'cross-modal contexts')
+    G = model.store.to_numpy('g')
+    gn_ref = O.global_norm(G_ref)
+    assert abs(gnorm - gn_ref) <= 5e-3 * gn_ref, (gnorm, gn_ref)
+    gmax = max(np.abs(g).max() for g in G_ref.values())
+    for name, g_ref in G_ref.items():
+        scale = max(np.abs(g_ref).max(), 1e-3 * gmax)
+        err = np.abs(G[name].astype(np.float64) - g_ref).max() / scale
+        assert err <= 5e-3, f'{name}: gradient scaled error {err:.3e}'
+
+
+def test_full_length_av_align(tensor_cores):
+    """BASELINE sequence lengths (Ta=300, Tv=75, 41 label steps) on the headline architecture."""
+    hp, batch, ds, model = build(5, {}, B=3, Ta=300, Tv=75, L=40)
+    om, P = oracle_for(hp, model)
+    loss_ref, G_ref, rec = om.loss_and_grads(cast_batch(batch, np.float64))
+    model.feed(ds)
+    model._set_step_scalars()
+    model.forward_backward()
+    model.finish_gradients()
+    loss, gnorm = model.fetch_scalars()
+    assert abs(loss - loss_ref) <= 1e-3 * abs(loss_ref)
+    out_ref, (c_ref, h_ref) = rec['enc']['audio']
+    d = model._audio_encoder.get_data()
+    close(d.outputs.transpose(0, 1), out_ref, 1e-3, 'audio outputs T=300')
+    close(d.final_state[1], h_ref, 1e-3, 'audio final h')
+    assert abs(gnorm - O.global_norm(G_ref)) <= 5e-3 * O.global_norm(G_ref)
+
+
+@pytest.mark.parametrize('cfg', [1, 2, 4, 5])
+def test_three_training_steps(cfg):
+    """loss / global-norm / parameters after clip + TF-Adam + warm-up, three steps."""
+    hp, batch, ds, model = build(cfg, {}, B=4, Ta=30, Tv=10, L=6)
+    om, P = oracle_for(hp, model)
+    names = model.store.names()
+    m = {k: np.zeros_like(P[k]) for k in names}
+    v = {k: np.zeros_like(P[k]) for k in names}
+    b64 = cast_batch(batch, np.float64)
+    for step in range(3):
+        loss_ref, G_ref, _ = om.loss_and_grads(b64)
+        Pt = {k: P[k] for k in names}
+        gn_ref = O.clip_and_adam(Pt, G_ref, m, v, step, hp.learning_rate, clip=hp.max_gradient_norm, warmup_steps=750)
+        P.update(Pt)
+        loss, gn = model.train_step(ds)
+        assert abs(loss - loss_ref) <= 1e-3 * abs(loss_ref), (step, loss, loss_ref)
+        assert abs(gn - gn_ref) <= 5e-3 * gn_ref, (step, gn, gn_ref)
+    got = model.store.to_numpy('p')
+    # Adam's first steps are sign-like (m/sqrt(v)): a weight whose gradient is at rounding-noise level may
+    # legitimately move the other way, by at most 2*lr_eff per step.  So: hard bound on every weight,
+    # tight bound on all but a vanishing fraction.
+    lr_sum = sum(hp.learning_rate * (s + 1) / 750.0 for s in range(3))
+    for k in names:
+        diff = np.abs(got[k].astype(np.float64) - P[k])
+        assert diff.max() <= 2.2 * lr_sum + 1e-6 * np.abs(P[k]).max() + 1e-7, (k, diff.max())
+        assert (diff > 0.05 * lr_sum + 1e-6 * np.abs(P[k]).max()).mean() < 2e-3, k
+    assert model.global_step == 3
+
+
+@pytest.mark.parametrize('cfg', [2, 5])
+def test_cuda_graph_replay_matches_eager(cfg):
+    """train_step through one captured CUDA graph per batch shape == eager launches."""
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    hp = config_hparams(cfg)
+    batches = [synthetic_batch(hp, B=4, Ta=30, Tv=10, L=6, ragged=True, seed=s) for s in range(3)]
+    for b in batches:  # same padded shapes, different lengths/content
+        b['labels_len'][0] = 7
+    res = {}
+    for graph in (False, True):
+        m = Seq2SeqModel(to_data_sequences(batches[0]), 'train', hp, seed=2001)
+        m.use_cuda_graph = graph
+        res[graph] = [m.train_step(to_data_sequences(b)) for b in batches] + [m.store.to_numpy('p')]
+    for s in range(3):
+        assert abs(res[True][s][0] - res[False][s][0]) <= 1e-5 * abs(res[False][s][0])
+        assert abs(res[True][s][1] - res[False][s][1]) <= 1e-4 * abs(res[False][s][1])
+    lr_sum = sum(hp.learning_rate * (s + 1) / 750.0 for s in range(3))
+    for k, v in res[False][3].items():
+        assert np.abs(res[True][3][k] - v).max() <= 2.2 * lr_sum + 1e-7, k
+
+
+def test_padding_invariance_full_size():
+    """Size-independent property at BASELINE config 2 size (B=64, Ta=300): extra zero padding
+    must not change outputs inside the valid region nor the loss (dynamic_rnn sequence_length)."""
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    hp = config_hparams(2, batch_normalisation=False)
+    batch = synthetic_batch(hp, B=64, Ta=280, L=40, ragged=True)
+    model = Seq2SeqModel(to_data_sequences(batch), 'train', hp, seed=2001)
+    model.feed(to_data_sequences(batch))
+    model._set_step_scalars()
+    model.forward_backward()
+    model.finish_gradients()
+    loss_a, gn_a = model.fetch_scalars()
+    out_a = model._audio_encoder.get_data().outputs.clone()
+    padded = dict(batch)
+    padded['audio'] = np.concatenate([batch['audio'], np.zeros((64, 20, 80), np.float32)], axis=1)
+    model.feed(to_data_sequences(padded))
+    model._set_step_scalars()
+    model.forward_backward()
+    model.finish_gradients()
+    loss_b, gn_b = model.fetch_scalars()
+    out_b = model._audio_encoder.get_data().outputs
+    assert out_b.shape[0] == 300
+    # split-K products use fp32 atomics (order varies with the padded length): equal to rounding
+    assert torch.allclose(out_b[:280], out_a, rtol=1e-4, atol=1e-6)
+    assert float(out_b[280:].abs().max()) == 0.0
+    lens = torch.from_numpy(batch['audio_len']).cuda()
+    tmask = torch.arange(280, device='cuda')[:, None] >= lens[None, :]
+    assert float((out_a.abs().sum(-1) * tmask).max()) == 0.0  # zeros past each utterance's length
+    assert abs(loss_a - loss_b) <= 1e-6 * abs(loss_a)
+    assert abs(gn_a - gn_b) <= 1e-4 * gn_a
+
+
+@pytest.mark.parametrize('cfg,algo', [(1, 'greedy'), (5, 'greedy'), (1, 'beam_search'), (4, 'beam_search'),
+                                      (5, 'beam_search')])
+def test_decoding_and_error_rates(cfg, algo):
+    """ids from greedy / beam search equal the oracle's; CER / WER computed from them are
+    bit-identical (integer Levenshtein, avsr/utils.py)."""
+    from avsr_tf1_b200 import ops, utils
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    old = ops.set_tensor_cores(False)  # exact fp32 so arg-max / top-k decisions are reproducible
+    try:
+        hp = config_hparams(cfg, decoding_algorithm=algo, beam_width=4 if algo == 'beam_search' else 10)
+        hp.max_label_length = 12
+        batch = synthetic_batch(hp, B=3, Ta=30, Tv=10, L=6, ragged=True)
+        ds = to_data_sequences(batch)
+        train = Seq2SeqModel(ds, 'train', hp, seed=2001)
+        # sharpen the output distribution so near-ties do not decide the comparison
+        train.store.p('Decoder/decoder/my_dense/kernel').mul_(20.0)
+        for _ in range(2):
+            train.train_step(ds)
+        ev = Seq2SeqModel(ds, 'evaluate', hp, share_params_with=train)
+        ids = ev.predict(ds)
+        om, P = oracle_for(hp, train, np.float32)
+        ohp = om.hp
+        if algo == 'greedy':
+            ref = om.greedy_decode(cast_batch(batch, np.float32))
+        else:
+            r = om.beam_decode(cast_batch(batch, np.float32))
+            ref = r['predicted_ids'][:, :, 0]
+            bo = ev._decoder.beam_search_output
+            assert np.array_equal(bo.predicted_ids, r['step_ids'])
+            assert np.array_equal(bo.parent_ids, r['parent_ids'])
+            np.testing.assert_allclose(bo.scores, r['scores'], rtol=1e-4, atol=1e-4)
+        assert ids.shape == ref.shape, (ids.shape, ref.shape)
+        assert np.array_equal(ids, ref)
+        ud = hp.unit_dict
+        pred = {f'utt{b}': utils.ids_to_symbols(ids[b], ud) for b in range(ids.shape[0])}
+        truth = {f'utt{b}': utils.ids_to_symbols(batch['labels'][b], ud) for b in range(ids.shape[0])}
+        assert utils.compute_wer(pred, truth) == O.compute_wer(pred, truth)
+        assert utils.compute_wer(pred, truth, split_words=True) == O.compute_wer(pred, truth, split_words=True)
+    finally:
+        ops.set_tensor_cores(old)

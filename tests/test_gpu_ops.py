@@ -1,0 +1,361 @@
+"""GPU parity of the layer-level C-ABI entry points against the oracle (fp64 truth on the
+same fp32 inputs).  Tolerances: exact-fp32 CUDA-core path 2e-5 (scaled by the tensor's
+largest magnitude); TF32 tensor-core path 1e-3 (north_star: "within 1e-3 rel fp32")."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import avsr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def ops_mod():
+    from avsr_tf1_b200 import ops
+    return ops
+
+
+def dev(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to('cuda').to(dtype)
+
+
+def close(got, want, rtol, what=''):
+    got = got.detach().cpu().numpy().astype(np.float64) if torch.is_tensor(got) else np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = max(1e-30, np.abs(want).max())
+    err = np.abs(got - want).max() / scale
+    assert np.isfinite(got).all(), what + ': non-finite values'
+    assert err <= rtol, f'{what}: max scaled error {err:.3e} > {rtol:.1e}'
+    return err
+
+
+@pytest.fixture(params=[False, True], ids=['fp32', 'tf32'])
+def tensor_cores(request):
+    ops = ops_mod()
+    old = ops.set_tensor_cores(request.param)
+    yield request.param
+    ops.set_tensor_cores(old)
+
+
+def tol(tc):
+    return 1e-3 if tc else 2e-5
+
+
+GEMM_SHAPES = [
+    (5, 7, 3), (1, 1, 1), (33, 31, 80), (64, 1024, 256), (128, 128, 64), (300, 31, 256), (257, 1024, 3888),
+    (2048, 1024, 80), (1024, 512, 4096), (96, 640, 1000), (17, 256, 512),
+]
+
+
+@pytest.mark.parametrize('M,N,K', GEMM_SHAPES)
+@pytest.mark.parametrize('ta,tb', [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm(M, N, K, ta, tb, tensor_cores):
+    ops = ops_mod()
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    Bm = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    C0 = rng.standard_normal((M, N)).astype(np.float32)
+    opA = A.T if ta else A
+    opB = Bm.T if tb else Bm
+    ref = opA.astype(np.float64) @ opB.astype(np.float64)
+    scale_tol = tol(tensor_cores) * np.sqrt(K)  # errors of a K-long dot product
+    out = dev(C0)
+    ops.gemm(dev(A), dev(Bm), out, ta=ta, tb=tb, beta=0.0, bias=dev(bias))
+    close(out, ref + bias, scale_tol, 'beta=0 + bias')
+    out = dev(C0)
+    ops.gemm(dev(A), dev(Bm), out, ta=ta, tb=tb, beta=1.0)
+    close(out, ref + C0, scale_tol, 'beta=1')
+
+
+def test_gemm_strided_views(tensor_cores):
+    """sub-blocks of larger matrices (row slices of the LSTM kernel, column slices of states)."""
+    ops = ops_mod()
+    rng = np.random.default_rng(0)
+    big_a = rng.standard_normal((70, 300)).astype(np.float32)
+    big_b = rng.standard_normal((400, 256)).astype(np.float32)
+    big_c = rng.standard_normal((70, 512)).astype(np.float32)
+    a, b, c = dev(big_a), dev(big_b), dev(big_c)
+    ops.gemm(a[:, 44:300], b[100:356], c[:, 128:384])
+    want = big_c.copy()
+    want[:, 128:384] = big_a[:, 44:300].astype(np.float64) @ big_b[100:356].astype(np.float64)
+    close(c, want, tol(tensor_cores) * 16, 'strided')
+
+
+def test_colsum_reverse_transpose_embedding():
+    ops = ops_mod()
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((1000, 37)).astype(np.float32)
+    out = torch.ones(37, device='cuda')
+    ops.colsum(dev(X), out)
+    close(out, 1.0 + X.astype(np.float64).sum(0), 1e-5, 'colsum')
+    x = rng.standard_normal((9, 4, 5)).astype(np.float32)  # [T,B,F]
+    lens = np.array([9, 3, 1, 6], np.int32)
+    y = ops.reverse_sequence(dev(x), dev(lens, torch.int32))
+    want = O.reverse_sequence(x.transpose(1, 0, 2), lens).transpose(1, 0, 2)
+    assert np.array_equal(y.cpu().numpy(), want)
+    t = ops.transpose01(dev(x))
+    assert np.array_equal(t.cpu().numpy(), x.transpose(1, 0, 2))
+    table = rng.standard_normal((31, 16)).astype(np.float32)
+    ids = rng.integers(0, 31, 50).astype(np.int32)
+    e = torch.empty(50, 16, device='cuda')
+    ops.embedding_fwd(dev(table), dev(ids, torch.int32), e)
+    assert np.array_equal(e.cpu().numpy(), table[ids])
+    d = rng.standard_normal((50, 16)).astype(np.float32)
+    dt = torch.zeros(31, 16, device='cuda')
+    ops.embedding_bwd(dev(d), dev(ids, torch.int32), dt)
+    want = np.zeros((31, 16))
+    np.add.at(want, ids, d.astype(np.float64))
+    close(dt, want, 1e-5, 'embedding_bwd')
+
+
+@pytest.mark.parametrize('rows,F', [(6, 5), (5 * 300, 80), (64 * 75, 128), (33, 3888)])
+def test_batchnorm(rows, F):
+    ops = ops_mod()
+    rng = np.random.default_rng(rows + F)
+    T = 3 if rows % 3 == 0 else 1
+    x = (rng.standard_normal((rows // T, T, F)) * 2 + 0.5).astype(np.float32)
+    gamma = rng.uniform(0.5, 1.5, F).astype(np.float32)
+    beta = rng.standard_normal(F).astype(np.float32)
+    y_ref, cache, mean, var = O.batchnorm_train_fwd(x.astype(np.float64), gamma.astype(np.float64), beta.astype(np.float64))
+    x2 = dev(x.reshape(rows, F))
+    sums = torch.zeros(2 * F, device='cuda')
+    ops.bn_stats(x2, sums)
+    y, xhat, invstd = torch.empty_like(x2), torch.empty_like(x2), torch.empty(F, device='cuda')
+    mm, mv = torch.zeros(F, device='cuda'), torch.ones(F, device='cuda')
+    ops.bn_apply_train(x2, sums, rows, dev(gamma), dev(beta), 1e-3, 0.99, y, xhat, invstd, mm, mv)
+    close(y, y_ref.reshape(rows, F), 1e-5, 'bn y')
+    close(mm, 0.01 * mean, 1e-4, 'moving mean')
+    close(mv, 0.99 + 0.01 * var, 1e-5, 'moving var')
+    dy = rng.standard_normal((rows // T, T, F)).astype(np.float32)
+    dx_ref, dg_ref, db_ref = O.batchnorm_train_bwd(dy.astype(np.float64), cache)
+    sums2 = torch.zeros(2 * F, device='cuda')
+    dy2 = dev(dy.reshape(rows, F))
+    ops.bn_bwd_stats(dy2, xhat, sums2)
+    dx, dg, db = torch.empty_like(x2), torch.zeros(F, device='cuda'), torch.zeros(F, device='cuda')
+    ops.bn_bwd_apply(dy2, xhat, sums2, rows, dev(gamma), invstd, dx, dg, db)
+    close(dx, dx_ref.reshape(rows, F), 2e-5, 'bn dx')
+    close(dg, dg_ref, 2e-5, 'bn dgamma')
+    close(db, db_ref, 2e-5, 'bn dbeta')
+    ye = torch.empty_like(x2)
+    ops.bn_apply_eval(x2, dev(gamma), dev(beta), mm, mv, 1e-3, ye)
+    close(ye, O.batchnorm_eval(x.astype(np.float64), gamma, beta, mm.cpu().numpy().astype(np.float64),
+                               mv.cpu().numpy().astype(np.float64)).reshape(rows, F), 1e-5, 'bn eval')
+
+
+def _lstm_case(B, T, I, H, seed, full=False):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, T, I)).astype(np.float32)
+    lens = np.full(B, T, np.int32) if full else rng.integers(1, T + 1, B).astype(np.int32)
+    lens[0] = T
+    x *= (np.arange(T)[None, :, None] < lens[:, None, None])
+    W = (rng.standard_normal((I + H, 4 * H)) / np.sqrt(I + H) * 1.5).astype(np.float32)
+    b = (0.1 * rng.standard_normal(4 * H)).astype(np.float32)
+    return x, lens, W, b, rng
+
+
+@pytest.mark.parametrize('B,T,I,H', [(3, 5, 4, 8), (5, 23, 80, 128), (8, 60, 256, 256), (64, 12, 128, 256)])
+def test_lstm_layer_fwd_bwd(B, T, I, H, tensor_cores):
+    ops = ops_mod()
+    x, lens, W, b, rng = _lstm_case(B, T, I, H, B + T + I)
+    f64 = lambda a: a.astype(np.float64)
+    out_ref, (c_ref, h_ref), cache = O.lstm_seq_fwd(f64(x), lens, f64(W), f64(b))
+    xt = dev(x.transpose(1, 0, 2))
+    Wd, bd, ld = dev(W), dev(b), dev(lens, torch.int32)
+    gates = torch.empty(T, B, 4 * H, device='cuda')
+    ops.gemm(xt.view(T * B, I), Wd[:I], gates.view(T * B, 4 * H), bias=bd)
+    rnn = ops.RnnSeq(T, B, H, ld, gates, Wd[I:])
+    out = rnn.forward()
+    rt = tol(tensor_cores)
+    close(out.transpose(0, 1), out_ref, rt, 'lstm outputs')
+    close(rnn.cT, c_ref, rt, 'final c')
+    close(rnn.hT, h_ref, rt, 'final h')
+    assert float(out.transpose(0, 1)[1, lens[1]:].abs().max() if lens[1] < T else 0.0) == 0.0
+    dout = rng.standard_normal((B, T, H)).astype(np.float32)
+    dc, dh = rng.standard_normal((B, H)).astype(np.float32), rng.standard_normal((B, H)).astype(np.float32)
+    dx_ref, dW_ref, db_ref, _ = O.lstm_seq_bwd(f64(dout), (f64(dc), f64(dh)), cache)
+    gW = torch.zeros_like(Wd)
+    dZ = rnn.backward(dev(dout.transpose(1, 0, 2)), gW[I:], dcT=dev(dc), dhT=dev(dh))
+    dZ2 = dZ.view(T * B, 4 * H)
+    ops.gemm(xt.view(T * B, I), dZ2, gW[:I], ta=True, beta=1.0)
+    gb = torch.zeros(4 * H, device='cuda')
+    ops.colsum(dZ2, gb)
+    dx = torch.empty(T, B, I, device='cuda')
+    ops.gemm(dZ2, Wd[:I], dx.view(T * B, I), tb=True)
+    rg = 5 * rt
+    close(dx.transpose(0, 1), dx_ref, rg, 'dx')
+    close(gW, dW_ref, rg, 'dW')
+    close(gb, db_ref, rg, 'db')
+
+
+KINDS = ['luong', 'scaled_luong', 'bahdanau', 'normed_bahdanau']
+
+
+def _attn_case(kinds, B, T, Dx, H, Tms, Dms, seed):
+    rng = np.random.default_rng(seed)
+    f32 = np.float32
+    x = rng.standard_normal((B, T, Dx)).astype(f32)
+    lens = rng.integers(1, T + 1, B).astype(np.int32)
+    lens[0] = T
+    A = H
+    At = A * len(kinds)
+    W = (rng.standard_normal((Dx + At + H, 4 * H)) / np.sqrt(Dx + At + H) * 1.5).astype(f32)
+    b = (0.1 * rng.standard_normal(4 * H)).astype(f32)
+    specs = []
+    for kind, Tm, Dm in zip(kinds, Tms, Dms):
+        mem_len = rng.integers(1, Tm + 1, B).astype(np.int32)
+        mem_len[0] = Tm
+        mem = rng.standard_normal((B, Tm, Dm)).astype(f32)
+        mem *= (np.arange(Tm)[None, :, None] < mem_len[:, None, None])
+        kw = dict(kind=kind, memory=mem, mem_len=mem_len, Wm=(rng.standard_normal((Dm, A)) / np.sqrt(Dm)).astype(f32),
+                  Wl=(rng.standard_normal((H + Dm, A)) / np.sqrt(H + Dm)).astype(f32))
+        if kind == 'scaled_luong':
+            kw['g'] = np.asarray(1.3, f32)
+        if 'bahdanau' in kind:
+            kw['Wq'] = (rng.standard_normal((H, A)) / np.sqrt(H)).astype(f32)
+            kw['v'] = rng.standard_normal(A).astype(f32)
+        if kind == 'normed_bahdanau':
+            kw['g'] = np.asarray(0.7, f32)
+            kw['b'] = (0.1 * rng.standard_normal(A)).astype(f32)
+        specs.append(O.AttnSpec(**kw))
+    c0 = (0.5 * rng.standard_normal((B, H))).astype(f32)
+    h0 = (0.5 * rng.standard_normal((B, H))).astype(f32)
+    return x, lens, W, b, specs, c0, h0, rng
+
+
+def _spec64(s):
+    c = lambda a: None if a is None else np.asarray(a, np.float64)
+    return O.AttnSpec(kind=s.kind, memory=c(s.memory), mem_len=s.mem_len, Wm=c(s.Wm), Wl=c(s.Wl), Wq=c(s.Wq), v=c(s.v),
+                      g=c(s.g), b=c(s.b))
+
+
+@pytest.mark.parametrize('kinds,B,T,Dx,H,Tms,Dms', [
+    (('luong',), 3, 5, 4, 8, (6,), (5,)),
+    (('scaled_luong',), 4, 11, 128, 128, (30,), (128,)),
+    (('bahdanau',), 4, 11, 128, 128, (30,), (256,)),
+    (('normed_bahdanau',), 3, 7, 16, 32, (9,), (24,)),
+    (('scaled_luong', 'scaled_luong'), 4, 9, 128, 256, (20, 75), (256, 256)),
+    (('bahdanau', 'bahdanau'), 3, 6, 32, 64, (10, 17), (64, 48)),
+    (('bahdanau',), 6, 41, 128, 256, (300,), (512,)),
+])
+def test_attention_rnn_fwd_bwd(kinds, B, T, Dx, H, Tms, Dms, tensor_cores):
+    ops = ops_mod()
+    x, lens, W, b, specs, c0, h0, rng = _attn_case(kinds, B, T, Dx, H, Tms, Dms, sum(Tms) + B)
+    f64 = lambda a: a.astype(np.float64)
+    r = O.attn_rnn_fwd(f64(x), lens, f64(W), f64(b), [_spec64(s) for s in specs], init_cell=(f64(c0), f64(h0)))
+    A = H
+    At = A * len(kinds)
+    xt = dev(x.transpose(1, 0, 2))
+    Wd, bd, ld = dev(W), dev(b), dev(lens, torch.int32)
+    gates = torch.empty(T, B, 4 * H, device='cuda')
+    ops.gemm(xt.view(T * B, Dx), Wd[:Dx], gates.view(T * B, 4 * H), bias=bd)
+    bufs, extra = [], []
+    for s in specs:
+        Tm, Dm = s.memory.shape[1], s.memory.shape[2]
+        values = dev(s.memory.transpose(1, 0, 2))
+        keys = torch.empty(Tm, B, A, device='cuda')
+        ops.gemm(values.view(Tm * B, Dm), dev(s.Wm), keys.view(Tm * B, A))
+        v = None if s.v is None else dev(s.v)
+        g = None if s.g is None else dev(np.asarray(s.g).reshape(1))
+        veff = v
+        if s.kind == 'normed_bahdanau':
+            veff = torch.empty(A, device='cuda')
+            ops.normed_v_fwd(v, g, veff)
+        mb = ops.MechBuffers(s.kind, values, keys, dev(s.mem_len, torch.int32), dev(s.Wl),
+                             Wq=None if s.Wq is None else dev(s.Wq), v=veff,
+                             g=g if s.kind == 'scaled_luong' else None, bias=None if s.b is None else dev(s.b))
+        bufs.append(mb)
+        extra.append((v, g))
+    rnn = ops.RnnSeq(T, B, H, ld, gates, Wd[Dx:], bufs, specs[-1].output_attention, c0=dev(c0), h0=dev(h0))
+    out = rnn.forward()
+    rt = tol(tensor_cores)
+    close(out.transpose(0, 1), r['outputs'], rt, 'outputs')
+    close(rnn.cT, r['final'][0], rt, 'final c')
+    close(rnn.hT, r['final'][1], rt, 'final h')
+    mask = (np.arange(T)[None, :] < lens[:, None])[:, :, None]
+    for k, mb in enumerate(bufs):
+        close(mb.align.transpose(0, 1) * dev(mask.astype(np.float32)), r['alignments'][k], rt, 'alignments')
+        close(mb.hc.transpose(0, 1)[:, :, H:] * dev(mask.astype(np.float32)), r['contexts'][k], rt, 'contexts')
+    # backward
+    O_dim = out.shape[2]
+    dout = rng.standard_normal((B, T, O_dim)).astype(np.float32)
+    dc, dh = rng.standard_normal((B, H)).astype(np.float32), rng.standard_normal((B, H)).astype(np.float32)
+    rb = O.attn_rnn_bwd(f64(dout), (f64(dc), f64(dh)), r['cache'])
+    gW = torch.zeros_like(Wd)
+    dveff = {}
+    for k, (s, mb) in enumerate(zip(specs, bufs)):
+        Tm, Dm = mb.Tm, mb.Dm
+        mb.dkeys, mb.dvalues = torch.zeros(Tm, B, A, device='cuda'), torch.zeros(Tm, B, Dm, device='cuda')
+        mb.dWl = torch.zeros(H + Dm, A, device='cuda')
+        if 'bahdanau' in s.kind:
+            mb.dWq = torch.zeros(H, A, device='cuda')
+            mb.dv = torch.zeros(A, device='cuda')
+        if s.kind == 'normed_bahdanau':
+            mb.dbias = torch.zeros(A, device='cuda')
+        if s.kind == 'scaled_luong':
+            mb.dg = torch.zeros(1, device='cuda')
+    dZ = rnn.backward(dev(dout.transpose(1, 0, 2)), gW[Dx:], dcT=dev(dc), dhT=dev(dh), want_init_grad=True)
+    dZ2 = dZ.view(T * B, 4 * H)
+    ops.gemm(xt.view(T * B, Dx), dZ2, gW[:Dx], ta=True, beta=1.0)
+    dx = torch.empty(T, B, Dx, device='cuda')
+    ops.gemm(dZ2, Wd[:Dx], dx.view(T * B, Dx), tb=True)
+    rg = 5 * rt
+    close(dx.transpose(0, 1), rb['dx'], rg, 'dx')
+    close(gW, rb['dW'], rg, 'dW')
+    close(rnn.dc0, rb['dinit'][0], rg, 'dc0')
+    close(rnn.dh0, rb['dinit'][1], rg, 'dh0')
+    for k, (s, mb) in enumerate(zip(specs, bufs)):
+        Tm, Dm = mb.Tm, mb.Dm
+        mg = rb['mech'][k]
+        close(mb.dWl, mg['Wl'], rg, 'dWl')
+        dWm = torch.zeros(Dm, A, device='cuda')
+        ops.gemm(mb.values.view(Tm * B, Dm), mb.dkeys.view(Tm * B, A), dWm, ta=True, beta=1.0)
+        close(dWm, mg['Wm'], rg, 'dWm')
+        ops.gemm(mb.dkeys.view(Tm * B, A), dev(s.Wm), mb.dvalues.view(Tm * B, Dm), tb=True, beta=1.0)
+        close(mb.dvalues.transpose(0, 1), rb['dmem'][k], rg, 'dmemory')
+        if 'bahdanau' in s.kind:
+            close(mb.dWq, mg['Wq'], rg, 'dWq')
+        if s.kind == 'bahdanau':
+            close(mb.dv, mg['v'], rg, 'dv')
+        if s.kind == 'scaled_luong':
+            close(mb.dg, np.asarray(mg['g']).reshape(1), rg, 'dg')
+        if s.kind == 'normed_bahdanau':
+            v, g = extra[k]
+            dv, dg = torch.zeros(A, device='cuda'), torch.zeros(1, device='cuda')
+            ops.normed_v_bwd(v, g, mb.dv, dv, dg)
+            close(dv, mg['v'], rg, 'dv (normed)')
+            close(dg, np.asarray(mg['g']).reshape(1), rg, 'dg (normed)')
+            close(mb.dbias, mg['b'], rg, 'dbias')
+
+
+def test_seq_loss_and_adam():
+    ops = ops_mod()
+    rng = np.random.default_rng(4)
+    B, T, V = 7, 9, 31
+    logits = (3 * rng.standard_normal((B, T, V))).astype(np.float32)
+    lens = rng.integers(1, T + 1, B).astype(np.int32)
+    lens[0] = T
+    labels = rng.integers(1, 30, (B, T + 2)).astype(np.int32)
+    loss_ref, d_ref = O.sequence_loss_fwd_bwd(logits.astype(np.float64), labels, lens)
+    inv = 1.0 / (float(lens.sum()) + 1e-12)
+    lsum = torch.zeros(1, device='cuda')
+    lt = dev(logits.transpose(1, 0, 2))
+    dl = torch.empty_like(lt)
+    ops.seq_loss(lt, dev(labels, torch.int32), dev(lens, torch.int32), inv, lsum, dl)
+    close(lsum * inv, np.asarray([loss_ref]), 1e-5, 'loss')
+    close(dl.transpose(0, 1), d_ref, 1e-5, 'dlogits')
+    n = 1000
+    P = {'w': rng.standard_normal(n)}
+    G = {'w': rng.standard_normal(n) * 0.3}
+    m, v = {'w': np.zeros(n)}, {'w': np.zeros(n)}
+    p, g_, mm, vv = dev(P['w']), dev(G['w']), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    for step in range(3):
+        gn = O.clip_and_adam(P, G, m, v, step, 1e-3, clip=1.0, warmup_steps=750)
+        ss = torch.zeros(1, device='cuda')
+        ops.sumsq(g_, ss)
+        close(ss.sqrt(), np.asarray([gn]), 1e-5, 'global norm')
+        lr = 1e-3 * min(1.0, (step + 1) / 750.0)
+        t = step + 1
+        ops.adam_clip_step(p, g_, mm, vv, ss, 1.0, lr * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t))
+        close(p, P['w'], 1e-6, 'adam params step %d' % step)
