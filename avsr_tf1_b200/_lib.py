@@ -48,7 +48,9 @@ PROTOTYPES = {
     'avsr_version': (_I, []),
     'avsr_launch_count': (C.c_ulonglong, []),
     'avsr_set_tensor_cores': (_I, [_I]),
-    'avsr_gemm': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _P]),
+    'avsr_get_tensor_cores': (_I, []),
+    'avsr_round_tf32': (_I, [_P, _P, _P, _L]),
+    'avsr_gemm': (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _F, _P, _I]),
     'avsr_colsum': (_I, [_P, _P, _I, _I, _I, _P]),
     'avsr_bn_stats': (_I, [_P, _P, _L, _I, _P]),
     'avsr_bn_apply_train': (_I, [_P, _P, _L, _I, _P, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
@@ -67,7 +69,7 @@ PROTOTYPES = {
     'avsr_seq_loss': (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P]),
     'avsr_sumsq': (_I, [_P, _P, _L, _P]),
     'avsr_axpy': (_I, [_P, _F, _P, _P, _L]),
-    'avsr_adam_clip_step': (_I, [_P, _P, _P, _P, _P, _L, _P, _F, _P, _F, _F, _F]),
+    'avsr_adam_clip_step': (_I, [_P, _P, _P, _P, _P, _L, _P, _F, _P, _F, _F, _F, _P]),
     'avsr_greedy_pick': (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     'avsr_beam_step': (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     'avsr_gather_rows': (_I, [_P, _P, _P, _L, _I, _P]),

@@ -22,15 +22,17 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r);
 size_t rnn_work_floats(int B, int H, int At, int maxHD, int maxA);
 // tcgen05 TF32 path (gemm_tc.cu); returns -1 when the shape is not eligible
 int gemm_tc(cudaStream_t st, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
-            int ldb, float* C, int ldc, float beta, const float* bias);
+            int ldb, float* C, int ldc, float beta, const float* bias, int round_out);
+int tensor_cores_enabled() { return g_use_tc; }
 
 int gemm(cudaStream_t st, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
-         int ldb, float* C, int ldc, float beta, const float* bias) {
+         int ldb, float* C, int ldc, float beta, const float* bias, int round_out) {
+  round_out = (round_out && g_use_tc) ? 1 : 0;
   if (g_use_tc) {
-    int r = gemm_tc(st, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias);
+    int r = gemm_tc(st, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias, round_out);
     if (r >= 0) return r;
   }
-  return gemm_simt(st, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias);
+  return gemm_simt(st, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias, round_out);
 }
 
 }  // namespace avsr
@@ -49,9 +51,10 @@ int avsr_set_tensor_cores(int enable) {
 }
 
 int avsr_gemm(avsr_stream_t s, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
-              int ldb, float* C, int ldc, float beta, const float* bias) {
-  return gemm((cudaStream_t)s, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias);
+              int ldb, float* C, int ldc, float beta, const float* bias, int round_out) {
+  return gemm((cudaStream_t)s, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, beta, bias, round_out);
 }
+int avsr_get_tensor_cores(void) { return g_use_tc; }
 
 size_t avsr_rnn_work_floats(int B, int H, int At, int maxHD, int maxA) {
   return rnn_work_floats(B, H, At, maxHD, maxA);

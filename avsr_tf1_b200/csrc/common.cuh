@@ -54,6 +54,16 @@ __device__ __forceinline__ float tanhf_acc(float x) {
   return copysignf(r, x);
 }
 
+// round-to-nearest fp32 -> tf32 (low 13 mantissa bits zero).  Operands of the tcgen05 kind::tf32 products
+// are rounded where they are PRODUCED, so the tensor core's own truncation is a no-op and the products
+// carry unbiased rounding error instead of a systematic -2^-11 shrink.
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float maybe_tf32(float x, int rnd) { return rnd ? tf32_rn(x) : x; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -98,10 +108,13 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
 // ---- internal entry points shared between translation units ------------------
 // C[M,N](ldc) = beta*C + op(A)*op(B) (+bias[N]); beta in {0,1}.  op(A) is MxK:
 // transA==0 -> A stored [M,K] row-major with leading dim lda; transA==1 -> stored [K,M].
+// round_out: store C rounded to tf32 (only with beta == 0; used when C is itself a tensor-core operand).
 int gemm(cudaStream_t st, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
-         int ldb, float* C, int ldc, float beta, const float* bias);
+         int ldb, float* C, int ldc, float beta, const float* bias, int round_out = 0);
 // exact fp32 CUDA-core implementation (gemm_simt.cu)
 int gemm_simt(cudaStream_t st, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
-              int ldb, float* C, int ldc, float beta, const float* bias);
+              int ldb, float* C, int ldc, float beta, const float* bias, int round_out = 0);
+// 1 when the tcgen05 TF32 path (and producer-side tf32 rounding) is enabled
+int tensor_cores_enabled();
 
 }  // namespace avsr

@@ -10,7 +10,8 @@ namespace avsr {
 template <int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                 float* __restrict__ C, int ldc, int accumulate, const float* __restrict__ bias, int splitk) {
+                 float* __restrict__ C, int ldc, int accumulate, const float* __restrict__ bias, int splitk,
+                 int round_out) {
   constexpr int NTHR = (BM / TM) * (BN / TN);
   constexpr int AE = BM * BK / NTHR, BE = BN * BK / NTHR;
   constexpr int RG = TM >= 4 ? 4 : TM, CG = TN >= 4 ? 4 : TN;
@@ -112,7 +113,7 @@ gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, cons
       if (bias != nullptr && blockIdx.z == 0) v += bias[gn];
       float* p = C + (size_t)gm * ldc + gn;
       if (splitk > 1) atomicAdd(p, v);
-      else *p = accumulate ? (*p + v) : v;
+      else *p = accumulate ? (*p + v) : maybe_tf32(v, round_out);
     }
   }
 }
@@ -124,19 +125,20 @@ __global__ void zero_block_kernel(float* C, int M, int N, int ldc) {
 
 template <int BM, int BN, int BK, int TM, int TN>
 static int launch_cfg(cudaStream_t st, int tA, int tB, int M, int N, int K, const float* A, int lda, const float* B,
-                      int ldb, float* C, int ldc, int acc, const float* bias, int splitk) {
+                      int ldb, float* C, int ldc, int acc, const float* bias, int splitk, int round_out) {
   dim3 grid(cdiv(N, BN), cdiv(M, BM), splitk);
   dim3 block((BM / TM) * (BN / TN));
-  if (!tA && !tB) AVSR_LAUNCH((gemm_simt_kernel<BM, BN, BK, TM, TN, false, false>), grid, block, 0, st, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk);
-  else if (!tA && tB) AVSR_LAUNCH((gemm_simt_kernel<BM, BN, BK, TM, TN, false, true>), grid, block, 0, st, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk);
-  else if (tA && !tB) AVSR_LAUNCH((gemm_simt_kernel<BM, BN, BK, TM, TN, true, false>), grid, block, 0, st, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk);
-  else AVSR_LAUNCH((gemm_simt_kernel<BM, BN, BK, TM, TN, true, true>), grid, block, 0, st, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk);
+  if (!tA && !tB) AVSR_LAUNCH((gemm_simt_kernel<BM, BN, BK, TM, TN, false, false>), grid, block, 0, st, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk, round_out);
+  else if (!tA && tB) AVSR_LAUNCH((gemm_simt_kernel<BM, BN, BK, TM, TN, false, true>), grid, block, 0, st, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk, round_out);
+  else if (tA && !tB) AVSR_LAUNCH((gemm_simt_kernel<BM, BN, BK, TM, TN, true, false>), grid, block, 0, st, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk, round_out);
+  else AVSR_LAUNCH((gemm_simt_kernel<BM, BN, BK, TM, TN, true, true>), grid, block, 0, st, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk, round_out);
   return 0;
 }
 
 int gemm_simt(cudaStream_t st, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
-              int ldb, float* C, int ldc, float beta, const float* bias) {
+              int ldb, float* C, int ldc, float beta, const float* bias, int round_out) {
   AVSR_REQUIRE(beta == 0.0f || beta == 1.0f, "gemm: beta must be 0 or 1 (got %f)", beta);
+  AVSR_REQUIRE(!(round_out && beta != 0.0f), "gemm: round_out needs beta == 0");
   if (M <= 0 || N <= 0) return 0;
   int acc = beta == 1.0f;
   if (K <= 0) {
@@ -154,9 +156,10 @@ int gemm_simt(cudaStream_t st, int transA, int transB, int M, int N, int K, cons
     long long tilesS = (long long)cdiv(M, 32) * cdiv(N, 64);
     if (tilesS < target && K >= 128) splitk = (int)min((long long)cdiv(K, 64), (long long)cdiv(target, tilesS));
   }
+  if (round_out) splitk = 1;  // rounding needs the complete sum in one place
   if (splitk > 1 && !acc) AVSR_LAUNCH(zero_block_kernel, cdiv((long long)M * N, 256), 256, 0, st, C, M, N, ldc);
-  if (large) return launch_cfg<128, 128, 8, 8, 8>(st, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk);
-  return launch_cfg<32, 64, 16, 2, 4>(st, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk);
+  if (large) return launch_cfg<128, 128, 8, 8, 8>(st, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk, round_out);
+  return launch_cfg<32, 64, 16, 2, 4>(st, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk, round_out);
 }
 
 }  // namespace avsr

@@ -67,7 +67,7 @@ __global__ void bn_apply_train_kernel(const float* __restrict__ x, long long n, 
                                       float inv_count, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float eps, float momentum,
                                       float* __restrict__ y, float* __restrict__ xhat, float* __restrict__ invstd,
-                                      float* __restrict__ moving_mean, float* __restrict__ moving_var) {
+                                      float* __restrict__ moving_mean, float* __restrict__ moving_var, int rnd) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int f = (int)(i % F);
@@ -76,7 +76,7 @@ __global__ void bn_apply_train_kernel(const float* __restrict__ x, long long n, 
   float is = rsqrtf(var + eps);
   float xh = (x[i] - mean) * is;
   xhat[i] = xh;
-  y[i] = fmaf(xh, gamma[f], beta[f]);
+  y[i] = maybe_tf32(fmaf(xh, gamma[f], beta[f]), rnd);
   if (i < F) {  // first row: per-feature side outputs
     invstd[f] = is;
     if (moving_mean) moving_mean[f] = moving_mean[f] * momentum + mean * (1.0f - momentum);
@@ -86,11 +86,11 @@ __global__ void bn_apply_train_kernel(const float* __restrict__ x, long long n, 
 
 __global__ void bn_apply_eval_kernel(const float* __restrict__ x, long long n, int F, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, const float* __restrict__ mm,
-                                     const float* __restrict__ mv, float eps, float* __restrict__ y) {
+                                     const float* __restrict__ mv, float eps, float* __restrict__ y, int rnd) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int f = (int)(i % F);
-  y[i] = fmaf((x[i] - mm[f]) * rsqrtf(mv[f] + eps), gamma[f], beta[f]);
+  y[i] = maybe_tf32(fmaf((x[i] - mm[f]) * rsqrtf(mv[f] + eps), gamma[f], beta[f]), rnd);
 }
 
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ xhat, long long n, int F,
@@ -198,7 +198,8 @@ __global__ void axpy_kernel(float a, const float* __restrict__ x, float* __restr
 
 __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, long long n, const float* __restrict__ sumsq, float clip,
-                                 const float* __restrict__ lr_t_dev, float b1, float b2, float eps) {
+                                 const float* __restrict__ lr_t_dev, float b1, float b2, float eps,
+                                 float* __restrict__ p_tf32) {
   const float lr_t = lr_t_dev[0];
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -212,7 +213,14 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
   float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
   m[i] = mi;
   v[i] = vi;
-  p[i] -= lr_t * mi / (sqrtf(vi) + eps);  // TF-Adam: epsilon outside the sqrt
+  const float pn = p[i] - lr_t * mi / (sqrtf(vi) + eps);  // TF-Adam: epsilon outside the sqrt
+  p[i] = pn;
+  if (p_tf32) p_tf32[i] = tf32_rn(pn);
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = tf32_rn(src[i]);
 }
 
 __global__ void normed_v_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g, int A,
@@ -390,7 +398,7 @@ int avsr_bn_apply_train(avsr_stream_t s, const float* x, long long rows, int F, 
   long long n = rows * F;
   AVSR_REQUIRE(rows >= 1 && count >= 1.0, "bn: empty batch");
   AVSR_LAUNCH(bn_apply_train_kernel, cdiv(n, 256), 256, 0, ST(s), x, n, F, sums, (float)(1.0 / count), gamma, beta,
-              eps, momentum, y, xhat, invstd, moving_mean, moving_var);
+              eps, momentum, y, xhat, invstd, moving_mean, moving_var, tensor_cores_enabled());
   return 0;
 }
 
@@ -399,7 +407,7 @@ int avsr_bn_apply_eval(avsr_stream_t s, const float* x, long long rows, int F, c
   long long n = rows * F;
   if (n <= 0) return 0;
   AVSR_LAUNCH(bn_apply_eval_kernel, cdiv(n, 256), 256, 0, ST(s), x, n, F, gamma, beta, moving_mean, moving_var, eps,
-              y);
+              y, tensor_cores_enabled());
   return 0;
 }
 
@@ -468,10 +476,17 @@ int avsr_axpy(avsr_stream_t s, float a, const float* x, float* y, long long n) {
 }
 
 int avsr_adam_clip_step(avsr_stream_t s, float* params, const float* grads, float* m, float* v, long long n,
-                        const float* sumsq_dev, float clip_norm, const float* lr_t, float beta1, float beta2, float eps) {
+                        const float* sumsq_dev, float clip_norm, const float* lr_t, float beta1, float beta2, float eps,
+                        float* params_tf32) {
   if (n <= 0) return 0;
   AVSR_LAUNCH(adam_clip_kernel, cdiv(n, 256), 256, 0, ST(s), params, grads, m, v, n, sumsq_dev, clip_norm, lr_t,
-              beta1, beta2, eps);
+              beta1, beta2, eps, params_tf32);
+  return 0;
+}
+
+int avsr_round_tf32(avsr_stream_t s, const float* src, float* dst, long long n) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(round_tf32_kernel, cdiv(n, 256), 256, 0, ST(s), src, dst, n);
   return 0;
 }
 

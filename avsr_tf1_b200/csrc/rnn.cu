@@ -24,7 +24,7 @@ __global__ void lstm_point_fwd_kernel(int t, int B, int H, float* __restrict__ g
                                       const int* __restrict__ len, const float* __restrict__ c_prev,
                                       const float* __restrict__ h_prev, int ldh_prev, float* __restrict__ c_next,
                                       float* __restrict__ h_next, int ldh_next, float* __restrict__ craw_t,
-                                      float* __restrict__ out_t, HcDst hc) {
+                                      float* __restrict__ out_t, HcDst hc, int rnd) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int b = idx / H, u = idx - b * H;
@@ -54,9 +54,11 @@ __global__ void lstm_point_fwd_kernel(int t, int B, int H, float* __restrict__ g
     if (out_t) out_t[idx] = hn;
   }
   c_next[idx] = cn;
-  h_next[(size_t)b * ldh_next + u] = hn;
-  if (hc.p[0]) hc.p[0][(size_t)b * hc.ld[0] + u] = hn;
-  if (hc.p[1]) hc.p[1][(size_t)b * hc.ld[1] + u] = hn;
+  // the state row and [h | ctx] are tensor-core operands: stored tf32-rounded (out_t keeps the exact h)
+  const float hr = maybe_tf32(hn, rnd);
+  h_next[(size_t)b * ldh_next + u] = hr;
+  if (hc.p[0]) hc.p[0][(size_t)b * hc.ld[0] + u] = hr;
+  if (hc.p[1]) hc.p[1][(size_t)b * hc.ld[1] + u] = hr;
 }
 
 struct DhSrc {
@@ -70,7 +72,7 @@ __global__ void lstm_point_bwd_kernel(int t, int B, int H, int At, const float* 
                                       const float* __restrict__ c0, const int* __restrict__ len,
                                       const float* __restrict__ dout_h_t, const float* __restrict__ dS_cur,
                                       const float* __restrict__ dc_cur, DhSrc extra, float* __restrict__ dZ_t,
-                                      float* __restrict__ dS_next, float* __restrict__ dc_next) {
+                                      float* __restrict__ dS_next, float* __restrict__ dc_next, int rnd) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int b = idx / H, u = idx - b * H;
@@ -98,10 +100,11 @@ __global__ void lstm_point_bwd_kernel(int t, int B, int H, int At, const float* 
     float cp = craw_prev ? fminf(fmaxf(craw_prev[idx], -1.0f), 1.0f) : (c0 ? c0[idx] : 0.0f);
     float dct = dc_in + dh * go * (1.0f - tc * tc);
     float dcr = (cr >= -1.0f && cr <= 1.0f) ? dct : 0.0f;
-    dz[u] = dcr * gj * gi * (1.0f - gi);
-    dz[H + u] = dcr * gi * (1.0f - gj * gj);
-    dz[2 * H + u] = dcr * cp * gf * (1.0f - gf);
-    dz[3 * H + u] = dh * tc * go * (1.0f - go);
+    // dZ only feeds tensor-core products (dZ Wrec^T, S^T dZ, x^T dZ, dZ Wx^T): stored tf32-rounded
+    dz[u] = maybe_tf32(dcr * gj * gi * (1.0f - gi), rnd);
+    dz[H + u] = maybe_tf32(dcr * gi * (1.0f - gj * gj), rnd);
+    dz[2 * H + u] = maybe_tf32(dcr * cp * gf * (1.0f - gf), rnd);
+    dz[3 * H + u] = maybe_tf32(dh * tc * go * (1.0f - go), rnd);
     dS_next[(size_t)b * SW + At + u] = 0.0f;
     dc_next[idx] = dcr * gf;
   }
@@ -112,13 +115,13 @@ __global__ void lstm_point_bwd_kernel(int t, int B, int H, int At, const float* 
 // dA_t[b,:] = mask * (dS_cur.att + (oa ? dout_t : 0))
 __global__ void attn_bwd_prep_kernel(int t, int B, int At, int SW, const int* __restrict__ len,
                                      const float* __restrict__ dS_cur, const float* __restrict__ dout_att_t,
-                                     float* __restrict__ dA_t) {
+                                     float* __restrict__ dA_t, int rnd) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * At) return;
   int b = idx / At, a = idx - b * At;
   float v = 0.0f;
   if (t < len[b]) v = dS_cur[(size_t)b * SW + a] + (dout_att_t ? dout_att_t[idx] : 0.0f);
-  dA_t[idx] = v;
+  dA_t[idx] = maybe_tf32(v, rnd);
 }
 
 // out_t[b,:] = t < len[b] ? S_next[b, :At] : 0
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(int kind, int Tm, int B, int Dm, int A, const float* __restrict__ q, int ldq,
                 const float* __restrict__ keys, const float* __restrict__ values, const int* __restrict__ mem_len,
                 const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ bias,
-                float* __restrict__ align_t, float* __restrict__ ctx_out, int ldctx) {
+                float* __restrict__ align_t, float* __restrict__ ctx_out, int ldctx, int rnd) {
   extern __shared__ float sm[];
   float* q_s = sm;            // A
   float* v_s = q_s + A;       // A
@@ -203,7 +206,7 @@ attn_fwd_kernel(int kind, int Tm, int B, int Dm, int A, const float* __restrict_
       a3 = fmaf(sc[tm + 3], vp[(size_t)(tm + 3) * stride], a3);
     }
     for (; tm < L; ++tm) a0 = fmaf(sc[tm], vp[(size_t)tm * stride], a0);
-    ctx_out[(size_t)b * ldctx + d] = (a0 + a1) + (a2 + a3);
+    ctx_out[(size_t)b * ldctx + d] = maybe_tf32((a0 + a1) + (a2 + a3), rnd);
   }
 }
 
@@ -217,7 +220,7 @@ attn_bwd_kernel(int kind, int t, const int* __restrict__ seq_len, int Tm, int B,
                 const float* __restrict__ g, const float* __restrict__ bias, const float* __restrict__ align_t,
                 const float* __restrict__ dctx, int lddctx, float* __restrict__ dq_out, int lddq,
                 float* __restrict__ dkeys, float* __restrict__ dvalues, float* __restrict__ dv,
-                float* __restrict__ dg, float* __restrict__ dbias) {
+                float* __restrict__ dg, float* __restrict__ dbias, int rnd) {
   extern __shared__ float sm[];
   float* q_s = sm;             // A
   float* v_s = q_s + A;        // A
@@ -303,6 +306,7 @@ attn_bwd_kernel(int kind, int t, const int* __restrict__ seq_len, int Tm, int B,
       }
       atomicAdd(dv + u, dvu);
       if (dbias) atomicAdd(dbias + u, dq);
+      dq = maybe_tf32(dq, rnd);  // d(processed query) feeds dpq Wq^T and h^T dpq
     }
     dq_out[(size_t)b * lddq + u] = dq;
   }
@@ -358,6 +362,7 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   int At, maxHD, maxA;
   AVSR_TRY(check_common(r, &At, &maxHD, &maxA));
   const int T = r->T, B = r->B, H = r->H, SW = At + H;
+  const int rnd = tensor_cores_enabled();
   WorkLayout wl = work_layout(B, H, At, maxHD, maxA);
   float* rec = r->work + wl.rec;
   float* cbuf[2] = {r->work + wl.cbuf, r->work + wl.cbuf + (size_t)B * H};
@@ -381,7 +386,7 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
     }
     float* out_h = (r->output_attention && r->n_mech > 0) ? nullptr : r->out + (size_t)t * B * H;
     AVSR_LAUNCH(lstm_point_fwd_kernel, pw_grid, 256, 0, st, t, B, H, gates_t, rec, r->len, cbuf[cur], S_t + At, SW,
-                cbuf[cur ^ 1], S_n + At, SW, r->craw + (size_t)t * B * H, out_h, hc);
+                cbuf[cur ^ 1], S_n + At, SW, r->craw + (size_t)t * B * H, out_h, hc, rnd);
     cur ^= 1;
     int off = 0;
     for (int k = 0; k < r->n_mech; ++k) {
@@ -396,8 +401,8 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
         ldq = m.A;
       }
       AVSR_LAUNCH(attn_fwd_kernel, B, ATT_THREADS, attn_fwd_smem(m), st, m.kind, m.Tm, B, m.Dm, m.A, q, ldq, m.keys,
-                  m.values, m.mem_len, m.v, m.g, m.bias, m.align + (size_t)t * B * m.Tm, hc.p[k] + H, hc.ld[k]);
-      AVSR_TRY(gemm(st, 0, 0, B, m.A, H + m.Dm, hc.p[k], hc.ld[k], m.Wl, m.A, S_n + off, SW, 0.0f, nullptr));
+                  m.values, m.mem_len, m.v, m.g, m.bias, m.align + (size_t)t * B * m.Tm, hc.p[k] + H, hc.ld[k], rnd);
+      AVSR_TRY(gemm(st, 0, 0, B, m.A, H + m.Dm, hc.p[k], hc.ld[k], m.Wl, m.A, S_n + off, SW, 0.0f, nullptr, 1));
       off += m.A;
     }
     if (r->output_attention && r->n_mech > 0)
@@ -414,6 +419,7 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   AVSR_TRY(check_common(r, &At, &maxHD, &maxA));
   const int T = r->T, B = r->B, H = r->H, SW = At + H;
   const bool oa = r->output_attention && r->n_mech > 0;
+  const int rnd = tensor_cores_enabled();
   WorkLayout wl = work_layout(B, H, At, maxHD, maxA);
   float* dS[2] = {r->work + wl.dS, r->work + wl.dS + (size_t)B * SW};
   float* dcb[2] = {r->work + wl.dcbuf, r->work + wl.dcbuf + (size_t)B * H};
@@ -437,7 +443,7 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
     if (r->n_mech > 0) {
       float* dA_t = r->dA + (size_t)t * B * At;
       AVSR_LAUNCH(attn_bwd_prep_kernel, cdiv((long long)B * At, 256), 256, 0, st, t, B, At, SW, r->len, dS[cur],
-                  (oa && r->dout) ? r->dout + (size_t)t * B * At : nullptr, dA_t);
+                  (oa && r->dout) ? r->dout + (size_t)t * B * At : nullptr, dA_t, rnd);
       int off = 0;
       for (int k = 0; k < r->n_mech; ++k) {
         const AvsrAttnMech& m = r->mech[k];
@@ -450,7 +456,7 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
         float* dq_out = luong ? dq[k] : m.dpq + (size_t)t * B * m.A;
         AVSR_LAUNCH(attn_bwd_kernel, B, ATT_THREADS, attn_bwd_smem(m), st, m.kind, t, r->len, m.Tm, B, m.Dm, m.A, q,
                     ldq, m.keys, m.values, m.mem_len, m.v, m.g, m.bias, m.align + (size_t)t * B * m.Tm,
-                    dHC[k] + H, HD, dq_out, m.A, m.dkeys, m.dvalues, m.dv, m.dg, m.dbias);
+                    dHC[k] + H, HD, dq_out, m.A, m.dkeys, m.dvalues, m.dv, m.dg, m.dbias, rnd);
         if (!luong) AVSR_TRY(gemm(st, 0, 1, B, H, m.A, dq_out, m.A, m.Wq, m.A, dq[k], H, 0.0f, nullptr));
         extra.p[2 * k] = dHC[k];
         extra.ld[2 * k] = HD;
@@ -462,7 +468,7 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
     AVSR_LAUNCH(lstm_point_bwd_kernel, pw_grid, 256, 0, st, t, B, H, At, r->gates + (size_t)t * B * 4 * H,
                 r->craw + (size_t)t * B * H, t > 0 ? r->craw + (size_t)(t - 1) * B * H : nullptr, r->c0, r->len,
                 (oa || !r->dout) ? nullptr : r->dout + (size_t)t * B * H, dS[cur], dcb[cur], extra, dZ_t, dS[cur ^ 1],
-                dcb[cur ^ 1]);
+                dcb[cur ^ 1], rnd);
     // [datt_{t-1} | dh_{t-1}] += dZ_t @ Wrec^T
     AVSR_TRY(gemm(st, 0, 1, B, SW, 4 * H, dZ_t, 4 * H, r->Wrec, 4 * H, dS[cur ^ 1], SW, 1.0f, nullptr));
     cur ^= 1;

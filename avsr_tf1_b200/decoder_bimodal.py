@@ -35,8 +35,8 @@ class Seq2SeqBimodalDecoder(Seq2SeqUnimodalDecoder):
         self._cat_c[:, :Hv].copy_(cv); self._cat_c[:, Hv:].copy_(ca)
         self._cat_h[:, :Hv].copy_(hv); self._cat_h[:, Hv:].copy_(ha)
         c0, h0 = ops.empty(B, self._H), ops.empty(B, self._H)
-        ops.gemm(self._cat_c, ctx.p(self._Wp), c0)
-        ops.gemm(self._cat_h, ctx.p(self._Wp), h0)
+        ops.gemm(self._cat_c, ctx.w(self._Wp), c0)
+        ops.gemm(self._cat_h, ctx.w(self._Wp), h0)
         return (c0, h0)
 
     def _initial_state_bwd(self, dinit):
@@ -47,7 +47,7 @@ class Seq2SeqBimodalDecoder(Seq2SeqUnimodalDecoder):
         ops.gemm(self._cat_c, dc0, ctx.g(self._Wp), ta=True, beta=1.0)
         ops.gemm(self._cat_h, dh0, ctx.g(self._Wp), ta=True, beta=1.0)
         dcc, dch = ops.empty(B, Hv + Ha), ops.empty(B, Hv + Ha)
-        ops.gemm(dc0, ctx.p(self._Wp), dcc, tb=True)
-        ops.gemm(dh0, ctx.p(self._Wp), dch, tb=True)
+        ops.gemm(dc0, ctx.w(self._Wp), dcc, tb=True)
+        ops.gemm(dh0, ctx.w(self._Wp), dch, tb=True)
         return [(dcc[:, :Hv].contiguous(), dch[:, :Hv].contiguous()),
                 (dcc[:, Hv:].contiguous(), dch[:, Hv:].contiguous())]

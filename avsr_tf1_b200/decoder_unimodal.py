@@ -116,7 +116,7 @@ class Seq2SeqUnimodalDecoder(object):
         init = self._initial_state_fwd(encoder_states)
         self._ids = dec_in_ids.reshape(-1)
         x = ops.empty(T, B, self._E)
-        ops.embedding_fwd(ctx.p(self._embedding), self._ids, x)
+        ops.embedding_fwd(ctx.w(self._embedding), self._ids, x)
         out = self._cell.forward(x, labels_len, memories=memories, init=init)
         O = self._cell.out_dim
         self._out = out
@@ -160,7 +160,7 @@ class Seq2SeqUnimodalDecoder(object):
         samples = []
         for _ in range(hp.max_label_length):
             x = ops.empty(1, B, self._E)
-            ops.embedding_fwd(ctx.p(self._embedding), ids, x)
+            ops.embedding_fwd(ctx.w(self._embedding), ids, x)
             torch.sub(1, finished, out=active)  # finished rows carry their state (impute_finished)
             out, state = self._cell.step(x, active, bufs, state)
             logits = self._logits_step(out)
@@ -181,8 +181,9 @@ class Seq2SeqUnimodalDecoder(object):
         W = hp.beam_width
         B = memories[0][0].shape[1]
         init = self._initial_state_fwd(encoder_states)
-        tiled = [(v.repeat_interleave(W, dim=1).contiguous(), l.repeat_interleave(W).contiguous())
-                 for v, l in memories]  # seq2seq.tile_batch (attention.py:101-106)
+        tiled = [(m[0].repeat_interleave(W, dim=1).contiguous(), m[1].repeat_interleave(W).contiguous(),
+                  m[2].repeat_interleave(W, dim=1).contiguous() if len(m) > 2 and m[2] is not None else None)
+                 for m in memories]  # seq2seq.tile_batch (attention.py:101-106)
         init = (init[0].repeat_interleave(W, dim=0).contiguous(), init[1].repeat_interleave(W, dim=0).contiguous())
         bufs = self._cell.prepare_memories(tiled)
         c, S = self._cell.initial_state(B * W, init)
@@ -196,7 +197,7 @@ class Seq2SeqUnimodalDecoder(object):
         words, parents, scores = [], [], []
         for _ in range(hp.max_label_length):
             x = ops.empty(1, B * W, self._E)
-            ops.embedding_fwd(ctx.p(self._embedding), ids, x)
+            ops.embedding_fwd(ctx.w(self._embedding), ids, x)
             out, (c, S) = self._cell.step(x, active, bufs, (c, S))
             logits = self._logits_step(out)
             word = torch.empty((B, W), dtype=torch.int32, device='cuda')

@@ -10,8 +10,13 @@ from .cells import build_rnn_layers
 from .layers import BatchNormInput, BuildContext, LSTMLayerOp
 
 
-class EncoderData(collections.namedtuple("EncoderData", ("outputs", "final_state"))):
-    pass
+class EncoderData(collections.namedtuple("EncoderData", ("outputs", "final_state", "outputs_operand"))):
+    """outputs / final_state as in the reference (encoder.py:10).  outputs_operand: the same sequence in the
+    form later matrix products read it (tf32-rounded in tensor-core mode; rows past the length unspecified)."""
+
+    def __new__(cls, outputs, final_state, outputs_operand=None):
+        return super(EncoderData, cls).__new__(cls, outputs, final_state,
+                                               outputs if outputs_operand is None else outputs_operand)
 
 
 def maybe_list(obj):
@@ -95,23 +100,30 @@ class Seq2SeqEncoder(object):
         train = self._mode == 'train'
         ctx = self._ctx
         self._lens = inputs_len
-        x = self._bn.forward(inputs, train) if self._bn is not None else inputs
-        cur = x
+        if self._bn is not None:
+            x = self._bn.forward(inputs, train)  # already a product operand (tf32-rounded in tensor-core mode)
+        else:
+            x = ops.round_tf32(inputs) if ops.tensor_cores_enabled() else inputs
+        cur, cur_op = None, x
         for op in self._fw:
-            cur = op.forward(cur, inputs_len)
+            cur = op.forward(cur_op, inputs_len)
+            cur_op = op.operand
         if self._bw is None:
             self._outputs = cur
+            self._outputs_op = cur_op
             self._final = self._fw[-1].final
         else:
-            curb = ops.reverse_sequence(x, inputs_len)
+            curb, curb_op = None, ops.reverse_sequence(x, inputs_len)
             for op in self._bw:
-                curb = op.forward(curb, inputs_len)
+                curb = op.forward(curb_op, inputs_len)
+                curb_op = op.operand
             outb = ops.reverse_sequence(curb, inputs_len)
             T, B, H = cur.shape
             out = ops.empty(T, B, 2 * H)
             out[:, :, :H].copy_(cur)
             out[:, :, H:].copy_(outb)
             self._outputs = out
+            self._outputs_op = ops.round_tf32(out) if ops.tensor_cores_enabled() else out
             cf, hf = self._fw[-1].final
             cb, hb = self._bw[-1].final
             self._cat_c = ops.empty(B, 2 * H)
@@ -120,13 +132,13 @@ class Seq2SeqEncoder(object):
             self._cat_h[:, :H].copy_(hf); self._cat_h[:, H:].copy_(hb)
             dec = self._hparams.decoder_units_per_layer[0]
             pc, ph = ops.empty(B, dec), ops.empty(B, dec)
-            ops.gemm(self._cat_c, ctx.p(self._proj[-2]), pc)
-            ops.gemm(self._cat_h, ctx.p(self._proj[-1]), ph)
+            ops.gemm(self._cat_c, ctx.w(self._proj[-2]), pc)
+            ops.gemm(self._cat_h, ctx.w(self._proj[-1]), ph)
             self._final = (pc, ph)
         return self.get_data()
 
     def get_data(self):
-        return EncoderData(outputs=self._outputs, final_state=self._final)
+        return EncoderData(outputs=self._outputs, final_state=self._final, outputs_operand=self._outputs_op)
 
     def backward(self, doutputs, dfinal_state=None, need_dx=False):
         """doutputs [T,B,out_dim] or None; dfinal_state = (dc, dh) wrt final_state or None."""
@@ -149,8 +161,8 @@ class Seq2SeqEncoder(object):
                 ops.gemm(self._cat_c, dpc, ctx.g(self._proj[-2]), ta=True, beta=1.0)
                 ops.gemm(self._cat_h, dph, ctx.g(self._proj[-1]), ta=True, beta=1.0)
                 dcc, dch = ops.empty(B, H2), ops.empty(B, H2)
-                ops.gemm(dpc, ctx.p(self._proj[-2]), dcc, tb=True)
-                ops.gemm(dph, ctx.p(self._proj[-1]), dch, tb=True)
+                ops.gemm(dpc, ctx.w(self._proj[-2]), dcc, tb=True)
+                ops.gemm(dph, ctx.w(self._proj[-1]), dch, tb=True)
                 dsf = (dcc[:, :H].contiguous(), dch[:, :H].contiguous())
                 dsb = (dcc[:, H:].contiguous(), dch[:, H:].contiguous())
             df = doutputs[:, :, :H].contiguous()
@@ -200,14 +212,21 @@ class AttentiveEncoder(Seq2SeqEncoder):
         self._bw = None
         self.output_dim = self._top.out_dim
 
-    def forward(self, inputs, inputs_len, attended_memory=None, attended_memory_length=None):
+    def forward(self, inputs, inputs_len, attended_memory=None, attended_memory_length=None,
+                attended_memory_operand=None):
         train = self._mode == 'train'
         self._lens = inputs_len
-        x = self._bn.forward(inputs, train) if self._bn is not None else inputs
-        cur = x
+        if self._bn is not None:
+            x = self._bn.forward(inputs, train)
+        else:
+            x = ops.round_tf32(inputs) if ops.tensor_cores_enabled() else inputs
+        cur_op = x
         for op in self._fw:
-            cur = op.forward(cur, inputs_len)
-        self._outputs = self._top.forward(cur, inputs_len, memories=[(attended_memory, attended_memory_length)])
+            op.forward(cur_op, inputs_len)
+            cur_op = op.operand
+        self._outputs = self._top.forward(
+            cur_op, inputs_len, memories=[(attended_memory, attended_memory_length, attended_memory_operand)])
+        self._outputs_op = self._top.operand
         self._final = self._top.final  # wrapper stripped: cell state only (encoder.py:314-330)
         self.attention_alignment = self._top.bufs[0].align  # [T_audio, B, T_video]
         self.attention_contexts = self._top.bufs[0].hc      # [T_audio, B, H + Dm]

@@ -35,6 +35,10 @@ class BuildContext:
     def g(self, name):
         return self.store.g(name)
 
+    def w(self, name):
+        """Parameter as the operand of a matrix product (tf32-rounded copy in tensor-core mode)."""
+        return self.store.w(name, ops.tensor_cores_enabled())
+
 
 class BatchNormInput:
     """tf.layers.batch_normalization(axis=-1) on the raw features (encoder.py:44-50):
@@ -95,26 +99,30 @@ class LSTMLayerOp:
         self.bias = ctx.declare(prefix + '/bias', (4 * H,), 'zeros')
 
     def forward(self, x: torch.Tensor, lens: torch.Tensor):
+        """x [T,B,I] must be a product operand (tf32-rounded in tensor-core mode).  Returns the exact
+        outputs (zero past the length); `self.operand` is the same sequence as the NEXT product's operand
+        (rounded h; rows past the length carry the last state instead of zero, which no consumer reads)."""
         T, B, I = x.shape
         H = self.H
-        W, b = self.ctx.p(self.kernel), self.ctx.p(self.bias)
+        W, b = self.ctx.w(self.kernel), self.ctx.p(self.bias)
         gates = ops.empty(T, B, 4 * H)
-        ops.gemm(x.view(T * B, I), W[:I], gates.view(T * B, 4 * H), bias=b)
+        ops.gemm(x.reshape(T * B, I), W[:I], gates.view(T * B, 4 * H), bias=b)
         self.x = x
         self.rnn = ops.RnnSeq(T, B, H, lens, gates, W[I:])
         out = self.rnn.forward()
         self.final = (self.rnn.cT, self.rnn.hT)
+        self.operand = self.rnn.S[1:]
         return out
 
     def backward(self, dout, dstate=None, need_dx=True):
         T, B, I = self.x.shape
         H = self.H
-        W = self.ctx.p(self.kernel)
+        W = self.ctx.w(self.kernel)
         gW, gb = self.ctx.g(self.kernel), self.ctx.g(self.bias)
         dcT, dhT = dstate if dstate is not None else (None, None)
         dZ = self.rnn.backward(dout, gW[I:], dcT=dcT, dhT=dhT)
         dZ2 = dZ.view(T * B, 4 * H)
-        ops.gemm(self.x.view(T * B, I), dZ2, gW[:I], ta=True, beta=1.0)
+        ops.gemm(self.x.reshape(T * B, I), dZ2, gW[:I], ta=True, beta=1.0)
         ops.colsum(dZ2, gb)
         dx = None
         if need_dx:
@@ -164,19 +172,23 @@ class AttnLSTMOp:
         """keys = memory_layer(values), once per batch (TF computes them at construction)."""
         ctx = self.ctx
         bufs = []
-        for md, (values, mem_len) in zip(self.mechs, memories):
+        for md, mem in zip(self.mechs, memories):
+            values, mem_len = mem[0], mem[1]
+            values_op = mem[2] if len(mem) > 2 and mem[2] is not None else values
             Tm, B, Dm = values.shape
             keys = ops.empty(Tm, B, md.A)
-            ops.gemm(values.view(Tm * B, Dm), ctx.p(md.Wm), keys.view(Tm * B, md.A))
+            ops.gemm(values_op.reshape(Tm * B, Dm), ctx.w(md.Wm), keys.view(Tm * B, md.A))
             v = ctx.p(md.v) if md.v else None
             if md.kind == 'normed_bahdanau':
                 veff = ops.empty(md.A)
                 ops.normed_v_fwd(ctx.p(md.v), ctx.p(md.g), veff)
                 v = veff
-            bufs.append(ops.MechBuffers(md.kind, values, keys, mem_len, ctx.p(md.Wl),
-                                        Wq=ctx.p(md.Wq) if md.Wq else None, v=v,
-                                        g=ctx.p(md.g) if md.kind == 'scaled_luong' else None,
-                                        bias=ctx.p(md.b) if md.b else None))
+            mb = ops.MechBuffers(md.kind, values, keys, mem_len, ctx.w(md.Wl),
+                                 Wq=ctx.w(md.Wq) if md.Wq else None, v=v,
+                                 g=ctx.p(md.g) if md.kind == 'scaled_luong' else None,
+                                 bias=ctx.p(md.b) if md.b else None)
+            mb.values_op = values_op
+            bufs.append(mb)
         return bufs
 
     def forward(self, x, lens, memories=None, init=None, mech_bufs=None):
@@ -184,15 +196,18 @@ class AttnLSTMOp:
         T, B, Dx = x.shape
         H = self.H
         ctx = self.ctx
-        W, b = ctx.p(self.kernel), ctx.p(self.bias)
+        W, b = ctx.w(self.kernel), ctx.p(self.bias)
         gates = ops.empty(T, B, 4 * H)
-        ops.gemm(x.view(T * B, Dx), W[:Dx], gates.view(T * B, 4 * H), bias=b)
+        ops.gemm(x.reshape(T * B, Dx), W[:Dx], gates.view(T * B, 4 * H), bias=b)
         self.x = x
         self.bufs = mech_bufs if mech_bufs is not None else self.prepare_memories(memories)
         c0, h0 = init if init is not None else (None, None)
         self.rnn = ops.RnnSeq(T, B, H, lens, gates, W[Dx:], self.bufs, self.output_attention, c0=c0, h0=h0)
         out = self.rnn.forward()
         self.final = (self.rnn.cT, self.rnn.hT)
+        # operand view of the outputs: the attention vectors are already tf32-rounded (and masked) when they
+        # are the output; otherwise the rounded h columns of the state rows
+        self.operand = out if self.output_attention else self.rnn.S[1:, :, self.At:]
         return out
 
     def step(self, x1, active, mech_bufs, state):
@@ -200,7 +215,7 @@ class AttnLSTMOp:
         emit zeros: impute_finished); state = (c [B,H], S [B,At+H]).  Returns (out [B,O], new state)."""
         _, B, Dx = x1.shape
         H = self.H
-        W, b = self.ctx.p(self.kernel), self.ctx.p(self.bias)
+        W, b = self.ctx.w(self.kernel), self.ctx.p(self.bias)
         gates = ops.empty(1, B, 4 * H)
         ops.gemm(x1.view(B, Dx), W[:Dx], gates.view(B, 4 * H), bias=b)
         c, S = state
@@ -223,7 +238,7 @@ class AttnLSTMOp:
         ctx = self.ctx
         T, B, Dx = self.x.shape
         H = self.H
-        W = ctx.p(self.kernel)
+        W = ctx.w(self.kernel)
         gW, gb = ctx.g(self.kernel), ctx.g(self.bias)
         dveff = {}
         for k, (md, mb) in enumerate(zip(self.mechs, self.bufs)):
@@ -243,7 +258,7 @@ class AttnLSTMOp:
         dcT, dhT = dstate if dstate is not None else (None, None)
         dZ = self.rnn.backward(dout, gW[Dx:], dcT=dcT, dhT=dhT, want_init_grad=want_init_grad)
         dZ2 = dZ.view(T * B, 4 * H)
-        ops.gemm(self.x.view(T * B, Dx), dZ2, gW[:Dx], ta=True, beta=1.0)
+        ops.gemm(self.x.reshape(T * B, Dx), dZ2, gW[:Dx], ta=True, beta=1.0)
         ops.colsum(dZ2, gb)
         dx = None
         if need_dx:
@@ -251,10 +266,10 @@ class AttnLSTMOp:
             ops.gemm(dZ2, W[:Dx], dx.view(T * B, Dx), tb=True)
         dmem = []
         for k, (md, mb) in enumerate(zip(self.mechs, self.bufs)):
-            v2 = mb.values.view(mb.Tm * B, mb.Dm)
+            v2 = mb.values_op.reshape(mb.Tm * B, mb.Dm)
             dk2 = mb.dkeys.view(mb.Tm * B, mb.A)
             ops.gemm(v2, dk2, ctx.g(md.Wm), ta=True, beta=1.0)  # dWm
-            ops.gemm(dk2, ctx.p(md.Wm), mb.dvalues.view(mb.Tm * B, mb.Dm), tb=True, beta=1.0)
+            ops.gemm(dk2, ctx.w(md.Wm), mb.dvalues.view(mb.Tm * B, mb.Dm), tb=True, beta=1.0)
             dmem.append(mb.dvalues)
             if k in dveff:
                 ops.normed_v_bwd(ctx.p(md.v), ctx.p(md.g), dveff[k], ctx.g(md.v), ctx.g(md.g))

@@ -35,6 +35,19 @@ def set_tensor_cores(enable: bool) -> bool:
     return bool(_lib.load().avsr_set_tensor_cores(1 if enable else 0))
 
 
+def tensor_cores_enabled() -> bool:
+    return bool(_lib.load().avsr_get_tensor_cores())
+
+
+def round_tf32(src: torch.Tensor, dst: torch.Tensor = None) -> torch.Tensor:
+    """Round-to-nearest fp32 -> tf32 (the operand format of the tcgen05 products)."""
+    src = src.contiguous()
+    if dst is None:
+        dst = torch.empty_like(src)
+    check(_lib.load().avsr_round_tf32(_stream(), src.data_ptr(), dst.data_ptr(), src.numel()))
+    return dst
+
+
 def empty(*shape, dtype=torch.float32):
     return torch.empty(*shape, dtype=dtype, device='cuda')
 
@@ -43,7 +56,8 @@ def zeros(*shape, dtype=torch.float32):
     return torch.zeros(*shape, dtype=dtype, device='cuda')
 
 
-def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, ta=False, tb=False, beta=0.0, bias=None):
+def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, ta=False, tb=False, beta=0.0, bias=None,
+         round_out=False):
     """out[M,N] = beta*out + op(A) op(B) (+bias).  2-D tensors, unit inner stride, any row stride."""
     _chk_f32(A, B, out, bias)
     assert A.dim() == 2 and B.dim() == 2 and out.dim() == 2
@@ -53,7 +67,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, ta=False, tb=False
     assert K == K2, f'gemm inner dims differ: {K} vs {K2}'
     assert tuple(out.shape) == (M, N), f'gemm out shape {tuple(out.shape)} != {(M, N)}'
     check(_lib.load().avsr_gemm(_stream(), int(ta), int(tb), M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(),
-                                B.stride(0), out.data_ptr(), out.stride(0), float(beta), _p(bias)))
+                                B.stride(0), out.data_ptr(), out.stride(0), float(beta), _p(bias), int(round_out)))
     return out
 
 
@@ -141,12 +155,13 @@ def axpy(a, x, y):
     check(_lib.load().avsr_axpy(_stream(), float(a), x.data_ptr(), y.data_ptr(), x.numel()))
 
 
-def adam_clip_step(params, grads, m, v, sumsq_dev, clip_norm, lr_t, beta1=0.9, beta2=0.999, eps=1e-8):
+def adam_clip_step(params, grads, m, v, sumsq_dev, clip_norm, lr_t, beta1=0.9, beta2=0.999, eps=1e-8,
+                   params_tf32=None):
     """lr_t: device scalar tensor (or a float, copied to the device)."""
     lr = _dev_scalar(lr_t)
     check(_lib.load().avsr_adam_clip_step(_stream(), params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(),
                                           params.numel(), sumsq_dev.data_ptr(), float(clip_norm), lr.data_ptr(),
-                                          beta1, beta2, eps))
+                                          beta1, beta2, eps, _p(params_tf32)))
 
 
 def normed_v_fwd(v, g, veff):

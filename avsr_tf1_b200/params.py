@@ -71,6 +71,9 @@ class ParamStore:
         self.numel = off
         self.n_trainable = sum(int(np.prod(s.shape)) if len(s.shape) else 1 for s in specs if s.trainable)
         self.flat = torch.zeros(max(off, ALIGN), dtype=torch.float32, device=device)
+        # tf32-rounded copy of the parameters: the operand the tcgen05 products read (kept in sync by the
+        # Adam kernel; refreshed by sync_tf32() after initialisation / restore)
+        self.flat_tc = torch.zeros_like(self.flat)
         self.grad = torch.zeros_like(self.flat) if with_optimizer else None
         self.m = torch.zeros_like(self.flat) if with_optimizer else None
         self.v = torch.zeros_like(self.flat) if with_optimizer else None
@@ -85,6 +88,17 @@ class ParamStore:
     def p(self, name) -> torch.Tensor:
         return self.state[name] if name in self.state else self._view(self.flat, name)
 
+    def w(self, name, rounded: bool) -> torch.Tensor:
+        """Parameter as a matrix-product operand: the tf32-rounded copy in tensor-core mode."""
+        if name in self.state or not rounded:
+            return self.p(name)
+        return self._view(self.flat_tc, name)
+
+    def sync_tf32(self):
+        if self.flat.is_cuda:
+            from . import ops
+            ops.round_tf32(self.flat, self.flat_tc)
+
     def g(self, name) -> torch.Tensor:
         return self._view(self.grad, name)
 
@@ -94,6 +108,7 @@ class ParamStore:
     def initialize(self, seed: int, vocab: int = 31):
         for s in self.specs:
             self.p(s.name).copy_(torch.from_numpy(init_array(s, seed, vocab)).view(self.p(s.name).shape))
+        self.sync_tf32()
 
     def load_numpy(self, arrays: Dict[str, np.ndarray], strict=True):
         for s in self.specs:
@@ -102,6 +117,7 @@ class ParamStore:
                 self.p(s.name).copy_(torch.from_numpy(a).reshape(self.p(s.name).shape))
             elif strict:
                 raise KeyError('missing variable ' + s.name)
+        self.sync_tf32()
 
     def to_numpy(self, what='p') -> Dict[str, np.ndarray]:
         out = {}

@@ -48,7 +48,7 @@ class Saver(object):
     def restore(self, sess=None, save_path=None):
         blob = np.load(save_path if save_path.endswith('.npz') else save_path + '.npz')
         st = self._model.store
-        st.load_numpy({k[4:]: blob[k] for k in blob.files if k.startswith('var/')})
+        st.load_numpy({k[4:]: blob[k] for k in blob.files if k.startswith('var/')})  # also refreshes the tf32 copy
         if st.m is not None and any(k.startswith('adam_m/') for k in blob.files):
             for s in st.specs:
                 if s.trainable:
@@ -251,18 +251,20 @@ class Seq2SeqModel(object):
             if isinstance(self._audio_encoder, AttentiveEncoder):
                 enc['audio'] = self._audio_encoder.forward(b['audio'], b['audio_len'],
                                                            attended_memory=enc['video'].outputs,
-                                                           attended_memory_length=b['video_len'])
+                                                           attended_memory_length=b['video_len'],
+                                                           attended_memory_operand=enc['video'].outputs_operand)
             else:
                 enc['audio'] = self._audio_encoder.forward(b['audio'], b['audio_len'])
         return enc
 
     def _decoder_inputs(self, b, enc):
         if self._hparams.architecture == 'bimodal':
-            mems = [(enc['video'].outputs, b['video_len']), (enc['audio'].outputs, b['audio_len'])]
+            mems = [(enc['video'].outputs, b['video_len'], enc['video'].outputs_operand),
+                    (enc['audio'].outputs, b['audio_len'], enc['audio'].outputs_operand)]
             states = [enc['video'].final_state, enc['audio'].final_state]
         else:
             key = 'audio' if 'audio' in enc else 'video'
-            mems = [(enc[key].outputs, b[key + '_len'])]
+            mems = [(enc[key].outputs, b[key + '_len'], enc[key].outputs_operand)]
             states = [enc[key].final_state]
         return mems, states
 
@@ -322,7 +324,7 @@ class Seq2SeqModel(object):
         hp, st = self._hparams, self.store
         clip = hp.max_gradient_norm if hp.clip_gradients is True else 0.0
         ops.adam_clip_step(st.flat, st.grad, st.m, st.v, self._loss_dev[2:3], clip, self._scal_dev[1:2], 0.9, 0.999,
-                           1e-8)
+                           1e-8, params_tf32=st.flat_tc)
 
     def _set_step_scalars(self):
         """Host scalars of this step -> device (outside any captured graph)."""
@@ -350,11 +352,11 @@ class Seq2SeqModel(object):
         """Capture one whole training step (thousands of launches) into a CUDA graph.  A throw-away eager
         step warms every kernel first; parameters, Adam slots and BN statistics are restored after it."""
         st = self.store
-        snap = [t.clone() for t in (st.flat, st.m, st.v)] + [v.clone() for v in st.state.values()]
+        snap = [t.clone() for t in (st.flat, st.flat_tc, st.m, st.v)] + [v.clone() for v in st.state.values()]
         n0 = ops.launch_count()
         self._step_body()
         torch.cuda.synchronize()
-        for dst, src in zip([st.flat, st.m, st.v] + list(st.state.values()), snap):
+        for dst, src in zip([st.flat, st.flat_tc, st.m, st.v] + list(st.state.values()), snap):
             dst.copy_(src)
         n1 = ops.launch_count()
         g = torch.cuda.CUDAGraph()

@@ -33,15 +33,23 @@ int avsr_version(void);
 unsigned long long avsr_launch_count(void);
 /* 1 if the tcgen05 tensor-core GEMM path is enabled (default), 0 = exact fp32 CUDA cores */
 int avsr_set_tensor_cores(int enable);
+int avsr_get_tensor_cores(void);
+/* Precision modes.  tensor cores ON (default): big products run on tcgen05 kind::tf32 with fp32
+ * accumulation; every operand is rounded to tf32 (round-to-nearest) by the kernel that produces it
+ * (weights: avsr_round_tf32 / the copy avsr_adam_clip_step maintains), so the hardware's truncation is a
+ * no-op.  OFF: exact fp32 everywhere on CUDA cores. */
+int avsr_round_tf32(avsr_stream_t stream, const float* src, float* dst, long long n);
 
 /* ---- dense products: tf.matmul / tf.layers.dense call sites ------------------
  * (LSTMCell kernel product cells.py:14; memory_layer attention.py:26; my_dense
  * decoder_unimodal.py:112; state projections encoder.py:134-137,
  * decoder_bimodal.py:480-492; and their tf.gradients counterparts seq2seq.py:222)
  * C[M,N](ldc) = beta*C + op(A) op(B) (+ bias[N]);  beta in {0,1}
- * transA=0: A is [M,K] row-major (lda); transA=1: A is stored [K,M].  Same for B. */
+ * transA=0: A is [M,K] row-major (lda); transA=1: A is stored [K,M].  Same for B.
+ * round_out=1 (beta=0 only, tensor-core mode only): C is stored tf32-rounded because it is itself
+ * the operand of a later tensor-core product (the attention vector). */
 int avsr_gemm(avsr_stream_t stream, int transA, int transB, int M, int N, int K, const float* A, int lda,
-              const float* B, int ldb, float* C, int ldc, float beta, const float* bias);
+              const float* B, int ldb, float* C, int ldc, float beta, const float* bias, int round_out);
 /* out[N] += column sums of X[M,N] (ldx)  (bias gradients) */
 int avsr_colsum(avsr_stream_t stream, const float* X, int M, int N, int ldx, float* out);
 
@@ -52,6 +60,7 @@ int avsr_bn_stats(avsr_stream_t stream, const float* x, long long rows, int F, f
 int avsr_bn_apply_train(avsr_stream_t stream, const float* x, long long rows, int F, const float* sums,
                         double count, const float* gamma, const float* beta, float eps, float momentum,
                         float* y, float* xhat, float* invstd /*[F]*/, float* moving_mean, float* moving_var);
+/* y of both apply calls is tf32-rounded in tensor-core mode (it only feeds the layer-0 gate product) */
 int avsr_bn_apply_eval(avsr_stream_t stream, const float* x, long long rows, int F, const float* gamma,
                        const float* beta, const float* moving_mean, const float* moving_var, float eps, float* y);
 /* backward: sums2 = [sum dy, sum dy*xhat] (all-reducible), then dx */
@@ -159,7 +168,7 @@ int avsr_axpy(avsr_stream_t stream, float a, const float* x, float* y, long long
  * squared global norm (device scalar); lr_t already contains the bias correction. */
 int avsr_adam_clip_step(avsr_stream_t stream, float* params, const float* grads, float* m, float* v, long long n,
                         const float* sumsq_dev, float clip_norm, const float* lr_t_dev, float beta1, float beta2,
-                        float eps);
+                        float eps, float* params_tf32 /* tf32-rounded copy kept in sync, or NULL */);
 
 /* ---- inference helpers (decoder_unimodal.py:176-271) -------------------------- */
 /* greedy: ids[b] = argmax_v logits[b,:] (lowest index on ties) unless finished[b]; updates finished */
