@@ -45,12 +45,12 @@ extern unsigned long long g_launch_count;  // kernels launched by this library
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- device helpers ---------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // tanh via exp: accurate to ~1e-7 relative (tanh.approx is only ~5e-4)
 __device__ __forceinline__ float tanhf_acc(float x) {
   float ax = fabsf(x);
   float e = __expf(-2.0f * ax);
-  float r = (1.0f - e) / (1.0f + e);
+  float r = __fdividef(1.0f - e, 1.0f + e);
   return copysignf(r, x);
 }
 

@@ -141,176 +141,20 @@ __global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __r
   dst[r * ldd + c] = src ? src[r * lds + c] : 0.0f;
 }
 
-// --------------------------------------------------------------------------- //
-// attention: score -> masked softmax -> context, one CTA per utterance
-// --------------------------------------------------------------------------- //
-constexpr int ATT_THREADS = 256;
-
-__global__ void __launch_bounds__(ATT_THREADS)
-attn_fwd_kernel(int kind, int Tm, int B, int Dm, int A, const float* __restrict__ q, int ldq,
-                const float* __restrict__ keys, const float* __restrict__ values, const int* __restrict__ mem_len,
-                const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ bias,
-                float* __restrict__ align_t, float* __restrict__ ctx_out, int ldctx, int rnd) {
-  extern __shared__ float sm[];
-  float* q_s = sm;            // A
-  float* v_s = q_s + A;       // A
-  float* sc = v_s + A;        // Tm
-  float* red = sc + Tm;       // 33
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int L = min(mem_len[b], Tm);
-  const bool luong = kind <= AVSR_ATTN_SCALED_LUONG;
-  for (int u = tid; u < A; u += ATT_THREADS) {
-    q_s[u] = q[(size_t)b * ldq + u] + ((!luong && bias) ? bias[u] : 0.0f);
-    v_s[u] = luong ? 0.0f : v[u];
-  }
-  __syncthreads();
-  const float gs = (kind == AVSR_ATTN_SCALED_LUONG) ? g[0] : 1.0f;
-  for (int tm = warp; tm < L; tm += ATT_THREADS / 32) {
-    const float* kr = keys + ((size_t)tm * B + b) * A;
-    float acc = 0.0f;
-    if (luong) {
-      for (int u = lane; u < A; u += 32) acc = fmaf(kr[u], q_s[u], acc);
-    } else {
-      for (int u = lane; u < A; u += 32) acc = fmaf(v_s[u], tanhf_acc(kr[u] + q_s[u]), acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) sc[tm] = gs * acc;
-  }
-  __syncthreads();
-  float mx = -INFINITY;
-  for (int tm = tid; tm < L; tm += ATT_THREADS) mx = fmaxf(mx, sc[tm]);
-  mx = block_max(mx, red);
-  float sum = 0.0f;
-  for (int tm = tid; tm < L; tm += ATT_THREADS) {
-    float e = __expf(sc[tm] - mx);
-    sc[tm] = e;
-    sum += e;
-  }
-  sum = block_sum(sum, red);
-  const float inv = L > 0 ? 1.0f / sum : 0.0f;
-  for (int tm = tid; tm < Tm; tm += ATT_THREADS) {
-    float a = tm < L ? sc[tm] * inv : 0.0f;
-    sc[tm] = a;
-    align_t[(size_t)b * Tm + tm] = a;
-  }
-  __syncthreads();
-  for (int d = tid; d < Dm; d += ATT_THREADS) {
-    const float* vp = values + (size_t)b * Dm + d;
-    const size_t stride = (size_t)B * Dm;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int tm = 0;
-    for (; tm + 3 < L; tm += 4) {
-      a0 = fmaf(sc[tm], vp[(size_t)tm * stride], a0);
-      a1 = fmaf(sc[tm + 1], vp[(size_t)(tm + 1) * stride], a1);
-      a2 = fmaf(sc[tm + 2], vp[(size_t)(tm + 2) * stride], a2);
-      a3 = fmaf(sc[tm + 3], vp[(size_t)(tm + 3) * stride], a3);
-    }
-    for (; tm < L; ++tm) a0 = fmaf(sc[tm], vp[(size_t)tm * stride], a0);
-    ctx_out[(size_t)b * ldctx + d] = maybe_tf32((a0 + a1) + (a2 + a3), rnd);
-  }
-}
-
-// Backward of attn_fwd for one query step.  dctx [B,Dm](lddctx).  Writes dq_out [B,A]
-// (gradient wrt q: h for Luong, processed query for Bahdanau) and accumulates
-// dkeys, dvalues (context path only), dv, dg, dbias.
-__global__ void __launch_bounds__(ATT_THREADS)
-attn_bwd_kernel(int kind, int t, const int* __restrict__ seq_len, int Tm, int B, int Dm, int A,
-                const float* __restrict__ q, int ldq, const float* __restrict__ keys,
-                const float* __restrict__ values, const int* __restrict__ mem_len, const float* __restrict__ v,
-                const float* __restrict__ g, const float* __restrict__ bias, const float* __restrict__ align_t,
-                const float* __restrict__ dctx, int lddctx, float* __restrict__ dq_out, int lddq,
-                float* __restrict__ dkeys, float* __restrict__ dvalues, float* __restrict__ dv,
-                float* __restrict__ dg, float* __restrict__ dbias, int rnd) {
-  extern __shared__ float sm[];
-  float* q_s = sm;             // A
-  float* v_s = q_s + A;        // A
-  float* dctx_s = v_s + A;     // Dm
-  float* a_s = dctx_s + Dm;    // Tm
-  float* ds_s = a_s + Tm;      // Tm
-  float* raw_s = ds_s + Tm;    // Tm
-  float* red = raw_s + Tm;     // 33
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (t >= seq_len[b]) {  // masked step: no gradient flows
-    for (int u = tid; u < A; u += ATT_THREADS) dq_out[(size_t)b * lddq + u] = 0.0f;
-    return;
-  }
-  const int L = min(mem_len[b], Tm);
-  const bool luong = kind <= AVSR_ATTN_SCALED_LUONG;
-  for (int u = tid; u < A; u += ATT_THREADS) {
-    q_s[u] = q[(size_t)b * ldq + u] + ((!luong && bias) ? bias[u] : 0.0f);
-    v_s[u] = luong ? 0.0f : v[u];
-  }
-  for (int d = tid; d < Dm; d += ATT_THREADS) dctx_s[d] = dctx[(size_t)b * lddctx + d];
-  for (int tm = tid; tm < Tm; tm += ATT_THREADS) a_s[tm] = align_t[(size_t)b * Tm + tm];
-  __syncthreads();
-  for (int tm = warp; tm < L; tm += ATT_THREADS / 32) {
-    const size_t row = (size_t)tm * B + b;
-    const float* vr = values + row * Dm;
-    float* dvr = dvalues + row * Dm;
-    const float a = a_s[tm];
-    float acc = 0.0f;
-    for (int d = lane; d < Dm; d += 32) {
-      acc = fmaf(dctx_s[d], vr[d], acc);
-      dvr[d] += a * dctx_s[d];
-    }
-    acc = warp_sum(acc);
-    float raw = 0.0f;
-    if (kind == AVSR_ATTN_SCALED_LUONG) {
-      const float* kr = keys + row * A;
-      for (int u = lane; u < A; u += 32) raw = fmaf(kr[u], q_s[u], raw);
-      raw = warp_sum(raw);
-    }
-    if (lane == 0) {
-      ds_s[tm] = acc;
-      raw_s[tm] = raw;
-    }
-  }
-  __syncthreads();
-  float dot = 0.0f;
-  for (int tm = tid; tm < L; tm += ATT_THREADS) dot = fmaf(a_s[tm], ds_s[tm], dot);
-  dot = block_sum(dot, red);
-  float gsum = 0.0f;
-  const float gs = (kind == AVSR_ATTN_SCALED_LUONG) ? g[0] : 1.0f;
-  for (int tm = tid; tm < L; tm += ATT_THREADS) {
-    float ds = a_s[tm] * (ds_s[tm] - dot);
-    gsum = fmaf(ds, raw_s[tm], gsum);
-    ds_s[tm] = ds * gs;
-  }
-  if (kind == AVSR_ATTN_SCALED_LUONG) {
-    gsum = block_sum(gsum, red);
-    if (tid == 0) atomicAdd(dg, gsum);
-  }
-  __syncthreads();
-  for (int u = tid; u < A; u += ATT_THREADS) {
-    const size_t stride = (size_t)B * A;
-    const float* kp = keys + (size_t)b * A + u;
-    float* dkp = dkeys + (size_t)b * A + u;
-    float dq = 0.0f;
-    if (luong) {
-      const float qu = q_s[u];
-      for (int tm = 0; tm < L; ++tm) {
-        const float ds = ds_s[tm];
-        dq = fmaf(ds, kp[(size_t)tm * stride], dq);
-        dkp[(size_t)tm * stride] += ds * qu;
-      }
-    } else {
-      const float qu = q_s[u], vu = v_s[u];
-      float dvu = 0.0f;
-      for (int tm = 0; tm < L; ++tm) {
-        const float ds = ds_s[tm];
-        const float th = tanhf_acc(kp[(size_t)tm * stride] + qu);
-        const float dE = ds * vu * (1.0f - th * th);
-        dkp[(size_t)tm * stride] += dE;
-        dq += dE;
-        dvu = fmaf(ds, th, dvu);
-      }
-      atomicAdd(dv + u, dvu);
-      if (dbias) atomicAdd(dbias + u, dq);
-      dq = maybe_tf32(dq, rnd);  // d(processed query) feeds dpq Wq^T and h^T dpq
-    }
-    dq_out[(size_t)b * lddq + u] = dq;
-  }
-}
+// attention kernels live in attention.cu
+size_t attn_fwd_smem(int Tm, int A);
+int attn_fwd(cudaStream_t st, int kind, int Tm, int B, int Dm, int A, const float* q, int ldq, const float* keys,
+             const float* values, const int* mem_len, const float* v, const float* g, const float* bias,
+             float* align_t, float* ctx_out, int ldctx, int rnd);
+int attn_bwd_step(cudaStream_t st, int kind, int t, const int* seq_len, int Tm, int B, int Dm, int A, const float* q,
+                  int ldq, const float* keys, const float* values, const int* mem_len, const float* v, const float* g,
+                  const float* bias, const float* align_t, const float* dctx, int lddctx, float* dq_out, int lddq,
+                  float* ds_out, float* dg, int rnd);
+int attn_outer(cudaStream_t st, int T, int B, int Tm, int C, const int* seq_len, const float* w, const float* x,
+               int ldx, const float* scale, float* out);
+int attn_bahdanau_post(cudaStream_t st, int T, int B, int Tm, int A, const int* seq_len, const int* mem_len,
+                       const float* ds, const float* pq, const float* keys, const float* v, const float* bias,
+                       float* dkeys, float* dv, float* dbias);
 
 // --------------------------------------------------------------------------- //
 // host orchestration
@@ -353,14 +197,16 @@ static int check_common(const AvsrRnnSeq* r, int* At_out, int* maxHD, int* maxA)
   return 0;
 }
 
-static size_t attn_fwd_smem(const AvsrAttnMech& m) { return (size_t)(2 * m.A + m.Tm + 33) * sizeof(float); }
-static size_t attn_bwd_smem(const AvsrAttnMech& m) {
-  return (size_t)(2 * m.A + m.Dm + 3 * m.Tm + 33) * sizeof(float);
-}
+
+int lstm_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r);  // lstm_persist.cu
 
 int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   int At, maxHD, maxA;
   AVSR_TRY(check_common(r, &At, &maxHD, &maxA));
+  if (r->n_mech == 0 && tensor_cores_enabled()) {  // persistent cluster kernel (tcgen05, weights resident)
+    const int rc = lstm_persist_fwd(st, r);
+    if (rc >= 0) return rc;
+  }
   const int T = r->T, B = r->B, H = r->H, SW = At + H;
   const int rnd = tensor_cores_enabled();
   WorkLayout wl = work_layout(B, H, At, maxHD, maxA);
@@ -369,11 +215,6 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   const int pw_grid = cdiv((long long)B * H, 256);
   AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->c0, H, cbuf[0], H, B, H);
   int cur = 0;
-  for (int k = 0; k < r->n_mech; ++k) {
-    AVSR_REQUIRE(attn_fwd_smem(r->mech[k]) <= 200 * 1024, "attention: Tm too large for shared memory");
-    if (attn_fwd_smem(r->mech[k]) > 48 * 1024)
-      AVSR_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  }
   for (int t = 0; t < T; ++t) {
     const float* S_t = r->S + (size_t)t * B * SW;
     float* S_n = r->S + (size_t)(t + 1) * B * SW;
@@ -400,8 +241,8 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
         q = pq_t;
         ldq = m.A;
       }
-      AVSR_LAUNCH(attn_fwd_kernel, B, ATT_THREADS, attn_fwd_smem(m), st, m.kind, m.Tm, B, m.Dm, m.A, q, ldq, m.keys,
-                  m.values, m.mem_len, m.v, m.g, m.bias, m.align + (size_t)t * B * m.Tm, hc.p[k] + H, hc.ld[k], rnd);
+      AVSR_TRY(attn_fwd(st, m.kind, m.Tm, B, m.Dm, m.A, q, ldq, m.keys, m.values, m.mem_len, m.v, m.g, m.bias,
+                        m.align + (size_t)t * B * m.Tm, hc.p[k] + H, hc.ld[k], rnd));
       AVSR_TRY(gemm(st, 0, 0, B, m.A, H + m.Dm, hc.p[k], hc.ld[k], m.Wl, m.A, S_n + off, SW, 0.0f, nullptr, 1));
       off += m.A;
     }
@@ -414,27 +255,33 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   return 0;
 }
 
+int lstm_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r);  // lstm_persist.cu
+
 int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   int At, maxHD, maxA;
   AVSR_TRY(check_common(r, &At, &maxHD, &maxA));
   const int T = r->T, B = r->B, H = r->H, SW = At + H;
+  if (r->n_mech == 0 && tensor_cores_enabled()) {
+    const int rc = lstm_persist_bwd(st, r);  // reverse-time recurrence in one persistent cluster kernel
+    if (rc >= 0) {
+      if (rc == 0 && T > 0)  // dWrec += S[0:T]^T @ dZ
+        AVSR_TRY(gemm(st, 1, 0, SW, 4 * H, T * B, r->S, SW, r->dZ, 4 * H, r->dWrec, 4 * H, 1.0f, nullptr));
+      return rc;
+    }
+  }
   const bool oa = r->output_attention && r->n_mech > 0;
   const int rnd = tensor_cores_enabled();
   WorkLayout wl = work_layout(B, H, At, maxHD, maxA);
   float* dS[2] = {r->work + wl.dS, r->work + wl.dS + (size_t)B * SW};
   float* dcb[2] = {r->work + wl.dcbuf, r->work + wl.dcbuf + (size_t)B * H};
-  float* dHC[2] = {r->work + wl.dHC, r->work + wl.dHC + (size_t)B * maxHD};
   const int qw = maxA > H ? maxA : H;
   float* dq[2] = {r->work + wl.dq, r->work + wl.dq + (size_t)B * qw};
   const int pw_grid = cdiv((long long)B * H, 256);
   AVSR_LAUNCH(copy2d_kernel, cdiv((long long)B * SW, 256), 256, 0, st, (const float*)nullptr, 0, dS[0], SW, B, SW);
   AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->dhT, H, dS[0] + At, SW, B, H);
   AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->dcT, H, dcb[0], H, B, H);
-  for (int k = 0; k < r->n_mech; ++k) {
-    AVSR_REQUIRE(attn_bwd_smem(r->mech[k]) <= 200 * 1024, "attention: Tm too large for shared memory");
-    if (attn_bwd_smem(r->mech[k]) > 48 * 1024)
-      AVSR_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  }
+  for (int k = 0; k < r->n_mech; ++k)
+    AVSR_REQUIRE(r->mech[k].ds && r->mech[k].dhc, "rnn bwd: mechanism scratch ds / dhc missing");
   int cur = 0;
   for (int t = T - 1; t >= 0; --t) {
     const float* S_n = r->S + (size_t)(t + 1) * B * SW;
@@ -449,16 +296,17 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
         const AvsrAttnMech& m = r->mech[k];
         const bool luong = m.kind <= AVSR_ATTN_SCALED_LUONG;
         const int HD = H + m.Dm;
-        // d[h | ctx] = dA_m @ Wl^T
-        AVSR_TRY(gemm(st, 0, 1, B, HD, m.A, dA_t + off, At, m.Wl, m.A, dHC[k], HD, 0.0f, nullptr));
+        // d[h | ctx] = dA_m @ Wl^T   (kept for all steps: dvalues is formed after the loop)
+        float* dHC_t = m.dhc + (size_t)t * B * HD;
+        AVSR_TRY(gemm(st, 0, 1, B, HD, m.A, dA_t + off, At, m.Wl, m.A, dHC_t, HD, 0.0f, nullptr));
         const float* q = luong ? S_n + At : m.pq + (size_t)t * B * m.A;
         const int ldq = luong ? SW : m.A;
         float* dq_out = luong ? dq[k] : m.dpq + (size_t)t * B * m.A;
-        AVSR_LAUNCH(attn_bwd_kernel, B, ATT_THREADS, attn_bwd_smem(m), st, m.kind, t, r->len, m.Tm, B, m.Dm, m.A, q,
-                    ldq, m.keys, m.values, m.mem_len, m.v, m.g, m.bias, m.align + (size_t)t * B * m.Tm,
-                    dHC[k] + H, HD, dq_out, m.A, m.dkeys, m.dvalues, m.dv, m.dg, m.dbias, rnd);
+        AVSR_TRY(attn_bwd_step(st, m.kind, t, r->len, m.Tm, B, m.Dm, m.A, q, ldq, m.keys, m.values, m.mem_len, m.v,
+                               m.g, m.bias, m.align + (size_t)t * B * m.Tm, dHC_t + H, HD, dq_out, m.A,
+                               m.ds + (size_t)t * B * m.Tm, m.dg, rnd));
         if (!luong) AVSR_TRY(gemm(st, 0, 1, B, H, m.A, dq_out, m.A, m.Wq, m.A, dq[k], H, 0.0f, nullptr));
-        extra.p[2 * k] = dHC[k];
+        extra.p[2 * k] = dHC_t;
         extra.ld[2 * k] = HD;
         extra.p[2 * k + 1] = dq[k];
         extra.ld[2 * k + 1] = luong ? m.A : H;
@@ -483,8 +331,16 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
       const AvsrAttnMech& m = r->mech[k];
       const int HD = H + m.Dm;
       AVSR_TRY(gemm(st, 1, 0, HD, m.A, T * B, m.hc, HD, r->dA + off, At, m.dWl, m.A, 1.0f, nullptr));
-      if (m.kind >= AVSR_ATTN_BAHDANAU)
+      // per-utterance accumulations taken off the sequential path
+      AVSR_TRY(attn_outer(st, T, B, m.Tm, m.Dm, r->len, m.align, m.dhc + H, HD, nullptr, m.dvalues));
+      if (m.kind >= AVSR_ATTN_BAHDANAU) {
         AVSR_TRY(gemm(st, 1, 0, H, m.A, T * B, m.hc, HD, m.dpq, m.A, m.dWq, m.A, 1.0f, nullptr));
+        AVSR_TRY(attn_bahdanau_post(st, T, B, m.Tm, m.A, r->len, m.mem_len, m.ds, m.pq, m.keys, m.v, m.bias, m.dkeys,
+                                    m.dv, m.dbias));
+      } else {
+        AVSR_TRY(attn_outer(st, T, B, m.Tm, m.A, r->len, m.ds, m.hc, HD,
+                            m.kind == AVSR_ATTN_SCALED_LUONG ? m.g : nullptr, m.dkeys));
+      }
       off += m.A;
     }
   }

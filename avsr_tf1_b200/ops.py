@@ -205,12 +205,13 @@ class MechBuffers:
         self.A = keys.shape[2]
         self.align = self.hc = self.pq = None
         self.dkeys = self.dvalues = self.dWl = self.dWq = self.dv = self.dg = self.dbias = self.dpq = None
+        self.ds = self.dhc = None
 
     def fill(self, m: AvsrAttnMech):
         m.kind = ATTN_KINDS[self.kind]
         m.Tm, m.Dm, m.A = self.Tm, self.Dm, self.A
         for k in ('values', 'keys', 'mem_len', 'Wl', 'Wq', 'v', 'g', 'bias', 'align', 'hc', 'pq', 'dkeys', 'dvalues',
-                  'dWl', 'dWq', 'dv', 'dg', 'dbias', 'dpq'):
+                  'dWl', 'dWq', 'dv', 'dg', 'dbias', 'dpq', 'ds', 'dhc'):
             setattr(m, k, _p(getattr(self, k)))
 
 
@@ -278,6 +279,8 @@ class RnnSeq:
         for m in self.mechs:
             if 'bahdanau' in m.kind:
                 m.dpq = empty(T, B, m.A)
+            m.ds = empty(T, B, m.Tm)
+            m.dhc = empty(T, B, H + m.Dm)
         r = self._desc(dout=dout, dcT=dcT, dhT=dhT, dZ=self.dZ, dA=self.dA, dWrec=dWrec, dc0=self.dc0, dh0=self.dh0)
         check(_lib.load().avsr_rnn_seq_bwd(_stream(), C.byref(r)))
         return self.dZ

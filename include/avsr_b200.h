@@ -110,6 +110,8 @@ typedef struct AvsrAttnMech {
   float* dg;            /* [1] */
   float* dbias;         /* [A] */
   float* dpq;           /* [T,B,A] scratch */
+  float* ds;            /* [T,B,Tm] scratch: d(score) of every step (dkeys is formed after the loop) */
+  float* dhc;           /* [T,B,H+Dm] scratch: d[cell output | context] of every step */
 } AvsrAttnMech;
 
 typedef struct AvsrRnnSeq {
