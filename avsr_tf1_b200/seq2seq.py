@@ -18,7 +18,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from . import ops
+from . import ops, parallel
 from .decoder_bimodal import Seq2SeqBimodalDecoder
 from .decoder_unimodal import Seq2SeqUnimodalDecoder
 from .encoder import AttentiveEncoder, Seq2SeqEncoder
@@ -70,9 +70,8 @@ class Seq2SeqModel(object):
         if hparams.cell_type != 'lstm':
             raise Exception('cell type not supported: {}'.format(hparams.cell_type))
         self._ctx = BuildContext()
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            self._ctx.world_size = torch.distributed.get_world_size()
-            self._ctx.allreduce = lambda t: torch.distributed.all_reduce(t)
+        self._ctx.world_size = parallel.world_size()
+        self._ctx.allreduce = parallel.allreduce_sum_
 
         self._make_encoders()
         self._make_decoder()
@@ -329,11 +328,9 @@ class Seq2SeqModel(object):
     def _set_step_scalars(self):
         """Host scalars of this step -> device (outside any captured graph)."""
         ctx = self._ctx
-        n_tok = self._meta['n_tokens']
-        if ctx.world_size > 1:  # exact large-batch loss denominator under data parallelism
-            t = torch.tensor([n_tok], dtype=torch.float64, device='cuda')
-            ctx.allreduce(t)
-            n_tok = float(t.item())
+        # exact large-batch loss denominator under data parallelism
+        n_tok = parallel.global_token_count(self._meta['n_tokens'], device='cuda') if ctx.world_size > 1 \
+            else self._meta['n_tokens']
         self._inv_denom = 1.0 / (n_tok + 1e-12)  # seq2seq.sequence_loss
         lr = self._lr_now()
         self.current_lr = lr

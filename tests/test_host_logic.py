@@ -1,0 +1,119 @@
+"""Host-side logic that needs no GPU: the variable table (names / shapes / counts of SURVEY.md 8e),
+hparams defaults, the reference's configuration errors, checkpoint round trip."""
+import numpy as np
+import pytest
+
+from avsr_tf1_b200 import make_hparams
+from avsr_tf1_b200.seq2seq import Seq2SeqModel
+from tests.helpers import config_hparams, synthetic_batch, to_data_sequences
+
+
+def build(cfg, **over):
+    hp = config_hparams(cfg, **over)
+    batch = synthetic_batch(hp, B=2, Ta=6, Tv=4, L=3)
+    return hp, Seq2SeqModel(to_data_sequences(batch), 'train', hp, device='cpu')
+
+
+@pytest.mark.parametrize('cfg,over,count', [
+    (1, {}, 361408),
+    (2, {}, 4639807),
+    (3, dict(attention_type=(('bahdanau',), ('bahdanau',))), 2375839),
+    (3, {}, 2310048),                                                             # scaled-Luong default
+    (4, dict(attention_type=(('bahdanau',), ('bahdanau',))), 4427327),
+    (5, dict(attention_type=(('bahdanau',), ('bahdanau',))), 4296255),
+    (5, {}, 4164673),
+])
+def test_trainable_parameter_counts_match_survey(cfg, over, count):
+    _, m = build(cfg, **over)
+    assert m.n_params == count
+
+
+def test_variable_names_follow_tf_scopes():
+    _, m = build(5, attention_type=(('bahdanau',), ('scaled_luong',)))
+    names = set(m.store.names(trainable_only=False))
+    for n in ['video/batch_normalization/gamma', 'video/batch_normalization/moving_variance',
+              'video/Encoder/multi_rnn_cell/cell_0/lstm_cell/kernel',
+              'audio/Encoder/multi_rnn_cell/cell_2/attention_wrapper/lstm_cell/kernel',
+              'audio/Encoder/multi_rnn_cell/cell_2/attention_wrapper/bahdanau_attention/query_layer/kernel',
+              'audio/Encoder/multi_rnn_cell/cell_2/attention_wrapper/bahdanau_attention/attention_v',
+              'audio/Encoder/multi_rnn_cell/cell_2/attention_wrapper/attention_layer/kernel',
+              'audio/Encoder/memory_layer/kernel', 'embeddings/embedding_matrix', 'Decoder/memory_layer/kernel',
+              'Decoder/decoder/attention_wrapper/lstm_cell/kernel',
+              'Decoder/decoder/attention_wrapper/luong_attention/attention_g',
+              'Decoder/decoder/attention_wrapper/attention_layer/kernel', 'Decoder/decoder/my_dense/kernel',
+              'Decoder/decoder/my_dense/bias']:
+        assert n in names, n
+    assert m.store.p('audio/Encoder/multi_rnn_cell/cell_2/attention_wrapper/lstm_cell/kernel').shape == (768, 1024)
+    assert m.store.p('Decoder/decoder/attention_wrapper/lstm_cell/kernel').shape == (128 + 256 + 256, 1024)
+    _, b = build(4)
+    assert b.store.p('Decoder/state_projection/kernel').shape == (512, 256)
+    assert b.store.p('Decoder/decoder/attention_wrapper/lstm_cell/kernel').shape == (128 + 512 + 256, 1024)
+    _, bi = build(2)
+    assert bi.store.p('audio/Encoder/dense_5/kernel').shape == (512, 256)
+    assert 'audio/Encoder/fw/multi_rnn_cell/cell_1/lstm_cell/kernel' in set(bi.store.names())
+    # L2 filter of seq2seq.py:283-290 selects exactly the LSTM kernels
+    assert sorted(bi._l2_names) == sorted(n for n in bi.store.names() if n.endswith('lstm_cell/kernel'))
+
+
+def test_initialisers():
+    _, m = build(1)
+    P = m.store.to_numpy('p')
+    k = P['audio/Encoder/lstm_cell/kernel']
+    assert abs(k.std() - np.sqrt(1.0 / k.shape[0])) < 0.1 * np.sqrt(1.0 / k.shape[0])
+    assert np.abs(k).max() <= 2.0 * np.sqrt(1.0 / k.shape[0]) / .87962566103423978 + 1e-6  # truncated normal
+    assert np.all(P['audio/Encoder/lstm_cell/bias'] == 0)
+    e = P['embeddings/embedding_matrix']
+    assert e.shape == (31, 128) and np.abs(e).max() <= 1.732 / 31
+    assert float(P['Decoder/decoder/attention_wrapper/luong_attention/attention_g'].reshape(-1)[0]) == 1.0
+    assert np.all(P['audio/batch_normalization/moving_variance'] == 1)
+
+
+def test_hparams_defaults_follow_reference():
+    hp = make_hparams()
+    assert hp.attention_type == (('scaled_luong',), ('scaled_luong',))       # avsr.py:50
+    assert hp.encoder_units_per_layer == ((256,), (256, 256, 256))           # avsr.py:46
+    assert hp.max_label_length == 150 and hp.beam_width == 10 and hp.embedding_size == 128
+    assert hp.recurrent_l2_regularisation == 0.0001 and hp.max_gradient_norm == 1.0
+    assert make_hparams(optimiser='AdamW').recurrent_l2_regularisation is None  # avsr.py:172
+    assert make_hparams(warmup_steps=10).kwargs == {'warmup_steps': 10}
+
+
+@pytest.mark.parametrize('over,exc', [
+    (dict(architecture='nonsense'), Exception),
+    (dict(encoder_type='sideways'), Exception),
+    (dict(cell_type='gru'), Exception),
+    (dict(attention_type=(('cosine',), ('cosine',))), Exception),
+    (dict(decoding_algorithm='viterbi'), Exception),
+    (dict(optimiser='SGD'), Exception),
+    (dict(loss_fun='hinge'), ValueError),
+    (dict(use_dropout=True), NotImplementedError),
+    (dict(sampling_probability_outputs=0.1), NotImplementedError),
+])
+def test_configuration_errors(over, exc):
+    with pytest.raises(exc):
+        build(1, **over)
+
+
+def test_bidirectional_single_layer_is_rejected_like_the_reference():
+    with pytest.raises(ValueError):  # encoder.py:125-133 cannot index a 1-layer state
+        build(1, encoder_type='bidirectional')
+
+
+def test_attentive_encoder_is_unidirectional_only():
+    with pytest.raises(Exception):
+        build(5, encoder_type='bidirectional')
+
+
+def test_checkpoint_round_trip(tmp_path):
+    _, m = build(1)
+    m._global_step = 17
+    m.store.m.normal_()
+    path = m.saver.save(None, str(tmp_path / 'checkpoint.ckp'), global_step=30)
+    assert path.endswith('checkpoint.ckp-30')
+    _, m2 = build(1)
+    m2.store.flat.zero_()
+    m2.saver.restore(None, path)
+    assert m2.global_step == 17
+    a, b = m.store.to_numpy('p'), m2.store.to_numpy('p')
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    assert all(np.array_equal(v, m2.store.to_numpy('m')[k]) for k, v in m.store.to_numpy('m').items())

@@ -1,0 +1,115 @@
+"""Algebraic invariants of the oracle (validation by independent means)."""
+import numpy as np
+
+from oracle import avsr_oracle as O
+
+
+def rnd(seed, *shape):
+    return np.random.default_rng(seed).standard_normal(shape)
+
+
+def test_lstm_cell_hand_case():
+    """H = 1, hand-computed: z = 0 everywhere -> i = o = 0.5, f = sigmoid(1), j = 0."""
+    W, b = np.zeros((2, 4)), np.zeros(4)
+    h, c, _ = O.lstm_cell(np.array([[0.3, -0.2]]), np.array([[0.5]]), W, b)
+    f = 1 / (1 + np.exp(-1.0))
+    assert np.allclose(c, f * 0.5) and np.allclose(h, 0.5 * np.tanh(f * 0.5))
+    # cell clip at 1.0 and gate order i, j, f, o
+    W = np.zeros((2, 4)); b = np.array([50.0, 50.0, 50.0, 50.0])
+    h, c, _ = O.lstm_cell(np.array([[0.0, 0.0]]), np.array([[1.0]]), W, b)
+    assert np.allclose(c, 1.0) and np.allclose(h, np.tanh(1.0))
+
+
+def test_padding_invariance_and_zero_outputs_past_length():
+    B, T, I, H = 3, 7, 4, 5
+    x, W, b = rnd(0, B, T, I), rnd(1, I + H, 4 * H) * 0.5, rnd(2, 4 * H) * 0.1
+    lens = np.array([7, 3, 5])
+    out, (c, h), _ = O.lstm_seq_fwd(x, lens, W, b)
+    x2 = x.copy()
+    x2[1, 3:] = 99.0  # garbage in the padding must not matter
+    out2, (c2, h2), _ = O.lstm_seq_fwd(x2, lens, W, b)
+    assert np.array_equal(out, out2) and np.array_equal(c, c2) and np.array_equal(h, h2)
+    assert np.all(out[1, 3:] == 0) and np.all(out[2, 5:] == 0)
+    assert np.allclose(h[1], out[1, 2]) and np.allclose(h[0], out[0, 6])  # final state = last valid step
+
+
+def test_birnn_backward_direction_is_forward_on_reversed_input():
+    B, T, I, H = 2, 6, 3, 4
+    x = rnd(3, B, T, I)
+    lens = np.array([6, 4])
+    x *= (np.arange(T)[None, :, None] < lens[:, None, None])
+    fw = [(rnd(4, I + H, 4 * H) * 0.4, rnd(5, 4 * H) * 0.1)]
+    bw = [(rnd(6, I + H, 4 * H) * 0.4, rnd(7, 4 * H) * 0.1)]
+    out, (sf, sb), _ = O.birnn_fwd(x, lens, fw, bw)
+    ob, (cb, hb), _ = O.lstm_seq_fwd(O.reverse_sequence(x, lens), lens, *bw[0])
+    assert np.allclose(out[..., H:], O.reverse_sequence(ob, lens))
+    assert np.allclose(sb[0][1], hb)
+    assert np.allclose(out[1, 0, H:], hb[1])  # bw final state sits at t = 0 of the un-reversed output
+
+
+def test_concat_matmul_equals_split_matmul():
+    B, I, H = 4, 6, 5
+    x, h, c = rnd(8, B, I), rnd(9, B, H), rnd(10, B, H) * 0.3
+    W, b = rnd(11, I + H, 4 * H), rnd(12, 4 * H)
+    h1, c1, _ = O.lstm_cell(np.concatenate([x, h], 1), c, W, b)
+    z = x @ W[:I] + h @ W[I:] + b
+    i, j, f, o = np.split(z, 4, axis=1)
+    c2 = np.clip(O.sigmoid(f + 1) * c + O.sigmoid(i) * np.tanh(j), -1, 1)
+    assert np.allclose(c1, c2) and np.allclose(h1, O.sigmoid(o) * np.tanh(c2))
+
+
+def test_attention_alignments_are_masked_distributions():
+    B, T, Dx, H, Tm, Dm = 3, 4, 3, 6, 7, 5
+    for kind in ('luong', 'scaled_luong', 'bahdanau', 'normed_bahdanau'):
+        mem_len = np.array([7, 2, 5])
+        spec = O.AttnSpec(kind=kind, memory=rnd(13, B, Tm, Dm), mem_len=mem_len, Wm=rnd(14, Dm, H), Wl=rnd(15, H + Dm, H),
+                          Wq=rnd(16, H, H), v=rnd(17, H), g=np.asarray(0.8), b=rnd(18, H) * 0.1)
+        r = O.attn_rnn_fwd(rnd(19, B, T, Dx), np.array([4, 4, 2]), rnd(20, Dx + 2 * H, 4 * H) * 0.3, np.zeros(4 * H),
+                           [spec])
+        a = r['alignments'][0]
+        assert np.allclose(a[:2].sum(-1), 1.0) and np.allclose(a[2, :2].sum(-1), 1.0)
+        assert np.all(a[1, :, 2:] == 0) and np.all(a[2, :, 5:] == 0)   # exactly zero past memory_len
+        assert np.all(a[2, 2:] == 0) and np.all(r['outputs'][2, 2:] == 0)  # zero past the query length
+        assert r['outputs'].shape[-1] == H and spec.output_attention == ('luong' in kind)
+
+
+def test_sequence_loss_and_clip_adam_identities():
+    B, T, V = 3, 5, 7
+    logits, lens = rnd(21, B, T, V), np.array([5, 2, 4])
+    targets = np.random.default_rng(22).integers(0, V, (B, T))
+    loss, d = O.sequence_loss_fwd_bwd(logits, targets, lens)
+    manual = 0.0
+    for b in range(B):
+        for t in range(lens[b]):
+            z = logits[b, t]
+            manual += np.log(np.exp(z).sum()) - z[targets[b, t]]
+    assert np.isclose(loss, manual / lens.sum())
+    assert np.all(d[1, 2:] == 0) and np.allclose(d.sum(-1), 0)
+    P = {'w': np.ones(4)}; G = {'w': np.array([3.0, 4.0, 0.0, 0.0])}
+    m, v = {'w': np.zeros(4)}, {'w': np.zeros(4)}
+    gn = O.clip_and_adam(P, G, m, v, 0, 1e-3, clip=1.0, warmup_steps=750)
+    assert np.isclose(gn, 5.0)
+    lr = 1e-3 / 750
+    g = np.array([0.6, 0.8, 0, 0])  # clipped to unit norm
+    lr_t = lr * np.sqrt(1 - 0.999) / (1 - 0.9)
+    assert np.allclose(P['w'], 1 - lr_t * (0.1 * g) / (np.sqrt(0.001 * g * g) + 1e-8))
+
+
+def test_gather_tree_and_beam_shapes_on_tiny_model():
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    from tests.helpers import cast_batch, config_hparams, oracle_hparams, synthetic_batch, to_data_sequences
+    hp = config_hparams(1, units=8, embedding_size=6, beam_width=3)
+    hp.max_label_length = 7
+    batch = synthetic_batch(hp, B=2, Ta=5, Fa=4, L=3)
+    m = Seq2SeqModel(to_data_sequences(batch), 'train', hp, device='cpu')
+    om = O.OracleModel(oracle_hparams(hp), {k: v.astype(np.float64) for k, v in m.store.to_numpy('p').items()})
+    r = om.beam_decode(cast_batch(batch, np.float64))
+    T = r['step_ids'].shape[1]
+    assert r['predicted_ids'].shape == (2, T, 3) and T <= 7
+    assert np.all(np.diff(r['scores'], axis=2) <= 1e-12)  # top_k returns beams best-first
+    g = om.greedy_decode(cast_batch(batch, np.float64))
+    assert g.shape[0] == 2 and g.shape[1] <= 7
+    for row in g:  # after EOS everything is 0 (impute_finished)
+        hits = np.nonzero(row == 29)[0]
+        if hits.size:
+            assert np.all(row[hits[0] + 1:] == 0)

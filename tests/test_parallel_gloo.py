@@ -1,0 +1,86 @@
+"""world_size-2 gloo test (CPU) of the data-parallel exchanges: summed batch-norm statistics, the global
+loss denominator and the gradient all-reduce reproduce the single-rank large-batch values (checked with
+the oracle's arithmetic)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import avsr_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from avsr_tf1_b200 import parallel
+    rng = np.random.default_rng(0)
+    B, T, F, V = 6, 5, 4, 7
+    x = rng.standard_normal((B, T, F))
+    logits = rng.standard_normal((B, T, V))
+    lens = np.array([5, 2, 4, 3, 5, 1])
+    tgt = rng.integers(0, V, (B, T))
+    lo, hi = parallel.shard_batch(B)
+    # (1) input batch-norm statistics: all-reduce [sum, sumsq], count = rows * world
+    xs = torch.from_numpy(x[lo:hi].reshape(-1, F))
+    sums = torch.cat([xs.sum(0), (xs * xs).sum(0)])
+    parallel.allreduce_sum_(sums)
+    count = xs.shape[0] * parallel.world_size()
+    mean = sums[:F] / count
+    var = sums[F:] / count - mean * mean
+    # (2) loss denominator and (3) summed gradients
+    n_tok = parallel.global_token_count(float(lens[lo:hi].sum()))
+    w = O.sequence_mask(lens[lo:hi], T, np.float64)
+    z = logits[lo:hi]
+    logp = z - np.log(np.exp(z).sum(-1, keepdims=True))
+    d = np.exp(logp)
+    np.put_along_axis(d, tgt[lo:hi, :, None], np.take_along_axis(d, tgt[lo:hi, :, None], 2) - 1.0, axis=2)
+    g_local = torch.from_numpy((d * (w / (n_tok + 1e-12))[:, :, None]).sum(0))  # a "parameter gradient"
+    parallel.allreduce_sum_(g_local)
+    if rank == 0:
+        out.put((mean.numpy(), var.numpy(), n_tok, g_local.numpy()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_exchanges_match_single_large_batch():
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    mean, var, n_tok, g = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(0)
+    B, T, F, V = 6, 5, 4, 7
+    x = rng.standard_normal((B, T, F))
+    logits = rng.standard_normal((B, T, V))
+    lens = np.array([5, 2, 4, 3, 5, 1])
+    tgt = rng.integers(0, V, (B, T))
+    _, _, m_ref, v_ref = O.batchnorm_train_fwd(x, np.ones(F), np.zeros(F))
+    assert np.allclose(mean, m_ref) and np.allclose(var, v_ref)
+    assert n_tok == float(lens.sum())
+    _, d_ref = O.sequence_loss_fwd_bwd(logits, tgt, lens)
+    assert np.allclose(g, d_ref.sum(0))
+
+
+def test_shard_batch_covers_everything_once():
+    from avsr_tf1_b200 import parallel
+    for n in (1, 7, 8, 256, 1000):
+        for w in (1, 2, 3, 8):
+            spans = [parallel.shard_batch(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
