@@ -60,7 +60,7 @@ PROTOTYPES = {
     'avsr_bn_bwd_apply': (_I, [_P, _P, _P, _L, _I, _P, _D, _P, _P, _P, _P, _P]),
     'avsr_reverse_sequence': (_I, [_P, _P, _P, _I, _I, _I, _P]),
     'avsr_transpose01': (_I, [_P, _P, _P, _I, _I, _I]),
-    'avsr_rnn_work_floats': (C.c_size_t, [_I, _I, _I, _I, _I]),
+    'avsr_rnn_work_floats': (C.c_size_t, [_I, _I, _I, _I, _I, _I]),
     'avsr_rnn_seq_fwd': (_I, [_P, C.POINTER(AvsrRnnSeq)]),
     'avsr_rnn_seq_bwd': (_I, [_P, C.POINTER(AvsrRnnSeq)]),
     'avsr_normed_v_fwd': (_I, [_P, _P, _P, _I, _P]),

@@ -19,7 +19,7 @@ void set_error(const char* fmt, ...) {
 
 int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r);
 int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r);
-size_t rnn_work_floats(int B, int H, int At, int maxHD, int maxA);
+size_t rnn_work_floats(int B, int H, int At, int maxHD, int maxA, int maxTm);
 // tcgen05 TF32 path (gemm_tc.cu); returns -1 when the shape is not eligible
 int gemm_tc(cudaStream_t st, int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B,
             int ldb, float* C, int ldc, float beta, const float* bias, int round_out);
@@ -56,8 +56,8 @@ int avsr_gemm(avsr_stream_t s, int transA, int transB, int M, int N, int K, cons
 }
 int avsr_get_tensor_cores(void) { return g_use_tc; }
 
-size_t avsr_rnn_work_floats(int B, int H, int At, int maxHD, int maxA) {
-  return rnn_work_floats(B, H, At, maxHD, maxA);
+size_t avsr_rnn_work_floats(int B, int H, int At, int maxHD, int maxA, int maxTm) {
+  return rnn_work_floats(B, H, At, maxHD, maxA, maxTm);
 }
 int avsr_rnn_seq_fwd(avsr_stream_t s, const AvsrRnnSeq* r) { return rnn_seq_fwd((cudaStream_t)s, r); }
 int avsr_rnn_seq_bwd(avsr_stream_t s, const AvsrRnnSeq* r) { return rnn_seq_bwd((cudaStream_t)s, r); }

@@ -7,6 +7,8 @@
 //   i,j,f,o= act(gates_t + rec); c,h update with length masking  (lstm_point_fwd)
 //   per mechanism: (pq = h @ Wq) ; score -> softmax -> context   (attn_fwd)
 //                  attention_m = [h | ctx] @ Wl                  (gemm)
+#include <stdlib.h>
+
 #include "../../include/avsr_b200.h"
 #include "common.cuh"
 
@@ -133,6 +135,17 @@ __global__ void emit_attention_kernel(int t, int B, int At, int SW, const int* _
   out_t[idx] = t < len[b] ? S_next[(size_t)b * SW + a] : 0.0f;
 }
 
+// all steps at once: rows = T*Bt, step of a row = row / Bt
+__global__ void emit_attention_all_kernel(int T, int Bt, int At, int SW, const int* __restrict__ len,
+                                          const float* __restrict__ S1, float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * Bt * At) return;
+  long long row = idx / At;
+  int a = (int)(idx - row * At);
+  int t = (int)(row / Bt), b = (int)(row - (long long)t * Bt);
+  out[idx] = t < len[b] ? S1[(size_t)row * SW + a] : 0.0f;
+}
+
 __global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows,
                               int cols) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,10 +172,13 @@ int attn_bahdanau_post(cudaStream_t st, int T, int B, int Tm, int A, const int* 
 // --------------------------------------------------------------------------- //
 // host orchestration
 // --------------------------------------------------------------------------- //
+size_t attn_persist_work_floats(int B, int H, int Dm, int Tm);                 // attn_persist.cu
+int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch);    // attn_persist.cu
+
 struct WorkLayout {
-  size_t rec, cbuf, dS, dcbuf, dHC, dq, total;
+  size_t rec, cbuf, dS, dcbuf, dHC, dq, persist, total;
 };
-static WorkLayout work_layout(int B, int H, int At, int maxHD, int maxA) {
+static WorkLayout work_layout(int B, int H, int At, int maxHD, int maxA, int maxTm) {
   WorkLayout w;
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
@@ -172,15 +188,16 @@ static WorkLayout work_layout(int B, int H, int At, int maxHD, int maxA) {
   w.dcbuf = take((size_t)2 * B * H);
   w.dHC = take((size_t)2 * B * maxHD);
   w.dq = take((size_t)2 * B * (maxA > H ? maxA : H));
+  w.persist = take(maxTm > 0 ? attn_persist_work_floats(B, H, maxHD - H, maxTm) : 0);
   w.total = o;
   return w;
 }
 
-static int check_common(const AvsrRnnSeq* r, int* At_out, int* maxHD, int* maxA) {
+static int check_common(const AvsrRnnSeq* r, int* At_out, int* maxHD, int* maxA, int* maxTm) {
   AVSR_REQUIRE(r != nullptr, "rnn: null descriptor");
   AVSR_REQUIRE(r->T >= 0 && r->B > 0 && r->H > 0, "rnn: bad dims T=%d B=%d H=%d", r->T, r->B, r->H);
   AVSR_REQUIRE(r->n_mech >= 0 && r->n_mech <= 2, "rnn: n_mech must be 0..2");
-  int At = 0, hd = 0, ma = 0;
+  int At = 0, hd = 0, ma = 0, mt = 0;
   for (int k = 0; k < r->n_mech; ++k) {
     const AvsrAttnMech& m = r->mech[k];
     AVSR_REQUIRE(m.kind >= 0 && m.kind <= 3, "rnn: unknown attention mechanism %d", m.kind);
@@ -190,10 +207,12 @@ static int check_common(const AvsrRnnSeq* r, int* At_out, int* maxHD, int* maxA)
     At += m.A;
     hd = hd > r->H + m.Dm ? hd : r->H + m.Dm;
     ma = ma > m.A ? ma : m.A;
+    mt = mt > m.Tm ? mt : m.Tm;
   }
   *At_out = At;
   *maxHD = hd;
   *maxA = ma;
+  *maxTm = mt;
   return 0;
 }
 
@@ -201,15 +220,25 @@ static int check_common(const AvsrRnnSeq* r, int* At_out, int* maxHD, int* maxA)
 int lstm_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r);  // lstm_persist.cu
 
 int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
-  int At, maxHD, maxA;
-  AVSR_TRY(check_common(r, &At, &maxHD, &maxA));
+  int At, maxHD, maxA, maxTm;
+  AVSR_TRY(check_common(r, &At, &maxHD, &maxA, &maxTm));
   if (r->n_mech == 0 && tensor_cores_enabled()) {  // persistent cluster kernel (tcgen05, weights resident)
     const int rc = lstm_persist_fwd(st, r);
     if (rc >= 0) return rc;
   }
   const int T = r->T, B = r->B, H = r->H, SW = At + H;
   const int rnd = tensor_cores_enabled();
-  WorkLayout wl = work_layout(B, H, At, maxHD, maxA);
+  WorkLayout wl = work_layout(B, H, At, maxHD, maxA, maxTm);
+  if (r->n_mech == 1 && rnd && T > 1 && !getenv("AVSR_NO_ATTN_PERSIST")) {  // T == 1: step-wise decoding (carried attention)
+    // persistent cluster kernel for the Luong-family attention layer (AV-Align top layer, LAS decoder)
+    const int rc = attn_persist_fwd(st, r, r->work + wl.persist);
+    if (rc >= 0) {
+      if (rc == 0 && r->output_attention)  // layer output = attention vectors, zero past the length
+        AVSR_LAUNCH(emit_attention_all_kernel, cdiv((long long)T * B * At, 256), 256, 0, st, T, B, At, SW, r->len,
+                    r->S + (size_t)B * SW, r->out);
+      return rc;
+    }
+  }
   float* rec = r->work + wl.rec;
   float* cbuf[2] = {r->work + wl.cbuf, r->work + wl.cbuf + (size_t)B * H};
   const int pw_grid = cdiv((long long)B * H, 256);
@@ -258,8 +287,8 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
 int lstm_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r);  // lstm_persist.cu
 
 int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
-  int At, maxHD, maxA;
-  AVSR_TRY(check_common(r, &At, &maxHD, &maxA));
+  int At, maxHD, maxA, maxTm;
+  AVSR_TRY(check_common(r, &At, &maxHD, &maxA, &maxTm));
   const int T = r->T, B = r->B, H = r->H, SW = At + H;
   if (r->n_mech == 0 && tensor_cores_enabled()) {
     const int rc = lstm_persist_bwd(st, r);  // reverse-time recurrence in one persistent cluster kernel
@@ -271,7 +300,7 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   }
   const bool oa = r->output_attention && r->n_mech > 0;
   const int rnd = tensor_cores_enabled();
-  WorkLayout wl = work_layout(B, H, At, maxHD, maxA);
+  WorkLayout wl = work_layout(B, H, At, maxHD, maxA, maxTm);
   float* dS[2] = {r->work + wl.dS, r->work + wl.dS + (size_t)B * SW};
   float* dcb[2] = {r->work + wl.dcbuf, r->work + wl.dcbuf + (size_t)B * H};
   const int qw = maxA > H ? maxA : H;
@@ -347,6 +376,8 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   return 0;
 }
 
-size_t rnn_work_floats(int B, int H, int At, int maxHD, int maxA) { return work_layout(B, H, At, maxHD, maxA).total; }
+size_t rnn_work_floats(int B, int H, int At, int maxHD, int maxA, int maxTm) {
+  return work_layout(B, H, At, maxHD, maxA, maxTm).total;
+}
 
 }  // namespace avsr

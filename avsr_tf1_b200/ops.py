@@ -247,7 +247,8 @@ class RnnSeq:
                 m.pq = empty(T, B, m.A)
         maxHD = max([H + m.Dm for m in self.mechs], default=0)
         maxA = max([m.A for m in self.mechs], default=0)
-        nwork = int(_lib.load().avsr_rnn_work_floats(B, H, self.At, maxHD, maxA))
+        maxTm = max([m.Tm for m in self.mechs], default=0)
+        nwork = int(_lib.load().avsr_rnn_work_floats(B, H, self.At, maxHD, maxA, maxTm))
         self.work = empty(max(nwork, 4))
         self.dZ = self.dA = None
 

@@ -40,7 +40,9 @@ def parse():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='per-GPU batch (weak scaling)')
     ap.add_argument('--video-input', default='crops3888', choices=['crops3888', 'features128'])
-    ap.add_argument('--attention', default='bahdanau', choices=['bahdanau', 'scaled_luong'])
+    ap.add_argument('--attention', default='scaled_luong', choices=['bahdanau', 'scaled_luong'],
+                    help='scorer of the cross-modal and decoder attention; scaled_luong is the reference default '
+                         '(avsr.py:50) used by its AV-Align script (run_audiovisual.py:55)')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of one CUDA graph per step')
     ap.add_argument('--no-tensor-cores', action='store_true')
     ap.add_argument('--cpu-sample', type=int, default=8, help='utterances per CPU-baseline step')

@@ -275,6 +275,8 @@ def _spec64(s):
     (('scaled_luong', 'scaled_luong'), 4, 9, 128, 256, (20, 75), (256, 256)),
     (('bahdanau', 'bahdanau'), 3, 6, 32, 64, (10, 17), (64, 48)),
     (('bahdanau',), 6, 41, 128, 256, (300,), (512,)),
+    (('scaled_luong',), 20, 9, 128, 256, (75,), (256,)),   # persistent cluster kernel (tf32 mode), 2 clusters
+    (('luong',), 5, 14, 256, 256, (300,), (256,)),
 ])
 def test_attention_rnn_fwd_bwd(kinds, B, T, Dx, H, Tms, Dms, tensor_cores):
     ops = ops_mod()

@@ -16,7 +16,7 @@ from tests.helpers import to_data_sequences  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=256)
 ap.add_argument('--video-input', default='crops3888')
-ap.add_argument('--attention', default='bahdanau')
+ap.add_argument('--attention', default='scaled_luong')
 ap.add_argument('--no-tensor-cores', action='store_true')
 ap.add_argument('--graph', action='store_true')
 args = ap.parse_args()
