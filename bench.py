@@ -232,15 +232,30 @@ def main():
     if args.impl == 'reference':
         reference_arm(args)
         return
+    import faulthandler
+
     import torch
     import torch.distributed as dist
 
+    # a hang (e.g. a mismatched collective) must end with a traceback, not with the driver's timeout
+    faulthandler.dump_traceback_later(int(os.environ.get('AVSR_BENCH_WATCHDOG_S', '900')), exit=True)
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        # NCCL announces its version on stdout at init; keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from avsr_tf1_b200 import ops
     from avsr_tf1_b200.seq2seq import Seq2SeqModel
     from tests.helpers import to_data_sequences
@@ -300,9 +315,17 @@ def main():
     h2d = model.h2d_bytes
     d2h = int(model._loss_dev.numel() * 4)
 
-    if rank != 0:
+    def finish():
+        # captured graphs hold NCCL work; tearing the process group down under them can hang, so leave hard
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     ms_step = ms_total / args.steps
@@ -334,8 +357,7 @@ def main():
             'sample': f'{r["sample"]} utterances per step of the same workload at full sequence lengths, 2 timed '
                       'steps; NumPy/OpenBLAS restatement of the TF1 graph (oracle/)'}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == '__main__':
