@@ -35,6 +35,7 @@ class AvsrRnnSeq(C.Structure):
         ('mech', AvsrAttnMech * 2),
         ('dout', C.c_void_p), ('dcT', C.c_void_p), ('dhT', C.c_void_p), ('dZ', C.c_void_p), ('dA', C.c_void_p),
         ('dWrec', C.c_void_p), ('dc0', C.c_void_p), ('dh0', C.c_void_p), ('work', C.c_void_p),
+        ('grad_scale', C.c_float),
     ]
 
 

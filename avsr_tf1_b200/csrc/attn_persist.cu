@@ -488,6 +488,427 @@ __global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict
   if (i < n) dst[i] = __float2half_rn(src[i]);
 }
 
+
+// =====================================================================================================
+// backward of the same layer, same fused algebra:
+//     [dh_{t-1} | dctx_{t-1}] = dz_t W'^T + (dout_{t-1} Wl^T)          (second term precomputed for all t)
+// CTA `rank` owns the gate columns of its 32 units (K split of the product, reduce-scattered through DSMEM:
+// h rows to the owners of the units, ctx rows to the owners of the utterances) and the attention backward
+// of 2 utterances:  d(align) = values.dctx -> softmax backward -> ds (saved; dkeys/dvalues are formed after
+// the loop) -> dq = g * sum_tm ds keys  -> all-to-all to the owners of the units.
+// dz enters the tensor core as fp16 scaled by a power of two (`grad_scale`, undone on the accumulators).
+// =====================================================================================================
+struct BwdParams {
+  int T, B, Tm, scaled;
+  float grad_scale, inv_grad_scale;
+  const int* len;
+  const int* mem_len;
+  const float* gates;    // [T,B,4H] activations
+  const float* craw;     // [T,B,H]
+  const float* c0;       // [B,H] or null
+  const float* Wp;       // fused recurrent matrix [(H+DM),4H]
+  const __half* keys;    // [Tm,B,H]
+  const __half* values;  // [Tm,B,DM]
+  const float* g;        // [1] or null
+  const float* hc;       // [T,B,H+DM] forward [h | ctx]
+  const float* align;    // [T,B,Tm]
+  const float* douthc;   // [T,B,H+DM] = dout Wl^T (unmasked) or null
+  const float* dcT;      // [B,H] or null
+  const float* dhT;      // [B,H] or null
+  float* dZ;             // [T,B,4H]
+  float* ds;             // [T,B,Tm]
+  float* dhc;            // [T,B,H+DM]: the ctx columns receive dctx_t
+  float* dg;             // [1] or null
+  float* dc0;            // [B,H] or null
+  float* dh0;            // [B,H] or null
+};
+
+constexpr int BW_W_BYTES = 2 * KTOT * 128;           // A operand: 2 K-blocks x [512 rows x 128 B]
+constexpr int BW_DZ_BYTES = 2 * NB * 128;            // B operand: 2 K-blocks x [16 rows x 128 B]
+constexpr int REDH_FLOATS = CL * 32 * NB;            // [src][u][b]
+constexpr int REDC_FLOATS = CL * 2 * DM;             // [src][utt][dim]
+constexpr int DQ_FLOATS = CL * 2 * 32;               // [src][utt][u]
+
+__device__ __forceinline__ void st_async_v4f(uint32_t addr, uint32_t mbar, float a, float b, float c, float d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%2, %3, %4, %5}, [%1];" ::"r"(addr),
+               "r"(mbar), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v2f(uint32_t addr, uint32_t mbar, float a, float b) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%2, %3}, [%1];" ::"r"(addr),
+               "r"(mbar), "f"(a), "f"(b)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW = base;
+  const uint32_t sDz = sW + BW_W_BYTES;
+  const uint32_t sRedH = sDz + BW_DZ_BYTES;                  // two parities
+  const uint32_t sRedC = sRedH + 2 * REDH_FLOATS * 4;
+  const uint32_t sDq = sRedC + REDC_FLOATS * 4;
+  const uint32_t sCtx = sDq + DQ_FLOATS * 4;                 // [2][DM] dctx of the two utterances
+  const uint32_t sSc = sCtx + 2 * DM * 4;                    // [2][MAX_TM] alignments
+  const uint32_t sDs = sSc + 2 * MAX_TM * 4;                 // [2][MAX_TM] d(align) / ds
+  const uint32_t sPart = sDs + 2 * MAX_TM * 4;               // [2][4][DM]
+  const uint32_t sRed = sPart + 2 * 4 * DM * 4;              // [2][8]
+  const uint32_t sBar = sRed + 64;  // [0] mma_done [1] dz_ready [2,3] redH_full[par] [4] redC_full [5] dq_full
+  const uint32_t sTmem = sBar + 48;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  float* redH = reinterpret_cast<float*>(gen + (sRedH - base));
+  float* redC = reinterpret_cast<float*>(gen + (sRedC - base));
+  float* dqb = reinterpret_cast<float*>(gen + (sDq - base));
+  float* ctx_all = reinterpret_cast<float*>(gen + (sCtx - base));
+  float* sc_all = reinterpret_cast<float*>(gen + (sSc - base));
+  float* ds_all = reinterpret_cast<float*>(gen + (sDs - base));
+  float* part_all = reinterpret_cast<float*>(gen + (sPart - base));
+  float* red_all = reinterpret_cast<float*>(gen + (sRed - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int b0 = cluster_id_x() * NB;
+  const int T = p.T, B = p.B, Tm = p.Tm;
+
+  if (tid == 0) {
+    mbar_init(sBar, 1);
+    mbar_init(sBar + 8, GM_WARPS * 32);
+    for (int i = 2; i < 6; ++i) mbar_init(sBar + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == GM_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(sTmem) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // resident operand: A[n][g*32 + u] = Wp[n][g*H + 32*rank + u] as fp16 (rows n = [h | ctx] dims)
+  for (int seg = warp; seg < KTOT * 4; seg += THREADS / 32) {
+    const int n = seg >> 2, g = seg & 3;
+    const float w = p.Wp[(size_t)n * 4 * H + g * H + 32 * rank + lane];
+    *reinterpret_cast<__half*>(gen + (sW - base) + sw128h_off(KTOT, n, g * 32 + lane)) = __float2half_rn(w);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
+  cluster_sync_all();
+
+  if (warp == GM_WARPS) {
+    // ================= MMA issuer: partial [h | ctx](512) x NB from this CTA's 128 gate columns ===========
+    for (int it = 0; it < T; ++it) {
+      mbar_wait(sBar + 8, it & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+#pragma unroll
+        for (int mt = 0; mt < KTOT / 128; ++mt)
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_f16(tmem_base + mt * NB, make_desc_k128(sW + kb * (KTOT * 128) + mt * (128 * 128) + k4 * 32),
+                       make_desc_k128(sDz + kb * (NB * 128) + k4 * 32), IDESC, (kb | k4) ? 1u : 0u);
+        umma_commit(sBar);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int unit = 32 * rank + lane;
+    constexpr int PB = 2;
+    float dc[PB], dh_carry[PB];
+    int len_t[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int b = b0 + warp * PB + j;
+      len_t[j] = (b < B) ? p.len[b] : 0;
+      dc[j] = (b < B && p.dcT) ? p.dcT[(size_t)b * H + unit] : 0.0f;
+      dh_carry[j] = (b < B && p.dhT) ? p.dhT[(size_t)b * H + unit] : 0.0f;
+    }
+    float gi[PB], gj[PB], gf[PB], go[PB], crw[PB], cpv[PB], dov[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) gi[j] = gj[j] = gf[j] = go[j] = crw[j] = cpv[j] = dov[j] = 0.0f;
+    auto load_step = [&](int t) {
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int b = b0 + warp * PB + j;
+        if (t >= 0 && t < len_t[j]) {
+          const float* g = p.gates + ((size_t)t * B + b) * 4 * H + unit;
+          gi[j] = g[0]; gj[j] = g[H]; gf[j] = g[2 * H]; go[j] = g[3 * H];
+          const size_t o = ((size_t)t * B + b) * H + unit;
+          crw[j] = p.craw[o];
+          cpv[j] = t > 0 ? p.craw[o - (size_t)B * H] : (p.c0 ? p.c0[(size_t)b * H + unit] : 0.0f);
+          dov[j] = p.douthc ? p.douthc[((size_t)t * B + b) * (H + DM) + unit] : 0.0f;
+        }
+      }
+    };
+    // attention role
+    const int jl = warp >> 2, w4 = warp & 3, gt = tid & 127;
+    const int bl_att = 2 * (int)rank + jl;
+    const int b_att = b0 + bl_att;
+    const int len_q = (b_att < B) ? p.len[b_att] : 0;
+    const int L = (b_att < B) ? min(p.mem_len[b_att], Tm) : 0;
+    const float gs = p.scaled ? p.g[0] : 1.0f;
+    float* dctx_s = ctx_all + jl * DM;
+    float* a_s = sc_all + jl * MAX_TM;
+    float* ds_s = ds_all + jl * MAX_TM;
+    float* part = part_all + jl * 4 * DM;
+    float* red = red_all + jl * 8;
+    const uint32_t att_bar_id = 2 + jl;
+    // reduce-scatter role after the product: warps 0-3 forward the h rows, warps 4-7 the ctx rows
+    const int q = warp & 3;
+
+    load_step(T - 1);
+    for (int it = 0; it < T; ++it) {
+      const int t = T - 1 - it;
+      const bool live_q = t < len_q;
+      // ---- (A/B) dctx_t of the two utterances, attention backward, dq all-to-all -----------------------
+      if (it > 0) {
+        if (tid == 0) mbar_expect_tx(sBar + 32, REDC_FLOATS * 4);
+        mbar_wait(sBar + 32, (it - 1) & 1);
+      }
+      float dqv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dqv[e] = 0.0f;
+      if (live_q) {
+        for (int d = gt; d < DM; d += 128) {
+          float v = p.douthc ? p.douthc[((size_t)t * B + b_att) * (H + DM) + H + d] : 0.0f;
+          if (it > 0) {
+#pragma unroll
+            for (int src = 0; src < CL; ++src) v += redC[(src * 2 + jl) * DM + d];
+          }
+          dctx_s[d] = v;
+          p.dhc[((size_t)t * B + b_att) * (H + DM) + H + d] = v;
+        }
+        for (int tm = gt; tm < Tm; tm += 128) a_s[tm] = p.align[((size_t)t * B + b_att) * Tm + tm];
+        asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        float dcx[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dcx[e] = dctx_s[8 * lane + e];
+        // d(align)[tm] = values[tm] . dctx
+        for (int tm0 = w4; tm0 < L; tm0 += 16) {
+          uint4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int tm = tm0 + 4 * j;
+            v[j] = tm < L ? __ldg(reinterpret_cast<const uint4*>(p.values + ((size_t)tm * B + b_att) * DM) + lane)
+                          : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 x0 = unpack_h2(v[j].x), x1 = unpack_h2(v[j].y), x2 = unpack_h2(v[j].z), x3 = unpack_h2(v[j].w);
+            float s = x0.x * dcx[0] + x0.y * dcx[1] + x1.x * dcx[2] + x1.y * dcx[3] + x2.x * dcx[4] + x2.y * dcx[5] +
+                      x3.x * dcx[6] + x3.y * dcx[7];
+            s = warp_sum(s);
+            if (lane == 0 && tm0 + 4 * j < L) ds_s[tm0 + 4 * j] = s;
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        float dot = 0.0f;
+        for (int tm = gt; tm < L; tm += 128) dot = fmaf(a_s[tm], ds_s[tm], dot);
+        dot = warp_sum(dot);
+        if (lane == 0) red[w4] = dot;
+        asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        dot = (red[0] + red[1]) + (red[2] + red[3]);
+        float* dsrow = p.ds + ((size_t)t * B + b_att) * Tm;
+        for (int tm = gt; tm < Tm; tm += 128) {
+          const float d = tm < L ? a_s[tm] * (ds_s[tm] - dot) : 0.0f;
+          dsrow[tm] = d;  // d(score) before the Luong scale (dkeys / dg use it after the loop)
+          if (tm < L) ds_s[tm] = d;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        // keys sweep: dq += g * ds[tm] * keys[tm];  raw score for d(attention_g)
+        const float* hrow = p.hc + ((size_t)t * B + b_att) * (H + DM) + 8 * lane;
+        float qv[8];
+        {
+          const float4 q0 = *reinterpret_cast<const float4*>(hrow), q1 = *reinterpret_cast<const float4*>(hrow + 4);
+          qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
+        }
+        float gacc = 0.0f;
+        for (int tm0 = w4; tm0 < L; tm0 += 16) {
+          uint4 k[4];
+          float d[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int tm = tm0 + 4 * j;
+            d[j] = tm < L ? ds_s[tm] : 0.0f;
+            k[j] = tm < L ? __ldg(reinterpret_cast<const uint4*>(p.keys + ((size_t)tm * B + b_att) * H) + lane)
+                          : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 x0 = unpack_h2(k[j].x), x1 = unpack_h2(k[j].y), x2 = unpack_h2(k[j].z), x3 = unpack_h2(k[j].w);
+            const float kk[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
+            float raw = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              dqv[e] = fmaf(d[j], kk[e], dqv[e]);
+              raw = fmaf(kk[e], qv[e], raw);
+            }
+            if (p.scaled) gacc = fmaf(d[j], raw, gacc);  // lane-partial of ds * (keys . q)
+          }
+        }
+        if (p.scaled) {
+          gacc = warp_sum(gacc);
+          if (lane == 0 && p.dg) atomicAdd(p.dg, gacc);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) part[w4 * DM + 8 * lane + e] = dqv[e];
+        asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        if (w4 == 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            dqv[e] = gs * ((part[8 * lane + e] + part[DM + 8 * lane + e]) + (part[2 * DM + 8 * lane + e] + part[3 * DM + 8 * lane + e]));
+        }
+      }
+      if (w4 == 0) {
+        // dq dims 8*lane .. +7 belong to the CTA owning units (8*lane)/32
+        const uint32_t dst = (uint32_t)(lane >> 2);
+        const uint32_t a0 = mapa(sDq + (uint32_t)(((rank * 2 + jl) * 32 + ((8 * lane) & 31)) * 4), dst);
+        const uint32_t bar = mapa(sBar + 40, dst);
+        st_async_v4f(a0, bar, dqv[0], dqv[1], dqv[2], dqv[3]);
+        st_async_v4f(a0 + 16, bar, dqv[4], dqv[5], dqv[6], dqv[7]);
+      }
+      // ---- (C/D) dq and h partials of this CTA's units -> gate gradients -------------------------------
+      if (tid == 0) mbar_expect_tx(sBar + 40, DQ_FLOATS * 4);
+      mbar_wait(sBar + 40, it & 1);
+      const float* rbuf = redH + (it & 1) * REDH_FLOATS;
+      if (it > 0) {
+        const uint32_t bar = sBar + 16 + 8 * (it & 1);
+        if (tid == 0) mbar_expect_tx(bar, REDH_FLOATS * 4);
+        mbar_wait(bar, ((it - 1) >> 1) & 1);
+      }
+      float dz[4][PB];
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int bl = warp * PB + j;
+        float dh = dh_carry[j];
+        if (it > 0) {
+#pragma unroll
+          for (int src = 0; src < CL; ++src) dh += rbuf[(src * 32 + lane) * NB + bl];
+        }
+        if (t < len_t[j]) {
+          dh += dov[j] + dqb[((bl >> 1) * 2 + (bl & 1)) * 32 + lane];
+          const float c = fminf(fmaxf(crw[j], -1.0f), 1.0f);
+          const float tc = tanhf_acc(c);
+          const float cp = t > 0 ? fminf(fmaxf(cpv[j], -1.0f), 1.0f) : cpv[j];
+          const float dct = dc[j] + dh * go[j] * (1.0f - tc * tc);
+          const float dcr = (crw[j] >= -1.0f && crw[j] <= 1.0f) ? dct : 0.0f;
+          dz[0][j] = dcr * gj[j] * gi[j] * (1.0f - gi[j]);
+          dz[1][j] = dcr * gi[j] * (1.0f - gj[j] * gj[j]);
+          dz[2][j] = dcr * cp * gf[j] * (1.0f - gf[j]);
+          dz[3][j] = dh * tc * go[j] * (1.0f - go[j]);
+          dc[j] = dcr * gf[j];
+          dh_carry[j] = 0.0f;
+        } else {
+          dz[0][j] = dz[1][j] = dz[2][j] = dz[3][j] = 0.0f;
+          dh_carry[j] = dh;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<__half*>(gen + (sDz - base) + sw128h_off(NB, bl, g * 32 + lane)) =
+              __float2half_rn(dz[g][j] * p.grad_scale);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(sBar + 8);
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int b = b0 + warp * PB + j;
+        if (b < B) {
+          float* o = p.dZ + ((size_t)t * B + b) * 4 * H + unit;
+          o[0] = tf32_rn(dz[0][j]); o[H] = tf32_rn(dz[1][j]); o[2 * H] = tf32_rn(dz[2][j]); o[3 * H] = tf32_rn(dz[3][j]);
+        }
+      }
+      load_step(t - 1);
+      // ---- (E) partial products -> owners ---------------------------------------------------------------
+      mbar_wait(sBar, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (warp < 4) {
+        const uint32_t rnext = sRedH + ((it + 1) & 1) * REDH_FLOATS * 4;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {  // h rows 128*mt + 32*q + lane -> owner CTA 4*mt + q
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NB, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const uint32_t dst = (uint32_t)(4 * mt + q);
+          const uint32_t a0 = mapa(rnext + (uint32_t)((rank * 32 + lane) * NB) * 4, dst);
+          const uint32_t bar = mapa(sBar + 16 + 8 * ((it + 1) & 1), dst);
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            st_async_v4f(a0 + v * 16, bar, __uint_as_float(r[4 * v]) * p.inv_grad_scale,
+                         __uint_as_float(r[4 * v + 1]) * p.inv_grad_scale, __uint_as_float(r[4 * v + 2]) * p.inv_grad_scale,
+                         __uint_as_float(r[4 * v + 3]) * p.inv_grad_scale);
+        }
+      } else if (it + 1 < T) {
+#pragma unroll
+        for (int mt = 2; mt < 4; ++mt) {  // ctx dims 128*(mt-2) + 32*q + lane; column c = utterance -> owner CTA c/2
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NB, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int dim = 128 * (mt - 2) + 32 * q + lane;
+#pragma unroll
+          for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) {
+            // redC[src = rank][utt 0..1][dim]: the two utterances are DM floats apart -> two scalar-pair stores
+            const uint32_t a0 = mapa(sRedC + (uint32_t)((rank * 2) * DM + dim) * 4, dst);
+            const uint32_t bar = mapa(sBar + 32, dst);
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %2, [%1];" ::"r"(a0), "r"(bar),
+                         "f"(__uint_as_float(r[2 * dst]) * p.inv_grad_scale)
+                         : "memory");
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %2, [%1];" ::"r"(a0 + DM * 4),
+                         "r"(bar), "f"(__uint_as_float(r[2 * dst + 1]) * p.inv_grad_scale)
+                         : "memory");
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    // drain the last reduce-scatter (nothing may be in flight towards this CTA when it exits).  Its content is
+    // NOT dh_0: step 0 saw att_{-1} = 0, so dh_0 = dz_0 Wh^T with the un-fused Wh - added by the host; here only
+    // the gradient carried through fully masked utterances is written.
+    if (T > 0) {
+      const uint32_t bar = sBar + 16 + 8 * (T & 1);
+      if (tid == 0) mbar_expect_tx(bar, REDH_FLOATS * 4);
+      mbar_wait(bar, ((T - 1) >> 1) & 1);
+    }
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int b = b0 + warp * PB + j;
+      if (b < B) {
+        if (p.dh0) p.dh0[(size_t)b * H + unit] = dh_carry[j];
+        if (p.dc0) p.dc0[(size_t)b * H + unit] = dc[j];
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == GM_WARPS)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base) : "memory");
+  cluster_sync_all();
+}
+
+constexpr size_t BW_SMEM_BYTES = (size_t)BW_W_BYTES + BW_DZ_BYTES + 2 * REDH_FLOATS * 4 + REDC_FLOATS * 4 + DQ_FLOATS * 4 +
+                                 2 * DM * 4 + 4 * MAX_TM * 4 + 2 * 4 * DM * 4 + 64 + 64 + 1024;
+
+// dA[t,b,:] += (t < len[b]) ? dout[t,b,:] : 0
+__global__ void masked_add_kernel(float* __restrict__ dA, const float* __restrict__ dout, const int* __restrict__ len,
+                                  int T, int Bt, int At, int rnd) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * Bt * At) return;
+  long long row = idx / At;
+  int t = (int)(row / Bt), b = (int)(row - (long long)t * Bt);
+  float v = dA[idx] + ((dout && t < len[b]) ? dout[idx] : 0.0f);
+  dA[idx] = maybe_tf32(v, rnd);
+}
+
 }  // namespace ap
 
 size_t attn_persist_work_floats(int B, int H, int Dm, int Tm) {
@@ -548,6 +969,76 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   ++g_launch_count;
   // attention vectors of all steps in one product: S[1:, :, :At] = [h | ctx] Wl (tf32-rounded operand rows)
   AVSR_TRY(gemm(st, 0, 0, T * B, At, H + DM, m.hc, H + DM, m.Wl, m.A, r->S + (size_t)B * SW, SW, 0.0f, nullptr, 1));
+  return 0;
+}
+
+// Backward counterpart.  `scratch` must still hold what attn_persist_fwd left there (fused matrix, fp16
+// keys / values): the same descriptor / work buffer, forward first.  Fills dZ, ds, dhc(ctx), dA; accumulates
+// dWrec, dWl, dkeys, dvalues, dg.  Returns -1 when unsupported.
+int attn_outer(cudaStream_t st, int T, int B, int Tm, int C, const int* seq_len, const float* w, const float* x,
+               int ldx, const float* scale, float* out);  // attention.cu
+
+int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
+  using namespace ap;
+  if (r->n_mech != 1 || r->T <= 1) return -1;
+  const AvsrAttnMech& m = r->mech[0];
+  if (m.kind > AVSR_ATTN_SCALED_LUONG) return -1;
+  if (r->H != H || m.A != H || m.Dm != DM || m.Tm > MAX_TM) return -1;
+  const int T = r->T, B = r->B, At = m.A, SW = At + H, HD = H + DM;
+  const bool oa = r->output_attention != 0;
+  float* Wp = scratch;
+  float* tmp = Wp + (size_t)HD * 4 * H;
+  __half* keys_h = reinterpret_cast<__half*>(tmp + (size_t)H * 4 * H);
+  __half* values_h = keys_h + (size_t)m.Tm * B * H;
+  // (dout Wl^T) for every step: the part of d[h | ctx] that does not depend on the recurrence
+  // It is written into m.dhc itself: the kernel reads an entry and then overwrites the ctx columns with the
+  // total dctx_t (same thread, same address).
+  const float* dhc_in = nullptr;
+  if (oa && r->dout) {
+    AVSR_TRY(gemm(st, 0, 1, T * B, HD, At, r->dout, At, m.Wl, m.A, m.dhc, HD, 0.0f, nullptr));
+    dhc_in = m.dhc;
+  } else {
+    AVSR_CHECK_CUDA(cudaMemsetAsync(m.dhc, 0, (size_t)T * B * HD * sizeof(float), st));
+  }
+  BwdParams p;
+  p.T = T; p.B = B; p.Tm = m.Tm; p.scaled = m.kind == AVSR_ATTN_SCALED_LUONG;
+  p.grad_scale = r->grad_scale > 0.0f ? r->grad_scale : 1.0f;
+  p.inv_grad_scale = 1.0f / p.grad_scale;
+  p.len = r->len; p.mem_len = m.mem_len; p.gates = r->gates; p.craw = r->craw; p.c0 = r->c0; p.Wp = Wp;
+  p.keys = keys_h; p.values = values_h; p.g = m.g; p.hc = m.hc; p.align = m.align; p.douthc = dhc_in;
+  p.dcT = r->dcT; p.dhT = r->dhT; p.dZ = r->dZ; p.ds = m.ds; p.dhc = m.dhc; p.dg = m.dg; p.dc0 = r->dc0; p.dh0 = r->dh0;
+  static bool attr = false;
+  if (!attr) {
+    AVSR_CHECK_CUDA(cudaFuncSetAttribute(attn_lstm_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)BW_SMEM_BYTES));
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cdiv(B, NB) * CL);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = BW_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_lstm_persist_bwd_kernel, p));
+  ++g_launch_count;
+  if (r->dh0)  // dh_0 += dz_0 Wh^T (un-fused: the zero attention state of step 0)
+    AVSR_TRY(gemm(st, 0, 1, B, H, 4 * H, r->dZ, 4 * H, r->Wrec + (size_t)At * 4 * H, 4 * H, r->dh0, H, 1.0f, nullptr));
+  // dA_t = dz_{t+1} Wa^T (+ dout_t, masked): gradient wrt the attention vectors, for dWl
+  AVSR_CHECK_CUDA(cudaMemsetAsync(r->dA + (size_t)(T - 1) * B * At, 0, (size_t)B * At * sizeof(float), st));
+  AVSR_TRY(gemm(st, 0, 1, (T - 1) * B, At, 4 * H, r->dZ + (size_t)B * 4 * H, 4 * H, r->Wrec, 4 * H, r->dA, At, 0.0f, nullptr));
+  AVSR_LAUNCH(masked_add_kernel, cdiv((long long)T * B * At, 256), 256, 0, st, r->dA, oa ? r->dout : nullptr, r->len, T, B,
+              At, tensor_cores_enabled());
+  // parameter gradients and per-utterance accumulations, all batched
+  AVSR_TRY(gemm(st, 1, 0, SW, 4 * H, T * B, r->S, SW, r->dZ, 4 * H, r->dWrec, 4 * H, 1.0f, nullptr));
+  AVSR_TRY(gemm(st, 1, 0, HD, At, T * B, m.hc, HD, r->dA, At, m.dWl, m.A, 1.0f, nullptr));
+  AVSR_TRY(attn_outer(st, T, B, m.Tm, DM, r->len, m.align, m.dhc + H, HD, nullptr, m.dvalues));
+  AVSR_TRY(attn_outer(st, T, B, m.Tm, At, r->len, m.ds, m.hc, HD, p.scaled ? m.g : nullptr, m.dkeys));
   return 0;
 }
 

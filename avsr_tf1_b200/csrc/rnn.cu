@@ -174,6 +174,7 @@ int attn_bahdanau_post(cudaStream_t st, int T, int B, int Tm, int A, const int* 
 // --------------------------------------------------------------------------- //
 size_t attn_persist_work_floats(int B, int H, int Dm, int Tm);                 // attn_persist.cu
 int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch);    // attn_persist.cu
+int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch);    // attn_persist.cu
 
 struct WorkLayout {
   size_t rec, cbuf, dS, dcbuf, dHC, dq, persist, total;
@@ -301,6 +302,11 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   const bool oa = r->output_attention && r->n_mech > 0;
   const int rnd = tensor_cores_enabled();
   WorkLayout wl = work_layout(B, H, At, maxHD, maxA, maxTm);
+  if (r->n_mech == 1 && rnd && T > 1 && !getenv("AVSR_NO_ATTN_PERSIST")) {
+    AVSR_REQUIRE(r->mech[0].ds && r->mech[0].dhc, "rnn bwd: mechanism scratch ds / dhc missing");
+    const int rc = attn_persist_bwd(st, r, r->work + wl.persist);  // needs the scratch attn_persist_fwd left
+    if (rc >= 0) return rc;
+  }
   float* dS[2] = {r->work + wl.dS, r->work + wl.dS + (size_t)B * SW};
   float* dcb[2] = {r->work + wl.dcbuf, r->work + wl.dcbuf + (size_t)B * H};
   const int qw = maxA > H ? maxA : H;

@@ -21,6 +21,7 @@ class BuildContext:
         self.specs: List[ParamSpec] = []
         self.store = None
         self.world_size = 1
+        self.grad_scale = 1.0  # power of two ~ number of target tokens (set per step by Seq2SeqModel)
         self.allreduce = None  # callable(tensor) -> None (in-place sum), set by Seq2SeqModel under DP
 
     def declare(self, name, shape, init, trainable=True):
@@ -256,6 +257,7 @@ class AttnLSTMOp:
             if md.kind == 'scaled_luong':
                 mb.dg = ctx.g(md.g)
         dcT, dhT = dstate if dstate is not None else (None, None)
+        self.rnn.grad_scale = ctx.grad_scale
         dZ = self.rnn.backward(dout, gW[Dx:], dcT=dcT, dhT=dhT, want_init_grad=want_init_grad)
         dZ2 = dZ.view(T * B, 4 * H)
         ops.gemm(self.x.reshape(T * B, Dx), dZ2, gW[:Dx], ta=True, beta=1.0)

@@ -251,6 +251,9 @@ class RnnSeq:
         nwork = int(_lib.load().avsr_rnn_work_floats(B, H, self.At, maxHD, maxA, maxTm))
         self.work = empty(max(nwork, 4))
         self.dZ = self.dA = None
+        # power-of-two scale that brings the gate gradients near 1 before they enter the tensor core as fp16
+        # (persistent attention backward); losses averaged over n tokens have gradients ~ 1/n
+        self.grad_scale = 1.0
 
     def _desc(self, **bw) -> AvsrRnnSeq:
         r = AvsrRnnSeq()
@@ -260,6 +263,7 @@ class RnnSeq:
         for k, m in enumerate(self.mechs):
             m.fill(r.mech[k])
         r.work = _p(self.work)
+        r.grad_scale = float(self.grad_scale)
         for k, v in bw.items():
             setattr(r, k, _p(v))
         return r

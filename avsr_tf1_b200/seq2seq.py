@@ -332,6 +332,7 @@ class Seq2SeqModel(object):
         n_tok = parallel.global_token_count(self._meta['n_tokens'], device='cuda') if ctx.world_size > 1 \
             else self._meta['n_tokens']
         self._inv_denom = 1.0 / (n_tok + 1e-12)  # seq2seq.sequence_loss
+        self._ctx.grad_scale = float(2 ** int(math.floor(math.log2(max(n_tok, 1.0)))))
         lr = self._lr_now()
         self.current_lr = lr
         t = self._global_step + 1

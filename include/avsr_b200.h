@@ -135,7 +135,9 @@ typedef struct AvsrRnnSeq {
   float* dWrec;         /* [(At+H),4H] accumulated */
   float* dc0;           /* [B,H] or NULL */
   float* dh0;           /* [B,H] or NULL */
-  float* work;          /* scratch, >= avsr_rnn_work_floats() floats */
+  float* work;          /* scratch, >= avsr_rnn_work_floats() floats; backward must see what forward left */
+  float grad_scale;     /* power of two ~ 1/|gradient scale| (e.g. the token count): fp16 tensor-core operand
+                           scaling of the persistent attention backward kernel; 0 = 1 */
 } AvsrRnnSeq;
 
 /* At = sum of mechanism A; maxHD = max(H+Dm); maxA = max A; maxTm = max memory length (0,0,0,0 without attention) */
