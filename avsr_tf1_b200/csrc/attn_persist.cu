@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
         float dh = dh_carry[j];
         if (it > 0) {
 #pragma unroll
-          for (int src = 0; src < CL; ++src) dh += rbuf[(src * 32 + lane) * NB + bl];
+          for (int src = 0; src < CL; ++src) dh += rbuf[(src * 32 + lane) * NB + ((((bl >> 2) ^ (lane & 3)) << 2) | (bl & 3))];
         }
         if (t < len_t[j]) {
           dh += dov[j] + dqb[((bl >> 1) * 2 + (bl & 1)) * 32 + lane];
@@ -842,8 +842,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
           const uint32_t a0 = mapa(rnext + (uint32_t)((rank * 32 + lane) * NB) * 4, dst);
           const uint32_t bar = mapa(sBar + 16 + 8 * ((it + 1) & 1), dst);
 #pragma unroll
-          for (int v = 0; v < 4; ++v)
-            st_async_v4f(a0 + v * 16, bar, __uint_as_float(r[4 * v]) * p.inv_grad_scale,
+          for (int v = 0; v < 4; ++v)  // 16-byte chunks XOR-swizzled by the unit: conflict-light reads on the owner
+            st_async_v4f(a0 + ((v ^ (lane & 3)) << 4), bar, __uint_as_float(r[4 * v]) * p.inv_grad_scale,
                          __uint_as_float(r[4 * v + 1]) * p.inv_grad_scale, __uint_as_float(r[4 * v + 2]) * p.inv_grad_scale,
                          __uint_as_float(r[4 * v + 3]) * p.inv_grad_scale);
         }

@@ -27,7 +27,8 @@ namespace lp {
 
 constexpr int GM_WARPS = 8;                   // gate-math warps
 constexpr int THREADS = (GM_WARPS + 1) * 32;  // + 1 MMA-issue warp
-constexpr int NB = 16;                        // utterances per cluster
+// NB = utterances per cluster (16 or 32).  A B200 can keep only 15 clusters of 8 CTAs resident (GPC granularity),
+// so batches above 240 use 32-utterance slices (8 clusters for B = 256) instead of a second wave of clusters.
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -103,6 +104,24 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&r)[N]);
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]);
+template <>
+__device__ __forceinline__ void tmem_ldn<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ldn<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -112,6 +131,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
 }
 
+template <>
+__device__ __forceinline__ void tmem_ldn<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+
 // shared-memory offset of element (row, k) of a K-major SWIZZLE_128B operand whose 32-float K-blocks
 // hold `rows` rows each
 __device__ __forceinline__ uint32_t sw128_off(int rows, int row, int k) {
@@ -120,7 +142,9 @@ __device__ __forceinline__ uint32_t sw128_off(int rows, int row, int k) {
 }
 
 // instruction descriptor: D = f32, A = B = tf32, both K-major, N = NB, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_for(int nb) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nb >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 
 // =====================================================================================================
 // forward
@@ -138,14 +162,24 @@ struct FwdParams {
   float* hT;          // [B,H] or null
   long long* dbg;     // optional per-phase clock samples [64 steps][8] of CTA 0 (AVSR_LP_DEBUG=1), else null
 };
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define LP_STAMP(slot)                                                                        \
   do {                                                                                        \
-    if (p.dbg && blockIdx.x == 0 && tid == 0 && t < 64) p.dbg[t * 8 + (slot)] = clock64();  \
+    if (p.dbg && blockIdx.x == 0 && tid == 0 && t < 64) {                                     \
+      p.dbg[t * 8 + (slot)] = clock64();                                                      \
+      if ((slot) == 0) p.dbg[t * 8 + 7] = globaltimer_ns();                                   \
+    }                                                                                         \
   } while (0)
 
-template <int CL>
+template <int CL, int NB>
 __global__ void __launch_bounds__(THREADS, 1) lstm_persist_fwd_kernel(const FwdParams p) {
   constexpr int H = 32 * CL;
+  constexpr int NA = NB / 2;                  // utterances per activation warp
+  constexpr uint32_t IDESC = idesc_for(NB);
   constexpr int KB = H / 32;                  // 32-float K blocks
   constexpr int W_BYTES = KB * 128 * 128;     // A operand: 128 gate rows x H
   constexpr int HB_BYTES = KB * NB * 128;     // B operand: NB utterances x H
@@ -222,12 +256,12 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist_fwd_kernel(const FwdP
       __syncwarp();
     }
   } else {
-    // ================= gate math: warp w <-> gate (w & 3), utterances 8*(w >> 2) .. +7 =================
+    // ================= gate math: warp w <-> gate (w & 3), utterances NA*(w >> 2) .. +NA-1 ============
     const int g = warp & 3, ch = warp >> 2;
     const int unit = 32 * rank + lane;     // global hidden unit of this lane's gate row
-    // combine mapping (threads 0..127): utterance bq, units 4*uq .. 4*uq+3
-    const bool comb = tid < 128;
-    const int uq = tid & 7, bq = (tid >> 3) & 15;
+    // combine mapping (threads 0 .. 8*NB-1): utterance bq, units 4*uq .. 4*uq+3
+    const bool comb = tid < 8 * NB;
+    const int uq = tid & 7, bq = (tid >> 3) & (NB - 1);
     float c_state[4], h_state[4];
     int len_c = 0;
 #pragma unroll
@@ -242,35 +276,35 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist_fwd_kernel(const FwdP
         h_state[e] = (b < B) ? p.S[(size_t)b * H + u] : 0.0f;
       }
     }
-    int len_a[8];  // lengths of this warp's utterances (activation phase)
+    int len_a[NA];  // lengths of this warp's utterances (activation phase)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) len_a[b] = (b0 + ch * 8 + b < B) ? p.len[b0 + ch * 8 + b] : 0;
-    float gx[8];   // x-projection; later steps are prefetched one step ahead
+    for (int b = 0; b < NA; ++b) len_a[b] = (b0 + ch * NA + b < B) ? p.len[b0 + ch * NA + b] : 0;
+    float gx[NA];   // x-projection; later steps are prefetched one step ahead
     {
-      const float* grow0 = p.gates + ((size_t)b0 + ch * 8) * 4 * H + g * H + unit;
+      const float* grow0 = p.gates + ((size_t)b0 + ch * NA) * 4 * H + g * H + unit;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) gx[b] = (0 < len_a[b]) ? grow0[(size_t)b * 4 * H] : 0.0f;
+      for (int b = 0; b < NA; ++b) gx[b] = (0 < len_a[b]) ? grow0[(size_t)b * 4 * H] : 0.0f;
     }
     for (int t = 0; t < T; ++t) {
-      float* grow = p.gates + ((size_t)t * B + b0 + ch * 8) * 4 * H + g * H + unit;
+      float* grow = p.gates + ((size_t)t * B + b0 + ch * NA) * 4 * H + g * H + unit;
       LP_STAMP(0);
       mbar_wait(sBar, t & 1);  // recurrent product of this step
       LP_STAMP(1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t r[8];
-      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + ch * 8, r);
+      uint32_t r[NA];
+      tmem_ldn<NA>(tmem_base + ((uint32_t)(32 * g) << 16) + ch * NA, r);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       LP_STAMP(2);
-      float av[8];
+      float av[NA];
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {  // i, f, o: sigmoid (forget bias 1); j: tanh
+      for (int b = 0; b < NA; ++b) {  // i, f, o: sigmoid (forget bias 1); j: tanh
         const float z = __uint_as_float(r[b]) + gx[b];
         float a;
         if (g == 1) a = tanhf_acc(z);
         else a = sigmoidf_acc(g == 2 ? z + 1.0f : z);
         av[b] = a;
-        act[(g * NB + ch * 8 + b) * 32 + lane] = a;
+        act[(g * NB + ch * NA + b) * 32 + lane] = a;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       LP_STAMP(3);
@@ -315,7 +349,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist_fwd_kernel(const FwdP
       LP_STAMP(4);
       // HBM side of this step + x-projection of the next, off the recurrent critical path
 #pragma unroll
-      for (int b = 0; b < 8; ++b)
+      for (int b = 0; b < NA; ++b)
         if (t < len_a[b]) grow[(size_t)b * 4 * H] = av[b];  // activations, kept for the backward pass
       if (comb && b0 + bq < B) {
         const size_t o = ((size_t)t * B + b0 + bq) * H + 32 * rank + 4 * uq;
@@ -326,7 +360,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist_fwd_kernel(const FwdP
       if (t + 1 < T) {
         const float* gnext = grow + (size_t)B * 4 * H;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) gx[b] = (t + 1 < len_a[b]) ? gnext[(size_t)b * 4 * H] : 0.0f;
+        for (int b = 0; b < NA; ++b) gx[b] = (t + 1 < len_a[b]) ? gnext[(size_t)b * 4 * H] : 0.0f;
       }
       LP_STAMP(5);
     }
@@ -344,12 +378,12 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist_fwd_kernel(const FwdP
   cluster_sync_all();  // no CTA exits while a peer could still address its shared memory
 }
 
-template <int CL>
+template <int CL, int NB>
 static int launch_fwd(cudaStream_t st, const FwdParams& p) {
   constexpr int H = 32 * CL;
   constexpr int KB = H / 32;
   const size_t smem = (size_t)KB * 128 * 128 + 2 * (size_t)KB * NB * 128 + 4 * NB * 32 * 4 + 64 + 1024;
-  auto kern = lstm_persist_fwd_kernel<CL>;
+  auto kern = lstm_persist_fwd_kernel<CL, NB>;
   static bool attr = false;
   if (!attr) {
     AVSR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -375,6 +409,12 @@ static int launch_fwd(cudaStream_t st, const FwdParams& p) {
 // =====================================================================================================
 // backward
 // =====================================================================================================
+// reduce buffer [src][u][b]: element (src, u, b) with the 16-byte chunks of a row XOR-swizzled by u, so the
+// reader (lanes = u, fixed b) is not a 32-way bank conflict while the writer keeps 16-byte stores
+template <int NB>
+__device__ __forceinline__ int red_off(int src, int u, int b) {
+  return (src * 32 + u) * NB + ((((b >> 2) ^ (u & (NB / 4 - 1))) << 2) | (b & 3));
+}
 struct BwdParams {
   int T, B, H;
   const int* len;
@@ -390,14 +430,17 @@ struct BwdParams {
   float* dh0;          // [B,H] or null
 };
 
-template <int CL>
+template <int CL, int NB>
 __global__ void __launch_bounds__(THREADS, 1) lstm_persist_bwd_kernel(const BwdParams p) {
   constexpr int H = 32 * CL;
+  constexpr uint32_t IDESC = idesc_for(NB);
   constexpr int MT = H / 128;                   // M tiles of the partial product (H out-units)
   constexpr int W_BYTES = 4 * H * 128;          // A operand: 4 gate blocks x [H rows x 32 cols]
   constexpr int DZ_BYTES = 4 * NB * 128;        // B operand: 4 gate blocks x [NB rows x 32 cols]
   constexpr int RED_FLOATS = CL * 32 * NB;      // one parity of the reduce buffer [src][u][b]
-  constexpr int PB = NB / GM_WARPS;             // utterances per thread (2)
+  constexpr int PB = NB / GM_WARPS;             // utterances per thread
+  constexpr int TCOLS = (MT * NB) < 32 ? 32 : MT * NB;  // TMEM columns (power of two >= 32)
+  constexpr int NH = NB / 2;                    // MT == 1: the two warps of a quadrant split the columns
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW = base;
@@ -421,7 +464,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist_bwd_kernel(const BwdP
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == GM_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(sTmem) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "n"(TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // resident weights: A[k][g*32 + u] = Wrec[k][g*H + 32*rank + u]   (K-major: gate block g, row k)
@@ -494,7 +537,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist_bwd_kernel(const BwdP
     // reduce-scatter role of this warp: TMEM tile / column range it forwards, and to which CTA
     const int q = warp & 3;
     const int mt = (MT == 2) ? (warp >> 2) : 0;
-    const int c0col = (MT == 2) ? 0 : (warp >> 2) * 8;  // MT == 1: the two warps of a quadrant split the columns
+    const int c0col = (MT == 2) ? 0 : (warp >> 2) * NH;
     const uint32_t dst = (uint32_t)(mt * 4 + q);        // owner of out-units 128*mt + 32*q + lane
     load_step(T - 1);
     for (int it = 0; it < T; ++it) {
@@ -512,7 +555,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist_bwd_kernel(const BwdP
         float dh = dh_carry[j];
         if (it > 0) {
 #pragma unroll
-          for (int src = 0; src < CL; ++src) dh += rbuf[(src * 32 + lane) * NB + warp * PB + j];
+          for (int src = 0; src < CL; ++src) dh += rbuf[red_off<NB>(src, lane, warp * PB + j)];
         }
         if (t < len_t[j]) {
           dh += dov[j];
@@ -557,22 +600,22 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist_bwd_kernel(const BwdP
       const uint32_t rnext = sRed + ((it + 1) & 1) * RED_FLOATS * 4;
       const uint32_t rbar = mapa(sBar + 16 + 8 * ((it + 1) & 1), dst);
       if (MT == 2) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NB, r);
+        uint32_t r[NB];
+        tmem_ldn<NB>(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NB, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const uint32_t a0 = mapa(rnext + (uint32_t)((rank * 32 + lane) * NB) * 4, dst);
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
-          st_async_v4(a0 + v * 16, rbar, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+        for (int v = 0; v < NB / 4; ++v)
+          st_async_v4(a0 + ((v ^ (lane & (NB / 4 - 1))) << 4), rbar, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
                       __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
       } else {
-        uint32_t r[8];
-        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + c0col, r);
+        uint32_t r[NH];
+        tmem_ldn<NH>(tmem_base + ((uint32_t)(32 * q) << 16) + c0col, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const uint32_t a0 = mapa(rnext + (uint32_t)((rank * 32 + lane) * NB + c0col) * 4, dst);
+        const uint32_t a0 = mapa(rnext + (uint32_t)((rank * 32 + lane) * NB) * 4, dst);
 #pragma unroll
-        for (int v = 0; v < 2; ++v)
-          st_async_v4(a0 + v * 16, rbar, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+        for (int v = 0; v < NH / 4; ++v)
+          st_async_v4(a0 + (((c0col / 4 + v) ^ (lane & (NB / 4 - 1))) << 4), rbar, __uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
                       __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -590,7 +633,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist_bwd_kernel(const BwdP
       float dh = dh_carry[j];
       if (T > 0) {
 #pragma unroll
-        for (int src = 0; src < CL; ++src) dh += rbuf[(src * 32 + lane) * NB + warp * PB + j];
+        for (int src = 0; src < CL; ++src) dh += rbuf[red_off<NB>(src, lane, warp * PB + j)];
       }
       if (b < B) {
         if (p.dh0) p.dh0[(size_t)b * H + unit] = dh;
@@ -602,15 +645,15 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist_bwd_kernel(const BwdP
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == GM_WARPS)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS) : "memory");
   cluster_sync_all();
 }
 
-template <int CL>
+template <int CL, int NB>
 static int launch_bwd(cudaStream_t st, const BwdParams& p) {
   constexpr int H = 32 * CL;
   const size_t smem = (size_t)4 * H * 128 + 4 * NB * 128 + 2 * (size_t)CL * 32 * NB * 4 + 64 + 1024;
-  auto kern = lstm_persist_bwd_kernel<CL>;
+  auto kern = lstm_persist_bwd_kernel<CL, NB>;
   static bool attr = false;
   if (!attr) {
     AVSR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -638,11 +681,32 @@ static int launch_bwd(cudaStream_t st, const BwdParams& p) {
 // Debug aid (AVSR_LP_DEBUG=1, never during graph capture): prints the average clocks CTA 0 spends between
 // the phases of a forward step.
 static int lp_debug_fwd(cudaStream_t st, lp::FwdParams p, int H) {
+  {  // how many clusters of 8 can be co-resident?  (GPC granularity can strand SMs)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(128);
+    cfg.blockDim = dim3(lp::THREADS);
+    cfg.dynamicSmemBytes = (size_t)8 * 128 * 128 + 2 * (size_t)8 * 16 * 128 + 4 * 16 * 32 * 4 + 64 + 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = -1;
+    cudaFuncSetAttribute(lp::lstm_persist_fwd_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, lp::lstm_persist_fwd_kernel<8, 16>, &cfg);
+    fprintf(stderr, "[lp] cudaOccupancyMaxActiveClusters(cluster 8, %zu B smem) = %d (%s)\n", cfg.dynamicSmemBytes, ncl,
+            cudaGetErrorString(e));
+    at[0].val.clusterDim.x = 4;
+    e = cudaOccupancyMaxActiveClusters(&ncl, lp::lstm_persist_fwd_kernel<8, 16>, &cfg);
+    fprintf(stderr, "[lp] ... cluster 4 = %d; ", ncl);
+    at[0].val.clusterDim.x = 2;
+    e = cudaOccupancyMaxActiveClusters(&ncl, lp::lstm_persist_fwd_kernel<8, 16>, &cfg);
+    fprintf(stderr, "cluster 2 = %d\n", ncl);
+  }
   long long* d = nullptr;
   AVSR_CHECK_CUDA(cudaMalloc(&d, 64 * 8 * sizeof(long long)));
   AVSR_CHECK_CUDA(cudaMemset(d, 0, 64 * 8 * sizeof(long long)));
   p.dbg = d;
-  int rc = H == 256 ? lp::launch_fwd<8>(st, p) : lp::launch_fwd<4>(st, p);
+  int rc = H == 256 ? (p.B > 240 ? lp::launch_fwd<8, 32>(st, p) : lp::launch_fwd<8, 16>(st, p)) : lp::launch_fwd<4, 16>(st, p);
   AVSR_CHECK_CUDA(cudaStreamSynchronize(st));
   long long h[64 * 8];
   AVSR_CHECK_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
@@ -661,7 +725,8 @@ static int lp_debug_fwd(cudaStream_t st, lp::FwdParams p, int H) {
     fprintf(stderr, " %s=%.0f", names[k], acc[k] / (n - 2));
     tot += acc[k] / (n - 2);
   }
-  fprintf(stderr, " total=%.0f\n", tot);
+  const double ns = (double)(h[(n - 1) * 8 + 7] - h[2 * 8 + 7]) / (n - 3);
+  fprintf(stderr, " total=%.0f  wall=%.0f ns/step -> SM clock %.0f MHz\n", tot, ns, tot / ns * 1e3);
   return rc;
 }
 
@@ -675,8 +740,9 @@ int lstm_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   p.cT = r->cT; p.hT = r->hT;
   p.dbg = nullptr;
   if (getenv("AVSR_LP_DEBUG")) return lp_debug_fwd(st, p, r->H);
-  if (r->H == 256) return lp::launch_fwd<8>(st, p);
-  return lp::launch_fwd<4>(st, p);
+  // more than 15 clusters of 8 cannot be co-resident: wider slices instead of a second wave
+  if (r->H == 256) return r->B > 240 ? lp::launch_fwd<8, 32>(st, p) : lp::launch_fwd<8, 16>(st, p);
+  return r->B > 33 * 16 ? lp::launch_fwd<4, 32>(st, p) : lp::launch_fwd<4, 16>(st, p);
 }
 
 int lstm_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
@@ -686,8 +752,8 @@ int lstm_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   p.T = r->T; p.B = r->B; p.H = r->H;
   p.len = r->len; p.gates = r->gates; p.Wrec = r->Wrec; p.c0 = r->c0; p.craw = r->craw; p.dout = r->dout;
   p.dcT = r->dcT; p.dhT = r->dhT; p.dZ = r->dZ; p.dc0 = r->dc0; p.dh0 = r->dh0;
-  if (r->H == 256) return lp::launch_bwd<8>(st, p);
-  return lp::launch_bwd<4>(st, p);
+  if (r->H == 256) return r->B > 240 ? lp::launch_bwd<8, 32>(st, p) : lp::launch_bwd<8, 16>(st, p);
+  return r->B > 33 * 16 ? lp::launch_bwd<4, 32>(st, p) : lp::launch_bwd<4, 16>(st, p);
 }
 
 }  // namespace avsr

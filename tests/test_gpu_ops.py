@@ -192,7 +192,8 @@ def _lstm_case(B, T, I, H, seed, full=False):
     return x, lens, W, b, rng
 
 
-@pytest.mark.parametrize('B,T,I,H', [(3, 5, 4, 8), (5, 23, 80, 128), (8, 60, 256, 256), (64, 12, 128, 256)])
+@pytest.mark.parametrize('B,T,I,H', [(3, 5, 4, 8), (5, 23, 80, 128), (8, 60, 256, 256), (64, 12, 128, 256),
+                                     (250, 7, 64, 256)])  # > 240 utterances: 32-utterance cluster slices
 def test_lstm_layer_fwd_bwd(B, T, I, H, tensor_cores):
     ops = ops_mod()
     x, lens, W, b, rng = _lstm_case(B, T, I, H, B + T + I)
