@@ -40,6 +40,7 @@ constexpr int KB = KTOT / 64;           // 8 K-blocks of 64 halves (128 B)
 constexpr int W_BYTES = KB * 128 * 128; // 128 KB
 constexpr int OP_BYTES = KB * NB * 128; // 16 KB per operand buffer
 constexpr int MAX_TM = 384;
+constexpr int RIF = 8;                  // memory rows in flight per warp in the attention sweeps (L2 latency hiding)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -126,6 +127,23 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
 
+// Sums each of the 8 per-lane values v[0..7] over the 32 lanes with 9 shuffles (instead of 8 x 5): after each
+// exchange a lane keeps half of the values.  Returns the complete sum of v[j] in the lanes with
+// j == ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1).
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+  float k0 = (h16 ? v[4] : v[0]) + __shfl_xor_sync(0xffffffffu, h16 ? v[0] : v[4], 16);
+  float k1 = (h16 ? v[5] : v[1]) + __shfl_xor_sync(0xffffffffu, h16 ? v[1] : v[5], 16);
+  float k2 = (h16 ? v[6] : v[2]) + __shfl_xor_sync(0xffffffffu, h16 ? v[2] : v[6], 16);
+  float k3 = (h16 ? v[7] : v[3]) + __shfl_xor_sync(0xffffffffu, h16 ? v[3] : v[7], 16);
+  float m0 = (h8 ? k2 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k2, 8);
+  float m1 = (h8 ? k3 : k1) + __shfl_xor_sync(0xffffffffu, h8 ? k1 : k3, 8);
+  float n = (h4 ? m1 : m0) + __shfl_xor_sync(0xffffffffu, h4 ? m0 : m1, 4);
+  n += __shfl_xor_sync(0xffffffffu, n, 2);
+  n += __shfl_xor_sync(0xffffffffu, n, 1);
+  return n;
+}
+
 // byte offset of half element (row, k) in a K-major SWIZZLE_128B operand with 64-half K blocks of `rows` rows
 __device__ __forceinline__ uint32_t sw128h_off(int rows, int row, int k) {
   const int kb = k >> 6, kk = k & 63;
@@ -155,7 +173,12 @@ struct Params {
   float* align;          // [T,B,Tm]
   float* cT;             // [B,H] or null
   float* hT;             // [B,H] or null
+  long long* dbg;        // AVSR_AP_DEBUG: clock samples [64 steps][12] of CTA 0, thread 0
 };
+#define AP_STAMP(slot)                                                                          \
+  do {                                                                                          \
+    if (p.dbg && blockIdx.x == 0 && tid == 0 && t < 64) p.dbg[t * 12 + (slot)] = clock64();  \
+  } while (0)
 
 __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -166,13 +189,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
   const uint32_t sSc = sAct + 4 * NB * 32 * 4;       // [2][MAX_TM] scores / alignments
   const uint32_t sPart = sSc + 2 * MAX_TM * 4;       // [2][4][DM] partial contexts
   const uint32_t sRed = sPart + 2 * 4 * DM * 4;      // [2][8] reduction scratch
-  const uint32_t sBar = sRed + 64;                   // [0] mma_done [1,2] h_full[buf] [3,4] ctx_full[buf]
+  const uint32_t sQ = sRed + 64;                     // [2][H] fp32 queries
+  const uint32_t sBar = sQ + 2 * H * 4;              // [0] mma_done [1,2] h_full[buf] [3,4] ctx_full[buf]
   const uint32_t sTmem = sBar + 40;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   float* act = reinterpret_cast<float*>(gen + (sAct - base));
   float* sc_all = reinterpret_cast<float*>(gen + (sSc - base));
   float* part_all = reinterpret_cast<float*>(gen + (sPart - base));
   float* red_all = reinterpret_cast<float*>(gen + (sRed - base));
+  float* q_all = reinterpret_cast<float*>(gen + (sQ - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -287,6 +312,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
     for (int t = 0; t < T; ++t) {
       float* grow = p.gates + ((size_t)t * B + b0 + ch * 8) * 4 * H + g * H + unit;
       uint32_t r[8];
+      AP_STAMP(0);
       if (t > 0) {
         mbar_wait(sBar, (t - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -297,6 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
 #pragma unroll
         for (int b = 0; b < 8; ++b) r[b] = 0u;  // att_{-1} = 0; h_0 Wh is already in the x-projection
       }
+      AP_STAMP(1);
       float av[8];
 #pragma unroll
       for (int b = 0; b < 8; ++b) {
@@ -308,6 +335,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
         act[(g * NB + ch * 8 + b) * 32 + lane] = a;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      AP_STAMP(2);
       const uint32_t nb = (t + 1) & 1;
       const uint32_t hbar_n = sBar + 8 + 8 * nb, cbar_n = sBar + 24 + 8 * nb;
       float hv[4], ov[4], cr[4];
@@ -346,6 +374,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
 #pragma unroll
         for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) st_async_v2(mapa(dbuf, dst), mapa(hbar_n, dst), u01, u23);
       }
+      AP_STAMP(3);
       // HBM side of this step + x-projection of the next (overlaps the all-gather)
 #pragma unroll
       for (int b = 0; b < 8; ++b)
@@ -364,7 +393,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
         for (int b = 0; b < 8; ++b) gx[b] = (t + 1 < len_a[b]) ? gnext[(size_t)b * 4 * H] : 0.0f;
       }
       // ---------------- attention of utterance b_att with query h_t ----------------
+      AP_STAMP(4);
       mbar_wait(hbar_n, (t >> 1) & 1);  // every CTA's h_t slice has landed in buffer nb
+      AP_STAMP(5);
       const bool live_q = t < len_q;    // masked steps (and padding utterances) skip the memory sweep
       float ctxv[8];
 #pragma unroll
@@ -377,24 +408,28 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
           float2 a = unpack_h2(qraw.x), b = unpack_h2(qraw.y), c = unpack_h2(qraw.z), d = unpack_h2(qraw.w);
           q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y; q[4] = c.x; q[5] = c.y; q[6] = d.x; q[7] = d.y;
         }
-        // scores: rows tm = w4 + 4*i, four rows in flight
-        for (int tm0 = w4; tm0 < L; tm0 += 16) {
-          uint4 k[4];
+        // scores: rows tm = w4 + 4*i, RIF rows in flight per warp, one 9-shuffle reduction per batch of 8 rows
+        static_assert(RIF == 8, "warp_reduce8 expects 8 rows per batch");
+        const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
+          uint4 k[RIF];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < RIF; ++j) {
             const int tm = tm0 + 4 * j;
             k[j] = tm < L ? __ldg(reinterpret_cast<const uint4*>(p.keys + ((size_t)tm * B + b_att) * H) + lane)
                           : make_uint4(0, 0, 0, 0);
           }
+          float sacc[RIF];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < RIF; ++j) {
             float2 a = unpack_h2(k[j].x), b = unpack_h2(k[j].y), c = unpack_h2(k[j].z), d = unpack_h2(k[j].w);
-            float s = a.x * q[0] + a.y * q[1] + b.x * q[2] + b.y * q[3] + c.x * q[4] + c.y * q[5] + d.x * q[6] + d.y * q[7];
-            s = warp_sum(s);
-            if (lane == 0 && tm0 + 4 * j < L) sc[tm0 + 4 * j] = gs * s;
+            sacc[j] = a.x * q[0] + a.y * q[1] + b.x * q[2] + b.y * q[3] + c.x * q[4] + c.y * q[5] + d.x * q[6] + d.y * q[7];
           }
+          const float tot = warp_reduce8(sacc, lane);
+          if ((lane & 3) == 0 && tm0 + 4 * jrow < L) sc[tm0 + 4 * jrow] = gs * tot;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        AP_STAMP(6);
         // masked softmax over the L scores (128 threads)
         float mx = -INFINITY;
         for (int tm = gt; tm < L; tm += 128) mx = fmaxf(mx, sc[tm]);
@@ -419,19 +454,20 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
           arow[tm] = a;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        AP_STAMP(7);
         // context: rows tm = w4 + 4*i, lane accumulates dims 8*lane .. +7
-        for (int tm0 = w4; tm0 < L; tm0 += 16) {
-          uint4 v[4];
-          float a[4];
+        for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
+          uint4 v[RIF];
+          float a[RIF];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < RIF; ++j) {
             const int tm = tm0 + 4 * j;
             a[j] = tm < L ? sc[tm] : 0.0f;
             v[j] = tm < L ? __ldg(reinterpret_cast<const uint4*>(p.values + ((size_t)tm * B + b_att) * DM) + lane)
                           : make_uint4(0, 0, 0, 0);
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < RIF; ++j) {
             float2 x0 = unpack_h2(v[j].x), x1 = unpack_h2(v[j].y), x2 = unpack_h2(v[j].z), x3 = unpack_h2(v[j].w);
             ctxv[0] = fmaf(a[j], x0.x, ctxv[0]); ctxv[1] = fmaf(a[j], x0.y, ctxv[1]);
             ctxv[2] = fmaf(a[j], x1.x, ctxv[2]); ctxv[3] = fmaf(a[j], x1.y, ctxv[3]);
@@ -439,6 +475,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
             ctxv[6] = fmaf(a[j], x3.x, ctxv[6]); ctxv[7] = fmaf(a[j], x3.y, ctxv[7]);
           }
         }
+        AP_STAMP(8);
 #pragma unroll
         for (int e = 0; e < 8; ++e) part[w4 * DM + 8 * lane + e] = ctxv[e];
         asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
@@ -466,6 +503,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
 #pragma unroll
         for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) st_async_v4(mapa(dbuf, dst), mapa(cbar_n, dst), c0, c1, c2, c3);
       }
+      AP_STAMP(9);
     }
     if (comb && b0 + bq < B) {
       const size_t o = (size_t)(b0 + bq) * H + 32 * rank + 4 * uq;
@@ -481,7 +519,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
   cluster_sync_all();
 }
 
-constexpr size_t SMEM_BYTES = (size_t)W_BYTES + 2 * OP_BYTES + 4 * NB * 32 * 4 + 2 * MAX_TM * 4 + 2 * 4 * DM * 4 + 64 + 64 + 1024;
+constexpr size_t SMEM_BYTES = (size_t)W_BYTES + 2 * OP_BYTES + 4 * NB * 32 * 4 + 2 * MAX_TM * 4 + 2 * 4 * DM * 4 + 64 + 2 * H * 4 + 64 + 1024;
 
 __global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -694,22 +732,24 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
 #pragma unroll
         for (int e = 0; e < 8; ++e) dcx[e] = dctx_s[8 * lane + e];
         // d(align)[tm] = values[tm] . dctx
-        for (int tm0 = w4; tm0 < L; tm0 += 16) {
-          uint4 v[4];
+        const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
+          uint4 v[RIF];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < RIF; ++j) {
             const int tm = tm0 + 4 * j;
             v[j] = tm < L ? __ldg(reinterpret_cast<const uint4*>(p.values + ((size_t)tm * B + b_att) * DM) + lane)
                           : make_uint4(0, 0, 0, 0);
           }
+          float sacc[RIF];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < RIF; ++j) {
             float2 x0 = unpack_h2(v[j].x), x1 = unpack_h2(v[j].y), x2 = unpack_h2(v[j].z), x3 = unpack_h2(v[j].w);
-            float s = x0.x * dcx[0] + x0.y * dcx[1] + x1.x * dcx[2] + x1.y * dcx[3] + x2.x * dcx[4] + x2.y * dcx[5] +
+            sacc[j] = x0.x * dcx[0] + x0.y * dcx[1] + x1.x * dcx[2] + x1.y * dcx[3] + x2.x * dcx[4] + x2.y * dcx[5] +
                       x3.x * dcx[6] + x3.y * dcx[7];
-            s = warp_sum(s);
-            if (lane == 0 && tm0 + 4 * j < L) ds_s[tm0 + 4 * j] = s;
           }
+          const float tot = warp_reduce8(sacc, lane);
+          if ((lane & 3) == 0 && tm0 + 4 * jrow < L) ds_s[tm0 + 4 * jrow] = tot;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
         float dot = 0.0f;
@@ -733,18 +773,18 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
           qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
         }
         float gacc = 0.0f;
-        for (int tm0 = w4; tm0 < L; tm0 += 16) {
-          uint4 k[4];
-          float d[4];
+        for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
+          uint4 k[RIF];
+          float d[RIF];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < RIF; ++j) {
             const int tm = tm0 + 4 * j;
             d[j] = tm < L ? ds_s[tm] : 0.0f;
             k[j] = tm < L ? __ldg(reinterpret_cast<const uint4*>(p.keys + ((size_t)tm * B + b_att) * H) + lane)
                           : make_uint4(0, 0, 0, 0);
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < RIF; ++j) {
             float2 x0 = unpack_h2(k[j].x), x1 = unpack_h2(k[j].y), x2 = unpack_h2(k[j].z), x3 = unpack_h2(k[j].w);
             const float kk[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
             float raw = 0.0f;
@@ -947,6 +987,13 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   p.len = r->len; p.mem_len = m.mem_len; p.gates = r->gates; p.Wp = Wp; p.keys = keys_h; p.values = values_h;
   p.g = m.g; p.c0 = r->c0; p.S = r->S; p.SW = SW; p.At = At; p.craw = r->craw; p.out = r->out; p.hc = m.hc;
   p.align = m.align; p.cT = r->cT; p.hT = r->hT;
+  p.dbg = nullptr;
+  long long* dbg_dev = nullptr;
+  if (getenv("AVSR_AP_DEBUG")) {
+    AVSR_CHECK_CUDA(cudaMalloc(&dbg_dev, 64 * 12 * sizeof(long long)));
+    AVSR_CHECK_CUDA(cudaMemset(dbg_dev, 0, 64 * 12 * sizeof(long long)));
+    p.dbg = dbg_dev;
+  }
   static bool attr = false;
   if (!attr) {
     AVSR_CHECK_CUDA(cudaFuncSetAttribute(attn_lstm_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -967,6 +1014,27 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   cfg.numAttrs = 1;
   AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_lstm_persist_fwd_kernel, p));
   ++g_launch_count;
+  if (dbg_dev) {
+    AVSR_CHECK_CUDA(cudaStreamSynchronize(st));
+    long long h[64 * 12];
+    AVSR_CHECK_CUDA(cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(dbg_dev);
+    const int n = T < 64 ? T : 64;
+    const char* names[10] = {"loop-top", "wait MMA+ld", "act+bar", "combine+send h", "hbm st/ld", "wait h gather",
+                             "scores", "softmax", "ctx sweep", "reduce+send ctx"};
+    double acc[10] = {0};
+    for (int t = 3; t < n; ++t) {
+      for (int k = 1; k < 10; ++k) acc[k] += (double)(h[t * 12 + k] - h[t * 12 + k - 1]);
+      acc[0] += (double)(h[t * 12] - h[(t - 1) * 12 + 9]);
+    }
+    fprintf(stderr, "[ap fwd T=%d B=%d Tm=%d] clocks/step:", T, B, m.Tm);
+    double tot = 0;
+    for (int k = 0; k < 10; ++k) {
+      fprintf(stderr, " %s=%.0f", names[k], acc[k] / (n - 3));
+      tot += acc[k] / (n - 3);
+    }
+    fprintf(stderr, " total=%.0f\n", tot);
+  }
   // attention vectors of all steps in one product: S[1:, :, :At] = [h | ctx] Wl (tf32-rounded operand rows)
   AVSR_TRY(gemm(st, 0, 0, T * B, At, H + DM, m.hc, H + DM, m.Wl, m.A, r->S + (size_t)B * SW, SW, 0.0f, nullptr, 1));
   return 0;

@@ -141,15 +141,24 @@ __global__ void embedding_fwd_kernel(const float* __restrict__ table, int V, int
   out[i] = (id >= 0 && id < V) ? table[(size_t)id * E + e] : 0.0f;
 }
 
-// deterministic: one block per vocabulary row scans all ids
+// block (v, chunk): sums the rows of one chunk of ids that hit vocabulary row v, one atomic per (v, e, chunk)
+constexpr int EMB_CHUNK = 512;
 __global__ void embedding_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ ids, long long n, int E,
                                      float* __restrict__ dtable) {
   const int v = blockIdx.x;
+  const long long r0 = (long long)blockIdx.y * EMB_CHUNK, r1 = min(n, r0 + EMB_CHUNK);
+  __shared__ int hit[EMB_CHUNK];
+  __shared__ int nhit;
+  if (threadIdx.x == 0) nhit = 0;
+  __syncthreads();
+  for (long long r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+    if (ids[r] == v) hit[atomicAdd(&nhit, 1)] = (int)(r - r0);
+  __syncthreads();
+  if (nhit == 0) return;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     float acc = 0.0f;
-    for (long long r = 0; r < n; ++r)
-      if (ids[r] == v) acc += dout[r * E + e];
-    dtable[(size_t)v * E + e] += acc;
+    for (int i = 0; i < nhit; ++i) acc += dout[(r0 + hit[i]) * E + e];
+    atomicAdd(dtable + (size_t)v * E + e, acc);
   }
 }
 
@@ -450,7 +459,7 @@ int avsr_embedding_fwd(avsr_stream_t s, const float* table, int V, int E, const 
 int avsr_embedding_bwd(avsr_stream_t s, const float* dout, const int* ids, long long n, int V, int E,
                        float* dtable) {
   if (n <= 0) return 0;
-  AVSR_LAUNCH(embedding_bwd_kernel, V, 128, 0, ST(s), dout, ids, n, E, dtable);
+  AVSR_LAUNCH(embedding_bwd_kernel, dim3(V, cdiv(n, EMB_CHUNK)), 128, 0, ST(s), dout, ids, n, E, dtable);
   return 0;
 }
 

@@ -92,6 +92,7 @@ class Seq2SeqModel(object):
         self._init_saver()
         self._batch = None
         self._in_sets, self._in, self._meta = {}, None, None
+        self._stage_sets, self._pending, self._copy_stream = {}, None, None
         self._graphs = {}
         self.use_cuda_graph = False  # opt-in: train_step replays one captured graph per batch shape
         self.launches_last_step = 0
@@ -184,9 +185,9 @@ class Seq2SeqModel(object):
             a = torch.from_numpy(np.ascontiguousarray(a))
         return a if a.dtype == dtype else a.to(dtype)
 
-    def feed(self, data_sequences):
-        """Copy one batch (batch-major like the reference; numpy / pinned host / device tensors) into
-        static device buffers.  The layout change to frame-major happens on the device (_prep)."""
+    def _collect(self, data_sequences):
+        """Batch (batch-major like the reference; numpy / pinned host / device tensors) -> source tensors,
+        host-side metadata and the shape key of the static buffers / captured graph."""
         video, audio = data_sequences
         ref = audio if audio is not None else video
         src = {}
@@ -207,20 +208,69 @@ class Seq2SeqModel(object):
             src['labels'] = self._as_tensor(ref.labels, torch.int32)
             src['labels_len'] = self._as_tensor(ll, torch.int32)
         key = tuple((k, tuple(v.shape)) for k, v in sorted(src.items())) + (meta.get('T_dec', 0),)
+        meta['key'] = key
+        meta['h2d_bytes'] = sum(v.numel() * v.element_size() for v in src.values() if not v.is_cuda)
+        return src, meta
+
+    def _static_buffers(self, key, src):
         bufs = self._in_sets.get(key)
         if bufs is None:
             bufs = {k: torch.empty(v.shape, dtype=v.dtype, device='cuda') for k, v in src.items()}
             self._in_sets[key] = bufs
-        nbytes = 0
+        return bufs
+
+    def feed(self, data_sequences):
+        """Copy one batch into the static device buffers of its shape (the layout change to frame-major
+        happens on the device, _prep)."""
+        src, meta = self._collect(data_sequences)
+        bufs = self._static_buffers(meta['key'], src)
         for k, v in src.items():
             bufs[k].copy_(v, non_blocking=True)
-            if not v.is_cuda:
-                nbytes += v.numel() * v.element_size()
-        self.h2d_bytes = nbytes
-        meta['key'] = key
+        self.h2d_bytes = meta['h2d_bytes']
         self._in, self._meta = bufs, meta
         self._batch = None
+        self._pending = None
         return meta
+
+    def prefetch(self, data_sequences):
+        """Input-pipeline overlap: start the host->device copy of the NEXT batch on a copy stream while the
+        current step computes (two staging sets per shape).  The next train_step() without arguments picks
+        it up.  Mirrors tf.data's prefetch in the reference (io_utils.py:145)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        src, meta = self._collect(data_sequences)
+        key = meta['key']
+        self._static_buffers(key, src)
+        sets = self._stage_sets.setdefault(key, [None, None, 0])
+        slot = sets[2] & 1
+        sets[2] += 1
+        if sets[slot] is None:
+            sets[slot] = ({k: torch.empty(v.shape, dtype=v.dtype, device='cuda') for k, v in src.items()}, None)
+        stage, free_ev = sets[slot]
+        with torch.cuda.stream(self._copy_stream):
+            if free_ev is not None:
+                self._copy_stream.wait_event(free_ev)  # the compute stream has finished reading this staging set
+            for k, v in src.items():
+                stage[k].copy_(v, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        self._pending = (key, slot, meta, ready)
+
+    def _consume_prefetch(self):
+        key, slot, meta, ready = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready)
+        stage, _ = self._stage_sets[key][slot]
+        bufs = self._in_sets[key]
+        for k, v in stage.items():
+            bufs[k].copy_(v, non_blocking=True)  # device-to-device into the buffers the captured graph reads
+        free_ev = torch.cuda.Event()
+        free_ev.record(cur)
+        self._stage_sets[key][slot] = (stage, free_ev)
+        self.h2d_bytes = meta['h2d_bytes']
+        self._in, self._meta = bufs, meta
+        self._batch = None
 
     def _prep(self):
         """Device-side batch preparation (capturable): batch-major -> frame-major, GO-prefixed ids."""
@@ -378,6 +428,8 @@ class Seq2SeqModel(object):
             raise Exception('train_step needs mode == `train`')
         if data_sequences is not None:
             self.feed(data_sequences)
+        elif self._pending is not None:
+            self._consume_prefetch()
         self._set_step_scalars()
         if self.use_cuda_graph:
             key = self._meta['key']
