@@ -62,6 +62,7 @@ PROTOTYPES = {
     'avsr_reverse_sequence': (_I, [_P, _P, _P, _I, _I, _I, _P]),
     'avsr_transpose01': (_I, [_P, _P, _P, _I, _I, _I]),
     'avsr_rnn_work_floats': (C.c_size_t, [_I, _I, _I, _I, _I, _I]),
+    'avsr_struct_sizes': (_I, [C.POINTER(C.c_int)]),
     'avsr_rnn_seq_fwd': (_I, [_P, C.POINTER(AvsrRnnSeq)]),
     'avsr_rnn_seq_bwd': (_I, [_P, C.POINTER(AvsrRnnSeq)]),
     'avsr_normed_v_fwd': (_I, [_P, _P, _P, _I, _P]),
@@ -97,6 +98,11 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    sizes = (C.c_int * 2)()
+    lib.avsr_struct_sizes(sizes)
+    if (sizes[0], sizes[1]) != (C.sizeof(AvsrAttnMech), C.sizeof(AvsrRnnSeq)):
+        raise AvsrError('struct layout mismatch between include/avsr_b200.h and _lib.py: C %s vs ctypes %s'
+                        % ((sizes[0], sizes[1]), (C.sizeof(AvsrAttnMech), C.sizeof(AvsrRnnSeq))))
     _lib = lib
     return lib
 

@@ -59,6 +59,11 @@ int avsr_get_tensor_cores(void) { return g_use_tc; }
 size_t avsr_rnn_work_floats(int B, int H, int At, int maxHD, int maxA, int maxTm) {
   return rnn_work_floats(B, H, At, maxHD, maxA, maxTm);
 }
+int avsr_struct_sizes(int* out2) {
+  out2[0] = (int)sizeof(AvsrAttnMech);
+  out2[1] = (int)sizeof(AvsrRnnSeq);
+  return 0;
+}
 int avsr_rnn_seq_fwd(avsr_stream_t s, const AvsrRnnSeq* r) { return rnn_seq_fwd((cudaStream_t)s, r); }
 int avsr_rnn_seq_bwd(avsr_stream_t s, const AvsrRnnSeq* r) { return rnn_seq_bwd((cudaStream_t)s, r); }
 

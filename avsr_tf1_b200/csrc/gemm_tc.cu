@@ -381,7 +381,8 @@ int gemm_tc(cudaStream_t st, int transA, int transB, int M, int N, int K, const 
   const int tiles = p.tiles_m * p.tiles_n;
   int splitk = 1;
   if (tiles < sm_count && p.k_tiles >= 16 && !round_out) {
-    splitk = min(p.k_tiles / 8, cdiv(sm_count, tiles));
+    // as many K splits as fit in ONE wave of CTAs (a 149th work item would double the kernel time)
+    splitk = min(p.k_tiles / 8, sm_count / tiles);
     if (splitk < 1) splitk = 1;
   }
   p.k_tiles_per_split = cdiv(p.k_tiles, splitk);

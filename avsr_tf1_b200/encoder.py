@@ -212,8 +212,9 @@ class AttentiveEncoder(Seq2SeqEncoder):
         self._bw = None
         self.output_dim = self._top.out_dim
 
-    def forward(self, inputs, inputs_len, attended_memory=None, attended_memory_length=None,
-                attended_memory_operand=None):
+    def forward_lower(self, inputs, inputs_len):
+        """Input BN + the plain layers under the attention layer (independent of the video stream, so the
+        model can run it concurrently with the video encoder)."""
         train = self._mode == 'train'
         self._lens = inputs_len
         if self._bn is not None:
@@ -224,22 +225,39 @@ class AttentiveEncoder(Seq2SeqEncoder):
         for op in self._fw:
             op.forward(cur_op, inputs_len)
             cur_op = op.operand
+        self._lower_out_op = cur_op
+
+    def forward_top(self, attended_memory, attended_memory_length, attended_memory_operand=None):
         self._outputs = self._top.forward(
-            cur_op, inputs_len, memories=[(attended_memory, attended_memory_length, attended_memory_operand)])
+            self._lower_out_op, self._lens,
+            memories=[(attended_memory, attended_memory_length, attended_memory_operand)])
         self._outputs_op = self._top.operand
         self._final = self._top.final  # wrapper stripped: cell state only (encoder.py:314-330)
         self.attention_alignment = self._top.bufs[0].align  # [T_audio, B, T_video]
         self.attention_contexts = self._top.bufs[0].hc      # [T_audio, B, H + Dm]
         return self.get_data()
 
-    def backward(self, doutputs, dfinal_state=None, need_dx=False):
-        """Returns (dx, dmemory) - dmemory is the gradient wrt the video encoder outputs."""
+    def forward(self, inputs, inputs_len, attended_memory=None, attended_memory_length=None,
+                attended_memory_operand=None):
+        self.forward_lower(inputs, inputs_len)
+        return self.forward_top(attended_memory, attended_memory_length, attended_memory_operand)
+
+    def backward_top(self, doutputs, dfinal_state=None):
+        """Returns (gradient wrt the lower layers' output, dmemory = gradient wrt the video encoder outputs)."""
         if doutputs is None:
             doutputs = ops.zeros(*self._outputs.shape)
         d, dmem, _ = self._top.backward(doutputs, dfinal_state, need_dx=True, want_init_grad=False)
+        return d, dmem[0]
+
+    def backward_lower(self, d, need_dx=False):
         for i in range(len(self._fw) - 1, -1, -1):
             need = (i > 0) or need_dx or self._bn is not None
             d = self._fw[i].backward(d, None, need_dx=need)
         if self._bn is not None and d is not None:
             d = self._bn.backward(d)
-        return d, dmem[0]
+        return d
+
+    def backward(self, doutputs, dfinal_state=None, need_dx=False):
+        """Returns (dx, dmemory) - dmemory is the gradient wrt the video encoder outputs."""
+        d, dmem = self.backward_top(doutputs, dfinal_state)
+        return self.backward_lower(d, need_dx), dmem

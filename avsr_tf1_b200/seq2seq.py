@@ -93,6 +93,8 @@ class Seq2SeqModel(object):
         self._batch = None
         self._in_sets, self._in, self._meta = {}, None, None
         self._stage_sets, self._pending, self._copy_stream = {}, None, None
+        self._side_stream = None
+        self.overlap_streams = True  # independent encoder branches run on two streams
         self._graphs = {}
         self.use_cuda_graph = False  # opt-in: train_step replays one captured graph per batch shape
         self.launches_last_step = 0
@@ -292,18 +294,39 @@ class Seq2SeqModel(object):
         return b
 
     # ---- forward ---------------------------------------------------------------------
+    def _fork(self):
+        """Side stream forked from the current one (also under graph capture): the video encoder and the
+        audio layers below the cross-modal attention are independent, and a persistent LSTM kernel with
+        32-utterance slices occupies only 64 of the 148 SMs, so two of them run side by side."""
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+        self._side_stream.wait_stream(torch.cuda.current_stream())
+        return self._side_stream
+
+    def _join(self):
+        torch.cuda.current_stream().wait_stream(self._side_stream)
+
     def _encode(self, b):
         enc = {}
+        both = self._video_encoder is not None and self._audio_encoder is not None
+        overlap = both and self.overlap_streams
         if self._video_encoder is not None:
-            enc['video'] = self._video_encoder.forward(b['video'], b['video_len'])
+            if overlap:
+                with torch.cuda.stream(self._fork()):
+                    enc['video'] = self._video_encoder.forward(b['video'], b['video_len'])
+            else:
+                enc['video'] = self._video_encoder.forward(b['video'], b['video_len'])
         if self._audio_encoder is not None:
             if isinstance(self._audio_encoder, AttentiveEncoder):
-                enc['audio'] = self._audio_encoder.forward(b['audio'], b['audio_len'],
-                                                           attended_memory=enc['video'].outputs,
-                                                           attended_memory_length=b['video_len'],
-                                                           attended_memory_operand=enc['video'].outputs_operand)
+                self._audio_encoder.forward_lower(b['audio'], b['audio_len'])
+                if overlap:
+                    self._join()
+                enc['audio'] = self._audio_encoder.forward_top(enc['video'].outputs, b['video_len'],
+                                                               enc['video'].outputs_operand)
             else:
                 enc['audio'] = self._audio_encoder.forward(b['audio'], b['audio_len'])
+                if overlap:
+                    self._join()
         return enc
 
     def _decoder_inputs(self, b, enc):
@@ -334,13 +357,28 @@ class Seq2SeqModel(object):
         self._decoder.forward_train(mems, states, b['dec_in_ids'], b['labels'], b['labels_len'], b['T_dec'],
                                     self._scal_dev[0:1], self._loss_dev[0:1])
         dmem, dstates = self._decoder.backward_train()
+        both = self._video_encoder is not None and self._audio_encoder is not None
+        overlap = both and self.overlap_streams
         if self._hparams.architecture == 'bimodal':
-            self._audio_encoder.backward(dmem[1], dstates[1])
-            self._video_encoder.backward(dmem[0], dstates[0])
+            if overlap:
+                with torch.cuda.stream(self._fork()):
+                    self._video_encoder.backward(dmem[0], dstates[0])
+                self._audio_encoder.backward(dmem[1], dstates[1])
+                self._join()
+            else:
+                self._audio_encoder.backward(dmem[1], dstates[1])
+                self._video_encoder.backward(dmem[0], dstates[0])
         elif self._audio_encoder is not None:
             if isinstance(self._audio_encoder, AttentiveEncoder):
-                _, dvid = self._audio_encoder.backward(dmem[0], dstates[0])
-                self._video_encoder.backward(dvid, None)
+                d_lower, dvid = self._audio_encoder.backward_top(dmem[0], dstates[0])
+                if overlap:
+                    with torch.cuda.stream(self._fork()):
+                        self._video_encoder.backward(dvid, None)
+                    self._audio_encoder.backward_lower(d_lower)
+                    self._join()
+                else:
+                    self._audio_encoder.backward_lower(d_lower)
+                    self._video_encoder.backward(dvid, None)
             else:
                 self._audio_encoder.backward(dmem[0], dstates[0])
         else:

@@ -142,6 +142,8 @@ typedef struct AvsrRnnSeq {
 
 /* At = sum of mechanism A; maxHD = max(H+Dm); maxA = max A; maxTm = max memory length (0,0,0,0 without attention) */
 size_t avsr_rnn_work_floats(int B, int H, int At, int maxHD, int maxA, int maxTm);
+/* sizeof(AvsrAttnMech), sizeof(AvsrRnnSeq) as compiled (bindings check their struct layout against it) */
+int avsr_struct_sizes(int* out2);
 int avsr_rnn_seq_fwd(avsr_stream_t stream, const AvsrRnnSeq* r);
 int avsr_rnn_seq_bwd(avsr_stream_t stream, const AvsrRnnSeq* r);
 
