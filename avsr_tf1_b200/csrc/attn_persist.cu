@@ -29,16 +29,14 @@
 namespace avsr {
 namespace ap {
 
-constexpr int GM_WARPS = 8;
-constexpr int THREADS = (GM_WARPS + 1) * 32;
-constexpr int NB = 16;
+// NB = utterances per cluster: 16 (8 gate/attention warps per CTA) up to 240 utterances; 32 (16 warps) above,
+// because a B200 keeps at most 15 clusters of 8 CTAs resident and a 16th cluster would run as a second wave.
 constexpr int CL = 8;
 constexpr int H = 256;
 constexpr int DM = 256;
 constexpr int KTOT = H + DM;            // 512
 constexpr int KB = KTOT / 64;           // 8 K-blocks of 64 halves (128 B)
 constexpr int W_BYTES = KB * 128 * 128; // 128 KB
-constexpr int OP_BYTES = KB * NB * 128; // 16 KB per operand buffer
 constexpr int MAX_TM = 384;
 constexpr int RIF = 8;                  // memory rows in flight per warp in the attention sweeps (L2 latency hiding)
 
@@ -150,8 +148,10 @@ __device__ __forceinline__ uint32_t sw128h_off(int rows, int row, int k) {
   return (uint32_t)(kb * rows * 128 + row * 128 + ((((kk >> 3) ^ (row & 7)) << 4)) + ((kk & 7) << 1));
 }
 
-// instruction descriptor: D = f32, A = B = f16, both K-major, N = NB, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor: D = f32, A = B = f16, both K-major, N = nb, M = 128
+__host__ __device__ constexpr uint32_t idesc_for(int nb) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(nb >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
 
 struct Params {
   int T, B, Tm;
@@ -180,24 +180,38 @@ struct Params {
     if (p.dbg && blockIdx.x == 0 && tid == 0 && t < 64) p.dbg[t * 12 + (slot)] = clock64();  \
   } while (0)
 
-__global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const Params p) {
+template <int NB>
+struct FwdCfg {
+  static constexpr int GMW = NB / 2;                  // gate-math / attention warps (4 per attended utterance)
+  static constexpr int THREADS = (GMW + 1) * 32;      // + 1 MMA-issue warp
+  static constexpr int NU = NB / CL;                  // utterances whose attention this CTA owns
+  static constexpr int OP_BYTES = KB * NB * 128;      // one [h | ctx] operand buffer
+  // the partial-context scratch [NU][4][DM] aliases the activation exchange buffer [4][NB][32] (same size): the
+  // activations of step t+1 are only written after every context of step t has been all-gathered
+  static constexpr size_t SMEM = (size_t)W_BYTES + 2 * OP_BYTES + 4 * NB * 32 * 4 + NU * MAX_TM * 4 + NU * 8 * 4 + 64 + 1024;
+  static_assert(NU * 4 * DM == 4 * NB * 32, "partial-context scratch must fit the activation buffer");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+template <int NB>
+__global__ void __launch_bounds__(FwdCfg<NB>::THREADS, 1) attn_lstm_persist_fwd_kernel(const Params p) {
+  constexpr int GM_WARPS = FwdCfg<NB>::GMW, THREADS = FwdCfg<NB>::THREADS, NU = FwdCfg<NB>::NU;
+  constexpr int OP_BYTES = FwdCfg<NB>::OP_BYTES;
+  constexpr uint32_t IDESC = idesc_for(NB);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW = base;
   const uint32_t sOp = sW + W_BYTES;                 // two operand buffers [h | ctx]
-  const uint32_t sAct = sOp + 2 * OP_BYTES;          // [4][NB][32] floats
-  const uint32_t sSc = sAct + 4 * NB * 32 * 4;       // [2][MAX_TM] scores / alignments
-  const uint32_t sPart = sSc + 2 * MAX_TM * 4;       // [2][4][DM] partial contexts
-  const uint32_t sRed = sPart + 2 * 4 * DM * 4;      // [2][8] reduction scratch
-  const uint32_t sQ = sRed + 64;                     // [2][H] fp32 queries
-  const uint32_t sBar = sQ + 2 * H * 4;              // [0] mma_done [1,2] h_full[buf] [3,4] ctx_full[buf]
+  const uint32_t sAct = sOp + 2 * OP_BYTES;          // [4][NB][32] floats; also [NU][4][DM] partial contexts
+  const uint32_t sSc = sAct + 4 * NB * 32 * 4;       // [NU][MAX_TM] scores / alignments
+  const uint32_t sRed = sSc + NU * MAX_TM * 4;       // [NU][8] reduction scratch
+  const uint32_t sBar = sRed + NU * 8 * 4;           // [0] mma_done [1,2] h_full[buf] [3,4] ctx_full[buf]
   const uint32_t sTmem = sBar + 40;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   float* act = reinterpret_cast<float*>(gen + (sAct - base));
   float* sc_all = reinterpret_cast<float*>(gen + (sSc - base));
-  float* part_all = reinterpret_cast<float*>(gen + (sPart - base));
+  float* part_all = act;
   float* red_all = reinterpret_cast<float*>(gen + (sRed - base));
-  float* q_all = reinterpret_cast<float*>(gen + (sQ - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -272,8 +286,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
     // ================= gate math + attention warps =================
     const int g = warp & 3, ch = warp >> 2;
     const int unit = 32 * rank + lane;
-    const bool comb = tid < 128;
-    const int uq = tid & 7, bq = (tid >> 3) & 15;
+    const bool comb = tid < 8 * NB;
+    const int uq = tid & 7, bq = (tid >> 3) & (NB - 1);
     float c_state[4], h_state[4];
     int len_c = 0;
 #pragma unroll
@@ -299,7 +313,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
     }
     // attention role: utterance jl of this CTA, warp w4 of its group of four
     const int jl = warp >> 2, w4 = warp & 3, gt = tid & 127;
-    const int bl_att = 2 * (int)rank + jl;       // row of the utterance in the operand buffers
+    const int bl_att = NU * (int)rank + jl;      // row of the utterance in the operand buffers
     const int b_att = b0 + bl_att;
     const int len_q = (b_att < B) ? p.len[b_att] : 0;
     const int L = (b_att < B) ? min(p.mem_len[b_att], Tm) : 0;
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
         av[b] = a;
         act[(g * NB + ch * 8 + b) * 32 + lane] = a;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(GM_WARPS * 32) : "memory");
       AP_STAMP(2);
       const uint32_t nb = (t + 1) & 1;
       const uint32_t hbar_n = sBar + 8 + 8 * nb, cbar_n = sBar + 24 + 8 * nb;
@@ -519,7 +533,6 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_fwd_kernel(const
   cluster_sync_all();
 }
 
-constexpr size_t SMEM_BYTES = (size_t)W_BYTES + 2 * OP_BYTES + 4 * NB * 32 * 4 + 2 * MAX_TM * 4 + 2 * 4 * DM * 4 + 64 + 2 * H * 4 + 64 + 1024;
 
 __global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -562,22 +575,36 @@ struct BwdParams {
 };
 
 constexpr int BW_W_BYTES = 2 * KTOT * 128;           // A operand: 2 K-blocks x [512 rows x 128 B]
-constexpr int BW_DZ_BYTES = 2 * NB * 128;            // B operand: 2 K-blocks x [16 rows x 128 B]
-constexpr int REDH_FLOATS = CL * 32 * NB;            // [src][u][b]
-constexpr int REDC_FLOATS = CL * 2 * DM;             // [src][utt][dim]
-constexpr int DQ_FLOATS = CL * 2 * 32;               // [src][utt][u]
+
+template <int NB>
+struct BwdCfg {
+  static constexpr int GMW = NB / 2;
+  static constexpr int THREADS = (GMW + 1) * 32;
+  static constexpr int NU = NB / CL;                   // utterances whose attention backward this CTA owns
+  static constexpr int DZ_BYTES = 2 * NB * 128;        // B operand: 2 K-blocks x [NB rows x 128 B]
+  static constexpr int REDH_FLOATS = CL * 32 * NB;     // [src][u][b]
+  static constexpr int REDC_FLOATS = CL * NU * DM;     // [src][utt][dim]; also the dq partial scratch [NU][4][DM]
+  static constexpr int DQ_FLOATS = CL * NU * 32;       // [src][utt][u]
+  static constexpr int TCOLS = 4 * NB;                 // TMEM columns: four 128-row tiles of [h | ctx]
+  static constexpr size_t SMEM = (size_t)BW_W_BYTES + DZ_BYTES + REDH_FLOATS * 4 + REDC_FLOATS * 4 + DQ_FLOATS * 4 +
+                                 NU * DM * 4 + 2 * NU * MAX_TM * 4 + NU * 8 * 4 + 64 + 1024;
+  static_assert(NU * 4 * DM <= REDC_FLOATS, "dq partial scratch must fit the ctx reduce buffer");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
 
 __device__ __forceinline__ void st_async_v4f(uint32_t addr, uint32_t mbar, float a, float b, float c, float d) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%2, %3, %4, %5}, [%1];" ::"r"(addr),
                "r"(mbar), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
-__device__ __forceinline__ void st_async_v2f(uint32_t addr, uint32_t mbar, float a, float b) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%2, %3}, [%1];" ::"r"(addr),
-               "r"(mbar), "f"(a), "f"(b)
+__device__ __forceinline__ void st_async_f(uint32_t addr, uint32_t mbar, float a) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %2, [%1];" ::"r"(addr), "r"(mbar), "f"(a)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+template <int N>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&r)[N]);
+template <>
+__device__ __forceinline__ void tmem_ldn<16>(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -585,22 +612,47 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+template <>
+__device__ __forceinline__ void tmem_ldn<32>(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 
-__global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const BwdParams p) {
+// Per iteration (time step t = T-1-it) and CTA:
+//   top   wait for the partial sums pushed during the previous iteration (h rows -> redH, ctx rows -> redC) and
+//         fold them into registers / dctx_s; ONE CTA-wide barrier: from here on redH and redC are free again, so a
+//         single copy of each suffices (a peer can only push the next partials after it has received this CTA's
+//         dq, which leaves after the barrier) and redC doubles as the dq partial scratch
+//   A/B   attention backward of the CTA's utterances, dq all-to-all
+//   C/D   gate gradients dz_t -> shared-memory operand, HBM
+//   E     partial products from TMEM -> owners (reduce-scatter through DSMEM)
+template <int NB>
+__global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_kernel(const BwdParams p) {
+  using C = BwdCfg<NB>;
+  constexpr int GM_WARPS = C::GMW, THREADS = C::THREADS, NU = C::NU;
+  constexpr int REDH_FLOATS = C::REDH_FLOATS, REDC_FLOATS = C::REDC_FLOATS, DQ_FLOATS = C::DQ_FLOATS;
+  constexpr uint32_t IDESC = idesc_for(NB);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW = base;
   const uint32_t sDz = sW + BW_W_BYTES;
-  const uint32_t sRedH = sDz + BW_DZ_BYTES;                  // two parities
-  const uint32_t sRedC = sRedH + 2 * REDH_FLOATS * 4;
+  const uint32_t sRedH = sDz + C::DZ_BYTES;
+  const uint32_t sRedC = sRedH + REDH_FLOATS * 4;
   const uint32_t sDq = sRedC + REDC_FLOATS * 4;
-  const uint32_t sCtx = sDq + DQ_FLOATS * 4;                 // [2][DM] dctx of the two utterances
-  const uint32_t sSc = sCtx + 2 * DM * 4;                    // [2][MAX_TM] alignments
-  const uint32_t sDs = sSc + 2 * MAX_TM * 4;                 // [2][MAX_TM] d(align) / ds
-  const uint32_t sPart = sDs + 2 * MAX_TM * 4;               // [2][4][DM]
-  const uint32_t sRed = sPart + 2 * 4 * DM * 4;              // [2][8]
-  const uint32_t sBar = sRed + 64;  // [0] mma_done [1] dz_ready [2,3] redH_full[par] [4] redC_full [5] dq_full
-  const uint32_t sTmem = sBar + 48;
+  const uint32_t sCtx = sDq + DQ_FLOATS * 4;                 // [NU][DM] dctx of the CTA's utterances
+  const uint32_t sSc = sCtx + NU * DM * 4;                   // [NU][MAX_TM] alignments
+  const uint32_t sDs = sSc + NU * MAX_TM * 4;                // [NU][MAX_TM] d(align) / ds
+  const uint32_t sRed = sDs + NU * MAX_TM * 4;               // [NU][8]
+  const uint32_t sBar = sRed + NU * 8 * 4;  // [0] mma_done [1] dz_ready [2] redH_full [3] redC_full [4] dq_full
+  const uint32_t sTmem = sBar + 40;
+  const uint32_t barMma = sBar, barDz = sBar + 8, barRedH = sBar + 16, barRedC = sBar + 24, barDq = sBar + 32;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   float* redH = reinterpret_cast<float*>(gen + (sRedH - base));
   float* redC = reinterpret_cast<float*>(gen + (sRedC - base));
@@ -608,7 +660,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
   float* ctx_all = reinterpret_cast<float*>(gen + (sCtx - base));
   float* sc_all = reinterpret_cast<float*>(gen + (sSc - base));
   float* ds_all = reinterpret_cast<float*>(gen + (sDs - base));
-  float* part_all = reinterpret_cast<float*>(gen + (sPart - base));
+  float* part_all = redC;
   float* red_all = reinterpret_cast<float*>(gen + (sRed - base));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -617,13 +669,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
   const int T = p.T, B = p.B, Tm = p.Tm;
 
   if (tid == 0) {
-    mbar_init(sBar, 1);
-    mbar_init(sBar + 8, GM_WARPS * 32);
-    for (int i = 2; i < 6; ++i) mbar_init(sBar + 8 * i, 1);
+    mbar_init(barMma, 1);
+    mbar_init(barDz, GM_WARPS * 32);
+    mbar_init(barRedH, 1);
+    mbar_init(barRedC, 1);
+    mbar_init(barDq, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == GM_WARPS) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(sTmem) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "n"(C::TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // resident operand: A[n][g*32 + u] = Wp[n][g*H + 32*rank + u] as fp16 (rows n = [h | ctx] dims)
@@ -643,7 +697,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
   if (warp == GM_WARPS) {
     // ================= MMA issuer: partial [h | ctx](512) x NB from this CTA's 128 gate columns ===========
     for (int it = 0; it < T; ++it) {
-      mbar_wait(sBar + 8, it & 1);
+      mbar_wait(barDz, it & 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
@@ -655,7 +709,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
             for (int k4 = 0; k4 < 4; ++k4)
               umma_f16(tmem_base + mt * NB, make_desc_k128(sW + kb * (KTOT * 128) + mt * (128 * 128) + k4 * 32),
                        make_desc_k128(sDz + kb * (NB * 128) + k4 * 32), IDESC, (kb | k4) ? 1u : 0u);
-        umma_commit(sBar);
+        umma_commit(barMma);
       }
       __syncwarp();
     }
@@ -690,7 +744,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
     };
     // attention role
     const int jl = warp >> 2, w4 = warp & 3, gt = tid & 127;
-    const int bl_att = 2 * (int)rank + jl;
+    const int bl_att = NU * (int)rank + jl;
     const int b_att = b0 + bl_att;
     const int len_q = (b_att < B) ? p.len[b_att] : 0;
     const int L = (b_att < B) ? min(p.mem_len[b_att], Tm) : 0;
@@ -701,33 +755,52 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
     float* part = part_all + jl * 4 * DM;
     float* red = red_all + jl * 8;
     const uint32_t att_bar_id = 2 + jl;
-    // reduce-scatter role after the product: warps 0-3 forward the h rows, warps 4-7 the ctx rows
+    // reduce-scatter role after the product: warp quad `jl` forwards the 128-row tiles TPW*jl .. TPW*jl+TPW-1
+    // (tiles 0, 1: h rows; tiles 2, 3: ctx dims)
+    constexpr int TPW = 4 / NU;
     const int q = warp & 3;
 
     load_step(T - 1);
     for (int it = 0; it < T; ++it) {
       const int t = T - 1 - it;
       const bool live_q = t < len_q;
-      // ---- (A/B) dctx_t of the two utterances, attention backward, dq all-to-all -----------------------
-      if (it > 0) {
-        if (tid == 0) mbar_expect_tx(sBar + 32, REDC_FLOATS * 4);
-        mbar_wait(sBar + 32, (it - 1) & 1);
-      }
-      float dqv[8];
+      // ---- top: partial sums of the previous iteration ---------------------------------------------------
+      float dh_in[PB];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) dqv[e] = 0.0f;
+      for (int j = 0; j < PB; ++j) dh_in[j] = dh_carry[j];
+      if (it > 0) {
+        if (tid == 0) {
+          mbar_expect_tx(barRedC, REDC_FLOATS * 4);
+          mbar_expect_tx(barRedH, REDH_FLOATS * 4);
+        }
+        mbar_wait(barRedH, (it - 1) & 1);
+#pragma unroll
+        for (int j = 0; j < PB; ++j) {
+          const int bl = warp * PB + j;
+#pragma unroll
+          for (int src = 0; src < CL; ++src)
+            dh_in[j] += redH[(src * 32 + lane) * NB + ((((bl >> 2) ^ (lane & (NB / 4 - 1))) << 2) | (bl & 3))];
+        }
+        mbar_wait(barRedC, (it - 1) & 1);
+      }
       if (live_q) {
         for (int d = gt; d < DM; d += 128) {
           float v = p.douthc ? p.douthc[((size_t)t * B + b_att) * (H + DM) + H + d] : 0.0f;
           if (it > 0) {
 #pragma unroll
-            for (int src = 0; src < CL; ++src) v += redC[(src * 2 + jl) * DM + d];
+            for (int src = 0; src < CL; ++src) v += redC[(src * NU + jl) * DM + d];
           }
           dctx_s[d] = v;
           p.dhc[((size_t)t * B + b_att) * (H + DM) + H + d] = v;
         }
         for (int tm = gt; tm < Tm; tm += 128) a_s[tm] = p.align[((size_t)t * B + b_att) * Tm + tm];
-        asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(GM_WARPS * 32) : "memory");
+      // ---- (A/B) attention backward of the CTA's utterances, dq all-to-all -------------------------------
+      float dqv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dqv[e] = 0.0f;
+      if (live_q) {
         float dcx[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) dcx[e] = dctx_s[8 * lane + e];
@@ -812,31 +885,21 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
       if (w4 == 0) {
         // dq dims 8*lane .. +7 belong to the CTA owning units (8*lane)/32
         const uint32_t dst = (uint32_t)(lane >> 2);
-        const uint32_t a0 = mapa(sDq + (uint32_t)(((rank * 2 + jl) * 32 + ((8 * lane) & 31)) * 4), dst);
-        const uint32_t bar = mapa(sBar + 40, dst);
+        const uint32_t a0 = mapa(sDq + (uint32_t)(((rank * NU + jl) * 32 + ((8 * lane) & 31)) * 4), dst);
+        const uint32_t bar = mapa(barDq, dst);
         st_async_v4f(a0, bar, dqv[0], dqv[1], dqv[2], dqv[3]);
         st_async_v4f(a0 + 16, bar, dqv[4], dqv[5], dqv[6], dqv[7]);
       }
-      // ---- (C/D) dq and h partials of this CTA's units -> gate gradients -------------------------------
-      if (tid == 0) mbar_expect_tx(sBar + 40, DQ_FLOATS * 4);
-      mbar_wait(sBar + 40, it & 1);
-      const float* rbuf = redH + (it & 1) * REDH_FLOATS;
-      if (it > 0) {
-        const uint32_t bar = sBar + 16 + 8 * (it & 1);
-        if (tid == 0) mbar_expect_tx(bar, REDH_FLOATS * 4);
-        mbar_wait(bar, ((it - 1) >> 1) & 1);
-      }
+      // ---- (C/D) dq of this CTA's units -> gate gradients ------------------------------------------------
+      if (tid == 0) mbar_expect_tx(barDq, DQ_FLOATS * 4);
+      mbar_wait(barDq, it & 1);
       float dz[4][PB];
 #pragma unroll
       for (int j = 0; j < PB; ++j) {
         const int bl = warp * PB + j;
-        float dh = dh_carry[j];
-        if (it > 0) {
-#pragma unroll
-          for (int src = 0; src < CL; ++src) dh += rbuf[(src * 32 + lane) * NB + ((((bl >> 2) ^ (lane & 3)) << 2) | (bl & 3))];
-        }
+        float dh = dh_in[j];
         if (t < len_t[j]) {
-          dh += dov[j] + dqb[((bl >> 1) * 2 + (bl & 1)) * 32 + lane];
+          dh += dov[j] + dqb[bl * 32 + lane];
           const float c = fminf(fmaxf(crw[j], -1.0f), 1.0f);
           const float tc = tanhf_acc(c);
           const float cp = t > 0 ? fminf(fmaxf(cpv[j], -1.0f), 1.0f) : cpv[j];
@@ -858,7 +921,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
               __float2half_rn(dz[g][j] * p.grad_scale);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(sBar + 8);
+      mbar_arrive(barDz);
 #pragma unroll
       for (int j = 0; j < PB; ++j) {
         const int b = b0 + warp * PB + j;
@@ -869,42 +932,36 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
       }
       load_step(t - 1);
       // ---- (E) partial products -> owners ---------------------------------------------------------------
-      mbar_wait(sBar, it & 1);
+      mbar_wait(barMma, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (warp < 4) {
-        const uint32_t rnext = sRedH + ((it + 1) & 1) * REDH_FLOATS * 4;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {  // h rows 128*mt + 32*q + lane -> owner CTA 4*mt + q
-          uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NB, r);
+      for (int mi = 0; mi < TPW; ++mi) {
+        const int mt = TPW * jl + mi;
+        if (mt < 2) {  // h rows 128*mt + 32*q + lane -> owner CTA 4*mt + q
+          uint32_t r[NB];
+          tmem_ldn<NB>(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NB, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           const uint32_t dst = (uint32_t)(4 * mt + q);
-          const uint32_t a0 = mapa(rnext + (uint32_t)((rank * 32 + lane) * NB) * 4, dst);
-          const uint32_t bar = mapa(sBar + 16 + 8 * ((it + 1) & 1), dst);
+          const uint32_t a0 = mapa(sRedH + (uint32_t)((rank * 32 + lane) * NB) * 4, dst);
+          const uint32_t bar = mapa(barRedH, dst);
 #pragma unroll
-          for (int v = 0; v < 4; ++v)  // 16-byte chunks XOR-swizzled by the unit: conflict-light reads on the owner
-            st_async_v4f(a0 + ((v ^ (lane & 3)) << 4), bar, __uint_as_float(r[4 * v]) * p.inv_grad_scale,
+          for (int v = 0; v < NB / 4; ++v)  // 16-byte chunks XOR-swizzled by the unit: conflict-light reads on the owner
+            st_async_v4f(a0 + ((v ^ (lane & (NB / 4 - 1))) << 4), bar, __uint_as_float(r[4 * v]) * p.inv_grad_scale,
                          __uint_as_float(r[4 * v + 1]) * p.inv_grad_scale, __uint_as_float(r[4 * v + 2]) * p.inv_grad_scale,
                          __uint_as_float(r[4 * v + 3]) * p.inv_grad_scale);
-        }
-      } else if (it + 1 < T) {
-#pragma unroll
-        for (int mt = 2; mt < 4; ++mt) {  // ctx dims 128*(mt-2) + 32*q + lane; column c = utterance -> owner CTA c/2
-          uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NB, r);
+        } else if (it + 1 < T) {  // ctx dims 128*(mt-2) + 32*q + lane; column c = utterance -> owner CTA c / NU
+          uint32_t r[NB];
+          tmem_ldn<NB>(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NB, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           const int dim = 128 * (mt - 2) + 32 * q + lane;
 #pragma unroll
           for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) {
-            // redC[src = rank][utt 0..1][dim]: the two utterances are DM floats apart -> two scalar-pair stores
-            const uint32_t a0 = mapa(sRedC + (uint32_t)((rank * 2) * DM + dim) * 4, dst);
-            const uint32_t bar = mapa(sBar + 32, dst);
-            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %2, [%1];" ::"r"(a0), "r"(bar),
-                         "f"(__uint_as_float(r[2 * dst]) * p.inv_grad_scale)
-                         : "memory");
-            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %2, [%1];" ::"r"(a0 + DM * 4),
-                         "r"(bar), "f"(__uint_as_float(r[2 * dst + 1]) * p.inv_grad_scale)
-                         : "memory");
+            // redC[src = rank][utt 0..NU-1][dim]: the utterances of one owner are DM floats apart
+            const uint32_t a0 = mapa(sRedC + (uint32_t)((rank * NU) * DM + dim) * 4, dst);
+            const uint32_t bar = mapa(barRedC, dst);
+#pragma unroll
+            for (int ul = 0; ul < NU; ++ul)
+              st_async_f(a0 + ul * DM * 4, bar, __uint_as_float(r[NU * dst + ul]) * p.inv_grad_scale);
           }
         }
       }
@@ -914,9 +971,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
     // NOT dh_0: step 0 saw att_{-1} = 0, so dh_0 = dz_0 Wh^T with the un-fused Wh - added by the host; here only
     // the gradient carried through fully masked utterances is written.
     if (T > 0) {
-      const uint32_t bar = sBar + 16 + 8 * (T & 1);
-      if (tid == 0) mbar_expect_tx(bar, REDH_FLOATS * 4);
-      mbar_wait(bar, ((T - 1) >> 1) & 1);
+      if (tid == 0) mbar_expect_tx(barRedH, REDH_FLOATS * 4);
+      mbar_wait(barRedH, (T - 1) & 1);
     }
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
@@ -931,12 +987,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist_bwd_kernel(const
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == GM_WARPS)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TCOLS) : "memory");
   cluster_sync_all();
 }
-
-constexpr size_t BW_SMEM_BYTES = (size_t)BW_W_BYTES + BW_DZ_BYTES + 2 * REDH_FLOATS * 4 + REDC_FLOATS * 4 + DQ_FLOATS * 4 +
-                                 2 * DM * 4 + 4 * MAX_TM * 4 + 2 * 4 * DM * 4 + 64 + 64 + 1024;
 
 // dA[t,b,:] += (t < len[b]) ? dout[t,b,:] : 0
 __global__ void masked_add_kernel(float* __restrict__ dA, const float* __restrict__ dout, const int* __restrict__ len,
@@ -947,6 +1000,37 @@ __global__ void masked_add_kernel(float* __restrict__ dA, const float* __restric
   int t = (int)(row / Bt), b = (int)(row - (long long)t * Bt);
   float v = dA[idx] + ((dout && t < len[b]) ? dout[idx] : 0.0f);
   dA[idx] = maybe_tf32(v, rnd);
+}
+
+// Utterances per cluster.  A B200 keeps at most 15 clusters of 8 CTAs resident, so more than 240 utterances
+// take 32-utterance slices (one wave of <= 8 clusters per 256) instead of a second wave of 16-utterance ones.
+// AVSR_AP_SLICE=16|32 overrides the choice (parity tests of the wide variant at small batches).
+static int slice_width(int B) {
+  if (const char* e = getenv("AVSR_AP_SLICE")) {
+    const int v = atoi(e);
+    if (v == 16 || v == 32) return v;
+  }
+  return B > 240 ? 32 : 16;
+}
+
+template <typename Kern, typename P>
+static int launch_cluster(cudaStream_t st, Kern kern, int B, int nb, int threads, size_t smem, const P& p) {
+  AVSR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cdiv(B, nb) * CL);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  ++g_launch_count;
+  return 0;
 }
 
 }  // namespace ap
@@ -994,26 +1078,8 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
     AVSR_CHECK_CUDA(cudaMemset(dbg_dev, 0, 64 * 12 * sizeof(long long)));
     p.dbg = dbg_dev;
   }
-  static bool attr = false;
-  if (!attr) {
-    AVSR_CHECK_CUDA(cudaFuncSetAttribute(attn_lstm_persist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SMEM_BYTES));
-    attr = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cdiv(B, NB) * CL);
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_lstm_persist_fwd_kernel, p));
-  ++g_launch_count;
+  AVSR_TRY(slice_width(B) == 32 ? launch_cluster(st, attn_lstm_persist_fwd_kernel<32>, B, 32, FwdCfg<32>::THREADS, FwdCfg<32>::SMEM, p)
+                                 : launch_cluster(st, attn_lstm_persist_fwd_kernel<16>, B, 16, FwdCfg<16>::THREADS, FwdCfg<16>::SMEM, p));
   if (dbg_dev) {
     AVSR_CHECK_CUDA(cudaStreamSynchronize(st));
     long long h[64 * 12];
@@ -1075,26 +1141,8 @@ int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   p.len = r->len; p.mem_len = m.mem_len; p.gates = r->gates; p.craw = r->craw; p.c0 = r->c0; p.Wp = Wp;
   p.keys = keys_h; p.values = values_h; p.g = m.g; p.hc = m.hc; p.align = m.align; p.douthc = dhc_in;
   p.dcT = r->dcT; p.dhT = r->dhT; p.dZ = r->dZ; p.ds = m.ds; p.dhc = m.dhc; p.dg = m.dg; p.dc0 = r->dc0; p.dh0 = r->dh0;
-  static bool attr = false;
-  if (!attr) {
-    AVSR_CHECK_CUDA(cudaFuncSetAttribute(attn_lstm_persist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)BW_SMEM_BYTES));
-    attr = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cdiv(B, NB) * CL);
-  cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = BW_SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = CL;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, attn_lstm_persist_bwd_kernel, p));
-  ++g_launch_count;
+  AVSR_TRY(slice_width(B) == 32 ? launch_cluster(st, attn_lstm_persist_bwd_kernel<32>, B, 32, BwdCfg<32>::THREADS, BwdCfg<32>::SMEM, p)
+                                 : launch_cluster(st, attn_lstm_persist_bwd_kernel<16>, B, 16, BwdCfg<16>::THREADS, BwdCfg<16>::SMEM, p));
   if (r->dh0)  // dh_0 += dz_0 Wh^T (un-fused: the zero attention state of step 0)
     AVSR_TRY(gemm(st, 0, 1, B, H, 4 * H, r->dZ, 4 * H, r->Wrec + (size_t)At * 4 * H, 4 * H, r->dh0, H, 1.0f, nullptr));
   // dA_t = dz_{t+1} Wa^T (+ dout_t, masked): gradient wrt the attention vectors, for dWl

@@ -278,8 +278,29 @@ def _spec64(s):
     (('bahdanau',), 6, 41, 128, 256, (300,), (512,)),
     (('scaled_luong',), 20, 9, 128, 256, (75,), (256,)),   # persistent cluster kernel (tf32 mode), 2 clusters
     (('luong',), 5, 14, 256, 256, (300,), (256,)),
+    (('scaled_luong',), 250, 6, 128, 256, (75,), (256,)),  # > 240 utterances: 32-utterance slices, 16-warp CTAs
 ])
 def test_attention_rnn_fwd_bwd(kinds, B, T, Dx, H, Tms, Dms, tensor_cores):
+    _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, tensor_cores)
+
+
+@pytest.mark.parametrize('kinds,B,T,Dx,H,Tms,Dms', [
+    (('scaled_luong',), 40, 9, 128, 256, (75,), (256,)),   # two clusters, the second one a quarter full
+    (('luong',), 33, 12, 256, 256, (300,), (256,)),
+])
+def test_attention_rnn_wide_slices(kinds, B, T, Dx, H, Tms, Dms, monkeypatch):
+    """The 32-utterance variant of the persistent attention-LSTM kernels (used above 240 utterances) forced at a
+    small batch."""
+    monkeypatch.setenv('AVSR_AP_SLICE', '32')
+    ops = ops_mod()
+    old = ops.set_tensor_cores(True)
+    try:
+        _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, True)
+    finally:
+        ops.set_tensor_cores(old)
+
+
+def _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, tensor_cores):
     ops = ops_mod()
     x, lens, W, b, specs, c0, h0, rng = _attn_case(kinds, B, T, Dx, H, Tms, Dms, sum(Tms) + B)
     f64 = lambda a: a.astype(np.float64)
