@@ -142,6 +142,22 @@ __device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
   return n;
 }
 
+// one memory row (256 halves) as 32 lanes x 16 bytes; rows at or past `L` read as zeros without touching memory
+__device__ __forceinline__ uint4 ld_row(const __half* __restrict__ mat, int tm, int L, int B, int b, int lane) {
+  return tm < L ? __ldg(reinterpret_cast<const uint4*>(mat + ((size_t)tm * B + b) * 256) + lane) : make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ float dot8(const uint4& r, const float (&q)[8]) {
+  const float2 a = unpack_h2(r.x), b = unpack_h2(r.y), c = unpack_h2(r.z), d = unpack_h2(r.w);
+  return a.x * q[0] + a.y * q[1] + b.x * q[2] + b.y * q[3] + c.x * q[4] + c.y * q[5] + d.x * q[6] + d.y * q[7];
+}
+__device__ __forceinline__ void axpy8(float w, const uint4& r, float (&acc)[8]) {
+  const float2 a = unpack_h2(r.x), b = unpack_h2(r.y), c = unpack_h2(r.z), d = unpack_h2(r.w);
+  acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]);
+  acc[2] = fmaf(w, b.x, acc[2]); acc[3] = fmaf(w, b.y, acc[3]);
+  acc[4] = fmaf(w, c.x, acc[4]); acc[5] = fmaf(w, c.y, acc[5]);
+  acc[6] = fmaf(w, d.x, acc[6]); acc[7] = fmaf(w, d.y, acc[7]);
+}
+
 // byte offset of half element (row, k) in a K-major SWIZZLE_128B operand with 64-half K blocks of `rows` rows
 __device__ __forceinline__ uint32_t sw128h_off(int rows, int row, int k) {
   const int kb = k >> 6, kk = k & 63;
@@ -182,8 +198,13 @@ struct Params {
 
 template <int NB>
 struct FwdCfg {
-  static constexpr int GMW = NB / 2;                  // gate-math / attention warps (4 per attended utterance)
-  static constexpr int THREADS = (GMW + 1) * 32;      // + 1 MMA-issue warp
+  // gate-math / attention warps (4 per attended utterance).  There is no separate MMA-issue warp: the register file
+  // is split per SM sub-partition (16384 each, warps dealt round-robin), so a 17th warp would cap every thread of
+  // the 32-utterance variant at 96 registers (5 warps on one sub-partition) and the memory sweeps would spill - and
+  // spills miss the ~28 KB of L1 left beside 220 KB of shared memory.  Lane 0 of warp 0 issues the products at
+  // the two points of the step where it has to wait for the same barriers anyway.
+  static constexpr int GMW = NB / 2;
+  static constexpr int THREADS = GMW * 32;
   static constexpr int NU = NB / CL;                  // utterances whose attention this CTA owns
   static constexpr int OP_BYTES = KB * NB * 128;      // one [h | ctx] operand buffer
   // the partial-context scratch [NU][4][DM] aliases the activation exchange buffer [4][NB][32] (same size): the
@@ -222,7 +243,7 @@ __global__ void __launch_bounds__(FwdCfg<NB>::THREADS, 1) attn_lstm_persist_fwd_
     for (int i = 0; i < 5; ++i) mbar_init(sBar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == GM_WARPS) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(sTmem) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -242,48 +263,8 @@ __global__ void __launch_bounds__(FwdCfg<NB>::THREADS, 1) attn_lstm_persist_fwd_
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
   cluster_sync_all();
 
-  if (warp == GM_WARPS) {
-    // ================= MMA issuer =================
-    // iteration t consumes [h_{t-1} | ctx_{t-1}] from buffer t&1; the extra iteration t = T only drains the
-    // final all-gathers so that no st.async is in flight towards this CTA when it exits
-    for (int t = 1; t <= T; ++t) {
-      const uint32_t ob = sOp + (t & 1) * OP_BYTES;
-      const uint32_t par = ((t - 1) >> 1) & 1;
-      const uint32_t hbar = sBar + 8 + 8 * (t & 1), cbar = sBar + 24 + 8 * (t & 1);
-      if (lane == 0) mbar_expect_tx(hbar, NB * H * 2);
-      mbar_wait(hbar, par);
-      if (t < T) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
-#pragma unroll
-          for (int kb = 0; kb < H / 64; ++kb)
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma_f16(tmem_base, make_desc_k128(sW + kb * (128 * 128) + k4 * 32),
-                       make_desc_k128(ob + kb * (NB * 128) + k4 * 32), IDESC, (kb | k4) ? 1u : 0u);
-        }
-        __syncwarp();
-      }
-      if (lane == 0) mbar_expect_tx(cbar, NB * DM * 2);
-      mbar_wait(cbar, par);
-      if (t < T) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
-#pragma unroll
-          for (int kb = H / 64; kb < KB; ++kb)
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma_f16(tmem_base, make_desc_k128(sW + kb * (128 * 128) + k4 * 32),
-                       make_desc_k128(ob + kb * (NB * 128) + k4 * 32), IDESC, 1u);
-          umma_commit(sBar);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ================= gate math + attention warps =================
+  {
+    // ================= gate math + attention warps (lane 0 of warp 0 also issues the products) =================
     const int g = warp & 3, ch = warp >> 2;
     const int unit = 32 * rank + lane;
     const bool comb = tid < 8 * NB;
@@ -408,9 +389,37 @@ __global__ void __launch_bounds__(FwdCfg<NB>::THREADS, 1) attn_lstm_persist_fwd_
       }
       // ---------------- attention of utterance b_att with query h_t ----------------
       AP_STAMP(4);
-      mbar_wait(hbar_n, (t >> 1) & 1);  // every CTA's h_t slice has landed in buffer nb
-      AP_STAMP(5);
       const bool live_q = t < len_q;    // masked steps (and padding utterances) skip the memory sweep
+      // Memory sweeps are software-pipelined in half-batches of 4 rows (ra: rows j = 0..3 of a batch of 8, rb:
+      // j = 4..7): the loads of the next half-batch are in flight while the current one is consumed, and the first
+      // batch of the keys is requested before the h all-gather has landed (it does not depend on the query).
+      uint4 ra[4], rb[4];
+      if (live_q) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ra[j] = ld_row(p.keys, w4 + 4 * j, L, B, b_att, lane);
+          rb[j] = ld_row(p.keys, w4 + 16 + 4 * j, L, B, b_att, lane);
+        }
+      }
+      if (tid == 0) mbar_expect_tx(hbar_n, NB * H * 2);
+      mbar_wait(hbar_n, (t >> 1) & 1);  // every CTA's h_t slice has landed in buffer nb
+      if (warp == 0 && t + 1 < T) {
+        // h half of the gate product of step t+1 (it overlaps this step's attention).  Every warp has read the
+        // accumulators of step t before its activations reached the barrier that precedes the h all-gather.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t ob = sOp + nb * OP_BYTES;
+#pragma unroll
+          for (int kb = 0; kb < H / 64; ++kb)
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_f16(tmem_base, make_desc_k128(sW + kb * (128 * 128) + k4 * 32),
+                       make_desc_k128(ob + kb * (NB * 128) + k4 * 32), IDESC, (kb | k4) ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+      AP_STAMP(5);
       float ctxv[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) ctxv[e] = 0.0f;
@@ -426,21 +435,23 @@ __global__ void __launch_bounds__(FwdCfg<NB>::THREADS, 1) attn_lstm_persist_fwd_
         static_assert(RIF == 8, "warp_reduce8 expects 8 rows per batch");
         const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
         for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
-          uint4 k[RIF];
-#pragma unroll
-          for (int j = 0; j < RIF; ++j) {
-            const int tm = tm0 + 4 * j;
-            k[j] = tm < L ? __ldg(reinterpret_cast<const uint4*>(p.keys + ((size_t)tm * B + b_att) * H) + lane)
-                          : make_uint4(0, 0, 0, 0);
-          }
           float sacc[RIF];
 #pragma unroll
-          for (int j = 0; j < RIF; ++j) {
-            float2 a = unpack_h2(k[j].x), b = unpack_h2(k[j].y), c = unpack_h2(k[j].z), d = unpack_h2(k[j].w);
-            sacc[j] = a.x * q[0] + a.y * q[1] + b.x * q[2] + b.y * q[3] + c.x * q[4] + c.y * q[5] + d.x * q[6] + d.y * q[7];
-          }
+          for (int j = 0; j < 4; ++j) sacc[j] = dot8(ra[j], q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.keys, tm0 + 32 + 4 * j, L, B, b_att, lane);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sacc[4 + j] = dot8(rb[j], q);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.keys, tm0 + 48 + 4 * j, L, B, b_att, lane);
           const float tot = warp_reduce8(sacc, lane);
           if ((lane & 3) == 0 && tm0 + 4 * jrow < L) sc[tm0 + 4 * jrow] = gs * tot;
+        }
+        // first batch of the values: in flight during the softmax
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ra[j] = ld_row(p.values, w4 + 4 * j, L, B, b_att, lane);
+          rb[j] = ld_row(p.values, w4 + 16 + 4 * j, L, B, b_att, lane);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
         AP_STAMP(6);
@@ -471,23 +482,17 @@ __global__ void __launch_bounds__(FwdCfg<NB>::THREADS, 1) attn_lstm_persist_fwd_
         AP_STAMP(7);
         // context: rows tm = w4 + 4*i, lane accumulates dims 8*lane .. +7
         for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
-          uint4 v[RIF];
           float a[RIF];
 #pragma unroll
-          for (int j = 0; j < RIF; ++j) {
-            const int tm = tm0 + 4 * j;
-            a[j] = tm < L ? sc[tm] : 0.0f;
-            v[j] = tm < L ? __ldg(reinterpret_cast<const uint4*>(p.values + ((size_t)tm * B + b_att) * DM) + lane)
-                          : make_uint4(0, 0, 0, 0);
-          }
+          for (int j = 0; j < RIF; ++j) a[j] = tm0 + 4 * j < L ? sc[tm0 + 4 * j] : 0.0f;
 #pragma unroll
-          for (int j = 0; j < RIF; ++j) {
-            float2 x0 = unpack_h2(v[j].x), x1 = unpack_h2(v[j].y), x2 = unpack_h2(v[j].z), x3 = unpack_h2(v[j].w);
-            ctxv[0] = fmaf(a[j], x0.x, ctxv[0]); ctxv[1] = fmaf(a[j], x0.y, ctxv[1]);
-            ctxv[2] = fmaf(a[j], x1.x, ctxv[2]); ctxv[3] = fmaf(a[j], x1.y, ctxv[3]);
-            ctxv[4] = fmaf(a[j], x2.x, ctxv[4]); ctxv[5] = fmaf(a[j], x2.y, ctxv[5]);
-            ctxv[6] = fmaf(a[j], x3.x, ctxv[6]); ctxv[7] = fmaf(a[j], x3.y, ctxv[7]);
-          }
+          for (int j = 0; j < 4; ++j) axpy8(a[j], ra[j], ctxv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.values, tm0 + 32 + 4 * j, L, B, b_att, lane);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) axpy8(a[4 + j], rb[j], ctxv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.values, tm0 + 48 + 4 * j, L, B, b_att, lane);
         }
         AP_STAMP(8);
 #pragma unroll
@@ -518,6 +523,27 @@ __global__ void __launch_bounds__(FwdCfg<NB>::THREADS, 1) attn_lstm_persist_fwd_
         for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) st_async_v4(mapa(dbuf, dst), mapa(cbar_n, dst), c0, c1, c2, c3);
       }
       AP_STAMP(9);
+      if (warp == 0) {
+        // ctx half of the gate product of step t+1, once every context of this step has landed.  After the last
+        // step the wait only drains the all-gathers: no st.async may be in flight towards this CTA when it exits.
+        if (lane == 0) mbar_expect_tx(cbar_n, NB * DM * 2);
+        mbar_wait(cbar_n, (t >> 1) & 1);
+        if (t + 1 < T) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            const uint32_t ob = sOp + nb * OP_BYTES;
+#pragma unroll
+            for (int kb = H / 64; kb < KB; ++kb)
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_f16(tmem_base, make_desc_k128(sW + kb * (128 * 128) + k4 * 32),
+                         make_desc_k128(ob + kb * (NB * 128) + k4 * 32), IDESC, 1u);
+            umma_commit(sBar);
+          }
+          __syncwarp();
+        }
+      }
     }
     if (comb && b0 + bq < B) {
       const size_t o = (size_t)(b0 + bq) * H + 32 * rank + 4 * uq;
@@ -528,7 +554,7 @@ __global__ void __launch_bounds__(FwdCfg<NB>::THREADS, 1) attn_lstm_persist_fwd_
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == GM_WARPS)
+  if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_base) : "memory");
   cluster_sync_all();
 }
@@ -572,14 +598,19 @@ struct BwdParams {
   float* dg;             // [1] or null
   float* dc0;            // [B,H] or null
   float* dh0;            // [B,H] or null
+  long long* dbg;        // AVSR_AP_DEBUG: clock samples [64 iterations][12] of CTA 0, thread 0
 };
+#define APB_STAMP(slot)                                                                          \
+  do {                                                                                           \
+    if (p.dbg && blockIdx.x == 0 && tid == 0 && it < 64) p.dbg[it * 12 + (slot)] = clock64(); \
+  } while (0)
 
 constexpr int BW_W_BYTES = 2 * KTOT * 128;           // A operand: 2 K-blocks x [512 rows x 128 B]
 
 template <int NB>
 struct BwdCfg {
   static constexpr int GMW = NB / 2;
-  static constexpr int THREADS = (GMW + 1) * 32;
+  static constexpr int THREADS = GMW * 32;             // no separate MMA-issue warp (see FwdCfg)
   static constexpr int NU = NB / CL;                   // utterances whose attention backward this CTA owns
   static constexpr int DZ_BYTES = 2 * NB * 128;        // B operand: 2 K-blocks x [NB rows x 128 B]
   static constexpr int REDH_FLOATS = CL * 32 * NB;     // [src][u][b]
@@ -676,7 +707,7 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
     mbar_init(barDq, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == GM_WARPS) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmem), "n"(C::TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -694,26 +725,7 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
   cluster_sync_all();
 
-  if (warp == GM_WARPS) {
-    // ================= MMA issuer: partial [h | ctx](512) x NB from this CTA's 128 gate columns ===========
-    for (int it = 0; it < T; ++it) {
-      mbar_wait(barDz, it & 1);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-#pragma unroll
-        for (int mt = 0; mt < KTOT / 128; ++mt)
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              umma_f16(tmem_base + mt * NB, make_desc_k128(sW + kb * (KTOT * 128) + mt * (128 * 128) + k4 * 32),
-                       make_desc_k128(sDz + kb * (NB * 128) + k4 * 32), IDESC, (kb | k4) ? 1u : 0u);
-        umma_commit(barMma);
-      }
-      __syncwarp();
-    }
-  } else {
+  {
     const int unit = 32 * rank + lane;
     constexpr int PB = 2;
     float dc[PB], dh_carry[PB];
@@ -768,6 +780,17 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
       float dh_in[PB];
 #pragma unroll
       for (int j = 0; j < PB; ++j) dh_in[j] = dh_carry[j];
+      APB_STAMP(0);
+      // software-pipelined memory sweeps (see the forward kernel): the first batch of the values is requested before
+      // the partial sums of the previous iteration have arrived
+      uint4 ra[4], rb[4];
+      if (live_q) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ra[j] = ld_row(p.values, w4 + 4 * j, L, B, b_att, lane);
+          rb[j] = ld_row(p.values, w4 + 16 + 4 * j, L, B, b_att, lane);
+        }
+      }
       if (it > 0) {
         if (tid == 0) {
           mbar_expect_tx(barRedC, REDC_FLOATS * 4);
@@ -783,6 +806,7 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
         }
         mbar_wait(barRedC, (it - 1) & 1);
       }
+      APB_STAMP(1);
       if (live_q) {
         for (int d = gt; d < DM; d += 128) {
           float v = p.douthc ? p.douthc[((size_t)t * B + b_att) * (H + DM) + H + d] : 0.0f;
@@ -796,6 +820,7 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
         for (int tm = gt; tm < Tm; tm += 128) a_s[tm] = p.align[((size_t)t * B + b_att) * Tm + tm];
       }
       asm volatile("bar.sync 1, %0;" ::"n"(GM_WARPS * 32) : "memory");
+      APB_STAMP(2);
       // ---- (A/B) attention backward of the CTA's utterances, dq all-to-all -------------------------------
       float dqv[8];
 #pragma unroll
@@ -807,72 +832,65 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
         // d(align)[tm] = values[tm] . dctx
         const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
         for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
-          uint4 v[RIF];
-#pragma unroll
-          for (int j = 0; j < RIF; ++j) {
-            const int tm = tm0 + 4 * j;
-            v[j] = tm < L ? __ldg(reinterpret_cast<const uint4*>(p.values + ((size_t)tm * B + b_att) * DM) + lane)
-                          : make_uint4(0, 0, 0, 0);
-          }
           float sacc[RIF];
 #pragma unroll
-          for (int j = 0; j < RIF; ++j) {
-            float2 x0 = unpack_h2(v[j].x), x1 = unpack_h2(v[j].y), x2 = unpack_h2(v[j].z), x3 = unpack_h2(v[j].w);
-            sacc[j] = x0.x * dcx[0] + x0.y * dcx[1] + x1.x * dcx[2] + x1.y * dcx[3] + x2.x * dcx[4] + x2.y * dcx[5] +
-                      x3.x * dcx[6] + x3.y * dcx[7];
-          }
+          for (int j = 0; j < 4; ++j) sacc[j] = dot8(ra[j], dcx);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.values, tm0 + 32 + 4 * j, L, B, b_att, lane);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sacc[4 + j] = dot8(rb[j], dcx);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.values, tm0 + 48 + 4 * j, L, B, b_att, lane);
           const float tot = warp_reduce8(sacc, lane);
           if ((lane & 3) == 0 && tm0 + 4 * jrow < L) ds_s[tm0 + 4 * jrow] = tot;
         }
+        // first batch of the keys: in flight during the softmax backward
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ra[j] = ld_row(p.keys, w4 + 4 * j, L, B, b_att, lane);
+          rb[j] = ld_row(p.keys, w4 + 16 + 4 * j, L, B, b_att, lane);
+        }
         asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        APB_STAMP(3);
         float dot = 0.0f;
         for (int tm = gt; tm < L; tm += 128) dot = fmaf(a_s[tm], ds_s[tm], dot);
         dot = warp_sum(dot);
         if (lane == 0) red[w4] = dot;
         asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
         dot = (red[0] + red[1]) + (red[2] + red[3]);
+        // d(score) of this step, before the Luong scale (dkeys is formed after the loop).  d(attention_g) =
+        // sum_tm ds[tm] (keys[tm].h) = (1/g) sum_tm ds[tm] log a[tm]: the scores are log a + log Z over g and
+        // sum_tm ds[tm] = 0, so the normaliser drops out and the keys need not be multiplied by the query again.
         float* dsrow = p.ds + ((size_t)t * B + b_att) * Tm;
+        float gacc = 0.0f;
         for (int tm = gt; tm < Tm; tm += 128) {
-          const float d = tm < L ? a_s[tm] * (ds_s[tm] - dot) : 0.0f;
-          dsrow[tm] = d;  // d(score) before the Luong scale (dkeys / dg use it after the loop)
+          const float a = tm < L ? a_s[tm] : 0.0f;
+          const float d = a * (ds_s[tm] - dot);
+          dsrow[tm] = tm < L ? d : 0.0f;
           if (tm < L) ds_s[tm] = d;
+          if (a > 0.0f) gacc = fmaf(d, __logf(a), gacc);
+        }
+        if (p.scaled && p.dg && gs != 0.0f) {
+          gacc = warp_sum(gacc);
+          if (lane == 0) atomicAdd(p.dg, gacc / gs);
         }
         asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
-        // keys sweep: dq += g * ds[tm] * keys[tm];  raw score for d(attention_g)
-        const float* hrow = p.hc + ((size_t)t * B + b_att) * (H + DM) + 8 * lane;
-        float qv[8];
-        {
-          const float4 q0 = *reinterpret_cast<const float4*>(hrow), q1 = *reinterpret_cast<const float4*>(hrow + 4);
-          qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
-        }
-        float gacc = 0.0f;
+        APB_STAMP(4);
+        // keys sweep: dq += g * ds[tm] * keys[tm]
         for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
-          uint4 k[RIF];
           float d[RIF];
 #pragma unroll
-          for (int j = 0; j < RIF; ++j) {
-            const int tm = tm0 + 4 * j;
-            d[j] = tm < L ? ds_s[tm] : 0.0f;
-            k[j] = tm < L ? __ldg(reinterpret_cast<const uint4*>(p.keys + ((size_t)tm * B + b_att) * H) + lane)
-                          : make_uint4(0, 0, 0, 0);
-          }
+          for (int j = 0; j < RIF; ++j) d[j] = tm0 + 4 * j < L ? ds_s[tm0 + 4 * j] : 0.0f;
 #pragma unroll
-          for (int j = 0; j < RIF; ++j) {
-            float2 x0 = unpack_h2(k[j].x), x1 = unpack_h2(k[j].y), x2 = unpack_h2(k[j].z), x3 = unpack_h2(k[j].w);
-            const float kk[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
-            float raw = 0.0f;
+          for (int j = 0; j < 4; ++j) axpy8(d[j], ra[j], dqv);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              dqv[e] = fmaf(d[j], kk[e], dqv[e]);
-              raw = fmaf(kk[e], qv[e], raw);
-            }
-            if (p.scaled) gacc = fmaf(d[j], raw, gacc);  // lane-partial of ds * (keys . q)
-          }
+          for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.keys, tm0 + 32 + 4 * j, L, B, b_att, lane);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) axpy8(d[4 + j], rb[j], dqv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.keys, tm0 + 48 + 4 * j, L, B, b_att, lane);
         }
-        if (p.scaled) {
-          gacc = warp_sum(gacc);
-          if (lane == 0 && p.dg) atomicAdd(p.dg, gacc);
-        }
+        APB_STAMP(5);
 #pragma unroll
         for (int e = 0; e < 8; ++e) part[w4 * DM + 8 * lane + e] = dqv[e];
         asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
@@ -891,8 +909,10 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
         st_async_v4f(a0 + 16, bar, dqv[4], dqv[5], dqv[6], dqv[7]);
       }
       // ---- (C/D) dq of this CTA's units -> gate gradients ------------------------------------------------
+      APB_STAMP(6);
       if (tid == 0) mbar_expect_tx(barDq, DQ_FLOATS * 4);
       mbar_wait(barDq, it & 1);
+      APB_STAMP(7);
       float dz[4][PB];
 #pragma unroll
       for (int j = 0; j < PB; ++j) {
@@ -922,6 +942,25 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(barDz);
+      if (warp == 0) {
+        // partial [h | ctx](512) x NB from this CTA's 128 gate columns, once every warp's dz is in shared memory
+        mbar_wait(barDz, it & 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+#pragma unroll
+          for (int mt = 0; mt < KTOT / 128; ++mt)
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_f16(tmem_base + mt * NB, make_desc_k128(sW + kb * (KTOT * 128) + mt * (128 * 128) + k4 * 32),
+                         make_desc_k128(sDz + kb * (NB * 128) + k4 * 32), IDESC, (kb | k4) ? 1u : 0u);
+          umma_commit(barMma);
+        }
+        __syncwarp();
+      }
+      APB_STAMP(8);
 #pragma unroll
       for (int j = 0; j < PB; ++j) {
         const int b = b0 + warp * PB + j;
@@ -931,8 +970,10 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
         }
       }
       load_step(t - 1);
+      APB_STAMP(9);
       // ---- (E) partial products -> owners ---------------------------------------------------------------
       mbar_wait(barMma, it & 1);
+      APB_STAMP(10);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int mi = 0; mi < TPW; ++mi) {
@@ -966,6 +1007,7 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      APB_STAMP(11);
     }
     // drain the last reduce-scatter (nothing may be in flight towards this CTA when it exits).  Its content is
     // NOT dh_0: step 0 saw att_{-1} = 0, so dh_0 = dz_0 Wh^T with the un-fused Wh - added by the host; here only
@@ -986,7 +1028,7 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == GM_WARPS)
+  if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TCOLS) : "memory");
   cluster_sync_all();
 }
@@ -1011,6 +1053,21 @@ static int slice_width(int B) {
     if (v == 16 || v == 32) return v;
   }
   return B > 240 ? 32 : 16;
+}
+
+static void print_phase_clocks(const char* tag, const long long* h, int n, int ns, const char* const* names) {
+  double acc[12] = {0};
+  for (int t = 3; t < n; ++t) {
+    for (int k = 1; k < ns; ++k) acc[k] += (double)(h[t * 12 + k] - h[t * 12 + k - 1]);
+    acc[0] += (double)(h[t * 12] - h[(t - 1) * 12 + ns - 1]);
+  }
+  fprintf(stderr, "%s clocks/step:", tag);
+  double tot = 0;
+  for (int k = 0; k < ns; ++k) {
+    fprintf(stderr, " %s=%.0f", names[k], acc[k] / (n - 3));
+    tot += acc[k] / (n - 3);
+  }
+  fprintf(stderr, " total=%.0f\n", tot);
 }
 
 template <typename Kern, typename P>
@@ -1085,21 +1142,11 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
     long long h[64 * 12];
     AVSR_CHECK_CUDA(cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(dbg_dev);
-    const int n = T < 64 ? T : 64;
     const char* names[10] = {"loop-top", "wait MMA+ld", "act+bar", "combine+send h", "hbm st/ld", "wait h gather",
                              "scores", "softmax", "ctx sweep", "reduce+send ctx"};
-    double acc[10] = {0};
-    for (int t = 3; t < n; ++t) {
-      for (int k = 1; k < 10; ++k) acc[k] += (double)(h[t * 12 + k] - h[t * 12 + k - 1]);
-      acc[0] += (double)(h[t * 12] - h[(t - 1) * 12 + 9]);
-    }
-    fprintf(stderr, "[ap fwd T=%d B=%d Tm=%d] clocks/step:", T, B, m.Tm);
-    double tot = 0;
-    for (int k = 0; k < 10; ++k) {
-      fprintf(stderr, " %s=%.0f", names[k], acc[k] / (n - 3));
-      tot += acc[k] / (n - 3);
-    }
-    fprintf(stderr, " total=%.0f\n", tot);
+    char tag[96];
+    snprintf(tag, sizeof tag, "[ap fwd T=%d B=%d Tm=%d]", T, B, m.Tm);
+    print_phase_clocks(tag, h, T < 64 ? T : 64, 10, names);
   }
   // attention vectors of all steps in one product: S[1:, :, :At] = [h | ctx] Wl (tf32-rounded operand rows)
   AVSR_TRY(gemm(st, 0, 0, T * B, At, H + DM, m.hc, H + DM, m.Wl, m.A, r->S + (size_t)B * SW, SW, 0.0f, nullptr, 1));
@@ -1141,8 +1188,26 @@ int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   p.len = r->len; p.mem_len = m.mem_len; p.gates = r->gates; p.craw = r->craw; p.c0 = r->c0; p.Wp = Wp;
   p.keys = keys_h; p.values = values_h; p.g = m.g; p.hc = m.hc; p.align = m.align; p.douthc = dhc_in;
   p.dcT = r->dcT; p.dhT = r->dhT; p.dZ = r->dZ; p.ds = m.ds; p.dhc = m.dhc; p.dg = m.dg; p.dc0 = r->dc0; p.dh0 = r->dh0;
+  p.dbg = nullptr;
+  long long* dbg_dev = nullptr;
+  if (getenv("AVSR_AP_DEBUG")) {
+    AVSR_CHECK_CUDA(cudaMalloc(&dbg_dev, 64 * 12 * sizeof(long long)));
+    AVSR_CHECK_CUDA(cudaMemset(dbg_dev, 0, 64 * 12 * sizeof(long long)));
+    p.dbg = dbg_dev;
+  }
   AVSR_TRY(slice_width(B) == 32 ? launch_cluster(st, attn_lstm_persist_bwd_kernel<32>, B, 32, BwdCfg<32>::THREADS, BwdCfg<32>::SMEM, p)
                                  : launch_cluster(st, attn_lstm_persist_bwd_kernel<16>, B, 16, BwdCfg<16>::THREADS, BwdCfg<16>::SMEM, p));
+  if (dbg_dev) {
+    AVSR_CHECK_CUDA(cudaStreamSynchronize(st));
+    long long h[64 * 12];
+    AVSR_CHECK_CUDA(cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(dbg_dev);
+    const char* names[12] = {"loop-top", "wait redH/redC+fold", "dctx+cta bar", "values sweep", "softmax bwd", "keys sweep",
+                             "reduce+send dq", "wait dq", "dz->smem", "hbm st/ld", "wait MMA", "tmem ld+push"};
+    char tag[96];
+    snprintf(tag, sizeof tag, "[ap bwd T=%d B=%d Tm=%d]", T, B, m.Tm);
+    print_phase_clocks(tag, h, T < 64 ? T : 64, 12, names);
+  }
   if (r->dh0)  // dh_0 += dz_0 Wh^T (un-fused: the zero attention state of step 0)
     AVSR_TRY(gemm(st, 0, 1, B, H, 4 * H, r->dZ, 4 * H, r->Wrec + (size_t)At * 4 * H, 4 * H, r->dh0, H, 1.0f, nullptr));
   // dA_t = dz_{t+1} Wa^T (+ dout_t, masked): gradient wrt the attention vectors, for dWl
