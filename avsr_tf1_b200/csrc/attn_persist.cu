@@ -1090,7 +1090,26 @@ static int launch_cluster(cudaStream_t st, Kern kern, int B, int nb, int threads
   return 0;
 }
 
+// Cluster width of the persistent attention kernels: 4 (attn_persist4.cu: 33 clusters fit a B200, 2 attended
+// utterances per CTA) unless AVSR_AP_CLUSTER=8 selects the kernels of this file.
+static int cluster_width() {
+  if (const char* e = getenv("AVSR_AP_CLUSTER")) {
+    if (atoi(e) == 8) return 8;
+  }
+  return 4;
+}
+
 }  // namespace ap
+
+int attn_persist4_launch_fwd(cudaStream_t st, int T, int B, int Tm, int scaled, const int* len, const int* mem_len,
+                             float* gates, const float* Wp, const void* keys_h, const void* values_h, const float* g,
+                             const float* c0, float* S, int SW, int At, float* craw, float* out, float* hc, float* align,
+                             float* cT, float* hT);  // attn_persist4.cu
+int attn_persist4_launch_bwd(cudaStream_t st, int T, int B, int Tm, int scaled, float grad_scale, const int* len,
+                             const int* mem_len, const float* gates, const float* craw, const float* c0, const float* Wp,
+                             const void* keys_h, const void* values_h, const float* g, const float* hc, const float* align,
+                             const float* douthc, const float* dcT, const float* dhT, float* dZ, float* ds, float* dhc,
+                             float* dg, float* dc0, float* dh0);  // attn_persist4.cu
 
 size_t attn_persist_work_floats(int B, int H, int Dm, int Tm) {
   // fused weights [(H+Dm),4H] + product scratch [H,4H] + fp16 keys / values
@@ -1135,8 +1154,13 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
     AVSR_CHECK_CUDA(cudaMemset(dbg_dev, 0, 64 * 12 * sizeof(long long)));
     p.dbg = dbg_dev;
   }
-  AVSR_TRY(slice_width(B) == 32 ? launch_cluster(st, attn_lstm_persist_fwd_kernel<32>, B, 32, FwdCfg<32>::THREADS, FwdCfg<32>::SMEM, p)
-                                 : launch_cluster(st, attn_lstm_persist_fwd_kernel<16>, B, 16, FwdCfg<16>::THREADS, FwdCfg<16>::SMEM, p));
+  if (cluster_width() == 4 && !dbg_dev) {
+    AVSR_TRY(attn_persist4_launch_fwd(st, T, B, m.Tm, p.scaled, p.len, p.mem_len, p.gates, p.Wp, p.keys, p.values, p.g, p.c0, p.S,
+                                      p.SW, p.At, p.craw, p.out, p.hc, p.align, p.cT, p.hT));
+  } else {
+    AVSR_TRY(slice_width(B) == 32 ? launch_cluster(st, attn_lstm_persist_fwd_kernel<32>, B, 32, FwdCfg<32>::THREADS, FwdCfg<32>::SMEM, p)
+                                   : launch_cluster(st, attn_lstm_persist_fwd_kernel<16>, B, 16, FwdCfg<16>::THREADS, FwdCfg<16>::SMEM, p));
+  }
   if (dbg_dev) {
     AVSR_CHECK_CUDA(cudaStreamSynchronize(st));
     long long h[64 * 12];
@@ -1195,8 +1219,14 @@ int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
     AVSR_CHECK_CUDA(cudaMemset(dbg_dev, 0, 64 * 12 * sizeof(long long)));
     p.dbg = dbg_dev;
   }
-  AVSR_TRY(slice_width(B) == 32 ? launch_cluster(st, attn_lstm_persist_bwd_kernel<32>, B, 32, BwdCfg<32>::THREADS, BwdCfg<32>::SMEM, p)
-                                 : launch_cluster(st, attn_lstm_persist_bwd_kernel<16>, B, 16, BwdCfg<16>::THREADS, BwdCfg<16>::SMEM, p));
+  if (cluster_width() == 4 && !dbg_dev) {
+    AVSR_TRY(attn_persist4_launch_bwd(st, T, B, m.Tm, p.scaled, p.grad_scale, p.len, p.mem_len, p.gates, p.craw, p.c0, p.Wp,
+                                      p.keys, p.values, p.g, p.hc, p.align, p.douthc, p.dcT, p.dhT, p.dZ, p.ds, p.dhc, p.dg,
+                                      p.dc0, p.dh0));
+  } else {
+    AVSR_TRY(slice_width(B) == 32 ? launch_cluster(st, attn_lstm_persist_bwd_kernel<32>, B, 32, BwdCfg<32>::THREADS, BwdCfg<32>::SMEM, p)
+                                   : launch_cluster(st, attn_lstm_persist_bwd_kernel<16>, B, 16, BwdCfg<16>::THREADS, BwdCfg<16>::SMEM, p));
+  }
   if (dbg_dev) {
     AVSR_CHECK_CUDA(cudaStreamSynchronize(st));
     long long h[64 * 12];

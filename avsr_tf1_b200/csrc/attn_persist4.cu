@@ -1,0 +1,1039 @@
+// Persistent fused AttentionWrapper(LSTMCell) layer on clusters of FOUR CTAs (forward and backward; Luong /
+// scaled-Luong scorer, one mechanism): the AV-Align cross-modal audio layer (reference encoder.py:265-290) and
+// the LAS / AV-Align decoder (decoder_unimodal.py:299-352).  Same algebra as attn_persist.cu (fused recurrent
+// matrix W' over the operand [h | ctx], attention folded out of the recurrence) - see the header there.
+//
+// Why four: a B200 keeps only 15 clusters of 8 CTAs resident (GPC granularity) but 33 clusters of 4, so a batch
+// of 256 utterances runs as ONE wave of 32 clusters x 8 utterances on 128 SMs, and every CTA owns the attention of
+// only 2 utterances.  The memory sweeps (scores / context, d(align) / dq) are bound by what one SM can pull out of
+// L2 and convert from fp16, so halving the utterances per SM is what shortens the step.
+//
+// A CTA now owns 64 hidden units = 256 gate rows = two 128-row M tiles of the per-step product, but only one
+// tile of W' (128 x 512 fp16 = 128 KB) fits in shared memory.  The second tile lives in TENSOR MEMORY and enters
+// tcgen05.mma as the A operand from TMEM (lane = row, 32-bit column c = K elements 2c, 2c+1; checked by
+// tools/micro/ts_mma_test.cu).  The backward kernel holds four 128 x 256 tiles of W'^T the same way: two in shared
+// memory, two in tensor memory.
+//
+// There is no separate MMA-issue warp: lane 0 of warp 0 issues the products at the points of the step where it
+// waits for the same barriers anyway (8 warps, 2 per SM sub-partition).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "../../include/avsr_b200.h"
+#include "common.cuh"
+
+namespace avsr {
+namespace ap4 {
+
+constexpr int CL = 4;
+constexpr int H = 256;
+constexpr int DM = 256;
+constexpr int KTOT = H + DM;            // 512
+constexpr int KB = KTOT / 64;           // 8 K-blocks of 64 halves (128 B)
+constexpr int UPC = H / CL;             // 64 hidden units per CTA
+constexpr int NB = 8;                   // utterances per cluster
+constexpr int NP = 16;                  // N of the products (M = 128 needs N % 16 == 0): 8 utterances + 8 zero rows
+constexpr int NU = NB / CL;             // utterances whose attention a CTA owns
+constexpr int THREADS = 256;
+constexpr int W_BYTES = KB * 128 * 128; // one 128 x 512 fp16 tile
+constexpr int OP_BYTES = KB * NP * 128; // one [h | ctx] operand buffer
+constexpr int MAX_TM = 384;
+constexpr int RIF = 8;                  // memory rows per batch of the attention sweeps
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v2(uint32_t addr, uint32_t mbar, uint32_t a, uint32_t b) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%2, %3}, [%1];" ::"r"(addr),
+               "r"(mbar), "r"(a), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t mbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%2, %3, %4, %5}, [%1];" ::"r"(addr),
+               "r"(mbar), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v4f(uint32_t addr, uint32_t mbar, float a, float b, float c, float d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%2, %3, %4, %5}, [%1];" ::"r"(addr),
+               "r"(mbar), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_f(uint32_t addr, uint32_t mbar, float a) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %2, [%1];" ::"r"(addr), "r"(mbar), "f"(a)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "AP4_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra AP4_DONE;\n\t"
+      "bra AP4_WAIT;\n\t"
+      "AP4_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {  // K-major, SWIZZLE_128B, SBO = 1024 B
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// A and B from shared-memory descriptors
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// A from tensor memory, B from a shared-memory descriptor
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+
+// Sums each of the 8 per-lane values v[0..7] over the 32 lanes with 9 shuffles.  Returns the complete sum of v[j] in
+// the lanes with j == ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1).
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+  float k0 = (h16 ? v[4] : v[0]) + __shfl_xor_sync(0xffffffffu, h16 ? v[0] : v[4], 16);
+  float k1 = (h16 ? v[5] : v[1]) + __shfl_xor_sync(0xffffffffu, h16 ? v[1] : v[5], 16);
+  float k2 = (h16 ? v[6] : v[2]) + __shfl_xor_sync(0xffffffffu, h16 ? v[2] : v[6], 16);
+  float k3 = (h16 ? v[7] : v[3]) + __shfl_xor_sync(0xffffffffu, h16 ? v[3] : v[7], 16);
+  float m0 = (h8 ? k2 : k0) + __shfl_xor_sync(0xffffffffu, h8 ? k0 : k2, 8);
+  float m1 = (h8 ? k3 : k1) + __shfl_xor_sync(0xffffffffu, h8 ? k1 : k3, 8);
+  float n = (h4 ? m1 : m0) + __shfl_xor_sync(0xffffffffu, h4 ? m0 : m1, 4);
+  n += __shfl_xor_sync(0xffffffffu, n, 2);
+  n += __shfl_xor_sync(0xffffffffu, n, 1);
+  return n;
+}
+// one memory row (256 halves) as 32 lanes x 16 bytes; rows at or past `L` read as zeros without touching memory
+__device__ __forceinline__ uint4 ld_row(const __half* __restrict__ mat, int tm, int L, int B, int b, int lane) {
+  return tm < L ? __ldg(reinterpret_cast<const uint4*>(mat + ((size_t)tm * B + b) * 256) + lane) : make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ float dot8(const uint4& r, const float (&q)[8]) {
+  const float2 a = unpack_h2(r.x), b = unpack_h2(r.y), c = unpack_h2(r.z), d = unpack_h2(r.w);
+  return a.x * q[0] + a.y * q[1] + b.x * q[2] + b.y * q[3] + c.x * q[4] + c.y * q[5] + d.x * q[6] + d.y * q[7];
+}
+__device__ __forceinline__ void axpy8(float w, const uint4& r, float (&acc)[8]) {
+  const float2 a = unpack_h2(r.x), b = unpack_h2(r.y), c = unpack_h2(r.z), d = unpack_h2(r.w);
+  acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]);
+  acc[2] = fmaf(w, b.x, acc[2]); acc[3] = fmaf(w, b.y, acc[3]);
+  acc[4] = fmaf(w, c.x, acc[4]); acc[5] = fmaf(w, c.y, acc[5]);
+  acc[6] = fmaf(w, d.x, acc[6]); acc[7] = fmaf(w, d.y, acc[7]);
+}
+// byte offset of half element (row, k) in a K-major SWIZZLE_128B operand with 64-half K blocks of `rows` rows
+__device__ __forceinline__ uint32_t sw128h_off(int rows, int row, int k) {
+  const int kb = k >> 6, kk = k & 63;
+  return (uint32_t)(kb * rows * 128 + row * 128 + ((((kk >> 3) ^ (row & 7)) << 4)) + ((kk & 7) << 1));
+}
+// instruction descriptor: D = f32, A = B = f16, both K-major, N = NP, M = 128
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+struct Params {
+  int T, B, Tm;
+  int scaled;            // scaled_luong: score *= g
+  int out_h;             // 1: `out` receives the cell output h; 0: out is filled by the host
+  const int* len;        // [B] query lengths
+  const int* mem_len;    // [B]
+  float* gates;          // [T,B,4H] in: x-projection (+ h0 Wh at t = 0); out: activations
+  const float* Wp;       // fused recurrent matrix [(H+DM), 4H] fp32
+  const __half* keys;    // [Tm,B,H] fp16 copy
+  const __half* values;  // [Tm,B,DM] fp16 copy
+  const float* g;        // attention_g [1] or null
+  const float* c0;       // [B,H] or null
+  float* S;              // [(T+1),B,At+H]; S[0] initialised by the caller; this kernel writes the h columns
+  int SW, At;            // row width of S and offset of the h columns
+  float* craw;           // [T,B,H]
+  float* out;            // [T,B,H] (only if out_h)
+  float* hc;             // [T,B,H+DM]  [h | ctx], tf32-rounded
+  float* align;          // [T,B,Tm]
+  float* cT;             // [B,H] or null
+  float* hT;             // [B,H] or null
+};
+
+constexpr size_t FWD_SMEM = (size_t)W_BYTES + 2 * OP_BYTES + 4 * NB * UPC * 4 + NU * MAX_TM * 4 + NU * 8 * 4 + 64 + 1024;
+static_assert(NU * 4 * DM == 4 * NB * UPC, "partial-context scratch aliases the activation buffer");
+
+__global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_fwd_kernel(const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW = base;                          // W' tile 0: gate rows of the CTA's units 0..31
+  const uint32_t sOp = sW + W_BYTES;                 // two operand buffers [h | ctx], NP rows (rows >= NB stay zero)
+  const uint32_t sAct = sOp + 2 * OP_BYTES;          // [4][NB][UPC] floats; also [NU][4][DM] partial contexts
+  const uint32_t sSc = sAct + 4 * NB * UPC * 4;      // [NU][MAX_TM] scores / alignments
+  const uint32_t sRed = sSc + NU * MAX_TM * 4;       // [NU][8] reduction scratch
+  const uint32_t sBar = sRed + NU * 8 * 4;           // [0] mma_done [1,2] h_full[buf] [3,4] ctx_full[buf]
+  const uint32_t sTmem = sBar + 40;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  float* act = reinterpret_cast<float*>(gen + (sAct - base));
+  float* sc_all = reinterpret_cast<float*>(gen + (sSc - base));
+  float* part_all = act;
+  float* red_all = reinterpret_cast<float*>(gen + (sRed - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int b0 = cluster_id_x() * NB;
+  const int T = p.T, B = p.B, Tm = p.Tm;
+
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(sBar + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // tensor memory (all 512 columns): [0, 16) / [16, 32) accumulators of the two gate tiles; [256, 512) W' tile 1
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // W' tile 0 -> shared memory as fp16: row r = gate*32 + u  <->  Wp[k][gate*H + 64*rank + u], u < 32
+  for (int seg = warp; seg < KTOT * 4; seg += THREADS / 32) {
+    const int k = seg >> 2, g = seg & 3;
+    const float w = p.Wp[(size_t)k * 4 * H + g * H + UPC * rank + lane];
+    *reinterpret_cast<__half*>(gen + (sW - base) + sw128h_off(128, g * 32 + lane, k)) = __float2half_rn(w);
+  }
+  // operand buffers start as zeros (no product is issued at t = 0; the padding rows stay zero)
+  for (int i = tid; i < 2 * OP_BYTES / 4; i += THREADS) reinterpret_cast<uint32_t*>(gen + (sOp - base))[i] = 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
+  const uint32_t tW1 = tmem_base + 256;
+  {
+    // W' tile 1 -> tensor memory: lane r = gate*32 + u <-> unit 32 + u; column c holds K elements 2c, 2c+1.
+    // warp w fills lane quarter (w & 3) = gate, columns 128*(w >> 2) .. +127
+    const int q = warp & 3, hh = warp >> 2;
+    const float* col = p.Wp + q * H + UPC * rank + 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t r[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = 2 * (128 * hh + c0 + c);
+        r[c] = pack_h2(col[(size_t)k * 4 * H], col[(size_t)(k + 1) * 4 * H]);
+      }
+      tmem_st32(tW1 + 128 * hh + c0 + ((uint32_t)(32 * q) << 16), r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  cluster_sync_all();
+
+  // gate-math role: warp <-> (gate g, tile m): the gate rows of units 32*m + lane for all NB utterances
+  const int g = warp & 3, m = warp >> 2;
+  const int unit_g = UPC * rank + 32 * m + lane;
+  // combine role (threads 0..127): utterance bq, units 4*uq .. 4*uq+3 of the CTA
+  const bool comb = tid < 4 * 32;
+  const int uq = tid & 15, bq = (tid >> 4) & 7;
+  float c_state[4], h_state[4];
+  int len_c = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) c_state[e] = h_state[e] = 0.0f;
+  if (comb) {
+    const int b = b0 + bq;
+    len_c = (b < B) ? p.len[b] : 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int u = UPC * rank + 4 * uq + e;
+      c_state[e] = (b < B && p.c0) ? p.c0[(size_t)b * H + u] : 0.0f;
+      h_state[e] = (b < B) ? p.S[(size_t)b * p.SW + p.At + u] : 0.0f;
+    }
+  }
+  int len_a[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) len_a[b] = (b0 + b < B) ? p.len[b0 + b] : 0;
+  float gx[NB];
+  {
+    const float* grow0 = p.gates + (size_t)b0 * 4 * H + g * H + unit_g;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) gx[b] = (0 < len_a[b]) ? grow0[(size_t)b * 4 * H] : 0.0f;
+  }
+  // attention role: utterance jl of this CTA, warp w4 of its group of four
+  const int jl = warp >> 2, w4 = warp & 3, gt = tid & 127;
+  const int bl_att = NU * (int)rank + jl;      // row of the utterance in the operand buffers
+  const int b_att = b0 + bl_att;
+  const int len_q = (b_att < B) ? p.len[b_att] : 0;
+  const int L = (b_att < B) ? min(p.mem_len[b_att], Tm) : 0;
+  const float gs = p.scaled ? p.g[0] : 1.0f;
+  float* sc = sc_all + jl * MAX_TM;
+  float* part = part_all + jl * 4 * DM;
+  float* red = red_all + jl * 8;
+  const uint32_t att_bar_id = 2 + jl;          // named barrier of the 128 threads of this utterance
+
+  for (int t = 0; t < T; ++t) {
+    float* grow = p.gates + ((size_t)t * B + b0) * 4 * H + g * H + unit_g;
+    uint32_t r[8];
+    if (t > 0) {
+      mbar_wait(sBar, (t - 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + m * NP, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+#pragma unroll
+      for (int b = 0; b < 8; ++b) r[b] = 0u;  // att_{-1} = 0; h_0 Wh is already in the x-projection
+    }
+    float av[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const float z = __uint_as_float(r[b]) + gx[b];
+      float a;
+      if (g == 1) a = tanhf_acc(z);
+      else a = sigmoidf_acc(g == 2 ? z + 1.0f : z);
+      av[b] = a;
+      act[(g * NB + b) * UPC + 32 * m + lane] = a;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const uint32_t nb = (t + 1) & 1;
+    const uint32_t hbar_n = sBar + 8 + 8 * nb, cbar_n = sBar + 24 + 8 * nb;
+    float hv[4], ov[4], cr[4];
+    if (comb) {
+      const bool live = t < len_c;
+      if (live) {
+        const float4 ai = *reinterpret_cast<const float4*>(&act[(0 * NB + bq) * UPC + 4 * uq]);
+        const float4 aj = *reinterpret_cast<const float4*>(&act[(1 * NB + bq) * UPC + 4 * uq]);
+        const float4 af = *reinterpret_cast<const float4*>(&act[(2 * NB + bq) * UPC + 4 * uq]);
+        const float4 ao = *reinterpret_cast<const float4*>(&act[(3 * NB + bq) * UPC + 4 * uq]);
+        const float vi[4] = {ai.x, ai.y, ai.z, ai.w}, vj[4] = {aj.x, aj.y, aj.z, aj.w};
+        const float vf[4] = {af.x, af.y, af.z, af.w}, vo[4] = {ao.x, ao.y, ao.z, ao.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          cr[e] = vf[e] * c_state[e] + vi[e] * vj[e];
+          const float c = fminf(fmaxf(cr[e], -1.0f), 1.0f);
+          const float h = vo[e] * tanhf_acc(c);
+          c_state[e] = c;
+          ov[e] = h;
+          h_state[e] = tf32_rn(h);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          cr[e] = c_state[e];
+          ov[e] = 0.0f;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hv[e] = h_state[e];
+      // all-gather of h_t (fp16): operand of step t+1 and query of this step's attention
+      const uint32_t off = sw128h_off(NP, bq, UPC * (int)rank + 4 * uq);
+      const uint32_t u01 = pack_h2(hv[0], hv[1]), u23 = pack_h2(hv[2], hv[3]);
+      const uint32_t dbuf = sOp + nb * OP_BYTES + off;
+#pragma unroll
+      for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) st_async_v2(mapa(dbuf, dst), mapa(hbar_n, dst), u01, u23);
+    }
+    // HBM side of this step + x-projection of the next (overlaps the all-gather)
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      if (t < len_a[b]) grow[(size_t)b * 4 * H] = av[b];
+    if (comb && b0 + bq < B) {
+      const size_t row = (size_t)t * B + b0 + bq;
+      const int u0 = UPC * rank + 4 * uq;
+      *reinterpret_cast<float4*>(p.craw + row * H + u0) = make_float4(cr[0], cr[1], cr[2], cr[3]);
+      if (p.out_h) *reinterpret_cast<float4*>(p.out + row * H + u0) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      *reinterpret_cast<float4*>(p.S + (row + B) * p.SW + p.At + u0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      *reinterpret_cast<float4*>(p.hc + row * (H + DM) + u0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    }
+    if (t + 1 < T) {
+      const float* gnext = grow + (size_t)B * 4 * H;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) gx[b] = (t + 1 < len_a[b]) ? gnext[(size_t)b * 4 * H] : 0.0f;
+    }
+    // ---------------- attention of utterance b_att with query h_t ----------------
+    const bool live_q = t < len_q;    // masked steps (and padding utterances) skip the memory sweep
+    // software-pipelined sweeps in half-batches of 4 rows; the first keys are requested before h_t has landed
+    uint4 ra[4], rb[4];
+    if (live_q) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ra[j] = ld_row(p.keys, w4 + 4 * j, L, B, b_att, lane);
+        rb[j] = ld_row(p.keys, w4 + 16 + 4 * j, L, B, b_att, lane);
+      }
+    }
+    if (tid == 0) mbar_expect_tx(hbar_n, NB * H * 2);
+    mbar_wait(hbar_n, (t >> 1) & 1);  // every CTA's h_t slice has landed in buffer nb
+    if (warp == 0 && t + 1 < T) {
+      // h half of the gate products of step t+1 (overlaps this step's attention).  Every warp has read the
+      // accumulators of step t before its activations reached the barrier that precedes the h all-gather.
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t ob = sOp + nb * OP_BYTES;
+#pragma unroll
+        for (int kb = 0; kb < H / 64; ++kb)
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t db = make_desc_k128(ob + kb * (NP * 128) + k4 * 32);
+            umma_ss(tmem_base, make_desc_k128(sW + kb * (128 * 128) + k4 * 32), db, IDESC, (kb | k4) ? 1u : 0u);
+            umma_ts(tmem_base + NP, tW1 + (kb * 4 + k4) * 8, db, IDESC, (kb | k4) ? 1u : 0u);
+          }
+      }
+      __syncwarp();
+    }
+    float ctxv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ctxv[e] = 0.0f;
+    if (live_q) {
+      // query: lane holds dims 8*lane .. 8*lane+7 (one swizzled 16-byte chunk of the operand row)
+      const uint4 qraw = *reinterpret_cast<const uint4*>(gen + (sOp - base) + nb * OP_BYTES + sw128h_off(NP, bl_att, 8 * lane));
+      float q[8];
+      {
+        float2 a = unpack_h2(qraw.x), b = unpack_h2(qraw.y), c = unpack_h2(qraw.z), d = unpack_h2(qraw.w);
+        q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y; q[4] = c.x; q[5] = c.y; q[6] = d.x; q[7] = d.y;
+      }
+      // scores: rows tm = w4 + 4*i, one 9-shuffle reduction per batch of 8 rows
+      const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+      for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
+        float sacc[RIF];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sacc[j] = dot8(ra[j], q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.keys, tm0 + 32 + 4 * j, L, B, b_att, lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sacc[4 + j] = dot8(rb[j], q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.keys, tm0 + 48 + 4 * j, L, B, b_att, lane);
+        const float tot = warp_reduce8(sacc, lane);
+        if ((lane & 3) == 0 && tm0 + 4 * jrow < L) sc[tm0 + 4 * jrow] = gs * tot;
+      }
+      // first batch of the values: in flight during the softmax
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ra[j] = ld_row(p.values, w4 + 4 * j, L, B, b_att, lane);
+        rb[j] = ld_row(p.values, w4 + 16 + 4 * j, L, B, b_att, lane);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+      // masked softmax over the L scores (128 threads)
+      float mx = -INFINITY;
+      for (int tm = gt; tm < L; tm += 128) mx = fmaxf(mx, sc[tm]);
+      mx = warp_max(mx);
+      if (lane == 0) red[w4] = mx;
+      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+      mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+      float sum = 0.0f;
+      for (int tm = gt; tm < L; tm += 128) {
+        const float e = __expf(sc[tm] - mx);
+        sc[tm] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) red[4 + w4] = sum;
+      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+      const float inv = L > 0 ? 1.0f / ((red[4] + red[5]) + (red[6] + red[7])) : 0.0f;
+      float* arow = p.align + ((size_t)t * B + b_att) * Tm;
+      for (int tm = gt; tm < Tm; tm += 128) {
+        const float a = tm < L ? sc[tm] * inv : 0.0f;
+        if (tm < L) sc[tm] = a;
+        arow[tm] = a;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+      // context: rows tm = w4 + 4*i, lane accumulates dims 8*lane .. +7
+      for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
+        float a[RIF];
+#pragma unroll
+        for (int j = 0; j < RIF; ++j) a[j] = tm0 + 4 * j < L ? sc[tm0 + 4 * j] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) axpy8(a[j], ra[j], ctxv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.values, tm0 + 32 + 4 * j, L, B, b_att, lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) axpy8(a[4 + j], rb[j], ctxv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.values, tm0 + 48 + 4 * j, L, B, b_att, lane);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part[w4 * DM + 8 * lane + e] = ctxv[e];
+      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+      if (w4 == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          ctxv[e] = tf32_rn((part[8 * lane + e] + part[DM + 8 * lane + e]) + (part[2 * DM + 8 * lane + e] + part[3 * DM + 8 * lane + e]));
+      }
+    }
+    if (w4 == 0) {
+      // ctx_t of this utterance: HBM (tf32-rounded fp32, for the backward pass) + all-gather (fp16 operand)
+      if (b_att < B) {
+        float* dst = p.hc + ((size_t)t * B + b_att) * (H + DM) + H + 8 * lane;
+        *reinterpret_cast<float4*>(dst) = make_float4(ctxv[0], ctxv[1], ctxv[2], ctxv[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(ctxv[4], ctxv[5], ctxv[6], ctxv[7]);
+        if (!live_q) {
+          float* arow = p.align + ((size_t)t * B + b_att) * Tm;
+          for (int tm = lane; tm < Tm; tm += 32) arow[tm] = 0.0f;
+        }
+      }
+      const uint32_t off = sw128h_off(NP, bl_att, H + 8 * lane);
+      const uint32_t dbuf = sOp + nb * OP_BYTES + off;
+      const uint32_t c0 = pack_h2(ctxv[0], ctxv[1]), c1 = pack_h2(ctxv[2], ctxv[3]);
+      const uint32_t c2 = pack_h2(ctxv[4], ctxv[5]), c3 = pack_h2(ctxv[6], ctxv[7]);
+#pragma unroll
+      for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) st_async_v4(mapa(dbuf, dst), mapa(cbar_n, dst), c0, c1, c2, c3);
+    }
+    if (warp == 0) {
+      // ctx half of the gate products of step t+1, once every context of this step has landed.  After the last
+      // step the wait only drains the all-gathers: no st.async may be in flight towards this CTA when it exits.
+      if (lane == 0) mbar_expect_tx(cbar_n, NB * DM * 2);
+      mbar_wait(cbar_n, (t >> 1) & 1);
+      if (t + 1 < T) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t ob = sOp + nb * OP_BYTES;
+#pragma unroll
+          for (int kb = H / 64; kb < KB; ++kb)
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t db = make_desc_k128(ob + kb * (NP * 128) + k4 * 32);
+              umma_ss(tmem_base, make_desc_k128(sW + kb * (128 * 128) + k4 * 32), db, IDESC, 1u);
+              umma_ts(tmem_base + NP, tW1 + (kb * 4 + k4) * 8, db, IDESC, 1u);
+            }
+          umma_commit(sBar);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if (comb && b0 + bq < B) {
+    const size_t o = (size_t)(b0 + bq) * H + UPC * rank + 4 * uq;
+    if (p.cT) *reinterpret_cast<float4*>(p.cT + o) = make_float4(c_state[0], c_state[1], c_state[2], c_state[3]);
+    if (p.hT) *reinterpret_cast<float4*>(p.hT + o) = make_float4(h_state[0], h_state[1], h_state[2], h_state[3]);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  cluster_sync_all();
+}
+
+// =====================================================================================================
+// backward:  [dh_{t-1} | dctx_{t-1}] = dz_t W'^T + (dout_{t-1} Wl^T)
+// A CTA owns the gate columns of its 64 units (K split of the product over the cluster): partial [h | ctx] rows are
+// reduce-scattered through DSMEM (h rows to the owners of the units, ctx rows to the owners of the utterances);
+// attention backward of its 2 utterances; dq all-to-all.  dz enters the tensor core as fp16 scaled by a power of two.
+// =====================================================================================================
+struct BwdParams {
+  int T, B, Tm, scaled;
+  float grad_scale, inv_grad_scale;
+  const int* len;
+  const int* mem_len;
+  const float* gates;    // [T,B,4H] activations
+  const float* craw;     // [T,B,H]
+  const float* c0;       // [B,H] or null
+  const float* Wp;       // fused recurrent matrix [(H+DM),4H]
+  const __half* keys;    // [Tm,B,H]
+  const __half* values;  // [Tm,B,DM]
+  const float* g;        // [1] or null
+  const float* hc;       // [T,B,H+DM] forward [h | ctx]
+  const float* align;    // [T,B,Tm]
+  const float* douthc;   // [T,B,H+DM] = dout Wl^T (unmasked) or null
+  const float* dcT;      // [B,H] or null
+  const float* dhT;      // [B,H] or null
+  float* dZ;             // [T,B,4H]
+  float* ds;             // [T,B,Tm]
+  float* dhc;            // [T,B,H+DM]: the ctx columns receive dctx_t
+  float* dg;             // [1] or null
+  float* dc0;            // [B,H] or null
+  float* dh0;            // [B,H] or null
+};
+
+constexpr int BW_TILE_BYTES = 4 * 128 * 128;         // one 128-row tile of W'^T restricted to the CTA's 256 gate columns
+constexpr int BW_DZ_BYTES = 4 * NP * 128;            // B operand: 4 K-blocks (gates) x [NP rows x 64 units]
+constexpr int REDH_FLOATS = CL * NB * UPC;           // [src][b][u]
+constexpr int REDC_FLOATS = CL * NU * DM;            // [src][utt][dim]; also the dq partial scratch [NU][4][DM]
+constexpr int DQ_FLOATS = CL * NU * UPC;             // [src][utt][u]
+constexpr size_t BWD_SMEM = (size_t)2 * BW_TILE_BYTES + BW_DZ_BYTES + REDH_FLOATS * 4 + REDC_FLOATS * 4 + DQ_FLOATS * 4 +
+                            NU * DM * 4 + 2 * NU * MAX_TM * 4 + NU * 8 * 4 + 64 + 1024;
+static_assert(NU * 4 * DM <= REDC_FLOATS, "dq partial scratch must fit the ctx reduce buffer");
+
+__global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW = base;                                  // tiles 0, 1 (h rows) of W'^T
+  const uint32_t sDz = sW + 2 * BW_TILE_BYTES;
+  const uint32_t sRedH = sDz + BW_DZ_BYTES;
+  const uint32_t sRedC = sRedH + REDH_FLOATS * 4;
+  const uint32_t sDq = sRedC + REDC_FLOATS * 4;
+  const uint32_t sCtx = sDq + DQ_FLOATS * 4;                 // [NU][DM] dctx of the CTA's utterances
+  const uint32_t sSc = sCtx + NU * DM * 4;                   // [NU][MAX_TM] alignments
+  const uint32_t sDs = sSc + NU * MAX_TM * 4;                // [NU][MAX_TM] d(align) / ds
+  const uint32_t sRed = sDs + NU * MAX_TM * 4;               // [NU][8]
+  const uint32_t sBar = sRed + NU * 8 * 4;  // [0] mma_done [1] dz_ready [2] redH_full [3] redC_full [4] dq_full
+  const uint32_t sTmem = sBar + 40;
+  const uint32_t barMma = sBar, barDz = sBar + 8, barRedH = sBar + 16, barRedC = sBar + 24, barDq = sBar + 32;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  float* redH = reinterpret_cast<float*>(gen + (sRedH - base));
+  float* redC = reinterpret_cast<float*>(gen + (sRedC - base));
+  float* dqb = reinterpret_cast<float*>(gen + (sDq - base));
+  float* ctx_all = reinterpret_cast<float*>(gen + (sCtx - base));
+  float* sc_all = reinterpret_cast<float*>(gen + (sSc - base));
+  float* ds_all = reinterpret_cast<float*>(gen + (sDs - base));
+  float* part_all = redC;
+  float* red_all = reinterpret_cast<float*>(gen + (sRed - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int b0 = cluster_id_x() * NB;
+  const int T = p.T, B = p.B, Tm = p.Tm;
+
+  if (tid == 0) {
+    mbar_init(barMma, 1);
+    mbar_init(barDz, THREADS);
+    mbar_init(barRedH, 1);
+    mbar_init(barRedC, 1);
+    mbar_init(barDq, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // tensor memory (all 512 columns): [0, 64) accumulators of the four 128-row tiles; [256, 512) tiles 2, 3 (ctx dims)
+  // of W'^T as A operands (128 columns = 256 K each)
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // A[n][k = g*64 + u] = Wp[n][g*H + 64*rank + u]; rows n < 256 -> shared memory (tile n >> 7)
+  for (int seg = warp; seg < 256 * 8; seg += THREADS / 32) {
+    const int n = seg >> 3, g = (seg >> 1) & 3, u = 32 * (seg & 1) + lane;
+    const float w = p.Wp[(size_t)n * 4 * H + g * H + UPC * rank + u];
+    *reinterpret_cast<__half*>(gen + (sW - base) + (n >> 7) * BW_TILE_BYTES + sw128h_off(128, n & 127, g * 64 + u)) =
+        __float2half_rn(w);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
+  const uint32_t tA = tmem_base + 256;
+  {
+    // rows n = 256 + 128*tt + 32*q + lane -> tensor memory tile tt; column c holds k = 2c, 2c+1 (adjacent units)
+    const int q = warp & 3, tt = warp >> 2;
+    const float* row = p.Wp + (size_t)(256 + 128 * tt + 32 * q + lane) * 4 * H + UPC * rank;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t r[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = 2 * (c0 + c), g = k >> 6, u = k & 63;
+        const float2 w = *reinterpret_cast<const float2*>(row + g * H + u);
+        r[c] = pack_h2(w.x, w.y);
+      }
+      tmem_st32(tA + 128 * tt + c0 + ((uint32_t)(32 * q) << 16), r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  cluster_sync_all();
+
+  // gate-gradient role: thread = (local unit ul, utterances 2*(warp >> 1) + j)
+  constexpr int PB = 2;
+  const int ul = 32 * (warp & 1) + lane;
+  const int unit = UPC * rank + ul;
+  float dc[PB], dh_carry[PB];
+  int len_t[PB];
+#pragma unroll
+  for (int j = 0; j < PB; ++j) {
+    const int b = b0 + (warp >> 1) * PB + j;
+    len_t[j] = (b < B) ? p.len[b] : 0;
+    dc[j] = (b < B && p.dcT) ? p.dcT[(size_t)b * H + unit] : 0.0f;
+    dh_carry[j] = (b < B && p.dhT) ? p.dhT[(size_t)b * H + unit] : 0.0f;
+  }
+  float gi[PB], gj[PB], gf[PB], go[PB], crw[PB], cpv[PB], dov[PB];
+#pragma unroll
+  for (int j = 0; j < PB; ++j) gi[j] = gj[j] = gf[j] = go[j] = crw[j] = cpv[j] = dov[j] = 0.0f;
+  auto load_step = [&](int t) {
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int b = b0 + (warp >> 1) * PB + j;
+      if (t >= 0 && t < len_t[j]) {
+        const float* g = p.gates + ((size_t)t * B + b) * 4 * H + unit;
+        gi[j] = g[0]; gj[j] = g[H]; gf[j] = g[2 * H]; go[j] = g[3 * H];
+        const size_t o = ((size_t)t * B + b) * H + unit;
+        crw[j] = p.craw[o];
+        cpv[j] = t > 0 ? p.craw[o - (size_t)B * H] : (p.c0 ? p.c0[(size_t)b * H + unit] : 0.0f);
+        dov[j] = p.douthc ? p.douthc[((size_t)t * B + b) * (H + DM) + unit] : 0.0f;
+      }
+    }
+  };
+  // attention role
+  const int jl = warp >> 2, w4 = warp & 3, gt = tid & 127;
+  const int bl_att = NU * (int)rank + jl;
+  const int b_att = b0 + bl_att;
+  const int len_q = (b_att < B) ? p.len[b_att] : 0;
+  const int L = (b_att < B) ? min(p.mem_len[b_att], Tm) : 0;
+  const float gs = p.scaled ? p.g[0] : 1.0f;
+  float* dctx_s = ctx_all + jl * DM;
+  float* a_s = sc_all + jl * MAX_TM;
+  float* ds_s = ds_all + jl * MAX_TM;
+  float* part = part_all + jl * 4 * DM;
+  float* red = red_all + jl * 8;
+  const uint32_t att_bar_id = 2 + jl;
+  // reduce-scatter role after the product: warps 0-3 forward tiles 0, 1 (h rows), warps 4-7 tiles 2, 3 (ctx dims)
+  const int q = warp & 3;
+
+  load_step(T - 1);
+  for (int it = 0; it < T; ++it) {
+    const int t = T - 1 - it;
+    const bool live_q = t < len_q;
+    // ---- top: partial sums pushed during the previous iteration ------------------------------------------
+    float dh_in[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) dh_in[j] = dh_carry[j];
+    uint4 ra[4], rb[4];  // software-pipelined sweeps: the first values are requested before the partials arrive
+    if (live_q) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ra[j] = ld_row(p.values, w4 + 4 * j, L, B, b_att, lane);
+        rb[j] = ld_row(p.values, w4 + 16 + 4 * j, L, B, b_att, lane);
+      }
+    }
+    if (it > 0) {
+      if (tid == 0) {
+        mbar_expect_tx(barRedC, REDC_FLOATS * 4);
+        mbar_expect_tx(barRedH, REDH_FLOATS * 4);
+      }
+      mbar_wait(barRedH, (it - 1) & 1);
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int bl = (warp >> 1) * PB + j;
+#pragma unroll
+        for (int src = 0; src < CL; ++src) dh_in[j] += redH[(src * NB + bl) * UPC + ul];
+      }
+      mbar_wait(barRedC, (it - 1) & 1);
+    }
+    if (live_q) {
+      for (int d = gt; d < DM; d += 128) {
+        float v = p.douthc ? p.douthc[((size_t)t * B + b_att) * (H + DM) + H + d] : 0.0f;
+        if (it > 0) {
+#pragma unroll
+          for (int src = 0; src < CL; ++src) v += redC[(src * NU + jl) * DM + d];
+        }
+        dctx_s[d] = v;
+        p.dhc[((size_t)t * B + b_att) * (H + DM) + H + d] = v;
+      }
+      for (int tm = gt; tm < Tm; tm += 128) a_s[tm] = p.align[((size_t)t * B + b_att) * Tm + tm];
+    }
+    // from here on redH and redC are free again: a peer can only push the next partials after it has received this
+    // CTA's dq, which leaves after this barrier (so one copy of each suffices, and redC doubles as dq scratch)
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- (A/B) attention backward of the CTA's utterances, dq all-to-all ---------------------------------
+    float dqv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dqv[e] = 0.0f;
+    if (live_q) {
+      float dcx[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dcx[e] = dctx_s[8 * lane + e];
+      // d(align)[tm] = values[tm] . dctx
+      const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+      for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
+        float sacc[RIF];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sacc[j] = dot8(ra[j], dcx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.values, tm0 + 32 + 4 * j, L, B, b_att, lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sacc[4 + j] = dot8(rb[j], dcx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.values, tm0 + 48 + 4 * j, L, B, b_att, lane);
+        const float tot = warp_reduce8(sacc, lane);
+        if ((lane & 3) == 0 && tm0 + 4 * jrow < L) ds_s[tm0 + 4 * jrow] = tot;
+      }
+      // first batch of the keys: in flight during the softmax backward
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        ra[j] = ld_row(p.keys, w4 + 4 * j, L, B, b_att, lane);
+        rb[j] = ld_row(p.keys, w4 + 16 + 4 * j, L, B, b_att, lane);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+      float dot = 0.0f;
+      for (int tm = gt; tm < L; tm += 128) dot = fmaf(a_s[tm], ds_s[tm], dot);
+      dot = warp_sum(dot);
+      if (lane == 0) red[w4] = dot;
+      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+      dot = (red[0] + red[1]) + (red[2] + red[3]);
+      // d(score) of this step, before the Luong scale (dkeys is formed after the loop).  d(attention_g) =
+      // sum_tm ds[tm] (keys[tm].h) = (1/g) sum_tm ds[tm] log a[tm]: the scores are (log a + log Z) / g and
+      // sum_tm ds[tm] = 0, so the normaliser drops out.
+      float* dsrow = p.ds + ((size_t)t * B + b_att) * Tm;
+      float gacc = 0.0f;
+      for (int tm = gt; tm < Tm; tm += 128) {
+        const float a = tm < L ? a_s[tm] : 0.0f;
+        const float d = tm < L ? a * (ds_s[tm] - dot) : 0.0f;
+        dsrow[tm] = d;
+        if (tm < L) ds_s[tm] = d;
+        if (a > 0.0f) gacc = fmaf(d, __logf(a), gacc);
+      }
+      if (p.scaled && p.dg && gs != 0.0f) {
+        gacc = warp_sum(gacc);
+        if (lane == 0) atomicAdd(p.dg, gacc / gs);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+      // keys sweep: dq += g * ds[tm] * keys[tm]
+      for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
+        float d[RIF];
+#pragma unroll
+        for (int j = 0; j < RIF; ++j) d[j] = tm0 + 4 * j < L ? ds_s[tm0 + 4 * j] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) axpy8(d[j], ra[j], dqv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.keys, tm0 + 32 + 4 * j, L, B, b_att, lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) axpy8(d[4 + j], rb[j], dqv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.keys, tm0 + 48 + 4 * j, L, B, b_att, lane);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part[w4 * DM + 8 * lane + e] = dqv[e];
+      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+      if (w4 == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          dqv[e] = gs * ((part[8 * lane + e] + part[DM + 8 * lane + e]) + (part[2 * DM + 8 * lane + e] + part[3 * DM + 8 * lane + e]));
+      }
+    }
+    if (w4 == 0) {
+      // dq dims 8*lane .. +7 belong to the CTA owning units (8*lane)/64
+      const uint32_t dst = (uint32_t)(lane >> 3);
+      const uint32_t a0 = mapa(sDq + (uint32_t)(((rank * NU + jl) * UPC + ((8 * lane) & (UPC - 1))) * 4), dst);
+      const uint32_t bar = mapa(barDq, dst);
+      st_async_v4f(a0, bar, dqv[0], dqv[1], dqv[2], dqv[3]);
+      st_async_v4f(a0 + 16, bar, dqv[4], dqv[5], dqv[6], dqv[7]);
+    }
+    // ---- (C/D) dq of this CTA's units -> gate gradients --------------------------------------------------
+    if (tid == 0) mbar_expect_tx(barDq, DQ_FLOATS * 4);
+    mbar_wait(barDq, it & 1);
+    float dz[4][PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int bl = (warp >> 1) * PB + j;
+      float dh = dh_in[j];
+      if (t < len_t[j]) {
+        dh += dov[j] + dqb[bl * UPC + ul];
+        const float c = fminf(fmaxf(crw[j], -1.0f), 1.0f);
+        const float tc = tanhf_acc(c);
+        const float cp = t > 0 ? fminf(fmaxf(cpv[j], -1.0f), 1.0f) : cpv[j];
+        const float dct = dc[j] + dh * go[j] * (1.0f - tc * tc);
+        const float dcr = (crw[j] >= -1.0f && crw[j] <= 1.0f) ? dct : 0.0f;
+        dz[0][j] = dcr * gj[j] * gi[j] * (1.0f - gi[j]);
+        dz[1][j] = dcr * gi[j] * (1.0f - gj[j] * gj[j]);
+        dz[2][j] = dcr * cp * gf[j] * (1.0f - gf[j]);
+        dz[3][j] = dh * tc * go[j] * (1.0f - go[j]);
+        dc[j] = dcr * gf[j];
+        dh_carry[j] = 0.0f;
+      } else {
+        dz[0][j] = dz[1][j] = dz[2][j] = dz[3][j] = 0.0f;
+        dh_carry[j] = dh;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<__half*>(gen + (sDz - base) + sw128h_off(NP, bl, g * 64 + ul)) = __float2half_rn(dz[g][j] * p.grad_scale);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(barDz);
+    if (warp == 0) {
+      // partial [h | ctx](512) x NB from this CTA's 256 gate columns, once every warp's dz is in shared memory
+      mbar_wait(barDz, it & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t db = make_desc_k128(sDz + kb * (NP * 128) + k4 * 32);
+              if (mt < 2)
+                umma_ss(tmem_base + mt * NP, make_desc_k128(sW + mt * BW_TILE_BYTES + kb * (128 * 128) + k4 * 32), db, IDESC,
+                        (kb | k4) ? 1u : 0u);
+              else
+                umma_ts(tmem_base + mt * NP, tA + (mt - 2) * 128 + (kb * 4 + k4) * 8, db, IDESC, (kb | k4) ? 1u : 0u);
+            }
+        umma_commit(barMma);
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int b = b0 + (warp >> 1) * PB + j;
+      if (b < B) {
+        float* o = p.dZ + ((size_t)t * B + b) * 4 * H + unit;
+        o[0] = tf32_rn(dz[0][j]); o[H] = tf32_rn(dz[1][j]); o[2 * H] = tf32_rn(dz[2][j]); o[3 * H] = tf32_rn(dz[3][j]);
+      }
+    }
+    load_step(t - 1);
+    // ---- (E) partial products -> owners -------------------------------------------------------------------
+    mbar_wait(barMma, it & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const int mt = 2 * (warp >> 2) + mi;
+      if (mt < 2) {  // h rows: global unit 128*mt + 32*q + lane -> owner CTA 2*mt + (q >> 1), local unit 32*(q & 1) + lane
+        uint32_t r[8];
+        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NP, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const uint32_t dst = (uint32_t)(2 * mt + (q >> 1));
+        const uint32_t a0 = mapa(sRedH + (uint32_t)((rank * NB) * UPC + 32 * (q & 1) + lane) * 4, dst);
+        const uint32_t bar = mapa(barRedH, dst);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) st_async_f(a0 + c * UPC * 4, bar, __uint_as_float(r[c]) * p.inv_grad_scale);
+      } else if (it + 1 < T) {  // ctx dims 128*(mt-2) + 32*q + lane; column c = utterance -> owner CTA c / NU
+        uint32_t r[8];
+        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NP, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int dim = 128 * (mt - 2) + 32 * q + lane;
+#pragma unroll
+        for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) {
+          const uint32_t a0 = mapa(sRedC + (uint32_t)((rank * NU) * DM + dim) * 4, dst);
+          const uint32_t bar = mapa(barRedC, dst);
+#pragma unroll
+          for (int u2 = 0; u2 < NU; ++u2) st_async_f(a0 + u2 * DM * 4, bar, __uint_as_float(r[NU * dst + u2]) * p.inv_grad_scale);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  // drain the last reduce-scatter (nothing may be in flight towards this CTA when it exits).  Its content is NOT
+  // dh_0: step 0 saw att_{-1} = 0, so dh_0 = dz_0 Wh^T with the un-fused Wh - added by the host; here only the
+  // gradient carried through fully masked utterances is written.
+  if (T > 0) {
+    if (tid == 0) mbar_expect_tx(barRedH, REDH_FLOATS * 4);
+    mbar_wait(barRedH, (T - 1) & 1);
+  }
+#pragma unroll
+  for (int j = 0; j < PB; ++j) {
+    const int b = b0 + (warp >> 1) * PB + j;
+    if (b < B) {
+      if (p.dh0) p.dh0[(size_t)b * H + unit] = dh_carry[j];
+      if (p.dc0) p.dc0[(size_t)b * H + unit] = dc[j];
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  cluster_sync_all();
+}
+
+template <typename Kern, typename P>
+static int launch_cluster(cudaStream_t st, Kern kern, int B, size_t smem, const P& p) {
+  AVSR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cdiv(B, NB) * CL);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  ++g_launch_count;
+  return 0;
+}
+
+}  // namespace ap4
+
+// launched by attn_persist_fwd / attn_persist_bwd (attn_persist.cu), which prepare the fused matrix, the fp16 copies
+// of keys / values and the batched products around the recurrent kernel
+int attn_persist4_launch_fwd(cudaStream_t st, int T, int B, int Tm, int scaled, const int* len, const int* mem_len,
+                             float* gates, const float* Wp, const void* keys_h, const void* values_h, const float* g,
+                             const float* c0, float* S, int SW, int At, float* craw, float* out, float* hc, float* align,
+                             float* cT, float* hT) {
+  ap4::Params p;
+  p.T = T; p.B = B; p.Tm = Tm; p.scaled = scaled; p.out_h = 0;
+  p.len = len; p.mem_len = mem_len; p.gates = gates; p.Wp = Wp;
+  p.keys = reinterpret_cast<const __half*>(keys_h); p.values = reinterpret_cast<const __half*>(values_h);
+  p.g = g; p.c0 = c0; p.S = S; p.SW = SW; p.At = At; p.craw = craw; p.out = out; p.hc = hc; p.align = align;
+  p.cT = cT; p.hT = hT;
+  return ap4::launch_cluster(st, ap4::attn_lstm_persist4_fwd_kernel, B, ap4::FWD_SMEM, p);
+}
+
+int attn_persist4_launch_bwd(cudaStream_t st, int T, int B, int Tm, int scaled, float grad_scale, const int* len,
+                             const int* mem_len, const float* gates, const float* craw, const float* c0, const float* Wp,
+                             const void* keys_h, const void* values_h, const float* g, const float* hc, const float* align,
+                             const float* douthc, const float* dcT, const float* dhT, float* dZ, float* ds, float* dhc,
+                             float* dg, float* dc0, float* dh0) {
+  ap4::BwdParams p;
+  p.T = T; p.B = B; p.Tm = Tm; p.scaled = scaled;
+  p.grad_scale = grad_scale; p.inv_grad_scale = 1.0f / grad_scale;
+  p.len = len; p.mem_len = mem_len; p.gates = gates; p.craw = craw; p.c0 = c0; p.Wp = Wp;
+  p.keys = reinterpret_cast<const __half*>(keys_h); p.values = reinterpret_cast<const __half*>(values_h);
+  p.g = g; p.hc = hc; p.align = align; p.douthc = douthc; p.dcT = dcT; p.dhT = dhT; p.dZ = dZ; p.ds = ds; p.dhc = dhc;
+  p.dg = dg; p.dc0 = dc0; p.dh0 = dh0;
+  return ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel, B, ap4::BWD_SMEM, p);
+}
+
+}  // namespace avsr
