@@ -1154,7 +1154,7 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
     AVSR_CHECK_CUDA(cudaMemset(dbg_dev, 0, 64 * 12 * sizeof(long long)));
     p.dbg = dbg_dev;
   }
-  if (cluster_width() == 4 && !dbg_dev) {
+  if (cluster_width() == 4) {
     AVSR_TRY(attn_persist4_launch_fwd(st, T, B, m.Tm, p.scaled, p.len, p.mem_len, p.gates, p.Wp, p.keys, p.values, p.g, p.c0, p.S,
                                       p.SW, p.At, p.craw, p.out, p.hc, p.align, p.cT, p.hT));
   } else {
@@ -1219,7 +1219,7 @@ int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
     AVSR_CHECK_CUDA(cudaMemset(dbg_dev, 0, 64 * 12 * sizeof(long long)));
     p.dbg = dbg_dev;
   }
-  if (cluster_width() == 4 && !dbg_dev) {
+  if (cluster_width() == 4) {
     AVSR_TRY(attn_persist4_launch_bwd(st, T, B, m.Tm, p.scaled, p.grad_scale, p.len, p.mem_len, p.gates, p.craw, p.c0, p.Wp,
                                       p.keys, p.values, p.g, p.hc, p.align, p.douthc, p.dcT, p.dhT, p.dZ, p.ds, p.dhc, p.dg,
                                       p.dc0, p.dh0));

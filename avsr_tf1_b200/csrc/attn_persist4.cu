@@ -109,6 +109,8 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {  // K-major
   d |= (uint64_t)2 << 61;
   return d;
 }
+// descriptor of the same operand `byte_off` bytes further (the start-address field counts 16-byte units)
+__device__ __forceinline__ uint64_t desc_at(uint64_t d, uint32_t byte_off) { return d + (uint64_t)(byte_off >> 4); }
 // A and B from shared-memory descriptors
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -186,6 +188,15 @@ __device__ __forceinline__ void axpy8(float w, const uint4& r, float (&acc)[8]) 
   acc[4] = fmaf(w, c.x, acc[4]); acc[5] = fmaf(w, c.y, acc[5]);
   acc[6] = fmaf(w, d.x, acc[6]); acc[7] = fmaf(w, d.y, acc[7]);
 }
+// lane that holds the total of row j of a batch after warp_reduce8 (its three neighbours hold copies)
+__device__ __forceinline__ int reduce8_src(int j) { return ((j >> 2) & 1) * 16 + ((j >> 1) & 1) * 8 + (j & 1) * 4; }
+// The SMALL variants of the kernels (memories of at most SMALL_TM rows, e.g. the 75 video frames of the cross-modal
+// layer) keep the scores / alignments of a warp's rows in registers: SMALL_B batches of 8 rows per warp (rows
+// w4 + 4*(8*i + j)), fully unrolled.  Longer memories (the decoder's 300 audio frames) use rolled loops and shared
+// memory instead - unrolling 12 batches three times over blows the instruction cache.
+constexpr int SMALL_TM = 96;
+constexpr int SMALL_B = SMALL_TM / 32;
+
 // byte offset of half element (row, k) in a K-major SWIZZLE_128B operand with 64-half K blocks of `rows` rows
 __device__ __forceinline__ uint32_t sw128h_off(int rows, int row, int k) {
   const int kb = k >> 6, kk = k & 63;
@@ -602,7 +613,12 @@ struct BwdParams {
   float* dg;             // [1] or null
   float* dc0;            // [B,H] or null
   float* dh0;            // [B,H] or null
+  long long* dbg;        // AVSR_AP_DEBUG: clock samples [64 iterations][12] of CTA 0, thread 0
 };
+#define AP4B_STAMP(slot)                                                                         \
+  do {                                                                                           \
+    if (p.dbg && blockIdx.x == 0 && tid == 0 && it < 64) p.dbg[it * 12 + (slot)] = clock64(); \
+  } while (0)
 
 constexpr int BW_TILE_BYTES = 4 * 128 * 128;         // one 128-row tile of W'^T restricted to the CTA's 256 gate columns
 constexpr int BW_DZ_BYTES = 4 * NP * 128;            // B operand: 4 K-blocks (gates) x [NP rows x 64 units]
@@ -613,7 +629,9 @@ constexpr size_t BWD_SMEM = (size_t)2 * BW_TILE_BYTES + BW_DZ_BYTES + REDH_FLOAT
                             NU * DM * 4 + 2 * NU * MAX_TM * 4 + NU * 8 * 4 + 64 + 1024;
 static_assert(NU * 4 * DM <= REDC_FLOATS, "dq partial scratch must fit the ctx reduce buffer");
 
+template <bool SMALL>
 __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(const BwdParams p) {
+  constexpr int MAXB = SMALL ? SMALL_B : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW = base;                                  // tiles 0, 1 (h rows) of W'^T
@@ -622,8 +640,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
   const uint32_t sRedC = sRedH + REDH_FLOATS * 4;
   const uint32_t sDq = sRedC + REDC_FLOATS * 4;
   const uint32_t sCtx = sDq + DQ_FLOATS * 4;                 // [NU][DM] dctx of the CTA's utterances
-  const uint32_t sSc = sCtx + NU * DM * 4;                   // [NU][MAX_TM] alignments
-  const uint32_t sDs = sSc + NU * MAX_TM * 4;                // [NU][MAX_TM] d(align) / ds
+  const uint32_t sSc = sCtx + NU * DM * 4;                   // [NU][MAX_TM] alignments (long memories only)
+  const uint32_t sDs = sSc + NU * MAX_TM * 4;                // [NU][MAX_TM] d(align) / ds (long memories only)
   const uint32_t sRed = sDs + NU * MAX_TM * 4;               // [NU][8]
   const uint32_t sBar = sRed + NU * 8 * 4;  // [0] mma_done [1] dz_ready [2] redH_full [3] redC_full [4] dq_full
   const uint32_t sTmem = sBar + 40;
@@ -633,8 +651,6 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
   float* redC = reinterpret_cast<float*>(gen + (sRedC - base));
   float* dqb = reinterpret_cast<float*>(gen + (sDq - base));
   float* ctx_all = reinterpret_cast<float*>(gen + (sCtx - base));
-  float* sc_all = reinterpret_cast<float*>(gen + (sSc - base));
-  float* ds_all = reinterpret_cast<float*>(gen + (sDs - base));
   float* part_all = redC;
   float* red_all = reinterpret_cast<float*>(gen + (sRed - base));
 
@@ -644,7 +660,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
   const int T = p.T, B = p.B, Tm = p.Tm;
 
   if (tid == 0) {
-    mbar_init(barMma, 1);
+    mbar_init(barMma, 4);  // one commit per 128-row tile (four issuing threads)
     mbar_init(barDz, THREADS);
     mbar_init(barRedH, 1);
     mbar_init(barRedC, 1);
@@ -693,6 +709,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   cluster_sync_all();
 
+  const uint64_t dWt = make_desc_k128(sW), dDz = make_desc_k128(sDz);
   // gate-gradient role: thread = (local unit ul, utterances 2*(warp >> 1) + j)
   constexpr int PB = 2;
   const int ul = 32 * (warp & 1) + lane;
@@ -731,8 +748,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
   const int L = (b_att < B) ? min(p.mem_len[b_att], Tm) : 0;
   const float gs = p.scaled ? p.g[0] : 1.0f;
   float* dctx_s = ctx_all + jl * DM;
-  float* a_s = sc_all + jl * MAX_TM;
-  float* ds_s = ds_all + jl * MAX_TM;
+  float* a_s = reinterpret_cast<float*>(gen + (sSc - base)) + jl * MAX_TM;
+  float* ds_s = reinterpret_cast<float*>(gen + (sDs - base)) + jl * MAX_TM;
   float* part = part_all + jl * 4 * DM;
   float* red = red_all + jl * 8;
   const uint32_t att_bar_id = 2 + jl;
@@ -747,12 +764,30 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
     float dh_in[PB];
 #pragma unroll
     for (int j = 0; j < PB; ++j) dh_in[j] = dh_carry[j];
+    AP4B_STAMP(0);
     uint4 ra[4], rb[4];  // software-pipelined sweeps: the first values are requested before the partials arrive
+    float dctx_pre[DM / 128];  // this step's dout part of dctx, likewise
+    float al[MAXB];            // and its alignments: al[i] = a[w4 + 32*i + 4*jrow], the row whose batch total this lane gets
+    const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) al[i] = 0.0f;
     if (live_q) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         ra[j] = ld_row(p.values, w4 + 4 * j, L, B, b_att, lane);
         rb[j] = ld_row(p.values, w4 + 16 + 4 * j, L, B, b_att, lane);
+      }
+#pragma unroll
+      for (int i = 0; i < DM / 128; ++i)
+        dctx_pre[i] = p.douthc ? p.douthc[((size_t)t * B + b_att) * (H + DM) + H + gt + 128 * i] : 0.0f;
+      if constexpr (SMALL) {
+#pragma unroll
+        for (int i = 0; i < MAXB; ++i) {
+          const int tm = w4 + 32 * i + 4 * jrow;
+          if (tm < L) al[i] = p.align[((size_t)t * B + b_att) * Tm + tm];
+        }
+      } else {
+        for (int tm = gt; tm < Tm; tm += 128) a_s[tm] = p.align[((size_t)t * B + b_att) * Tm + tm];
       }
     }
     if (it > 0) {
@@ -769,9 +804,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
       }
       mbar_wait(barRedC, (it - 1) & 1);
     }
+    AP4B_STAMP(1);
     if (live_q) {
-      for (int d = gt; d < DM; d += 128) {
-        float v = p.douthc ? p.douthc[((size_t)t * B + b_att) * (H + DM) + H + d] : 0.0f;
+#pragma unroll
+      for (int i = 0; i < DM / 128; ++i) {
+        const int d = gt + 128 * i;
+        float v = dctx_pre[i];
         if (it > 0) {
 #pragma unroll
           for (int src = 0; src < CL; ++src) v += redC[(src * NU + jl) * DM + d];
@@ -779,78 +817,143 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
         dctx_s[d] = v;
         p.dhc[((size_t)t * B + b_att) * (H + DM) + H + d] = v;
       }
-      for (int tm = gt; tm < Tm; tm += 128) a_s[tm] = p.align[((size_t)t * B + b_att) * Tm + tm];
     }
     // from here on redH and redC are free again: a peer can only push the next partials after it has received this
     // CTA's dq, which leaves after this barrier (so one copy of each suffices, and redC doubles as dq scratch)
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    AP4B_STAMP(2);
     // ---- (A/B) attention backward of the CTA's utterances, dq all-to-all ---------------------------------
     float dqv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) dqv[e] = 0.0f;
+    float ds_keep[MAXB];  // d(score) of the rows this lane owns (written to HBM off the critical path)
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) ds_keep[i] = 0.0f;
     if (live_q) {
       float dcx[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) dcx[e] = dctx_s[8 * lane + e];
-      // d(align)[tm] = values[tm] . dctx
-      const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-      for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
-        float sacc[RIF];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sacc[j] = dot8(ra[j], dcx);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.values, tm0 + 32 + 4 * j, L, B, b_att, lane);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sacc[4 + j] = dot8(rb[j], dcx);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.values, tm0 + 48 + 4 * j, L, B, b_att, lane);
-        const float tot = warp_reduce8(sacc, lane);
-        if ((lane & 3) == 0 && tm0 + 4 * jrow < L) ds_s[tm0 + 4 * jrow] = tot;
+      if constexpr (SMALL) {
+        // d(align)[tm] = values[tm] . dctx: the batch totals stay in registers (da[i] = row jrow of batch i)
+        float da[MAXB];
+  #pragma unroll
+        for (int i = 0; i < MAXB; ++i) da[i] = 0.0f;
+  #pragma unroll
+        for (int i = 0; i < MAXB; ++i) {
+          const int tm0 = w4 + 32 * i;
+          if (tm0 >= L) break;
+          float sacc[RIF];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) sacc[j] = dot8(ra[j], dcx);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.values, tm0 + 32 + 4 * j, L, B, b_att, lane);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) sacc[4 + j] = dot8(rb[j], dcx);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.values, tm0 + 48 + 4 * j, L, B, b_att, lane);
+          da[i] = warp_reduce8(sacc, lane);
+        }
+        // first batch of the keys: in flight during the softmax backward
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ra[j] = ld_row(p.keys, w4 + 4 * j, L, B, b_att, lane);
+          rb[j] = ld_row(p.keys, w4 + 16 + 4 * j, L, B, b_att, lane);
+        }
+        AP4B_STAMP(3);
+        // dot = sum_tm a da over all rows of the utterance (al is zero past the memory length): one value per warp,
+        // merged through shared memory - the only barrier between the two sweeps
+        float dot = 0.0f;
+  #pragma unroll
+        for (int i = 0; i < MAXB; ++i) dot = fmaf(al[i], da[i], dot);
+        dot = warp_sum((lane & 3) == 0 ? dot : 0.0f);
+        if (lane == 0) red[w4] = dot;
+        asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        dot = (red[0] + red[1]) + (red[2] + red[3]);
+        // d(score) before the Luong scale: ds = a (da - dot), again in registers (da[i] is reused for it)
+  #pragma unroll
+        for (int i = 0; i < MAXB; ++i) da[i] = al[i] * (da[i] - dot);
+        AP4B_STAMP(4);
+        // keys sweep: dq += g * ds[tm] * keys[tm]
+  #pragma unroll
+        for (int i = 0; i < MAXB; ++i) {
+          const int tm0 = w4 + 32 * i;
+          if (tm0 >= L) break;
+          float d[RIF];
+  #pragma unroll
+          for (int j = 0; j < RIF; ++j) d[j] = __shfl_sync(0xffffffffu, da[i], reduce8_src(j));
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) axpy8(d[j], ra[j], dqv);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.keys, tm0 + 32 + 4 * j, L, B, b_att, lane);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) axpy8(d[4 + j], rb[j], dqv);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.keys, tm0 + 48 + 4 * j, L, B, b_att, lane);
+        }
+  #pragma unroll
+        for (int i = 0; i < MAXB; ++i) ds_keep[i] = da[i];
+      } else {
+        // d(align)[tm] = values[tm] . dctx
+        const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
+          float sacc[RIF];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) sacc[j] = dot8(ra[j], dcx);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.values, tm0 + 32 + 4 * j, L, B, b_att, lane);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) sacc[4 + j] = dot8(rb[j], dcx);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.values, tm0 + 48 + 4 * j, L, B, b_att, lane);
+          const float tot = warp_reduce8(sacc, lane);
+          if ((lane & 3) == 0 && tm0 + 4 * jrow < L) ds_s[tm0 + 4 * jrow] = tot;
+        }
+        // first batch of the keys: in flight during the softmax backward
+  #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ra[j] = ld_row(p.keys, w4 + 4 * j, L, B, b_att, lane);
+          rb[j] = ld_row(p.keys, w4 + 16 + 4 * j, L, B, b_att, lane);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        float dot = 0.0f;
+        for (int tm = gt; tm < L; tm += 128) dot = fmaf(a_s[tm], ds_s[tm], dot);
+        dot = warp_sum(dot);
+        if (lane == 0) red[w4] = dot;
+        asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        dot = (red[0] + red[1]) + (red[2] + red[3]);
+        // d(score) of this step, before the Luong scale (dkeys is formed after the loop).  d(attention_g) =
+        // sum_tm ds[tm] (keys[tm].h) = (1/g) sum_tm ds[tm] log a[tm]: the scores are (log a + log Z) / g and
+        // sum_tm ds[tm] = 0, so the normaliser drops out.
+        float* dsrow = p.ds + ((size_t)t * B + b_att) * Tm;
+        float gacc = 0.0f;
+        for (int tm = gt; tm < Tm; tm += 128) {
+          const float a = tm < L ? a_s[tm] : 0.0f;
+          const float d = tm < L ? a * (ds_s[tm] - dot) : 0.0f;
+          dsrow[tm] = d;
+          if (tm < L) ds_s[tm] = d;
+          if (a > 0.0f) gacc = fmaf(d, __logf(a), gacc);
+        }
+        if (p.scaled && p.dg && gs != 0.0f) {
+          gacc = warp_sum(gacc);
+          if (lane == 0) atomicAdd(p.dg, gacc / gs);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
+        // keys sweep: dq += g * ds[tm] * keys[tm]
+        for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
+          float d[RIF];
+  #pragma unroll
+          for (int j = 0; j < RIF; ++j) d[j] = tm0 + 4 * j < L ? ds_s[tm0 + 4 * j] : 0.0f;
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) axpy8(d[j], ra[j], dqv);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.keys, tm0 + 32 + 4 * j, L, B, b_att, lane);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) axpy8(d[4 + j], rb[j], dqv);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.keys, tm0 + 48 + 4 * j, L, B, b_att, lane);
+        }
       }
-      // first batch of the keys: in flight during the softmax backward
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        ra[j] = ld_row(p.keys, w4 + 4 * j, L, B, b_att, lane);
-        rb[j] = ld_row(p.keys, w4 + 16 + 4 * j, L, B, b_att, lane);
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
-      float dot = 0.0f;
-      for (int tm = gt; tm < L; tm += 128) dot = fmaf(a_s[tm], ds_s[tm], dot);
-      dot = warp_sum(dot);
-      if (lane == 0) red[w4] = dot;
-      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
-      dot = (red[0] + red[1]) + (red[2] + red[3]);
-      // d(score) of this step, before the Luong scale (dkeys is formed after the loop).  d(attention_g) =
-      // sum_tm ds[tm] (keys[tm].h) = (1/g) sum_tm ds[tm] log a[tm]: the scores are (log a + log Z) / g and
-      // sum_tm ds[tm] = 0, so the normaliser drops out.
-      float* dsrow = p.ds + ((size_t)t * B + b_att) * Tm;
-      float gacc = 0.0f;
-      for (int tm = gt; tm < Tm; tm += 128) {
-        const float a = tm < L ? a_s[tm] : 0.0f;
-        const float d = tm < L ? a * (ds_s[tm] - dot) : 0.0f;
-        dsrow[tm] = d;
-        if (tm < L) ds_s[tm] = d;
-        if (a > 0.0f) gacc = fmaf(d, __logf(a), gacc);
-      }
-      if (p.scaled && p.dg && gs != 0.0f) {
-        gacc = warp_sum(gacc);
-        if (lane == 0) atomicAdd(p.dg, gacc / gs);
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
-      // keys sweep: dq += g * ds[tm] * keys[tm]
-      for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
-        float d[RIF];
-#pragma unroll
-        for (int j = 0; j < RIF; ++j) d[j] = tm0 + 4 * j < L ? ds_s[tm0 + 4 * j] : 0.0f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) axpy8(d[j], ra[j], dqv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ra[j] = ld_row(p.keys, tm0 + 32 + 4 * j, L, B, b_att, lane);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) axpy8(d[4 + j], rb[j], dqv);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rb[j] = ld_row(p.keys, tm0 + 48 + 4 * j, L, B, b_att, lane);
-      }
+      AP4B_STAMP(5);
 #pragma unroll
       for (int e = 0; e < 8; ++e) part[w4 * DM + 8 * lane + e] = dqv[e];
       asm volatile("bar.sync %0, 128;" ::"r"(att_bar_id) : "memory");
@@ -869,8 +972,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
       st_async_v4f(a0 + 16, bar, dqv[4], dqv[5], dqv[6], dqv[7]);
     }
     // ---- (C/D) dq of this CTA's units -> gate gradients --------------------------------------------------
+    AP4B_STAMP(6);
     if (tid == 0) mbar_expect_tx(barDq, DQ_FLOATS * 4);
     mbar_wait(barDq, it & 1);
+    AP4B_STAMP(7);
     float dz[4][PB];
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
@@ -899,29 +1004,30 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_arrive(barDz);
-    if (warp == 0) {
-      // partial [h | ctx](512) x NB from this CTA's 256 gate columns, once every warp's dz is in shared memory
+    if ((warp & 1) == 0) {
+      // partial [h | ctx](512) x NB from this CTA's 256 gate columns, once every warp's dz is in shared memory:
+      // lane 0 of warp 2*mt issues the 128-row tile mt (independent accumulators, four threads side by side)
+      const int mt = warp >> 1;
       mbar_wait(barDz, it & 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+        for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb)
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t db = make_desc_k128(sDz + kb * (NP * 128) + k4 * 32);
-              if (mt < 2)
-                umma_ss(tmem_base + mt * NP, make_desc_k128(sW + mt * BW_TILE_BYTES + kb * (128 * 128) + k4 * 32), db, IDESC,
-                        (kb | k4) ? 1u : 0u);
-              else
-                umma_ts(tmem_base + mt * NP, tA + (mt - 2) * 128 + (kb * 4 + k4) * 8, db, IDESC, (kb | k4) ? 1u : 0u);
-            }
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t db = desc_at(dDz, kb * (NP * 128) + k4 * 32);
+            if (mt < 2)
+              umma_ss(tmem_base + mt * NP, desc_at(dWt, mt * BW_TILE_BYTES + kb * (128 * 128) + k4 * 32), db, IDESC,
+                      (kb | k4) ? 1u : 0u);
+            else
+              umma_ts(tmem_base + mt * NP, tA + (mt - 2) * 128 + (kb * 4 + k4) * 8, db, IDESC, (kb | k4) ? 1u : 0u);
+          }
         umma_commit(barMma);
       }
       __syncwarp();
     }
+    AP4B_STAMP(8);
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
       const int b = b0 + (warp >> 1) * PB + j;
@@ -931,8 +1037,31 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
       }
     }
     load_step(t - 1);
+    if (SMALL && live_q) {
+      // d(score) of this step (dkeys is formed after the loop) and d(attention_g) = sum_tm ds[tm] (keys[tm].h) =
+      // (1/g) sum_tm ds[tm] log a[tm]: the scores are (log a + log Z) / g and sum_tm ds[tm] = 0
+      float* dsrow = p.ds + ((size_t)t * B + b_att) * Tm;
+      float gacc = 0.0f;
+      if ((lane & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < MAXB; ++i) {
+          const int tm = w4 + 32 * i + 4 * jrow;
+          if (tm < L) {
+            dsrow[tm] = ds_keep[i];
+            if (al[i] > 0.0f) gacc = fmaf(ds_keep[i], __logf(al[i]), gacc);
+          }
+        }
+      }
+      for (int tm = L + gt; tm < Tm; tm += 128) dsrow[tm] = 0.0f;
+      if (p.scaled && p.dg && gs != 0.0f) {
+        gacc = warp_sum(gacc);
+        if (lane == 0) atomicAdd(p.dg, gacc / gs);
+      }
+    }
+    AP4B_STAMP(9);
     // ---- (E) partial products -> owners -------------------------------------------------------------------
     mbar_wait(barMma, it & 1);
+    AP4B_STAMP(10);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi) {
@@ -961,6 +1090,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    AP4B_STAMP(11);
   }
   // drain the last reduce-scatter (nothing may be in flight towards this CTA when it exits).  Its content is NOT
   // dh_0: step 0 saw att_{-1} = 0, so dh_0 = dz_0 Wh^T with the un-fused Wh - added by the host; here only the
@@ -1004,6 +1134,28 @@ static int launch_cluster(cudaStream_t st, Kern kern, int B, size_t smem, const 
   return 0;
 }
 
+// AVSR_AP_DEBUG (never during graph capture): average clocks CTA 0 / thread 0 spends in each phase of a step
+static int print_dbg(cudaStream_t st, long long* dbg, const char* tag, int T, int Tm, int ns, const char* const* names) {
+  AVSR_CHECK_CUDA(cudaStreamSynchronize(st));
+  long long h[64 * 12];
+  AVSR_CHECK_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(dbg);
+  const int n = T < 64 ? T : 64;
+  double acc[12] = {0};
+  for (int t = 3; t < n; ++t) {
+    for (int k = 1; k < ns; ++k) acc[k] += (double)(h[t * 12 + k] - h[t * 12 + k - 1]);
+    acc[0] += (double)(h[t * 12] - h[(t - 1) * 12 + ns - 1]);
+  }
+  fprintf(stderr, "%s T=%d Tm=%d clocks/step:", tag, T, Tm);
+  double tot = 0;
+  for (int k = 0; k < ns; ++k) {
+    fprintf(stderr, " %s=%.0f", names[k], acc[k] / (n - 3));
+    tot += acc[k] / (n - 3);
+  }
+  fprintf(stderr, " total=%.0f\n", tot);
+  return 0;
+}
+
 }  // namespace ap4
 
 // launched by attn_persist_fwd / attn_persist_bwd (attn_persist.cu), which prepare the fused matrix, the fp16 copies
@@ -1033,7 +1185,18 @@ int attn_persist4_launch_bwd(cudaStream_t st, int T, int B, int Tm, int scaled, 
   p.keys = reinterpret_cast<const __half*>(keys_h); p.values = reinterpret_cast<const __half*>(values_h);
   p.g = g; p.hc = hc; p.align = align; p.douthc = douthc; p.dcT = dcT; p.dhT = dhT; p.dZ = dZ; p.ds = ds; p.dhc = dhc;
   p.dg = dg; p.dc0 = dc0; p.dh0 = dh0;
-  return ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel, B, ap4::BWD_SMEM, p);
+  p.dbg = nullptr;
+  if (getenv("AVSR_AP_DEBUG")) {
+    static const char* names[12] = {"loop-top", "wait redH/redC+fold", "dctx+cta bar", "values sweep", "softmax bwd", "keys sweep",
+                                    "reduce+send dq", "wait dq", "dz->smem+issue", "hbm st/ld", "wait MMA", "tmem ld+push"};
+    AVSR_CHECK_CUDA(cudaMalloc(&p.dbg, 64 * 12 * sizeof(long long)));
+    AVSR_CHECK_CUDA(cudaMemset(p.dbg, 0, 64 * 12 * sizeof(long long)));
+    AVSR_TRY(Tm <= ap4::SMALL_TM ? ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<true>, B, ap4::BWD_SMEM, p)
+                                 : ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<false>, B, ap4::BWD_SMEM, p));
+    return ap4::print_dbg(st, p.dbg, "[ap4 bwd]", T, Tm, 12, names);
+  }
+  return Tm <= ap4::SMALL_TM ? ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<true>, B, ap4::BWD_SMEM, p)
+                             : ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<false>, B, ap4::BWD_SMEM, p);
 }
 
 }  // namespace avsr
