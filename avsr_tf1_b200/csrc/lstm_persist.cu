@@ -730,9 +730,16 @@ static int lp_debug_fwd(cudaStream_t st, lp::FwdParams p, int H) {
   return rc;
 }
 
+int lstm_persist4_fwd(cudaStream_t st, const AvsrRnnSeq* r);  // lstm_persist4.cu (clusters of 4, H = 256)
+int lstm_persist4_bwd(cudaStream_t st, const AvsrRnnSeq* r);
+
 // Returns -1 if this layer shape is not handled by the persistent kernels.
 int lstm_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   if (r->n_mech != 0 || r->T <= 0) return -1;
+  if (!getenv("AVSR_LP_DEBUG")) {
+    const int rc = lstm_persist4_fwd(st, r);
+    if (rc >= 0) return rc;
+  }
   if (r->H != 128 && r->H != 256) return -1;
   lp::FwdParams p;
   p.T = r->T; p.B = r->B; p.H = r->H;
@@ -747,6 +754,10 @@ int lstm_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
 
 int lstm_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   if (r->n_mech != 0 || r->T <= 0) return -1;
+  {
+    const int rc = lstm_persist4_bwd(st, r);
+    if (rc >= 0) return rc;
+  }
   if (r->H != 128 && r->H != 256) return -1;
   lp::BwdParams p;
   p.T = r->T; p.B = r->B; p.H = r->H;

@@ -121,6 +121,7 @@ class LSTMLayerOp:
         W = self.ctx.w(self.kernel)
         gW, gb = self.ctx.g(self.kernel), self.ctx.g(self.bias)
         dcT, dhT = dstate if dstate is not None else (None, None)
+        self.rnn.grad_scale = self.ctx.grad_scale  # fp16 dz operand of the cluster-of-4 backward kernel
         dZ = self.rnn.backward(dout, gW[I:], dcT=dcT, dhT=dhT)
         dZ2 = dZ.view(T * B, 4 * H)
         ops.gemm(self.x.reshape(T * B, I), dZ2, gW[:I], ta=True, beta=1.0)

@@ -47,6 +47,8 @@ def parse():
     ap.add_argument('--no-tensor-cores', action='store_true')
     ap.add_argument('--cpu-sample', type=int, default=8, help='utterances per CPU-baseline step')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--overlap', action='store_true', help='run the video and audio encoder branches on two streams')
+    ap.add_argument('--skip-roofline', action='store_true')
     return ap.parse_args()
 
 
@@ -266,6 +268,7 @@ def main():
     ds_host = to_data_sequences(pinned)
     model = Seq2SeqModel(ds_host, 'train', hp, seed=2001)
     model.use_cuda_graph = not args.no_graph
+    model.overlap_streams = bool(args.overlap)
 
     def barrier():
         torch.cuda.synchronize()
@@ -354,7 +357,7 @@ def main():
         'loss': round(float(loss), 6), 'global_norm': round(float(gnorm), 6), 'n_params': int(model.n_params),
     }
     try:
-        line['roofline'] = gate_gemm_roofline(args, torch, ops)
+        line['roofline'] = None if args.skip_roofline else gate_gemm_roofline(args, torch, ops)
     except Exception as ex:  # keep the headline number even if the side measurement fails
         line['roofline'] = {'error': repr(ex)}
     if world == 1 and not args.skip_cpu_baseline:

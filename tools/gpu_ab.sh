@@ -1,4 +1,4 @@
 set -u
-for v in "" "AVSR_B200_LIB=/root/repo/avsr_tf1_b200/lib/libavsr_b200_old.so" "" "AVSR_B200_LIB=/root/repo/avsr_tf1_b200/lib/libavsr_b200_old.so"; do
-  echo "--- $v"; env $v timeout -s KILL 200 python tools/ap_time.py 2>&1 | tail -2
-done
+for v in "" "--no-overlap"; do for e in "AVSR_X=1" "AVSR_LP_CLUSTER=8"; do
+  echo "--- $e $v"; env $e timeout -s KILL 300 python bench.py --steps 8 --warmup 3 --skip-cpu-baseline --skip-roofline $v 2>/dev/null | cut -c1-160
+done; done
