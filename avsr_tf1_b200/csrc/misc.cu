@@ -63,18 +63,27 @@ __global__ void colsum_kernel(const float* __restrict__ a, long long rows, int N
   }
 }
 
+// d0 > 0: x is stored [d0, d1, F] and y / xhat are written [d1, d0, F] (the batch-major -> frame-major change of
+// layout at the boundary, fused into the normalisation instead of a separate pass over the features)
 __global__ void bn_apply_train_kernel(const float* __restrict__ x, long long n, int F, const float* __restrict__ sums,
                                       float inv_count, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float eps, float momentum,
                                       float* __restrict__ y, float* __restrict__ xhat, float* __restrict__ invstd,
-                                      float* __restrict__ moving_mean, float* __restrict__ moving_var, int rnd) {
+                                      float* __restrict__ moving_mean, float* __restrict__ moving_var, int rnd, int d0,
+                                      int d1) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int f = (int)(i % F);
   float mean = sums[f] * inv_count;
   float var = fmaxf(sums[F + f] * inv_count - mean * mean, 0.0f);
   float is = rsqrtf(var + eps);
-  float xh = (x[i] - mean) * is;
+  long long src = i;
+  if (d0 > 0) {
+    const long long r = i / F;  // output row = j*d0 + k  (j in d1, k in d0)
+    const int k = (int)(r % d0), j = (int)(r / d0);
+    src = ((long long)k * d1 + j) * F + f;
+  }
+  float xh = (x[src] - mean) * is;
   xhat[i] = xh;
   y[i] = maybe_tf32(fmaf(xh, gamma[f], beta[f]), rnd);
   if (i < F) {  // first row: per-feature side outputs
@@ -407,7 +416,18 @@ int avsr_bn_apply_train(avsr_stream_t s, const float* x, long long rows, int F, 
   long long n = rows * F;
   AVSR_REQUIRE(rows >= 1 && count >= 1.0, "bn: empty batch");
   AVSR_LAUNCH(bn_apply_train_kernel, cdiv(n, 256), 256, 0, ST(s), x, n, F, sums, (float)(1.0 / count), gamma, beta,
-              eps, momentum, y, xhat, invstd, moving_mean, moving_var, tensor_cores_enabled());
+              eps, momentum, y, xhat, invstd, moving_mean, moving_var, tensor_cores_enabled(), 0, 0);
+  return 0;
+}
+
+int avsr_bn_apply_train_t(avsr_stream_t s, const float* x, int d0, int d1, int F, const float* sums, double count,
+                          const float* gamma, const float* beta, float eps, float momentum, float* y, float* xhat,
+                          float* invstd, float* moving_mean, float* moving_var) {
+  long long n = (long long)d0 * d1 * F;
+  AVSR_REQUIRE(d0 >= 1 && d1 >= 1 && count >= 1.0, "bn: empty batch");
+  AVSR_REQUIRE(x != y && x != xhat, "bn_apply_train_t cannot run in place");
+  AVSR_LAUNCH(bn_apply_train_kernel, cdiv(n, 256), 256, 0, ST(s), x, n, F, sums, (float)(1.0 / count), gamma, beta,
+              eps, momentum, y, xhat, invstd, moving_mean, moving_var, tensor_cores_enabled(), d0, d1);
   return 0;
 }
 

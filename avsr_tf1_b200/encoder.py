@@ -95,15 +95,20 @@ class Seq2SeqEncoder(object):
         return hp.video_encoder_dropout_probability if scope == 'video' else hp.audio_encoder_dropout_probability
 
     # ---- compute -------------------------------------------------------------
-    def forward(self, inputs, inputs_len):
-        """inputs [T,B,F] frame-major; returns EncoderData."""
+    def _normalised_inputs(self, inputs, batch_major):
+        """Input BN (or the plain operand rounding) -> frame-major [T,B,F] product operand."""
         train = self._mode == 'train'
+        if self._bn is not None:
+            return self._bn.forward(inputs, train, batch_major=batch_major)  # tf32-rounded in tensor-core mode
+        if batch_major:
+            inputs = ops.transpose01(inputs)
+        return ops.round_tf32(inputs) if ops.tensor_cores_enabled() else inputs
+
+    def forward(self, inputs, inputs_len, batch_major=False):
+        """inputs [T,B,F] frame-major (or [B,T,F] with batch_major=True); returns EncoderData."""
         ctx = self._ctx
         self._lens = inputs_len
-        if self._bn is not None:
-            x = self._bn.forward(inputs, train)  # already a product operand (tf32-rounded in tensor-core mode)
-        else:
-            x = ops.round_tf32(inputs) if ops.tensor_cores_enabled() else inputs
+        x = self._normalised_inputs(inputs, batch_major)
         cur, cur_op = None, x
         for op in self._fw:
             cur = op.forward(cur_op, inputs_len)
@@ -175,7 +180,7 @@ class Seq2SeqEncoder(object):
             ops.axpy(1.0, dxb, df)
             dx = df
         if self._bn is not None and dx is not None:
-            dx = self._bn.backward(dx)
+            dx = self._bn.backward(dx, need_dx=need_dx)
         return dx
 
 
@@ -212,15 +217,11 @@ class AttentiveEncoder(Seq2SeqEncoder):
         self._bw = None
         self.output_dim = self._top.out_dim
 
-    def forward_lower(self, inputs, inputs_len):
+    def forward_lower(self, inputs, inputs_len, batch_major=False):
         """Input BN + the plain layers under the attention layer (independent of the video stream, so the
         model can run it concurrently with the video encoder)."""
-        train = self._mode == 'train'
         self._lens = inputs_len
-        if self._bn is not None:
-            x = self._bn.forward(inputs, train)
-        else:
-            x = ops.round_tf32(inputs) if ops.tensor_cores_enabled() else inputs
+        x = self._normalised_inputs(inputs, batch_major)
         cur_op = x
         for op in self._fw:
             op.forward(cur_op, inputs_len)
@@ -254,7 +255,7 @@ class AttentiveEncoder(Seq2SeqEncoder):
             need = (i > 0) or need_dx or self._bn is not None
             d = self._fw[i].backward(d, None, need_dx=need)
         if self._bn is not None and d is not None:
-            d = self._bn.backward(d)
+            d = self._bn.backward(d, need_dx=need_dx)
         return d
 
     def backward(self, doutputs, dfinal_state=None, need_dx=False):

@@ -53,39 +53,52 @@ class BatchNormInput:
         self.mm = ctx.declare(pre + 'moving_mean', (F,), 'zeros', trainable=False)
         self.mv = ctx.declare(pre + 'moving_variance', (F,), 'ones', trainable=False)
 
-    def forward(self, x: torch.Tensor, train: bool) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, train: bool, batch_major: bool = False) -> torch.Tensor:
+        """x [T,B,F] frame-major, or [B,T,F] with batch_major=True (the reference's layout); the result is frame-major
+        either way - in train mode the change of layout is fused into the normalisation."""
         ctx = self.ctx
-        T, B, F = x.shape
-        x2 = x.view(T * B, F)
-        y = torch.empty_like(x)
+        if batch_major and not train:
+            x, batch_major = ops.transpose01(x), False
+        d0, d1, F = x.shape
+        T, B = (d1, d0) if batch_major else (d0, d1)
+        y = ops.empty(T, B, F)
         if not train:
-            ops.bn_apply_eval(x2, ctx.p(self.gamma), ctx.p(self.beta), ctx.p(self.mm), ctx.p(self.mv), BN_EPS, y)
+            ops.bn_apply_eval(x.view(T * B, F), ctx.p(self.gamma), ctx.p(self.beta), ctx.p(self.mm), ctx.p(self.mv),
+                              BN_EPS, y)
             return y
         sums = ops.zeros(2 * F)
-        ops.bn_stats(x2, sums)
+        ops.bn_stats(x.view(T * B, F), sums)  # column sums: the order of the rows does not matter
         count = float(T * B)
         if ctx.world_size > 1:  # exact large-batch statistics under data parallelism
             ctx.allreduce(sums)
             count *= ctx.world_size
-        self.xhat = torch.empty_like(x)
+        self.xhat = ops.empty(T, B, F)
         self.invstd = ops.empty(F)
         self.count = count
-        ops.bn_apply_train(x2, sums, count, ctx.p(self.gamma), ctx.p(self.beta), BN_EPS, BN_MOMENTUM, y,
-                           self.xhat, self.invstd, ctx.p(self.mm), ctx.p(self.mv))
+        if batch_major:
+            ops.bn_apply_train_t(x, sums, count, ctx.p(self.gamma), ctx.p(self.beta), BN_EPS, BN_MOMENTUM, y,
+                                 self.xhat, self.invstd, ctx.p(self.mm), ctx.p(self.mv))
+        else:
+            ops.bn_apply_train(x.view(T * B, F), sums, count, ctx.p(self.gamma), ctx.p(self.beta), BN_EPS, BN_MOMENTUM,
+                               y.view(T * B, F), self.xhat.view(T * B, F), self.invstd, ctx.p(self.mm), ctx.p(self.mv))
         return y
 
-    def backward(self, dy: torch.Tensor) -> torch.Tensor:
+    def backward(self, dy: torch.Tensor, need_dx: bool = True) -> Optional[torch.Tensor]:
+        """Accumulates dgamma / dbeta; the gradient wrt the raw features is only formed on request (nothing upstream
+        of the input normalisation is trained on this path)."""
         ctx = self.ctx
         T, B, F = dy.shape
         dy2, xh2 = dy.view(T * B, F), self.xhat.view(T * B, F)
         sums2 = ops.zeros(2 * F)
         ops.bn_bwd_stats(dy2, xh2, sums2)
         local = sums2
-        if ctx.world_size > 1:
+        if ctx.world_size > 1 and need_dx:
             local = sums2.clone()  # dgamma/dbeta stay local sums (the gradient all-reduce adds them up)
             ctx.allreduce(sums2)
-        dx = torch.empty_like(dy)
-        ops.bn_bwd_apply(dy2, xh2, sums2, self.count, ctx.p(self.gamma), self.invstd, dx, None, None)
+        dx = None
+        if need_dx:
+            dx = torch.empty_like(dy)
+            ops.bn_bwd_apply(dy2, xh2, sums2, self.count, ctx.p(self.gamma), self.invstd, dx, None, None)
         ops.axpy(1.0, local[F:], ctx.g(self.gamma))
         ops.axpy(1.0, local[:F], ctx.g(self.beta))
         return dx

@@ -87,6 +87,14 @@ def bn_apply_train(x2d, sums, count, gamma, beta, eps, momentum, y, xhat, invstd
                                           y.data_ptr(), xhat.data_ptr(), invstd.data_ptr(), _p(mm), _p(mv)))
 
 
+def bn_apply_train_t(x3d, sums, count, gamma, beta, eps, momentum, y, xhat, invstd, mm, mv):
+    """x3d [d0,d1,F] (batch-major) -> y, xhat [d1,d0,F] (frame-major): boundary transpose fused into the BN."""
+    d0, d1, F = x3d.shape
+    check(_lib.load().avsr_bn_apply_train_t(_stream(), x3d.data_ptr(), d0, d1, F, sums.data_ptr(), float(count),
+                                            gamma.data_ptr(), beta.data_ptr(), eps, momentum, y.data_ptr(),
+                                            xhat.data_ptr(), invstd.data_ptr(), _p(mm), _p(mv)))
+
+
 def bn_apply_eval(x2d, gamma, beta, mm, mv, eps, y):
     check(_lib.load().avsr_bn_apply_eval(_stream(), x2d.data_ptr(), x2d.shape[0], x2d.shape[1], gamma.data_ptr(),
                                          beta.data_ptr(), mm.data_ptr(), mv.data_ptr(), eps, y.data_ptr()))

@@ -279,12 +279,13 @@ class Seq2SeqModel(object):
         self._batch = None
 
     def _prep(self):
-        """Device-side batch preparation (capturable): batch-major -> frame-major, GO-prefixed ids."""
+        """Device-side batch preparation (capturable): GO-prefixed ids.  The features stay batch-major [B,T,F] (the
+        reference's layout): the encoders change to the frame-major device layout inside their input normalisation."""
         src, meta = self._in, self._meta
         b: Dict[str, object] = {}
         for key in ('video', 'audio'):
             if key in src:
-                b[key] = ops.transpose01(src[key])
+                b[key] = src[key]
                 b[key + '_len'] = src[key + '_len']
         if 'labels' in src:
             T = meta['T_dec']
@@ -317,18 +318,18 @@ class Seq2SeqModel(object):
         if self._video_encoder is not None:
             if overlap:
                 with torch.cuda.stream(self._fork()):
-                    enc['video'] = self._video_encoder.forward(b['video'], b['video_len'])
+                    enc['video'] = self._video_encoder.forward(b['video'], b['video_len'], batch_major=True)
             else:
-                enc['video'] = self._video_encoder.forward(b['video'], b['video_len'])
+                enc['video'] = self._video_encoder.forward(b['video'], b['video_len'], batch_major=True)
         if self._audio_encoder is not None:
             if isinstance(self._audio_encoder, AttentiveEncoder):
-                self._audio_encoder.forward_lower(b['audio'], b['audio_len'])
+                self._audio_encoder.forward_lower(b['audio'], b['audio_len'], batch_major=True)
                 if overlap:
                     self._join()
                 enc['audio'] = self._audio_encoder.forward_top(enc['video'].outputs, b['video_len'],
                                                                enc['video'].outputs_operand)
             else:
-                enc['audio'] = self._audio_encoder.forward(b['audio'], b['audio_len'])
+                enc['audio'] = self._audio_encoder.forward(b['audio'], b['audio_len'], batch_major=True)
                 if overlap:
                     self._join()
         return enc

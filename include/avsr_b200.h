@@ -60,6 +60,12 @@ int avsr_bn_stats(avsr_stream_t stream, const float* x, long long rows, int F, f
 int avsr_bn_apply_train(avsr_stream_t stream, const float* x, long long rows, int F, const float* sums,
                         double count, const float* gamma, const float* beta, float eps, float momentum,
                         float* y, float* xhat, float* invstd /*[F]*/, float* moving_mean, float* moving_var);
+/* same, for x stored [d0,d1,F] (batch-major, as the reference's tensors are: encoder.py:44-50 normalises
+ * [B,T,F]) with y / xhat written [d1,d0,F] (frame-major device layout): the boundary transpose of
+ * avsr_transpose01 fused into the normalisation */
+int avsr_bn_apply_train_t(avsr_stream_t stream, const float* x, int d0, int d1, int F, const float* sums,
+                          double count, const float* gamma, const float* beta, float eps, float momentum,
+                          float* y, float* xhat, float* invstd /*[F]*/, float* moving_mean, float* moving_var);
 /* y of both apply calls is tf32-rounded in tensor-core mode (it only feeds the layer-0 gate product) */
 int avsr_bn_apply_eval(avsr_stream_t stream, const float* x, long long rows, int F, const float* gamma,
                        const float* beta, const float* moving_mean, const float* moving_var, float eps, float* y);

@@ -147,6 +147,31 @@ def test_batchnorm_output_is_tf32_operand_in_tensor_core_mode():
         ops.set_tensor_cores(old)
 
 
+@pytest.mark.parametrize('B,T,F', [(3, 5, 7), (8, 75, 128), (5, 11, 3888)])
+def test_batchnorm_fused_boundary_transpose(B, T, F, exact_fp32):
+    """avsr_bn_apply_train_t: batch-major [B,T,F] in (the reference's layout, encoder.py:44-50), frame-major [T,B,F]
+    out - against the oracle on the same data and bit-identical to transpose + plain apply."""
+    ops = ops_mod()
+    rng = np.random.default_rng(B + T + F)
+    x = (rng.standard_normal((B, T, F)) * 2 + 0.5).astype(np.float32)
+    gamma = rng.uniform(0.5, 1.5, F).astype(np.float32)
+    beta = rng.standard_normal(F).astype(np.float32)
+    y_ref, _, _, _ = O.batchnorm_train_fwd(x.astype(np.float64), gamma.astype(np.float64), beta.astype(np.float64))
+    xd = dev(x)
+    sums = torch.zeros(2 * F, device='cuda')
+    ops.bn_stats(xd.view(B * T, F), sums)
+    y, xhat = torch.empty(T, B, F, device='cuda'), torch.empty(T, B, F, device='cuda')
+    invstd = torch.empty(F, device='cuda')
+    mm, mv = torch.zeros(F, device='cuda'), torch.ones(F, device='cuda')
+    ops.bn_apply_train_t(xd, sums, B * T, dev(gamma), dev(beta), 1e-3, 0.99, y, xhat, invstd, mm, mv)
+    close(y.transpose(0, 1), y_ref, 1e-5, 'bn y (fused transpose)')
+    xt = ops.transpose01(xd)
+    y2, xhat2, invstd2 = torch.empty_like(y), torch.empty_like(y), torch.empty(F, device='cuda')
+    ops.bn_apply_train(xt.view(T * B, F), sums, B * T, dev(gamma), dev(beta), 1e-3, 0.99, y2.view(T * B, F),
+                       xhat2.view(T * B, F), invstd2, None, None)
+    assert torch.equal(y, y2) and torch.equal(xhat, xhat2) and torch.equal(invstd, invstd2)
+
+
 @pytest.mark.parametrize('rows,F', [(6, 5), (5 * 300, 80), (64 * 75, 128), (33, 3888)])
 def test_batchnorm(rows, F, exact_fp32):
     ops = ops_mod()
