@@ -49,6 +49,8 @@ PROTOTYPES = {
     'avsr_last_error': (C.c_char_p, []),
     'avsr_version': (_I, []),
     'avsr_launch_count': (C.c_ulonglong, []),
+    'avsr_kernel_timing': (_I, [_I]),
+    'avsr_kernel_times': (_I, [_P, _P]),
     'avsr_set_tensor_cores': (_I, [_I]),
     'avsr_get_tensor_cores': (_I, []),
     'avsr_round_tf32': (_I, [_P, _P, _P, _L]),

@@ -1115,7 +1115,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
 }
 
 template <typename Kern, typename P>
-static int launch_cluster(cudaStream_t st, Kern kern, int B, size_t smem, const P& p) {
+static int launch_cluster(cudaStream_t st, Kern kern, int B, size_t smem, const P& p, int klass) {
   AVSR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cdiv(B, NB) * CL);
@@ -1129,7 +1129,9 @@ static int launch_cluster(cudaStream_t st, Kern kern, int B, size_t smem, const 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  const int slot = kernel_timer_begin(st, klass);
   AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  kernel_timer_end(st, slot);
   ++g_launch_count;
   return 0;
 }
@@ -1170,7 +1172,7 @@ int attn_persist4_launch_fwd(cudaStream_t st, int T, int B, int Tm, int scaled, 
   p.keys = reinterpret_cast<const __half*>(keys_h); p.values = reinterpret_cast<const __half*>(values_h);
   p.g = g; p.c0 = c0; p.S = S; p.SW = SW; p.At = At; p.craw = craw; p.out = out; p.hc = hc; p.align = align;
   p.cT = cT; p.hT = hT;
-  return ap4::launch_cluster(st, ap4::attn_lstm_persist4_fwd_kernel, B, ap4::FWD_SMEM, p);
+  return ap4::launch_cluster(st, ap4::attn_lstm_persist4_fwd_kernel, B, ap4::FWD_SMEM, p, AVSR_K_ATTN_FWD);
 }
 
 int attn_persist4_launch_bwd(cudaStream_t st, int T, int B, int Tm, int scaled, float grad_scale, const int* len,
@@ -1191,12 +1193,12 @@ int attn_persist4_launch_bwd(cudaStream_t st, int T, int B, int Tm, int scaled, 
                                     "reduce+send dq", "wait dq", "dz->smem+issue", "hbm st/ld", "wait MMA", "tmem ld+push"};
     AVSR_CHECK_CUDA(cudaMalloc(&p.dbg, 64 * 12 * sizeof(long long)));
     AVSR_CHECK_CUDA(cudaMemset(p.dbg, 0, 64 * 12 * sizeof(long long)));
-    AVSR_TRY(Tm <= ap4::SMALL_TM ? ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<true>, B, ap4::BWD_SMEM, p)
-                                 : ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<false>, B, ap4::BWD_SMEM, p));
+    AVSR_TRY(Tm <= ap4::SMALL_TM ? ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<true>, B, ap4::BWD_SMEM, p, AVSR_K_ATTN_BWD)
+                                 : ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<false>, B, ap4::BWD_SMEM, p, AVSR_K_ATTN_BWD));
     return ap4::print_dbg(st, p.dbg, "[ap4 bwd]", T, Tm, 12, names);
   }
-  return Tm <= ap4::SMALL_TM ? ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<true>, B, ap4::BWD_SMEM, p)
-                             : ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<false>, B, ap4::BWD_SMEM, p);
+  return Tm <= ap4::SMALL_TM ? ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<true>, B, ap4::BWD_SMEM, p, AVSR_K_ATTN_BWD)
+                             : ap4::launch_cluster(st, ap4::attn_lstm_persist4_bwd_kernel<false>, B, ap4::BWD_SMEM, p, AVSR_K_ATTN_BWD);
 }
 
 }  // namespace avsr

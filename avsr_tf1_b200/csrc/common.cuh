@@ -44,6 +44,15 @@ extern unsigned long long g_launch_count;  // kernels launched by this library
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- optional device timing of the persistent kernels (avsr_kernel_timing) ----
+// Kernel classes; when timing is enabled a launcher brackets its kernel with CUDA events on the launching stream
+// (never under stream capture) and the elapsed times are summed per class.
+enum { AVSR_K_ATTN_FWD = 0, AVSR_K_ATTN_BWD = 1, AVSR_K_LSTM_FWD = 2, AVSR_K_LSTM_BWD = 3, AVSR_K_GEMM = 4, AVSR_K_COUNT = 5 };
+bool kernel_timing_enabled();
+// returns an opaque slot (>= 0) after recording the start event, or -1 when timing is off
+int kernel_timer_begin(cudaStream_t st, int klass);
+void kernel_timer_end(cudaStream_t st, int slot);
+
 // ---- device helpers ---------------------------------------------------------
 __device__ __forceinline__ float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 // tanh via exp: accurate to ~1e-7 relative (tanh.approx is only ~5e-4)

@@ -409,7 +409,9 @@ int gemm_tc(cudaStream_t st, int transA, int transB, int M, int N, int K, const 
     AVSR_CHECK_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
   }
   const int grid = min(p.num_work, sm_count);
+  const int slot = kernel_timer_begin(st, AVSR_K_GEMM);
   gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmC, p);
+  kernel_timer_end(st, slot);
   ++g_launch_count;
   AVSR_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
 }
 
 template <typename Kern, typename P>
-static int launch_cluster(cudaStream_t st, Kern kern, int B, size_t smem, const P& p) {
+static int launch_cluster(cudaStream_t st, Kern kern, int B, size_t smem, const P& p, int klass) {
   AVSR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cdiv(B, NB) * CL);
@@ -602,7 +602,9 @@ static int launch_cluster(cudaStream_t st, Kern kern, int B, size_t smem, const 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  const int slot = kernel_timer_begin(st, klass);
   AVSR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  kernel_timer_end(st, slot);
   ++g_launch_count;
   return 0;
 }
@@ -621,7 +623,7 @@ int lstm_persist4_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   p.T = r->T; p.B = r->B;
   p.len = r->len; p.gates = r->gates; p.Wrec = r->Wrec; p.c0 = r->c0; p.S = r->S; p.craw = r->craw; p.out = r->out;
   p.cT = r->cT; p.hT = r->hT;
-  return lp4::launch_cluster(st, lp4::lstm_persist4_fwd_kernel, r->B, lp4::FWD_SMEM, p);
+  return lp4::launch_cluster(st, lp4::lstm_persist4_fwd_kernel, r->B, lp4::FWD_SMEM, p, AVSR_K_LSTM_FWD);
 }
 
 int lstm_persist4_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
@@ -632,7 +634,7 @@ int lstm_persist4_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   p.inv_grad_scale = 1.0f / p.grad_scale;
   p.len = r->len; p.gates = r->gates; p.Wrec = r->Wrec; p.c0 = r->c0; p.craw = r->craw; p.dout = r->dout;
   p.dcT = r->dcT; p.dhT = r->dhT; p.dZ = r->dZ; p.dc0 = r->dc0; p.dh0 = r->dh0;
-  return lp4::launch_cluster(st, lp4::lstm_persist4_bwd_kernel, r->B, lp4::BWD_SMEM, p);
+  return lp4::launch_cluster(st, lp4::lstm_persist4_bwd_kernel, r->B, lp4::BWD_SMEM, p, AVSR_K_LSTM_BWD);
 }
 
 }  // namespace avsr

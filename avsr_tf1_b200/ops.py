@@ -27,6 +27,22 @@ def _chk_f32(*ts):
             raise _lib.AvsrError('expected a CUDA float32 tensor, got %s %s' % (t.device, t.dtype))
 
 
+KERNEL_CLASSES = ('attn_lstm_fwd', 'attn_lstm_bwd', 'lstm_fwd', 'lstm_bwd', 'gemm')
+
+
+def kernel_timing(enable: bool) -> bool:
+    """Switch the in-library CUDA-event timing of the hot kernels on/off (resets the record)."""
+    return bool(_lib.load().avsr_kernel_timing(int(bool(enable))))
+
+
+def kernel_times():
+    """{class: (summed ms, launches)} since kernel_timing(True); synchronises on the recorded events."""
+    ms = (C.c_float * 5)()
+    n = (C.c_int * 5)()
+    check(_lib.load().avsr_kernel_times(ms, n))
+    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(KERNEL_CLASSES)}
+
+
 def launch_count() -> int:
     return int(_lib.load().avsr_launch_count())
 

@@ -31,6 +31,13 @@ const char* avsr_last_error(void);
 int avsr_version(void);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 unsigned long long avsr_launch_count(void);
+/* Device timing of the hot kernels (bench.py roofline): while enabled, every launch of a persistent
+ * attention-LSTM / LSTM kernel and of the tcgen05 GEMM outside stream capture is bracketed by CUDA events on its
+ * launching stream.  avsr_kernel_timing(enable) resets the record and returns the previous setting;
+ * avsr_kernel_times fills the summed milliseconds and launch counts of the 5 classes
+ * {0 attention-LSTM fwd, 1 attention-LSTM bwd, 2 LSTM fwd, 3 LSTM bwd, 4 GEMM} (synchronises on the events). */
+int avsr_kernel_timing(int enable);
+int avsr_kernel_times(float* ms_out5, int* launches_out5);
 /* 1 if the tcgen05 tensor-core GEMM path is enabled (default), 0 = exact fp32 CUDA cores */
 int avsr_set_tensor_cores(int enable);
 int avsr_get_tensor_cores(void);
