@@ -59,6 +59,7 @@ PROTOTYPES = {
     'avsr_bn_stats': (_I, [_P, _P, _L, _I, _P]),
     'avsr_bn_apply_train': (_I, [_P, _P, _L, _I, _P, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
     'avsr_bn_apply_train_t': (_I, [_P, _P, _I, _I, _I, _P, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
+    'avsr_bn_input_grads': (_I, [_P, _P, _I, _P, _I, _P, _P, _P, _I, _I, _P, _P]),
     'avsr_bn_apply_eval': (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _F, _P]),
     'avsr_bn_bwd_stats': (_I, [_P, _P, _P, _L, _I, _P]),
     'avsr_bn_bwd_apply': (_I, [_P, _P, _P, _L, _I, _P, _D, _P, _P, _P, _P, _P]),

@@ -373,11 +373,14 @@ int gemm_tc(cudaStream_t st, int transA, int transB, int M, int N, int K, const 
   p.M = M; p.N = N; p.K = K;
   p.block_n = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
   p.tiles_m = cdiv(M, BLOCK_M);
-  // few output tiles (per-step recurrent products, weight gradients): narrower N tiles spread the
-  // work over more SMs; these launches are latency-bound, not tensor-pipe bound
-  while (p.block_n > 64 && p.tiles_m * cdiv(N, p.block_n) < sm_count / 2) p.block_n >>= 1;
-  p.tiles_n = cdiv(N, p.block_n);
   p.k_tiles = cdiv(K, BLOCK_K);
+  // few output tiles and a shallow K (per-step recurrent products): narrower N tiles spread the work over more
+  // SMs; these launches are latency-bound, not tensor-pipe bound.  With a DEEP K (weight gradients: K = T*B) split-K
+  // fills the SMs instead and the tiles stay wide: a 128 x 64 tile re-reads every A element 16 times and the launch is
+  // bound by the 1.8 GB it pulls through L2, a 128 x 256 tile halves that.
+  const bool deep = p.k_tiles >= 128 && !round_out;
+  while (!deep && p.block_n > 64 && p.tiles_m * cdiv(N, p.block_n) < sm_count / 2) p.block_n >>= 1;
+  p.tiles_n = cdiv(N, p.block_n);
   const int tiles = p.tiles_m * p.tiles_n;
   int splitk = 1;
   if (tiles < sm_count && p.k_tiles >= 16 && !round_out) {

@@ -84,12 +84,54 @@ __global__ void bn_apply_train_kernel(const float* __restrict__ x, long long n, 
     src = ((long long)k * d1 + j) * F + f;
   }
   float xh = (x[src] - mean) * is;
-  xhat[i] = xh;
+  if (xhat) xhat[i] = xh;  // only kept when the gradient wrt the raw features will be asked for
   y[i] = maybe_tf32(fmaf(xh, gamma[f], beta[f]), rnd);
   if (i < F) {  // first row: per-feature side outputs
     invstd[f] = is;
     if (moving_mean) moving_mean[f] = moving_mean[f] * momentum + mean * (1.0f - momentum);
     if (moving_var) moving_var[f] = moving_var[f] * momentum + var * (1.0f - momentum);
+  }
+}
+
+// Gradients of the input normalisation's gamma / beta WITHOUT the gradient wrt its output: with y = gamma xhat + beta
+// feeding only the layer-0 gate product z = y Wx, and dWx = y^T dZ, cs = colsum(dZ) already computed,
+//   dbeta_f  = sum_r dy[r,f]           = sum_n Wx[f,n] cs[n]
+//   dgamma_f = sum_r dy[r,f] xhat[r,f] = sum_n Wx[f,n] (xhat^T dZ)[f,n] = sum_n Wx[f,n] (dWx[f,n] - beta_f cs[n]) / gamma_f
+// so neither dy = dZ Wx^T (a [T*B, F] product) nor xhat is needed.  One block per feature f; accumulates.
+__global__ void bn_input_grads_kernel(const float* __restrict__ Wx, int ldw, const float* __restrict__ dWx, int ldg,
+                                      const float* __restrict__ cs, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, int N, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta) {
+  const int f = blockIdx.x;
+  const float* w = Wx + (size_t)f * ldw;
+  const float* g = dWx + (size_t)f * ldg;
+  const float bf = beta[f];
+  float sb = 0.0f, sg = 0.0f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float wn = w[n], c = cs[n];
+    sb = fmaf(wn, c, sb);
+    sg = fmaf(wn, g[n] - bf * c, sg);
+  }
+  __shared__ float red[2][32];
+  sb = warp_sum(sb);
+  sg = warp_sum(sg);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[0][warp] = sb;
+    red[1][warp] = sg;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    sb = lane < nw ? red[0][lane] : 0.0f;
+    sg = lane < nw ? red[1][lane] : 0.0f;
+    sb = warp_sum(sb);
+    sg = warp_sum(sg);
+    if (lane == 0) {
+      dbeta[f] += sb;
+      const float gf = gamma[f];
+      if (gf != 0.0f) dgamma[f] += sg / gf;  // gamma_f = 0 exactly: xhat^T dZ cannot be recovered from dWx (contributes 0)
+    }
   }
 }
 
@@ -437,6 +479,13 @@ int avsr_bn_apply_eval(avsr_stream_t s, const float* x, long long rows, int F, c
   if (n <= 0) return 0;
   AVSR_LAUNCH(bn_apply_eval_kernel, cdiv(n, 256), 256, 0, ST(s), x, n, F, gamma, beta, moving_mean, moving_var, eps,
               y, tensor_cores_enabled());
+  return 0;
+}
+
+int avsr_bn_input_grads(avsr_stream_t s, const float* Wx, int ldw, const float* dWx, int ldg, const float* colsum_dZ,
+                         const float* gamma, const float* beta, int F, int N, float* dgamma, float* dbeta) {
+  if (F <= 0 || N <= 0) return 0;
+  AVSR_LAUNCH(bn_input_grads_kernel, F, 128, 0, ST(s), Wx, ldw, dWx, ldg, colsum_dZ, gamma, beta, N, dgamma, dbeta);
   return 0;
 }
 

@@ -50,6 +50,7 @@ class Seq2SeqEncoder(object):
         if hparams.input_dense_layers[0] > 0:
             raise NotImplementedError('input_dense_layers is off in every reference config (avsr.py:38)')
         self._bn = BatchNormInput(ctx, scope, self._F) if hparams.batch_normalisation is True else None
+        self.input_gradient = False  # True: keep what the gradient wrt the raw features needs (backward(need_dx=True))
         self._init_encoder()
 
     def _init_encoder(self):
@@ -99,7 +100,8 @@ class Seq2SeqEncoder(object):
         """Input BN (or the plain operand rounding) -> frame-major [T,B,F] product operand."""
         train = self._mode == 'train'
         if self._bn is not None:
-            return self._bn.forward(inputs, train, batch_major=batch_major)  # tf32-rounded in tensor-core mode
+            # tf32-rounded in tensor-core mode; xhat is only stored if the gradient wrt the raw features is wanted
+            return self._bn.forward(inputs, train, batch_major=batch_major, keep_xhat=self.input_gradient)
         if batch_major:
             inputs = ops.transpose01(inputs)
         return ops.round_tf32(inputs) if ops.tensor_cores_enabled() else inputs
@@ -152,7 +154,7 @@ class Seq2SeqEncoder(object):
             d = doutputs if doutputs is not None else ops.zeros(*self._outputs.shape)
             n = len(self._fw)
             for i in range(n - 1, -1, -1):
-                need = (i > 0) or need_dx or self._bn is not None
+                need = (i > 0) or need_dx
                 d = self._fw[i].backward(d, dfinal_state if i == n - 1 else None, need_dx=need)
             dx = d
         else:
@@ -174,14 +176,29 @@ class Seq2SeqEncoder(object):
             db = ops.reverse_sequence(doutputs[:, :, H:].contiguous(), self._lens)
             n = len(self._fw)
             for i in range(n - 1, -1, -1):
-                df = self._fw[i].backward(df, dsf if i == n - 1 else None, need_dx=True)
-                db = self._bw[i].backward(db, dsb if i == n - 1 else None, need_dx=True)
-            dxb = ops.reverse_sequence(db, self._lens)
-            ops.axpy(1.0, dxb, df)
-            dx = df
-        if self._bn is not None and dx is not None:
-            dx = self._bn.backward(dx, need_dx=need_dx)
-        return dx
+                need = (i > 0) or need_dx
+                df = self._fw[i].backward(df, dsf if i == n - 1 else None, need_dx=need)
+                db = self._bw[i].backward(db, dsb if i == n - 1 else None, need_dx=need)
+            dx = None
+            if need_dx:
+                dxb = ops.reverse_sequence(db, self._lens)
+                ops.axpy(1.0, dxb, df)
+                dx = df
+        return self._input_bn_backward(dx, need_dx)
+
+    def _input_bn_backward(self, dx, need_dx):
+        """Gradients of the input normalisation.  Its output only feeds the layer-0 gate product(s), so dgamma / dbeta
+        follow from the layer-0 weight gradients (BatchNormInput.backward_from_layer0) and the [T*B,F] gradient wrt the
+        normalised features is only formed when the caller asks for the gradient wrt the raw features."""
+        if self._bn is None:
+            return dx
+        if need_dx:
+            if not self.input_gradient:
+                raise Exception('encoder: set input_gradient = True before forward to get the gradient wrt the features')
+            return self._bn.backward(dx, need_dx=True)
+        first = [self._fw[0]] if self._fw else [self._top]  # (an AV-Align encoder of one layer: the attention cell)
+        self._bn.backward_from_layer0(first + ([self._bw[0]] if self._bw is not None else []))
+        return None
 
 
 class AttentiveEncoder(Seq2SeqEncoder):
@@ -252,11 +269,9 @@ class AttentiveEncoder(Seq2SeqEncoder):
 
     def backward_lower(self, d, need_dx=False):
         for i in range(len(self._fw) - 1, -1, -1):
-            need = (i > 0) or need_dx or self._bn is not None
+            need = (i > 0) or need_dx
             d = self._fw[i].backward(d, None, need_dx=need)
-        if self._bn is not None and d is not None:
-            d = self._bn.backward(d, need_dx=need_dx)
-        return d
+        return self._input_bn_backward(d if need_dx else None, need_dx)
 
     def backward(self, doutputs, dfinal_state=None, need_dx=False):
         """Returns (dx, dmemory) - dmemory is the gradient wrt the video encoder outputs."""

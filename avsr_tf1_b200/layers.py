@@ -53,9 +53,10 @@ class BatchNormInput:
         self.mm = ctx.declare(pre + 'moving_mean', (F,), 'zeros', trainable=False)
         self.mv = ctx.declare(pre + 'moving_variance', (F,), 'ones', trainable=False)
 
-    def forward(self, x: torch.Tensor, train: bool, batch_major: bool = False) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, train: bool, batch_major: bool = False, keep_xhat: bool = True) -> torch.Tensor:
         """x [T,B,F] frame-major, or [B,T,F] with batch_major=True (the reference's layout); the result is frame-major
-        either way - in train mode the change of layout is fused into the normalisation."""
+        either way - in train mode the change of layout is fused into the normalisation.  keep_xhat=False: the
+        normalised features are not stored; dgamma / dbeta then come from `backward_from_layer0`."""
         ctx = self.ctx
         if batch_major and not train:
             x, batch_major = ops.transpose01(x), False
@@ -72,7 +73,7 @@ class BatchNormInput:
         if ctx.world_size > 1:  # exact large-batch statistics under data parallelism
             ctx.allreduce(sums)
             count *= ctx.world_size
-        self.xhat = ops.empty(T, B, F)
+        self.xhat = ops.empty(T, B, F) if keep_xhat else None
         self.invstd = ops.empty(F)
         self.count = count
         if batch_major:
@@ -80,14 +81,27 @@ class BatchNormInput:
                                  self.xhat, self.invstd, ctx.p(self.mm), ctx.p(self.mv))
         else:
             ops.bn_apply_train(x.view(T * B, F), sums, count, ctx.p(self.gamma), ctx.p(self.beta), BN_EPS, BN_MOMENTUM,
-                               y.view(T * B, F), self.xhat.view(T * B, F), self.invstd, ctx.p(self.mm), ctx.p(self.mv))
+                               y.view(T * B, F), None if self.xhat is None else self.xhat.view(T * B, F), self.invstd,
+                               ctx.p(self.mm), ctx.p(self.mv))
         return y
+
+    def backward_from_layer0(self, layer0_ops) -> None:
+        """dgamma / dbeta from what the weight-gradient pass of the layer(s) fed by this normalisation has just formed
+        (their dWx = y^T dZ and bias gradient colsum(dZ) sit in the gradient buffer, still free of the L2 term and of
+        other ranks' sums): no gradient wrt y, no stored xhat.  See avsr_bn_input_grads."""
+        ctx = self.ctx
+        for op in layer0_ops:
+            I = op.I if hasattr(op, 'I') else op.Dx  # rows of the cell kernel that multiply the layer input
+            ops.bn_input_grads(ctx.w(op.kernel)[:I], ctx.g(op.kernel)[:I], ctx.g(op.bias), ctx.p(self.gamma),
+                               ctx.p(self.beta), ctx.g(self.gamma), ctx.g(self.beta))
 
     def backward(self, dy: torch.Tensor, need_dx: bool = True) -> Optional[torch.Tensor]:
         """Accumulates dgamma / dbeta; the gradient wrt the raw features is only formed on request (nothing upstream
         of the input normalisation is trained on this path)."""
         ctx = self.ctx
         T, B, F = dy.shape
+        if self.xhat is None:
+            raise Exception('input BN: forward ran with keep_xhat=False, use backward_from_layer0')
         dy2, xh2 = dy.view(T * B, F), self.xhat.view(T * B, F)
         sums2 = ops.zeros(2 * F)
         ops.bn_bwd_stats(dy2, xh2, sums2)

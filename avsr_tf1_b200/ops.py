@@ -100,7 +100,7 @@ def bn_stats(x2d, sums):
 def bn_apply_train(x2d, sums, count, gamma, beta, eps, momentum, y, xhat, invstd, mm, mv):
     check(_lib.load().avsr_bn_apply_train(_stream(), x2d.data_ptr(), x2d.shape[0], x2d.shape[1], sums.data_ptr(),
                                           float(count), gamma.data_ptr(), beta.data_ptr(), eps, momentum,
-                                          y.data_ptr(), xhat.data_ptr(), invstd.data_ptr(), _p(mm), _p(mv)))
+                                          y.data_ptr(), _p(xhat), invstd.data_ptr(), _p(mm), _p(mv)))
 
 
 def bn_apply_train_t(x3d, sums, count, gamma, beta, eps, momentum, y, xhat, invstd, mm, mv):
@@ -108,7 +108,15 @@ def bn_apply_train_t(x3d, sums, count, gamma, beta, eps, momentum, y, xhat, invs
     d0, d1, F = x3d.shape
     check(_lib.load().avsr_bn_apply_train_t(_stream(), x3d.data_ptr(), d0, d1, F, sums.data_ptr(), float(count),
                                             gamma.data_ptr(), beta.data_ptr(), eps, momentum, y.data_ptr(),
-                                            xhat.data_ptr(), invstd.data_ptr(), _p(mm), _p(mv)))
+                                            _p(xhat), invstd.data_ptr(), _p(mm), _p(mv)))
+
+
+def bn_input_grads(Wx, dWx, colsum_dZ, gamma, beta, dgamma, dbeta):
+    """dgamma / dbeta of the input BN from the layer-0 weight gradient (see avsr_bn_input_grads); accumulates."""
+    F, N = Wx.shape
+    check(_lib.load().avsr_bn_input_grads(_stream(), Wx.data_ptr(), Wx.stride(0), dWx.data_ptr(), dWx.stride(0),
+                                          colsum_dZ.data_ptr(), gamma.data_ptr(), beta.data_ptr(), F, N,
+                                          dgamma.data_ptr(), dbeta.data_ptr()))
 
 
 def bn_apply_eval(x2d, gamma, beta, mm, mv, eps, y):

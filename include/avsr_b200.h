@@ -76,6 +76,13 @@ int avsr_bn_apply_train_t(avsr_stream_t stream, const float* x, int d0, int d1, 
 /* y of both apply calls is tf32-rounded in tensor-core mode (it only feeds the layer-0 gate product) */
 int avsr_bn_apply_eval(avsr_stream_t stream, const float* x, long long rows, int F, const float* gamma,
                        const float* beta, const float* moving_mean, const float* moving_var, float eps, float* y);
+/* dgamma / dbeta of the input normalisation from what the layer-0 weight-gradient pass already formed (the
+ * normalised features only feed z = y Wx): dbeta = Wx colsum(dZ), dgamma_f = sum_n Wx[f,n] (dWx[f,n] - beta_f
+ * colsum(dZ)[n]) / gamma_f with dWx = y^T dZ.  Accumulates into dgamma / dbeta; a feature whose gamma is exactly 0
+ * contributes 0 to dgamma.  Saves the [T*B,F] product dZ Wx^T and two passes over it. */
+int avsr_bn_input_grads(avsr_stream_t stream, const float* Wx, int ldw, const float* dWx, int ldg,
+                        const float* colsum_dZ /*[N]*/, const float* gamma, const float* beta, int F, int N,
+                        float* dgamma, float* dbeta);
 /* backward: sums2 = [sum dy, sum dy*xhat] (all-reducible), then dx */
 int avsr_bn_bwd_stats(avsr_stream_t stream, const float* dy, const float* xhat, long long rows, int F,
                       float* sums2 /*[2F]*/);

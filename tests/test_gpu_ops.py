@@ -54,6 +54,7 @@ def opnd(t, tc):
 GEMM_SHAPES = [
     (5, 7, 3), (1, 1, 1), (33, 31, 80), (64, 1024, 256), (128, 128, 64), (300, 31, 256), (257, 1024, 3888),
     (2048, 1024, 80), (1024, 512, 4096), (96, 640, 1000), (17, 256, 512),
+    (256, 1024, 19200),  # weight-gradient shape: deep K, wide tiles + split-K
 ]
 
 
