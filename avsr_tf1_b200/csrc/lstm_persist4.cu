@@ -146,7 +146,12 @@ struct FwdParams {
   float* out;         // [T,B,H]
   float* cT;          // [B,H] or null
   float* hT;          // [B,H] or null
+  long long* dbg;     // AVSR_LP_DEBUG: clock samples [64 steps][8] of CTA 0 (thread 0: slots 0-5, thread 128+32: 6-7)
 };
+#define LP4_STAMP(slot)                                                                        \
+  do {                                                                                         \
+    if (p.dbg && blockIdx.x == 0 && tid == 0 && t < 64) p.dbg[t * 8 + (slot)] = clock64();  \
+  } while (0)
 
 constexpr size_t FWD_SMEM = (size_t)2 * OP_BYTES + 4 * NB * UPC * 4 + 64 + 1024;
 
@@ -166,11 +171,14 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_fwd_kernel(const Fwd
   const int T = p.T, B = p.B;
 
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(sBar + 8 * i, 1);
+    mbar_init(sBar, 4);       // mma_done[tile 0]: one commit per issuing warp
+    mbar_init(sBar + 8, 4);   // mma_done[tile 1]
+    mbar_init(sBar + 16, 1);  // h_full[buffer 0]
+    mbar_init(sBar + 24, 1);  // h_full[buffer 1]
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // tensor memory (all 512 columns): [0, 16) / [16, 32) accumulators of the two gate tiles; [256, 512) the two
-  // 128 x 256 tiles of Wh^T (tile m: gate rows of the CTA's units 32*m .. 32*m+31), 128 columns each
+  // tensor memory (all 512 columns): [0, 128) accumulators: tile m, K quarter j at column 16 (4 m + j); [256, 512)
+  // the two 128 x 256 tiles of Wh^T (tile m: gate rows of the CTA's units 32*m .. 32*m+31), 128 columns each
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -216,9 +224,22 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_fwd_kernel(const Fwd
   const int g = warp & 3, m = warp >> 2;
   const int unit_g = UPC * rank + 32 * m + lane;
   const uint32_t mbar_m = sBar + 8 * m;
-  // product-issue role: lane 0 of warp 4*m issues the products of tile m (independent accumulators)
-  const bool issuer = (warp & 3) == 0;
+  // product-issue role.  Issuing a tcgen05.mma costs ~80 clocks of one thread (descriptor -> uniform registers), far
+  // more than the 128 x 16 x 16 product takes, and the 16 K steps of a tile sit on the critical path of the step.  So
+  // EVERY warp issues: lane 0 of warp (m, j) issues the K quarter j (= K block j, four steps) of tile m into its own
+  // accumulator columns, and the gate math adds the four partial accumulators of its tile.
+  const int jq = warp & 3;
+  const uint32_t acc_col = tmem_base + (4 * m + jq) * NP;
   const uint64_t dOp[2] = {make_desc_k128(sOp), make_desc_k128(sOp + OP_BYTES)};
+  auto issue_quarter = [&](uint32_t nbuf) {
+    if (lane == 0) {
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4)
+        umma_ts(acc_col, tW + 128 * m + (jq * 4 + k4) * 8, desc_at(dOp[nbuf], jq * (NP * 128) + k4 * 32), IDESC, k4 ? 1u : 0u);
+      umma_commit(mbar_m);
+    }
+    __syncwarp();
+  };
   // combine role (threads 0..127): utterance bq, units 4*uq .. 4*uq+3 of the CTA
   const bool comb = tid < 4 * 32;
   const int uq = tid & 15, bq = (tid >> 4) & 7;
@@ -246,29 +267,34 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_fwd_kernel(const Fwd
     for (int b = 0; b < NB; ++b) gx[b] = (0 < len_a[b]) ? grow0[(size_t)b * 4 * H] : 0.0f;
   }
   // product of step 0: h_0 is in buffer 0
-  if (issuer && T > 0) {
-    if (lane == 0) {
+  if (T > 0) issue_quarter(0);
+  // x-projection of step 1, two steps ahead of its use: the stream of gate rows comes from HBM (~1000+ clocks), more
+  // than what is left of a step after the prefetch is issued
+  float gx1[NB];
+  {
+    const float* grow1 = p.gates + ((size_t)B + b0) * 4 * H + g * H + unit_g;
 #pragma unroll
-      for (int ks = 0; ks < 16; ++ks)
-        umma_ts(tmem_base + m * NP, tW + 128 * m + ks * 8, desc_at(dOp[0], (ks >> 2) * (NP * 128) + (ks & 3) * 32), IDESC,
-                ks ? 1u : 0u);
-      umma_commit(mbar_m);
-    }
-    __syncwarp();
+    for (int b = 0; b < NB; ++b) gx1[b] = (1 < T && 1 < len_a[b]) ? grow1[(size_t)b * 4 * H] : 0.0f;
   }
 
   for (int t = 0; t < T; ++t) {
     float* grow = p.gates + ((size_t)t * B + b0) * 4 * H + g * H + unit_g;
     uint32_t r[8];
+    LP4_STAMP(0);
     mbar_wait(mbar_m, t & 1);  // recurrent product of this step (tile m)
+    LP4_STAMP(1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + m * NP, r);
+    uint32_t r1[8], r2[8], r3[8];
+    tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 0) * NP, r);
+    tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 1) * NP, r1);
+    tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 2) * NP, r2);
+    tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 3) * NP, r3);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     float av[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {  // i, f, o: sigmoid (forget bias 1); j: tanh
-      const float z = __uint_as_float(r[b]) + gx[b];
+      const float z = ((__uint_as_float(r[b]) + __uint_as_float(r1[b])) + (__uint_as_float(r2[b]) + __uint_as_float(r3[b]))) + gx[b];
       float a;
       if (g == 1) a = tanhf_acc(z);
       else a = sigmoidf_acc(g == 2 ? z + 1.0f : z);
@@ -276,6 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_fwd_kernel(const Fwd
       act[(g * NB + b) * UPC + 32 * m + lane] = a;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    LP4_STAMP(2);
     const uint32_t nb = (t + 1) & 1;
     const uint32_t hbar_n = sBar + 16 + 8 * nb;
     float hv[4], ov[4], cr[4];
@@ -315,23 +342,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_fwd_kernel(const Fwd
         for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) st_async_v2(mapa(dbuf, dst), mapa(hbar_n, dst), u01, u23);
       }
     }
-    if (issuer && t + 1 < T) {
-      // product of step t+1 for tile m, as soon as every CTA's h_t slice has landed.  Every warp has read the
-      // accumulators of step t before its activations reached the barrier above.
-      if (tid == 0) mbar_expect_tx(hbar_n, NB * H * 2);  // (warp 4 only waits: the barrier expects one arrival)
-      mbar_wait(hbar_n, (t >> 1) & 1);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-#pragma unroll
-        for (int ks = 0; ks < 16; ++ks)
-          umma_ts(tmem_base + m * NP, tW + 128 * m + ks * 8, desc_at(dOp[nb], (ks >> 2) * (NP * 128) + (ks & 3) * 32), IDESC,
-                  ks ? 1u : 0u);
-        umma_commit(mbar_m);
-      }
-      __syncwarp();
-    }
-    // HBM side of this step + x-projection of the next, off the recurrent critical path
+    LP4_STAMP(3);
+    // HBM side of this step and the x-projection of step t+2, issued before the wait for the exchange
 #pragma unroll
     for (int b = 0; b < NB; ++b)
       if (t < len_a[b]) grow[(size_t)b * 4 * H] = av[b];  // activations, kept for the backward pass
@@ -341,11 +353,25 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_fwd_kernel(const Fwd
       *reinterpret_cast<float4*>(p.out + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
       *reinterpret_cast<float4*>(p.S + o + (size_t)B * H) = make_float4(hv[0], hv[1], hv[2], hv[3]);
     }
-    if (t + 1 < T) {
-      const float* gnext = grow + (size_t)B * 4 * H;
 #pragma unroll
-      for (int b = 0; b < NB; ++b) gx[b] = (t + 1 < len_a[b]) ? gnext[(size_t)b * 4 * H] : 0.0f;
+    for (int b = 0; b < NB; ++b) gx[b] = gx1[b];
+    if (t + 2 < T) {
+      const float* gnext = grow + (size_t)2 * B * 4 * H;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) gx1[b] = (t + 2 < len_a[b]) ? gnext[(size_t)b * 4 * H] : 0.0f;
     }
+    LP4_STAMP(4);
+    if (t + 1 < T) {
+      // product of step t+1, as soon as every CTA's h_t slice has landed.  Every warp has read the accumulators of
+      // step t before its activations reached the barrier above.
+      if (tid == 0) mbar_expect_tx(hbar_n, NB * H * 2);
+      mbar_wait(hbar_n, (t >> 1) & 1);
+      LP4_STAMP(5);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      issue_quarter(nb);
+    }
+    LP4_STAMP(6);
   }
   if (comb && b0 + bq < B) {  // final states
     const size_t o = (size_t)(b0 + bq) * H + UPC * rank + 4 * uq;
@@ -400,14 +426,14 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
   const int T = p.T, B = p.B;
 
   if (tid == 0) {
-    mbar_init(sBar, 2);  // one commit per 128-row tile (two issuing threads)
+    mbar_init(sBar, 8);  // one commit per issuing warp
     mbar_init(sBar + 8, THREADS);
     mbar_init(sBar + 16, 1);
     mbar_init(sBar + 24, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // tensor memory (all 512 columns): [0, 32) accumulators of the two 128-row tiles of dh; [256, 512) the two tiles of
-  // A[n][k = g*64 + u] = Wrec[n][g*H + 64*rank + u] (tile = n >> 7), 128 columns each
+  // tensor memory (all 512 columns): [0, 128) accumulators: 128-row tile mt of dh, K quarter j (= gate j) at column
+  // 16 (4 mt + j); [256, 512) the two tiles of A[n][k = g*64 + u] = Wrec[n][g*H + 64*rank + u] (tile = n >> 7)
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -455,27 +481,36 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
     dc[j] = (b < B && p.dcT) ? p.dcT[(size_t)b * H + unit] : 0.0f;
     dh_carry[j] = (b < B && p.dhT) ? p.dhT[(size_t)b * H + unit] : 0.0f;
   }
-  float gi[PB], gj[PB], gf[PB], go[PB], crw[PB], cpv[PB], dov[PB];
+  // saved forward values of a step (activations, cell values, incoming gradient), loaded TWO iterations ahead of their
+  // use: they stream from HBM and one iteration is shorter than that latency
+  struct StepVals {
+    float gi[PB], gj[PB], gf[PB], go[PB], crw[PB], cpv[PB], dov[PB];
+  };
+  StepVals cur, nxt;
 #pragma unroll
-  for (int j = 0; j < PB; ++j) gi[j] = gj[j] = gf[j] = go[j] = crw[j] = cpv[j] = dov[j] = 0.0f;
-  auto load_step = [&](int t) {
+  for (int j = 0; j < PB; ++j) {
+    cur.gi[j] = cur.gj[j] = cur.gf[j] = cur.go[j] = cur.crw[j] = cur.cpv[j] = cur.dov[j] = 0.0f;
+    nxt = cur;
+  }
+  auto load_step = [&](StepVals& v, int t) {
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
       const int b = b0 + (warp >> 1) * PB + j;
       if (t >= 0 && t < len_t[j]) {
         const float* g = p.gates + ((size_t)t * B + b) * 4 * H + unit;
-        gi[j] = g[0]; gj[j] = g[H]; gf[j] = g[2 * H]; go[j] = g[3 * H];
+        v.gi[j] = g[0]; v.gj[j] = g[H]; v.gf[j] = g[2 * H]; v.go[j] = g[3 * H];
         const size_t o = ((size_t)t * B + b) * H + unit;
-        crw[j] = p.craw[o];
-        cpv[j] = t > 0 ? p.craw[o - (size_t)B * H] : (p.c0 ? p.c0[(size_t)b * H + unit] : 0.0f);
-        dov[j] = p.dout ? p.dout[o] : 0.0f;
+        v.crw[j] = p.craw[o];
+        v.cpv[j] = t > 0 ? p.craw[o - (size_t)B * H] : (p.c0 ? p.c0[(size_t)b * H + unit] : 0.0f);
+        v.dov[j] = p.dout ? p.dout[o] : 0.0f;
       }
     }
   };
   // reduce-scatter role after the product: warps 0-3 forward tile 0, warps 4-7 tile 1; lane quarter q = warp & 3
   const int q = warp & 3, mt_push = warp >> 2;
 
-  load_step(T - 1);
+  load_step(cur, T - 1);
+  load_step(nxt, T - 2);
   for (int it = 0; it < T; ++it) {
     const int t = T - 1 - it;
     // recurrent dh of this step: partial sums pushed by all CTAs during the previous iteration + carry
@@ -495,17 +530,17 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
         for (int src = 0; src < CL; ++src) dh += rbuf[(src * NB + bl) * UPC + ul];
       }
       if (t < len_t[j]) {
-        dh += dov[j];
-        const float c = fminf(fmaxf(crw[j], -1.0f), 1.0f);
+        dh += cur.dov[j];
+        const float c = fminf(fmaxf(cur.crw[j], -1.0f), 1.0f);
         const float tc = tanhf_acc(c);
-        const float cp = t > 0 ? fminf(fmaxf(cpv[j], -1.0f), 1.0f) : cpv[j];
-        const float dct = dc[j] + dh * go[j] * (1.0f - tc * tc);
-        const float dcr = (crw[j] >= -1.0f && crw[j] <= 1.0f) ? dct : 0.0f;  // gradient of the cell clip
-        dz[0][j] = tf32_rn(dcr * gj[j] * gi[j] * (1.0f - gi[j]));
-        dz[1][j] = tf32_rn(dcr * gi[j] * (1.0f - gj[j] * gj[j]));
-        dz[2][j] = tf32_rn(dcr * cp * gf[j] * (1.0f - gf[j]));
-        dz[3][j] = tf32_rn(dh * tc * go[j] * (1.0f - go[j]));
-        dc[j] = dcr * gf[j];
+        const float cp = t > 0 ? fminf(fmaxf(cur.cpv[j], -1.0f), 1.0f) : cur.cpv[j];
+        const float dct = dc[j] + dh * cur.go[j] * (1.0f - tc * tc);
+        const float dcr = (cur.crw[j] >= -1.0f && cur.crw[j] <= 1.0f) ? dct : 0.0f;  // gradient of the cell clip
+        dz[0][j] = tf32_rn(dcr * cur.gj[j] * cur.gi[j] * (1.0f - cur.gi[j]));
+        dz[1][j] = tf32_rn(dcr * cur.gi[j] * (1.0f - cur.gj[j] * cur.gj[j]));
+        dz[2][j] = tf32_rn(dcr * cp * cur.gf[j] * (1.0f - cur.gf[j]));
+        dz[3][j] = tf32_rn(dh * tc * cur.go[j] * (1.0f - cur.go[j]));
+        dc[j] = dcr * cur.gf[j];
         dh_carry[j] = 0.0f;
       } else {
         dz[0][j] = dz[1][j] = dz[2][j] = dz[3][j] = 0.0f;
@@ -517,17 +552,21 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_arrive(sBar + 8);
-    if ((warp & 3) == 0) {
-      // partial dh (256 rows) x NB from this CTA's 256 gate columns: lane 0 of warp 4*mt issues the 128-row tile mt
-      const int mt = warp >> 2;
+    cur = nxt;
+    load_step(nxt, t - 2);
+    {
+      // partial dh (256 rows) x NB from this CTA's 256 gate columns, once every warp's dz is in shared memory.  Every
+      // warp issues (see the forward kernel): lane 0 of warp (mt, j) the K quarter j (gate j) of the 128-row tile mt
+      // into its own accumulator columns; the reduce-scatter below adds the four partial accumulators.
+      const int mt = warp >> 2, jq = warp & 3;
       mbar_wait(sBar + 8, it & 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks)
-          umma_ts(tmem_base + mt * NP, tA + 128 * mt + ks * 8, desc_at(dDz, (ks >> 2) * (NP * 128) + (ks & 3) * 32), IDESC,
-                  ks ? 1u : 0u);
+        for (int k4 = 0; k4 < 4; ++k4)
+          umma_ts(tmem_base + (4 * mt + jq) * NP, tA + 128 * mt + (jq * 4 + k4) * 8, desc_at(dDz, jq * (NP * 128) + k4 * 32), IDESC,
+                  k4 ? 1u : 0u);
         umma_commit(sBar);
       }
       __syncwarp();
@@ -541,14 +580,19 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
         o[0] = dz[0][j]; o[H] = dz[1][j]; o[2 * H] = dz[2][j]; o[3 * H] = dz[3][j];
       }
     }
-    load_step(t - 1);
     // partial dh_{t-1}[k, b] for the 128 out-units of tile mt_push -> pushed to the owners of k
     mbar_wait(sBar, it & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
-      uint32_t r[8];
-      tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + mt_push * NP, r);
+      uint32_t r[8], r1[8], r2[8], r3[8];
+      tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (4 * mt_push + 0) * NP, r);
+      tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (4 * mt_push + 1) * NP, r1);
+      tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (4 * mt_push + 2) * NP, r2);
+      tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (4 * mt_push + 3) * NP, r3);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < NB; ++c)
+        r[c] = __float_as_uint((__uint_as_float(r[c]) + __uint_as_float(r1[c])) + (__uint_as_float(r2[c]) + __uint_as_float(r3[c])));
       // global unit 128*mt + 32*q + lane -> owner CTA 2*mt + (q >> 1), local unit 32*(q & 1) + lane
       const uint32_t dst = (uint32_t)(2 * mt_push + (q >> 1));
       const uint32_t rnext = sRed + ((it + 1) & 1) * REDH_FLOATS * 4;
@@ -623,6 +667,31 @@ int lstm_persist4_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   p.T = r->T; p.B = r->B;
   p.len = r->len; p.gates = r->gates; p.Wrec = r->Wrec; p.c0 = r->c0; p.S = r->S; p.craw = r->craw; p.out = r->out;
   p.cT = r->cT; p.hT = r->hT;
+  p.dbg = nullptr;
+  if (getenv("AVSR_LP4_DEBUG")) {
+    AVSR_CHECK_CUDA(cudaMalloc(&p.dbg, 64 * 8 * sizeof(long long)));
+    AVSR_CHECK_CUDA(cudaMemset(p.dbg, 0, 64 * 8 * sizeof(long long)));
+    AVSR_TRY(lp4::launch_cluster(st, lp4::lstm_persist4_fwd_kernel, r->B, lp4::FWD_SMEM, p, AVSR_K_LSTM_FWD));
+    AVSR_CHECK_CUDA(cudaStreamSynchronize(st));
+    long long h[64 * 8];
+    AVSR_CHECK_CUDA(cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(p.dbg);
+    const int n = r->T < 64 ? r->T : 64;
+    const char* names[7] = {"loop-top", "wait MMA", "ld+act+bar", "combine+send h", "hbm st/ld", "wait h", "issue"};
+    double acc[7] = {0};
+    for (int t = 3; t < n - 1; ++t) {
+      for (int k = 1; k < 7; ++k) acc[k] += (double)(h[t * 8 + k] - h[t * 8 + k - 1]);
+      acc[0] += (double)(h[t * 8] - h[(t - 1) * 8 + 6]);
+    }
+    fprintf(stderr, "[lp4 fwd T=%d B=%d] clocks/step:", r->T, r->B);
+    double tot = 0;
+    for (int k = 0; k < 7; ++k) {
+      fprintf(stderr, " %s=%.0f", names[k], acc[k] / (n - 4));
+      tot += acc[k] / (n - 4);
+    }
+    fprintf(stderr, " total=%.0f\n", tot);
+    return 0;
+  }
   return lp4::launch_cluster(st, lp4::lstm_persist4_fwd_kernel, r->B, lp4::FWD_SMEM, p, AVSR_K_LSTM_FWD);
 }
 
