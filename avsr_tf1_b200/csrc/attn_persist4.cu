@@ -255,10 +255,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_fwd_kernel(cons
   const int T = p.T, B = p.B, Tm = p.Tm;
 
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(sBar + 8 * i, 1);
+    mbar_init(sBar, THREADS / 32);  // mma_done: one commit per issuing warp
+    for (int i = 1; i < 5; ++i) mbar_init(sBar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // tensor memory (all 512 columns): [0, 16) / [16, 32) accumulators of the two gate tiles; [256, 512) W' tile 1
+  // tensor memory (all 512 columns): [0, 128) gate accumulators: tile m, K slice j at column 16 (4 m + j);
+  // [256, 512) W' tile 1
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -302,6 +304,26 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_fwd_kernel(cons
 
   // gate-math role: warp <-> (gate g, tile m): the gate rows of units 32*m + lane for all NB utterances
   const int g = warp & 3, m = warp >> 2;
+  // product-issue role.  Issuing a tcgen05.mma costs ~80 clocks of one thread (descriptor -> uniform registers), far
+  // more than a 128 x 16 x 16 product takes, and the issue of the ctx half sits on the critical path of the step.  So
+  // EVERY warp issues: lane 0 of warp (m, j) issues K blocks j (h half) and 4 + j (ctx half) of tile m into its own
+  // accumulator columns; the gate math adds the four partial accumulators of its tile.
+  const int jq = warp & 3;
+  const uint32_t acc_col = tmem_base + (4 * m + jq) * NP;
+  const uint64_t dW0 = make_desc_k128(sW);
+  const uint64_t dOp[2] = {make_desc_k128(sOp), make_desc_k128(sOp + OP_BYTES)};
+  auto issue_block = [&](int kb, uint32_t nbuf, bool clears) {
+    if (lane == 0) {
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) {
+        const uint64_t db = desc_at(dOp[nbuf], kb * (NP * 128) + k4 * 32);
+        const uint32_t acc = (clears && k4 == 0) ? 0u : 1u;
+        if (m == 0) umma_ss(acc_col, desc_at(dW0, kb * (128 * 128) + k4 * 32), db, IDESC, acc);
+        else umma_ts(acc_col, tW1 + (kb * 4 + k4) * 8, db, IDESC, acc);
+      }
+    }
+    __syncwarp();
+  };
   const int unit_g = UPC * rank + 32 * m + lane;
   // combine role (threads 0..127): utterance bq, units 4*uq .. 4*uq+3 of the CTA
   const bool comb = tid < 4 * 32;
@@ -347,9 +369,16 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_fwd_kernel(cons
     if (t > 0) {
       mbar_wait(sBar, (t - 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + m * NP, r);
+      uint32_t r1[8], r2[8], r3[8];
+      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 0) * NP, r);
+      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 1) * NP, r1);
+      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 2) * NP, r2);
+      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 3) * NP, r3);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+        r[b] = __float_as_uint((__uint_as_float(r[b]) + __uint_as_float(r1[b])) + (__uint_as_float(r2[b]) + __uint_as_float(r3[b])));
     } else {
 #pragma unroll
       for (int b = 0; b < 8; ++b) r[b] = 0u;  // att_{-1} = 0; h_0 Wh is already in the x-projection
@@ -432,23 +461,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_fwd_kernel(cons
     }
     if (tid == 0) mbar_expect_tx(hbar_n, NB * H * 2);
     mbar_wait(hbar_n, (t >> 1) & 1);  // every CTA's h_t slice has landed in buffer nb
-    if (warp == 0 && t + 1 < T) {
+    if (t + 1 < T) {
       // h half of the gate products of step t+1 (overlaps this step's attention).  Every warp has read the
       // accumulators of step t before its activations reached the barrier that precedes the h all-gather.
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        const uint32_t ob = sOp + nb * OP_BYTES;
-#pragma unroll
-        for (int kb = 0; kb < H / 64; ++kb)
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint64_t db = make_desc_k128(ob + kb * (NP * 128) + k4 * 32);
-            umma_ss(tmem_base, make_desc_k128(sW + kb * (128 * 128) + k4 * 32), db, IDESC, (kb | k4) ? 1u : 0u);
-            umma_ts(tmem_base + NP, tW1 + (kb * 4 + k4) * 8, db, IDESC, (kb | k4) ? 1u : 0u);
-          }
-      }
-      __syncwarp();
+      issue_block(jq, nb, true);
     }
     float ctxv[8];
 #pragma unroll
@@ -548,26 +566,16 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_fwd_kernel(cons
 #pragma unroll
       for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) st_async_v4(mapa(dbuf, dst), mapa(cbar_n, dst), c0, c1, c2, c3);
     }
-    if (warp == 0) {
+    {
       // ctx half of the gate products of step t+1, once every context of this step has landed.  After the last
       // step the wait only drains the all-gathers: no st.async may be in flight towards this CTA when it exits.
-      if (lane == 0) mbar_expect_tx(cbar_n, NB * DM * 2);
+      if (tid == 0) mbar_expect_tx(cbar_n, NB * DM * 2);
       mbar_wait(cbar_n, (t >> 1) & 1);
       if (t + 1 < T) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
-          const uint32_t ob = sOp + nb * OP_BYTES;
-#pragma unroll
-          for (int kb = H / 64; kb < KB; ++kb)
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint64_t db = make_desc_k128(ob + kb * (NP * 128) + k4 * 32);
-              umma_ss(tmem_base, make_desc_k128(sW + kb * (128 * 128) + k4 * 32), db, IDESC, 1u);
-              umma_ts(tmem_base + NP, tW1 + (kb * 4 + k4) * 8, db, IDESC, 1u);
-            }
-          umma_commit(sBar);
-        }
+        issue_block(4 + jq, nb, false);
+        if (lane == 0) umma_commit(sBar);
         __syncwarp();
       }
     }
@@ -660,15 +668,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
   const int T = p.T, B = p.B, Tm = p.Tm;
 
   if (tid == 0) {
-    mbar_init(barMma, 4);  // one commit per 128-row tile (four issuing threads)
+    mbar_init(barMma, THREADS / 32);  // one commit per issuing warp
     mbar_init(barDz, THREADS);
     mbar_init(barRedH, 1);
     mbar_init(barRedC, 1);
     mbar_init(barDq, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // tensor memory (all 512 columns): [0, 64) accumulators of the four 128-row tiles; [256, 512) tiles 2, 3 (ctx dims)
-  // of W'^T as A operands (128 columns = 256 K each)
+  // tensor memory (all 512 columns): [0, 128) accumulators: 128-row tile mt, K half hj at column 16 (2 mt + hj);
+  // [256, 512) tiles 2, 3 (ctx dims) of W'^T as A operands (128 columns = 256 K each)
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -1004,24 +1012,26 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_arrive(barDz);
-    if ((warp & 1) == 0) {
-      // partial [h | ctx](512) x NB from this CTA's 256 gate columns, once every warp's dz is in shared memory:
-      // lane 0 of warp 2*mt issues the 128-row tile mt (independent accumulators, four threads side by side)
-      const int mt = warp >> 1;
+    {
+      // partial [h | ctx](512) x NB from this CTA's 256 gate columns, once every warp's dz is in shared memory.  Every
+      // warp issues (a tcgen05.mma costs ~80 clocks of its issuing thread): lane 0 of warp (mt, hj) the K half hj
+      // (gates 2 hj, 2 hj + 1) of the 128-row tile mt into its own accumulator columns; the reduce-scatter adds the two.
+      const int mt = warp >> 1, hj = warp & 1;
       mbar_wait(barDz, it & 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
+        for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
+            const int kb = 2 * hj + kk;
             const uint64_t db = desc_at(dDz, kb * (NP * 128) + k4 * 32);
             if (mt < 2)
-              umma_ss(tmem_base + mt * NP, desc_at(dWt, mt * BW_TILE_BYTES + kb * (128 * 128) + k4 * 32), db, IDESC,
-                      (kb | k4) ? 1u : 0u);
+              umma_ss(tmem_base + (2 * mt + hj) * NP, desc_at(dWt, mt * BW_TILE_BYTES + kb * (128 * 128) + k4 * 32), db, IDESC,
+                      (kk | k4) ? 1u : 0u);
             else
-              umma_ts(tmem_base + mt * NP, tA + (mt - 2) * 128 + (kb * 4 + k4) * 8, db, IDESC, (kb | k4) ? 1u : 0u);
+              umma_ts(tmem_base + (2 * mt + hj) * NP, tA + (mt - 2) * 128 + (kb * 4 + k4) * 8, db, IDESC, (kk | k4) ? 1u : 0u);
           }
         umma_commit(barMma);
       }
@@ -1067,18 +1077,24 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
     for (int mi = 0; mi < 2; ++mi) {
       const int mt = 2 * (warp >> 2) + mi;
       if (mt < 2) {  // h rows: global unit 128*mt + 32*q + lane -> owner CTA 2*mt + (q >> 1), local unit 32*(q & 1) + lane
-        uint32_t r[8];
-        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NP, r);
+        uint32_t r[8], r1[8];
+        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (2 * mt) * NP, r);
+        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (2 * mt + 1) * NP, r1);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < NB; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(r1[c]));
         const uint32_t dst = (uint32_t)(2 * mt + (q >> 1));
         const uint32_t a0 = mapa(sRedH + (uint32_t)((rank * NB) * UPC + 32 * (q & 1) + lane) * 4, dst);
         const uint32_t bar = mapa(barRedH, dst);
 #pragma unroll
         for (int c = 0; c < NB; ++c) st_async_f(a0 + c * UPC * 4, bar, __uint_as_float(r[c]) * p.inv_grad_scale);
       } else if (it + 1 < T) {  // ctx dims 128*(mt-2) + 32*q + lane; column c = utterance -> owner CTA c / NU
-        uint32_t r[8];
-        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + mt * NP, r);
+        uint32_t r[8], r1[8];
+        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (2 * mt) * NP, r);
+        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (2 * mt + 1) * NP, r1);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < NB; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(r1[c]));
         const int dim = 128 * (mt - 2) + 32 * q + lane;
 #pragma unroll
         for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) {
