@@ -34,7 +34,7 @@ class AvsrRnnSeq(C.Structure):
         ('S', C.c_void_p), ('craw', C.c_void_p), ('out', C.c_void_p), ('cT', C.c_void_p), ('hT', C.c_void_p),
         ('mech', AvsrAttnMech * 2),
         ('dout', C.c_void_p), ('dcT', C.c_void_p), ('dhT', C.c_void_p), ('dZ', C.c_void_p), ('dA', C.c_void_p),
-        ('dWrec', C.c_void_p), ('dc0', C.c_void_p), ('dh0', C.c_void_p), ('work', C.c_void_p),
+        ('dWrec', C.c_void_p), ('dc0', C.c_void_p), ('dh0', C.c_void_p), ('dbias', C.c_void_p), ('work', C.c_void_p),
         ('grad_scale', C.c_float),
     ]
 

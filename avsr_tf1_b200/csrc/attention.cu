@@ -387,22 +387,24 @@ int attn_bwd_step(cudaStream_t st, int kind, int t, const int* seq_len, int Tm, 
 constexpr int OUT_TM = 16;   // memory rows per CTA
 constexpr int OUT_TT = 32;   // query steps staged per chunk
 
+constexpr int OUTER_TM = 16;  // memory rows per CTA of attn_outer (32 rows: 128 registers, fewer resident CTAs - slower)
+
 __global__ void __launch_bounds__(256)
 attn_outer_kernel(int T, int B, int Tm, int C, const int* __restrict__ seq_len, const float* __restrict__ w,
                   const float* __restrict__ x, int ldx, const float* __restrict__ scale, float* __restrict__ out) {
-  __shared__ float w_s[OUT_TT][OUT_TM];
-  const int b = blockIdx.x, tm0 = blockIdx.y * OUT_TM, tid = threadIdx.x;
+  __shared__ float w_s[OUT_TT][OUTER_TM];
+  const int b = blockIdx.x, tm0 = blockIdx.y * OUTER_TM, tid = threadIdx.x;
   const int Tb = min(T, seq_len[b]);
-  const int ntm = min(OUT_TM, Tm - tm0);
+  const int ntm = min(OUTER_TM, Tm - tm0);
   for (int c0 = 0; c0 < C; c0 += 256) {
     const int c = c0 + tid;
-    float acc[OUT_TM];
+    float acc[OUTER_TM];
 #pragma unroll
-    for (int i = 0; i < OUT_TM; ++i) acc[i] = 0.0f;
+    for (int i = 0; i < OUTER_TM; ++i) acc[i] = 0.0f;
     for (int t0 = 0; t0 < Tb; t0 += OUT_TT) {
       __syncthreads();
-      for (int e = tid; e < OUT_TT * OUT_TM; e += 256) {
-        const int tt = e / OUT_TM, i = e % OUT_TM;
+      for (int e = tid; e < OUT_TT * OUTER_TM; e += 256) {
+        const int tt = e / OUTER_TM, i = e % OUTER_TM;
         const int t = t0 + tt;
         w_s[tt][i] = (t < Tb && i < ntm) ? w[((size_t)t * B + b) * Tm + tm0 + i] : 0.0f;
       }
@@ -419,13 +421,15 @@ attn_outer_kernel(int T, int B, int Tm, int C, const int* __restrict__ seq_len, 
 #pragma unroll
           for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int i = 0; i < OUT_TM; ++i) acc[i] = fmaf(w_s[tt0 + j][i], xv[j], acc[i]);
+            for (int i = 0; i < OUTER_TM; ++i) acc[i] = fmaf(w_s[tt0 + j][i], xv[j], acc[i]);
         }
       }
     }
     if (c < C) {
       const float s = scale ? scale[0] : 1.0f;
-      for (int i = 0; i < ntm; ++i) out[((size_t)(tm0 + i) * B + b) * C + c] += s * acc[i];
+#pragma unroll
+      for (int i = 0; i < OUTER_TM; ++i)  // (constant indices keep acc[] in registers)
+        if (i < ntm) out[((size_t)(tm0 + i) * B + b) * C + c] += s * acc[i];
     }
   }
 }
@@ -433,7 +437,7 @@ attn_outer_kernel(int T, int B, int Tm, int C, const int* __restrict__ seq_len, 
 int attn_outer(cudaStream_t st, int T, int B, int Tm, int C, const int* seq_len, const float* w, const float* x,
                int ldx, const float* scale, float* out) {
   if (T <= 0) return 0;
-  dim3 grid(B, cdiv(Tm, OUT_TM));
+  dim3 grid(B, cdiv(Tm, OUTER_TM));
   AVSR_LAUNCH(attn_outer_kernel, grid, 256, 0, st, T, B, Tm, C, seq_len, w, x, ldx, scale, out);
   return 0;
 }

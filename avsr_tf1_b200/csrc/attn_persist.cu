@@ -1109,7 +1109,7 @@ int attn_persist4_launch_bwd(cudaStream_t st, int T, int B, int Tm, int scaled, 
                              const int* mem_len, const float* gates, const float* craw, const float* c0, const float* Wp,
                              const void* keys_h, const void* values_h, const float* g, const float* hc, const float* align,
                              const float* douthc, const float* dcT, const float* dhT, float* dZ, float* ds, float* dhc,
-                             float* dg, float* dc0, float* dh0);  // attn_persist4.cu
+                             float* dg, float* dc0, float* dh0, float* dbias);  // attn_persist4.cu
 
 size_t attn_persist_work_floats(int B, int H, int Dm, int Tm) {
   // fused weights [(H+Dm),4H] + product scratch [H,4H] + fp16 keys / values
@@ -1222,10 +1222,11 @@ int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   if (cluster_width() == 4) {
     AVSR_TRY(attn_persist4_launch_bwd(st, T, B, m.Tm, p.scaled, p.grad_scale, p.len, p.mem_len, p.gates, p.craw, p.c0, p.Wp,
                                       p.keys, p.values, p.g, p.hc, p.align, p.douthc, p.dcT, p.dhT, p.dZ, p.ds, p.dhc, p.dg,
-                                      p.dc0, p.dh0));
+                                      p.dc0, p.dh0, r->dbias));
   } else {
     AVSR_TRY(slice_width(B) == 32 ? launch_cluster(st, attn_lstm_persist_bwd_kernel<32>, B, 32, BwdCfg<32>::THREADS, BwdCfg<32>::SMEM, p)
                                    : launch_cluster(st, attn_lstm_persist_bwd_kernel<16>, B, 16, BwdCfg<16>::THREADS, BwdCfg<16>::SMEM, p));
+    if (r->dbias) AVSR_TRY(avsr_colsum((avsr_stream_t)st, r->dZ, T * B, 4 * H, 4 * H, r->dbias));
   }
   if (dbg_dev) {
     AVSR_CHECK_CUDA(cudaStreamSynchronize(st));

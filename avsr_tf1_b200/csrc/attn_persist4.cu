@@ -461,13 +461,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_fwd_kernel(cons
     }
     if (tid == 0) mbar_expect_tx(hbar_n, NB * H * 2);
     mbar_wait(hbar_n, (t >> 1) & 1);  // every CTA's h_t slice has landed in buffer nb
-    if (t + 1 < T) {
-      // h half of the gate products of step t+1 (overlaps this step's attention).  Every warp has read the
-      // accumulators of step t before its activations reached the barrier that precedes the h all-gather.
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_block(jq, nb, true);
-    }
+
     float ctxv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) ctxv[e] = 0.0f;
@@ -567,8 +561,16 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_fwd_kernel(cons
       for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) st_async_v4(mapa(dbuf, dst), mapa(cbar_n, dst), c0, c1, c2, c3);
     }
     {
-      // ctx half of the gate products of step t+1, once every context of this step has landed.  After the last
-      // step the wait only drains the all-gathers: no st.async may be in flight towards this CTA when it exits.
+      // Gate products of step t+1.  The h half is issued here, after this warp's share of the attention and while the
+      // contexts of the other CTAs are still in flight (h_t has landed: every warp waited for it above; every warp
+      // has read the accumulators of step t before its activations reached the barrier that precedes the h
+      // all-gather); the ctx half once every context of this step has landed.  After the last step the wait only
+      // drains the all-gathers: no st.async may be in flight towards this CTA when it exits.
+      if (t + 1 < T) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_block(jq, nb, true);
+      }
       if (tid == 0) mbar_expect_tx(cbar_n, NB * DM * 2);
       mbar_wait(cbar_n, (t >> 1) & 1);
       if (t + 1 < T) {
@@ -621,6 +623,7 @@ struct BwdParams {
   float* dg;             // [1] or null
   float* dc0;            // [B,H] or null
   float* dh0;            // [B,H] or null
+  float* dbias;          // [4H] or null: += column sums of dZ
   long long* dbg;        // AVSR_AP_DEBUG: clock samples [64 iterations][12] of CTA 0, thread 0
 };
 #define AP4B_STAMP(slot)                                                                         \
@@ -764,6 +767,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
   // reduce-scatter role after the product: warps 0-3 forward tiles 0, 1 (h rows), warps 4-7 tiles 2, 3 (ctx dims)
   const int q = warp & 3;
 
+  float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // bias gradient of this thread's unit: sum of dz over its utterances / steps
   load_step(T - 1);
   for (int it = 0; it < T; ++it) {
     const int t = T - 1 - it;
@@ -1044,6 +1048,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
       if (b < B) {
         float* o = p.dZ + ((size_t)t * B + b) * 4 * H + unit;
         o[0] = tf32_rn(dz[0][j]); o[H] = tf32_rn(dz[1][j]); o[2 * H] = tf32_rn(dz[2][j]); o[3 * H] = tf32_rn(dz[3][j]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) bsum[g] += tf32_rn(dz[g][j]);
       }
     }
     load_step(t - 1);
@@ -1123,6 +1129,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
       if (p.dc0) p.dc0[(size_t)b * H + unit] = dc[j];
     }
   }
+  if (p.dbias) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) atomicAdd(p.dbias + g * H + unit, bsum[g]);
+  }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -1195,14 +1205,14 @@ int attn_persist4_launch_bwd(cudaStream_t st, int T, int B, int Tm, int scaled, 
                              const int* mem_len, const float* gates, const float* craw, const float* c0, const float* Wp,
                              const void* keys_h, const void* values_h, const float* g, const float* hc, const float* align,
                              const float* douthc, const float* dcT, const float* dhT, float* dZ, float* ds, float* dhc,
-                             float* dg, float* dc0, float* dh0) {
+                             float* dg, float* dc0, float* dh0, float* dbias) {
   ap4::BwdParams p;
   p.T = T; p.B = B; p.Tm = Tm; p.scaled = scaled;
   p.grad_scale = grad_scale; p.inv_grad_scale = 1.0f / grad_scale;
   p.len = len; p.mem_len = mem_len; p.gates = gates; p.craw = craw; p.c0 = c0; p.Wp = Wp;
   p.keys = reinterpret_cast<const __half*>(keys_h); p.values = reinterpret_cast<const __half*>(values_h);
   p.g = g; p.hc = hc; p.align = align; p.douthc = douthc; p.dcT = dcT; p.dhT = dhT; p.dZ = dZ; p.ds = ds; p.dhc = dhc;
-  p.dg = dg; p.dc0 = dc0; p.dh0 = dh0;
+  p.dg = dg; p.dc0 = dc0; p.dh0 = dh0; p.dbias = dbias;
   p.dbg = nullptr;
   if (getenv("AVSR_AP_DEBUG")) {
     static const char* names[12] = {"loop-top", "wait redH/redC+fold", "dctx+cta bar", "values sweep", "softmax bwd", "keys sweep",

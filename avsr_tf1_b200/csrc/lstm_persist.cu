@@ -754,10 +754,6 @@ int lstm_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
 
 int lstm_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   if (r->n_mech != 0 || r->T <= 0) return -1;
-  {
-    const int rc = lstm_persist4_bwd(st, r);
-    if (rc >= 0) return rc;
-  }
   if (r->H != 128 && r->H != 256) return -1;
   lp::BwdParams p;
   p.T = r->T; p.B = r->B; p.H = r->H;

@@ -404,6 +404,7 @@ struct BwdParams {
   float* dZ;           // [T,B,4H]
   float* dc0;          // [B,H] or null
   float* dh0;          // [B,H] or null
+  float* dbias;        // [4H] or null: += column sums of dZ
 };
 
 constexpr int BW_DZ_BYTES = 4 * NP * 128;            // B operand: 4 K-blocks (gates) x [NP rows x 64 units]
@@ -509,6 +510,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
   // reduce-scatter role after the product: warps 0-3 forward tile 0, warps 4-7 tile 1; lane quarter q = warp & 3
   const int q = warp & 3, mt_push = warp >> 2;
 
+  float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // bias gradient of this thread's unit: sum of dz over its utterances / steps
   load_step(cur, T - 1);
   load_step(nxt, T - 2);
   for (int it = 0; it < T; ++it) {
@@ -542,6 +544,10 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
         dz[3][j] = tf32_rn(dh * tc * cur.go[j] * (1.0f - cur.go[j]));
         dc[j] = dcr * cur.gf[j];
         dh_carry[j] = 0.0f;
+        if (b0 + bl < B) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) bsum[g] += dz[g][j];
+        }
       } else {
         dz[0][j] = dz[1][j] = dz[2][j] = dz[3][j] = 0.0f;
         dh_carry[j] = dh;  // state (and its gradient) is carried through masked steps
@@ -624,6 +630,10 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
       if (p.dc0) p.dc0[(size_t)b * H + unit] = dc[j];
     }
   }
+  if (p.dbias) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) atomicAdd(p.dbias + g * H + unit, bsum[g]);
+  }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -702,7 +712,7 @@ int lstm_persist4_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   p.grad_scale = r->grad_scale > 0.0f ? r->grad_scale : 1.0f;
   p.inv_grad_scale = 1.0f / p.grad_scale;
   p.len = r->len; p.gates = r->gates; p.Wrec = r->Wrec; p.c0 = r->c0; p.craw = r->craw; p.dout = r->dout;
-  p.dcT = r->dcT; p.dhT = r->dhT; p.dZ = r->dZ; p.dc0 = r->dc0; p.dh0 = r->dh0;
+  p.dcT = r->dcT; p.dhT = r->dhT; p.dZ = r->dZ; p.dc0 = r->dc0; p.dh0 = r->dh0; p.dbias = r->dbias;
   return lp4::launch_cluster(st, lp4::lstm_persist4_bwd_kernel, r->B, lp4::BWD_SMEM, p, AVSR_K_LSTM_BWD);
 }
 

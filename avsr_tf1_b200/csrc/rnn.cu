@@ -285,14 +285,20 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   return 0;
 }
 
-int lstm_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r);  // lstm_persist.cu
+int lstm_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r);   // lstm_persist.cu (clusters of 8)
+int lstm_persist4_bwd(cudaStream_t st, const AvsrRnnSeq* r);  // lstm_persist4.cu (clusters of 4; forms dbias itself)
 
 int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   int At, maxHD, maxA, maxTm;
   AVSR_TRY(check_common(r, &At, &maxHD, &maxA, &maxTm));
   const int T = r->T, B = r->B, H = r->H, SW = At + H;
   if (r->n_mech == 0 && tensor_cores_enabled()) {
-    const int rc = lstm_persist_bwd(st, r);  // reverse-time recurrence in one persistent cluster kernel
+    // reverse-time recurrence in one persistent cluster kernel
+    int rc = lstm_persist4_bwd(st, r);
+    if (rc < 0) {
+      rc = lstm_persist_bwd(st, r);
+      if (rc == 0 && r->dbias && T > 0) AVSR_TRY(avsr_colsum((avsr_stream_t)st, r->dZ, T * B, 4 * H, 4 * H, r->dbias));
+    }
     if (rc >= 0) {
       if (rc == 0 && T > 0)  // dWrec += S[0:T]^T @ dZ
         AVSR_TRY(gemm(st, 1, 0, SW, 4 * H, T * B, r->S, SW, r->dZ, 4 * H, r->dWrec, 4 * H, 1.0f, nullptr));
@@ -359,6 +365,7 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   if (r->dh0) AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, dS[cur] + At, SW, r->dh0, H, B, H);
   if (r->dc0) AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, dcb[cur], H, r->dc0, H, B, H);
   if (T > 0) {
+    if (r->dbias) AVSR_TRY(avsr_colsum((avsr_stream_t)st, r->dZ, T * B, 4 * H, 4 * H, r->dbias));
     // dWrec += S[0:T]^T @ dZ
     AVSR_TRY(gemm(st, 1, 0, SW, 4 * H, T * B, r->S, SW, r->dZ, 4 * H, r->dWrec, 4 * H, 1.0f, nullptr));
     int off = 0;

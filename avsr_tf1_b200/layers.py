@@ -149,10 +149,9 @@ class LSTMLayerOp:
         gW, gb = self.ctx.g(self.kernel), self.ctx.g(self.bias)
         dcT, dhT = dstate if dstate is not None else (None, None)
         self.rnn.grad_scale = self.ctx.grad_scale  # fp16 dz operand of the cluster-of-4 backward kernel
-        dZ = self.rnn.backward(dout, gW[I:], dcT=dcT, dhT=dhT)
+        dZ = self.rnn.backward(dout, gW[I:], dcT=dcT, dhT=dhT, dbias=gb)  # (bias gradient inside the recurrent op)
         dZ2 = dZ.view(T * B, 4 * H)
         ops.gemm(self.x.reshape(T * B, I), dZ2, gW[:I], ta=True, beta=1.0)
-        ops.colsum(dZ2, gb)
         dx = None
         if need_dx:
             dx = ops.empty(T, B, I)
@@ -286,10 +285,9 @@ class AttnLSTMOp:
                 mb.dg = ctx.g(md.g)
         dcT, dhT = dstate if dstate is not None else (None, None)
         self.rnn.grad_scale = ctx.grad_scale
-        dZ = self.rnn.backward(dout, gW[Dx:], dcT=dcT, dhT=dhT, want_init_grad=want_init_grad)
+        dZ = self.rnn.backward(dout, gW[Dx:], dcT=dcT, dhT=dhT, want_init_grad=want_init_grad, dbias=gb)
         dZ2 = dZ.view(T * B, 4 * H)
         ops.gemm(self.x.reshape(T * B, Dx), dZ2, gW[:Dx], ta=True, beta=1.0)
-        ops.colsum(dZ2, gb)
         dx = None
         if need_dx:
             dx = ops.empty(T, B, Dx)

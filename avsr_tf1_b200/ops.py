@@ -305,8 +305,9 @@ class RnnSeq:
         check(_lib.load().avsr_rnn_seq_fwd(_stream(), C.byref(r)))
         return self.out
 
-    def backward(self, dout, dWrec, dcT=None, dhT=None, want_init_grad=False):
-        """Fills self.dZ [T,B,4H]; accumulates dWrec and the mechanism grads (set on the MechBuffers)."""
+    def backward(self, dout, dWrec, dcT=None, dhT=None, want_init_grad=False, dbias=None):
+        """Fills self.dZ [T,B,4H]; accumulates dWrec, the mechanism grads (set on the MechBuffers) and, if given,
+        the bias gradient dbias [4H] += column sums of dZ."""
         T, B, H = self.T, self.B, self.H
         self.dZ = empty(T, B, 4 * H)
         if self.At > 0:
@@ -318,6 +319,7 @@ class RnnSeq:
                 m.dpq = empty(T, B, m.A)
             m.ds = empty(T, B, m.Tm)
             m.dhc = empty(T, B, H + m.Dm)
-        r = self._desc(dout=dout, dcT=dcT, dhT=dhT, dZ=self.dZ, dA=self.dA, dWrec=dWrec, dc0=self.dc0, dh0=self.dh0)
+        r = self._desc(dout=dout, dcT=dcT, dhT=dhT, dZ=self.dZ, dA=self.dA, dWrec=dWrec, dc0=self.dc0, dh0=self.dh0,
+                       dbias=dbias)
         check(_lib.load().avsr_rnn_seq_bwd(_stream(), C.byref(r)))
         return self.dZ

@@ -155,6 +155,7 @@ typedef struct AvsrRnnSeq {
   float* dWrec;         /* [(At+H),4H] accumulated */
   float* dc0;           /* [B,H] or NULL */
   float* dh0;           /* [B,H] or NULL */
+  float* dbias;         /* [4H] or NULL: += column sums of dZ (the gradient of the cell bias) */
   float* work;          /* scratch, >= avsr_rnn_work_floats() floats; backward must see what forward left */
   float grad_scale;     /* power of two ~ 1/|gradient scale| (e.g. the token count): fp16 tensor-core operand
                            scaling of the persistent attention backward kernel; 0 = 1 */
