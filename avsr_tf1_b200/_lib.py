@@ -36,12 +36,14 @@ class AvsrRnnSeq(C.Structure):
         ('dout', C.c_void_p), ('dcT', C.c_void_p), ('dhT', C.c_void_p), ('dZ', C.c_void_p), ('dA', C.c_void_p),
         ('dWrec', C.c_void_p), ('dc0', C.c_void_p), ('dh0', C.c_void_p), ('dbias', C.c_void_p), ('work', C.c_void_p),
         ('grad_scale', C.c_float),
+        ('rng', C.c_void_p), ('drop_stream', C.c_uint32), ('thr_in', C.c_uint32), ('thr_state', C.c_uint32),
+        ('thr_out', C.c_uint32), ('t_begin', C.c_int), ('t_end', C.c_int), ('stepwise', C.c_int),
     ]
 
 
 ATTN_KINDS = {'luong': 0, 'scaled_luong': 1, 'bahdanau': 2, 'normed_bahdanau': 3}
 
-_P, _I, _L, _F, _D = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+_P, _I, _L, _F, _D, _U = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double, C.c_uint32
 
 # name -> (restype, argtypes).  Must list every symbol include/avsr_b200.h declares
 # (tests/test_abi.py checks both directions).
@@ -71,6 +73,8 @@ PROTOTYPES = {
     'avsr_rnn_seq_bwd': (_I, [_P, C.POINTER(AvsrRnnSeq)]),
     'avsr_normed_v_fwd': (_I, [_P, _P, _P, _I, _P]),
     'avsr_normed_v_bwd': (_I, [_P, _P, _P, _P, _I, _P, _P]),
+    'avsr_dropout': (_I, [_P, _P, _L, _L, _P, _U, _U, _I, _P]),
+    'avsr_sched_sample': (_I, [_P, _P, _I, _I, _P, _U, _I, _U, _P, _P, _P]),
     'avsr_embedding_fwd': (_I, [_P, _P, _I, _I, _P, _L, _P]),
     'avsr_embedding_bwd': (_I, [_P, _P, _P, _L, _I, _I, _P]),
     'avsr_seq_loss': (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P]),

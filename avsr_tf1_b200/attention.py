@@ -45,4 +45,4 @@ def add_attention(cell, attention_types, num_units, memory_depths, ctx, wrap_pre
     Returns the AttnLSTMOp that runs the wrapped cell over a whole sequence."""
     mechs, _ = create_attention_mechanisms(num_units, attention_types, memory_depths, ctx, wrap_prefix,
                                            mem_layer_names, cell.num_units, fusion_type)
-    return AttnLSTMOp(ctx, wrap_prefix, in_dim, cell.num_units, mechs)
+    return AttnLSTMOp(ctx, wrap_prefix, in_dim, cell.num_units, mechs, drop=ctx.drop_state(cell, wrap_prefix))

@@ -19,11 +19,10 @@ class LSTMCellSpec(object):
 def _build_single_cell(cell_type, num_units, use_dropout, mode, dropout_probability, dtype=None, device=None):
     if cell_type != 'lstm':
         raise Exception('cell type not supported: {}'.format(cell_type))
-    drop = use_dropout is True and mode == 'train'
-    if drop and any(p < 1.0 for p in dropout_probability):
-        raise NotImplementedError(
-            'DropoutWrapper (cells.py:46-54) is not implemented on the B200 path yet: TF\'s Philox streams are '
-            'not reproducible, so parity runs use use_dropout=False (SURVEY.md section 7). Pass use_dropout=False.')
+    # DropoutWrapper(input, state, output keep probabilities) in train mode only (cells.py:46-54).  TF's Philox
+    # streams are not reproducible: the masks come from the library's counter-based generator (avsr_dropout), the
+    # oracle restates it, parity holds mask for mask.
+    drop = use_dropout is True and mode == 'train' and any(p < 1.0 for p in dropout_probability)
     return LSTMCellSpec(num_units, drop, dropout_probability)
 
 

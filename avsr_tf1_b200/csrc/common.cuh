@@ -73,6 +73,31 @@ __device__ __forceinline__ float tf32_rn(float x) {
 }
 __device__ __forceinline__ float maybe_tf32(float x, int rnd) { return rnd ? tf32_rn(x) : x; }
 
+// ---- counter-based random words (dropout masks, scheduled sampling) -----------------------------------------------
+// Two rounds of the murmur3 32-bit finaliser over (seed, step, stream, hi, lo); no state, so forward and backward
+// regenerate the same mask.  Restated bit for bit in oracle/avsr_oracle.py (rand_u32).
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t avsr_rand_u32(uint32_t seed, uint32_t step, uint32_t stream, uint32_t hi,
+                                                          uint32_t lo) {
+  uint32_t x = fmix32(lo * 0x9E3779B1u + seed);
+  x += hi * 0x27D4EB2Fu + stream * 0x165667B1u + step * 0x9E3779B9u;
+  return fmix32(x ^ 0x5BD1E995u);
+}
+// inverted-dropout factor of element (hi, lo): 1/keep if kept, else 0.  thr == 0: dropout off (factor 1).
+__device__ __forceinline__ float drop_factor(const uint32_t* __restrict__ rng, uint32_t stream, uint32_t thr,
+                                             float inv_keep, uint32_t hi, uint32_t lo) {
+  if (thr == 0u) return 1.0f;
+  return avsr_rand_u32(rng[0], rng[1], stream, hi, lo) < thr ? inv_keep : 0.0f;
+}
+static inline float inv_keep_of(uint32_t thr) { return thr ? (float)(4294967296.0 / (double)thr) : 1.0f; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

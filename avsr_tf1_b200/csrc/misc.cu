@@ -310,6 +310,47 @@ __global__ void normed_v_bwd_kernel(const float* __restrict__ v, const float* __
   for (int u = threadIdx.x; u < A; u += blockDim.x) dv[u] += g[0] * inv * (dveff[u] - dvhat * v[u] * inv);
 }
 
+// ---- randomness of the training graph (dropout, scheduled sampling) -----------------------------------------------
+__global__ void dropout_kernel(const float* __restrict__ x, long long n, long long first,
+                               const uint32_t* __restrict__ rng, uint32_t stream_id, uint32_t thr, float inv_keep,
+                               int rnd, float* __restrict__ y) {
+  const uint32_t seed = rng[0], step = rng[1];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float f = avsr_rand_u32(seed, step, stream_id, 0u, (uint32_t)(first + i)) < thr ? inv_keep : 0.0f;
+    y[i] = maybe_tf32(x[i] * f, rnd);
+  }
+}
+
+// one thread per row: V is the output alphabet (31)
+__global__ void sched_sample_kernel(const float* __restrict__ logits, int B, int V, const uint32_t* __restrict__ rng,
+                                    uint32_t stream_id, int t, uint32_t thr_p, const int* __restrict__ true_next,
+                                    int* __restrict__ next_ids, int* __restrict__ sampled) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const uint32_t seed = rng[0], step = rng[1];
+  int pick = -1;
+  if (avsr_rand_u32(seed, step, stream_id, (uint32_t)t, (uint32_t)b) < thr_p) {
+    const float* z = logits + (size_t)b * V;
+    float m = z[0];
+    for (int v = 1; v < V; ++v) m = fmaxf(m, z[v]);
+    float total = 0.0f;
+    for (int v = 0; v < V; ++v) total += expf(z[v] - m);
+    const float u = (float)(avsr_rand_u32(seed, step, stream_id + 1u, (uint32_t)t, (uint32_t)b) >> 8) * (1.0f / 16777216.0f);
+    const float target = u * total;
+    float cum = 0.0f;
+    pick = V - 1;
+    for (int v = 0; v < V; ++v) {
+      cum += expf(z[v] - m);
+      if (cum > target) {
+        pick = v;
+        break;
+      }
+    }
+  }
+  sampled[b] = pick;
+  next_ids[b] = pick >= 0 ? pick : true_next[b];
+}
+
 // ---- decoding helpers -----------------------------------------------------------
 __global__ void greedy_pick_kernel(const float* __restrict__ logits, int B, int V, int eos, int* __restrict__ finished,
                                    int* __restrict__ sample_out, int* __restrict__ next_ids) {
@@ -576,6 +617,26 @@ int avsr_normed_v_fwd(avsr_stream_t s, const float* v, const float* g, int A, fl
 int avsr_normed_v_bwd(avsr_stream_t s, const float* v, const float* g, const float* dveff, int A, float* dv,
                       float* dg) {
   AVSR_LAUNCH(normed_v_bwd_kernel, 1, 256, 0, ST(s), v, g, dveff, A, dv, dg);
+  return 0;
+}
+
+int avsr_dropout(avsr_stream_t s, const float* x, long long n, long long first, const uint32_t* rng,
+                 uint32_t stream_id, uint32_t thr, int round_out, float* y) {
+  AVSR_REQUIRE(rng != nullptr && thr != 0u, "dropout: needs the rng words and a non-zero keep threshold");
+  AVSR_REQUIRE(n >= 0 && first >= 0 && first + n <= (1ll << 32), "dropout: element indices must stay below 2^32");
+  if (n == 0) return 0;
+  int grid = cdiv(n, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  AVSR_LAUNCH(dropout_kernel, grid, 256, 0, ST(s), x, n, first, rng, stream_id, thr, inv_keep_of(thr),
+              round_out && tensor_cores_enabled(), y);
+  return 0;
+}
+
+int avsr_sched_sample(avsr_stream_t s, const float* logits, int B, int V, const uint32_t* rng, uint32_t stream_id,
+                      int t, uint32_t thr_p, const int* true_next, int* next_ids, int* sampled) {
+  AVSR_REQUIRE(rng != nullptr && B > 0 && V > 0, "sched_sample: bad arguments");
+  AVSR_LAUNCH(sched_sample_kernel, cdiv(B, 128), 128, 0, ST(s), logits, B, V, rng, stream_id, t, thr_p, true_next,
+              next_ids, sampled);
   return 0;
 }
 

@@ -22,19 +22,43 @@ struct HcDst {
   int ld[2];
 };
 
+// DropoutWrapper masks applied inside the loop (see AvsrRnnSeq.rng): streams +0 attention part of the cell input,
+// +1 recurrent state h, +2 cell output.  thr == 0 switches a mask off.
+struct Drop {
+  const uint32_t* rng;
+  uint32_t stream, thr_in, thr_state, thr_out;
+  float inv_in, inv_state, inv_out;
+};
+static Drop drop_of(const AvsrRnnSeq* r) {
+  Drop d = {r->rng, r->drop_stream, 0u, 0u, 0u, 1.0f, 1.0f, 1.0f};
+  if (r->rng) {
+    d.thr_in = r->thr_in;
+    d.thr_state = r->thr_state;
+    d.thr_out = r->thr_out;
+    d.inv_in = inv_keep_of(d.thr_in);
+    d.inv_state = inv_keep_of(d.thr_state);
+    d.inv_out = inv_keep_of(d.thr_out);
+  }
+  return d;
+}
+static bool stepwise_only(const AvsrRnnSeq* r) {
+  return r->stepwise || r->t_begin || r->t_end || (r->rng && (r->thr_in | r->thr_state | r->thr_out));
+}
+
 __global__ void lstm_point_fwd_kernel(int t, int B, int H, float* __restrict__ gates_t, const float* __restrict__ rec,
                                       const int* __restrict__ len, const float* __restrict__ c_prev,
                                       const float* __restrict__ h_prev, int ldh_prev, float* __restrict__ c_next,
                                       float* __restrict__ h_next, int ldh_next, float* __restrict__ craw_t,
-                                      float* __restrict__ out_t, HcDst hc, int rnd) {
+                                      float* __restrict__ out_t, HcDst hc, int rnd, Drop dr) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int b = idx / H, u = idx - b * H;
   float cp = c_prev[idx];
   float hp = h_prev[(size_t)b * ldh_prev + u];
-  float hn, cn;
+  float hn, cn, ho;  // hn: what recurs (state dropout), ho: what the cell emits (output dropout)
   if (t >= len[b]) {
     hn = hp;
+    ho = hp;
     cn = cp;
     craw_t[idx] = cp;
     if (out_t) out_t[idx] = 0.0f;  // dynamic_rnn emits zeros past the sequence length
@@ -47,20 +71,32 @@ __global__ void lstm_point_fwd_kernel(int t, int B, int H, float* __restrict__ g
     float go = sigmoidf_acc(g[3 * H + u] + r[3 * H + u]);
     float cr = gf * cp + gi * gj;
     cn = fminf(fmaxf(cr, -1.0f), 1.0f);  // cell_clip = 1.0 (cells.py:16)
-    hn = go * tanhf_acc(cn);
+    const float h = go * tanhf_acc(cn);
+    ho = h * drop_factor(dr.rng, dr.stream + 2u, dr.thr_out, dr.inv_out, (uint32_t)t, (uint32_t)idx);
+    hn = h * drop_factor(dr.rng, dr.stream + 1u, dr.thr_state, dr.inv_state, (uint32_t)t, (uint32_t)idx);
     g[u] = gi;
     g[H + u] = gj;
     g[2 * H + u] = gf;
     g[3 * H + u] = go;
     craw_t[idx] = cr;
-    if (out_t) out_t[idx] = hn;
+    if (out_t) out_t[idx] = ho;
   }
   c_next[idx] = cn;
   // the state row and [h | ctx] are tensor-core operands: stored tf32-rounded (out_t keeps the exact h)
-  const float hr = maybe_tf32(hn, rnd);
-  h_next[(size_t)b * ldh_next + u] = hr;
+  h_next[(size_t)b * ldh_next + u] = maybe_tf32(hn, rnd);
+  const float hr = maybe_tf32(ho, rnd);
   if (hc.p[0]) hc.p[0][(size_t)b * hc.ld[0] + u] = hr;
   if (hc.p[1]) hc.p[1][(size_t)b * hc.ld[1] + u] = hr;
+}
+
+// attention part of the next cell input: S_next[b, :At] *= input-dropout factor of step t_next (in place, after the
+// attention vectors have been emitted as the layer output)
+__global__ void drop_attention_kernel(int t_next, int B, int At, int SW, float* __restrict__ S_next, int rnd, Drop dr) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * At) return;
+  int b = idx / At, a = idx - b * At;
+  float* p = S_next + (size_t)b * SW + a;
+  *p = maybe_tf32(*p * drop_factor(dr.rng, dr.stream, dr.thr_in, dr.inv_in, (uint32_t)t_next, (uint32_t)idx), rnd);
 }
 
 struct DhSrc {
@@ -74,7 +110,7 @@ __global__ void lstm_point_bwd_kernel(int t, int B, int H, int At, const float* 
                                       const float* __restrict__ c0, const int* __restrict__ len,
                                       const float* __restrict__ dout_h_t, const float* __restrict__ dS_cur,
                                       const float* __restrict__ dc_cur, DhSrc extra, float* __restrict__ dZ_t,
-                                      float* __restrict__ dS_next, float* __restrict__ dc_next, int rnd) {
+                                      float* __restrict__ dS_next, float* __restrict__ dc_next, int rnd, Drop dr) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   int b = idx / H, u = idx - b * H;
@@ -90,10 +126,12 @@ __global__ void lstm_point_bwd_kernel(int t, int B, int H, int At, const float* 
     dS_next[(size_t)b * SW + At + u] = dh_in;
     dc_next[idx] = dc_in;
   } else {
-    float dh = dh_in + (dout_h_t ? dout_h_t[idx] : 0.0f);
+    float dho = dout_h_t ? dout_h_t[idx] : 0.0f;  // wrt the emitted (output-dropped) h
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (extra.p[k]) dh += extra.p[k][(size_t)b * extra.ld[k] + u];
+      if (extra.p[k]) dho += extra.p[k][(size_t)b * extra.ld[k] + u];
+    const float dh = dh_in * drop_factor(dr.rng, dr.stream + 1u, dr.thr_state, dr.inv_state, (uint32_t)t, (uint32_t)idx) +
+                     dho * drop_factor(dr.rng, dr.stream + 2u, dr.thr_out, dr.inv_out, (uint32_t)t, (uint32_t)idx);
     const float* g = gates_t + (size_t)b * 4 * H;
     float gi = g[u], gj = g[H + u], gf = g[2 * H + u], go = g[3 * H + u];
     float cr = craw_t[idx];
@@ -117,12 +155,14 @@ __global__ void lstm_point_bwd_kernel(int t, int B, int H, int At, const float* 
 // dA_t[b,:] = mask * (dS_cur.att + (oa ? dout_t : 0))
 __global__ void attn_bwd_prep_kernel(int t, int B, int At, int SW, const int* __restrict__ len,
                                      const float* __restrict__ dS_cur, const float* __restrict__ dout_att_t,
-                                     float* __restrict__ dA_t, int rnd) {
+                                     float* __restrict__ dA_t, int rnd, Drop dr) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * At) return;
   int b = idx / At, a = idx - b * At;
   float v = 0.0f;
-  if (t < len[b]) v = dS_cur[(size_t)b * SW + a] + (dout_att_t ? dout_att_t[idx] : 0.0f);
+  if (t < len[b])  // dS_cur.att is wrt the dropped attention input of step t + 1
+    v = dS_cur[(size_t)b * SW + a] * drop_factor(dr.rng, dr.stream, dr.thr_in, dr.inv_in, (uint32_t)(t + 1), (uint32_t)idx) +
+        (dout_att_t ? dout_att_t[idx] : 0.0f);
   dA_t[idx] = maybe_tf32(v, rnd);
 }
 
@@ -223,14 +263,15 @@ int lstm_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r);  // lstm_persist.cu
 int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   int At, maxHD, maxA, maxTm;
   AVSR_TRY(check_common(r, &At, &maxHD, &maxA, &maxTm));
-  if (r->n_mech == 0 && tensor_cores_enabled()) {  // persistent cluster kernel (tcgen05, weights resident)
+  const bool stepwise = stepwise_only(r);
+  if (r->n_mech == 0 && tensor_cores_enabled() && !stepwise) {  // persistent cluster kernel (tcgen05, weights resident)
     const int rc = lstm_persist_fwd(st, r);
     if (rc >= 0) return rc;
   }
   const int T = r->T, B = r->B, H = r->H, SW = At + H;
   const int rnd = tensor_cores_enabled();
   WorkLayout wl = work_layout(B, H, At, maxHD, maxA, maxTm);
-  if (r->n_mech == 1 && rnd && T > 1 && !getenv("AVSR_NO_ATTN_PERSIST")) {  // T == 1: step-wise decoding (carried attention)
+  if (r->n_mech == 1 && rnd && T > 1 && !stepwise && !getenv("AVSR_NO_ATTN_PERSIST")) {  // T == 1: step-wise decoding (carried attention)
     // persistent cluster kernel for the Luong-family attention layer (AV-Align top layer, LAS decoder)
     const int rc = attn_persist_fwd(st, r, r->work + wl.persist);
     if (rc >= 0) {
@@ -243,9 +284,12 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   float* rec = r->work + wl.rec;
   float* cbuf[2] = {r->work + wl.cbuf, r->work + wl.cbuf + (size_t)B * H};
   const int pw_grid = cdiv((long long)B * H, 256);
-  AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->c0, H, cbuf[0], H, B, H);
-  int cur = 0;
-  for (int t = 0; t < T; ++t) {
+  const Drop dr = drop_of(r);
+  const int t0 = r->t_begin, t1 = (r->t_begin || r->t_end) ? r->t_end : T;
+  AVSR_REQUIRE(0 <= t0 && t0 <= t1 && t1 <= T, "rnn: bad step range [%d, %d) of %d", t0, t1, T);
+  if (t0 == 0) AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->c0, H, cbuf[0], H, B, H);
+  int cur = t0 & 1;  // the cell state of step t sits in cbuf[t & 1] (ranged calls continue where the last one stopped)
+  for (int t = t0; t < t1; ++t) {
     const float* S_t = r->S + (size_t)t * B * SW;
     float* S_n = r->S + (size_t)(t + 1) * B * SW;
     float* gates_t = r->gates + (size_t)t * B * 4 * H;
@@ -257,17 +301,17 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
     }
     float* out_h = (r->output_attention && r->n_mech > 0) ? nullptr : r->out + (size_t)t * B * H;
     AVSR_LAUNCH(lstm_point_fwd_kernel, pw_grid, 256, 0, st, t, B, H, gates_t, rec, r->len, cbuf[cur], S_t + At, SW,
-                cbuf[cur ^ 1], S_n + At, SW, r->craw + (size_t)t * B * H, out_h, hc, rnd);
+                cbuf[cur ^ 1], S_n + At, SW, r->craw + (size_t)t * B * H, out_h, hc, rnd, dr);
     cur ^= 1;
     int off = 0;
     for (int k = 0; k < r->n_mech; ++k) {
       const AvsrAttnMech& m = r->mech[k];
       const bool luong = m.kind <= AVSR_ATTN_SCALED_LUONG;
-      const float* q = S_n + At;
-      int ldq = SW;
+      const float* q = hc.p[k];  // the query is the cell OUTPUT (= the state h unless dropout separates them)
+      int ldq = hc.ld[k];
       if (!luong) {
         float* pq_t = m.pq + (size_t)t * B * m.A;
-        AVSR_TRY(gemm(st, 0, 0, B, m.A, H, S_n + At, SW, m.Wq, m.A, pq_t, m.A, 0.0f, nullptr));
+        AVSR_TRY(gemm(st, 0, 0, B, m.A, H, hc.p[k], hc.ld[k], m.Wq, m.A, pq_t, m.A, 0.0f, nullptr));
         q = pq_t;
         ldq = m.A;
       }
@@ -279,9 +323,13 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
     if (r->output_attention && r->n_mech > 0)
       AVSR_LAUNCH(emit_attention_kernel, cdiv((long long)B * At, 256), 256, 0, st, t, B, At, SW, r->len, S_n,
                   r->out + (size_t)t * B * At);
+    if (dr.thr_in && At > 0)
+      AVSR_LAUNCH(drop_attention_kernel, cdiv((long long)B * At, 256), 256, 0, st, t + 1, B, At, SW, S_n, rnd, dr);
   }
-  if (r->cT) AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, cbuf[cur], H, r->cT, H, B, H);
-  if (r->hT) AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->S + (size_t)T * B * SW + At, SW, r->hT, H, B, H);
+  if (t1 == T) {
+    if (r->cT) AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, cbuf[cur], H, r->cT, H, B, H);
+    if (r->hT) AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->S + (size_t)T * B * SW + At, SW, r->hT, H, B, H);
+  }
   return 0;
 }
 
@@ -292,7 +340,9 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   int At, maxHD, maxA, maxTm;
   AVSR_TRY(check_common(r, &At, &maxHD, &maxA, &maxTm));
   const int T = r->T, B = r->B, H = r->H, SW = At + H;
-  if (r->n_mech == 0 && tensor_cores_enabled()) {
+  const bool stepwise = stepwise_only(r);
+  AVSR_REQUIRE(!(r->t_begin || r->t_end), "rnn bwd: step ranges are a forward-only feature");
+  if (r->n_mech == 0 && tensor_cores_enabled() && !stepwise) {
     // reverse-time recurrence in one persistent cluster kernel
     int rc = lstm_persist4_bwd(st, r);
     if (rc < 0) {
@@ -308,7 +358,7 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   const bool oa = r->output_attention && r->n_mech > 0;
   const int rnd = tensor_cores_enabled();
   WorkLayout wl = work_layout(B, H, At, maxHD, maxA, maxTm);
-  if (r->n_mech == 1 && rnd && T > 1 && !getenv("AVSR_NO_ATTN_PERSIST")) {
+  if (r->n_mech == 1 && rnd && T > 1 && !stepwise && !getenv("AVSR_NO_ATTN_PERSIST")) {
     AVSR_REQUIRE(r->mech[0].ds && r->mech[0].dhc, "rnn bwd: mechanism scratch ds / dhc missing");
     const int rc = attn_persist_bwd(st, r, r->work + wl.persist);  // needs the scratch attn_persist_fwd left
     if (rc >= 0) return rc;
@@ -318,6 +368,7 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   const int qw = maxA > H ? maxA : H;
   float* dq[2] = {r->work + wl.dq, r->work + wl.dq + (size_t)B * qw};
   const int pw_grid = cdiv((long long)B * H, 256);
+  const Drop dr = drop_of(r);
   AVSR_LAUNCH(copy2d_kernel, cdiv((long long)B * SW, 256), 256, 0, st, (const float*)nullptr, 0, dS[0], SW, B, SW);
   AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->dhT, H, dS[0] + At, SW, B, H);
   AVSR_LAUNCH(copy2d_kernel, pw_grid, 256, 0, st, r->dcT, H, dcb[0], H, B, H);
@@ -325,13 +376,12 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
     AVSR_REQUIRE(r->mech[k].ds && r->mech[k].dhc, "rnn bwd: mechanism scratch ds / dhc missing");
   int cur = 0;
   for (int t = T - 1; t >= 0; --t) {
-    const float* S_n = r->S + (size_t)(t + 1) * B * SW;
     float* dZ_t = r->dZ + (size_t)t * B * 4 * H;
     DhSrc extra = {{nullptr, nullptr, nullptr, nullptr}, {0, 0, 0, 0}};
     if (r->n_mech > 0) {
       float* dA_t = r->dA + (size_t)t * B * At;
       AVSR_LAUNCH(attn_bwd_prep_kernel, cdiv((long long)B * At, 256), 256, 0, st, t, B, At, SW, r->len, dS[cur],
-                  (oa && r->dout) ? r->dout + (size_t)t * B * At : nullptr, dA_t, rnd);
+                  (oa && r->dout) ? r->dout + (size_t)t * B * At : nullptr, dA_t, rnd, dr);
       int off = 0;
       for (int k = 0; k < r->n_mech; ++k) {
         const AvsrAttnMech& m = r->mech[k];
@@ -340,8 +390,8 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
         // d[h | ctx] = dA_m @ Wl^T   (kept for all steps: dvalues is formed after the loop)
         float* dHC_t = m.dhc + (size_t)t * B * HD;
         AVSR_TRY(gemm(st, 0, 1, B, HD, m.A, dA_t + off, At, m.Wl, m.A, dHC_t, HD, 0.0f, nullptr));
-        const float* q = luong ? S_n + At : m.pq + (size_t)t * B * m.A;
-        const int ldq = luong ? SW : m.A;
+        const float* q = luong ? m.hc + (size_t)t * B * HD : m.pq + (size_t)t * B * m.A;
+        const int ldq = luong ? HD : m.A;
         float* dq_out = luong ? dq[k] : m.dpq + (size_t)t * B * m.A;
         AVSR_TRY(attn_bwd_step(st, m.kind, t, r->len, m.Tm, B, m.Dm, m.A, q, ldq, m.keys, m.values, m.mem_len, m.v,
                                m.g, m.bias, m.align + (size_t)t * B * m.Tm, dHC_t + H, HD, dq_out, m.A,
@@ -357,7 +407,7 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
     AVSR_LAUNCH(lstm_point_bwd_kernel, pw_grid, 256, 0, st, t, B, H, At, r->gates + (size_t)t * B * 4 * H,
                 r->craw + (size_t)t * B * H, t > 0 ? r->craw + (size_t)(t - 1) * B * H : nullptr, r->c0, r->len,
                 (oa || !r->dout) ? nullptr : r->dout + (size_t)t * B * H, dS[cur], dcb[cur], extra, dZ_t, dS[cur ^ 1],
-                dcb[cur ^ 1], rnd);
+                dcb[cur ^ 1], rnd, dr);
     // [datt_{t-1} | dh_{t-1}] += dZ_t @ Wrec^T
     AVSR_TRY(gemm(st, 0, 1, B, SW, 4 * H, dZ_t, 4 * H, r->Wrec, 4 * H, dS[cur ^ 1], SW, 1.0f, nullptr));
     cur ^= 1;

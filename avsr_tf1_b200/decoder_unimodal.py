@@ -51,13 +51,18 @@ class Seq2SeqUnimodalDecoder(object):
         self._EOS_ID = reverse_dict['EOS']
         self._sampling_probability_outputs = hparams.sampling_probability_outputs
         self._vocab_size = len(hparams.unit_dict) - 1  # decoder_unimodal.py:49
-        if mode == 'train' and self._sampling_probability_outputs > 0.0:
-            raise NotImplementedError(
-                'ScheduledEmbeddingTrainingHelper sampling (decoder_unimodal.py:304-309) draws from TF Philox '
-                'streams and is not implemented on the B200 path yet; pass sampling_probability_outputs=0.0')
         self._mem_depths = list(encoder_output_depths)
         self._init_embedding()
         self._init_decoder()
+        # ScheduledEmbeddingTrainingHelper(sampling_probability) (decoder_unimodal.py:304-309): TF's Philox draws are
+        # not reproducible; the library's counter-based generator stands in (streams: +0 Bernoulli select, +1 draw)
+        self._ss_thr, self._ss_stream = 0, None
+        if mode == 'train' and self._sampling_probability_outputs > 0.0:
+            p = float(self._sampling_probability_outputs)
+            self._ss_thr = max(1, min(int(p * 4294967296.0), 4294967295))
+            self._ss_stream = ctx.new_stream(2)
+            ctx.streams['Decoder/sampling'] = self._ss_stream
+        self.sample_ids = None  # [T,B] int32 device: ids drawn by the helper (-1 = ground truth kept), last train step
         self.inference_predicted_ids = None
         self.beam_search_output = None
 
@@ -114,17 +119,44 @@ class Seq2SeqUnimodalDecoder(object):
         ctx = self._ctx
         B = labels.shape[0]
         init = self._initial_state_fwd(encoder_states)
-        self._ids = dec_in_ids.reshape(-1)
-        x = ops.empty(T, B, self._E)
-        ops.embedding_fwd(ctx.w(self._embedding), self._ids, x)
-        out = self._cell.forward(x, labels_len, memories=memories, init=init)
         O = self._cell.out_dim
-        self._out = out
         self._logits = ops.empty(T, B, self._vocab_size)
-        ops.gemm(out.view(T * B, O), ctx.p(self._Wd), self._logits.view(T * B, self._vocab_size), bias=ctx.p(self._bd))
+        if self._ss_thr:
+            out = self._forward_train_sampled(memories, init, dec_in_ids, labels_len, T, B)
+        else:
+            self._ids = dec_in_ids.reshape(-1)
+            x = ops.empty(T, B, self._E)
+            ops.embedding_fwd(ctx.w(self._embedding), self._ids, x)
+            out = self._cell.forward(x, labels_len, memories=memories, init=init)
+            ops.gemm(out.view(T * B, O), ctx.p(self._Wd), self._logits.view(T * B, self._vocab_size),
+                     bias=ctx.p(self._bd))
+        self._out = out
         self._dlogits = torch.empty_like(self._logits)
         ops.seq_loss(self._logits, labels, labels_len, inv_denom, loss_sum, self._dlogits)
         return self._logits
+
+    def _forward_train_sampled(self, memories, init, dec_in_ids, labels_len, T, B):
+        """Scheduled sampling: step t's logits decide (per row, with probability p) the input of step t + 1, so the
+        recurrence advances one step at a time (AvsrRnnSeq step ranges) with the output layer and the draw in between.
+        The ids actually fed are kept for the embedding gradient; no gradient flows through the draws."""
+        ctx, cell = self._ctx, self._cell
+        V = self._vocab_size
+        used = torch.empty((T, B), dtype=torch.int32, device='cuda')
+        used[0].copy_(dec_in_ids[0])
+        self.sample_ids = torch.full((T, B), -1, dtype=torch.int32, device='cuda')
+        cell.begin_stepwise(T, B, labels_len, memories, init)
+        table = ctx.w(self._embedding)
+        for t in range(T):
+            x_t = ops.empty(B, self._E)
+            ops.embedding_fwd(table, used[t], x_t)
+            out_t = cell.stepwise_step(t, x_t)
+            ops.gemm(out_t, ctx.p(self._Wd), self._logits[t], bias=ctx.p(self._bd))
+            if t + 1 < T:
+                ops.sched_sample(self._logits[t], ctx.rng, self._ss_stream, t, self._ss_thr, dec_in_ids[t + 1],
+                                 used[t + 1], self.sample_ids[t])
+        self._ids = used.reshape(-1)
+        self.decoder_input_ids = used  # [T,B]: what the decoder was fed (parity probe)
+        return cell.end_stepwise()
 
     def backward_train(self):
         """Returns ([dmemory...], [(dc, dh) per encoder state])."""

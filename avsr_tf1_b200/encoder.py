@@ -68,7 +68,7 @@ class Seq2SeqEncoder(object):
                 weight_sharing=hp.encoder_weight_sharing if not sub else False))
             ops_, in_dim = [], self._F
             for prefix, cell in zip(_layer_prefixes(scope, L, sub), cells):
-                ops_.append(LSTMLayerOp(ctx, prefix, in_dim, cell.num_units))
+                ops_.append(LSTMLayerOp(ctx, prefix, in_dim, cell.num_units, drop=ctx.drop_state(cell, prefix)))
                 in_dim = cell.num_units
             return ops_
 
@@ -101,10 +101,25 @@ class Seq2SeqEncoder(object):
         train = self._mode == 'train'
         if self._bn is not None:
             # tf32-rounded in tensor-core mode; xhat is only stored if the gradient wrt the raw features is wanted
-            return self._bn.forward(inputs, train, batch_major=batch_major, keep_xhat=self.input_gradient)
+            # (or if layer 0 drops its input: then dgamma / dbeta need the gradient wrt the normalised features)
+            return self._bn.forward(inputs, train, batch_major=batch_major,
+                                    keep_xhat=self.input_gradient or self._layer0_drops_input())
         if batch_major:
             inputs = ops.transpose01(inputs)
         return ops.round_tf32(inputs) if ops.tensor_cores_enabled() else inputs
+
+    def _layer0_ops(self):
+        first = [self._fw[0]] if self._fw else [self._top]  # (an AV-Align encoder of one layer: the attention cell)
+        return first + ([self._bw[0]] if self._bw is not None else [])
+
+    def _layer0_drops_input(self):
+        return self._mode == 'train' and any(op.drop is not None and op.drop.thr_in for op in self._layer0_ops())
+
+    def _round_outputs(self, out, op):
+        """Operand view of a stack's outputs: with a DropoutWrapper the layer hands back its exact outputs."""
+        if op.drop is not None and ops.tensor_cores_enabled():
+            return ops.round_tf32(out)
+        return op.operand
 
     def forward(self, inputs, inputs_len, batch_major=False):
         """inputs [T,B,F] frame-major (or [B,T,F] with batch_major=True); returns EncoderData."""
@@ -117,7 +132,7 @@ class Seq2SeqEncoder(object):
             cur_op = op.operand
         if self._bw is None:
             self._outputs = cur
-            self._outputs_op = cur_op
+            self._outputs_op = self._round_outputs(cur, self._fw[-1])
             self._final = self._fw[-1].final
         else:
             curb, curb_op = None, ops.reverse_sequence(x, inputs_len)
@@ -153,6 +168,7 @@ class Seq2SeqEncoder(object):
         if self._bw is None:
             d = doutputs if doutputs is not None else ops.zeros(*self._outputs.shape)
             n = len(self._fw)
+            need_dx = need_dx or self._layer0_drops_input()
             for i in range(n - 1, -1, -1):
                 need = (i > 0) or need_dx
                 d = self._fw[i].backward(d, dfinal_state if i == n - 1 else None, need_dx=need)
@@ -175,6 +191,7 @@ class Seq2SeqEncoder(object):
             df = doutputs[:, :, :H].contiguous()
             db = ops.reverse_sequence(doutputs[:, :, H:].contiguous(), self._lens)
             n = len(self._fw)
+            need_dx = need_dx or self._layer0_drops_input()
             for i in range(n - 1, -1, -1):
                 need = (i > 0) or need_dx
                 df = self._fw[i].backward(df, dsf if i == n - 1 else None, need_dx=need)
@@ -192,12 +209,14 @@ class Seq2SeqEncoder(object):
         normalised features is only formed when the caller asks for the gradient wrt the raw features."""
         if self._bn is None:
             return dx
+        if self._layer0_drops_input() and not self.input_gradient:
+            self._bn.backward(dx, need_dx=False)  # dx: gradient wrt the normalised features (input dropout undone)
+            return None
         if need_dx:
             if not self.input_gradient:
                 raise Exception('encoder: set input_gradient = True before forward to get the gradient wrt the features')
             return self._bn.backward(dx, need_dx=True)
-        first = [self._fw[0]] if self._fw else [self._top]  # (an AV-Align encoder of one layer: the attention cell)
-        self._bn.backward_from_layer0(first + ([self._bw[0]] if self._bw is not None else []))
+        self._bn.backward_from_layer0(self._layer0_ops())
         return None
 
 
@@ -222,8 +241,8 @@ class AttentiveEncoder(Seq2SeqEncoder):
             dropout_probability=hp.audio_encoder_dropout_probability, mode=self._mode, as_list=True))
         self._fw, in_dim = [], self._F
         for k in range(L - 1):
-            self._fw.append(LSTMLayerOp(ctx, f'{scope}/Encoder/multi_rnn_cell/cell_{k}/lstm_cell', in_dim,
-                                        cells[k].num_units))
+            prefix = f'{scope}/Encoder/multi_rnn_cell/cell_{k}/lstm_cell'
+            self._fw.append(LSTMLayerOp(ctx, prefix, in_dim, cells[k].num_units, drop=ctx.drop_state(cells[k], prefix)))
             in_dim = cells[k].num_units
         wrap = f'{scope}/Encoder/multi_rnn_cell/cell_{L - 1}/attention_wrapper' if L > 1 \
             else f'{scope}/Encoder/attention_wrapper'
@@ -249,7 +268,8 @@ class AttentiveEncoder(Seq2SeqEncoder):
         self._outputs = self._top.forward(
             self._lower_out_op, self._lens,
             memories=[(attended_memory, attended_memory_length, attended_memory_operand)])
-        self._outputs_op = self._top.operand
+        self._outputs_op = self._round_outputs(self._outputs, self._top) if not self._top.output_attention \
+            else self._top.operand
         self._final = self._top.final  # wrapper stripped: cell state only (encoder.py:314-330)
         self.attention_alignment = self._top.bufs[0].align  # [T_audio, B, T_video]
         self.attention_contexts = self._top.bufs[0].hc      # [T_audio, B, H + Dm]
@@ -268,6 +288,7 @@ class AttentiveEncoder(Seq2SeqEncoder):
         return d, dmem[0]
 
     def backward_lower(self, d, need_dx=False):
+        need_dx = need_dx or self._layer0_drops_input()
         for i in range(len(self._fw) - 1, -1, -1):
             need = (i > 0) or need_dx
             d = self._fw[i].backward(d, None, need_dx=need)

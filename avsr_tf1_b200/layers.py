@@ -23,6 +23,23 @@ class BuildContext:
         self.world_size = 1
         self.grad_scale = 1.0  # power of two ~ number of target tokens (set per step by Seq2SeqModel)
         self.allreduce = None  # callable(tensor) -> None (in-place sum), set by Seq2SeqModel under DP
+        self.rng = None  # device int32[2] {seed, step}: counter-based generator of dropout / scheduled sampling
+        self._streams = 0
+        self.streams = {}  # cell name (variable prefix) -> first stream id: lets the oracle regenerate every mask
+
+    def new_stream(self, n=4):
+        """Reserves n consecutive stream ids of the generator (one independent random sequence each)."""
+        base = 8 + self._streams
+        self._streams += n
+        return base
+
+    def drop_state(self, cell, name):
+        """DropState of a cell spec built by cells.build_rnn_layers, or None when its DropoutWrapper is off."""
+        if not getattr(cell, 'use_dropout', False):
+            return None
+        ds = DropState(self, cell.dropout_probability)
+        self.streams[name] = ds.stream
+        return ds
 
     def declare(self, name, shape, init, trainable=True):
         if any(s.name == name for s in self.specs):
@@ -39,6 +56,36 @@ class BuildContext:
     def w(self, name):
         """Parameter as the operand of a matrix product (tf32-rounded copy in tensor-core mode)."""
         return self.store.w(name, ops.tensor_cores_enabled())
+
+
+class DropState:
+    """DropoutWrapper(input_keep, state_keep, output_keep) of one cell (cells.py:46-54), non-variational.
+    Streams: +0 attention part of the cell input, +1 recurrent h, +2 cell output (these three are applied inside the
+    recurrent op), +3 the x part of the cell input (applied to the whole sequence before the x-projection)."""
+
+    def __init__(self, ctx: 'BuildContext', keep_probs):
+        self.ctx = ctx
+        self.stream = ctx.new_stream(4)
+        self.thr_in, self.thr_state, self.thr_out = (ops.keep_threshold(p) for p in keep_probs)
+
+    @property
+    def any(self):
+        return bool(self.thr_in or self.thr_state or self.thr_out)
+
+    @property
+    def rng(self):
+        return self.ctx.rng
+
+    def drop_input(self, x):
+        """x part of the cell input -> product operand (tf32-rounded in tensor-core mode)."""
+        if self.thr_in:
+            return ops.dropout(x, self.rng, self.stream + 3, self.thr_in, round_out=True)
+        return ops.round_tf32(x) if ops.tensor_cores_enabled() else x
+
+    def drop_input_grad(self, dx):
+        if self.thr_in and dx is not None:
+            ops.dropout(dx, self.rng, self.stream + 3, self.thr_in, out=dx)
+        return dx
 
 
 class BatchNormInput:
@@ -121,25 +168,30 @@ class BatchNormInput:
 class LSTMLayerOp:
     """One LSTMCell layer under dynamic_rnn (cells.py:14-18, encoder.py:80)."""
 
-    def __init__(self, ctx: BuildContext, prefix: str, in_dim: int, H: int):
+    def __init__(self, ctx: BuildContext, prefix: str, in_dim: int, H: int, drop: 'DropState' = None):
         self.ctx, self.I, self.H = ctx, in_dim, H
+        self.drop = drop
         self.kernel = ctx.declare(prefix + '/kernel', (in_dim + H, 4 * H), 'lstm_kernel')
         self.bias = ctx.declare(prefix + '/bias', (4 * H,), 'zeros')
 
     def forward(self, x: torch.Tensor, lens: torch.Tensor):
         """x [T,B,I] must be a product operand (tf32-rounded in tensor-core mode).  Returns the exact
         outputs (zero past the length); `self.operand` is the same sequence as the NEXT product's operand
-        (rounded h; rows past the length carry the last state instead of zero, which no consumer reads)."""
+        (rounded h; rows past the length carry the last state instead of zero, which no consumer reads).
+        With a DropoutWrapper: x is the un-dropped layer input (any precision), the outputs carry the output
+        dropout and `operand` is the outputs (the consumer drops / rounds them itself)."""
         T, B, I = x.shape
         H = self.H
         W, b = self.ctx.w(self.kernel), self.ctx.p(self.bias)
+        if self.drop is not None:
+            x = self.drop.drop_input(x)
         gates = ops.empty(T, B, 4 * H)
         ops.gemm(x.reshape(T * B, I), W[:I], gates.view(T * B, 4 * H), bias=b)
         self.x = x
-        self.rnn = ops.RnnSeq(T, B, H, lens, gates, W[I:])
+        self.rnn = ops.RnnSeq(T, B, H, lens, gates, W[I:], drop=self.drop)
         out = self.rnn.forward()
-        self.final = (self.rnn.cT, self.rnn.hT)
-        self.operand = self.rnn.S[1:]
+        self.final = (self.rnn.cT, self.rnn.hT)  # (with state dropout hT is the dropped h, as in the reference)
+        self.operand = self.rnn.S[1:] if self.drop is None else out
         return out
 
     def backward(self, dout, dstate=None, need_dx=True):
@@ -156,6 +208,8 @@ class LSTMLayerOp:
         if need_dx:
             dx = ops.empty(T, B, I)
             ops.gemm(dZ2, W[:I], dx.view(T * B, I), tb=True)
+            if self.drop is not None:
+                self.drop.drop_input_grad(dx)
         self.rnn = None
         return dx
 
@@ -188,8 +242,10 @@ class MechDef:
 class AttnLSTMOp:
     """AttentionWrapper(LSTMCell) under dynamic_rnn / dynamic_decode (attention.py:132-191)."""
 
-    def __init__(self, ctx: BuildContext, wrap_prefix: str, in_dim: int, H: int, mechs: Sequence[MechDef]):
+    def __init__(self, ctx: BuildContext, wrap_prefix: str, in_dim: int, H: int, mechs: Sequence[MechDef],
+                 drop: 'DropState' = None):
         self.ctx, self.Dx, self.H, self.mechs = ctx, in_dim, H, list(mechs)
+        self.drop = drop  # DropoutWrapper of the wrapped cell: acts on concat(x, attention), the state h, the cell output
         self.At = sum(m.A for m in self.mechs)
         self.kernel = ctx.declare(wrap_prefix + '/lstm_cell/kernel', (in_dim + self.At + H, 4 * H), 'lstm_kernel')
         self.bias = ctx.declare(wrap_prefix + '/lstm_cell/bias', (4 * H,), 'zeros')
@@ -225,17 +281,55 @@ class AttnLSTMOp:
         H = self.H
         ctx = self.ctx
         W, b = ctx.w(self.kernel), ctx.p(self.bias)
+        if self.drop is not None:
+            x = self.drop.drop_input(x)
         gates = ops.empty(T, B, 4 * H)
         ops.gemm(x.reshape(T * B, Dx), W[:Dx], gates.view(T * B, 4 * H), bias=b)
         self.x = x
         self.bufs = mech_bufs if mech_bufs is not None else self.prepare_memories(memories)
         c0, h0 = init if init is not None else (None, None)
-        self.rnn = ops.RnnSeq(T, B, H, lens, gates, W[Dx:], self.bufs, self.output_attention, c0=c0, h0=h0)
+        self.rnn = ops.RnnSeq(T, B, H, lens, gates, W[Dx:], self.bufs, self.output_attention, c0=c0, h0=h0,
+                              drop=self.drop)
         out = self.rnn.forward()
         self.final = (self.rnn.cT, self.rnn.hT)
         # operand view of the outputs: the attention vectors are already tf32-rounded (and masked) when they
-        # are the output; otherwise the rounded h columns of the state rows
-        self.operand = out if self.output_attention else self.rnn.S[1:, :, self.At:]
+        # are the output; otherwise the rounded h columns of the state rows (with dropout the state rows hold the
+        # state-dropped h, not the emitted one: the consumer rounds the outputs itself)
+        self.operand = out if (self.output_attention or self.drop is not None) else self.rnn.S[1:, :, self.At:]
+        return out
+
+    def begin_stepwise(self, T, B, lens, memories, init=None):
+        """Scheduled sampling (decoder_unimodal.py:304-309): the decoder inputs are only known step by step.  Sets up
+        the whole-sequence buffers; `stepwise_step(t, x_t)` then advances one step and returns that step's output."""
+        H, Dx, ctx = self.H, self.Dx, self.ctx
+        self.x = ops.empty(T, B, Dx)
+        self._gates = ops.empty(T, B, 4 * H)
+        self.bufs = self.prepare_memories(memories)
+        c0, h0 = init if init is not None else (None, None)
+        self.rnn = ops.RnnSeq(T, B, H, lens, self._gates, ctx.w(self.kernel)[Dx:], self.bufs, self.output_attention,
+                              c0=c0, h0=h0, drop=self.drop)
+
+    def stepwise_step(self, t, x_t):
+        """x_t [B,Dx] un-dropped decoder input of step t."""
+        W, b = self.ctx.w(self.kernel), self.ctx.p(self.bias)
+        B, Dx, H = x_t.shape[0], self.Dx, self.H
+        xt = self.x[t]
+        if self.drop is not None and self.drop.thr_in:
+            # element index of the whole-sequence mask: (t*B + b)*Dx + column -> offset the flat index by t*B*Dx
+            ops.dropout(x_t, self.drop.rng, self.drop.stream + 3, self.drop.thr_in, round_out=True, out=xt,
+                        first=t * B * Dx)
+        elif ops.tensor_cores_enabled():
+            ops.round_tf32(x_t, xt)
+        else:
+            xt.copy_(x_t)
+        ops.gemm(xt, W[:Dx], self._gates[t].view(B, 4 * H), bias=b)
+        self.rnn.forward_range(t, t + 1)
+        return self.rnn.out[t]
+
+    def end_stepwise(self):
+        self.final = (self.rnn.cT, self.rnn.hT)
+        out = self.rnn.out
+        self.operand = out if (self.output_attention or self.drop is not None) else self.rnn.S[1:, :, self.At:]
         return out
 
     def step(self, x1, active, mech_bufs, state):
@@ -292,6 +386,8 @@ class AttnLSTMOp:
         if need_dx:
             dx = ops.empty(T, B, Dx)
             ops.gemm(dZ2, W[:Dx], dx.view(T * B, Dx), tb=True)
+            if self.drop is not None:
+                self.drop.drop_input_grad(dx)
         dmem = []
         for k, (md, mb) in enumerate(zip(self.mechs, self.bufs)):
             v2 = mb.values_op.reshape(mb.Tm * B, mb.Dm)

@@ -205,6 +205,32 @@ def normed_v_bwd(v, g, dveff, dv, dg):
                                         dv.data_ptr(), dg.data_ptr()))
 
 
+def keep_threshold(keep_prob) -> int:
+    """keep probability -> the uint32 threshold of the counter-based generator (0 = never drop)."""
+    keep_prob = float(keep_prob)
+    if keep_prob >= 1.0:
+        return 0
+    if not keep_prob > 0.0:
+        raise ValueError('keep probability must be in (0, 1]')
+    return max(1, min(int(keep_prob * 4294967296.0), 4294967295))
+
+
+def dropout(x, rng, stream_id, thr, round_out=False, out=None, first=0):
+    """tf.nn.dropout with the library's generator (include/avsr_b200.h avsr_dropout); the same call maps dy -> dx.
+    `first`: mask index of x's first element (a slice of a larger masked tensor)."""
+    _chk_f32(x)
+    y = torch.empty_like(x) if out is None else out
+    check(_lib.load().avsr_dropout(_stream(), x.data_ptr(), x.numel(), int(first), rng.data_ptr(), int(stream_id),
+                                   int(thr), int(bool(round_out)), y.data_ptr()))
+    return y
+
+
+def sched_sample(logits, rng, stream_id, t, thr_p, true_next, next_ids, sampled):
+    B, V = logits.shape
+    check(_lib.load().avsr_sched_sample(_stream(), logits.data_ptr(), B, V, rng.data_ptr(), int(stream_id), int(t),
+                                        int(thr_p), true_next.data_ptr(), next_ids.data_ptr(), sampled.data_ptr()))
+
+
 def greedy_pick(logits, eos, finished, sample_out, next_ids):
     B, V = logits.shape
     check(_lib.load().avsr_greedy_pick(_stream(), logits.data_ptr(), B, V, eos, finished.data_ptr(),
@@ -251,8 +277,10 @@ class RnnSeq:
     """One dynamic_rnn / dynamic_decode loop (see AvsrRnnSeq in include/avsr_b200.h)."""
 
     def __init__(self, T, B, H, lens, gates, Wrec, mechs: Sequence[MechBuffers] = (), output_attention=False,
-                 c0=None, h0=None, s0=None):
+                 c0=None, h0=None, s0=None, drop=None):
         self.T, self.B, self.H = T, B, H
+        self.drop = drop  # DropState (layers.py) or None: DropoutWrapper masks applied inside the loop
+        self.stepwise = False
         self.lens, self.gates, self.Wrec, self.c0 = lens, gates, Wrec, c0
         self.mechs = list(mechs)
         self.oa = bool(output_attention) and len(self.mechs) > 0
@@ -296,12 +324,26 @@ class RnnSeq:
             m.fill(r.mech[k])
         r.work = _p(self.work)
         r.grad_scale = float(self.grad_scale)
+        if self.drop is not None:
+            d = self.drop
+            r.rng, r.drop_stream = _p(d.rng), d.stream
+            r.thr_in, r.thr_state, r.thr_out = d.thr_in, d.thr_state, d.thr_out
+        r.stepwise = int(self.stepwise)
         for k, v in bw.items():
             setattr(r, k, _p(v))
         return r
 
     def forward(self):
         r = self._desc()
+        check(_lib.load().avsr_rnn_seq_fwd(_stream(), C.byref(r)))
+        return self.out
+
+    def forward_range(self, t_begin, t_end):
+        """Steps [t_begin, t_end) only (step-wise kernels): scheduled sampling interleaves its draws with the
+        recurrence.  The backward pass of such a forward runs step-wise too."""
+        self.stepwise = True
+        r = self._desc()
+        r.t_begin, r.t_end = int(t_begin), int(t_end)
         check(_lib.load().avsr_rnn_seq_fwd(_stream(), C.byref(r)))
         return self.out
 

@@ -103,8 +103,12 @@ class Seq2SeqModel(object):
         self.use_cuda_graph = False  # opt-in: train_step replays one captured graph per batch shape
         self.launches_last_step = 0
         self.h2d_bytes = 0
+        # words {seed, training step} of the counter-based generator behind dropout and scheduled sampling
+        # (graph-replay safe: written by _set_step_scalars outside the captured region)
+        self.rng_seed = int(hparams.kwargs.get('random_seed', seed))
         if self.store.flat.is_cuda:
             self._scal_dev = torch.zeros(2, dtype=torch.float32, device='cuda')
+            self._ctx.rng = torch.zeros(2, dtype=torch.int32, device='cuda')
 
     # ---- construction (seq2seq.py:30-126) ---------------------------------------
     def _make_encoders(self):
@@ -432,6 +436,16 @@ class Seq2SeqModel(object):
         # pageable source: the driver stages it at call time, so the host may run ahead of the GPU safely
         self._scal_dev.copy_(torch.tensor([self._inv_denom, lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)],
                                           dtype=torch.float32))
+        self._ctx.rng.copy_(torch.tensor(self.rng_words(), dtype=torch.int32))
+
+    def rng_words(self):
+        """(seed, step) of the generator for the CURRENT training step (31-bit so they fit the int32 device words)."""
+        return (self.rng_seed & 0x7FFFFFFF, self._global_step & 0x7FFFFFFF)
+
+    @property
+    def random_streams(self):
+        """cell name -> first generator stream (what the oracle needs to regenerate the masks)."""
+        return dict(self._ctx.streams)
 
     def _step_body(self):
         self._prep()

@@ -159,6 +159,18 @@ typedef struct AvsrRnnSeq {
   float* work;          /* scratch, >= avsr_rnn_work_floats() floats; backward must see what forward left */
   float grad_scale;     /* power of two ~ 1/|gradient scale| (e.g. the token count): fp16 tensor-core operand
                            scaling of the persistent attention backward kernel; 0 = 1 */
+  /* DropoutWrapper(LSTMCell) inside the loop (cells.py:46-54; non-variational: fresh masks every step).  The masks
+   * are not stored: forward and backward regenerate them from the counter-based generator of avsr_dropout
+   * (element (t, b, column) of stream drop_stream + {0: attention part of the cell input, 1: recurrent state h,
+   * 2: cell output}).  The x part of the cell input is dropped by the caller (avsr_dropout on the sequence) before
+   * the x-projection.  thr = keep probability * 2^32 (0 = keep everything, i.e. that dropout is off). */
+  const uint32_t* rng;  /* [2] device words {seed, step counter}; NULL = no dropout */
+  uint32_t drop_stream;
+  uint32_t thr_in, thr_state, thr_out;
+  /* step range [t_begin, t_end) of this call; 0,0 = the whole sequence.  A range forces the step-wise kernels: it
+   * is how ScheduledEmbeddingTrainingHelper (decoder_unimodal.py:304-309) interleaves sampling with the recurrence.
+   * stepwise != 0 forces them for a whole-sequence call too (the backward of a ranged forward). */
+  int t_begin, t_end, stepwise;
 } AvsrRnnSeq;
 
 /* At = sum of mechanism A; maxHD = max(H+Dm); maxA = max A; maxTm = max memory length (0,0,0,0 without attention) */
@@ -172,6 +184,26 @@ int avsr_rnn_seq_bwd(avsr_stream_t stream, const AvsrRnnSeq* r);
 int avsr_normed_v_fwd(avsr_stream_t stream, const float* v, const float* g, int A, float* veff);
 int avsr_normed_v_bwd(avsr_stream_t stream, const float* v, const float* g, const float* dveff, int A, float* dv,
                       float* dg);
+
+/* ---- randomness of the training graph -----------------------------------------
+ * TF's Philox streams cannot be reproduced, so the reference's masks and samples are not bit-reproducible by
+ * anyone; what is kept is their distribution and where they act.  One counter-based generator serves all of it:
+ * word(seed, step, stream, hi, lo) = two rounds of the murmur3 32-bit finaliser over the five counters
+ * (common.cuh avsr_rand_u32; restated in oracle/avsr_oracle.py rand_u32 so masks are bit-equal in the parity tests).
+ * rng = device words {seed, step}: the host bumps `step` once per training step (graph-replay safe). */
+/* inverted dropout tf.nn.dropout (DropoutWrapper cells.py:46-54): y[i] = word(first + i) < thr ? x[i] * 2^32 / thr : 0
+ * for i < n (first + n <= 2^32) of stream `stream_id` (hi = 0, lo = first + i); `first` lets a step-wise caller
+ * process a slice of a sequence with the mask of the whole-sequence call; in place allowed; the same call maps
+ * dy -> dx.  thr = keep_prob * 2^32 (the exact keep probability is thr / 2^32, so the scaling is unbiased);
+ * round_out: y stored tf32-rounded (it feeds a tensor-core product). */
+int avsr_dropout(avsr_stream_t stream, const float* x, long long n, long long first, const uint32_t* rng,
+                 uint32_t stream_id, uint32_t thr, int round_out, float* y);
+/* ScheduledEmbeddingTrainingHelper.sample + next_inputs (decoder_unimodal.py:304-309): for row b,
+ * with probability p (thr_p = p * 2^32; stream_id, hi = t, lo = b) the next decoder input id is drawn from
+ * Categorical(logits[b,:]) (inverse CDF of the fp32 softmax with the word of stream_id + 1), else it is
+ * true_next[b].  sampled[b] = drawn id or -1 (the helper's sample_ids). */
+int avsr_sched_sample(avsr_stream_t stream, const float* logits, int B, int V, const uint32_t* rng,
+                      uint32_t stream_id, int t, uint32_t thr_p, const int* true_next, int* next_ids, int* sampled);
 
 /* ---- embedding lookup and its gradient (decoder_unimodal.py:170) ------------- */
 int avsr_embedding_fwd(avsr_stream_t stream, const float* table, int V, int E, const int* ids, long long n,

@@ -37,9 +37,19 @@ def config_hparams(cfg: int, units=None, **over):
     return make_hparams(**kw)
 
 
-def oracle_hparams(hp) -> OracleHParams:
+def oracle_hparams(hp, model=None) -> OracleHParams:
+    """model: the product model whose generator words / stream ids the oracle should use (dropout, sampling)."""
     rev = {v: k for k, v in hp.unit_dict.items()}
+    rand = {}
+    if model is not None:
+        if hp.use_dropout:
+            rand['dropout'] = dict(video=hp.video_encoder_dropout_probability,
+                                   audio=hp.audio_encoder_dropout_probability,
+                                   decoder=hp.decoder_dropout_probability)
+        rand.update(sampling_probability_outputs=hp.sampling_probability_outputs, rng=model.rng_words(),
+                    streams=model.random_streams)
     return OracleHParams(
+        **rand,
         architecture=hp.architecture, encoder_type=hp.encoder_type,
         encoder_units_per_layer=hp.encoder_units_per_layer, decoder_units_per_layer=hp.decoder_units_per_layer,
         attention_type=hp.attention_type, embedding_size=hp.embedding_size, vocab_size=len(hp.unit_dict) - 1,

@@ -1,0 +1,180 @@
+"""GPU parity of the training graph's randomness - DropoutWrapper (cells.py:46-54) and
+ScheduledEmbeddingTrainingHelper (decoder_unimodal.py:304-309) - against the oracle.  TF's Philox streams are
+not reproducible, so both sides draw from the same counter-based generator and the comparison is mask for mask."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import avsr_oracle as O
+from tests.helpers import cast_batch, config_hparams, oracle_hparams, synthetic_batch, to_data_sequences
+from tests.test_gpu_model import close, tensor_cores  # noqa: F401  (fixture)
+
+pytestmark = pytest.mark.gpu
+
+KEEP = dict(use_dropout=True, audio_encoder_dropout_probability=(0.9, 0.8, 0.7),
+            video_encoder_dropout_probability=(0.8, 0.9, 0.75), decoder_dropout_probability=(0.85, 0.9, 0.8))
+
+
+def build(cfg, over, B, Ta, Tv, L, seed=2001):
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    hp = config_hparams(cfg, **over)
+    batch = synthetic_batch(hp, B=B, Ta=Ta, Tv=Tv, Fa=80, Fv=128, L=L, ragged=True)
+    ds = to_data_sequences(batch)
+    model = Seq2SeqModel(ds, 'train', hp, seed=seed)
+    return hp, batch, ds, model
+
+
+def oracle_for(hp, model):
+    P = {k: v.astype(np.float64) for k, v in model.store.to_numpy('p').items()}
+    return O.OracleModel(oracle_hparams(hp, model), P)
+
+
+def forward_backward(model, ds):
+    model.feed(ds)
+    model._set_step_scalars()
+    model.forward_backward()
+    model.finish_gradients()
+    return model.fetch_scalars()
+
+
+def check_gradients(model, G_ref, gnorm, tc):
+    G = model.store.to_numpy('g')
+    gn_ref = O.global_norm(G_ref)
+    assert abs(gnorm - gn_ref) <= 5e-3 * gn_ref, (gnorm, gn_ref)
+    gmax = max(np.abs(g).max() for g in G_ref.values())
+    gtol = 1.5e-2 if tc else 1e-3
+    for name, g_ref in G_ref.items():
+        scale = max(np.abs(g_ref).max(), 1e-3 * gmax)
+        err = np.abs(G[name].astype(np.float64) - g_ref).max() / scale
+        assert err <= gtol, f'{name}: gradient scaled error {err:.3e}'
+
+
+def check_states(model, rec, rt):
+    for key, enc in (('video', model._video_encoder), ('audio', model._audio_encoder)):
+        if enc is None or key not in rec['enc']:
+            continue
+        out_ref, (c_ref, h_ref) = rec['enc'][key]
+        d = enc.get_data()
+        close(d.outputs.transpose(0, 1), out_ref, rt, key + ' encoder outputs')
+        close(d.final_state[0], c_ref, rt, key + ' final c')
+        close(d.final_state[1], h_ref, rt, key + ' final h')
+
+
+def test_dropout_op_is_the_oracles_mask():
+    from avsr_tf1_b200 import ops
+    T, B, F = 7, 5, 33
+    x = torch.randn(T, B, F, device='cuda')
+    rng = torch.tensor([1234, 56], dtype=torch.int32, device='cuda')
+    thr = ops.keep_threshold(0.7)
+    y = ops.dropout(x, rng, 11 + 3, thr)
+    spec = O.DropSpec((1234, 56), 11, (0.7, 1.0, 1.0))
+    f = spec.x_factor(B, T, F, np.float32)  # [B,T,F]
+    want = x.cpu().numpy() * f.transpose(1, 0, 2)
+    assert np.array_equal(y.cpu().numpy(), want)
+    kept = float((y != 0).float().mean())
+    assert abs(kept - 0.7) < 0.06
+    # a slice with `first` reproduces the whole-sequence mask (step-wise decoder inputs)
+    y3 = ops.dropout(x[3].contiguous(), rng, 11 + 3, thr, first=3 * B * F)
+    assert torch.equal(y3, y[3])
+    # the same call maps dy -> dx
+    ops.dropout(x, rng, 11 + 3, thr, out=x)
+    assert torch.equal(x, y)
+
+
+CASES = [
+    (1, {}), (2, {}), (3, {}), (4, {}), (5, {}),
+    (1, dict(attention_type=(('bahdanau',), ('bahdanau',)))),
+    (5, dict(attention_type=(('bahdanau',), ('normed_bahdanau',)))),
+    (5, dict(batch_normalisation=False)),
+]
+
+
+@pytest.mark.parametrize('cfg,over', CASES)
+def test_dropout_loss_states_and_gradients(cfg, over, tensor_cores):
+    """Every DropoutWrapper of the graph on, with different keep probabilities per position."""
+    hp, batch, ds, model = build(cfg, dict(KEEP, **over), B=4, Ta=24, Tv=10, L=6)
+    model._global_step = 5  # a non-zero step word
+    om = oracle_for(hp, model)
+    loss_ref, G_ref, rec = om.loss_and_grads(cast_batch(batch, np.float64))
+    loss, gnorm = forward_backward(model, ds)
+    assert abs(loss - loss_ref) <= 1e-3 * abs(loss_ref), (loss, loss_ref)
+    # keep probabilities down to 0.7 scale every tf32 operand rounding error by up to 1/0.7: 2e-3 in tensor-core
+    # mode here; the reference's own 0.9 meets 1e-3 (test_reference_default_training_graph)
+    check_states(model, rec, 2e-3 if tensor_cores else 1e-3)
+    check_gradients(model, G_ref, gnorm, tensor_cores)
+
+
+def test_dropout_masks_change_with_the_step_and_not_in_evaluate_mode():
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    hp, batch, ds, model = build(1, KEEP, B=3, Ta=12, Tv=4, L=4)
+    l0, _ = forward_backward(model, ds)
+    l0b, _ = forward_backward(model, ds)
+    model._global_step = 1
+    l1, _ = forward_backward(model, ds)
+    assert abs(l0 - l0b) <= 1e-6 * abs(l0)  # same step word, same masks (the loss sum uses fp32 atomics)
+    assert abs(l0 - l1) > 1e-4 * abs(l0)    # next step, fresh masks
+    ev = Seq2SeqModel(ds, 'evaluate', hp, share_params_with=model)
+    a = ev.encode(ds)['audio'].outputs.clone()
+    b = ev.encode(ds)['audio'].outputs
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('cfg,over', [(1, {}), (4, {}), (5, {}),
+                                      (5, dict(attention_type=(('bahdanau',), ('bahdanau',))))])
+def test_scheduled_sampling(cfg, over, tensor_cores):
+    """p = 0.5 so that about half of the decoder inputs are draws.  Which (step, row) pairs are replaced is an integer
+    decision and must agree exactly; the drawn ids agree unless the uniform lands within rounding of a CDF step, so
+    loss and gradients are compared with the oracle fed the product's own draws."""
+    hp, batch, ds, model = build(cfg, dict(sampling_probability_outputs=0.5, **over), B=6, Ta=20, Tv=8, L=7)
+    model._global_step = 3
+    om = oracle_for(hp, model)
+    b64 = cast_batch(batch, np.float64)
+    _, rec_self = om.forward_train(b64)
+    loss, gnorm = forward_backward(model, ds)
+    dec = model._decoder
+    used = dec.decoder_input_ids.cpu().numpy().T  # [B,T]
+    drawn = dec.sample_ids.cpu().numpy().T
+    T = used.shape[1]
+    valid = (np.arange(T)[None, :] + 1 < batch['labels_len'][:, None])  # steps whose successor is a real step
+    sel, sel_ref = (drawn >= 0)[:, :T - 1], (rec_self['sample_ids'] >= 0)[:, :T - 1]
+    assert np.array_equal(sel, sel_ref)
+    assert 0.25 < sel.mean() < 0.75
+    both = sel & valid[:, :T - 1]
+    agree = (drawn[:, :T - 1] == rec_self['sample_ids'][:, :T - 1])[both].mean()
+    assert agree >= 0.9, agree
+    # ground truth kept where nothing was drawn
+    go = np.full((used.shape[0], 1), dec._GO_ID)
+    truth = np.concatenate([go, batch['labels']], axis=1)[:, :T]
+    assert np.array_equal(used[:, 1:][~sel], truth[:, 1:][~sel])
+    assert np.array_equal(used[:, 1:][sel], drawn[:, :T - 1][sel])
+    # parity with the same decoder inputs
+    b64['dec_in_ids'] = used
+    loss_ref, G_ref, _ = om.loss_and_grads(b64)
+    assert abs(loss - loss_ref) <= 1e-3 * abs(loss_ref), (loss, loss_ref)
+    check_gradients(model, G_ref, gnorm, tensor_cores)
+
+
+def test_reference_default_training_graph(tensor_cores):
+    """The reference's defaults (avsr.py:49-56): dropout 0.9 everywhere AND scheduled sampling 0.1, AV-Align."""
+    over = dict(use_dropout=True, sampling_probability_outputs=0.1)
+    hp, batch, ds, model = build(5, over, B=4, Ta=24, Tv=10, L=6)
+    om = oracle_for(hp, model)
+    loss, gnorm = forward_backward(model, ds)
+    b64 = cast_batch(batch, np.float64)
+    b64['dec_in_ids'] = model._decoder.decoder_input_ids.cpu().numpy().T
+    loss_ref, G_ref, rec = om.loss_and_grads(b64)
+    assert abs(loss - loss_ref) <= 1e-3 * abs(loss_ref), (loss, loss_ref)
+    check_states(model, rec, 1e-3)
+    check_gradients(model, G_ref, gnorm, tensor_cores)
+
+
+def test_default_graph_trains_and_replays_as_a_cuda_graph():
+    over = dict(use_dropout=True, sampling_probability_outputs=0.1)
+    hp, batch, ds, eager = build(5, over, B=4, Ta=24, Tv=10, L=6)
+    _, _, _, graphed = build(5, over, B=4, Ta=24, Tv=10, L=6)
+    graphed.use_cuda_graph = True
+    for step in range(3):
+        le, ge = eager.train_step(ds)
+        lg, gg = graphed.train_step(ds)
+        assert np.isfinite(le) and np.isfinite(ge)
+        assert abs(le - lg) <= 1e-5 * abs(le) and abs(ge - gg) <= 1e-4 * ge, (step, le, lg, ge, gg)

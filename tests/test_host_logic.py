@@ -86,8 +86,6 @@ def test_hparams_defaults_follow_reference():
     (dict(decoding_algorithm='viterbi'), Exception),
     (dict(optimiser='SGD'), Exception),
     (dict(loss_fun='hinge'), ValueError),
-    (dict(use_dropout=True), NotImplementedError),
-    (dict(sampling_probability_outputs=0.1), NotImplementedError),
 ])
 def test_configuration_errors(over, exc):
     with pytest.raises(exc):
@@ -117,3 +115,20 @@ def test_checkpoint_round_trip(tmp_path):
     a, b = m.store.to_numpy('p'), m2.store.to_numpy('p')
     assert all(np.array_equal(a[k], b[k]) for k in a)
     assert all(np.array_equal(v, m2.store.to_numpy('m')[k]) for k, v in m.store.to_numpy('m').items())
+
+
+def test_reference_default_randomness_builds_and_gets_its_own_streams():
+    """use_dropout=True / sampling_probability_outputs=0.1 are the reference defaults (avsr.py:49-56): every
+    DropoutWrapper-ed cell and the sampling helper get disjoint generator streams; evaluate mode gets none."""
+    hp, m = build(5, use_dropout=True, sampling_probability_outputs=0.1)
+    streams = m.random_streams
+    assert 'Decoder/sampling' in streams
+    cells = [n for n in streams if n != 'Decoder/sampling']
+    assert len(cells) == 3 + 3 + 1  # video 3, audio 2 + cross-modal wrapper, decoder wrapper
+    spans = sorted((s, s + (2 if n == 'Decoder/sampling' else 4)) for n, s in streams.items())
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    from tests.helpers import synthetic_batch, to_data_sequences
+    ds = to_data_sequences(synthetic_batch(hp, B=2, Ta=8, Tv=4, L=3))
+    ev = Seq2SeqModel(ds, 'evaluate', hp, device='cpu')
+    assert ev.random_streams == {}

@@ -19,6 +19,16 @@ CASES = [
     (5, dict(attention_type=(('bahdanau',), ('scaled_luong',)))),
     (5, dict(batch_normalisation=False)),
 ]
+# DropoutWrapper masks (fixed by the counter-based generator, so the loss stays differentiable) and decoder inputs
+# chosen by scheduled sampling (the draws of a first pass are fed back: no gradient flows through them)
+DROP = dict(use_dropout=True, audio_encoder_dropout_probability=(0.8, 0.7, 0.9),
+            video_encoder_dropout_probability=(0.9, 0.8, 0.7), decoder_dropout_probability=(0.7, 0.9, 0.8))
+CASES += [
+    (1, DROP), (2, DROP), (4, DROP), (5, DROP),
+    (5, dict(DROP, attention_type=(('bahdanau',), ('bahdanau',)))),
+    (1, dict(sampling_probability_outputs=0.5)),
+    (5, dict(DROP, sampling_probability_outputs=0.5)),
+]
 
 
 def tiny_model(cfg, over, seed=7):
@@ -38,7 +48,12 @@ def tiny_model(cfg, over, seed=7):
 @pytest.mark.parametrize('cfg,over', CASES)
 def test_backward_matches_finite_differences(cfg, over):
     hp, batch, P, model = tiny_model(cfg, over)
-    om = OracleModel(oracle_hparams(hp), P)
+    model._global_step = 2
+    om = OracleModel(oracle_hparams(hp, model), P)
+    if hp.sampling_probability_outputs > 0.0:
+        _, rec = om.forward_train(batch)
+        assert (rec['sample_ids'] >= 0).any()
+        batch['dec_in_ids'] = rec['dec_in_ids']
     loss, G, _ = om.loss_and_grads(batch)
     assert np.isfinite(loss)
     trainable = set(model.store.names())

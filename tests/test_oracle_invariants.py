@@ -113,3 +113,24 @@ def test_gather_tree_and_beam_shapes_on_tiny_model():
         hits = np.nonzero(row == 29)[0]
         if hits.size:
             assert np.all(row[hits[0] + 1:] == 0)
+
+
+def test_generator_known_answers_and_uniformity():
+    """rand_u32 restates csrc/common.cuh avsr_rand_u32: the words below were printed by the C function compiled for
+    the host (nvcc, same header).  Keep rates follow the thresholds; streams / steps / hi words decorrelate."""
+    from oracle.avsr_oracle import DropSpec, keep_threshold, rand_u32
+    assert rand_u32(1, 2, 3, 4, np.arange(4)).tolist() == [1982725394, 627806037, 120824804, 4077171900]
+    assert int(rand_u32(0xDEADBEEF, 123456, 77, 4000000000, 4294967295)) == 873638011
+    n = 200000
+    w = rand_u32(7, 0, 9, 0, np.arange(n)).astype(np.float64) / 2.0 ** 32
+    assert abs(w.mean() - 0.5) < 5e-3 and abs((w < 0.9).mean() - 0.9) < 3e-3
+    for other in (rand_u32(7, 1, 9, 0, np.arange(n)), rand_u32(7, 0, 10, 0, np.arange(n)),
+                  rand_u32(7, 0, 9, 1, np.arange(n)), rand_u32(8, 0, 9, 0, np.arange(n))):
+        c = np.corrcoef(w, other.astype(np.float64))[0, 1]
+        assert abs(c) < 0.01
+    assert keep_threshold(1.0) == 0 and keep_threshold(0.5) == 2 ** 31
+    spec = DropSpec((3, 4), 16, (0.9, 0.8, 1.0))
+    fx = spec.x_factor(4, 50, 64, np.float64)
+    assert set(np.unique(fx)) == {0.0, 4294967296.0 / keep_threshold(0.9)}
+    assert abs(fx.mean() - 1.0) < 0.02  # inverted dropout is unbiased
+    assert np.all(spec.step_factor(2, 5, 4, 64, np.float64) == 1.0)  # output keep 1.0: no mask
