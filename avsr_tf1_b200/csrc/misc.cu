@@ -242,6 +242,29 @@ __global__ void seq_loss_kernel(const float* __restrict__ logits, int T, int B, 
   if (lane == 0) atomicAdd(loss_sum, lse - z[y]);
 }
 
+// Action-Unit head: one thread per (t, b, k)
+__global__ void au_loss_kernel(const float* __restrict__ z, int T, int B, const float* __restrict__ aus,
+                               const int* __restrict__ len, const float* __restrict__ scale_dev,
+                               float* __restrict__ loss_sum, float* __restrict__ dz) {
+  __shared__ float red[33];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float sq = 0.0f;
+  if (i < T * B * 2) {
+    const int k = i & 1, row = i >> 1, t = row / B, b = row - t * B;
+    float d = 0.0f;
+    if (t < len[b]) {
+      const float p = sigmoidf_acc(z[i]);
+      const float y = fminf(fmaxf(aus[((size_t)b * T + t) * 2 + k], 0.0f), 3.0f) * (1.0f / 3.0f);
+      const float e = p - y;
+      sq = e * e;
+      d = 2.0f * e * p * (1.0f - p) * scale_dev[0];
+    }
+    dz[i] = d;
+  }
+  sq = block_sum(sq, red);
+  if (threadIdx.x == 0 && sq != 0.0f) atomicAdd(loss_sum, sq);
+}
+
 __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
   __shared__ float red[33];
   float acc = 0.0f;
@@ -578,6 +601,13 @@ int avsr_seq_loss(avsr_stream_t s, const float* logits, int T, int B, int V, con
   if (T * B <= 0) return 0;
   AVSR_LAUNCH(seq_loss_kernel, cdiv((long long)T * B * 32, 256), 256, 0, ST(s), logits, T, B, V, labels, ldl,
               labels_len, inv_denom, loss_sum, dlogits);
+  return 0;
+}
+
+int avsr_au_loss(avsr_stream_t s, const float* z, int T, int B, const float* aus, const int* len,
+                 const float* scale_dev, float* loss_sum, float* dz) {
+  if (T * B <= 0) return 0;
+  AVSR_LAUNCH(au_loss_kernel, cdiv((long long)T * B * 2, 256), 256, 0, ST(s), z, T, B, aus, len, scale_dev, loss_sum, dz);
   return 0;
 }
 

@@ -43,8 +43,8 @@ class Seq2SeqEncoder(object):
         self._num_units_per_layer = tuple(num_units_per_layer)
         self._scope, self._ctx = scope, ctx
         self._F = int(feature_dim if feature_dim is not None else data.inputs.shape[-1])
-        if kwargs.get('regress_aus', False) and mode == 'train':
-            raise NotImplementedError('Action-Unit regression head (encoder.py:173-189) is row f-4, not built')
+        # Action-Unit regression head (encoder.py:28-29, 173-189): train mode only
+        self._regress_aus = bool(kwargs.get('regress_aus', False)) and mode == 'train'
         if hparams.instance_normalisation:
             raise NotImplementedError('instance_normalisation is off in every reference config')
         if hparams.input_dense_layers[0] > 0:
@@ -52,6 +52,10 @@ class Seq2SeqEncoder(object):
         self._bn = BatchNormInput(ctx, scope, self._F) if hparams.batch_normalisation is True else None
         self.input_gradient = False  # True: keep what the gradient wrt the raw features needs (backward(need_dx=True))
         self._init_encoder()
+        if self._regress_aus:
+            self._au_W = ctx.declare(f'{scope}/dense/kernel', (self.output_dim, 2), 'glorot')
+            self._au_b = ctx.declare(f'{scope}/dense/bias', (2,), 'zeros')
+        self._au_dz = None
 
     def _init_encoder(self):
         hp, ctx, scope = self._hparams, self._ctx, self._scope
@@ -161,6 +165,30 @@ class Seq2SeqEncoder(object):
 
     def get_data(self):
         return EncoderData(outputs=self._outputs, final_state=self._final, outputs_operand=self._outputs_op)
+
+    # ---- Action-Unit regression head (encoder.py:173-189) ---------------------------------------
+    def au_loss_forward(self, aus, scale_dev, loss_sum):
+        """aus [B,T,2] (payload, batch-major); scale_dev: device scalar au_loss_weight / non-zero weight count;
+        loss_sum[0] += masked sum of squared errors.  Keeps d(loss)/d(pre-sigmoid) for au_loss_backward."""
+        ctx = self._ctx
+        T, B, D = self._outputs.shape
+        z = ops.empty(T, B, 2)
+        ops.gemm(self._outputs.view(T * B, D), ctx.p(self._au_W), z.view(T * B, 2), bias=ctx.p(self._au_b))
+        self._au_dz = ops.empty(T, B, 2)
+        ops.au_loss(z, aus, self._lens, scale_dev, loss_sum, self._au_dz)
+
+    def au_loss_backward(self, doutputs):
+        """Adds the head's gradient to doutputs (allocated when None); accumulates the head's weight gradients."""
+        ctx = self._ctx
+        T, B, D = self._outputs.shape
+        dz2 = self._au_dz.view(T * B, 2)
+        ops.gemm(self._outputs.view(T * B, D), dz2, ctx.g(self._au_W), ta=True, beta=1.0)
+        ops.colsum(dz2, ctx.g(self._au_b))
+        if doutputs is None:
+            doutputs = ops.zeros(T, B, D)
+        ops.gemm(dz2, ctx.p(self._au_W), doutputs.view(T * B, D), tb=True, beta=1.0)
+        self._au_dz = None
+        return doutputs
 
     def backward(self, doutputs, dfinal_state=None, need_dx=False):
         """doutputs [T,B,out_dim] or None; dfinal_state = (dc, dh) wrt final_state or None."""

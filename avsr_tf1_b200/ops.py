@@ -179,6 +179,13 @@ def seq_loss(logits, labels, labels_len, inv_denom, loss_sum, dlogits):
                                     labels_len.data_ptr(), inv.data_ptr(), loss_sum.data_ptr(), dlogits.data_ptr()))
 
 
+def au_loss(z, aus, lens, scale_dev, loss_sum, dz):
+    """Action-Unit head loss (include/avsr_b200.h avsr_au_loss): z [T,B,2], aus [B,T,2]."""
+    T, B, _ = z.shape
+    check(_lib.load().avsr_au_loss(_stream(), z.data_ptr(), T, B, aus.data_ptr(), lens.data_ptr(),
+                                   scale_dev.data_ptr(), loss_sum.data_ptr(), dz.data_ptr()))
+
+
 def sumsq(x, out):
     check(_lib.load().avsr_sumsq(_stream(), x.data_ptr(), x.numel(), out.data_ptr()))
 

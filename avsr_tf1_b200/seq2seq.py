@@ -73,6 +73,8 @@ class Seq2SeqModel(object):
         self._ctx.world_size = parallel.world_size()
         self._ctx.allreduce = parallel.allreduce_sum_
 
+        # Action-Unit regression head on the video encoder (train mode, seq2seq.py:188-190)
+        self._au_head = bool(hparams.regress_aus) and mode == 'train' and self._video_data is not None
         self._make_encoders()
         self._make_decoder()
 
@@ -107,7 +109,7 @@ class Seq2SeqModel(object):
         # (graph-replay safe: written by _set_step_scalars outside the captured region)
         self.rng_seed = int(hparams.kwargs.get('random_seed', seed))
         if self.store.flat.is_cuda:
-            self._scal_dev = torch.zeros(2, dtype=torch.float32, device='cuda')
+            self._scal_dev = torch.zeros(3, dtype=torch.float32, device='cuda')  # inv_denom, lr_t, AU scale
             self._ctx.rng = torch.zeros(2, dtype=torch.int32, device='cuda')
 
     # ---- construction (seq2seq.py:30-126) ---------------------------------------
@@ -210,6 +212,14 @@ class Seq2SeqModel(object):
             src[key] = x
             src[key + '_len'] = self._as_tensor(d.inputs_length, torch.int32)
         meta = {}
+        if self._au_head:
+            aus = (video.payload or {}).get('aus') if video is not None else None
+            if aus is None:
+                raise Exception('regress_aus=True needs the `aus` payload of the video stream (io_utils.py:45-46)')
+            src['aus'] = self._as_tensor(aus, torch.float32)
+            vl = video.inputs_length
+            vl = vl.cpu().numpy() if torch.is_tensor(vl) else np.asarray(vl)
+            meta['au_count'] = 2.0 * float(vl.sum())  # non-zero weights of tf.losses.mean_squared_error
         if ref.labels is not None:
             ll = ref.labels_length
             lab_len_host = ll.cpu().numpy() if torch.is_tensor(ll) else np.asarray(ll)
@@ -291,6 +301,8 @@ class Seq2SeqModel(object):
             if key in src:
                 b[key] = src[key]
                 b[key + '_len'] = src[key + '_len']
+        if 'aus' in src:
+            b['aus'] = src['aus']
         if 'labels' in src:
             T = meta['T_dec']
             labels = src['labels']
@@ -366,32 +378,45 @@ class Seq2SeqModel(object):
         self._decoder.forward_train(mems, states, b['dec_in_ids'], b['labels'], b['labels_len'], b['T_dec'],
                                     self._scal_dev[0:1], self._loss_dev[0:1])
         dmem, dstates = self._decoder.backward_train()
+        dvid_au = None
+        if self._au_head:  # batch_loss += au_loss_weight * au_loss (seq2seq.py:188-190)
+            self._video_encoder.au_loss_forward(b['aus'], self._scal_dev[2:3], self._loss_dev[3:4])
+            dvid_au = self._video_encoder.au_loss_backward(None)
         both = self._video_encoder is not None and self._audio_encoder is not None
         overlap = both and self.overlap_streams
         if self._hparams.architecture == 'bimodal':
             if overlap:
                 with torch.cuda.stream(self._fork()):
-                    self._video_encoder.backward(dmem[0], dstates[0])
+                    self._video_encoder.backward(self._plus(dmem[0], dvid_au), dstates[0])
                 self._audio_encoder.backward(dmem[1], dstates[1])
                 self._join()
             else:
                 self._audio_encoder.backward(dmem[1], dstates[1])
-                self._video_encoder.backward(dmem[0], dstates[0])
+                self._video_encoder.backward(self._plus(dmem[0], dvid_au), dstates[0])
         elif self._audio_encoder is not None:
             if isinstance(self._audio_encoder, AttentiveEncoder):
                 d_lower, dvid = self._audio_encoder.backward_top(dmem[0], dstates[0])
                 if overlap:
                     with torch.cuda.stream(self._fork()):
-                        self._video_encoder.backward(dvid, None)
+                        self._video_encoder.backward(self._plus(dvid, dvid_au), None)
                     self._audio_encoder.backward_lower(d_lower)
                     self._join()
                 else:
                     self._audio_encoder.backward_lower(d_lower)
-                    self._video_encoder.backward(dvid, None)
+                    self._video_encoder.backward(self._plus(dvid, dvid_au), None)
             else:
                 self._audio_encoder.backward(dmem[0], dstates[0])
         else:
-            self._video_encoder.backward(dmem[0], dstates[0])
+            self._video_encoder.backward(self._plus(dmem[0], dvid_au), dstates[0])
+
+    @staticmethod
+    def _plus(d, extra):
+        if extra is None:
+            return d
+        if d is None:
+            return extra
+        ops.axpy(1.0, extra, d)
+        return d
 
     def _lr_now(self):
         hp = self._hparams
@@ -408,6 +433,8 @@ class Seq2SeqModel(object):
         if ctx.world_size > 1:
             ctx.allreduce(st.grad)
             ctx.allreduce(self._loss_dev[0:1])
+            if self._au_head:
+                ctx.allreduce(self._loss_dev[3:4])
         if hp.recurrent_l2_regularisation is not None:
             for n in self._l2_names:
                 ops.axpy(hp.recurrent_l2_regularisation, st.p(n), st.g(n))
@@ -434,8 +461,13 @@ class Seq2SeqModel(object):
         self.current_lr = lr
         t = self._global_step + 1
         # pageable source: the driver stages it at call time, so the host may run ahead of the GPU safely
-        self._scal_dev.copy_(torch.tensor([self._inv_denom, lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)],
-                                          dtype=torch.float32))
+        self._au_scale = 0.0
+        if self._au_head:
+            cnt = parallel.global_token_count(self._meta['au_count'], device='cuda') if ctx.world_size > 1 \
+                else self._meta['au_count']
+            self._au_scale = float(self._hparams.kwargs.get('au_loss_weight', 10.0)) / max(cnt, 1.0)
+        self._scal_dev.copy_(torch.tensor([self._inv_denom, lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t),
+                                           self._au_scale], dtype=torch.float32))
         self._ctx.rng.copy_(torch.tensor(self.rng_words(), dtype=torch.int32))
 
     def rng_words(self):
@@ -476,7 +508,9 @@ class Seq2SeqModel(object):
         vals = self._loss_dev.cpu().numpy()
         xent = float(vals[0]) * self._inv_denom  # sum(xent*w) / (sum(w) + 1e-12)
         reg = 0.5 * (hp.recurrent_l2_regularisation or 0.0) * float(vals[1])
-        self.batch_loss = xent + reg
+        self.au_loss = float(vals[3]) * self._au_scale / float(hp.kwargs.get('au_loss_weight', 10.0)) \
+            if self._au_head else None
+        self.batch_loss = xent + reg + (float(vals[3]) * self._au_scale if self._au_head else 0.0)
         self.global_norm = math.sqrt(float(vals[2]))
         return self.batch_loss, self.global_norm
 

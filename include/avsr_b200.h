@@ -218,6 +218,14 @@ int avsr_embedding_bwd(avsr_stream_t stream, const float* dout, const int* ids, 
 int avsr_seq_loss(avsr_stream_t stream, const float* logits, int T, int B, int V, const int* labels, int ldl,
                   const int* labels_len, const float* inv_denom_dev, float* loss_sum, float* dlogits);
 
+/* ---- Action-Unit regression head of the video encoder (encoder.py:173-189, seq2seq.py:188-190) -------------------
+ * z [T,B,2] = encoder outputs @ video/dense/kernel + bias (pre-sigmoid); aus [B,T,2] as the reader delivers them
+ * (batch-major payload, io_utils.py:45-46).  tf.losses.mean_squared_error(sigmoid(z), clip(aus,0,3)/3, weights =
+ * sequence_mask(len)): loss_sum[0] += sum over t < len[b] of (p - y)^2; dz = 2 (p - y) p (1 - p) * scale_dev[0] there,
+ * 0 past the length (scale = au_loss_weight / number of non-zero weights, a device scalar: graph replay). */
+int avsr_au_loss(avsr_stream_t stream, const float* z, int T, int B, const float* aus, const int* len,
+                 const float* scale_dev, float* loss_sum, float* dz);
+
 /* ---- optimiser (seq2seq.py:175-178, 195-257) --------------------------------- */
 /* out[0] += sum x^2 */
 int avsr_sumsq(avsr_stream_t stream, const float* x, long long n, float* out);

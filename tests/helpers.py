@@ -48,6 +48,7 @@ def oracle_hparams(hp, model=None) -> OracleHParams:
                                    decoder=hp.decoder_dropout_probability)
         rand.update(sampling_probability_outputs=hp.sampling_probability_outputs, rng=model.rng_words(),
                     streams=model.random_streams)
+    rand.update(regress_aus=bool(hp.regress_aus), au_loss_weight=hp.kwargs.get('au_loss_weight', 10.0))
     return OracleHParams(
         **rand,
         architecture=hp.architecture, encoder_type=hp.encoder_type,
@@ -90,11 +91,20 @@ def synthetic_batch(hp, B, Ta=300, Tv=75, Fa=80, Fv=128, L=40, ragged=False, see
     return out
 
 
+def add_aus(batch, seed=1005):
+    """Action-Unit payload of the video stream: [B,Tv,2] intensities in [-0.5, 4] (the loader clips to [0, 3])."""
+    B, Tv = batch['video'].shape[:2]
+    batch['aus'] = np.random.default_rng(seed).uniform(-0.5, 4.0, (B, Tv, 2)).astype(np.float32)
+    return batch
+
+
 def to_data_sequences(batch):
     def one(key):
         if key not in batch:
             return None
-        return make_batched_data(batch[key], batch[key + '_len'], batch['labels'], batch['labels_len'])
+        payload = {'aus': batch['aus']} if key == 'video' and 'aus' in batch else None
+        return make_batched_data(batch[key], batch[key + '_len'], batch['labels'], batch['labels_len'],
+                                 payload=payload)
     return (one('video'), one('audio'))
 
 

@@ -178,3 +178,26 @@ def test_default_graph_trains_and_replays_as_a_cuda_graph():
         lg, gg = graphed.train_step(ds)
         assert np.isfinite(le) and np.isfinite(ge)
         assert abs(le - lg) <= 1e-5 * abs(le) and abs(ge - gg) <= 1e-4 * ge, (step, le, lg, ge, gg)
+
+
+@pytest.mark.parametrize('cfg,over', [(3, {}), (4, {}), (5, {}), (5, dict(use_dropout=True, au_loss_weight=3.0))])
+def test_action_unit_regression_head(cfg, over, tensor_cores):
+    """regress_aus=True (run_video.py:36, run_audiovisual.py:56): Dense(2, sigmoid) on the video encoder outputs
+    against clip(aus, 0, 3) / 3, masked MSE, added to the loss with weight 10 (encoder.py:173-189, seq2seq.py:188-190)."""
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    from tests.helpers import add_aus
+    hp = config_hparams(cfg, **dict(over, regress_aus=True))
+    batch = add_aus(synthetic_batch(hp, B=4, Ta=24, Tv=10, Fa=80, Fv=128, L=6, ragged=True))
+    ds = to_data_sequences(batch)
+    model = Seq2SeqModel(ds, 'train', hp, seed=2001)
+    assert 'video/dense/kernel' in model.store.names() and 'video/dense/bias' in model.store.names()
+    om = oracle_for(hp, model)
+    loss_ref, G_ref, rec = om.loss_and_grads(cast_batch(batch, np.float64))
+    loss, gnorm = forward_backward(model, ds)
+    assert abs(model.au_loss - rec['au_loss']) <= 1e-3 * rec['au_loss'], (model.au_loss, rec['au_loss'])
+    assert abs(loss - loss_ref) <= 1e-3 * abs(loss_ref), (loss, loss_ref)
+    assert np.abs(G_ref['video/dense/kernel']).max() > 0
+    check_gradients(model, G_ref, gnorm, tensor_cores)
+    # the head only exists in the training graph (encoder.py:28-29)
+    ev = Seq2SeqModel(ds, 'evaluate', hp, device='cpu')
+    assert 'video/dense/kernel' not in ev.store.names()

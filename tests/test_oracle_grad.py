@@ -5,7 +5,7 @@ import pytest
 
 from avsr_tf1_b200.seq2seq import Seq2SeqModel
 from oracle.avsr_oracle import OracleModel
-from tests.helpers import cast_batch, config_hparams, oracle_hparams, synthetic_batch, to_data_sequences
+from tests.helpers import add_aus, cast_batch, config_hparams, oracle_hparams, synthetic_batch, to_data_sequences
 
 CASES = [
     (1, {}),
@@ -28,12 +28,15 @@ CASES += [
     (5, dict(DROP, attention_type=(('bahdanau',), ('bahdanau',)))),
     (1, dict(sampling_probability_outputs=0.5)),
     (5, dict(DROP, sampling_probability_outputs=0.5)),
+    (3, dict(regress_aus=True)), (4, dict(regress_aus=True)), (5, dict(DROP, regress_aus=True, au_loss_weight=3.0)),
 ]
 
 
 def tiny_model(cfg, over, seed=7):
     hp = config_hparams(cfg, units=6, embedding_size=5, **over)
     batch = synthetic_batch(hp, B=3, Ta=7, Tv=5, Fa=4, Fv=3, L=4, ragged=True, seed=seed)
+    if hp.regress_aus:
+        add_aus(batch)
     model = Seq2SeqModel(to_data_sequences(batch), 'train', hp, seed=11, device='cpu')
     P = {k: v.astype(np.float64) for k, v in model.store.to_numpy('p').items()}
     rng = np.random.default_rng(5)
