@@ -6,7 +6,15 @@ SRC := $(wildcard avsr_tf1_b200/csrc/*.cu)
 OBJ := $(SRC:.cu=.o)
 LIB := avsr_tf1_b200/lib/libavsr_b200.so
 
-all: $(LIB)
+IOLIB := avsr_tf1_b200/lib/libavsr_io.so
+CXX ?= g++
+
+all: $(LIB) $(IOLIB)
+
+# host-only input pipeline (TFRecord / SequenceExample reader + padded-batch assembler), include/avsr_io.h
+$(IOLIB): avsr_tf1_b200/csrc_host/tfrecord.cc include/avsr_io.h
+	mkdir -p avsr_tf1_b200/lib
+	$(CXX) -O3 -std=c++17 -fPIC -Wall -shared -pthread -o $@ $<
 
 %.o: %.cu avsr_tf1_b200/csrc/common.cuh include/avsr_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
@@ -16,4 +24,4 @@ $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)
 
 clean:
-	rm -f $(OBJ) $(LIB)
+	rm -f $(OBJ) $(LIB) $(IOLIB)

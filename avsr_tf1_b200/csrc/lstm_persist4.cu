@@ -147,6 +147,10 @@ struct FwdParams {
   float* cT;          // [B,H] or null
   float* hT;          // [B,H] or null
   long long* dbg;     // AVSR_LP_DEBUG: clock samples [64 steps][8] of CTA 0 (thread 0: slots 0-5, thread 128+32: 6-7)
+  // DropoutWrapper state / output masks (AvsrRnnSeq.rng), used by the DROP instantiation only
+  const uint32_t* rng;
+  uint32_t stream, thr_state, thr_out;
+  float inv_state, inv_out;
 };
 #define LP4_STAMP(slot)                                                                        \
   do {                                                                                         \
@@ -155,6 +159,10 @@ struct FwdParams {
 
 constexpr size_t FWD_SMEM = (size_t)2 * OP_BYTES + 4 * NB * UPC * 4 + 64 + 1024;
 
+// DROP: the cell sits in a DropoutWrapper (cells.py:46-54): the emitted h carries the output mask, the recurrent h
+// (operand of the next step, S rows, final state) the state mask; both are regenerated from the counter-based
+// generator, computed one step ahead (off the exchange -> product -> gate-math chain).
+template <bool DROP>
 __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_fwd_kernel(const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -257,6 +265,25 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_fwd_kernel(const Fwd
       h_state[e] = (b < B) ? p.S[(size_t)b * H + u] : 0.0f;
     }
   }
+  float f_state[4] = {1.0f, 1.0f, 1.0f, 1.0f}, f_out[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+  uint32_t rng_seed = 0u, rng_step = 0u;
+  if (DROP) {
+    rng_seed = p.rng[0];
+    rng_step = p.rng[1];
+  }
+  auto drop_factors = [&](int t) {  // masks of step t for this thread's 4 units of utterance b0 + bq
+    if (DROP && comb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t idx = (uint32_t)((b0 + bq) * H + UPC * (int)rank + 4 * uq + e);
+        f_state[e] = (p.thr_state == 0u || avsr_rand_u32(rng_seed, rng_step, p.stream + 1u, (uint32_t)t, idx) < p.thr_state)
+                         ? p.inv_state : 0.0f;
+        f_out[e] = (p.thr_out == 0u || avsr_rand_u32(rng_seed, rng_step, p.stream + 2u, (uint32_t)t, idx) < p.thr_out)
+                       ? p.inv_out : 0.0f;
+      }
+    }
+  };
+  drop_factors(0);
   int len_a[NB];
 #pragma unroll
   for (int b = 0; b < NB; ++b) len_a[b] = (b0 + b < B) ? p.len[b0 + b] : 0;
@@ -321,8 +348,13 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_fwd_kernel(const Fwd
           const float c = fminf(fmaxf(cr[e], -1.0f), 1.0f);  // cell_clip = 1.0 (cells.py:16)
           const float h = vo[e] * tanhf_acc(c);
           c_state[e] = c;
-          ov[e] = h;
-          h_state[e] = tf32_rn(h);  // the recurrent operand / next layer's operand
+          if (DROP) {
+            ov[e] = h * f_out[e];
+            h_state[e] = tf32_rn(h * f_state[e]);
+          } else {
+            ov[e] = h;
+            h_state[e] = tf32_rn(h);  // the recurrent operand / next layer's operand
+          }
         }
       } else {
 #pragma unroll
@@ -353,6 +385,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_fwd_kernel(const Fwd
       *reinterpret_cast<float4*>(p.out + o) = make_float4(ov[0], ov[1], ov[2], ov[3]);
       *reinterpret_cast<float4*>(p.S + o + (size_t)B * H) = make_float4(hv[0], hv[1], hv[2], hv[3]);
     }
+    if (DROP && t + 1 < T) drop_factors(t + 1);
 #pragma unroll
     for (int b = 0; b < NB; ++b) gx[b] = gx1[b];
     if (t + 2 < T) {
@@ -405,12 +438,16 @@ struct BwdParams {
   float* dc0;          // [B,H] or null
   float* dh0;          // [B,H] or null
   float* dbias;        // [4H] or null: += column sums of dZ
+  const uint32_t* rng;  // DropoutWrapper state / output masks (DROP instantiation only)
+  uint32_t stream, thr_state, thr_out;
+  float inv_state, inv_out;
 };
 
 constexpr int BW_DZ_BYTES = 4 * NP * 128;            // B operand: 4 K-blocks (gates) x [NP rows x 64 units]
 constexpr int REDH_FLOATS = CL * NB * UPC;           // one parity of the reduce buffer [src][b][u]
 constexpr size_t BWD_SMEM = (size_t)BW_DZ_BYTES + 2 * REDH_FLOATS * 4 + 64 + 1024;
 
+template <bool DROP>
 __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -510,6 +547,11 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
   // reduce-scatter role after the product: warps 0-3 forward tile 0, warps 4-7 tile 1; lane quarter q = warp & 3
   const int q = warp & 3, mt_push = warp >> 2;
 
+  uint32_t rng_seed = 0u, rng_step = 0u;
+  if (DROP) {
+    rng_seed = p.rng[0];
+    rng_step = p.rng[1];
+  }
   float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // bias gradient of this thread's unit: sum of dz over its utterances / steps
   load_step(cur, T - 1);
   load_step(nxt, T - 2);
@@ -517,6 +559,18 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
     const int t = T - 1 - it;
     // recurrent dh of this step: partial sums pushed by all CTAs during the previous iteration + carry
     const float* rbuf = red + (it & 1) * REDH_FLOATS;
+    float f_state[PB], f_out[PB];  // DropoutWrapper masks of step t (regenerated; before the wait: independent of it)
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      f_state[j] = f_out[j] = 1.0f;
+      if (DROP) {
+        const uint32_t idx = (uint32_t)((b0 + (warp >> 1) * PB + j) * H + unit);
+        if (p.thr_state != 0u)
+          f_state[j] = avsr_rand_u32(rng_seed, rng_step, p.stream + 1u, (uint32_t)t, idx) < p.thr_state ? p.inv_state : 0.0f;
+        if (p.thr_out != 0u)
+          f_out[j] = avsr_rand_u32(rng_seed, rng_step, p.stream + 2u, (uint32_t)t, idx) < p.thr_out ? p.inv_out : 0.0f;
+      }
+    }
     if (it > 0) {
       const uint32_t bar = sBar + 16 + 8 * (it & 1);
       if (tid == 0) mbar_expect_tx(bar, REDH_FLOATS * 4);
@@ -532,7 +586,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
         for (int src = 0; src < CL; ++src) dh += rbuf[(src * NB + bl) * UPC + ul];
       }
       if (t < len_t[j]) {
-        dh += cur.dov[j];
+        if (DROP) dh = dh * f_state[j] + cur.dov[j] * f_out[j];  // state-dropped h recurs, output-dropped h is emitted
+        else dh += cur.dov[j];
         const float c = fminf(fmaxf(cur.crw[j], -1.0f), 1.0f);
         const float tc = tanhf_acc(c);
         const float cp = t > 0 ? fminf(fmaxf(cur.cpv[j], -1.0f), 1.0f) : cur.cpv[j];
@@ -678,10 +733,17 @@ int lstm_persist4_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   p.len = r->len; p.gates = r->gates; p.Wrec = r->Wrec; p.c0 = r->c0; p.S = r->S; p.craw = r->craw; p.out = r->out;
   p.cT = r->cT; p.hT = r->hT;
   p.dbg = nullptr;
+  p.rng = r->rng;
+  p.stream = r->drop_stream;
+  p.thr_state = r->rng ? r->thr_state : 0u;
+  p.thr_out = r->rng ? r->thr_out : 0u;
+  p.inv_state = inv_keep_of(p.thr_state);
+  p.inv_out = inv_keep_of(p.thr_out);
+  const bool drop = (p.thr_state | p.thr_out) != 0u;
   if (getenv("AVSR_LP4_DEBUG")) {
     AVSR_CHECK_CUDA(cudaMalloc(&p.dbg, 64 * 8 * sizeof(long long)));
     AVSR_CHECK_CUDA(cudaMemset(p.dbg, 0, 64 * 8 * sizeof(long long)));
-    AVSR_TRY(lp4::launch_cluster(st, lp4::lstm_persist4_fwd_kernel, r->B, lp4::FWD_SMEM, p, AVSR_K_LSTM_FWD));
+    AVSR_TRY(lp4::launch_cluster(st, lp4::lstm_persist4_fwd_kernel<false>, r->B, lp4::FWD_SMEM, p, AVSR_K_LSTM_FWD));
     AVSR_CHECK_CUDA(cudaStreamSynchronize(st));
     long long h[64 * 8];
     AVSR_CHECK_CUDA(cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost));
@@ -702,7 +764,9 @@ int lstm_persist4_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
     fprintf(stderr, " total=%.0f\n", tot);
     return 0;
   }
-  return lp4::launch_cluster(st, lp4::lstm_persist4_fwd_kernel, r->B, lp4::FWD_SMEM, p, AVSR_K_LSTM_FWD);
+  if (drop)
+    return lp4::launch_cluster(st, lp4::lstm_persist4_fwd_kernel<true>, r->B, lp4::FWD_SMEM, p, AVSR_K_LSTM_FWD);
+  return lp4::launch_cluster(st, lp4::lstm_persist4_fwd_kernel<false>, r->B, lp4::FWD_SMEM, p, AVSR_K_LSTM_FWD);
 }
 
 int lstm_persist4_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
@@ -713,7 +777,15 @@ int lstm_persist4_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   p.inv_grad_scale = 1.0f / p.grad_scale;
   p.len = r->len; p.gates = r->gates; p.Wrec = r->Wrec; p.c0 = r->c0; p.craw = r->craw; p.dout = r->dout;
   p.dcT = r->dcT; p.dhT = r->dhT; p.dZ = r->dZ; p.dc0 = r->dc0; p.dh0 = r->dh0; p.dbias = r->dbias;
-  return lp4::launch_cluster(st, lp4::lstm_persist4_bwd_kernel, r->B, lp4::BWD_SMEM, p, AVSR_K_LSTM_BWD);
+  p.rng = r->rng;
+  p.stream = r->drop_stream;
+  p.thr_state = r->rng ? r->thr_state : 0u;
+  p.thr_out = r->rng ? r->thr_out : 0u;
+  p.inv_state = inv_keep_of(p.thr_state);
+  p.inv_out = inv_keep_of(p.thr_out);
+  if (p.thr_state | p.thr_out)
+    return lp4::launch_cluster(st, lp4::lstm_persist4_bwd_kernel<true>, r->B, lp4::BWD_SMEM, p, AVSR_K_LSTM_BWD);
+  return lp4::launch_cluster(st, lp4::lstm_persist4_bwd_kernel<false>, r->B, lp4::BWD_SMEM, p, AVSR_K_LSTM_BWD);
 }
 
 }  // namespace avsr

@@ -41,8 +41,11 @@ static Drop drop_of(const AvsrRnnSeq* r) {
   }
   return d;
 }
+static bool has_dropout(const AvsrRnnSeq* r) { return r->rng && (r->thr_in | r->thr_state | r->thr_out); }
+// The attention-LSTM persistent kernels fold the attention layer into the recurrent matrix, which a mask between the
+// two forbids; the plain-LSTM cluster-of-4 kernels apply the state / output masks themselves (H = 256).
 static bool stepwise_only(const AvsrRnnSeq* r) {
-  return r->stepwise || r->t_begin || r->t_end || (r->rng && (r->thr_in | r->thr_state | r->thr_out));
+  return r->stepwise || r->t_begin || r->t_end || (has_dropout(r) && r->n_mech > 0);
 }
 
 __global__ void lstm_point_fwd_kernel(int t, int B, int H, float* __restrict__ gates_t, const float* __restrict__ rec,
@@ -258,14 +261,15 @@ static int check_common(const AvsrRnnSeq* r, int* At_out, int* maxHD, int* maxA,
 }
 
 
-int lstm_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r);  // lstm_persist.cu
+int lstm_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r);   // lstm_persist.cu (tries the clusters of 4 first)
+int lstm_persist4_fwd(cudaStream_t st, const AvsrRnnSeq* r);  // lstm_persist4.cu (also under dropout)
 
 int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   int At, maxHD, maxA, maxTm;
   AVSR_TRY(check_common(r, &At, &maxHD, &maxA, &maxTm));
   const bool stepwise = stepwise_only(r);
   if (r->n_mech == 0 && tensor_cores_enabled() && !stepwise) {  // persistent cluster kernel (tcgen05, weights resident)
-    const int rc = lstm_persist_fwd(st, r);
+    const int rc = has_dropout(r) ? lstm_persist4_fwd(st, r) : lstm_persist_fwd(st, r);
     if (rc >= 0) return rc;
   }
   const int T = r->T, B = r->B, H = r->H, SW = At + H;
@@ -345,7 +349,7 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   if (r->n_mech == 0 && tensor_cores_enabled() && !stepwise) {
     // reverse-time recurrence in one persistent cluster kernel
     int rc = lstm_persist4_bwd(st, r);
-    if (rc < 0) {
+    if (rc < 0 && !has_dropout(r)) {
       rc = lstm_persist_bwd(st, r);
       if (rc == 0 && r->dbias && T > 0) AVSR_TRY(avsr_colsum((avsr_stream_t)st, r->dZ, T * B, 4 * H, 4 * H, r->dbias));
     }

@@ -201,3 +201,26 @@ def test_action_unit_regression_head(cfg, over, tensor_cores):
     # the head only exists in the training graph (encoder.py:28-29)
     ev = Seq2SeqModel(ds, 'evaluate', hp, device='cpu')
     assert 'video/dense/kernel' not in ev.store.names()
+
+
+def test_dropout_persistent_lstm_many_clusters():
+    """Plain LSTM layers keep the cluster-of-4 persistent kernels under dropout (state / output masks regenerated in
+    the kernels): 5 clusters (one partially filled), ragged lengths, tensor-core mode."""
+    from avsr_tf1_b200 import ops
+    old = ops.set_tensor_cores(True)
+    try:
+        hp, batch, ds, model = build(3, KEEP, B=36, Ta=20, Tv=16, L=4)
+        model._global_step = 9
+        om = oracle_for(hp, model)
+        loss_ref, G_ref, rec = om.loss_and_grads(cast_batch(batch, np.float64))
+        ops.kernel_timing(True)
+        loss, gnorm = forward_backward(model, ds)
+        times = ops.kernel_times()
+        ops.kernel_timing(False)
+        # the persistent LSTM kernels ran, forward and backward, for all three layers
+        assert times['lstm_fwd'][1] == 3 and times['lstm_bwd'][1] == 3, times
+        assert abs(loss - loss_ref) <= 1e-3 * abs(loss_ref), (loss, loss_ref)
+        check_states(model, rec, 2e-3)
+        check_gradients(model, G_ref, gnorm, True)
+    finally:
+        ops.set_tensor_cores(old)
