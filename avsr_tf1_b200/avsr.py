@@ -1,0 +1,195 @@
+"""AVSR - the runtime shell around Seq2SeqModel, drop-in for reference avsr/avsr.py (class AVSR :19-760;
+SURVEY.md section 8, row f-1): epoch loop, logfile lines, checkpoint every 10 epochs followed by an evaluation,
+predictions dumped as .mlf, error rates via utils.compute_wer.
+
+What differs by construction: there is no TF graph / session.  The train and evaluate "graphs" are two
+Seq2SeqModel objects fed by eager record iterators (io_utils.RecordBatcher); a checkpoint is the Saver's .npz.
+Front-ends that are out of scope here (`resnet_cnn` and the other CNNs, `wav` audio) raise: video enters as the
+features the record holds ('features' on a feature record, or raw lip crops as flat vectors)."""
+from __future__ import annotations
+
+import collections
+import glob
+import re
+import time
+from os import makedirs, path
+
+import numpy as np
+
+from . import parallel
+from .hparams import create_unit_dict, make_hparams
+from .io_utils import (BatchedData, OutOfRangeError, make_iterator_from_one_record, make_iterator_from_two_records)
+from .utils import compute_wer, write_sequences_to_labelfile
+
+
+class Model(collections.namedtuple("Model", ("data", "model", "initializer", "batch_size"))):
+    pass
+
+
+def latest_checkpoint(checkpoint_dir):
+    """tf.train.latest_checkpoint: the save path (without extension) with the highest epoch suffix, or None."""
+    best, best_epoch = None, -1
+    for f in glob.glob(path.join(checkpoint_dir, '*.npz')):
+        m = re.search(r'-(\d+)\.npz$', f)
+        if m and int(m.group(1)) > best_epoch:
+            best, best_epoch = f[:-4], int(m.group(1))
+    return best
+
+
+class AVSR(object):
+    def __init__(self, unit, unit_file=None, video_processing=None, video_train_record=None, video_test_record=None,
+                 audio_processing=None, audio_train_record=None, audio_test_record=None, labels_train_record=None,
+                 labels_test_record=None, batch_size=(64, 64), write_attention_alignment=False,
+                 write_beam_search_graphs=False, write_estimated_modality_lags=False,
+                 required_grahps=('train', 'eval'), workdir='.', seed=2001, verbose=True, **kwargs):
+        """Keyword surface of avsr.py:21-75 (`required_grahps` is the reference's spelling); everything that is a
+        hyper-parameter goes to make_hparams.  `workdir` roots the reference's relative output directories
+        (checkpoints/, predictions/)."""
+        if video_processing is not None and video_processing != 'features':
+            raise NotImplementedError('the CNN front-ends (avsr/video.py) are row f-3 of SURVEY.md section 8, not '
+                                      'built: use video_processing=`features`')
+        if audio_processing is not None and audio_processing != 'features':
+            raise NotImplementedError('`wav` audio processing (avsr/audio.py) is out of scope: use `features`')
+        if write_attention_alignment or write_beam_search_graphs or write_estimated_modality_lags:
+            raise NotImplementedError('visualisation artefacts (avsr/visualise) are out of scope')
+        self._unit = unit
+        self._unit_dict = create_unit_dict(unit_file=unit_file)
+        self._video_processing, self._audio_processing = video_processing, audio_processing
+        self._video_train_record, self._video_test_record = video_train_record, video_test_record
+        self._audio_train_record, self._audio_test_record = audio_train_record, audio_test_record
+        self._labels_train_record, self._labels_test_record = labels_train_record, labels_test_record
+        self._required_graphs = required_grahps
+        self._workdir, self._seed, self._verbose = workdir, seed, verbose
+        self._hparams = make_hparams(unit=unit, unit_file=unit_file, video_processing=video_processing,
+                                     audio_processing=audio_processing, batch_size=batch_size,
+                                     unit_dict=self._unit_dict, **kwargs)
+        self._train_model = self._evaluate_model = None
+        self._create_models()
+
+    # ---- construction (avsr.py:514-572) --------------------------------------------------------------------
+    def _create_models(self):
+        if 'train' in self._required_graphs:
+            self._train_model = self._make_model('train', self._hparams.batch_size[0])
+        if 'eval' in self._required_graphs:
+            self._evaluate_model = self._make_model('evaluate', self._hparams.batch_size[1])
+
+    def _fetch_data(self, mode, batch_size):
+        """avsr.py:628-679: one iterator over both streams when both are on (bucket width 45 on the video length),
+        else one iterator per stream."""
+        train = mode == 'train'
+        pick = (lambda a, b: a if train else b)
+        labels = pick(self._labels_train_record, self._labels_test_record)
+        video = pick(self._video_train_record, self._video_test_record)
+        audio = pick(self._audio_train_record, self._audio_test_record)
+        common = dict(batch_size=batch_size, unit_dict=self._hparams.unit_dict, shuffle=train, reverse_input=False,
+                      bucket_width=45, seed=self._seed)
+        if self._video_processing is not None and self._audio_processing is not None:
+            return make_iterator_from_two_records(video_record=video, audio_record=audio, label_record=labels, **common)
+        if self._video_processing is not None:
+            return make_iterator_from_one_record(data_record=video, label_record=labels, **common)
+        if self._audio_processing is not None:
+            return make_iterator_from_one_record(data_record=audio, label_record=labels,
+                                                 max_sentence_length=self._hparams.max_sentence_length, **common)
+        raise ValueError('At least one of A/V streams must be enabled')
+
+    def _make_model(self, mode, batch_size):
+        from .seq2seq import Seq2SeqModel
+        iterator = self._fetch_data(mode, batch_size)
+        # the model only needs the feature sizes of each stream at construction: a one-step placeholder batch
+        spec = []
+        for f in iterator._inputs:
+            x = np.zeros((1, 1, f.feat), np.float32)
+            spec.append(BatchedData(iterator_initializer=iterator.iterator_initializer, inputs=x,
+                                    inputs_length=np.ones(1, np.int32), inputs_filenames=None,
+                                    labels=np.zeros((1, 1), np.int32), labels_length=np.ones(1, np.int32),
+                                    labels_filenames=None, payload={}))
+        if len(spec) == 2:
+            data = (spec[0], spec[1])
+        elif self._video_processing is not None:
+            data = (spec[0], None)
+        else:
+            data = (None, spec[0])
+        model = Seq2SeqModel(data_sequences=data, mode=mode, hparams=self._hparams, seed=self._seed)
+        return Model(data=iterator, model=model, initializer=None, batch_size=batch_size)
+
+    def _say(self, msg):
+        if self._verbose and parallel.rank() == 0:
+            print(msg)
+
+    # ---- training (avsr.py:227-320) ---------------------------------------------------------------------------
+    def train(self, logfile, num_epochs=400, try_restore_latest_checkpoint=False):
+        checkpoint_dir = path.join(self._workdir, 'checkpoints', path.split(logfile)[-1])
+        checkpoint_path = path.join(checkpoint_dir, 'checkpoint.ckp')
+        makedirs(checkpoint_dir, exist_ok=True)
+        makedirs(path.dirname(path.abspath(logfile)), exist_ok=True)
+        tm = self._train_model
+        last_epoch = 0
+        if try_restore_latest_checkpoint is True:
+            try:
+                latest_ckp = latest_checkpoint(checkpoint_dir)
+                last_epoch = int(latest_ckp.split('-')[-1])
+                tm.model.saver.restore(sess=None, save_path=latest_ckp)
+                self._say('Restoring checkpoint from epoch {}\n'.format(last_epoch))
+            except Exception:
+                last_epoch = 0
+                self._say('Could not restore from checkpoint, training from scratch!\n')
+        self.last_error_rate = None
+        with open(logfile, 'a') as f:
+            for current_epoch in range(1, num_epochs):
+                epoch = last_epoch + current_epoch
+                tm.data.iterator_initializer()
+                sum_loss, batches = 0.0, 0
+                start = time.time()
+                try:
+                    while True:
+                        tm.data.next()
+                        batch_loss, global_norm = tm.model.train_step(tm.data.data_sequences())
+                        sum_loss += batch_loss
+                        self._say('batch: {}, batch loss: {:.2f}, gradient norm: {:.2f}'.format(
+                            batches, batch_loss, global_norm))
+                        batches += 1
+                except OutOfRangeError:
+                    pass
+                self._say('epoch time: {}'.format(time.time() - start))
+                f.write('Average batch_loss as epoch {} is {}\n'.format(epoch, sum_loss / max(batches, 1)))
+                f.flush()
+                if epoch % 10 == 0:
+                    save_path = tm.model.saver.save(sess=None, save_path=checkpoint_path, global_step=epoch)
+                    if self._evaluate_model is not None:
+                        error_rate = self.evaluate(save_path, epoch)
+                        for (k, v) in error_rate.items():
+                            f.write(k + ': {:.4f}% '.format(v * 100))
+                        f.write('\n')
+                        f.flush()
+                        self.last_error_rate = error_rate
+
+    # ---- evaluation (avsr.py:322-512) ---------------------------------------------------------------------------
+    def evaluate(self, checkpoint_path, epoch=None, alignments_outdir='./alignments/tmp/',
+                 beam_graphs_outdir='./beam_graphs/tmp/'):
+        em = self._evaluate_model
+        em.model.saver.restore(sess=None, save_path=checkpoint_path)
+        em.data.iterator_initializer()
+        predictions_dict, labels_dict = {}, {}
+        while True:
+            try:
+                em.data.next()
+            except OutOfRangeError:
+                break
+            predicted = em.model.predict(em.data.data_sequences())
+            names = em.data.inputs_filenames
+            names = names[0] if isinstance(names, tuple) else names
+            labels = em.data.labels.numpy()
+            for idx in range(len(names)):
+                file = names[idx].decode('utf-8')
+                predictions_dict[file] = [self._unit_dict[int(sym)] for sym in predicted[idx]]
+                labels_dict[file] = [self._unit_dict[int(sym)] for sym in labels[idx]]
+        uer, uer_dict = compute_wer(predictions_dict, labels_dict)
+        error_rate = {self._unit: uer}
+        if self._unit == 'character':
+            wer, _ = compute_wer(predictions_dict, labels_dict, split_words=True)
+            error_rate['word'] = wer
+        outdir = path.join(self._workdir, 'predictions', path.split(path.split(checkpoint_path)[0])[-1])
+        makedirs(outdir, exist_ok=True)
+        write_sequences_to_labelfile(predictions_dict, path.join(outdir, 'predicted_epoch_{}.mlf'.format(epoch)),
+                                     labels_dict, uer_dict, sep=' ' if self._unit == 'phoneme' else '')
+        return error_rate

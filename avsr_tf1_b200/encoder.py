@@ -4,6 +4,8 @@ from __future__ import annotations
 
 import collections
 
+import numpy as np
+
 from . import ops
 from .attention import add_attention
 from .cells import build_rnn_layers
@@ -42,7 +44,8 @@ class Seq2SeqEncoder(object):
         self._mode, self._hparams = mode, hparams
         self._num_units_per_layer = tuple(num_units_per_layer)
         self._scope, self._ctx = scope, ctx
-        self._F = int(feature_dim if feature_dim is not None else data.inputs.shape[-1])
+        # raw lip crops [B,T,h,w,c] enter as flat features (video_processing='features' on a video record)
+        self._F = int(feature_dim if feature_dim is not None else np.prod(tuple(data.inputs.shape[2:])))
         # Action-Unit regression head (encoder.py:28-29, 173-189): train mode only
         self._regress_aus = bool(kwargs.get('regress_aus', False)) and mode == 'train'
         if hparams.instance_normalisation:

@@ -30,8 +30,10 @@ class Saver(object):
     """tf.train.Saver stand-in (seq2seq.py:132-133): all global variables incl. Adam slots,
     BN moving statistics and global_step, keyed by TF variable name, in one .npz file."""
 
-    def __init__(self, model):
+    def __init__(self, model, max_to_keep=1):
         self._model = model
+        self._max_to_keep = max_to_keep  # tf.train.Saver(max_to_keep=1), seq2seq.py:133
+        self._kept = []
 
     def save(self, sess=None, save_path=None, global_step=None):
         path = save_path if global_step is None else '%s-%d' % (save_path, global_step)
@@ -43,6 +45,12 @@ class Saver(object):
             blob.update({'adam_v/' + k: v for k, v in st.to_numpy('v').items()})
         blob['global_step'] = np.asarray(self._model._global_step, np.int64)
         np.savez(path + '.npz', **blob)
+        if path not in self._kept:
+            self._kept.append(path)
+        while self._max_to_keep and len(self._kept) > self._max_to_keep:
+            old = self._kept.pop(0) + '.npz'
+            if os.path.exists(old):
+                os.remove(old)
         return path
 
     def restore(self, sess=None, save_path=None):
