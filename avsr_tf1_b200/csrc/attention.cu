@@ -10,6 +10,8 @@
 //   attn_outer      after the loop: dvalues += align^T dctx ;  Luong: dkeys += ds^T q  (per utterance)
 //   attn_bahdanau_post  after the loop: dkeys, dv, dbias of the tanh scorer, recomputing tanh
 #include "../../include/avsr_b200.h"
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace avsr {
@@ -411,15 +413,15 @@ attn_outer_kernel(int T, int B, int Tm, int C, const int* __restrict__ seq_len, 
       __syncthreads();
       if (c < C) {
         const int nt = min(OUT_TT, Tb - t0);
-        for (int tt0 = 0; tt0 < nt; tt0 += 4) {
-          float xv[4];
+        for (int tt0 = 0; tt0 < nt; tt0 += 8) {  // 8 independent row loads in flight per thread (L2 / HBM latency)
+          float xv[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 8; ++j) {
             const int t = t0 + tt0 + j;
             xv[j] = (tt0 + j < nt) ? __ldg(x + ((size_t)t * B + b) * ldx + c) : 0.0f;
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < 8; ++j)
 #pragma unroll
             for (int i = 0; i < OUTER_TM; ++i) acc[i] = fmaf(w_s[tt0 + j][i], xv[j], acc[i]);
         }
@@ -434,9 +436,106 @@ attn_outer_kernel(int T, int B, int Tm, int C, const int* __restrict__ seq_len, 
   }
 }
 
+// Tensor-core form of the same accumulation (tensor-core mode only): per utterance out[Tm, C] += w^T[Tm, T] x[T, C] is a
+// small dense product, 256 of them per batch.  CTA = (utterance, 32 memory rows); 8 warps x 32 columns; the w chunk
+// (A operand, [32 steps][32 rows]) is staged tf32-rounded in shared memory, the x rows (B operand) are read straight
+// from global memory in fragment order (8 consecutive floats of 4 rows per load instruction = full 32-byte sectors) and
+// rounded to tf32 on the fly; mma.sync.m16n8k8 with fp32 accumulators.  The SIMT kernel above spends 168 issue slots per
+// warp and 8 steps, this one 14.
+constexpr int OM_ROWS = 32;       // memory rows per CTA (two m16 tiles)
+constexpr int OM_TT = 32;         // query steps per staged chunk (four k8 steps)
+constexpr int OM_LD = 40;         // padded row stride of the staged chunk: conflict-free A-fragment reads
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256)
+attn_outer_mma_kernel(int T, int B, int Tm, int C, const int* __restrict__ seq_len, const float* __restrict__ w,
+                      const float* __restrict__ x, int ldx, const float* __restrict__ scale, float* __restrict__ out) {
+  __shared__ float w_s[OM_TT][OM_LD];
+  const int b = blockIdx.x, tm0 = blockIdx.y * OM_ROWS, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  const int Tb = min(T, seq_len[b]);
+  const int ntm = min(OM_ROWS, Tm - tm0);
+  for (int c0 = 0; c0 < C; c0 += 256) {
+    const int cw = c0 + warp * 32;  // first column of this warp
+    float acc[2][4][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[m][n][e] = 0.0f;
+    for (int t0 = 0; t0 < Tb; t0 += OM_TT) {
+      __syncthreads();
+      for (int e = tid; e < OM_TT * OM_ROWS; e += 256) {
+        const int tt = e / OM_ROWS, i = e % OM_ROWS;
+        const int t = t0 + tt;
+        w_s[tt][i] = (t < Tb && i < ntm) ? tf32_rn(w[((size_t)t * B + b) * Tm + tm0 + i]) : 0.0f;
+      }
+      // B fragments of the whole chunk first (independent loads in flight), then the products
+      uint32_t bf[4][4][2];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int t = t0 + ks * 8 + tg + 4 * h;
+            const int c = cw + n * 8 + g;
+            const float v = (t < Tb && c < C) ? __ldg(x + ((size_t)t * B + b) * ldx + c) : 0.0f;
+            bf[ks][n][h] = __float_as_uint(tf32_rn(v));
+          }
+      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        if (t0 + ks * 8 >= Tb) break;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          uint32_t a[4];
+          a[0] = __float_as_uint(w_s[ks * 8 + tg][m * 16 + g]);
+          a[1] = __float_as_uint(w_s[ks * 8 + tg][m * 16 + g + 8]);
+          a[2] = __float_as_uint(w_s[ks * 8 + tg + 4][m * 16 + g]);
+          a[3] = __float_as_uint(w_s[ks * 8 + tg + 4][m * 16 + g + 8]);
+#pragma unroll
+          for (int n = 0; n < 4; ++n) mma_tf32_16x8x8(acc[m][n], a, bf[ks][n][0], bf[ks][n][1]);
+        }
+      }
+    }
+    const float s = scale ? scale[0] : 1.0f;
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = m * 16 + g + 8 * h, c = cw + n * 8 + 2 * tg;
+          if (row < ntm && c < C) {  // (C is even for every caller: attention / memory depths)
+            float* o = out + ((size_t)(tm0 + row) * B + b) * C + c;
+            if (c + 1 < C) {
+              float2 v = *reinterpret_cast<float2*>(o);
+              v.x += s * acc[m][n][2 * h];
+              v.y += s * acc[m][n][2 * h + 1];
+              *reinterpret_cast<float2*>(o) = v;
+            } else {
+              o[0] += s * acc[m][n][2 * h];
+            }
+          }
+        }
+  }
+}
+
 int attn_outer(cudaStream_t st, int T, int B, int Tm, int C, const int* seq_len, const float* w, const float* x,
                int ldx, const float* scale, float* out) {
   if (T <= 0) return 0;
+  if (tensor_cores_enabled() && (C % 2 == 0) && (((uintptr_t)out & 7) == 0) && !getenv("AVSR_OUTER_SIMT")) {
+    dim3 grid(B, cdiv(Tm, OM_ROWS));
+    AVSR_LAUNCH(attn_outer_mma_kernel, grid, 256, 0, st, T, B, Tm, C, seq_len, w, x, ldx, scale, out);
+    return 0;
+  }
   dim3 grid(B, cdiv(Tm, OUTER_TM));
   AVSR_LAUNCH(attn_outer_kernel, grid, 256, 0, st, T, B, Tm, C, seq_len, w, x, ldx, scale, out);
   return 0;

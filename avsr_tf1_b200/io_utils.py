@@ -39,12 +39,26 @@ class OutOfRangeError(Exception):
     """End of the epoch (tf.errors.OutOfRangeError)."""
 
 
-def _host_tensor(shape, dtype, pin):
-    import torch
-    t = torch.empty(shape, dtype=dtype)
-    if pin and torch.cuda.is_available():
-        t = t.pin_memory()
-    return t
+class _HostRing(object):
+    """Page-locked staging buffers, reused round-robin per shape (cudaHostAlloc of a 300 MB batch costs more than
+    decoding it).  A buffer is handed out again `depth` batches later: the consumer must have finished its
+    host-to-device copy by then (the training loop reads the loss back every step, which synchronises)."""
+
+    def __init__(self, pin, depth):
+        self._pin, self._depth, self._slots = pin, max(2, int(depth)), {}
+
+    def get(self, shape, dtype):
+        import torch
+        key = (tuple(shape), dtype)
+        ring = self._slots.setdefault(key, [[], 0])
+        if len(ring[0]) < self._depth:
+            t = torch.empty(shape, dtype=dtype)
+            if self._pin and torch.cuda.is_available():
+                t = t.pin_memory()
+            ring[0].append(t)
+            return t
+        ring[1] = (ring[1] + 1) % self._depth
+        return ring[0][ring[1]]
 
 
 class RecordBatcher(object):
@@ -80,6 +94,7 @@ class RecordBatcher(object):
         self._queue = self._thread = None
         self._current = None
         self._stop = threading.Event()
+        self._ring = _HostRing(pin_memory, self._prefetch + 3)  # queue depth + one in assembly + one being consumed
 
     # ---- epoch order -----------------------------------------------------------------------------------
     def _element_order(self):
@@ -129,9 +144,9 @@ class RecordBatcher(object):
         streams = []
         for k, f in enumerate(self._inputs):
             t_pad = int(f.lengths[idx].max())
-            x = _host_tensor((n, t_pad, f.feat), torch.float32, self._pin)
+            x = self._ring.get((n, t_pad, f.feat), torch.float32)
             lens = torch.empty(n, dtype=torch.int32)
-            aus = _host_tensor((n, t_pad, 2), torch.float32, self._pin) if (k == 0 and f.has_aus) else None
+            aus = self._ring.get((n, t_pad, 2), torch.float32) if (k == 0 and f.has_aus) else None
             f.fill_inputs(idx, t_pad, x, lens, aus_dst=aus, reverse=self.reverse_input and len(self._inputs) == 1,
                           n_threads=self.num_cores)
             if len(f.input_shape) == 3:

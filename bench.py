@@ -49,6 +49,10 @@ def parse():
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--overlap', action='store_true', help='run the video and audio encoder branches on two streams')
     ap.add_argument('--skip-roofline', action='store_true')
+    ap.add_argument('--skip-extras', action='store_true',
+                    help='skip the two side measurements: the reference-default training graph (dropout + scheduled '
+                         'sampling on) and the TFRecord-fed end-to-end loop')
+    ap.add_argument('--tfrecord-utterances', type=int, default=1024)
     return ap.parse_args()
 
 
@@ -68,8 +72,9 @@ def config_dict(args, N):
         'T_video': 75, 'video_features': 3888 if args.video_input == 'crops3888' else 128,
         'video_input': '36x36x3 lip crops as flat features' if args.video_input == 'crops3888'
         else '128-d visual features', 'label_len': 41, 'parallelism': f'dp{N}',
-        'dropout': 'off', 'scheduled_sampling': 'off (parity switches of SURVEY.md 8d; TF Philox streams are '
-                                                'not reproducible)',
+        'dropout': 'off', 'scheduled_sampling': 'off (the parity switches of SURVEY.md 8d, the graph the reference '
+                                                'arm / cpu_baseline runs too; the reference-default graph with '
+                                                'both ON is timed beside it: key reference_default_graph)',
         'l2_flush': 'not needed: every step streams > 2 GB of activations through a 126 MB L2',
     }
 
@@ -308,6 +313,91 @@ def persistent_kernel_rooflines(args, torch, ops, model, gate):
     return roof, tensor
 
 
+def default_graph_throughput(args, torch, ds_host, steps):
+    """The reference's DEFAULT training graph (avsr.py:49-56: DropoutWrapper keep 0.9 on input / state / output of
+    every cell, scheduled sampling 0.1) on the same workload.  Plain LSTM layers keep their persistent kernels (masks
+    regenerated in-kernel); the two attention layers run step-wise (a mask sits between the attention layer and the
+    recurrent matrix, so the folded recurrence of the persistent attention kernel does not apply)."""
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    from tests.helpers import config_hparams
+    hp = config_hparams(5, attention_type=((args.attention,), (args.attention,)), use_dropout=True,
+                        sampling_probability_outputs=0.1)
+    model = Seq2SeqModel(ds_host, 'train', hp, seed=2001)
+    model.use_cuda_graph = not args.no_graph
+    model.feed(ds_host)
+    for _ in range(3):
+        model.train_step(fetch=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        model.train_step(fetch=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    loss, gnorm = model.fetch_scalars()
+    return {'value': round(args.batch / (ms / 1e3), 2), 'unit': UNIT, 'ms_per_step': round(ms, 4), 'steps': steps,
+            'gpu_launches_per_step': int(model.launches_last_step), 'loss': round(float(loss), 6),
+            'config': 'same workload with use_dropout=True (keep 0.9/0.9/0.9 on every cell) and '
+                      'sampling_probability_outputs=0.1: the reference defaults; masks and draws from the '
+                      'counter-based generator (include/avsr_b200.h avsr_dropout / avsr_sched_sample)'}
+
+
+def tfrecord_e2e(args, torch, model, n_utt):
+    """the same training step fed from synthetic TFRecords in the reference's schema (8d) through
+    the native reader (include/avsr_io.h) - shuffle, bucket, padded batch into pinned memory on a prefetch thread -
+    instead of one resident pinned batch."""
+    import shutil
+    import tempfile
+
+    from avsr_tf1_b200 import io_utils
+    from avsr_tf1_b200.synthetic import write_synthetic_records
+    d = tempfile.mkdtemp(prefix='avsr_records_')
+    try:
+        t0 = time.perf_counter()
+        paths = write_synthetic_records(d, n=n_utt, Ta=300, Tv=75, Fa=80, hw=36, channels=3, L=40)
+        t_write = time.perf_counter() - t0
+        cores = max(1, min(16, (os.cpu_count() or 4) - 1))
+        it = io_utils.make_iterator_from_two_records(
+            paths['video'], paths['audio'], paths['labels'], batch_size=args.batch,
+            unit_dict=model._hparams.unit_dict, shuffle=True, bucket_width=45, num_cores=cores, prefetch=3)
+        bytes_on_disk = sum(os.path.getsize(p) for p in paths.values())
+
+        def epoch():
+            """One pass over the records; the H2D copy of batch k+1 (copy stream) overlaps the step of batch k."""
+            n = 0
+            batches = iter(it)
+            b = next(batches, None)
+            if b is not None:
+                model.prefetch(b.data_sequences())
+            while b is not None:
+                size = b.labels.shape[0]
+                model.train_step(fetch=False)  # consumes the staged batch
+                b = next(batches, None)
+                if b is not None:
+                    model.prefetch(b.data_sequences())
+                model.fetch_scalars()  # D2H loss of this step (synchronises: staging buffers may be reused)
+                n += size
+            return n
+        epoch()  # page cache, pinned staging ring and static device buffers warm
+        epoch()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = epoch() + epoch() + epoch()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        # reader alone (no GPU work): what the host side sustains
+        t0 = time.perf_counter()
+        m = sum(b.labels.shape[0] for b in it)
+        dt_read = time.perf_counter() - t0
+        return {'value': round(n / dt, 2), 'unit': UNIT, 'utterances': n, 'reader_only_utterances_per_s': round(m / dt_read, 1),
+                'reader_threads': cores, 'record_bytes': int(bytes_on_disk), 'write_s': round(t_write, 2),
+                'timing': 'wall clock over three epochs incl. record decode, H2D (overlapped with the previous step), step, '
+                          'D2H loss every step'}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -443,6 +533,15 @@ def main():
             line['roofline'], line['roofline_tensor'] = persistent_kernel_rooflines(args, torch, ops, model, gate)
     except Exception as ex:  # keep the headline number even if the side measurement fails
         line['roofline'] = {'error': repr(ex)}
+    if world == 1 and not args.skip_extras:
+        try:
+            line['reference_default_graph'] = default_graph_throughput(args, torch, ds_host, max(2, min(args.steps, 5)))
+        except Exception as ex:
+            line['reference_default_graph'] = {'error': repr(ex)}
+        try:
+            line['e2e_tfrecord'] = tfrecord_e2e(args, torch, model, args.tfrecord_utterances)
+        except Exception as ex:
+            line['e2e_tfrecord'] = {'error': repr(ex)}
     if world == 1 and not args.skip_cpu_baseline:
         r = run_oracle(args, steps=2, warmup=1, sample=args.cpu_sample)
         line['cpu_baseline'] = {
