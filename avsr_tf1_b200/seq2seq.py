@@ -479,8 +479,11 @@ class Seq2SeqModel(object):
         self._ctx.rng.copy_(torch.tensor(self.rng_words(), dtype=torch.int32))
 
     def rng_words(self):
-        """(seed, step) of the generator for the CURRENT training step (31-bit so they fit the int32 device words)."""
-        return (self.rng_seed & 0x7FFFFFFF, self._global_step & 0x7FFFFFFF)
+        """(seed, step) of the generator for the CURRENT training step (31-bit so they fit the int32 device words).
+        Under data parallelism every rank draws its own masks (its utterances are different ones): the rank is folded
+        into the seed."""
+        seed = (self.rng_seed + 0x3C6EF35F * parallel.rank()) & 0x7FFFFFFF
+        return (seed, self._global_step & 0x7FFFFFFF)
 
     @property
     def random_streams(self):

@@ -23,10 +23,27 @@ for graph in (False, True):
         out = m.train_step(to_data_sequences(mine))
         torch.cuda.synchronize()
         log('graph' if graph else 'eager', 'step', s, 'loss %.6f gnorm %.6f' % out)
+# the reference-default training graph under data parallelism: dropout + scheduled sampling + AU head
+from tests.helpers import add_aus
+hp2 = config_hparams(5, use_dropout=True, sampling_probability_outputs=0.1, regress_aus=True)
+full2 = add_aus(dict(full))
+mine2 = {k: v[lo:hi] for k, v in full2.items()}
+for graph in (False, True):
+    m = Seq2SeqModel(to_data_sequences(mine2), 'train', hp2, seed=2001)
+    m.use_cuda_graph = graph
+    for s in range(2):
+        out = m.train_step(to_data_sequences(mine2))
+        torch.cuda.synchronize()
+        log('default-graph', 'graph' if graph else 'eager', 'step', s, 'loss %.6f gnorm %.6f au %.6f' % (out + (m.au_loss,)),
+            'rng', m.rng_words())
+        assert all(np.isfinite(out))
 if rank == 0:
     # single-rank large batch reference: same loss / grad-norm at step 0
     dist.barrier()
 else:
     dist.barrier()
 log('done')
-dist.destroy_process_group()
+# captured graphs hold NCCL work: tearing the process group down under them can hang (see bench.py finish())
+sys.stdout.flush()
+torch.cuda.synchronize()
+os._exit(0)
