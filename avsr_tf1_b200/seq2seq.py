@@ -26,6 +26,25 @@ from .layers import BuildContext
 from .params import ParamStore
 
 
+class _PendingScalars(object):
+    """Result of Seq2SeqModel.fetch_scalars_async()."""
+
+    def __init__(self, model, buf, event, inv_denom, au_scale):
+        self._model, self._buf, self._event = model, buf, event
+        self._inv_denom, self._au_scale = inv_denom, au_scale
+
+    def result(self):
+        self._event.synchronize()
+        m, hp = self._model, self._model._hparams
+        vals = self._buf.numpy()
+        xent = float(vals[0]) * self._inv_denom
+        reg = 0.5 * (hp.recurrent_l2_regularisation or 0.0) * float(vals[1])
+        au = float(vals[3]) * self._au_scale if m._au_head else 0.0
+        m.batch_loss = xent + reg + au
+        m.global_norm = math.sqrt(float(vals[2]))
+        return m.batch_loss, m.global_norm
+
+
 class Saver(object):
     """tf.train.Saver stand-in (seq2seq.py:132-133): all global variables incl. Adam slots,
     BN moving statistics and global_step, keyed by TF variable name, in one .npz file."""
@@ -524,6 +543,20 @@ class Seq2SeqModel(object):
         self.batch_loss = xent + reg + (float(vals[3]) * self._au_scale if self._au_head else 0.0)
         self.global_norm = math.sqrt(float(vals[2]))
         return self.batch_loss, self.global_norm
+
+    def fetch_scalars_async(self):
+        """Starts the device -> host copy of THIS step's results into pinned memory and returns a handle whose
+        `result()` waits for just that copy.  Lets the host launch step k+1 before it reads the loss of step k, so the
+        GPU never waits for the host between steps (session.run pipelines the same way behind its fetches)."""
+        if not hasattr(self, '_pinned_scalars'):
+            self._pinned_scalars = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._pinned_next = 0
+        buf = self._pinned_scalars[self._pinned_next % len(self._pinned_scalars)]
+        self._pinned_next += 1
+        buf.copy_(self._loss_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return _PendingScalars(self, buf, ev, self._inv_denom, self._au_scale)
 
     def train_step(self, data_sequences=None, fetch=True):
         if self._mode != 'train':

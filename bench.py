@@ -370,14 +370,20 @@ def tfrecord_e2e(args, torch, model, n_utt):
             b = next(batches, None)
             if b is not None:
                 model.prefetch(b.data_sequences())
+            pending = None
             while b is not None:
                 size = b.labels.shape[0]
                 model.train_step(fetch=False)  # consumes the staged batch
+                handle = model.fetch_scalars_async()  # D2H loss of this step
                 b = next(batches, None)
                 if b is not None:
                     model.prefetch(b.data_sequences())
-                model.fetch_scalars()  # D2H loss of this step (synchronises: staging buffers may be reused)
+                if pending is not None:
+                    pending.result()  # read step k-1 while step k runs (staging buffers are reused 6 batches later)
+                pending = handle
                 n += size
+            if pending is not None:
+                pending.result()
             return n
         epoch()  # page cache, pinned staging ring and static device buffers warm
         epoch()
@@ -472,7 +478,8 @@ def main():
     # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ---------------
     # The H2D copy of step k+1's batch is issued (copy stream) right after step k is launched, so it overlaps
     # the compute of step k - the input-pipeline prefetch the reference gets from tf.data (io_utils.py:145).
-    # Every step still copies its full batch from pinned host memory and reads its loss back.
+    # Every step still copies its full batch from pinned host memory and reads its loss back (the read of step k is
+    # waited for after step k+1 has been launched, so the host round trip is off the GPU's critical path).
     for _ in range(2):
         model.train_step(ds_host, fetch=True)
     barrier()
@@ -480,11 +487,16 @@ def main():
     t_wall = time.perf_counter()
     e2.record()
     model.prefetch(ds_host)
+    pending = None
     for i in range(args.steps):
         model.train_step(fetch=False)          # consumes the prefetched batch, launches the step
+        handle = model.fetch_scalars_async()   # D2H of THIS step's loss / grad norm into pinned memory
         if i + 1 < args.steps:
             model.prefetch(ds_host)            # next batch's H2D overlaps this step
-        loss, gnorm = model.fetch_scalars()    # D2H read of this step's loss / grad norm (synchronises)
+        if pending is not None:
+            loss, gnorm = pending.result()     # the host reads step i-1 while step i runs: the GPU never idles
+        pending = handle
+    loss, gnorm = pending.result()
     e3.record()
     barrier()
     e2e_wall = (time.perf_counter() - t_wall) * 1e3

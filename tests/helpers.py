@@ -5,7 +5,6 @@ from __future__ import annotations
 import numpy as np
 
 from avsr_tf1_b200 import make_batched_data, make_hparams
-from oracle.avsr_oracle import OracleHParams
 
 PARITY = dict(use_dropout=False, sampling_probability_outputs=0.0, regress_aus=False)
 
@@ -37,8 +36,11 @@ def config_hparams(cfg: int, units=None, **over):
     return make_hparams(**kw)
 
 
-def oracle_hparams(hp, model=None) -> OracleHParams:
-    """model: the product model whose generator words / stream ids the oracle should use (dropout, sampling)."""
+def oracle_hparams(hp, model=None):
+    """model: the product model whose generator words / stream ids the oracle should use (dropout, sampling).
+    (The oracle is imported here, not at module level: bench.py's product arm uses this module's workload helpers and
+    must not load the checker.)"""
+    from oracle.avsr_oracle import OracleHParams
     rev = {v: k for k, v in hp.unit_dict.items()}
     rand = {}
     if model is not None:
