@@ -373,6 +373,36 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
   if (p_tf32) p_tf32[i] = tf32_rn(pn);
 }
 
+// the reference's other optimisers (seq2seq.py:200-219), same single pass: Nadam (apply_adam use_nesterov=True), AdamW
+// (tf.contrib.opt: var -= weight_decay * var, NOT scaled by the learning rate, then the Adam update), Momentum 0.9
+__global__ void optim_clip_kernel(int kind, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                  float* __restrict__ v, long long n, const float* __restrict__ sumsq, float clip,
+                                  const float* __restrict__ lr_t_dev, float b1, float b2, float eps, float wd,
+                                  float* __restrict__ p_tf32) {
+  const float lr_t = lr_t_dev[0];
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float scale = 1.0f;
+  if (clip > 0.0f) scale = clip / fmaxf(sqrtf(sumsq[0]), clip);
+  const float gi = g[i] * scale;
+  float pn = p[i];
+  if (kind == AVSR_OPT_MOMENTUM) {
+    const float acc = b1 * m[i] + gi;
+    m[i] = acc;
+    pn -= lr_t * acc;
+  } else {
+    if (kind == AVSR_OPT_ADAMW) pn -= wd * pn;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float num = kind == AVSR_OPT_NADAM ? mi * b1 + (1.0f - b1) * gi : mi;
+    pn -= lr_t * num / (sqrtf(vi) + eps);
+  }
+  p[i] = pn;
+  if (p_tf32) p_tf32[i] = tf32_rn(pn);
+}
+
 __global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = tf32_rn(src[i]);
@@ -698,6 +728,16 @@ int avsr_adam_clip_step(avsr_stream_t s, float* params, const float* grads, floa
   if (n <= 0) return 0;
   AVSR_LAUNCH(adam_clip_kernel, cdiv(n, 256), 256, 0, ST(s), params, grads, m, v, n, sumsq_dev, clip_norm, lr_t,
               beta1, beta2, eps, params_tf32);
+  return 0;
+}
+
+int avsr_optim_clip_step(avsr_stream_t s, int kind, float* params, const float* grads, float* m, float* v, long long n,
+                         const float* sumsq_dev, float clip_norm, const float* lr_t, float beta1, float beta2, float eps,
+                         float weight_decay, float* params_tf32) {
+  AVSR_REQUIRE(kind >= AVSR_OPT_ADAM && kind <= AVSR_OPT_MOMENTUM, "optimiser kind %d unknown", kind);
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(optim_clip_kernel, cdiv(n, 256), 256, 0, ST(s), kind, params, grads, m, v, n, sumsq_dev, clip_norm, lr_t,
+              beta1, beta2, eps, weight_decay, params_tf32);
   return 0;
 }
 

@@ -203,6 +203,19 @@ def adam_clip_step(params, grads, m, v, sumsq_dev, clip_norm, lr_t, beta1=0.9, b
                                           beta1, beta2, eps, _p(params_tf32)))
 
 
+OPTIMISERS = {'Adam': 0, 'Nadam': 1, 'AdamW': 2, 'Momentum': 3}
+
+
+def optim_clip_step(kind, params, grads, m, v, sumsq_dev, clip_norm, lr_t, beta1=0.9, beta2=0.999, eps=1e-8,
+                    weight_decay=0.0, params_tf32=None):
+    """clip_by_global_norm + one of the reference's optimisers (include/avsr_b200.h avsr_optim_clip_step)."""
+    lr = _dev_scalar(lr_t)
+    check(_lib.load().avsr_optim_clip_step(_stream(), OPTIMISERS[kind], params.data_ptr(), grads.data_ptr(),
+                                           m.data_ptr(), v.data_ptr(), params.numel(), sumsq_dev.data_ptr(),
+                                           float(clip_norm), lr.data_ptr(), beta1, beta2, eps, float(weight_decay),
+                                           _p(params_tf32)))
+
+
 def normed_v_fwd(v, g, veff):
     check(_lib.load().avsr_normed_v_fwd(_stream(), v.data_ptr(), g.data_ptr(), v.numel(), veff.data_ptr()))
 

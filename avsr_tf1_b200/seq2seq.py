@@ -202,9 +202,8 @@ class Seq2SeqModel(object):
                 'focal_loss', 'mc_loss') else NotImplementedError('devel.py losses are self-described untested')
         if hp.label_smoothing > 0.0:
             raise NotImplementedError('label smoothing is off in every reference config')
-        if hp.optimiser != 'Adam':
-            raise Exception('Unsupported optimiser, try Adam') if hp.optimiser not in (
-                'Nadam', 'AdamW', 'Momentum') else NotImplementedError('only Adam is built on the B200 path')
+        if hp.optimiser not in ops.OPTIMISERS:  # Adam, Nadam, AdamW, Momentum (seq2seq.py:195-219)
+            raise Exception('Unsupported optimiser, try Adam')
         if hp.lr_decay is not None:
             raise NotImplementedError('cosine_restarts lr decay is not used by any shipped script')
         self._l2_names = [n for n in self.store.names() if 'lstm_' in n and 'bias' not in n]  # seq2seq.py:283-290
@@ -473,8 +472,14 @@ class Seq2SeqModel(object):
         _scal_dev[1] written by _set_step_scalars (warm-up + bias correction, seq2seq.py:275-280)."""
         hp, st = self._hparams, self.store
         clip = hp.max_gradient_norm if hp.clip_gradients is True else 0.0
-        ops.adam_clip_step(st.flat, st.grad, st.m, st.v, self._loss_dev[2:3], clip, self._scal_dev[1:2], 0.9, 0.999,
-                           1e-8, params_tf32=st.flat_tc)
+        if hp.optimiser == 'Adam':
+            ops.adam_clip_step(st.flat, st.grad, st.m, st.v, self._loss_dev[2:3], clip, self._scal_dev[1:2], 0.9, 0.999,
+                               1e-8, params_tf32=st.flat_tc)
+        else:
+            ops.optim_clip_step(hp.optimiser, st.flat, st.grad, st.m, st.v, self._loss_dev[2:3], clip,
+                                self._scal_dev[1:2], 0.9, 0.999, 1e-8,
+                                weight_decay=hp.weight_decay if hp.optimiser == 'AdamW' else 0.0,
+                                params_tf32=st.flat_tc)
 
     def _set_step_scalars(self):
         """Host scalars of this step -> device (outside any captured graph)."""
@@ -493,8 +498,9 @@ class Seq2SeqModel(object):
             cnt = parallel.global_token_count(self._meta['au_count'], device='cuda') if ctx.world_size > 1 \
                 else self._meta['au_count']
             self._au_scale = float(self._hparams.kwargs.get('au_loss_weight', 10.0)) / max(cnt, 1.0)
-        self._scal_dev.copy_(torch.tensor([self._inv_denom, lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t),
-                                           self._au_scale], dtype=torch.float32))
+        # Adam family: the bias correction is folded into the step size; Momentum takes the plain learning rate
+        lr_t = lr if self._hparams.optimiser == 'Momentum' else lr * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        self._scal_dev.copy_(torch.tensor([self._inv_denom, lr_t, self._au_scale], dtype=torch.float32))
         self._ctx.rng.copy_(torch.tensor(self.rng_words(), dtype=torch.int32))
 
     def rng_words(self):

@@ -237,6 +237,16 @@ int avsr_adam_clip_step(avsr_stream_t stream, float* params, const float* grads,
                         const float* sumsq_dev, float clip_norm, const float* lr_t_dev, float beta1, float beta2,
                         float eps, float* params_tf32 /* tf32-rounded copy kept in sync, or NULL */);
 
+/* the optimisers of seq2seq.py:195-219 in the same single pass.  ADAM: as above.  NADAM: tf.contrib.opt.NadamOptimizer
+ * (apply_adam with use_nesterov: numerator beta1*m + (1-beta1)*g).  ADAMW: tf.contrib.opt.AdamWOptimizer - decoupled
+ * decay var -= weight_decay * var (not scaled by the learning rate) before the Adam update.  MOMENTUM:
+ * tf.train.MomentumOptimizer(momentum = beta1, no nesterov): m = beta1*m + g; var -= lr*m (lr_t_dev holds the plain
+ * learning rate; v, beta2, eps unused). */
+enum { AVSR_OPT_ADAM = 0, AVSR_OPT_NADAM = 1, AVSR_OPT_ADAMW = 2, AVSR_OPT_MOMENTUM = 3 };
+int avsr_optim_clip_step(avsr_stream_t stream, int kind, float* params, const float* grads, float* m, float* v,
+                         long long n, const float* sumsq_dev, float clip_norm, const float* lr_t_dev, float beta1,
+                         float beta2, float eps, float weight_decay, float* params_tf32);
+
 /* ---- inference helpers (decoder_unimodal.py:176-271) -------------------------- */
 /* greedy: ids[b] = argmax_v logits[b,:] (lowest index on ties) unless finished[b]; updates finished */
 int avsr_greedy_pick(avsr_stream_t stream, const float* logits, int B, int V, int eos, int* finished,

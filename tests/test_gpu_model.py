@@ -237,3 +237,40 @@ def test_decoding_and_error_rates(cfg, algo):
         assert utils.compute_wer(pred, truth, split_words=True) == O.compute_wer(pred, truth, split_words=True)
     finally:
         ops.set_tensor_cores(old)
+
+
+@pytest.mark.parametrize('optimiser', ['Nadam', 'AdamW', 'Momentum'])
+def test_other_optimisers(optimiser, tensor_cores):
+    """The reference's alternatives to Adam (seq2seq.py:200-219), three steps against the oracle.  AdamW switches the
+    recurrent L2 term off (avsr.py:172) and decays every variable by weight_decay (not scaled by the learning rate)."""
+    hp, batch, ds, model = build(5, dict(optimiser=optimiser, weight_decay=1e-2), B=4, Ta=30, Tv=10, L=6)
+    assert (hp.recurrent_l2_regularisation is None) == (optimiser == 'AdamW')
+    om, P = oracle_for(hp, model)
+    names = model.store.names()
+    m = {k: np.zeros_like(P[k]) for k in names}
+    v = {k: np.zeros_like(P[k]) for k in names}
+    P0 = {k: P[k].copy() for k in names}
+    b64 = cast_batch(batch, np.float64)
+    for step in range(3):
+        loss_ref, G_ref, _ = om.loss_and_grads(b64)
+        Pt = {k: P[k] for k in names}
+        gn_ref = O.clip_and_adam(Pt, G_ref, m, v, step, hp.learning_rate, clip=hp.max_gradient_norm, warmup_steps=750,
+                                 optimiser=optimiser, weight_decay=hp.weight_decay)
+        P.update(Pt)
+        loss, gn = model.train_step(ds)
+        assert abs(loss - loss_ref) <= 1e-3 * abs(loss_ref), (step, loss, loss_ref)
+        assert abs(gn - gn_ref) <= 5e-3 * gn_ref, (step, gn, gn_ref)
+    got = model.store.to_numpy('p')
+    lr_sum = sum(hp.learning_rate * (s + 1) / 750.0 for s in range(3))
+    for k in names:
+        moved = np.abs(P[k] - P0[k]).max()
+        diff = np.abs(got[k].astype(np.float64) - P[k])
+        if optimiser == 'Momentum':  # linear in the gradient: tight everywhere
+            assert diff.max() <= 2e-2 * moved + 1e-9, (k, diff.max(), moved)
+        else:  # sign-like first steps, see test_three_training_steps
+            assert diff.max() <= 2.2 * lr_sum + 1e-6 * np.abs(P[k]).max() + 1e-7, (k, diff.max())
+            frac = (diff > 0.05 * lr_sum + 1e-6 * np.abs(P[k]).max()).mean()
+            assert frac < (3e-2 if tensor_cores else 2e-3), (k, frac)
+    if optimiser == 'AdamW':  # the decay is visible: a bias-free kernel shrinks by about 3 * weight_decay
+        k = 'Decoder/decoder/my_dense/kernel'
+        assert abs(np.abs(got[k]).sum() / np.abs(P0[k]).sum() - (1 - 3e-2)) < 5e-3
