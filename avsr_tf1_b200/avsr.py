@@ -50,8 +50,10 @@ class AVSR(object):
                                       'built: use video_processing=`features`')
         if audio_processing is not None and audio_processing != 'features':
             raise NotImplementedError('`wav` audio processing (avsr/audio.py) is out of scope: use `features`')
-        if write_attention_alignment or write_beam_search_graphs or write_estimated_modality_lags:
-            raise NotImplementedError('visualisation artefacts (avsr/visualise) are out of scope')
+        if write_beam_search_graphs or write_estimated_modality_lags:
+            raise NotImplementedError('beam-search html graphs and modality-lag artefacts (avsr/visualise) are out '
+                                      'of scope')
+        self._write_attention_alignment = write_attention_alignment
         self._unit = unit
         self._unit_dict = create_unit_dict(unit_file=unit_file)
         self._video_processing, self._audio_processing = video_processing, audio_processing
@@ -62,7 +64,8 @@ class AVSR(object):
         self._workdir, self._seed, self._verbose = workdir, seed, verbose
         self._hparams = make_hparams(unit=unit, unit_file=unit_file, video_processing=video_processing,
                                      audio_processing=audio_processing, batch_size=batch_size,
-                                     unit_dict=self._unit_dict, **kwargs)
+                                     unit_dict=self._unit_dict,
+                                     write_attention_alignment=write_attention_alignment, **kwargs)
         self._train_model = self._evaluate_model = None
         self._create_models()
 
@@ -163,6 +166,23 @@ class AVSR(object):
                         f.flush()
                         self.last_error_rate = error_rate
 
+    def _write_alignment_images(self, model, names, outdir):
+        """avsr.py:409-436: <file>.png (decoder attention; `_video` / `_audio` for the bimodal decoder) and <file>_av.png
+        (cross-modal attention of the AV-Align encoder); pixel = 1 - alignment, rows = memory steps."""
+        from .utils import write_png_gray
+        dec = model._decoder.attention_summary
+        arch = self._hparams.architecture
+        for idx in range(len(names)):
+            fname = path.join(outdir, names[idx].decode('utf-8'))
+            makedirs(path.dirname(fname) or '.', exist_ok=True)
+            if arch == 'bimodal':
+                write_png_gray(fname + '_video.png', dec[0][idx, :, :, 0])
+                write_png_gray(fname + '_audio.png', dec[1][idx, :, :, 0])
+            else:
+                write_png_gray(fname + '.png', dec[idx, :, :, 0])
+                if arch == 'av_align':
+                    write_png_gray(fname + '_av.png', model._audio_encoder.attention_summary[idx, :, :, 0])
+
     # ---- evaluation (avsr.py:322-512) ---------------------------------------------------------------------------
     def evaluate(self, checkpoint_path, epoch=None, alignments_outdir='./alignments/tmp/',
                  beam_graphs_outdir='./beam_graphs/tmp/'):
@@ -179,6 +199,8 @@ class AVSR(object):
             names = em.data.inputs_filenames
             names = names[0] if isinstance(names, tuple) else names
             labels = em.data.labels.numpy()
+            if self._write_attention_alignment is True:
+                self._write_alignment_images(em.model, names, alignments_outdir)
             for idx in range(len(names)):
                 file = names[idx].decode('utf-8')
                 predictions_dict[file] = [self._unit_dict[int(sym)] for sym in predicted[idx]]

@@ -65,6 +65,7 @@ class Seq2SeqUnimodalDecoder(object):
         self.sample_ids = None  # [T,B] int32 device: ids drawn by the helper (-1 = ground truth kept), last train step
         self.inference_predicted_ids = None
         self.beam_search_output = None
+        self.attention_alignment = self.attention_summary = None
 
     def _init_embedding(self):
         hp, ctx = self._hparams, self._ctx
@@ -190,11 +191,15 @@ class Seq2SeqUnimodalDecoder(object):
         finished = torch.zeros(B, dtype=torch.int32, device='cuda')
         active = torch.ones(B, dtype=torch.int32, device='cuda')
         samples = []
+        history = [[] for _ in bufs] if hp.write_attention_alignment else None
         for _ in range(hp.max_label_length):
             x = ops.empty(1, B, self._E)
             ops.embedding_fwd(ctx.w(self._embedding), ids, x)
             torch.sub(1, finished, out=active)  # finished rows carry their state (impute_finished)
             out, state = self._cell.step(x, active, bufs, state)
+            if history is not None:  # alignment_history (attention.py:178)
+                for k, mb in enumerate(bufs):
+                    history[k].append(mb.align[0].clone())
             logits = self._logits_step(out)
             sample = torch.empty(B, dtype=torch.int32, device='cuda')
             nxt = torch.empty(B, dtype=torch.int32, device='cuda')
@@ -204,12 +209,21 @@ class Seq2SeqUnimodalDecoder(object):
             if bool(finished.all().item()):
                 break
         self.inference_predicted_ids = torch.stack(samples, dim=1).cpu().numpy().astype(np.int32)
+        if history is not None:
+            # _create_attention_alignments_summary (decoder_unimodal.py:273-290, decoder_bimodal.py:447-467):
+            # [T, B, Tm] -> [B, Tm, T, 1]; one per mechanism for the bimodal decoder (video first)
+            al = [torch.stack(h, 0).permute(1, 2, 0).unsqueeze(-1).cpu().numpy() for h in history]
+            self.attention_alignment = al[0] if len(al) == 1 else al
+            self.attention_summary = 1.0 - al[0] if len(al) == 1 else [1.0 - a for a in al]
         return self.inference_predicted_ids
 
     def decode_beam(self, memories, encoder_states):
         """BeamSearchDecoder(beam_width, length_penalty_weight) + gather_tree
         (decoder_unimodal.py:222-271).  Returns beam 0 ids [B, T]."""
         ctx, hp = self._ctx, self._hparams
+        if hp.write_attention_alignment:
+            raise NotImplementedError('alignment images are produced by greedy decoding here: the reference reads '
+                                      'cell_state.alignment_history[0] of the beam-search state, which is not a history')
         W = hp.beam_width
         B = memories[0][0].shape[1]
         init = self._initial_state_fwd(encoder_states)

@@ -302,8 +302,13 @@ class AttentiveEncoder(Seq2SeqEncoder):
         self._outputs_op = self._round_outputs(self._outputs, self._top) if not self._top.output_attention \
             else self._top.operand
         self._final = self._top.final  # wrapper stripped: cell state only (encoder.py:314-330)
-        self.attention_alignment = self._top.bufs[0].align  # [T_audio, B, T_video]
+        self.alignment_history = self._top.bufs[0].align    # [T_audio, B, T_video] device tensor
         self.attention_contexts = self._top.bufs[0].hc      # [T_audio, B, H + Dm]
+        if self._hparams.write_attention_alignment:
+            # encoder.py:296-310: alignment_history stacked and transposed to [B, T_video, T_audio, 1]; the summary is
+            # the image 1 - alignment (host arrays here instead of tf.Summary protos)
+            self.attention_alignment = self.alignment_history.permute(1, 2, 0).unsqueeze(-1).cpu().numpy()
+            self.attention_summary = 1.0 - self.attention_alignment
         return self.get_data()
 
     def forward(self, inputs, inputs_len, attended_memory=None, attended_memory_length=None,

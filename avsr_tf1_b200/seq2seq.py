@@ -26,6 +26,21 @@ from .layers import BuildContext
 from .params import ParamStore
 
 
+def cosine_decay_restarts(learning_rate, global_step, first_decay_steps, t_mul=2.0, m_mul=1.0, alpha=0.0):
+    """tf.train.cosine_decay_restarts (SGDR) with the TF 1.13 defaults the reference uses (seq2seq.py:266-270): cosine
+    from 1 to alpha over a period, periods growing by t_mul, peak scaled by m_mul per restart."""
+    completed = float(global_step) / float(first_decay_steps)
+    if t_mul == 1.0:
+        i_restart = math.floor(completed)
+        completed -= i_restart
+    else:
+        i_restart = math.floor(math.log(1.0 - completed * (1.0 - t_mul)) / math.log(t_mul))
+        sum_r = (1.0 - t_mul ** i_restart) / (1.0 - t_mul)
+        completed = (completed - sum_r) / t_mul ** i_restart
+    cosine_decayed = 0.5 * (m_mul ** i_restart) * (1.0 + math.cos(math.pi * completed))
+    return learning_rate * ((1.0 - alpha) * cosine_decayed + alpha)
+
+
 class _PendingScalars(object):
     """Result of Seq2SeqModel.fetch_scalars_async()."""
 
@@ -204,8 +219,6 @@ class Seq2SeqModel(object):
             raise NotImplementedError('label smoothing is off in every reference config')
         if hp.optimiser not in ops.OPTIMISERS:  # Adam, Nadam, AdamW, Momentum (seq2seq.py:195-219)
             raise Exception('Unsupported optimiser, try Adam')
-        if hp.lr_decay is not None:
-            raise NotImplementedError('cosine_restarts lr decay is not used by any shipped script')
         self._l2_names = [n for n in self.store.names() if 'lstm_' in n and 'bias' not in n]  # seq2seq.py:283-290
         self._loss_dev = torch.zeros(4, dtype=torch.float32, device=self.store.flat.device)
 
@@ -447,6 +460,12 @@ class Seq2SeqModel(object):
     def _lr_now(self):
         hp = self._hparams
         lr = hp.learning_rate
+        if hp.lr_decay is not None:  # seq2seq.py:263-273
+            if hp.lr_decay[0] == 'cosine_restarts':
+                lr = cosine_decay_restarts(lr, self._global_step, hp.lr_decay[1])
+            elif not getattr(self, '_lr_policy_warned', False):
+                print('learning rate policy not implemented, falling back to constant learning rate')
+                self._lr_policy_warned = True
         steps = hp.kwargs.get('warmup_steps', 750)
         if steps:
             lr *= min(1.0, (self._global_step + 1) / float(steps))  # seq2seq.py:275-280

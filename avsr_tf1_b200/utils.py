@@ -50,3 +50,21 @@ def write_sequences_to_labelfile(sequence_dict, fname, original_dict, error_dict
             label_str = sep.join(_strip_extra_chars(v))
             truth = sep.join(_strip_extra_chars(original_dict[k]))
             f.write(' '.join([k, label_str, '[{}] [{:.3f}]'.format(truth, error_dict[k])]) + '\n')
+
+
+def write_png_gray(fname, image):
+    """8-bit greyscale PNG of a [H, W] array in [0, 1] (what tf.summary.image encodes for the alignment images,
+    avsr.py:409-436); zlib + the PNG chunk format only."""
+    import struct
+    import zlib
+
+    import numpy as np
+    img = (np.clip(np.asarray(image, np.float64), 0.0, 1.0) * 255.0 + 0.5).astype(np.uint8)
+    h, w = img.shape
+    raw = b''.join(b'\x00' + img[r].tobytes() for r in range(h))
+
+    def chunk(tag, data):
+        return struct.pack('>I', len(data)) + tag + data + struct.pack('>I', zlib.crc32(tag + data) & 0xFFFFFFFF)
+    with open(fname, 'wb') as f:
+        f.write(b'\x89PNG\r\n\x1a\n' + chunk(b'IHDR', struct.pack('>IIBBBBB', w, h, 8, 0, 0, 0, 0)) +
+                chunk(b'IDAT', zlib.compress(raw, 6)) + chunk(b'IEND', b''))

@@ -79,3 +79,28 @@ def test_run_experiment_curriculum(records, tmp_path):
     assert lines[0].startswith('Warm up on short sentences up to 6 tokens for 2 epochs')
     assert lines.count('=====') == 2 and lines.count('=' * 20) == 1
     assert sum(l.startswith('Average batch_loss') for l in lines) == 1 + 2 + 1
+
+
+def test_alignment_images(records, tmp_path):
+    """write_attention_alignment=True (avsr.py:353-436): alignment_history of the decoder and of the cross-modal encoder
+    in the reference's [B, T_memory, T_query, 1] layout, dumped as <file>.png / <file>_av.png (pixel = 1 - weight)."""
+    cv2 = pytest.importorskip('cv2')
+    exp = make(records, tmp_path, write_attention_alignment=True, use_dropout=False, sampling_probability_outputs=0.0)
+    exp.train(logfile=str(tmp_path / 'logs' / 'al'), num_epochs=2)
+    ckpt = exp._train_model.model.saver.save(None, str(tmp_path / 'checkpoints' / 'al' / 'checkpoint.ckp'), global_step=1)
+    out = str(tmp_path / 'alignments')
+    exp.evaluate(ckpt, epoch=1, alignments_outdir=out)
+    model = exp._evaluate_model.model
+    dec, enc = model._decoder.attention_alignment, model._audio_encoder.attention_alignment
+    B = dec.shape[0]
+    assert dec.ndim == 4 and dec.shape[3] == 1 and enc.shape[0] == B and enc.shape[3] == 1
+    assert dec.shape[1] == enc.shape[2]  # decoder memory = audio steps; encoder memory = video steps
+    ids = model._decoder.inference_predicted_ids
+    for b in range(B):
+        steps = int((ids[b] != 0).sum())  # steps before the row finished carry a distribution over the memory
+        col = dec[b, :, :steps, 0].sum(axis=0)
+        assert np.allclose(col, 1.0, atol=1e-4), col
+    pngs = sorted(os.listdir(out))
+    assert len(pngs) == 2 * 10 and pngs[0] == 'utt000000.png' and pngs[1] == 'utt000000_av.png'
+    img = cv2.imread(os.path.join(out, pngs[-2]), cv2.IMREAD_GRAYSCALE)
+    assert img.shape == dec.shape[1:3]  # last batch: same padded sizes as the arrays still held by the model

@@ -132,3 +132,34 @@ def test_reference_default_randomness_builds_and_gets_its_own_streams():
     ds = to_data_sequences(synthetic_batch(hp, B=2, Ta=8, Tv=4, L=3))
     ev = Seq2SeqModel(ds, 'evaluate', hp, device='cpu')
     assert ev.random_streams == {}
+
+
+def test_cosine_decay_restarts_schedule():
+    """tf.train.cosine_decay_restarts(lr, step, first_decay_steps) with t_mul = 2, m_mul = 1, alpha = 0: hand values of
+    the closed form, then the model's lr with the 750-step warm-up on top (seq2seq.py:263-280)."""
+    from avsr_tf1_b200.seq2seq import cosine_decay_restarts as cdr
+    lr, first = 1e-3, 100
+    assert cdr(lr, 0, first) == pytest.approx(lr)
+    assert cdr(lr, 50, first) == pytest.approx(0.5 * lr)
+    assert cdr(lr, 99, first) == pytest.approx(0.5 * lr * (1 + np.cos(np.pi * 0.99)))
+    assert cdr(lr, 100, first) == pytest.approx(lr)            # first restart, period 200
+    assert cdr(lr, 200, first) == pytest.approx(0.5 * lr)      # halfway through it
+    assert cdr(lr, 300, first) == pytest.approx(lr)            # second restart, period 400
+    assert cdr(lr, 500, first) == pytest.approx(0.5 * lr)
+    assert cdr(lr, 25, first, t_mul=1.0) == pytest.approx(cdr(lr, 125, first, t_mul=1.0))
+    hp, m = build(1, lr_decay=('cosine_restarts', 100))
+    m._global_step = 50
+    assert m._lr_now() == pytest.approx(0.5 * hp.learning_rate * 51 / 750.0)
+    hp, m = build(1, lr_decay=('exponential', 10))  # unknown policy: constant lr, like the reference
+    assert m._lr_now() == pytest.approx(hp.learning_rate / 750.0)
+
+
+def test_png_writer_round_trips(tmp_path):
+    cv2 = pytest.importorskip('cv2')
+    from avsr_tf1_b200.utils import write_png_gray
+    img = np.random.default_rng(0).uniform(0, 1, (37, 53))
+    f = str(tmp_path / 'a.png')
+    write_png_gray(f, img)
+    back = cv2.imread(f, cv2.IMREAD_GRAYSCALE)
+    assert back.shape == (37, 53)
+    assert np.array_equal(back, (img * 255.0 + 0.5).astype(np.uint8))
