@@ -266,7 +266,7 @@ def test_other_optimisers(optimiser, tensor_cores):
         moved = np.abs(P[k] - P0[k]).max()
         diff = np.abs(got[k].astype(np.float64) - P[k])
         if optimiser == 'Momentum':  # linear in the gradient: tight everywhere
-            assert diff.max() <= 2e-2 * moved + 1e-9, (k, diff.max(), moved)
+            assert diff.max() <= 2e-2 * moved + 1.2e-7 * np.abs(P[k]).max() + 1e-9, (k, diff.max(), moved)  # (+ 1 fp32 ulp)
         else:  # sign-like first steps, see test_three_training_steps
             assert diff.max() <= 2.2 * lr_sum + 1e-6 * np.abs(P[k]).max() + 1e-7, (k, diff.max())
             frac = (diff > 0.05 * lr_sum + 1e-6 * np.abs(P[k]).max()).mean()
