@@ -1,0 +1,20 @@
+"""`ncu -i X.ncu-rep --page raw --csv` -> a small transposed table of the metrics the design notes quote."""
+import csv, sys
+KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__inst_issued.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size',
+        'launch__block_size', 'launch__cluster_size', 'smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct',
+        'smsp__warp_issue_stalled_barrier_per_warp_active.pct', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct']
+rows = list(csv.reader(open(sys.argv[1])))
+hdr = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
+names, units, data = rows[hdr], rows[hdr + 1], rows[hdr + 2:]
+kcol = names.index('Kernel Name')
+print('metric,unit,' + ','.join('"%s"' % r[kcol][:70] for r in data))
+for m in KEEP:
+    cols = [i for i, n in enumerate(names) if n == m or n.endswith('.' + m)]
+    if not cols:
+        continue
+    c = cols[0]
+    print('%s,%s,%s' % (m, units[c], ','.join(r[c].replace(',', '') for r in data)))
