@@ -12,7 +12,7 @@ import collections
 import glob
 import re
 import time
-from os import makedirs, path
+from os import devnull, makedirs, path
 
 import numpy as np
 
@@ -86,6 +86,8 @@ class AVSR(object):
         audio = pick(self._audio_train_record, self._audio_test_record)
         common = dict(batch_size=batch_size, unit_dict=self._hparams.unit_dict, shuffle=train, reverse_input=False,
                       bucket_width=45, seed=self._seed)
+        if train:  # one process per GPU: batch_size is the GLOBAL batch, every rank trains on its slice of each batch
+            common['shard'] = (parallel.rank(), parallel.world_size())
         if self._video_processing is not None and self._audio_processing is not None:
             return make_iterator_from_two_records(video_record=video, audio_record=audio, label_record=labels, **common)
         if self._video_processing is not None:
@@ -137,7 +139,7 @@ class AVSR(object):
                 last_epoch = 0
                 self._say('Could not restore from checkpoint, training from scratch!\n')
         self.last_error_rate = None
-        with open(logfile, 'a') as f:
+        with open(logfile if parallel.rank() == 0 else devnull, 'a') as f:
             for current_epoch in range(1, num_epochs):
                 epoch = last_epoch + current_epoch
                 tm.data.iterator_initializer()
@@ -157,14 +159,16 @@ class AVSR(object):
                 f.write('Average batch_loss as epoch {} is {}\n'.format(epoch, sum_loss / max(batches, 1)))
                 f.flush()
                 if epoch % 10 == 0:
-                    save_path = tm.model.saver.save(sess=None, save_path=checkpoint_path, global_step=epoch)
-                    if self._evaluate_model is not None:
-                        error_rate = self.evaluate(save_path, epoch)
-                        for (k, v) in error_rate.items():
-                            f.write(k + ': {:.4f}% '.format(v * 100))
-                        f.write('\n')
-                        f.flush()
-                        self.last_error_rate = error_rate
+                    if parallel.rank() == 0:  # replicas hold identical parameters: rank 0 saves and evaluates
+                        save_path = tm.model.saver.save(sess=None, save_path=checkpoint_path, global_step=epoch)
+                        if self._evaluate_model is not None:
+                            error_rate = self.evaluate(save_path, epoch)
+                            for (k, v) in error_rate.items():
+                                f.write(k + ': {:.4f}% '.format(v * 100))
+                            f.write('\n')
+                            f.flush()
+                            self.last_error_rate = error_rate
+                    parallel.barrier()
 
     def _write_alignment_images(self, model, names, outdir):
         """avsr.py:409-436: <file>.png (decoder attention; `_video` / `_audio` for the bimodal decoder) and <file>_av.png

@@ -71,7 +71,7 @@ class RecordBatcher(object):
 
     def __init__(self, input_records, label_record, unit_dict, batch_size, shuffle=False, reverse_input=False,
                  bucket_width=-1, num_cores=4, max_sentence_length=None, seed=0, pin_memory=True, prefetch=2,
-                 shuffle_buffer=SHUFFLE_BUFFER):
+                 shuffle_buffer=SHUFFLE_BUFFER, shard=None):
         from .tfrecord import KIND_LABELS, RecordFile
         self._inputs = [RecordFile(p) for p in input_records]
         self._labels = RecordFile(label_record)
@@ -90,6 +90,10 @@ class RecordBatcher(object):
         self.max_sentence_length = max_sentence_length
         self._rng = np.random.default_rng(seed)
         self._pin, self._prefetch, self._shuffle_buffer = pin_memory, int(prefetch), int(shuffle_buffer)
+        # data parallelism (no counterpart in the single-device reference): every rank walks the SAME global batches
+        # (same seed) and assembles only its contiguous slice of each; batches smaller than the world are dropped so
+        # that all ranks take the same number of steps (their collectives must pair up)
+        self._shard = None if shard is None or int(shard[1]) <= 1 else (int(shard[0]), int(shard[1]))
         self.has_aus = any(f.has_aus for f in self._inputs[:1])
         self._queue = self._thread = None
         self._current = None
@@ -121,7 +125,21 @@ class RecordBatcher(object):
         return out
 
     def batches_of_epoch(self):
-        """List of index arrays, one per batch, in emission order."""
+        """List of index arrays, one per batch, in emission order (this rank's slice under data parallelism)."""
+        batches = self._global_batches()
+        if self._shard is None:
+            return batches
+        from .parallel import shard_batch
+        r, w = self._shard
+        out = []
+        for idx in batches:
+            if len(idx) < w:
+                continue
+            lo, hi = shard_batch(len(idx), r, w)
+            out.append(idx[lo:hi])
+        return out
+
+    def _global_batches(self):
         order = self._element_order()
         B = self.batch_size
         if self.bucket_width == -1:

@@ -26,6 +26,11 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def barrier():
+    if world_size() > 1:
+        dist.barrier()
+
+
 def global_token_count(local_tokens: float, device=None) -> float:
     """Sum of labels_len over all ranks: the loss denominator of the global batch."""
     if world_size() == 1:

@@ -302,3 +302,30 @@ def test_one_record_iterator_order_filter_and_reverse(tmp_path):
     lit = io_utils.make_iterator_from_label_record(lp, batch_size=5, unit_dict=unit_dict, prefetch=0)
     b = next(iter(lit))
     assert b.inputs is None and b.labels.shape[0] == 5
+
+
+def test_data_parallel_shards_walk_the_same_batches(tmp_path):
+    """shard=(rank, world): same global batches on every rank (same seed), disjoint contiguous slices, the same number
+    of steps everywhere (batches smaller than the world are dropped), union = the unsharded epoch."""
+    unit_dict = create_unit_dict(None)
+    vp, ap, lp, data = _write_set(tmp_path, 45)
+    kw = dict(batch_size=8, unit_dict=unit_dict, shuffle=True, bucket_width=4, seed=11, shuffle_buffer=8, prefetch=0)
+    full = io_utils.make_iterator_from_two_records(vp, ap, lp, **kw)
+    world = 3
+    ranks = [io_utils.make_iterator_from_two_records(vp, ap, lp, shard=(r, world), **kw) for r in range(world)]
+    glob = full.batches_of_epoch()
+    per_rank = [it.batches_of_epoch() for it in ranks]
+    assert len({len(b) for b in per_rank}) == 1  # same number of steps on every rank
+    kept = [g for g in glob if len(g) >= world]
+    assert len(per_rank[0]) == len(kept)
+    for step, g in enumerate(kept):
+        parts = [per_rank[r][step] for r in range(world)]
+        assert np.array_equal(np.concatenate(parts), g)
+        sizes = [len(p) for p in parts]
+        assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 1
+    # the assembled batch of a rank is its slice of the global one (a fresh epoch reshuffles: rewind the generator)
+    ranks[1]._rng = np.random.default_rng(11)
+    first = ranks[1].batches_of_epoch()[0]
+    ranks[1]._rng = np.random.default_rng(11)
+    b = next(iter(ranks[1]))
+    assert b.labels_filenames.tolist() == [b'utt%06d' % i for i in first]
