@@ -271,11 +271,17 @@ class Seq2SeqModel(object):
         meta['h2d_bytes'] = sum(v.numel() * v.element_size() for v in src.values() if not v.is_cuda)
         return src, meta
 
+    MAX_INPUT_SETS = 16  # static input buffers kept per batch shape (bucketed epochs produce many shapes)
+
     def _static_buffers(self, key, src):
-        bufs = self._in_sets.get(key)
+        bufs = self._in_sets.pop(key, None)
         if bufs is None:
             bufs = {k: torch.empty(v.shape, dtype=v.dtype, device='cuda') for k, v in src.items()}
-            self._in_sets[key] = bufs
+            # least-recently-used shapes go first; a shape with a captured graph keeps its buffers (the graph reads them)
+            for old in [k for k in self._in_sets if k not in self._graphs][:max(0, len(self._in_sets) + 1 - self.MAX_INPUT_SETS)]:
+                del self._in_sets[old]
+                self._stage_sets.pop(old, None)
+        self._in_sets[key] = bufs  # (re)inserted last = most recently used
         return bufs
 
     def feed(self, data_sequences):
