@@ -329,3 +329,35 @@ def test_data_parallel_shards_walk_the_same_batches(tmp_path):
     ranks[1]._rng = np.random.default_rng(11)
     b = next(iter(ranks[1]))
     assert b.labels_filenames.tolist() == [b'utt%06d' % i for i in first]
+
+
+def test_golden_records_written_by_protobuf():
+    """tests/golden/sequence_examples_*.tfrecord were serialised by google.protobuf and framed with tensorboard's crc
+    (make_golden_records.py); the native reader must decode them to the JSON stored beside them."""
+    import json
+    g = os.path.join(ROOT, 'tests', 'golden')
+    want = json.load(open(os.path.join(g, 'sequence_examples.json')))
+    f = tfrecord.RecordFile(os.path.join(g, 'sequence_examples_feature.tfrecord'), verify_data=True)
+    v = tfrecord.RecordFile(os.path.join(g, 'sequence_examples_video.tfrecord'), verify_data=True)
+    l = tfrecord.RecordFile(os.path.join(g, 'sequence_examples_labels.tfrecord'), verify_data=True)
+    assert (f.kind, f.input_shape, f.has_aus) == (tfrecord.KIND_FEATURE, [5], False)
+    assert (v.kind, v.input_shape, v.has_aus) == (tfrecord.KIND_VIDEO, [2, 3, 3], True)  # [width, height, channels]
+    assert (l.kind, l.unit) == (tfrecord.KIND_LABELS, 'character')
+    n = len(want['labels'])
+    assert len(f) == len(v) == len(l) == n
+    idx = np.arange(n)
+    tf_, tv = int(f.lengths.max()), int(v.lengths.max())
+    xf, lf = np.zeros((n, tf_, 5), np.float32), np.zeros(n, np.int32)
+    xv, av, lv = np.zeros((n, tv, 18), np.float32), np.zeros((n, tv, 2), np.float32), np.zeros(n, np.int32)
+    f.fill_inputs(idx, tf_, xf, lf)
+    v.fill_inputs(idx, tv, xv, lv, aus_dst=av)
+    lp = int(l.lengths.max()) + 1
+    y, ly = np.zeros((n, lp), np.int32), np.zeros(n, np.int32)
+    l.fill_labels(idx, lp, 29, y, ly)
+    for i in range(n):
+        wf, wv, wl = want['feature'][i], want['video'][i], want['labels'][i]
+        assert f.filename(i).decode() == wf['filename'] == v.filename(i).decode() == l.filename(i).decode()
+        assert np.array_equal(xf[i, :lf[i]], np.asarray(wf['inputs'], np.float32)) and not xf[i, lf[i]:].any()
+        assert np.array_equal(xv[i, :lv[i]], np.asarray(wv['inputs'], np.float32))
+        assert np.array_equal(av[i, :lv[i]], np.asarray(wv['aus'], np.float32))
+        assert y[i, :ly[i]].tolist() == wl['labels'] + [29]
