@@ -4,8 +4,8 @@ predictions dumped as .mlf, error rates via utils.compute_wer.
 
 What differs by construction: there is no TF graph / session.  The train and evaluate "graphs" are two
 Seq2SeqModel objects fed by eager record iterators (io_utils.RecordBatcher); a checkpoint is the Saver's .npz.
-Front-ends that are out of scope here (`resnet_cnn` and the other CNNs, `wav` audio) raise: video enters as the
-features the record holds ('features' on a feature record, or raw lip crops as flat vectors)."""
+Video enters as the features a record holds (`features`, also raw lip crops as flat vectors) or as lip crops through
+the `resnet_cnn` front-end (video.py); the other CNNs and `wav` audio raise."""
 from __future__ import annotations
 
 import collections
@@ -45,9 +45,8 @@ class AVSR(object):
         """Keyword surface of avsr.py:21-75 (`required_grahps` is the reference's spelling); everything that is a
         hyper-parameter goes to make_hparams.  `workdir` roots the reference's relative output directories
         (checkpoints/, predictions/)."""
-        if video_processing is not None and video_processing != 'features':
-            raise NotImplementedError('the CNN front-ends (avsr/video.py) are row f-3 of SURVEY.md section 8, not '
-                                      'built: use video_processing=`features`')
+        if video_processing not in (None, 'features', 'resnet_cnn'):
+            raise NotImplementedError('of the CNN front-ends (avsr/video.py) only `resnet_cnn` is built')
         if audio_processing is not None and audio_processing != 'features':
             raise NotImplementedError('`wav` audio processing (avsr/audio.py) is out of scope: use `features`')
         if write_beam_search_graphs or write_estimated_modality_lags:
@@ -103,7 +102,10 @@ class AVSR(object):
         # the model only needs the feature sizes of each stream at construction: a one-step placeholder batch
         spec = []
         for f in iterator._inputs:
-            x = np.zeros((1, 1, f.feat), np.float32)
+            cnn = self._video_processing is not None and 'cnn' in self._video_processing and len(f.input_shape) == 3
+            # (the record stores [width, height, channels]; frames are laid out rows first: avsr/io_utils.py:318-332)
+            x = np.zeros((1, 1) + ((f.input_shape[1], f.input_shape[0], f.input_shape[2]) if cnn else (f.feat,)),
+                         np.float32)
             spec.append(BatchedData(iterator_initializer=iterator.iterator_initializer, inputs=x,
                                     inputs_length=np.ones(1, np.int32), inputs_filenames=None,
                                     labels=np.zeros((1, 1), np.int32), labels_length=np.ones(1, np.int32),

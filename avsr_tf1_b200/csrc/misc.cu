@@ -435,6 +435,60 @@ __global__ void normed_v_bwd_kernel(const float* __restrict__ v, const float* __
   for (int u = threadIdx.x; u < A; u += blockDim.x) dv[u] += g[0] * inv * (dveff[u] - dvhat * v[u] * inv);
 }
 
+// ---- visual front-end helpers (video.py: tf.layers.conv2d as im2col + dense product, batch_norm_relu) ----------------
+// cols[row = (n, oy, ox)][col = (ky, kx, c)] = x[n, oy*stride - pad_top + ky, ox*stride - pad_left + kx, c] (0 outside);
+// the column order is the kernel variable [kh, kw, Cin, Cout] flattened to [kh*kw*Cin, Cout]
+__global__ void im2col_kernel(const float* __restrict__ x, int N, int H, int W, int C, int kh, int kw, int stride, int pt,
+                              int pl, int Ho, int Wo, int rnd, float* __restrict__ cols) {
+  const long long K = (long long)kh * kw * C, total = (long long)N * Ho * Wo * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / K;
+    const int col = (int)(i - row * K);
+    const int c = col % C, kx = (col / C) % kw, ky = col / (C * kw);
+    const int ox = (int)(row % Wo), oy = (int)((row / Wo) % Ho), n = (int)(row / ((long long)Wo * Ho));
+    const int iy = oy * stride - pt + ky, ix = ox * stride - pl + kx;
+    float v = 0.0f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long long)n * H + iy) * W + ix) * C + c];
+    cols[i] = maybe_tf32(v, rnd);
+  }
+}
+
+// transpose of im2col as a gather (deterministic, no atomics): dx[n, y, x, c] = sum over the (ky, kx) whose window
+// position (oy, ox) covers the pixel
+__global__ void col2im_kernel(const float* __restrict__ dcols, int N, int H, int W, int C, int kh, int kw, int stride,
+                              int pt, int pl, int Ho, int Wo, float* __restrict__ dx) {
+  const long long K = (long long)kh * kw * C, total = (long long)N * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), xx = (int)((i / C) % W), yy = (int)((i / ((long long)C * W)) % H);
+    const int n = (int)(i / ((long long)C * W * H));
+    float acc = 0.0f;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int ny = yy + pt - ky;
+      if (ny < 0 || ny % stride) continue;
+      const int oy = ny / stride;
+      if (oy >= Ho) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int nx = xx + pl - kx;
+        if (nx < 0 || nx % stride) continue;
+        const int ox = nx / stride;
+        if (ox >= Wo) continue;
+        acc += dcols[(((long long)n * Ho + oy) * Wo + ox) * K + ((long long)ky * kw + kx) * C + c];
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+__global__ void relu_fwd_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = fmaxf(x[i], 0.0f);
+}
+__global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, long long n,
+                                float* __restrict__ dx) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = y[i] > 0.0f ? dy[i] : 0.0f;
+}
+
 // ---- randomness of the training graph (dropout, scheduled sampling) -----------------------------------------------
 __global__ void dropout_kernel(const float* __restrict__ x, long long n, long long first,
                                const uint32_t* __restrict__ rng, uint32_t stream_id, uint32_t thr, float inv_keep,
@@ -775,6 +829,39 @@ int avsr_sched_sample(avsr_stream_t s, const float* logits, int B, int V, const 
   AVSR_REQUIRE(rng != nullptr && B > 0 && V > 0, "sched_sample: bad arguments");
   AVSR_LAUNCH(sched_sample_kernel, cdiv(B, 128), 128, 0, ST(s), logits, B, V, rng, stream_id, t, thr_p, true_next,
               next_ids, sampled);
+  return 0;
+}
+
+static int grid_for(long long n) {
+  long long g = (n + 255) / 256;
+  return (int)(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g));
+}
+
+int avsr_im2col(avsr_stream_t s, const float* x, int N, int H, int W, int C, int kh, int kw, int stride, int pad_top,
+                int pad_left, int Ho, int Wo, int round_out, float* cols) {
+  AVSR_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0 && Ho > 0 && Wo > 0, "im2col: bad geometry");
+  AVSR_LAUNCH(im2col_kernel, grid_for((long long)N * Ho * Wo * kh * kw * C), 256, 0, ST(s), x, N, H, W, C, kh, kw, stride,
+              pad_top, pad_left, Ho, Wo, round_out && tensor_cores_enabled(), cols);
+  return 0;
+}
+
+int avsr_col2im(avsr_stream_t s, const float* dcols, int N, int H, int W, int C, int kh, int kw, int stride, int pad_top,
+                int pad_left, int Ho, int Wo, float* dx) {
+  AVSR_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0 && Ho > 0 && Wo > 0, "col2im: bad geometry");
+  AVSR_LAUNCH(col2im_kernel, grid_for((long long)N * H * W * C), 256, 0, ST(s), dcols, N, H, W, C, kh, kw, stride, pad_top,
+              pad_left, Ho, Wo, dx);
+  return 0;
+}
+
+int avsr_relu_fwd(avsr_stream_t s, const float* x, long long n, float* y) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(relu_fwd_kernel, grid_for(n), 256, 0, ST(s), x, n, y);
+  return 0;
+}
+
+int avsr_relu_bwd(avsr_stream_t s, const float* y, const float* dy, long long n, float* dx) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(relu_bwd_kernel, grid_for(n), 256, 0, ST(s), y, dy, n, dx);
   return 0;
 }
 

@@ -203,6 +203,52 @@ def adam_clip_step(params, grads, m, v, sumsq_dev, clip_norm, lr_t, beta1=0.9, b
                                           beta1, beta2, eps, _p(params_tf32)))
 
 
+def same_padding(size, k, stride):
+    """TF `SAME`: (output size, pad before, pad after); the extra pixel of an odd total goes to the end."""
+    out = -(-size // stride)
+    total = max((out - 1) * stride + k - size, 0)
+    return out, total // 2, total - total // 2
+
+
+def conv_geometry(H, W, kh, kw, stride, padding):
+    if padding == 'SAME':
+        Ho, pt, _ = same_padding(H, kh, stride)
+        Wo, pl, _ = same_padding(W, kw, stride)
+        return Ho, Wo, pt, pl
+    return (H - kh) // stride + 1, (W - kw) // stride + 1, 0, 0
+
+
+def im2col(x, kh, kw, stride, padding, round_out=True):
+    """x [N,H,W,C] -> (cols [N*Ho*Wo, kh*kw*C], geometry)."""
+    _chk_f32(x)
+    N, H, W, Cc = x.shape
+    Ho, Wo, pt, pl = conv_geometry(H, W, kh, kw, stride, padding)
+    cols = empty(N * Ho * Wo, kh * kw * Cc)
+    check(_lib.load().avsr_im2col(_stream(), x.data_ptr(), N, H, W, Cc, kh, kw, stride, pt, pl, Ho, Wo,
+                                  int(bool(round_out)), cols.data_ptr()))
+    return cols, (N, H, W, Cc, kh, kw, stride, pt, pl, Ho, Wo)
+
+
+def col2im(dcols, geom):
+    N, H, W, Cc, kh, kw, stride, pt, pl, Ho, Wo = geom
+    dx = empty(N, H, W, Cc)
+    check(_lib.load().avsr_col2im(_stream(), dcols.data_ptr(), N, H, W, Cc, kh, kw, stride, pt, pl, Ho, Wo,
+                                  dx.data_ptr()))
+    return dx
+
+
+def relu_fwd(x, out=None):
+    y = torch.empty_like(x) if out is None else out
+    check(_lib.load().avsr_relu_fwd(_stream(), x.data_ptr(), x.numel(), y.data_ptr()))
+    return y
+
+
+def relu_bwd(y, dy, out=None):
+    dx = torch.empty_like(dy) if out is None else out
+    check(_lib.load().avsr_relu_bwd(_stream(), y.data_ptr(), dy.data_ptr(), dy.numel(), dx.data_ptr()))
+    return dx
+
+
 OPTIMISERS = {'Adam': 0, 'Nadam': 1, 'AdamW': 2, 'Momentum': 3}
 
 

@@ -18,7 +18,7 @@ ALIGN = 64  # floats (256 B): keeps every tensor TMA / float4 aligned
 class ParamSpec:
     name: str
     shape: Tuple[int, ...]
-    init: str  # lstm_kernel | glorot | embedding | zeros | ones | const:<v>
+    init: str  # lstm_kernel | conv_kernel | glorot | embedding | zeros | ones | const:<v>
     trainable: bool = True
 
 
@@ -45,6 +45,9 @@ def init_array(spec: ParamSpec, seed: int, vocab: int = 31) -> np.ndarray:
     elif spec.init == 'lstm_kernel':
         fan_in = shape[0]
         a = _truncated_normal(rng, shape, math.sqrt(1.0 / fan_in) / .87962566103423978)
+    elif spec.init == 'conv_kernel':  # video.py:26 variance_scaling_initializer(scale=2.0, mode='fan_in')
+        fan_in = int(np.prod(shape[:-1]))
+        a = _truncated_normal(rng, shape, math.sqrt(2.0 / fan_in) / .87962566103423978)
     elif spec.init == 'glorot':
         fan_in, fan_out = (shape[0], shape[1]) if len(shape) == 2 else (shape[0], shape[0])
         lim = math.sqrt(6.0 / (fan_in + fan_out))

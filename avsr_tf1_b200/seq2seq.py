@@ -53,7 +53,7 @@ class _PendingScalars(object):
         m, hp = self._model, self._model._hparams
         vals = self._buf.numpy()
         xent = float(vals[0]) * self._inv_denom
-        reg = 0.5 * (hp.recurrent_l2_regularisation or 0.0) * float(vals[1])
+        reg = 0.5 * (hp.recurrent_l2_regularisation or 0.0) * float(vals[1]) + 0.5 * 1e-3 * float(vals[4])
         au = float(vals[3]) * self._au_scale if m._au_head else 0.0
         m.batch_loss = xent + reg + au
         m.global_norm = math.sqrt(float(vals[2]))
@@ -157,12 +157,26 @@ class Seq2SeqModel(object):
     # ---- construction (seq2seq.py:30-126) ---------------------------------------
     def _make_encoders(self):
         hp, ctx = self._hparams, self._ctx
+        self._cnn = None
         if self._video_data is not None:
+            feature_dim = None
+            if hp.video_processing is not None and 'cnn' in hp.video_processing:
+                # avsr.py:686-696: the lip crops [B,T,H,W,C] go through the CNN front-end, the encoder sees its features
+                from .video import cnn_layers
+                shape = tuple(self._video_data.inputs.shape)
+                if len(shape) != 5:
+                    raise Exception('`%s` needs image sequences [B,T,H,W,C], got %r' % (hp.video_processing, shape))
+                self._cnn = cnn_layers(ctx, shape[2], shape[3], shape[4], hp.video_processing,
+                                       hp.kwargs.get('cnn_filters', (8, 16, 32, 64)),
+                                       hp.kwargs.get('cnn_dense_units', 128))
+                feature_dim = self._cnn.out_dim
             self._video_encoder = Seq2SeqEncoder(
                 data=self._video_data, mode=self._mode, hparams=hp,
                 num_units_per_layer=hp.encoder_units_per_layer[0],
                 dropout_probability=hp.video_encoder_dropout_probability, regress_aus=hp.regress_aus, ctx=ctx,
-                scope='video')
+                scope='video', feature_dim=feature_dim)
+            if self._cnn is not None and self._mode == 'train':
+                self._video_encoder.input_gradient = True  # the CNN trains through the encoder's input
         else:
             self._video_encoder = None
         if self._audio_data is not None:
@@ -220,7 +234,7 @@ class Seq2SeqModel(object):
         if hp.optimiser not in ops.OPTIMISERS:  # Adam, Nadam, AdamW, Momentum (seq2seq.py:195-219)
             raise Exception('Unsupported optimiser, try Adam')
         self._l2_names = [n for n in self.store.names() if 'lstm_' in n and 'bias' not in n]  # seq2seq.py:283-290
-        self._loss_dev = torch.zeros(4, dtype=torch.float32, device=self.store.flat.device)
+        self._loss_dev = torch.zeros(5, dtype=torch.float32, device=self.store.flat.device)  # xent, L2, |g|^2, AU, CNN L2
 
     @property
     def global_step(self):
@@ -246,8 +260,8 @@ class Seq2SeqModel(object):
             if d is None:
                 continue
             x = self._as_tensor(d.inputs, torch.float32)
-            if x.dim() > 3:  # raw lip crops [B,T,h,w,c] fed as flat features (video_processing='features')
-                x = x.reshape(x.shape[0], x.shape[1], -1)
+            if x.dim() > 3 and not (key == 'video' and self._cnn is not None):
+                x = x.reshape(x.shape[0], x.shape[1], -1)  # raw lip crops fed as flat features (`features`)
             src[key] = x
             src[key + '_len'] = self._as_tensor(d.inputs_length, torch.int32)
         meta = {}
@@ -372,6 +386,24 @@ class Seq2SeqModel(object):
     def _join(self):
         torch.cuda.current_stream().wait_stream(self._side_stream)
 
+    def _video_features(self, b):
+        """Lip crops -> CNN features [B,T,cnn_dense_units] (avsr.py:686-696), or the features as they are."""
+        x = b['video']
+        if self._cnn is None:
+            return x
+        B, T = x.shape[0], x.shape[1]
+        feats = self._cnn.forward(x.reshape(B * T, *x.shape[2:]), train=self._mode == 'train')
+        return feats.view(B, T, self._cnn.out_dim)
+
+    def _video_backward(self, d, dstate):
+        """Backward of the video branch: encoder, then the CNN front-end if there is one."""
+        if self._cnn is None:
+            self._video_encoder.backward(d, dstate)
+            return
+        dfeat = self._video_encoder.backward(d, dstate, need_dx=True)  # frame-major [T,B,F]
+        T, B, F = dfeat.shape
+        self._cnn.backward(ops.transpose01(dfeat).view(B * T, F))
+
     def _encode(self, b):
         enc = {}
         both = self._video_encoder is not None and self._audio_encoder is not None
@@ -379,9 +411,9 @@ class Seq2SeqModel(object):
         if self._video_encoder is not None:
             if overlap:
                 with torch.cuda.stream(self._fork()):
-                    enc['video'] = self._video_encoder.forward(b['video'], b['video_len'], batch_major=True)
+                    enc['video'] = self._video_encoder.forward(self._video_features(b), b['video_len'], batch_major=True)
             else:
-                enc['video'] = self._video_encoder.forward(b['video'], b['video_len'], batch_major=True)
+                enc['video'] = self._video_encoder.forward(self._video_features(b), b['video_len'], batch_major=True)
         if self._audio_encoder is not None:
             if isinstance(self._audio_encoder, AttentiveEncoder):
                 self._audio_encoder.forward_lower(b['audio'], b['audio_len'], batch_major=True)
@@ -432,27 +464,27 @@ class Seq2SeqModel(object):
         if self._hparams.architecture == 'bimodal':
             if overlap:
                 with torch.cuda.stream(self._fork()):
-                    self._video_encoder.backward(self._plus(dmem[0], dvid_au), dstates[0])
+                    self._video_backward(self._plus(dmem[0], dvid_au), dstates[0])
                 self._audio_encoder.backward(dmem[1], dstates[1])
                 self._join()
             else:
                 self._audio_encoder.backward(dmem[1], dstates[1])
-                self._video_encoder.backward(self._plus(dmem[0], dvid_au), dstates[0])
+                self._video_backward(self._plus(dmem[0], dvid_au), dstates[0])
         elif self._audio_encoder is not None:
             if isinstance(self._audio_encoder, AttentiveEncoder):
                 d_lower, dvid = self._audio_encoder.backward_top(dmem[0], dstates[0])
                 if overlap:
                     with torch.cuda.stream(self._fork()):
-                        self._video_encoder.backward(self._plus(dvid, dvid_au), None)
+                        self._video_backward(self._plus(dvid, dvid_au), None)
                     self._audio_encoder.backward_lower(d_lower)
                     self._join()
                 else:
                     self._audio_encoder.backward_lower(d_lower)
-                    self._video_encoder.backward(self._plus(dvid, dvid_au), None)
+                    self._video_backward(self._plus(dvid, dvid_au), None)
             else:
                 self._audio_encoder.backward(dmem[0], dstates[0])
         else:
-            self._video_encoder.backward(self._plus(dmem[0], dvid_au), dstates[0])
+            self._video_backward(self._plus(dmem[0], dvid_au), dstates[0])
 
     @staticmethod
     def _plus(d, extra):
@@ -490,6 +522,8 @@ class Seq2SeqModel(object):
             for n in self._l2_names:
                 ops.axpy(hp.recurrent_l2_regularisation, st.p(n), st.g(n))
                 ops.sumsq(st.p(n), self._loss_dev[1:2])
+        if self._cnn is not None:  # conv kernel_regularizer (video.py:27), summed into the loss by seq2seq.py:180-184
+            self._cnn.add_l2(self._loss_dev[4:5])
         ops.sumsq(st.grad, self._loss_dev[2:3])
 
     def apply_gradients(self):
@@ -568,7 +602,7 @@ class Seq2SeqModel(object):
         hp = self._hparams
         vals = self._loss_dev.cpu().numpy()
         xent = float(vals[0]) * self._inv_denom  # sum(xent*w) / (sum(w) + 1e-12)
-        reg = 0.5 * (hp.recurrent_l2_regularisation or 0.0) * float(vals[1])
+        reg = 0.5 * (hp.recurrent_l2_regularisation or 0.0) * float(vals[1]) + 0.5 * 1e-3 * float(vals[4])
         self.au_loss = float(vals[3]) * self._au_scale / float(hp.kwargs.get('au_loss_weight', 10.0)) \
             if self._au_head else None
         self.batch_loss = xent + reg + (float(vals[3]) * self._au_scale if self._au_head else 0.0)
@@ -580,7 +614,7 @@ class Seq2SeqModel(object):
         `result()` waits for just that copy.  Lets the host launch step k+1 before it reads the loss of step k, so the
         GPU never waits for the host between steps (session.run pipelines the same way behind its fetches)."""
         if not hasattr(self, '_pinned_scalars'):
-            self._pinned_scalars = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._pinned_scalars = [torch.empty(5, dtype=torch.float32).pin_memory() for _ in range(4)]
             self._pinned_next = 0
         buf = self._pinned_scalars[self._pinned_next % len(self._pinned_scalars)]
         self._pinned_next += 1

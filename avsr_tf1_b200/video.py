@@ -1,0 +1,191 @@
+"""Visual front-end - drop-in for reference avsr/video.py (`resnet_cnn` :143-195 applied per frame by `cnn_layers`
+:224-248).  NHWC like the reference (`data_format='channels_last'`).
+
+    layer0: conv3x3(C -> f0) -> BN-ReLU
+    res_block_0 (skip_bn): conv3x3 -> BN-ReLU -> conv3x3, + input
+    res_block_k (k >= 1): BN-ReLU(x) -> conv3x3 stride 2 -> BN-ReLU -> conv3x3, + conv1x1 stride 2 of the RAW x
+    flatten: VALID conv over what is left of the image -> cnn_dense_units, ReLU
+
+Every convolution is avsr_im2col + avsr_gemm (bias in the product's epilogue), its gradients avsr_gemm + avsr_colsum +
+avsr_col2im; BN is the same stats / apply pair as the input normalisation (rows = N*H*W; eps 1e-5, momentum 0.98;
+all-reduced sums under data parallelism).  im2col buffers are not kept: the backward pass rebuilds them from the saved
+layer inputs.  This is the functional version of the row (parity against the oracle); a fused implicit-GEMM tcgen05
+convolution is the next step - the im2col detour moves ~30 GB per step at the bench batch.
+
+`2dconv_cnn` / `3dconv_cnn` (video.py:108-140, 198-221) are not built (no reference script selects them)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .layers import BuildContext
+
+BN_EPS = 1e-5        # video.py:10
+BN_MOMENTUM = 0.98   # video.py:10
+L2_SCALE = 1e-3      # video.py:27 kernel_regularizer
+
+
+class _Conv(object):
+    def __init__(self, ctx: BuildContext, name, kh, kw, cin, cout, stride=1, padding='SAME'):
+        self.ctx, self.kh, self.kw, self.cin, self.cout, self.stride, self.padding = ctx, kh, kw, cin, cout, stride, padding
+        self.kernel = ctx.declare(name + '/kernel', (kh, kw, cin, cout), 'conv_kernel')
+        self.bias = ctx.declare(name + '/bias', (cout,), 'zeros')
+
+    def forward(self, x):
+        """x [N,H,W,Cin] -> [N,Ho,Wo,Cout] (exact fp32 out; the operand copy of x is made by im2col)."""
+        ctx = self.ctx
+        cols, geom = ops.im2col(x, self.kh, self.kw, self.stride, self.padding)
+        self._x, self._geom = x, geom
+        N, Ho, Wo = geom[0], geom[9], geom[10]
+        y = ops.empty(N, Ho, Wo, self.cout)
+        ops.gemm(cols, ctx.w(self.kernel).view(-1, self.cout), y.view(-1, self.cout), bias=ctx.p(self.bias))
+        return y
+
+    def backward(self, dy, need_dx=True):
+        ctx = self.ctx
+        cols, geom = ops.im2col(self._x, self.kh, self.kw, self.stride, self.padding)  # rebuilt, not stored
+        d2 = dy.reshape(-1, self.cout)
+        if ops.tensor_cores_enabled():
+            d2 = ops.round_tf32(d2)  # operand of the two products below
+        ops.gemm(cols, d2, ctx.g(self.kernel).view(-1, self.cout), ta=True, beta=1.0)
+        ops.colsum(d2, ctx.g(self.bias))
+        self._x = None
+        if not need_dx:
+            return None
+        dcols = torch.empty_like(cols)
+        ops.gemm(d2, ctx.w(self.kernel).view(-1, self.cout), dcols, tb=True)
+        return ops.col2im(dcols, geom)
+
+
+class _BatchNormRelu(object):
+    """batch_norm_relu (video.py:4-15) over NHWC: per-channel statistics over N, H, W."""
+
+    def __init__(self, ctx: BuildContext, name, C):
+        self.ctx, self.C = ctx, C
+        self.gamma = ctx.declare(name + '/gamma', (C,), 'ones')
+        self.beta = ctx.declare(name + '/beta', (C,), 'zeros')
+        self.mm = ctx.declare(name + '/moving_mean', (C,), 'zeros', trainable=False)
+        self.mv = ctx.declare(name + '/moving_variance', (C,), 'ones', trainable=False)
+
+    def forward(self, x, train):
+        ctx, C = self.ctx, self.C
+        x2 = x.reshape(-1, C)
+        y = torch.empty_like(x)
+        if not train:
+            ops.bn_apply_eval(x2, ctx.p(self.gamma), ctx.p(self.beta), ctx.p(self.mm), ctx.p(self.mv), BN_EPS,
+                              y.view(-1, C))
+            return ops.relu_fwd(y, out=y)
+        sums = ops.zeros(2 * C)
+        ops.bn_stats(x2, sums)
+        count = float(x2.shape[0])
+        if ctx.world_size > 1:
+            ctx.allreduce(sums)
+            count *= ctx.world_size
+        self.xhat, self.invstd, self.count = torch.empty_like(x2), ops.empty(C), count
+        ops.bn_apply_train(x2, sums, count, ctx.p(self.gamma), ctx.p(self.beta), BN_EPS, BN_MOMENTUM, y.view(-1, C),
+                           self.xhat, self.invstd, ctx.p(self.mm), ctx.p(self.mv))
+        self.y = ops.relu_fwd(y, out=y)
+        return self.y
+
+    def backward(self, dy):
+        ctx, C = self.ctx, self.C
+        d = ops.relu_bwd(self.y, dy).view(-1, C)
+        sums2 = ops.zeros(2 * C)
+        ops.bn_bwd_stats(d, self.xhat, sums2)
+        local = sums2
+        if ctx.world_size > 1:
+            local = sums2.clone()
+            ctx.allreduce(sums2)
+        dx = torch.empty_like(d)
+        ops.bn_bwd_apply(d, self.xhat, sums2, self.count, ctx.p(self.gamma), self.invstd, dx, None, None)
+        ops.axpy(1.0, local[C:], ctx.g(self.gamma))
+        ops.axpy(1.0, local[:C], ctx.g(self.beta))
+        self.xhat = self.y = None
+        return dx.view(dy.shape)
+
+
+class ResNetCNN(object):
+    """resnet_cnn(inputs, is_training, cnn_dense_units, cnn_filters) of video.py:143-195 with explicit backward."""
+
+    def __init__(self, ctx: BuildContext, height, width, channels, cnn_filters=(8, 16, 32, 64), cnn_dense_units=128,
+                 prefix='CNN/'):
+        self.ctx = ctx
+        self.in_shape = (int(height), int(width), int(channels))
+        self.out_dim = int(cnn_dense_units)
+        f = list(cnn_filters)
+        self.layer0 = _Conv(ctx, prefix + 'layer0', 3, 3, channels, f[0])
+        self.layer0_bn = _BatchNormRelu(ctx, prefix + 'layer0_bn', f[0])
+        self.blocks = []
+        cin, h, w = f[0], int(height), int(width)
+        for k, filt in enumerate(f):
+            name = prefix + 'res_block_%d' % k
+            blk = {}
+            stride = 1 if k == 0 else 2
+            if k > 0:  # skip_bn only for block 0; projection shortcut for the strided blocks
+                blk['first_bn'] = _BatchNormRelu(ctx, name + '_first_bn', cin)
+                blk['shortcut'] = _Conv(ctx, name + '_shortcut', 1, 1, cin, filt, stride=2)
+                h, w = -(-h // 2), -(-w // 2)
+            blk['conv1'] = _Conv(ctx, name + '_conv1', 3, 3, cin, filt, stride=stride)
+            blk['second_bn'] = _BatchNormRelu(ctx, name + '_second_bn', filt)
+            blk['conv2'] = _Conv(ctx, name + '_conv2', 3, 3, filt, filt)
+            self.blocks.append(blk)
+            cin = filt
+        self.flatten = _Conv(ctx, prefix + 'flatten', h, w, cin, self.out_dim, padding='VALID')
+        self.kernels = [c.kernel for c in self._convs()]
+
+    def _convs(self):
+        out = [self.layer0]
+        for blk in self.blocks:
+            out += [blk[k] for k in ('shortcut', 'conv1', 'conv2') if k in blk]
+        return out + [self.flatten]
+
+    def forward(self, frames, train):
+        """frames [N,H,W,C] device tensor -> features [N, cnn_dense_units]."""
+        flow = self.layer0_bn.forward(self.layer0.forward(frames), train)
+        for blk in self.blocks:
+            shortcut = flow
+            if 'first_bn' in blk:
+                flow = blk['first_bn'].forward(flow, train)
+                shortcut = blk['shortcut'].forward(shortcut)
+            flow = blk['conv1'].forward(flow)
+            flow = blk['second_bn'].forward(flow, train)
+            flow = blk['conv2'].forward(flow)
+            ops.axpy(1.0, shortcut, flow)
+        y = self.flatten.forward(flow)
+        self._feat = ops.relu_fwd(y, out=y)
+        return self._feat.view(frames.shape[0], self.out_dim)
+
+    def backward(self, dfeat):
+        """Accumulates the gradients of every CNN variable (nothing upstream of the frames is trained)."""
+        d = ops.relu_bwd(self._feat, dfeat.reshape(self._feat.shape).contiguous())
+        d = self.flatten.backward(d)
+        for k in range(len(self.blocks) - 1, -1, -1):
+            blk = self.blocks[k]
+            d_short = d  # flow + shortcut
+            d = blk['conv2'].backward(d)
+            d = blk['second_bn'].backward(d)
+            d = blk['conv1'].backward(d)
+            if 'first_bn' in blk:
+                d = blk['first_bn'].backward(d)
+                d_short = blk['shortcut'].backward(d_short)
+            ops.axpy(1.0, d_short, d)
+        d = self.layer0_bn.backward(d)
+        self.layer0.backward(d, need_dx=False)
+        self._feat = None
+
+    def add_l2(self, loss_sumsq):
+        """kernel_regularizer l2(1e-3) of every convolution (video.py:27, seq2seq.py:180-184): gradient += 1e-3 * w;
+        loss_sumsq[0] += sum w^2 (the caller adds 1e-3 / 2 of it to the loss)."""
+        ctx = self.ctx
+        for name in self.kernels:
+            ops.axpy(L2_SCALE, ctx.p(name).reshape(-1), ctx.g(name).reshape(-1))
+            ops.sumsq(ctx.p(name).reshape(-1), loss_sumsq)
+
+
+def cnn_layers(ctx, height, width, channels, cnn_type, cnn_filters, cnn_dense_units=128):
+    """Factory with the dispatch of video.py:224-248."""
+    if cnn_type == 'resnet_cnn':
+        return ResNetCNN(ctx, height, width, channels, cnn_filters, cnn_dense_units)
+    if cnn_type in ('2dconv_cnn', '3dconv_cnn'):
+        raise NotImplementedError('%s (video.py) is not selected by any reference script and is not built' % cnn_type)
+    raise Exception('undefined CNN, did you mean `resnet_cnn` ?')

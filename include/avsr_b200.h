@@ -226,6 +226,20 @@ int avsr_seq_loss(avsr_stream_t stream, const float* logits, int T, int B, int V
 int avsr_au_loss(avsr_stream_t stream, const float* z, int T, int B, const float* aus, const int* len,
                  const float* scale_dev, float* loss_sum, float* dz);
 
+/* ---- visual front-end (avsr/video.py resnet_cnn :143-195, per frame via cnn_layers :224-248) --------
+ * tf.layers.conv2d on NHWC activations = avsr_im2col + avsr_gemm (+ bias) with the kernel variable [kh, kw, Cin, Cout]
+ * read as [kh*kw*Cin, Cout]; its gradients = avsr_gemm (transposed) + avsr_colsum + avsr_col2im.  pad_top / pad_left are
+ * TF's SAME padding (the extra pixel of an odd total goes to the end) or 0 for VALID; rows of `cols` = (n, oy, ox),
+ * columns = (ky, kx, c).  round_out: cols stored tf32-rounded (operand of a tensor-core product).  batch_norm_relu
+ * (:4-15) = avsr_bn_stats / avsr_bn_apply_train over rows = N*H*W with eps 1e-5, momentum 0.98, then avsr_relu_fwd. */
+int avsr_im2col(avsr_stream_t stream, const float* x, int N, int H, int W, int C, int kh, int kw, int stride,
+                int pad_top, int pad_left, int Ho, int Wo, int round_out, float* cols);
+/* dx[N,H,W,C] = transpose of im2col applied to dcols (overwrites dx; gather form, deterministic) */
+int avsr_col2im(avsr_stream_t stream, const float* dcols, int N, int H, int W, int C, int kh, int kw, int stride,
+                int pad_top, int pad_left, int Ho, int Wo, float* dx);
+int avsr_relu_fwd(avsr_stream_t stream, const float* x, long long n, float* y);               /* in place allowed */
+int avsr_relu_bwd(avsr_stream_t stream, const float* y, const float* dy, long long n, float* dx); /* dx = dy [y > 0] */
+
 /* ---- optimiser (seq2seq.py:175-178, 195-257) --------------------------------- */
 /* out[0] += sum x^2 */
 int avsr_sumsq(avsr_stream_t stream, const float* x, long long n, float* out);

@@ -50,7 +50,8 @@ def oracle_hparams(hp, model=None):
                                    decoder=hp.decoder_dropout_probability)
         rand.update(sampling_probability_outputs=hp.sampling_probability_outputs, rng=model.rng_words(),
                     streams=model.random_streams)
-    rand.update(regress_aus=bool(hp.regress_aus), au_loss_weight=hp.kwargs.get('au_loss_weight', 10.0))
+    rand.update(regress_aus=bool(hp.regress_aus), au_loss_weight=hp.kwargs.get('au_loss_weight', 10.0),
+                video_processing=hp.video_processing, cnn_filters=tuple(hp.kwargs.get('cnn_filters', (8, 16, 32, 64))))
     return OracleHParams(
         **rand,
         architecture=hp.architecture, encoder_type=hp.encoder_type,
@@ -91,6 +92,15 @@ def synthetic_batch(hp, B, Ta=300, Tv=75, Fa=80, Fv=128, L=40, ragged=False, see
         v *= (np.arange(Tv)[None, :, None] < vlen[:, None, None])
         out.update(video=v, video_len=vlen.astype(np.int32))
     return out
+
+
+def to_image_sequences(batch, hw, channels=3, seed=1006):
+    """Replaces the video features by lip crops [B,Tv,hw,hw,channels] ~ U(-1,1), zero past the length (resnet_cnn)."""
+    B, Tv = batch['video'].shape[:2]
+    v = np.random.default_rng(seed).uniform(-1, 1, (B, Tv, hw, hw, channels)).astype(np.float32)
+    v *= (np.arange(Tv)[None, :, None, None, None] < batch['video_len'][:, None, None, None, None])
+    batch['video'] = v
+    return batch
 
 
 def add_aus(batch, seed=1005):

@@ -1,0 +1,122 @@
+"""GPU parity of the visual front-end (avsr/video.py resnet_cnn) against the oracle: the im2col /
+col2im pair, the CNN alone (features and every gradient), and the whole model with lip crops as input."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import avsr_oracle as O
+from tests.helpers import (add_aus, cast_batch, config_hparams, oracle_hparams, synthetic_batch, to_data_sequences,
+                           to_image_sequences)
+from tests.test_gpu_model import close, tensor_cores  # noqa: F401  (fixture)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('H,W,C,k,stride,padding', [(9, 9, 3, 3, 1, 'SAME'), (9, 7, 4, 3, 2, 'SAME'),
+                                                     (36, 36, 3, 3, 2, 'SAME'), (18, 18, 8, 1, 2, 'SAME'),
+                                                     (5, 5, 6, 5, 1, 'VALID'), (8, 8, 2, 3, 2, 'VALID')])
+def test_im2col_col2im(H, W, C, k, stride, padding):
+    from avsr_tf1_b200 import ops
+    old = ops.set_tensor_cores(False)
+    try:
+        rng = np.random.default_rng(H + W + C + k + stride)
+        x = rng.standard_normal((3, H, W, C)).astype(np.float32)
+        cols_ref, geom_ref = O.im2col(x, k, k, stride, padding)
+        cols, geom = ops.im2col(torch.from_numpy(x).cuda(), k, k, stride, padding)
+        assert np.array_equal(cols.cpu().numpy(), cols_ref)
+        d = rng.standard_normal(cols_ref.shape).astype(np.float32)
+        dx_ref = O.col2im(d.astype(np.float64), geom_ref, k, k, stride)
+        dx = ops.col2im(torch.from_numpy(d).cuda(), geom)
+        close(dx, dx_ref, 1e-6, 'col2im')
+    finally:
+        ops.set_tensor_cores(old)
+
+
+def test_resnet_cnn_alone(tensor_cores):
+    """36x36x3 crops, the reference's filters (8, 16, 32, 64) -> 128 features; training-mode batch statistics."""
+    from avsr_tf1_b200.layers import BuildContext
+    from avsr_tf1_b200.params import ParamStore
+    from avsr_tf1_b200.video import ResNetCNN
+    ctx = BuildContext()
+    cnn = ResNetCNN(ctx, 36, 36, 3)
+    ctx.store = ParamStore(ctx.specs, device='cuda', with_optimizer=True)
+    ctx.store.initialize(7)
+    rng = np.random.default_rng(0)
+    for s in ctx.specs:  # non-trivial BN affine parameters and biases
+        if s.name.endswith(('gamma', 'beta', 'bias')):
+            ctx.store.p(s.name).add_(torch.from_numpy(0.2 * rng.standard_normal(s.shape).astype(np.float32)).cuda())
+    ctx.store.sync_tf32()
+    P = {k: v.astype(np.float64) for k, v in ctx.store.to_numpy('p').items()}
+    frames = rng.uniform(-1, 1, (6, 36, 36, 3)).astype(np.float32)
+    w = rng.standard_normal((6, 128)).astype(np.float32)
+    feat_ref, cache, stats = O.resnet_cnn_fwd(P, frames.astype(np.float64))
+    _, G_ref = O.resnet_cnn_bwd(w.astype(np.float64), cache)
+    ctx.store.grad.zero_()
+    feat = cnn.forward(torch.from_numpy(frames).cuda(), train=True)
+    rt = 5e-3 if tensor_cores else 1e-4  # 13 tf32 products deep
+    close(feat, feat_ref, rt, 'cnn features')
+    cnn.backward(torch.from_numpy(w).cuda())
+    G = ctx.store.to_numpy('g')
+    gmax = max(np.abs(g).max() for g in G_ref.values())
+    for name, g_ref in G_ref.items():
+        scale = max(np.abs(g_ref).max(), 1e-3 * gmax)
+        err = np.abs(G[name].astype(np.float64) - g_ref).max() / scale
+        assert err <= (1e-1 if tensor_cores else 1e-3), f'{name}: gradient scaled error {err:.3e}'
+    # moving statistics: momentum 0.98 (video.py:10)
+    mean, var = stats['CNN/layer0_bn']
+    close(ctx.store.p('CNN/layer0_bn/moving_mean'), 0.02 * mean, 2e-3, 'moving mean')
+    close(ctx.store.p('CNN/layer0_bn/moving_variance'), 0.98 + 0.02 * var, 1e-4, 'moving variance')
+    # inference mode uses them
+    feat_eval = cnn.forward(torch.from_numpy(frames).cuda(), train=False)
+    P2 = {k: v.astype(np.float64) for k, v in ctx.store.to_numpy('p').items()}
+    feat_eval_ref, _, _ = O.resnet_cnn_fwd(P2, frames.astype(np.float64), train=False)
+    close(feat_eval, feat_eval_ref, rt, 'cnn features (inference)')
+
+
+@pytest.mark.parametrize('cfg,over', [(3, {}), (5, {}), (4, dict(regress_aus=True)),
+                                      (5, dict(use_dropout=True, sampling_probability_outputs=0.0))])
+def test_model_with_cnn_front_end(cfg, over, tensor_cores):
+    """video_processing='resnet_cnn' (run_video.py:34, run_audiovisual.py): lip crops -> CNN -> video encoder -> ...;
+    loss (incl. the conv L2 term), encoder states and every gradient incl. the CNN's."""
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    hp = config_hparams(cfg, video_processing='resnet_cnn', cnn_filters=(4, 8, 8, 16), cnn_dense_units=32, **over)
+    batch = to_image_sequences(synthetic_batch(hp, B=3, Ta=24, Tv=6, L=5, ragged=True), hw=12)
+    if hp.regress_aus:
+        add_aus(batch)
+    ds = to_data_sequences(batch)
+    model = Seq2SeqModel(ds, 'train', hp, seed=2001)
+    P = {k: v.astype(np.float64) for k, v in model.store.to_numpy('p').items()}
+    om = O.OracleModel(oracle_hparams(hp, model), P)
+    loss_ref, G_ref, rec = om.loss_and_grads(cast_batch(batch, np.float64))
+    model.feed(ds)
+    model._set_step_scalars()
+    model.forward_backward()
+    model.finish_gradients()
+    loss, gnorm = model.fetch_scalars()
+    assert abs(loss - loss_ref) <= 1e-3 * abs(loss_ref), (loss, loss_ref)
+    out_ref, (c_ref, h_ref) = rec['enc']['video']
+    d = model._video_encoder.get_data()
+    rt = 3e-3 if tensor_cores else 1e-3
+    close(d.outputs.transpose(0, 1), out_ref, rt, 'video encoder outputs')
+    close(d.final_state[1], h_ref, rt, 'video final h')
+    G = model.store.to_numpy('g')
+    gn_ref = O.global_norm(G_ref)
+    assert abs(gnorm - gn_ref) <= 1e-2 * gn_ref, (gnorm, gn_ref)
+    gmax = max(np.abs(g).max() for g in G_ref.values())
+    for name, g_ref in G_ref.items():
+        scale = max(np.abs(g_ref).max(), 1e-3 * gmax)
+        err = np.abs(G[name].astype(np.float64) - g_ref).max() / scale
+        # exact-fp32 mode pins the algorithm at 1e-3; in tensor-core mode every operand of the 13 convolutions (and of
+        # their two gradient products) is tf32-rounded, and the BN / bias gradients are cancellation-heavy sums over all
+        # pixels of a tiny batch: 1e-1 of the tensor's largest entry for the CNN's variables, 3e-2 elsewhere
+        tol = 1e-3 if not tensor_cores else (1e-1 if name.startswith('CNN/') else 3e-2)
+        assert err <= tol, f'{name}: gradient scaled error {err:.3e}'
+    # three optimiser steps run, and inference works on crops
+    for _ in range(2):
+        l2, _ = model.train_step(ds)
+        assert np.isfinite(l2)
+    hp_eval = config_hparams(cfg, video_processing='resnet_cnn', cnn_filters=(4, 8, 8, 16), cnn_dense_units=32,
+                             decoding_algorithm='greedy', **over)
+    ev = Seq2SeqModel(ds, 'evaluate', hp_eval, share_params_with=model)
+    ids = ev.predict(ds)
+    assert ids.shape[0] == 3

@@ -104,3 +104,20 @@ def test_alignment_images(records, tmp_path):
     assert len(pngs) == 2 * 10 and pngs[0] == 'utt000000.png' and pngs[1] == 'utt000000_av.png'
     img = cv2.imread(os.path.join(out, pngs[-2]), cv2.IMREAD_GRAYSCALE)
     assert img.shape == dec.shape[1:3]  # last batch: same padded sizes as the arrays still held by the model
+
+
+def test_runtime_shell_with_cnn_front_end(tmp_path):
+    """run_video.py's configuration in miniature: AVSR(video_processing='resnet_cnn') on a video record of lip crops."""
+    from avsr_tf1_b200.avsr import AVSR
+    from avsr_tf1_b200.synthetic import write_synthetic_records
+    train = write_synthetic_records(str(tmp_path), n=12, Tv=6, hw=12, L=4, ragged=True, audio=False, prefix='tr')
+    test = write_synthetic_records(str(tmp_path), n=5, Tv=6, hw=12, L=4, ragged=True, audio=False, prefix='te', seed=9)
+    exp = AVSR(unit='character', video_processing='resnet_cnn', video_train_record=train['video'],
+               video_test_record=test['video'], labels_train_record=train['labels'],
+               labels_test_record=test['labels'], batch_size=(6, 5), architecture='unimodal',
+               encoder_units_per_layer=((128,), (128,)), decoder_units_per_layer=(128,), cnn_filters=(4, 8, 8, 16),
+               cnn_dense_units=32, decoding_algorithm='greedy', workdir=str(tmp_path), verbose=False)
+    exp.train(logfile=str(tmp_path / 'logs' / 'cnn'), num_epochs=11)
+    lines = open(str(tmp_path / 'logs' / 'cnn')).read().splitlines()
+    assert sum(l.startswith('Average batch_loss') for l in lines) == 10 and lines[-1].startswith('character: ')
+    assert any(n.startswith('CNN/') for n in exp._train_model.model.store.names())

@@ -163,3 +163,21 @@ def test_png_writer_round_trips(tmp_path):
     back = cv2.imread(f, cv2.IMREAD_GRAYSCALE)
     assert back.shape == (37, 53)
     assert np.array_equal(back, (img * 255.0 + 0.5).astype(np.uint8))
+
+
+def test_resnet_cnn_variable_table():
+    """video_processing='resnet_cnn' on 36x36x3 crops adds the 282 288 trainable CNN parameters of SURVEY.md 8e under
+    the TF names of video.py (conv2d / batch_normalization `name=` arguments inside variable_scope('CNN'))."""
+    from tests.helpers import to_image_sequences
+    hp = config_hparams(3, video_processing='resnet_cnn', attention_type=(('bahdanau',), ('bahdanau',)))
+    batch = to_image_sequences(synthetic_batch(hp, B=2, Ta=6, Tv=4, L=3), hw=36)
+    m = Seq2SeqModel(to_data_sequences(batch), 'train', hp, device='cpu')
+    assert m.n_params == 2375839 + 282288
+    names = set(m.store.names(trainable_only=False))
+    for n in ('CNN/layer0/kernel', 'CNN/layer0_bn/moving_variance', 'CNN/res_block_0_conv1/bias',
+              'CNN/res_block_0_second_bn/gamma', 'CNN/res_block_1_first_bn/beta', 'CNN/res_block_3_shortcut/kernel',
+              'CNN/res_block_3_conv2/kernel', 'CNN/flatten/kernel'):
+        assert n in names, n
+    assert 'CNN/res_block_0_first_bn/gamma' not in names and 'CNN/res_block_0_shortcut/kernel' not in names
+    assert m.store.table['CNN/flatten/kernel'][1] == (5, 5, 64, 128)  # 36 -> 18 -> 9 -> 5, VALID over the rest
+    assert m.store.table['CNN/res_block_2_shortcut/kernel'][1] == (1, 1, 16, 32)
