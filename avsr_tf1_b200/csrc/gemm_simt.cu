@@ -22,7 +22,7 @@ gemm_simt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, cons
 
   const int tid = threadIdx.x;
   const int tx = tid % (BN / TN), ty = tid / (BN / TN);
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;  // M tiles on grid.x: no 65535 limit (im2col products: M = N*Ho*Wo)
   const int ktiles = (K + BK - 1) / BK;
   const int kt_per = (ktiles + splitk - 1) / splitk;
   const int kbeg = blockIdx.z * kt_per * BK;
@@ -126,7 +126,7 @@ __global__ void zero_block_kernel(float* C, int M, int N, int ldc) {
 template <int BM, int BN, int BK, int TM, int TN>
 static int launch_cfg(cudaStream_t st, int tA, int tB, int M, int N, int K, const float* A, int lda, const float* B,
                       int ldb, float* C, int ldc, int acc, const float* bias, int splitk, int round_out) {
-  dim3 grid(cdiv(N, BN), cdiv(M, BM), splitk);
+  dim3 grid(cdiv(M, BM), cdiv(N, BN), splitk);
   dim3 block((BM / TM) * (BN / TN));
   if (!tA && !tB) AVSR_LAUNCH((gemm_simt_kernel<BM, BN, BK, TM, TN, false, false>), grid, block, 0, st, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk, round_out);
   else if (!tA && tB) AVSR_LAUNCH((gemm_simt_kernel<BM, BN, BK, TM, TN, false, true>), grid, block, 0, st, M, N, K, A, lda, B, ldb, C, ldc, acc, bias, splitk, round_out);

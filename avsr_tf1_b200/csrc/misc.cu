@@ -40,6 +40,7 @@ __global__ void colstats_kernel(const float* __restrict__ a, const float* __rest
 static int colstats(cudaStream_t st, const float* a, const float* b, long long rows, int F, float* out) {
   if (rows <= 0) return 0;
   int rpb = 256;
+  while (cdiv(rows, rpb) > 65535) rpb *= 2;  // grid.y limit (the CNN's batch norms see N*H*W = tens of millions of rows)
   dim3 grid(cdiv(F, 32), cdiv(rows, rpb));
   AVSR_LAUNCH(colstats_kernel, grid, dim3(32, 8), 0, st, a, b, rows, F, rpb, out);
   return 0;
@@ -103,7 +104,7 @@ bn_apply_train_v4_kernel(const float* __restrict__ x, long long rows, int F, con
                          float inv_count, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                          float momentum, float* __restrict__ y, float* __restrict__ xhat, float* __restrict__ invstd,
                          float* __restrict__ moving_mean, float* __restrict__ moving_var, int rnd, int d0, int d1) {
-  const int f = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const int f = (blockIdx.y * 256 + threadIdx.x) * 4;  // (rows on grid.x: no 65535 limit)
   if (f >= F) return;
   const float4 s1 = *reinterpret_cast<const float4*>(sums + f), s2 = *reinterpret_cast<const float4*>(sums + F + f);
   const float4 g4 = *reinterpret_cast<const float4*>(gamma + f), b4 = *reinterpret_cast<const float4*>(beta + f);
@@ -116,7 +117,7 @@ bn_apply_train_v4_kernel(const float* __restrict__ x, long long rows, int F, con
     var[e] = fmaxf(sq[e] * inv_count - mean[e] * mean[e], 0.0f);
     is[e] = rsqrtf(var[e] + eps);
   }
-  if (blockIdx.y == 0) {  // per-feature side outputs, once
+  if (blockIdx.x == 0) {  // per-feature side outputs, once
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       invstd[f + e] = is[e];
@@ -124,7 +125,7 @@ bn_apply_train_v4_kernel(const float* __restrict__ x, long long rows, int F, con
       if (moving_var) moving_var[f + e] = moving_var[f + e] * momentum + var[e] * (1.0f - momentum);
     }
   }
-  const long long r0 = (long long)blockIdx.y * BN_ROWS;
+  const long long r0 = (long long)blockIdx.x * BN_ROWS;
 #pragma unroll 4
   for (int k = 0; k < BN_ROWS; ++k) {
     const long long r = r0 + k;  // output row
@@ -154,7 +155,7 @@ static int bn_apply_train_launch(cudaStream_t st, const float* x, long long rows
   const bool aligned = (F % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)xhat | (uintptr_t)sums |
                                           (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0);
   if (aligned) {
-    dim3 grid(cdiv(F, 1024), cdiv(rows, BN_ROWS));
+    dim3 grid(cdiv(rows, BN_ROWS), cdiv(F, 1024));
     AVSR_LAUNCH(bn_apply_train_v4_kernel, grid, 256, 0, st, x, rows, F, sums, inv_count, gamma, beta, eps, momentum, y,
                 xhat, invstd, moving_mean, moving_var, tensor_cores_enabled(), d0, d1);
     return 0;
@@ -663,6 +664,7 @@ extern "C" {
 int avsr_colsum(avsr_stream_t s, const float* X, int M, int N, int ldx, float* out) {
   if (M <= 0 || N <= 0) return 0;
   int rpb = 256;
+  while (cdiv(M, rpb) > 65535) rpb *= 2;  // grid.y limit
   dim3 grid(cdiv(N, 32), cdiv(M, rpb));
   AVSR_LAUNCH(colsum_kernel, grid, dim3(32, 8), 0, ST(s), X, (long long)M, N, ldx, rpb, out);
   return 0;
