@@ -85,6 +85,8 @@ PROTOTYPES = {
     'avsr_optim_clip_step': (_I, [_P, _I, _P, _P, _P, _P, _L, _P, _F, _P, _F, _F, _F, _F, _P]),
     'avsr_im2col': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'avsr_col2im': (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'avsr_conv2d_direct': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'avsr_conv2d_wgrad': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'avsr_relu_fwd': (_I, [_P, _P, _L, _P]),
     'avsr_relu_bwd': (_I, [_P, _P, _P, _L, _P]),
     'avsr_greedy_pick': (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),

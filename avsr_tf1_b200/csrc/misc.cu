@@ -490,6 +490,101 @@ __global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __rest
     dx[i] = y[i] > 0.0f ? dy[i] : 0.0f;
 }
 
+// ---- direct convolutions for the narrow layers of the front-end (8 / 16 output channels: almost all of its pixels) ---
+// One thread per output pixel, all CO output channels in registers, the kernel [kh*kw*Ci][CO] in shared memory (broadcast
+// reads); NHWC input read straight from global memory (the 3x3 neighbourhoods of adjacent threads overlap in L1).  No
+// im2col buffer: at the bench batch the 8-channel layers alone would write and re-read 7 GB each.
+template <int CO>
+__global__ void __launch_bounds__(256)
+conv_direct_kernel(const float* __restrict__ x, int N, int H, int W, int Ci, const float* __restrict__ w,
+                   const float* __restrict__ bias, int kh, int kw, int stride, int pt, int pl, int Ho, int Wo,
+                   float* __restrict__ y) {
+  extern __shared__ __align__(16) float conv_ws[];
+  const int K = kh * kw * Ci;
+  for (int i = threadIdx.x; i < K * CO; i += blockDim.x) conv_ws[i] = w[i];
+  __syncthreads();
+  const long long total = (long long)N * Ho * Wo;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho), n = (int)(p / ((long long)Wo * Ho));
+    float acc[CO];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) acc[co] = bias ? bias[co] : 0.0f;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int iy = oy * stride - pt + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int ix = ox * stride - pl + kx;
+        if (ix < 0 || ix >= W) continue;
+        const float* xp = x + (((long long)n * H + iy) * W + ix) * Ci;
+        const float* wp = conv_ws + (ky * kw + kx) * Ci * CO;
+        for (int ci = 0; ci < Ci; ++ci) {
+          const float v = __ldg(xp + ci);
+#pragma unroll
+          for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, wp[ci * CO + co], acc[co]);
+        }
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(y + p * CO);
+#pragma unroll
+    for (int q = 0; q < CO / 4; ++q) o[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+}
+
+// dW[k = (ky, kx, ci)][co] += sum over output pixels of x-patch[k] * dy[co].  A CTA stages tiles of 64 output pixels (their
+// im2col rows and dy rows) in shared memory; every thread owns up to 9 of the K*CO <= 2304 outputs and keeps them in
+// registers across all the tiles the CTA visits (grid-stride), one atomicAdd per output at the end.
+constexpr int WG_PIX = 64;
+template <int CO>
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int N, int H, int W, int Ci, int kh, int kw,
+                  int stride, int pt, int pl, int Ho, int Wo, float* __restrict__ dW) {
+  extern __shared__ __align__(16) float wg_sm[];
+  const int K = kh * kw * Ci, KP = K | 1, nout = K * CO;
+  float* xs = wg_sm;                 // [WG_PIX][KP]
+  float* ds = wg_sm + WG_PIX * KP;   // [WG_PIX][CO]
+  const long long total = (long long)N * Ho * Wo;
+  float acc[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) acc[j] = 0.0f;
+  for (long long tile = blockIdx.x; tile * WG_PIX < total; tile += gridDim.x) {
+    const long long p0 = tile * WG_PIX;
+    __syncthreads();
+    for (int e = threadIdx.x; e < WG_PIX * K; e += 256) {
+      const int pp = e / K, k = e - pp * K;
+      const long long p = p0 + pp;
+      float v = 0.0f;
+      if (p < total) {
+        const int ci = k % Ci, kx = (k / Ci) % kw, ky = k / (Ci * kw);
+        const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho), n = (int)(p / ((long long)Wo * Ho));
+        const int iy = oy * stride - pt + ky, ix = ox * stride - pl + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((long long)n * H + iy) * W + ix) * Ci + ci);
+      }
+      xs[pp * KP + k] = v;
+    }
+    for (int e = threadIdx.x; e < WG_PIX * CO; e += 256) {
+      const long long p = p0 + e / CO;
+      ds[e] = p < total ? __ldg(dy + p0 * CO + e) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int o = threadIdx.x + 256 * j;
+      if (o < nout) {
+        const int k = o / CO, co = o - k * CO;
+        float a = acc[j];
+#pragma unroll 8
+        for (int pp = 0; pp < WG_PIX; ++pp) a = fmaf(xs[pp * KP + k], ds[pp * CO + co], a);
+        acc[j] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 9; ++j) {
+    const int o = threadIdx.x + 256 * j;
+    if (o < nout) atomicAdd(dW + o, acc[j]);
+  }
+}
+
 // ---- randomness of the training graph (dropout, scheduled sampling) -----------------------------------------------
 __global__ void dropout_kernel(const float* __restrict__ x, long long n, long long first,
                                const uint32_t* __restrict__ rng, uint32_t stream_id, uint32_t thr, float inv_keep,
@@ -852,6 +947,36 @@ int avsr_col2im(avsr_stream_t s, const float* dcols, int N, int H, int W, int C,
   AVSR_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && kh > 0 && kw > 0 && stride > 0 && Ho > 0 && Wo > 0, "col2im: bad geometry");
   AVSR_LAUNCH(col2im_kernel, grid_for((long long)N * H * W * C), 256, 0, ST(s), dcols, N, H, W, C, kh, kw, stride, pad_top,
               pad_left, Ho, Wo, dx);
+  return 0;
+}
+
+int avsr_conv2d_direct(avsr_stream_t s, const float* x, int N, int H, int W, int Ci, const float* w, const float* bias,
+                       int kh, int kw, int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, float* y) {
+  AVSR_REQUIRE(Co == 8 || Co == 16, "conv2d_direct: 8 or 16 output channels (got %d)", Co);
+  AVSR_REQUIRE(N > 0 && H > 0 && W > 0 && Ci > 0 && kh > 0 && kw > 0 && stride > 0 && Ho > 0 && Wo > 0, "conv2d_direct: bad geometry");
+  const size_t smem = (size_t)kh * kw * Ci * Co * sizeof(float);
+  AVSR_REQUIRE(smem <= 48 * 1024, "conv2d_direct: kernel of %zu bytes does not fit shared memory", smem);
+  const int grid = grid_for((long long)N * Ho * Wo);
+  if (Co == 8)
+    AVSR_LAUNCH(conv_direct_kernel<8>, grid, 256, smem, ST(s), x, N, H, W, Ci, w, bias, kh, kw, stride, pad_top, pad_left, Ho, Wo, y);
+  else
+    AVSR_LAUNCH(conv_direct_kernel<16>, grid, 256, smem, ST(s), x, N, H, W, Ci, w, bias, kh, kw, stride, pad_top, pad_left, Ho, Wo, y);
+  return 0;
+}
+
+int avsr_conv2d_wgrad(avsr_stream_t s, const float* x, const float* dy, int N, int H, int W, int Ci, int kh, int kw,
+                      int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, float* dW) {
+  AVSR_REQUIRE(Co == 8 || Co == 16, "conv2d_wgrad: 8 or 16 output channels (got %d)", Co);
+  const int K = kh * kw * Ci;
+  AVSR_REQUIRE(K * Co <= 9 * 256, "conv2d_wgrad: at most 2304 kernel entries (got %d)", K * Co);
+  const size_t smem = (size_t)WG_PIX * ((K | 1) + Co) * sizeof(float);
+  AVSR_REQUIRE(smem <= 48 * 1024, "conv2d_wgrad: tile of %zu bytes does not fit shared memory", smem);
+  const long long tiles = cdiv((long long)N * Ho * Wo, WG_PIX);
+  const int grid = (int)(tiles < 148 * 4 ? tiles : 148 * 4);
+  if (Co == 8)
+    AVSR_LAUNCH(conv_wgrad_kernel<8>, grid, 256, smem, ST(s), x, dy, N, H, W, Ci, kh, kw, stride, pad_top, pad_left, Ho, Wo, dW);
+  else
+    AVSR_LAUNCH(conv_wgrad_kernel<16>, grid, 256, smem, ST(s), x, dy, N, H, W, Ci, kh, kw, stride, pad_top, pad_left, Ho, Wo, dW);
   return 0;
 }
 

@@ -237,6 +237,27 @@ def col2im(dcols, geom):
     return dx
 
 
+def conv2d_direct(x, wmat, bias, kh, kw, stride, padding):
+    """Direct NHWC convolution for 8 / 16 output channels (avsr_conv2d_direct).  wmat [kh*kw*Ci, Co]."""
+    _chk_f32(x, wmat, bias)
+    N, H, W, Ci = x.shape
+    Co = wmat.shape[1]
+    Ho, Wo, pt, pl = conv_geometry(H, W, kh, kw, stride, padding)
+    y = empty(N, Ho, Wo, Co)
+    check(_lib.load().avsr_conv2d_direct(_stream(), x.data_ptr(), N, H, W, Ci, wmat.data_ptr(), _p(bias), kh, kw, stride,
+                                         pt, pl, Ho, Wo, Co, y.data_ptr()))
+    return y
+
+
+def conv2d_wgrad(x, dy, kh, kw, stride, padding, dW):
+    """dW [kh*kw*Ci, Co] += patches(x)^T dy (avsr_conv2d_wgrad)."""
+    N, H, W, Ci = x.shape
+    Ho, Wo, pt, pl = conv_geometry(H, W, kh, kw, stride, padding)
+    Co = dy.shape[-1]
+    check(_lib.load().avsr_conv2d_wgrad(_stream(), x.data_ptr(), dy.data_ptr(), N, H, W, Ci, kh, kw, stride, pt, pl, Ho,
+                                        Wo, Co, dW.data_ptr()))
+
+
 def relu_fwd(x, out=None):
     y = torch.empty_like(x) if out is None else out
     check(_lib.load().avsr_relu_fwd(_stream(), x.data_ptr(), x.numel(), y.data_ptr()))

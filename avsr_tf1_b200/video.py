@@ -6,14 +6,18 @@
     res_block_k (k >= 1): BN-ReLU(x) -> conv3x3 stride 2 -> BN-ReLU -> conv3x3, + conv1x1 stride 2 of the RAW x
     flatten: VALID conv over what is left of the image -> cnn_dense_units, ReLU
 
-Every convolution is avsr_im2col + avsr_gemm (bias in the product's epilogue), its gradients avsr_gemm + avsr_colsum +
-avsr_col2im; BN is the same stats / apply pair as the input normalisation (rows = N*H*W; eps 1e-5, momentum 0.98;
-all-reduced sums under data parallelism).  im2col buffers are not kept: the backward pass rebuilds them from the saved
-layer inputs.  This is the functional version of the row (parity against the oracle); a fused implicit-GEMM tcgen05
-convolution is the next step - the im2col detour moves ~30 GB per step at the bench batch.
+The narrow convolutions (8 / 16 output channels at 36x36 and 18x18: nearly all pixels) run on direct kernels
+(avsr_conv2d_direct, avsr_conv2d_wgrad; exact fp32); the 32- / 64-channel ones are avsr_im2col + avsr_gemm (bias in the
+product's epilogue), their gradients avsr_gemm + avsr_colsum + avsr_col2im.  BN is the same stats / apply pair as the
+input normalisation (rows = N*H*W; eps 1e-5, momentum 0.98; all-reduced sums under data parallelism).  im2col buffers
+are not kept: the backward pass rebuilds them from the saved layer inputs.  This is the functional version of the row
+(parity against the oracle); fusing BN statistics / BN-ReLU into the convolutions and tcgen05 implicit GEMMs for the
+wide layers are the next step.
 
 `2dconv_cnn` / `3dconv_cnn` (video.py:108-140, 198-221) are not built (no reference script selects them)."""
 from __future__ import annotations
+
+import os
 
 import torch
 
@@ -31,18 +35,49 @@ class _Conv(object):
         self.kernel = ctx.declare(name + '/kernel', (kh, kw, cin, cout), 'conv_kernel')
         self.bias = ctx.declare(name + '/bias', (cout,), 'zeros')
 
+    @property
+    def direct(self):
+        """8 / 16 output channels (nearly all pixels of the network): direct convolution kernels, no im2col buffer."""
+        return (self.cout in (8, 16) and self.kh * self.kw * self.cin * self.cout <= 2304
+                and not os.environ.get('AVSR_CNN_IM2COL'))
+
     def forward(self, x):
         """x [N,H,W,Cin] -> [N,Ho,Wo,Cout] (exact fp32 out; the operand copy of x is made by im2col)."""
         ctx = self.ctx
+        self._x = x
+        if self.direct:
+            return ops.conv2d_direct(x, ctx.p(self.kernel).view(-1, self.cout), ctx.p(self.bias), self.kh, self.kw,
+                                     self.stride, self.padding)
         cols, geom = ops.im2col(x, self.kh, self.kw, self.stride, self.padding)
-        self._x, self._geom = x, geom
         N, Ho, Wo = geom[0], geom[9], geom[10]
         y = ops.empty(N, Ho, Wo, self.cout)
         ops.gemm(cols, ctx.w(self.kernel).view(-1, self.cout), y.view(-1, self.cout), bias=ctx.p(self.bias))
         return y
 
+    def _geometry(self):
+        N, H, W, C = self._x.shape
+        Ho, Wo, pt, pl = ops.conv_geometry(H, W, self.kh, self.kw, self.stride, self.padding)
+        return (N, H, W, C, self.kh, self.kw, self.stride, pt, pl, Ho, Wo)
+
     def backward(self, dy, need_dx=True):
         ctx = self.ctx
+        if self.direct:
+            dyc = dy.contiguous()
+            ops.conv2d_wgrad(self._x, dyc, self.kh, self.kw, self.stride, self.padding,
+                             ctx.g(self.kernel).view(-1, self.cout))
+            ops.colsum(dyc.view(-1, self.cout), ctx.g(self.bias))
+            geom = self._geometry()
+            self._x = None
+            if not need_dx:
+                return None
+            if self.stride == 1 and self.padding == 'SAME' and self.cin in (8, 16) and self.kh % 2 == 1:
+                # gradient wrt the input of a stride-1 SAME convolution = the same convolution of dy with the kernel
+                # flipped in space and transposed in channels
+                wt = ctx.p(self.kernel).flip(0, 1).permute(0, 1, 3, 2).contiguous().view(-1, self.cin)
+                return ops.conv2d_direct(dyc, wt, None, self.kh, self.kw, 1, 'SAME')
+            dcols = ops.empty(dyc.numel() // self.cout, self.kh * self.kw * self.cin)
+            ops.gemm(dyc.view(-1, self.cout), ctx.p(self.kernel).view(-1, self.cout), dcols, tb=True)
+            return ops.col2im(dcols, geom)
         cols, geom = ops.im2col(self._x, self.kh, self.kw, self.stride, self.padding)  # rebuilt, not stored
         d2 = dy.reshape(-1, self.cout)
         if ops.tensor_cores_enabled():

@@ -237,6 +237,14 @@ int avsr_im2col(avsr_stream_t stream, const float* x, int N, int H, int W, int C
 /* dx[N,H,W,C] = transpose of im2col applied to dcols (overwrites dx; gather form, deterministic) */
 int avsr_col2im(avsr_stream_t stream, const float* dcols, int N, int H, int W, int C, int kh, int kw, int stride,
                 int pad_top, int pad_left, int Ho, int Wo, float* dx);
+/* the narrow layers (Cout = 8 or 16: nearly all pixels of the front-end) without the im2col buffer: y[N,Ho,Wo,Co] =
+ * conv(x[N,H,W,Ci], w[kh*kw*Ci, Co]) + bias (bias may be NULL), exact fp32; the gradient wrt a stride-1 SAME input is the
+ * same call on dy with the kernel flipped and transposed.  avsr_conv2d_wgrad: dW[kh*kw*Ci, Co] += x-patches^T dy. */
+int avsr_conv2d_direct(avsr_stream_t stream, const float* x, int N, int H, int W, int Ci, const float* w,
+                       const float* bias, int kh, int kw, int stride, int pad_top, int pad_left, int Ho, int Wo, int Co,
+                       float* y);
+int avsr_conv2d_wgrad(avsr_stream_t stream, const float* x, const float* dy, int N, int H, int W, int Ci, int kh, int kw,
+                      int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, float* dW);
 int avsr_relu_fwd(avsr_stream_t stream, const float* x, long long n, float* y);               /* in place allowed */
 int avsr_relu_bwd(avsr_stream_t stream, const float* y, const float* dy, long long n, float* dx); /* dx = dy [y > 0] */
 
