@@ -84,3 +84,50 @@ def test_shard_batch_covers_everything_once():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _shard_worker(rank, world, port, paths, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from avsr_tf1_b200 import io_utils, parallel
+    from avsr_tf1_b200.hparams import create_unit_dict
+    it = io_utils.make_iterator_from_two_records(
+        paths['video'], paths['audio'], paths['labels'], batch_size=6, unit_dict=create_unit_dict(None), shuffle=True,
+        bucket_width=3, seed=5, shuffle_buffer=8, prefetch=1, pin_memory=False,
+        shard=(parallel.rank(), parallel.world_size()))
+    steps = []
+    for b in it:
+        names = [n.decode() for n in b.labels_filenames.tolist()]
+        # what a training step does between ranks: one collective per step must pair up on every rank
+        t = torch.tensor([float(len(names))])
+        parallel.allreduce_sum_(t)
+        steps.append((names, int(t.item())))
+    parallel.barrier()
+    out.put((rank, steps))
+    dist.destroy_process_group()
+
+
+def test_record_iterator_shards_pair_up_across_ranks(tmp_path):
+    """Two gloo ranks walk the same shuffled, bucketed epoch of synthetic TFRecords: same number of steps (their per-step
+    collective pairs up), disjoint slices, and together every utterance of every kept global batch exactly once."""
+    from avsr_tf1_b200.synthetic import write_synthetic_records
+    paths = write_synthetic_records(str(tmp_path), n=31, Ta=16, Tv=8, Fa=4, hw=3, L=4, ragged=True)
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, paths, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    s0, s1 = got[0], got[1]
+    assert len(s0) == len(s1) > 0
+    seen = []
+    for (n0, tot0), (n1, tot1) in zip(s0, s1):
+        assert tot0 == tot1 == len(n0) + len(n1)      # the all-reduce saw both slices of the same global batch
+        assert not set(n0) & set(n1) and abs(len(n0) - len(n1)) <= 1
+        seen += n0 + n1
+    assert len(seen) == len(set(seen))
+    assert len(seen) >= 31 - 2 * 4  # only batches smaller than the world (at most one per bucket) are dropped
