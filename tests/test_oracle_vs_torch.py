@@ -158,3 +158,34 @@ def test_sequence_loss_matches_torch_cross_entropy():
     lt.backward()
     assert abs(loss - float(lt.detach())) < 1e-12
     assert np.allclose(dlogits, zt.grad.numpy(), atol=1e-14)
+
+
+@pytest.mark.parametrize('optimiser', ['Adam', 'AdamW', 'Momentum'])
+def test_optimisers_match_torch_optim(optimiser):
+    """clip_by_global_norm + the optimisers of seq2seq.py:195-219 against torch.optim over five steps.
+    TF-Adam folds the bias corrections into the step size and adds epsilon to sqrt(v) un-corrected; torch corrects v
+    first: the two differ only through epsilon (1e-8 against gradients of order 1), hence the 1e-6 tolerance on the
+    updates.  tf.contrib's AdamW decays by weight_decay un-scaled by the learning rate = torch's AdamW with
+    weight_decay / lr.  torch's clip_grad_norm_ divides by (norm + 1e-6)."""
+    rng = np.random.default_rng(5)
+    lr, wd, clip = 1e-2, 1e-3, 1.0
+    P = {'a': rng.standard_normal((4, 3)), 'b': rng.standard_normal(5)}
+    P0 = {k: v.copy() for k, v in P.items()}
+    grads = [{k: rng.standard_normal(v.shape) * (3.0 if s % 2 else 0.2) for k, v in P.items()} for s in range(5)]
+    m = {k: np.zeros_like(v) for k, v in P.items()}
+    v_ = {k: np.zeros_like(v) for k, v in P.items()}
+    tp = {k: torch.nn.Parameter(torch.tensor(v)) for k, v in P.items()}
+    opt = {'Adam': lambda: torch.optim.Adam(tp.values(), lr=lr, eps=1e-8),
+           'AdamW': lambda: torch.optim.AdamW(tp.values(), lr=lr, eps=1e-8, weight_decay=wd / lr),
+           'Momentum': lambda: torch.optim.SGD(tp.values(), lr=lr, momentum=0.9)}[optimiser]()
+    for s, G in enumerate(grads):
+        gn = O.clip_and_adam(P, G, m, v_, s, lr, clip=clip, warmup_steps=None, optimiser=optimiser, weight_decay=wd)
+        for k in tp:
+            tp[k].grad = torch.tensor(G[k])
+        gn_t = torch.nn.utils.clip_grad_norm_(tp.values(), clip)
+        assert abs(gn - float(gn_t)) < 1e-12  # both return the pre-clip norm
+        opt.step()
+    for k in P:
+        moved = np.abs(P[k] - P0[k]).max()
+        assert moved > 1e-3
+        assert np.abs(P[k] - tp[k].detach().numpy()).max() <= 2e-6 * max(moved, 1.0), k
