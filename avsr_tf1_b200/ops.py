@@ -3,7 +3,7 @@ buffers (allocation, streams); every arithmetic kernel is in libavsr_b200.so."""
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 import torch

@@ -3,7 +3,6 @@ a single frame inside a ragged batch, a memory longer than the persistent attent
 the step-wise kernels), the decoding cap."""
 import numpy as np
 import pytest
-import torch
 
 from oracle import avsr_oracle as O
 from tests.helpers import cast_batch, config_hparams, oracle_hparams, synthetic_batch, to_data_sequences
