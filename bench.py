@@ -404,6 +404,45 @@ def tfrecord_e2e(args, torch, model, n_utt):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def cer_check(args, torch, ops):
+    """Second half of BASELINE.json's metric ("CER match vs TF1 ref"): greedy decoding of a small AV-Align batch by the
+    product (exact-fp32 mode, so arg-max decisions are reproducible) against the CPU restatement of the TF1 graph; the
+    predicted ids must be equal, hence the integer edit distances and the CER.  Part of the cpu_baseline leg (the only
+    place besides the reference arm where bench.py runs the oracle)."""
+    from avsr_tf1_b200 import utils
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    from oracle import avsr_oracle as O
+    from tests.helpers import cast_batch, config_hparams, oracle_hparams, synthetic_batch, to_data_sequences
+    old = ops.set_tensor_cores(False)
+    try:
+        hp = config_hparams(5, attention_type=((args.attention,), (args.attention,)), decoding_algorithm='greedy')
+        hp.max_label_length = 12
+        # (the configuration of tests/test_gpu_model.py::test_decoding_and_error_rates[5-greedy])
+        batch = synthetic_batch(hp, B=3, Ta=30, Tv=10, L=6, ragged=True)
+        ds = to_data_sequences(batch)
+        train = Seq2SeqModel(ds, 'train', hp, seed=2001)
+        train.store.p('Decoder/decoder/my_dense/kernel').mul_(20.0)  # sharpen the outputs: no near-ties
+        train.store.sync_tf32()
+        for _ in range(2):
+            train.train_step(ds)
+        ev = Seq2SeqModel(ds, 'evaluate', hp, share_params_with=train)
+        ids = ev.predict(ds)
+        P = {k: v.astype(np.float32) for k, v in train.store.to_numpy('p').items()}
+        ref = O.OracleModel(oracle_hparams(hp), P).greedy_decode(cast_batch(batch, np.float32))
+        ud = hp.unit_dict
+        names = ['utt%d' % b for b in range(ids.shape[0])]
+        truth = {n: utils.ids_to_symbols(batch['labels'][b], ud) for b, n in enumerate(names)}
+        cer = utils.compute_wer({n: utils.ids_to_symbols(ids[b], ud) for b, n in enumerate(names)}, truth)[0]
+        cer_ref = O.compute_wer({n: utils.ids_to_symbols(ref[b], ud) for b, n in enumerate(names)}, truth)[0]
+        same = ids.shape == ref.shape and bool(np.array_equal(ids, ref))
+        return {'ids_equal': same, 'cer': cer, 'cer_oracle': cer_ref, 'cer_equal': cer == cer_ref,
+                'utterances': int(ids.shape[0]), 'decoded_steps': int(ids.shape[1]),
+                'how': 'greedy decoding, exact-fp32 mode, AV-Align 3x256, after two training steps; oracle = CPU '
+                       'restatement of the TF1 graph (TensorFlow 1.13 cannot run here)'}
+    finally:
+        ops.set_tensor_cores(old)
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -560,6 +599,10 @@ def main():
             'value': round(r['value'], 3), 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
             'sample': f'{r["sample"]} utterances per step of the same workload at full sequence lengths, 3 timed '
                       'steps (about 10 s of host work); NumPy/OpenBLAS restatement of the TF1 graph (oracle/)'}
+        try:
+            line['cpu_baseline']['cer_check'] = cer_check(args, torch, ops)
+        except Exception as ex:
+            line['cpu_baseline']['cer_check'] = {'error': repr(ex)}
     print(json.dumps(line), flush=True)
     finish()
 
