@@ -306,3 +306,28 @@ def make_iterator_from_label_record(label_record, batch_size, unit_dict, shuffle
     kw.setdefault('shuffle_buffer', 45000)
     return RecordBatcher([], label_record, unit_dict, batch_size, shuffle=shuffle, bucket_width=bucket_width,
                          num_cores=num_cores, **kw)
+
+
+def _get_input_shape_from_record(record):
+    """io_utils.py:308-341: ([input_size] | [width, height, channels], {'stream': 'feature' | 'video'[, 'aus': True]})."""
+    from .tfrecord import KIND_FEATURE, KIND_LABELS, RecordFile
+    f = RecordFile(record)
+    try:
+        if f.kind == KIND_LABELS:
+            raise Exception('%s is a label record' % record)
+        content_type = {'stream': 'feature' if f.kind == KIND_FEATURE else 'video'}
+        if f.has_aus:
+            content_type['aus'] = True
+        return list(f.input_shape), content_type
+    finally:
+        f.close()
+
+
+def _get_unit_from_record(record):
+    """io_utils.py:344-351: the `unit` string stored in the context of a label record."""
+    from .tfrecord import RecordFile
+    f = RecordFile(record)
+    try:
+        return f.unit
+    finally:
+        f.close()

@@ -361,3 +361,12 @@ def test_golden_records_written_by_protobuf():
         assert np.array_equal(xv[i, :lv[i]], np.asarray(wv['inputs'], np.float32))
         assert np.array_equal(av[i, :lv[i]], np.asarray(wv['aus'], np.float32))
         assert y[i, :ly[i]].tolist() == wl['labels'] + [29]
+
+
+def test_record_inspection_helpers_keep_the_reference_names():
+    g = os.path.join(ROOT, 'tests', 'golden')
+    assert io_utils._get_input_shape_from_record(os.path.join(g, 'sequence_examples_feature.tfrecord')) == \
+        ([5], {'stream': 'feature'})
+    assert io_utils._get_input_shape_from_record(os.path.join(g, 'sequence_examples_video.tfrecord')) == \
+        ([2, 3, 3], {'stream': 'video', 'aus': True})
+    assert io_utils._get_unit_from_record(os.path.join(g, 'sequence_examples_labels.tfrecord')) == 'character'
