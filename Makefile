@@ -16,7 +16,7 @@ $(IOLIB): avsr_tf1_b200/csrc_host/tfrecord.cc include/avsr_io.h
 	mkdir -p avsr_tf1_b200/lib
 	$(CXX) -O3 -std=c++17 -fPIC -Wall -shared -pthread -o $@ $<
 
-%.o: %.cu avsr_tf1_b200/csrc/common.cuh include/avsr_b200.h
+%.o: %.cu avsr_tf1_b200/csrc/common.cuh avsr_tf1_b200/csrc/ap4_common.cuh include/avsr_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(OBJ)

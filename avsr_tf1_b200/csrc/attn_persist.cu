@@ -1033,6 +1033,17 @@ __global__ void __launch_bounds__(BwdCfg<NB>::THREADS, 1) attn_lstm_persist_bwd_
   cluster_sync_all();
 }
 
+// all steps at once: rows = T*Bt, step of a row = row / Bt
+__global__ void emit_attention_all_kernel(int T, int Bt, int At, int SW, const int* __restrict__ len,
+                                          const float* __restrict__ S1, float* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)T * Bt * At) return;
+  long long row = idx / At;
+  int a = (int)(idx - row * At);
+  int t = (int)(row / Bt), b = (int)(row - (long long)t * Bt);
+  out[idx] = t < len[b] ? S1[(size_t)row * SW + a] : 0.0f;
+}
+
 // dA[t,b,:] += (t < len[b]) ? dout[t,b,:] : 0
 __global__ void masked_add_kernel(float* __restrict__ dA, const float* __restrict__ dout, const int* __restrict__ len,
                                   int T, int Bt, int At, int rnd) {
@@ -1111,6 +1122,12 @@ int attn_persist4_launch_bwd(cudaStream_t st, int T, int B, int Tm, int scaled, 
                              const float* douthc, const float* dcT, const float* dhT, float* dZ, float* ds, float* dhc,
                              float* dg, float* dc0, float* dh0, float* dbias);  // attn_persist4.cu
 
+int attn_persist4d_launch_fwd(cudaStream_t st, const AvsrRnnSeq* r, const void* keys_h, const void* values_h);  // attn_persist4d.cu
+int attn_persist4d_launch_bwd(cudaStream_t st, const AvsrRnnSeq* r, const void* keys_h, const void* values_h);  // attn_persist4d.cu
+
+// DropoutWrapper of the wrapped cell on: the two-product kernels of attn_persist4d.cu (no fold of the attention layer)
+static bool layer_dropout(const AvsrRnnSeq* r) { return r->rng && (r->thr_in | r->thr_state | r->thr_out); }
+
 size_t attn_persist_work_floats(int B, int H, int Dm, int Tm) {
   // fused weights [(H+Dm),4H] + product scratch [H,4H] + fp16 keys / values
   return (size_t)(H + Dm) * 4 * H + (size_t)H * 4 * H + ((size_t)Tm * B * (H + Dm) + 1) / 2 + 64;
@@ -1124,6 +1141,7 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   const AvsrAttnMech& m = r->mech[0];
   if (m.kind > AVSR_ATTN_SCALED_LUONG) return -1;
   if (r->H != H || m.A != H || m.Dm != DM || m.Tm > MAX_TM) return -1;
+  if (layer_dropout(r) && (!r->output_attention || cluster_width() != 4)) return -1;
   const int T = r->T, B = r->B, At = m.A, SW = At + H;
   float* Wp = scratch;
   float* tmp = Wp + (size_t)(H + DM) * 4 * H;
@@ -1131,6 +1149,14 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   __half* values_h = keys_h + (size_t)m.Tm * B * H;
   // step 0: att_{-1} = 0, so only h_0 Wh enters (exact AttentionWrapper zero-state semantics)
   AVSR_TRY(gemm(st, 0, 0, B, 4 * H, H, r->S + At, SW, r->Wrec + (size_t)At * 4 * H, 4 * H, r->gates, 4 * H, 1.0f, nullptr));
+  if (layer_dropout(r)) {
+    // DropoutWrapper on: no fused matrix; the kernel forms the attention vectors itself and writes `out` (attention
+    // vectors, zero past the length) and the state rows [a (.) m_in | hs]
+    const long long nk = (long long)m.Tm * B * H, nv = (long long)m.Tm * B * DM;
+    AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
+    AVSR_LAUNCH(to_half_kernel, cdiv(nv, 256), 256, 0, st, m.values, values_h, nv);
+    return attn_persist4d_launch_fwd(st, r, keys_h, values_h);
+  }
   // fused recurrent matrix W' = [Wh + Wl_h Wa ; Wl_c Wa]
   AVSR_CHECK_CUDA(cudaMemcpyAsync(Wp, r->Wrec + (size_t)At * 4 * H, (size_t)H * 4 * H * sizeof(float),
                                   cudaMemcpyDeviceToDevice, st));
@@ -1174,6 +1200,9 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   }
   // attention vectors of all steps in one product: S[1:, :, :At] = [h | ctx] Wl (tf32-rounded operand rows)
   AVSR_TRY(gemm(st, 0, 0, T * B, At, H + DM, m.hc, H + DM, m.Wl, m.A, r->S + (size_t)B * SW, SW, 0.0f, nullptr, 1));
+  if (r->output_attention)  // layer output = attention vectors, zero past the length
+    AVSR_LAUNCH(emit_attention_all_kernel, cdiv((long long)T * B * At, 256), 256, 0, st, T, B, At, SW, r->len,
+                r->S + (size_t)B * SW, r->out);
   return 0;
 }
 
@@ -1183,18 +1212,37 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
 int attn_outer(cudaStream_t st, int T, int B, int Tm, int C, const int* seq_len, const float* w, const float* x,
                int ldx, const float* scale, float* out);  // attention.cu
 
-int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
+int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch, bool unfused) {
   using namespace ap;
   if (r->n_mech != 1 || r->T <= 1) return -1;
   const AvsrAttnMech& m = r->mech[0];
   if (m.kind > AVSR_ATTN_SCALED_LUONG) return -1;
   if (r->H != H || m.A != H || m.Dm != DM || m.Tm > MAX_TM) return -1;
+  unfused = unfused || layer_dropout(r);
+  if (unfused && (!r->output_attention || cluster_width() != 4)) return -1;
   const int T = r->T, B = r->B, At = m.A, SW = At + H, HD = H + DM;
   const bool oa = r->output_attention != 0;
   float* Wp = scratch;
   float* tmp = Wp + (size_t)HD * 4 * H;
   __half* keys_h = reinterpret_cast<__half*>(tmp + (size_t)H * 4 * H);
   __half* values_h = keys_h + (size_t)m.Tm * B * H;
+  if (unfused) {
+    // two-product kernel: forms dZ, ds, dhc (ctx columns), dA itself; the fp16 memories are rebuilt here so that the
+    // backward does not depend on which forward path ran (a ranged step-wise forward leaves the same activations)
+    AVSR_REQUIRE(r->dA != nullptr, "rnn bwd: dA scratch missing");
+    const long long nk = (long long)m.Tm * B * H, nv = (long long)m.Tm * B * DM;
+    AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
+    AVSR_LAUNCH(to_half_kernel, cdiv(nv, 256), 256, 0, st, m.values, values_h, nv);
+    AVSR_CHECK_CUDA(cudaMemsetAsync(m.dhc, 0, (size_t)T * B * HD * sizeof(float), st));
+    AVSR_TRY(attn_persist4d_launch_bwd(st, r, keys_h, values_h));
+    if (r->dh0)  // dh_0 += dz_0 Wh^T (the kernel stops before the product of step 0)
+      AVSR_TRY(gemm(st, 0, 1, B, H, 4 * H, r->dZ, 4 * H, r->Wrec + (size_t)At * 4 * H, 4 * H, r->dh0, H, 1.0f, nullptr));
+    AVSR_TRY(gemm(st, 1, 0, SW, 4 * H, T * B, r->S, SW, r->dZ, 4 * H, r->dWrec, 4 * H, 1.0f, nullptr));
+    AVSR_TRY(gemm(st, 1, 0, HD, At, T * B, m.hc, HD, r->dA, At, m.dWl, m.A, 1.0f, nullptr));
+    AVSR_TRY(attn_outer(st, T, B, m.Tm, DM, r->len, m.align, m.dhc + H, HD, nullptr, m.dvalues));
+    AVSR_TRY(attn_outer(st, T, B, m.Tm, At, r->len, m.ds, m.hc, HD, m.kind == AVSR_ATTN_SCALED_LUONG ? m.g : nullptr, m.dkeys));
+    return 0;
+  }
   // (dout Wl^T) for every step: the part of d[h | ctx] that does not depend on the recurrence
   // It is written into m.dhc itself: the kernel reads an entry and then overwrites the ctx columns with the
   // total dctx_t (same thread, same address).

@@ -1,0 +1,966 @@
+// Persistent AttentionWrapper(DropoutWrapper(LSTMCell)) layer on clusters of four CTAs: the reference's DEFAULT
+// training graph (cells.py:46-54 wraps every cell in DropoutWrapper(input, state, output keep = 0.9); avsr.py:51-56;
+// attention.py:132-191 wraps that in the AttentionWrapper; encoder.py:265-290 AV-Align layer,
+// decoder_unimodal.py:299-352 decoder).  Luong / scaled-Luong scorer, one mechanism, H = A = Dm = 256.
+//
+// Why a second kernel family next to attn_persist4.cu: there the attention layer is folded into the recurrent matrix
+// (W' = [Wh + Wl_h Wa ; Wl_c Wa] over the operand [h | ctx]).  The DropoutWrapper's INPUT mask acts on the fed-back
+// attention vector, i.e. exactly between the two factors of that fold, so the step needs two dependent products:
+//
+//   a_t      = [ho_t | ctx_t] Wa                       ho_t = h_t (.) m_out(t)   (the cell output: query and emitted h)
+//   z_{t+1}  = gx_{t+1} + [a_t (.) m_in(t+1) | hs_t] [Wl_att ; Wh]              hs_t = h_t (.) m_state(t)
+//
+// Same cluster geometry as attn_persist4.cu (4 CTAs x 8 utterances; a CTA owns 64 hidden units = 256 gate rows, 64
+// attention units and the attention of 2 utterances).  Per CTA:
+//   * recurrent matrix [Wl_att ; Wh] restricted to its gate rows: tile 0 (128 x 512 fp16) in shared memory, tile 1 in
+//     tensor memory (columns 256..511), as before;
+//   * its 64 x 512 slice of Wa in tensor memory columns 128..255 as ONE 128-row A operand with K = 256: lanes 0..63
+//     hold the rows that multiply ho, lanes 64..127 the rows that multiply ctx; the B operand has ho in rows 0..7 and
+//     ctx in rows 8..15, so D[u][b] (lanes 0..63, columns 0..7) + D[64+u][8+b] is a_t - half the MMAs of a K = 512
+//     product and exactly the tensor memory that was left;
+//   * 128 accumulator columns shared by both products (they never overlap in time: the recurrent product of step t+1
+//     can only start when a_t has been all-gathered).
+// Exchanges per step (DSMEM st.async + mbarrier complete_tx, all-gathers over the 4 CTAs): {hs_t, ho_t}, ctx_t, a_t.
+// Masks come from the counter-based generator (common.cuh avsr_rand_u32), computed one step ahead of their use.
+#include "ap4_common.cuh"
+
+namespace avsr {
+namespace ap4 {
+
+constexpr int AT = 256;                   // attention units (Luong: = H)
+constexpr int Q_BYTES = 4 * NP * 128;     // P2 operand: [rows 0..7 ho | rows 8..15 ctx] x K = 256
+constexpr int APART_FLOATS = 4 * NB * UPC;  // partial a_t planes [K group (2)][part (2)][b][u]
+
+struct DropCfg {
+  const uint32_t* rng;  // {seed, step}
+  uint32_t stream, thr_in, thr_state, thr_out;
+  float inv_in, inv_state, inv_out;
+};
+__device__ __forceinline__ float dfac(uint32_t seed, uint32_t step, uint32_t stream, uint32_t thr, float inv, uint32_t hi,
+                                      uint32_t lo) {
+  return (thr == 0u || avsr_rand_u32(seed, step, stream, hi, lo) < thr) ? inv : 0.0f;
+}
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+struct DParams {
+  int T, B, Tm;
+  int scaled;
+  const int* len;
+  const int* mem_len;
+  float* gates;          // [T,B,4H] in: x-projection (+ h0 Wh at t = 0); out: activations
+  const float* Wrec;     // [(AT+H), 4H] rows [attention ; h]
+  const float* Wa;       // attention_layer kernel [(H+DM), AT]
+  const __half* keys;    // [Tm,B,H]
+  const __half* values;  // [Tm,B,DM]
+  const float* g;        // attention_g [1] or null
+  const float* c0;       // [B,H] or null
+  float* S;              // [(T+1),B,AT+H]; S[0] by the caller; rows 1.. = [a (.) m_in | hs], tf32-rounded
+  float* craw;           // [T,B,H]
+  float* out;            // [T,B,AT] attention vectors (tf32-rounded), zero past the length
+  float* hc;             // [T,B,H+DM]  [ho | ctx], tf32-rounded
+  float* align;          // [T,B,Tm]
+  float* cT;             // [B,H] or null
+  float* hT;             // [B,H] or null
+  DropCfg d;
+};
+
+constexpr size_t DFWD_SMEM = (size_t)W_BYTES + 2 * OP_BYTES + Q_BYTES + 4 * NB * UPC * 4 + APART_FLOATS * 4 +
+                             NU * MAX_TM * 4 + NU * 8 * 4 + 64 + 1024;
+
+__global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(const DParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW = base;                          // recurrent tile 0: gate rows of the CTA's units 0..31
+  const uint32_t sOp = sW + W_BYTES;                 // two operand buffers [a (.) m_in | hs], NP rows (rows >= NB zero)
+  const uint32_t sQ = sOp + 2 * OP_BYTES;            // [rows 0..7 ho | rows 8..15 ctx] x 256
+  const uint32_t sAct = sQ + Q_BYTES;                // [4][NB][UPC] floats; also [NU][4][DM] partial contexts
+  const uint32_t sAp = sAct + 4 * NB * UPC * 4;      // [4][NB][UPC] partial attention vectors
+  const uint32_t sSc = sAp + APART_FLOATS * 4;       // [NU][MAX_TM] scores / alignments
+  const uint32_t sRed = sSc + NU * MAX_TM * 4;       // [NU][8]
+  const uint32_t sBar = sRed + NU * 8 * 4;           // [0] mma1 [1] mma2 [2,3] h_full[buf] [4] ctx_full [5] a_full
+  const uint32_t sTmem = sBar + 48;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  float* act = reinterpret_cast<float*>(gen + (sAct - base));
+  float* apart = reinterpret_cast<float*>(gen + (sAp - base));
+  float* sc_all = reinterpret_cast<float*>(gen + (sSc - base));
+  float* part_all = act;
+  float* red_all = reinterpret_cast<float*>(gen + (sRed - base));
+  const uint32_t barM1 = sBar, barM2 = sBar + 8, barCtx = sBar + 32, barA = sBar + 40;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int b0 = cluster_id_x() * NB;
+  const int T = p.T, B = p.B, Tm = p.Tm;
+
+  if (tid == 0) {
+    mbar_init(barM1, THREADS / 32);  // one commit per issuing warp
+    mbar_init(barM2, THREADS / 32);
+    for (int i = 2; i < 6; ++i) mbar_init(sBar + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // tensor memory (all 512 columns): [0, 128) accumulators (8 x 16 columns, shared by the two products);
+  // [128, 256) Wa slice (paired layout); [256, 512) recurrent tile 1
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // recurrent tile 0 -> shared memory as fp16: row r = gate*32 + u  <->  Wrec[k][gate*H + 64*rank + u], u < 32
+  for (int seg = warp; seg < KTOT * 4; seg += THREADS / 32) {
+    const int k = seg >> 2, g = seg & 3;
+    const float w = p.Wrec[(size_t)k * 4 * H + g * H + UPC * rank + lane];
+    *reinterpret_cast<__half*>(gen + (sW - base) + sw128h_off(128, g * 32 + lane, k)) = __float2half_rn(w);
+  }
+  // operand buffers start as zeros (the padding rows stay zero; no product reads them before they are filled)
+  for (int i = tid; i < (2 * OP_BYTES + Q_BYTES) / 4; i += THREADS) reinterpret_cast<uint32_t*>(gen + (sOp - base))[i] = 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
+  const uint32_t tWa = tmem_base + 128, tW1 = tmem_base + 256;
+  {
+    // recurrent tile 1 -> tensor memory: lane r = gate*32 + u <-> unit 32 + u; column c holds K elements 2c, 2c+1.
+    // warp w fills lane quarter (w & 3) = gate, columns 128*(w >> 2) .. +127
+    const int q = warp & 3, hh = warp >> 2;
+    const float* col = p.Wrec + q * H + UPC * rank + 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t r[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = 2 * (128 * hh + c0 + c);
+        r[c] = pack_h2(col[(size_t)k * 4 * H], col[(size_t)(k + 1) * 4 * H]);
+      }
+      tmem_st32(tW1 + 128 * hh + c0 + ((uint32_t)(32 * q) << 16), r);
+    }
+    // Wa slice: lane l = 32 q + lane: part = l >> 6 (0: rows multiplying ho, 1: rows multiplying ctx), attention unit
+    // 64*rank + (l & 63); column c holds K elements 2c, 2c+1 of that part; warp w fills columns 64*(w >> 2) .. +63
+    const int l = 32 * q + lane;
+    const float* wcol = p.Wa + (size_t)((l >> 6) * H) * AT + UPC * rank + (l & 63);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t r[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = 2 * (64 * hh + c0 + c);
+        r[c] = pack_h2(wcol[(size_t)k * AT], wcol[(size_t)(k + 1) * AT]);
+      }
+      tmem_st32(tWa + 64 * hh + c0 + ((uint32_t)(32 * q) << 16), r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  cluster_sync_all();
+
+  // gate-math role: warp <-> (gate g, tile m): the gate rows of units 32*m + lane for all NB utterances
+  const int g = warp & 3, m = warp >> 2;
+  // product-issue role (lane 0 of EVERY warp; a tcgen05.mma costs ~80 clocks of its issuing thread).  Recurrent product:
+  // warp (m, j) issues K blocks j (attention half) and 4 + j (h half) of tile m into accumulator 4 m + j.  Attention
+  // product: warp w issues K steps 2 w, 2 w + 1 (of 16) into accumulator w.
+  const int jq = warp & 3;
+  const uint32_t acc1 = tmem_base + (4 * m + jq) * NP, acc2 = tmem_base + warp * NP;
+  const uint64_t dW0 = make_desc_k128(sW), dQ = make_desc_k128(sQ);
+  const uint64_t dOp[2] = {make_desc_k128(sOp), make_desc_k128(sOp + OP_BYTES)};
+  auto issue_rec = [&](uint32_t nbuf) {
+    if (lane == 0) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int kb = 4 * half + jq;
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint64_t db = desc_at(dOp[nbuf], kb * (NP * 128) + k4 * 32);
+          const uint32_t acc = (half | k4) ? 1u : 0u;
+          if (m == 0) umma_ss(acc1, desc_at(dW0, kb * (128 * 128) + k4 * 32), db, IDESC, acc);
+          else umma_ts(acc1, tW1 + (kb * 4 + k4) * 8, db, IDESC, acc);
+        }
+      }
+      umma_commit(barM1);
+    }
+    __syncwarp();
+  };
+  auto issue_att = [&]() {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int s = 2 * warp + i;  // K step of 16: K block s >> 2, 32-byte slice s & 3
+        umma_ts(acc2, tWa + s * 8, desc_at(dQ, (s >> 2) * (NP * 128) + (s & 3) * 32), IDESC, i ? 1u : 0u);
+      }
+      umma_commit(barM2);
+    }
+    __syncwarp();
+  };
+  const int unit_g = UPC * rank + 32 * m + lane;
+  // combine role (threads 0..127): utterance bq, units (hidden and attention) 4*uq .. 4*uq+3 of the CTA
+  const bool comb = tid < 4 * 32;
+  const int uq = tid & 15, bq = (tid >> 4) & 7;
+  float c_state[4], h_state[4];
+  int len_c = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) c_state[e] = h_state[e] = 0.0f;
+  if (comb) {
+    const int b = b0 + bq;
+    len_c = (b < B) ? p.len[b] : 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int u = UPC * rank + 4 * uq + e;
+      c_state[e] = (b < B && p.c0) ? p.c0[(size_t)b * H + u] : 0.0f;
+      h_state[e] = (b < B) ? p.S[(size_t)b * (AT + H) + AT + u] : 0.0f;
+    }
+  }
+  const uint32_t seed = p.d.rng ? p.d.rng[0] : 0u, rstep = p.d.rng ? p.d.rng[1] : 0u;
+  float f_state[4], f_out[4], f_in[4];
+  auto drop_factors = [&](int t) {  // state / output masks of step t, input mask of step t + 1 (acts on a_t)
+    if (comb) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t col = (uint32_t)(UPC * (int)rank + 4 * uq + e);
+        const uint32_t idx = (uint32_t)(b0 + bq) * (uint32_t)H + col;  // H == AT
+        f_state[e] = dfac(seed, rstep, p.d.stream + 1u, p.d.thr_state, p.d.inv_state, (uint32_t)t, idx);
+        f_out[e] = dfac(seed, rstep, p.d.stream + 2u, p.d.thr_out, p.d.inv_out, (uint32_t)t, idx);
+        f_in[e] = dfac(seed, rstep, p.d.stream, p.d.thr_in, p.d.inv_in, (uint32_t)(t + 1), idx);
+      }
+    }
+  };
+#pragma unroll
+  for (int e = 0; e < 4; ++e) f_state[e] = f_out[e] = f_in[e] = 1.0f;
+  drop_factors(0);
+  int len_a[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) len_a[b] = (b0 + b < B) ? p.len[b0 + b] : 0;
+  float gx[NB];
+  {
+    const float* grow0 = p.gates + (size_t)b0 * 4 * H + g * H + unit_g;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) gx[b] = (0 < len_a[b]) ? grow0[(size_t)b * 4 * H] : 0.0f;
+  }
+  // attention role: utterance jl of this CTA, warp w4 of its group of four
+  const int jl = warp >> 2, w4 = warp & 3, gt = tid & 127;
+  const int bl_att = NU * (int)rank + jl;      // row of the utterance in the operand buffers
+  const int b_att = b0 + bl_att;
+  const int len_q = (b_att < B) ? p.len[b_att] : 0;
+  const int L = (b_att < B) ? min(p.mem_len[b_att], Tm) : 0;
+  const float gs = p.scaled ? p.g[0] : 1.0f;
+  float* sc = sc_all + jl * MAX_TM;
+  float* part = part_all + jl * 4 * DM;
+  float* red = red_all + jl * 8;
+  const uint32_t att_bar_id = 2 + jl;          // named barrier of the 128 threads of this utterance
+  const AttRole role = {p.keys, p.values, L, B, b_att, Tm, w4, gt, lane, gs, att_bar_id, sc, part, red};
+
+  for (int t = 0; t < T; ++t) {
+    float* grow = p.gates + ((size_t)t * B + b0) * 4 * H + g * H + unit_g;
+    uint32_t r[8];
+    if (t > 0) {
+      mbar_wait(barM1, (t - 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r1[8], r2[8], r3[8];
+      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 0) * NP, r);
+      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 1) * NP, r1);
+      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 2) * NP, r2);
+      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 3) * NP, r3);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+        r[b] = __float_as_uint((__uint_as_float(r[b]) + __uint_as_float(r1[b])) + (__uint_as_float(r2[b]) + __uint_as_float(r3[b])));
+    } else {
+#pragma unroll
+      for (int b = 0; b < 8; ++b) r[b] = 0u;  // att_{-1} = 0; h_0 Wh is already in the x-projection
+    }
+    float av[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const float z = __uint_as_float(r[b]) + gx[b];
+      float a;
+      if (g == 1) a = tanhf_acc(z);
+      else a = sigmoidf_acc(g == 2 ? z + 1.0f : z);
+      av[b] = a;
+      act[(g * NB + b) * UPC + 32 * m + lane] = a;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const uint32_t nb = (t + 1) & 1;
+    const uint32_t hbar_n = sBar + 16 + 8 * nb;
+    float hs[4], ho[4], cr[4];
+    if (comb) {
+      const bool live = t < len_c;
+      if (live) {
+        const float4 ai = *reinterpret_cast<const float4*>(&act[(0 * NB + bq) * UPC + 4 * uq]);
+        const float4 aj = *reinterpret_cast<const float4*>(&act[(1 * NB + bq) * UPC + 4 * uq]);
+        const float4 af = *reinterpret_cast<const float4*>(&act[(2 * NB + bq) * UPC + 4 * uq]);
+        const float4 ao = *reinterpret_cast<const float4*>(&act[(3 * NB + bq) * UPC + 4 * uq]);
+        const float vi[4] = {ai.x, ai.y, ai.z, ai.w}, vj[4] = {aj.x, aj.y, aj.z, aj.w};
+        const float vf[4] = {af.x, af.y, af.z, af.w}, vo[4] = {ao.x, ao.y, ao.z, ao.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          cr[e] = vf[e] * c_state[e] + vi[e] * vj[e];
+          const float c = fminf(fmaxf(cr[e], -1.0f), 1.0f);
+          const float h = vo[e] * tanhf_acc(c);
+          c_state[e] = c;
+          ho[e] = tf32_rn(h * f_out[e]);         // the cell output: query, attention-layer operand
+          h_state[e] = tf32_rn(h * f_state[e]);  // what recurs
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          cr[e] = c_state[e];
+          ho[e] = h_state[e];  // the carried state stands in for the output of a finished row (nobody reads it)
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hs[e] = h_state[e];
+      // all-gathers (fp16): hs_t -> h half of the recurrent operand of step t+1; ho_t -> rows 0..7 of the attention operand
+      const int ucol = UPC * (int)rank + 4 * uq;
+      const uint32_t s01 = pack_h2(hs[0], hs[1]), s23 = pack_h2(hs[2], hs[3]);
+      const uint32_t o01 = pack_h2(ho[0], ho[1]), o23 = pack_h2(ho[2], ho[3]);
+      const uint32_t dS = sOp + nb * OP_BYTES + sw128h_off(NP, bq, AT + ucol);
+      const uint32_t dO = sQ + sw128h_off(NP, bq, ucol);
+#pragma unroll
+      for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) {
+        const uint32_t bar = mapa(hbar_n, dst);
+        st_async_v2(mapa(dS, dst), bar, s01, s23);
+        st_async_v2(mapa(dO, dst), bar, o01, o23);
+      }
+    }
+    // HBM side of this step + x-projection of the next (overlaps the all-gather)
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      if (t < len_a[b]) grow[(size_t)b * 4 * H] = av[b];
+    if (comb && b0 + bq < B) {
+      const size_t row = (size_t)t * B + b0 + bq;
+      const int u0 = UPC * rank + 4 * uq;
+      *reinterpret_cast<float4*>(p.craw + row * H + u0) = make_float4(cr[0], cr[1], cr[2], cr[3]);
+      *reinterpret_cast<float4*>(p.S + (row + B) * (AT + H) + AT + u0) = make_float4(hs[0], hs[1], hs[2], hs[3]);
+      *reinterpret_cast<float4*>(p.hc + row * (H + DM) + u0) = make_float4(ho[0], ho[1], ho[2], ho[3]);
+    }
+    if (t + 1 < T) {
+      const float* gnext = grow + (size_t)B * 4 * H;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) gx[b] = (t + 1 < len_a[b]) ? gnext[(size_t)b * 4 * H] : 0.0f;
+    }
+    // ---------------- attention of utterance b_att with query ho_t ----------------
+    const bool live_q = t < len_q;    // masked steps (and padding utterances) skip the memory sweep
+    uint4 ra[4], rb[4];
+    if (live_q) att_prefetch(role, p.keys, ra, rb);
+    if (tid == 0) mbar_expect_tx(hbar_n, 2 * NB * H * 2);
+    mbar_wait(hbar_n, (t >> 1) & 1);  // every CTA's hs_t / ho_t slices have landed
+
+    float ctxv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ctxv[e] = 0.0f;
+    if (live_q) {
+      // query: lane holds dims 8*lane .. 8*lane+7 (one swizzled 16-byte chunk of the operand row)
+      const uint4 qraw = *reinterpret_cast<const uint4*>(gen + (sQ - base) + sw128h_off(NP, bl_att, 8 * lane));
+      att_fwd_core(role, qraw, ra, rb, p.align + ((size_t)t * B + b_att) * Tm, ctxv);
+    }
+    if (w4 == 0) {
+      // ctx_t of this utterance: HBM (tf32-rounded fp32, for the backward pass) + all-gather (fp16, rows 8..15 of sQ)
+      if (b_att < B) {
+        float* dst = p.hc + ((size_t)t * B + b_att) * (H + DM) + H + 8 * lane;
+        *reinterpret_cast<float4*>(dst) = make_float4(ctxv[0], ctxv[1], ctxv[2], ctxv[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(ctxv[4], ctxv[5], ctxv[6], ctxv[7]);
+        if (!live_q) {
+          float* arow = p.align + ((size_t)t * B + b_att) * Tm;
+          for (int tm = lane; tm < Tm; tm += 32) arow[tm] = 0.0f;
+        }
+      }
+      const uint32_t dbuf = sQ + sw128h_off(NP, NB + bl_att, 8 * lane);
+      const uint32_t c0 = pack_h2(ctxv[0], ctxv[1]), c1 = pack_h2(ctxv[2], ctxv[3]);
+      const uint32_t c2 = pack_h2(ctxv[4], ctxv[5]), c3 = pack_h2(ctxv[6], ctxv[7]);
+#pragma unroll
+      for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) st_async_v4(mapa(dbuf, dst), mapa(barCtx, dst), c0, c1, c2, c3);
+    }
+    // masks of the next step: off the critical chain (this step's a_t needs f_in, kept in `fi`)
+    float fi[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) fi[e] = f_in[e];
+    drop_factors(t + 1);
+    // ---------------- a_t = [ho | ctx] Wa for the CTA's 64 attention units ----------------
+    if (tid == 0) mbar_expect_tx(barCtx, NB * DM * 2);
+    mbar_wait(barCtx, t & 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    issue_att();
+    mbar_wait(barM2, t & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      // warp (grp, q): accumulators 4 grp .. 4 grp + 3 of lane quarter q; quarters 0, 1 (ho rows) take columns 0..7,
+      // quarters 2, 3 (ctx rows) columns 8..15
+      const int grp = warp >> 2, q = warp & 3;
+      const uint32_t a0 = tmem_base + ((uint32_t)(32 * q) << 16) + (4 * grp) * NP + (q >= 2 ? 8 : 0);
+      uint32_t r0[8], r1[8], r2[8], r3[8];
+      tmem_ld8(a0, r0);
+      tmem_ld8(a0 + NP, r1);
+      tmem_ld8(a0 + 2 * NP, r2);
+      tmem_ld8(a0 + 3 * NP, r3);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      float* ap = apart + ((grp * 2 + (q >> 1)) * NB) * UPC + 32 * (q & 1) + lane;
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        ap[b * UPC] = (__uint_as_float(r0[b]) + __uint_as_float(r1[b])) + (__uint_as_float(r2[b]) + __uint_as_float(r3[b]));
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (comb) {
+      float a[4];
+      {
+        const float4 p0 = *reinterpret_cast<const float4*>(&apart[(0 * NB + bq) * UPC + 4 * uq]);
+        const float4 p1 = *reinterpret_cast<const float4*>(&apart[(1 * NB + bq) * UPC + 4 * uq]);
+        const float4 p2 = *reinterpret_cast<const float4*>(&apart[(2 * NB + bq) * UPC + 4 * uq]);
+        const float4 p3 = *reinterpret_cast<const float4*>(&apart[(3 * NB + bq) * UPC + 4 * uq]);
+        a[0] = (p0.x + p1.x) + (p2.x + p3.x); a[1] = (p0.y + p1.y) + (p2.y + p3.y);
+        a[2] = (p0.z + p1.z) + (p2.z + p3.z); a[3] = (p0.w + p1.w) + (p2.w + p3.w);
+      }
+      float ad[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        a[e] = tf32_rn(a[e]);
+        ad[e] = tf32_rn(a[e] * fi[e]);  // input dropout of step t+1 on the fed-back attention vector
+      }
+      const int ucol = UPC * (int)rank + 4 * uq;
+      const uint32_t dA = sOp + nb * OP_BYTES + sw128h_off(NP, bq, ucol);
+      const uint32_t a01 = pack_h2(ad[0], ad[1]), a23 = pack_h2(ad[2], ad[3]);
+#pragma unroll
+      for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) st_async_v2(mapa(dA, dst), mapa(barA, dst), a01, a23);
+      if (b0 + bq < B) {
+        const size_t row = (size_t)t * B + b0 + bq;
+        const bool live = t < len_c;
+        *reinterpret_cast<float4*>(p.out + row * AT + ucol) =
+            live ? make_float4(a[0], a[1], a[2], a[3]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        *reinterpret_cast<float4*>(p.S + (row + B) * (AT + H) + ucol) = make_float4(ad[0], ad[1], ad[2], ad[3]);
+      }
+    }
+    // recurrent product of step t+1 once every CTA's a_t slice has landed (hs_t landed before the attention).  After
+    // the last step the wait only drains the all-gather: no st.async may be in flight towards a CTA that exits.
+    if (tid == 0) mbar_expect_tx(barA, NB * AT * 2);
+    mbar_wait(barA, t & 1);
+    if (t + 1 < T) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      issue_rec(nb);
+    }
+  }
+  if (comb && b0 + bq < B) {
+    const size_t o = (size_t)(b0 + bq) * H + UPC * rank + 4 * uq;
+    if (p.cT) *reinterpret_cast<float4*>(p.cT + o) = make_float4(c_state[0], c_state[1], c_state[2], c_state[3]);
+    if (p.hT) *reinterpret_cast<float4*>(p.hT + o) = make_float4(h_state[0], h_state[1], h_state[2], h_state[3]);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  cluster_sync_all();
+}
+
+// =====================================================================================================
+// backward.  Per step t (descending), with dS_t = [dSa_t | dSh_t] = dz_{t+1} [Wl_att ; Wh]^T from the previous iteration:
+//   da_t        = dSa_t (.) m_in(t+1) + dout_t                      (gradient wrt the attention vector; kept for dWa)
+//   d[ho | ctx] = da_t Wa^T                                         (product 2: K = the CTA's 64 attention units)
+//   attention backward of the CTA's 2 utterances: dctx -> d(align) -> ds -> dq (wrt the query ho)
+//   dh_t        = (d ho + dq) (.) m_out(t) + dSh_t (.) m_state(t)   -> gate gradients dz_t
+//   dS_{t-1}    = dz_t [Wl_att ; Wh]^T                              (product 1: K = the CTA's 256 gate columns)
+// Both products are K-split over the cluster; their partial tiles are reduce-scattered through DSMEM to the owners of
+// the rows (attention units / hidden units: all 8 utterances; ctx dims: the owners of the utterances).
+// =====================================================================================================
+struct DBwdParams {
+  int T, B, Tm, scaled;
+  float grad_scale, inv_grad_scale;
+  const int* len;
+  const int* mem_len;
+  const float* gates;    // [T,B,4H] activations
+  const float* craw;     // [T,B,H]
+  const float* c0;       // [B,H] or null
+  const float* Wrec;     // [(AT+H),4H]
+  const float* Wa;       // [(H+DM),AT]
+  const __half* keys;    // [Tm,B,H]
+  const __half* values;  // [Tm,B,DM]
+  const float* g;        // [1] or null
+  const float* align;    // [T,B,Tm]
+  const float* dout;     // [T,B,AT] gradient wrt the emitted attention vectors, or null
+  const float* dcT;      // [B,H] or null
+  const float* dhT;      // [B,H] or null
+  float* dZ;             // [T,B,4H]
+  float* ds;             // [T,B,Tm]
+  float* dhc;            // [T,B,H+DM]: the ctx columns receive dctx_t
+  float* dA;             // [T,B,AT] da_t (tf32-rounded)
+  float* dg;             // [1] or null
+  float* dc0;            // [B,H] or null
+  float* dh0;            // [B,H] or null
+  float* dbias;          // [4H] or null: += column sums of dZ
+  DropCfg d;
+};
+
+constexpr int BW_TILE_BYTES = 4 * 128 * 128;         // one 128-row tile of Wrec^T restricted to the CTA's 256 gate columns
+constexpr int BW_DZ_BYTES = 4 * NP * 128;            // B operand of product 1: 4 K-blocks (gates) x [NP rows x 64 units]
+constexpr int BW_DA_BYTES = NP * 128;                // B operand of product 2: [NP rows x 64 attention units]
+constexpr int REDH_FLOATS = CL * NB * UPC;           // [src][b][u]
+constexpr int REDC_FLOATS = CL * NU * DM;            // [src][utt][dim]; also the dq partial scratch [NU][4][DM]
+constexpr int DQ_FLOATS = CL * NU * UPC;             // [src][utt][u]
+constexpr size_t DBWD_SMEM = (size_t)2 * BW_TILE_BYTES + BW_DZ_BYTES + BW_DA_BYTES + 3 * REDH_FLOATS * 4 + REDC_FLOATS * 4 +
+                             DQ_FLOATS * 4 + NU * DM * 4 + 2 * NU * MAX_TM * 4 + NU * 8 * 4 + 80 + 1024;
+static_assert(NU * 4 * DM <= REDC_FLOATS, "dq partial scratch must fit the ctx reduce buffer");
+
+template <bool SMALL>
+__global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bwd_kernel(const DBwdParams p) {
+  constexpr int MAXB = SMALL ? SMALL_B : 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW = base;                                  // tiles 0, 1 (attention rows) of Wrec^T
+  const uint32_t sDz = sW + 2 * BW_TILE_BYTES;
+  const uint32_t sDa = sDz + BW_DZ_BYTES;
+  const uint32_t sRedA = sDa + BW_DA_BYTES;                  // partial dSa of the CTA's attention units
+  const uint32_t sRedH = sRedA + REDH_FLOATS * 4;            // partial dSh of the CTA's hidden units
+  const uint32_t sRedH2 = sRedH + REDH_FLOATS * 4;           // partial d ho of the CTA's hidden units
+  const uint32_t sRedC = sRedH2 + REDH_FLOATS * 4;           // partial dctx of the CTA's utterances
+  const uint32_t sDq = sRedC + REDC_FLOATS * 4;
+  const uint32_t sCtx = sDq + DQ_FLOATS * 4;                 // [NU][DM] dctx of the CTA's utterances
+  const uint32_t sSc = sCtx + NU * DM * 4;                   // [NU][MAX_TM] alignments (long memories only)
+  const uint32_t sDs = sSc + NU * MAX_TM * 4;                // [NU][MAX_TM] d(align) / ds (long memories only)
+  const uint32_t sRed = sDs + NU * MAX_TM * 4;               // [NU][8]
+  const uint32_t sBar = sRed + NU * 8 * 4;
+  const uint32_t sTmem = sBar + 64;
+  const uint32_t barMma = sBar, barMma2 = sBar + 8, barDz = sBar + 16, barRedA = sBar + 24, barRedH = sBar + 32,
+                 barRedH2 = sBar + 40, barRedC = sBar + 48, barDq = sBar + 56;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  float* redA = reinterpret_cast<float*>(gen + (sRedA - base));
+  float* redH = reinterpret_cast<float*>(gen + (sRedH - base));
+  float* redH2 = reinterpret_cast<float*>(gen + (sRedH2 - base));
+  float* redC = reinterpret_cast<float*>(gen + (sRedC - base));
+  float* dqb = reinterpret_cast<float*>(gen + (sDq - base));
+  float* ctx_all = reinterpret_cast<float*>(gen + (sCtx - base));
+  float* part_all = redC;
+  float* red_all = reinterpret_cast<float*>(gen + (sRed - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int b0 = cluster_id_x() * NB;
+  const int T = p.T, B = p.B, Tm = p.Tm;
+
+  if (tid == 0) {
+    mbar_init(barMma, THREADS / 32);   // one commit per issuing warp
+    mbar_init(barMma2, THREADS / 32);
+    mbar_init(barDz, THREADS);
+    mbar_init(barRedA, 1);
+    mbar_init(barRedH, 1);
+    mbar_init(barRedH2, 1);
+    mbar_init(barRedC, 1);
+    mbar_init(barDq, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // tensor memory (all 512 columns): [0, 128) accumulators of both products: 128-row tile mt, K half hj at column
+  // 16 (2 mt + hj); [128, 256) the four 128 x 64 tiles of Wa^T (32 columns each); [256, 512) tiles 2, 3 (h rows) of Wrec^T
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // A[n][k = g*64 + u] = Wrec[n][g*H + 64*rank + u]; rows n < 256 (attention) -> shared memory (tile n >> 7)
+  for (int seg = warp; seg < 256 * 8; seg += THREADS / 32) {
+    const int n = seg >> 3, g = (seg >> 1) & 3, u = 32 * (seg & 1) + lane;
+    const float w = p.Wrec[(size_t)n * 4 * H + g * H + UPC * rank + u];
+    *reinterpret_cast<__half*>(gen + (sW - base) + (n >> 7) * BW_TILE_BYTES + sw128h_off(128, n & 127, g * 64 + u)) =
+        __float2half_rn(w);
+  }
+  for (int i = tid; i < (BW_DZ_BYTES + BW_DA_BYTES) / 4; i += THREADS) reinterpret_cast<uint32_t*>(gen + (sDz - base))[i] = 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
+  const uint32_t tWaT = tmem_base + 128, tA = tmem_base + 256;
+  {
+    // rows n = 256 + 128*tt + 32*q + lane (h rows) -> tensor memory tile tt; column c holds k = 2c, 2c+1 (adjacent units)
+    const int q = warp & 3, tt = warp >> 2;
+    const float* row = p.Wrec + (size_t)(256 + 128 * tt + 32 * q + lane) * 4 * H + UPC * rank;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t r[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = 2 * (c0 + c), g = k >> 6, u = k & 63;
+        const float2 w = *reinterpret_cast<const float2*>(row + g * H + u);
+        r[c] = pack_h2(w.x, w.y);
+      }
+      tmem_st32(tA + 128 * tt + c0 + ((uint32_t)(32 * q) << 16), r);
+    }
+    // Wa^T: row n = 128*wt + 32*q + lane of [ho dims | ctx dims], K = the CTA's 64 attention units
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+      const int wt = 2 * tt + i;
+      const float* wrow = p.Wa + (size_t)(128 * wt + 32 * q + lane) * AT + UPC * rank;
+      uint32_t r[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float2 w = *reinterpret_cast<const float2*>(wrow + 2 * c);
+        r[c] = pack_h2(w.x, w.y);
+      }
+      tmem_st32(tWaT + 32 * wt + ((uint32_t)(32 * q) << 16), r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  cluster_sync_all();
+
+  const uint64_t dWt = make_desc_k128(sW), dDz = make_desc_k128(sDz), dDa = make_desc_k128(sDa);
+  // gate-gradient role: thread = (local unit ul - hidden and attention -, utterances 2*(warp >> 1) + j)
+  constexpr int PB = 2;
+  const int ul = 32 * (warp & 1) + lane;
+  const int unit = UPC * rank + ul;
+  float dc[PB], dh_carry[PB];
+  int len_t[PB];
+#pragma unroll
+  for (int j = 0; j < PB; ++j) {
+    const int b = b0 + (warp >> 1) * PB + j;
+    len_t[j] = (b < B) ? p.len[b] : 0;
+    dc[j] = (b < B && p.dcT) ? p.dcT[(size_t)b * H + unit] : 0.0f;
+    dh_carry[j] = (b < B && p.dhT) ? p.dhT[(size_t)b * H + unit] : 0.0f;
+  }
+  const uint32_t seed = p.d.rng ? p.d.rng[0] : 0u, rstep = p.d.rng ? p.d.rng[1] : 0u;
+  float gi[PB], gj[PB], gf[PB], go[PB], crw[PB], cpv[PB], dov[PB];
+#pragma unroll
+  for (int j = 0; j < PB; ++j) gi[j] = gj[j] = gf[j] = go[j] = crw[j] = cpv[j] = dov[j] = 0.0f;
+  auto load_step = [&](int t) {
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int b = b0 + (warp >> 1) * PB + j;
+      if (t >= 0 && t < len_t[j]) {
+        const float* g = p.gates + ((size_t)t * B + b) * 4 * H + unit;
+        gi[j] = g[0]; gj[j] = g[H]; gf[j] = g[2 * H]; go[j] = g[3 * H];
+        const size_t o = ((size_t)t * B + b) * H + unit;
+        crw[j] = p.craw[o];
+        cpv[j] = t > 0 ? p.craw[o - (size_t)B * H] : (p.c0 ? p.c0[(size_t)b * H + unit] : 0.0f);
+        dov[j] = p.dout ? p.dout[((size_t)t * B + b) * AT + unit] : 0.0f;  // wrt the emitted attention unit `unit`
+      }
+    }
+  };
+  // attention role
+  const int jl = warp >> 2, w4 = warp & 3, gt = tid & 127;
+  const int bl_att = NU * (int)rank + jl;
+  const int b_att = b0 + bl_att;
+  const int len_q = (b_att < B) ? p.len[b_att] : 0;
+  const int L = (b_att < B) ? min(p.mem_len[b_att], Tm) : 0;
+  const float gs = p.scaled ? p.g[0] : 1.0f;
+  float* dctx_s = ctx_all + jl * DM;
+  float* a_s = reinterpret_cast<float*>(gen + (sSc - base)) + jl * MAX_TM;
+  float* ds_s = reinterpret_cast<float*>(gen + (sDs - base)) + jl * MAX_TM;
+  float* part = part_all + jl * 4 * DM;
+  float* red = red_all + jl * 8;
+  const uint32_t att_bar_id = 2 + jl;
+  const AttRole role = {p.keys, p.values, L, B, b_att, Tm, w4, gt, lane, gs, att_bar_id, nullptr, part, red};
+  // product-issue / reduce-scatter roles
+  const int q = warp & 3;
+  const int mt_i = warp >> 1, hj_i = warp & 1;
+  const uint32_t acc_i = tmem_base + (2 * mt_i + hj_i) * NP;
+
+  float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // bias gradient of this thread's unit
+  load_step(T - 1);
+  for (int it = 0; it < T; ++it) {
+    const int t = T - 1 - it;
+    const bool live_q = t < len_q;
+    // first values and this step's alignments: requested before the partial sums of the previous iteration arrive
+    uint4 ra[4], rb[4];
+    float al[MAXB];
+    const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) al[i] = 0.0f;
+    if (live_q) {
+      att_prefetch(role, p.values, ra, rb);
+      if constexpr (SMALL) {
+#pragma unroll
+        for (int i = 0; i < MAXB; ++i) {
+          const int tm = w4 + 32 * i + 4 * jrow;
+          if (tm < L) al[i] = p.align[((size_t)t * B + b_att) * Tm + tm];
+        }
+      } else {
+        for (int tm = gt; tm < Tm; tm += 128) a_s[tm] = p.align[((size_t)t * B + b_att) * Tm + tm];
+      }
+    }
+    // masks of this step for the thread's unit (attention unit: input mask of step t+1; hidden unit: state / output)
+    float f_in[PB], f_st[PB], f_o[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const uint32_t idx = (uint32_t)(b0 + (warp >> 1) * PB + j) * (uint32_t)H + (uint32_t)unit;  // H == AT
+      f_in[j] = dfac(seed, rstep, p.d.stream, p.d.thr_in, p.d.inv_in, (uint32_t)(t + 1), idx);
+      f_st[j] = dfac(seed, rstep, p.d.stream + 1u, p.d.thr_state, p.d.inv_state, (uint32_t)t, idx);
+      f_o[j] = dfac(seed, rstep, p.d.stream + 2u, p.d.thr_out, p.d.inv_out, (uint32_t)t, idx);
+    }
+    // ---- (A) dS_t pushed during the previous iteration -> da_t, dSh_t ------------------------------------------
+    float dh_in[PB], sa[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      dh_in[j] = dh_carry[j];
+      sa[j] = 0.0f;
+    }
+    if (it > 0) {
+      if (tid == 0) {
+        mbar_expect_tx(barRedA, REDH_FLOATS * 4);
+        mbar_expect_tx(barRedH, REDH_FLOATS * 4);
+      }
+      mbar_wait(barRedA, (it - 1) & 1);
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int bl = (warp >> 1) * PB + j;
+#pragma unroll
+        for (int src = 0; src < CL; ++src) sa[j] += redA[(src * NB + bl) * UPC + ul];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int bl = (warp >> 1) * PB + j;
+      const float da = (t < len_t[j]) ? tf32_rn(sa[j] * f_in[j] + dov[j]) : 0.0f;
+      if (b0 + bl < B) p.dA[((size_t)t * B + b0 + bl) * AT + unit] = da;
+      *reinterpret_cast<__half*>(gen + (sDa - base) + sw128h_off(NP, bl, ul)) = __float2half_rn(da * p.grad_scale);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- (B) product 2: d[ho | ctx] partial from the CTA's 64 attention units ------------------------------------
+    if (lane == 0) {
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int s4 = 2 * hj_i + kk;  // K step of 16 attention units
+        umma_ts(acc_i, tWaT + 32 * mt_i + s4 * 8, desc_at(dDa, s4 * 32), IDESC, kk ? 1u : 0u);
+      }
+      umma_commit(barMma2);
+    }
+    __syncwarp();
+    if (it > 0) {
+      mbar_wait(barRedH, (it - 1) & 1);
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int bl = (warp >> 1) * PB + j;
+#pragma unroll
+        for (int src = 0; src < CL; ++src) dh_in[j] += redH[(src * NB + bl) * UPC + ul];
+      }
+    }
+    // ---- (C) partial d[ho | ctx] -> owners ------------------------------------------------------------------------
+    mbar_wait(barMma2, it & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const int mt = 2 * (warp >> 2) + mi;
+      uint32_t r[8], r1[8];
+      tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (2 * mt) * NP, r);
+      tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (2 * mt + 1) * NP, r1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < NB; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(r1[c]));
+      if (mt < 2) {  // ho dims 128*mt + 32*q + lane -> owner CTA 2*mt + (q >> 1), local unit 32*(q & 1) + lane
+        const uint32_t dst = (uint32_t)(2 * mt + (q >> 1));
+        const uint32_t a0 = mapa(sRedH2 + (uint32_t)((rank * NB) * UPC + 32 * (q & 1) + lane) * 4, dst);
+        const uint32_t bar = mapa(barRedH2, dst);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) st_async_f(a0 + c * UPC * 4, bar, __uint_as_float(r[c]) * p.inv_grad_scale);
+      } else {       // ctx dims 128*(mt-2) + 32*q + lane; column c = utterance -> owner CTA c / NU
+        const int dim = 128 * (mt - 2) + 32 * q + lane;
+#pragma unroll
+        for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) {
+          const uint32_t a0 = mapa(sRedC + (uint32_t)((rank * NU) * DM + dim) * 4, dst);
+          const uint32_t bar = mapa(barRedC, dst);
+#pragma unroll
+          for (int u2 = 0; u2 < NU; ++u2) st_async_f(a0 + u2 * DM * 4, bar, __uint_as_float(r[NU * dst + u2]) * p.inv_grad_scale);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    // ---- (D) dctx of the CTA's utterances -------------------------------------------------------------------------
+    if (tid == 0) mbar_expect_tx(barRedC, REDC_FLOATS * 4);
+    mbar_wait(barRedC, it & 1);
+    if (live_q) {
+#pragma unroll
+      for (int i = 0; i < DM / 128; ++i) {
+        const int d = gt + 128 * i;
+        float v = 0.0f;
+#pragma unroll
+        for (int src = 0; src < CL; ++src) v += redC[(src * NU + jl) * DM + d];
+        dctx_s[d] = v;
+        p.dhc[((size_t)t * B + b_att) * (H + DM) + H + d] = v;
+      }
+    }
+    // redC is free from here on (a peer pushes its next partials only after it has received this CTA's dS partials of
+    // this iteration): it doubles as the dq partial scratch
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- (E) attention backward of the CTA's utterances, dq all-to-all --------------------------------------------
+    float dqv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dqv[e] = 0.0f;
+    float ds_keep[MAXB];
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) ds_keep[i] = 0.0f;
+    if (live_q)
+      att_bwd_core<SMALL>(role, dctx_s, ra, rb, al, ds_keep, a_s, ds_s, p.ds + ((size_t)t * B + b_att) * Tm, p.scaled != 0, p.dg, dqv);
+    if (w4 == 0) {
+      // dq dims 8*lane .. +7 belong to the CTA owning units (8*lane)/64
+      const uint32_t dst = (uint32_t)(lane >> 3);
+      const uint32_t a0 = mapa(sDq + (uint32_t)(((rank * NU + jl) * UPC + ((8 * lane) & (UPC - 1))) * 4), dst);
+      const uint32_t bar = mapa(barDq, dst);
+      st_async_v4f(a0, bar, dqv[0], dqv[1], dqv[2], dqv[3]);
+      st_async_v4f(a0 + 16, bar, dqv[4], dqv[5], dqv[6], dqv[7]);
+    }
+    // ---- (F) d ho + dq of this CTA's units -> gate gradients ------------------------------------------------------
+    if (tid == 0) {
+      mbar_expect_tx(barDq, DQ_FLOATS * 4);
+      mbar_expect_tx(barRedH2, REDH_FLOATS * 4);
+    }
+    mbar_wait(barRedH2, it & 1);
+    mbar_wait(barDq, it & 1);
+    float dz[4][PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int bl = (warp >> 1) * PB + j;
+      if (t < len_t[j]) {
+        float dho = dqb[bl * UPC + ul];
+#pragma unroll
+        for (int src = 0; src < CL; ++src) dho += redH2[(src * NB + bl) * UPC + ul];
+        const float dh = dh_in[j] * f_st[j] + dho * f_o[j];  // state-dropped h recurs, output-dropped h is the query / operand
+        const float c = fminf(fmaxf(crw[j], -1.0f), 1.0f);
+        const float tc = tanhf_acc(c);
+        const float cp = t > 0 ? fminf(fmaxf(cpv[j], -1.0f), 1.0f) : cpv[j];
+        const float dct = dc[j] + dh * go[j] * (1.0f - tc * tc);
+        const float dcr = (crw[j] >= -1.0f && crw[j] <= 1.0f) ? dct : 0.0f;
+        dz[0][j] = dcr * gj[j] * gi[j] * (1.0f - gi[j]);
+        dz[1][j] = dcr * gi[j] * (1.0f - gj[j] * gj[j]);
+        dz[2][j] = dcr * cp * gf[j] * (1.0f - gf[j]);
+        dz[3][j] = dh * tc * go[j] * (1.0f - go[j]);
+        dc[j] = dcr * gf[j];
+        dh_carry[j] = 0.0f;
+      } else {
+        dz[0][j] = dz[1][j] = dz[2][j] = dz[3][j] = 0.0f;
+        dh_carry[j] = dh_in[j];
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<__half*>(gen + (sDz - base) + sw128h_off(NP, bl, g * 64 + ul)) = __float2half_rn(dz[g][j] * p.grad_scale);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(barDz);
+    {
+      // product 1: partial [dSa | dSh](512) x NB from this CTA's 256 gate columns; warp (mt, hj) issues the K half hj
+      // (gates 2 hj, 2 hj + 1) of the 128-row tile mt into its own accumulator
+      mbar_wait(barDz, it & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int kb = 2 * hj_i + kk;
+            const uint64_t db = desc_at(dDz, kb * (NP * 128) + k4 * 32);
+            if (mt_i < 2)
+              umma_ss(acc_i, desc_at(dWt, mt_i * BW_TILE_BYTES + kb * (128 * 128) + k4 * 32), db, IDESC, (kk | k4) ? 1u : 0u);
+            else
+              umma_ts(acc_i, tA + (mt_i - 2) * 128 + (kb * 4 + k4) * 8, db, IDESC, (kk | k4) ? 1u : 0u);
+          }
+        umma_commit(barMma);
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int b = b0 + (warp >> 1) * PB + j;
+      if (b < B) {
+        float* o = p.dZ + ((size_t)t * B + b) * 4 * H + unit;
+        o[0] = tf32_rn(dz[0][j]); o[H] = tf32_rn(dz[1][j]); o[2 * H] = tf32_rn(dz[2][j]); o[3 * H] = tf32_rn(dz[3][j]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) bsum[g] += tf32_rn(dz[g][j]);
+      }
+    }
+    load_step(t - 1);
+    if constexpr (SMALL) {
+      if (live_q) att_bwd_small_tail(role, p.ds + ((size_t)t * B + b_att) * Tm, al, ds_keep, p.scaled != 0, p.dg);
+    }
+    // ---- (G) partial dS_{t-1} -> owners of the attention / hidden units -------------------------------------------
+    mbar_wait(barMma, it & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (it + 1 < T) {
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int mt = 2 * (warp >> 2) + mi;  // tiles 0, 1: attention units; 2, 3: hidden units
+        uint32_t r[8], r1[8];
+        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (2 * mt) * NP, r);
+        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (2 * mt + 1) * NP, r1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < NB; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(r1[c]));
+        const uint32_t dst = (uint32_t)(2 * (mt & 1) + (q >> 1));
+        const uint32_t buf = mt < 2 ? sRedA : sRedH;
+        const uint32_t a0 = mapa(buf + (uint32_t)((rank * NB) * UPC + 32 * (q & 1) + lane) * 4, dst);
+        const uint32_t bar = mapa(mt < 2 ? barRedA : barRedH, dst);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) st_async_f(a0 + c * UPC * 4, bar, __uint_as_float(r[c]) * p.inv_grad_scale);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+#pragma unroll
+  for (int j = 0; j < PB; ++j) {
+    const int b = b0 + (warp >> 1) * PB + j;
+    if (b < B) {
+      // dh_0 = dz_0 Wh^T is added by the host; here only what fully masked utterances carry through
+      if (p.dh0) p.dh0[(size_t)b * H + unit] = dh_carry[j];
+      if (p.dc0) p.dc0[(size_t)b * H + unit] = dc[j];
+    }
+  }
+  if (p.dbias) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) atomicAdd(p.dbias + g * H + unit, bsum[g]);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  cluster_sync_all();
+}
+
+}  // namespace ap4
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side: called by attn_persist_fwd / attn_persist_bwd (attn_persist.cu) when the layer's DropoutWrapper is on
+// ---------------------------------------------------------------------------------------------------------------------
+static ap4::DropCfg drop_cfg(const AvsrRnnSeq* r) {
+  ap4::DropCfg d;
+  d.rng = r->rng;
+  d.stream = r->drop_stream;
+  d.thr_in = r->rng ? r->thr_in : 0u; d.thr_state = r->rng ? r->thr_state : 0u; d.thr_out = r->rng ? r->thr_out : 0u;
+  d.inv_in = inv_keep_of(d.thr_in); d.inv_state = inv_keep_of(d.thr_state); d.inv_out = inv_keep_of(d.thr_out);
+  return d;
+}
+
+int attn_persist4d_launch_fwd(cudaStream_t st, const AvsrRnnSeq* r, const void* keys_h, const void* values_h) {
+  const AvsrAttnMech& m = r->mech[0];
+  ap4::DParams p;
+  p.T = r->T; p.B = r->B; p.Tm = m.Tm; p.scaled = m.kind == AVSR_ATTN_SCALED_LUONG;
+  p.len = r->len; p.mem_len = m.mem_len; p.gates = r->gates; p.Wrec = r->Wrec; p.Wa = m.Wl;
+  p.keys = reinterpret_cast<const __half*>(keys_h); p.values = reinterpret_cast<const __half*>(values_h);
+  p.g = m.g; p.c0 = r->c0; p.S = r->S; p.craw = r->craw; p.out = r->out; p.hc = m.hc; p.align = m.align;
+  p.cT = r->cT; p.hT = r->hT;
+  p.d = drop_cfg(r);
+  return ap4::launch_cluster(st, ap4::attn_lstm_persist4d_fwd_kernel, r->B, ap4::DFWD_SMEM, p, AVSR_K_ATTN_FWD);
+}
+
+int attn_persist4d_launch_bwd(cudaStream_t st, const AvsrRnnSeq* r, const void* keys_h, const void* values_h) {
+  const AvsrAttnMech& m = r->mech[0];
+  ap4::DBwdParams p;
+  p.T = r->T; p.B = r->B; p.Tm = m.Tm; p.scaled = m.kind == AVSR_ATTN_SCALED_LUONG;
+  p.grad_scale = r->grad_scale > 0.0f ? r->grad_scale : 1.0f;
+  p.inv_grad_scale = 1.0f / p.grad_scale;
+  p.len = r->len; p.mem_len = m.mem_len; p.gates = r->gates; p.craw = r->craw; p.c0 = r->c0;
+  p.Wrec = r->Wrec; p.Wa = m.Wl;
+  p.keys = reinterpret_cast<const __half*>(keys_h); p.values = reinterpret_cast<const __half*>(values_h);
+  p.g = m.g; p.align = m.align; p.dout = r->dout; p.dcT = r->dcT; p.dhT = r->dhT;
+  p.dZ = r->dZ; p.ds = m.ds; p.dhc = m.dhc; p.dA = r->dA; p.dg = m.dg; p.dc0 = r->dc0; p.dh0 = r->dh0; p.dbias = r->dbias;
+  p.d = drop_cfg(r);
+  return m.Tm <= ap4::SMALL_TM
+             ? ap4::launch_cluster(st, ap4::attn_lstm_persist4d_bwd_kernel<true>, r->B, ap4::DBWD_SMEM, p, AVSR_K_ATTN_BWD)
+             : ap4::launch_cluster(st, ap4::attn_lstm_persist4d_bwd_kernel<false>, r->B, ap4::DBWD_SMEM, p, AVSR_K_ATTN_BWD);
+}
+
+}  // namespace avsr

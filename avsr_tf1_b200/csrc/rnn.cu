@@ -42,11 +42,9 @@ static Drop drop_of(const AvsrRnnSeq* r) {
   return d;
 }
 static bool has_dropout(const AvsrRnnSeq* r) { return r->rng && (r->thr_in | r->thr_state | r->thr_out); }
-// The attention-LSTM persistent kernels fold the attention layer into the recurrent matrix, which a mask between the
-// two forbids; the plain-LSTM cluster-of-4 kernels apply the state / output masks themselves (H = 256).
-static bool stepwise_only(const AvsrRnnSeq* r) {
-  return r->stepwise || r->t_begin || r->t_end || (has_dropout(r) && r->n_mech > 0);
-}
+// Step ranges (scheduled sampling) advance one step per call; everything else tries the persistent kernels first (under
+// a DropoutWrapper: lstm_persist4.cu DROP variants, attn_persist4d.cu two-product kernels).
+static bool stepwise_only(const AvsrRnnSeq* r) { return r->stepwise || r->t_begin || r->t_end; }
 
 __global__ void lstm_point_fwd_kernel(int t, int B, int H, float* __restrict__ gates_t, const float* __restrict__ rec,
                                       const int* __restrict__ len, const float* __restrict__ c_prev,
@@ -178,17 +176,6 @@ __global__ void emit_attention_kernel(int t, int B, int At, int SW, const int* _
   out_t[idx] = t < len[b] ? S_next[(size_t)b * SW + a] : 0.0f;
 }
 
-// all steps at once: rows = T*Bt, step of a row = row / Bt
-__global__ void emit_attention_all_kernel(int T, int Bt, int At, int SW, const int* __restrict__ len,
-                                          const float* __restrict__ S1, float* __restrict__ out) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)T * Bt * At) return;
-  long long row = idx / At;
-  int a = (int)(idx - row * At);
-  int t = (int)(row / Bt), b = (int)(row - (long long)t * Bt);
-  out[idx] = t < len[b] ? S1[(size_t)row * SW + a] : 0.0f;
-}
-
 __global__ void copy2d_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows,
                               int cols) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,7 +204,7 @@ int attn_bahdanau_post(cudaStream_t st, int T, int B, int Tm, int A, const int* 
 // --------------------------------------------------------------------------- //
 size_t attn_persist_work_floats(int B, int H, int Dm, int Tm);                 // attn_persist.cu
 int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch);    // attn_persist.cu
-int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch);    // attn_persist.cu
+int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch, bool unfused);  // attn_persist.cu
 
 struct WorkLayout {
   size_t rec, cbuf, dS, dcbuf, dHC, dq, persist, total;
@@ -277,13 +264,8 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   WorkLayout wl = work_layout(B, H, At, maxHD, maxA, maxTm);
   if (r->n_mech == 1 && rnd && T > 1 && !stepwise && !getenv("AVSR_NO_ATTN_PERSIST")) {  // T == 1: step-wise decoding (carried attention)
     // persistent cluster kernel for the Luong-family attention layer (AV-Align top layer, LAS decoder)
-    const int rc = attn_persist_fwd(st, r, r->work + wl.persist);
-    if (rc >= 0) {
-      if (rc == 0 && r->output_attention)  // layer output = attention vectors, zero past the length
-        AVSR_LAUNCH(emit_attention_all_kernel, cdiv((long long)T * B * At, 256), 256, 0, st, T, B, At, SW, r->len,
-                    r->S + (size_t)B * SW, r->out);
-      return rc;
-    }
+    const int rc = attn_persist_fwd(st, r, r->work + wl.persist);  // also writes `out` when it is the attention
+    if (rc >= 0) return rc;
   }
   float* rec = r->work + wl.rec;
   float* cbuf[2] = {r->work + wl.cbuf, r->work + wl.cbuf + (size_t)B * H};
@@ -362,9 +344,12 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
   const bool oa = r->output_attention && r->n_mech > 0;
   const int rnd = tensor_cores_enabled();
   WorkLayout wl = work_layout(B, H, At, maxHD, maxA, maxTm);
-  if (r->n_mech == 1 && rnd && T > 1 && !stepwise && !getenv("AVSR_NO_ATTN_PERSIST")) {
+  if (r->n_mech == 1 && rnd && T > 1 && !getenv("AVSR_NO_ATTN_PERSIST")) {
+    // After a step-wise forward (r->stepwise: scheduled sampling advanced the recurrence in ranges) only the two-product
+    // kernels apply: they need nothing but the saved activations, while the folded ones need the scratch their own
+    // forward left (fused matrix).
     AVSR_REQUIRE(r->mech[0].ds && r->mech[0].dhc, "rnn bwd: mechanism scratch ds / dhc missing");
-    const int rc = attn_persist_bwd(st, r, r->work + wl.persist);  // needs the scratch attn_persist_fwd left
+    const int rc = attn_persist_bwd(st, r, r->work + wl.persist, r->stepwise != 0);
     if (rc >= 0) return rc;
   }
   float* dS[2] = {r->work + wl.dS, r->work + wl.dS + (size_t)B * SW};

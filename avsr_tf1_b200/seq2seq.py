@@ -234,7 +234,8 @@ class Seq2SeqModel(object):
         if hp.optimiser not in ops.OPTIMISERS:  # Adam, Nadam, AdamW, Momentum (seq2seq.py:195-219)
             raise Exception('Unsupported optimiser, try Adam')
         self._l2_names = [n for n in self.store.names() if 'lstm_' in n and 'bias' not in n]  # seq2seq.py:283-290
-        self._loss_dev = torch.zeros(5, dtype=torch.float32, device=self.store.flat.device)  # xent, L2, |g|^2, AU, CNN L2
+        # xent sum, L2, |g|^2, AU, CNN L2, 1 / (global token count + 1e-12) (the denominator the step actually used)
+        self._loss_dev = torch.zeros(6, dtype=torch.float32, device=self.store.flat.device)
 
     @property
     def global_step(self):
@@ -450,6 +451,13 @@ class Seq2SeqModel(object):
         b = self._batch if self._batch is not None else self._prep()
         self.store.grad.zero_()
         self._loss_dev.zero_()
+        if self._ctx.world_size > 1:
+            # exact large-batch loss denominator (seq2seq.sequence_loss, seq2seq.py:165-171): the token count of the
+            # GLOBAL batch, summed over ranks on the device inside the step (no host round trip, graph-capturable)
+            tok = b['labels_len'].sum(dtype=torch.float32).reshape(1)
+            self._ctx.allreduce(tok)
+            torch.reciprocal(tok + 1e-12, out=self._scal_dev[0:1])
+        self._loss_dev[5:6].copy_(self._scal_dev[0:1])
         enc = self._encode(b)
         mems, states = self._decoder_inputs(b, enc)
         self._decoder.forward_train(mems, states, b['dec_in_ids'], b['labels'], b['labels_len'], b['T_dec'],
@@ -543,9 +551,10 @@ class Seq2SeqModel(object):
     def _set_step_scalars(self):
         """Host scalars of this step -> device (outside any captured graph)."""
         ctx = self._ctx
-        # exact large-batch loss denominator under data parallelism
-        n_tok = parallel.global_token_count(self._meta['n_tokens'], device='cuda') if ctx.world_size > 1 \
-            else self._meta['n_tokens']
+        # Loss denominator: one rank knows it on the host; under data parallelism the device sums the token counts of
+        # all ranks inside the step (forward_backward) and overwrites this local estimate, which then only sizes the
+        # power-of-two operand scale of the backward kernels.
+        n_tok = self._meta['n_tokens'] * ctx.world_size
         self._inv_denom = 1.0 / (n_tok + 1e-12)  # seq2seq.sequence_loss
         self._ctx.grad_scale = float(2 ** int(math.floor(math.log2(max(n_tok, 1.0)))))
         lr = self._lr_now()
@@ -601,6 +610,7 @@ class Seq2SeqModel(object):
         """Device -> host read of the step's results (what session.run returns, avsr.py:265-271)."""
         hp = self._hparams
         vals = self._loss_dev.cpu().numpy()
+        self._inv_denom = float(vals[5])  # the denominator the device used (global token count under DP)
         xent = float(vals[0]) * self._inv_denom  # sum(xent*w) / (sum(w) + 1e-12)
         reg = 0.5 * (hp.recurrent_l2_regularisation or 0.0) * float(vals[1]) + 0.5 * 1e-3 * float(vals[4])
         self.au_loss = float(vals[3]) * self._au_scale / float(hp.kwargs.get('au_loss_weight', 10.0)) \
@@ -614,7 +624,7 @@ class Seq2SeqModel(object):
         `result()` waits for just that copy.  Lets the host launch step k+1 before it reads the loss of step k, so the
         GPU never waits for the host between steps (session.run pipelines the same way behind its fetches)."""
         if not hasattr(self, '_pinned_scalars'):
-            self._pinned_scalars = [torch.empty(5, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._pinned_scalars = [torch.empty(6, dtype=torch.float32).pin_memory() for _ in range(4)]
             self._pinned_next = 0
         buf = self._pinned_scalars[self._pinned_next % len(self._pinned_scalars)]
         self._pinned_next += 1

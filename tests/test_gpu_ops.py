@@ -328,15 +328,55 @@ def test_attention_rnn_cluster8(kinds, B, T, Dx, H, Tms, Dms, slice_width, monke
         ops.set_tensor_cores(old)
 
 
-def _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, tensor_cores):
+class _Drop:
+    """What ops.RnnSeq reads of a layers.DropState."""
+
+    def __init__(self, ops, rng_words, stream, keep):
+        self.rng = torch.tensor(rng_words, dtype=torch.int32, device='cuda')
+        self.stream = stream
+        self.thr_in, self.thr_state, self.thr_out = (ops.keep_threshold(p) for p in keep)
+
+
+@pytest.mark.parametrize('kinds,B,T,Dx,H,Tms,Dms,keep', [
+    (('scaled_luong',), 20, 9, 128, 256, (75,), (256,), (0.9, 0.9, 0.9)),     # 3 clusters, the last one half full
+    (('luong',), 36, 14, 256, 256, (300,), (256,), (0.8, 0.9, 0.7)),          # long memory: shared-memory softmax path
+    (('scaled_luong',), 8, 70, 80, 256, (96,), (256,), (0.9, 0.85, 0.95)),    # many steps, memory = SMALL_TM
+    (('scaled_luong',), 250, 6, 128, 256, (75,), (256,), (0.9, 0.9, 0.9)),    # 32 clusters
+    (('luong',), 9, 7, 32, 256, (40,), (256,), (1.0, 0.8, 1.0)),              # only the state mask
+    (('scaled_luong',), 9, 7, 32, 256, (40,), (256,), (0.8, 1.0, 1.0)),       # only the input mask
+])
+def test_attention_rnn_dropout_persistent(kinds, B, T, Dx, H, Tms, Dms, keep):
+    """AttentionWrapper(DropoutWrapper(LSTMCell)) - the reference's default training graph (cells.py:46-54) - on the
+    two-product persistent kernels of attn_persist4d.cu, mask for mask against the oracle; the kernel timers prove
+    that the persistent kernels (not the per-step path) ran."""
+    ops = ops_mod()
+    old = ops.set_tensor_cores(True)
+    try:
+        ops.kernel_timing(True)
+        _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, True, keep=keep)
+        times = ops.kernel_times()
+        assert times['attn_lstm_fwd'][1] == 1 and times['attn_lstm_bwd'][1] == 1, times
+    finally:
+        ops.kernel_timing(False)
+        ops.set_tensor_cores(old)
+
+
+def _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, tensor_cores, keep=None):
     ops = ops_mod()
     x, lens, W, b, specs, c0, h0, rng = _attn_case(kinds, B, T, Dx, H, Tms, Dms, sum(Tms) + B)
     f64 = lambda a: a.astype(np.float64)
-    r = O.attn_rnn_fwd(f64(x), lens, f64(W), f64(b), [_spec64(s) for s in specs], init_cell=(f64(c0), f64(h0)))
+    drop = odrop = None
+    if keep is not None:
+        words, stream = (4321, 17), 12
+        drop, odrop = _Drop(ops, words, stream, keep), O.DropSpec(words, stream, keep)
+    r = O.attn_rnn_fwd(f64(x), lens, f64(W), f64(b), [_spec64(s) for s in specs], init_cell=(f64(c0), f64(h0)),
+                       drop=odrop)
     A = H
     At = A * len(kinds)
     tc = tensor_cores
     xt = opnd(dev(x.transpose(1, 0, 2)), tc)
+    if drop is not None and drop.thr_in:  # the x part of the cell input is dropped before the x-projection
+        xt = ops.dropout(dev(x.transpose(1, 0, 2)).contiguous(), drop.rng, drop.stream + 3, drop.thr_in, round_out=tc)
     Wd, bd, ld = opnd(dev(W), tc), dev(b), dev(lens, torch.int32)
     gates = torch.empty(T, B, 4 * H, device='cuda')
     ops.gemm(xt.view(T * B, Dx), Wd[:Dx], gates.view(T * B, 4 * H), bias=bd)
@@ -357,9 +397,9 @@ def _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, tensor_cores):
                              g=g if s.kind == 'scaled_luong' else None, bias=None if s.b is None else dev(s.b))
         bufs.append(mb)
         extra.append((v, g))
-    rnn = ops.RnnSeq(T, B, H, ld, gates, Wd[Dx:], bufs, specs[-1].output_attention, c0=dev(c0), h0=dev(h0))
+    rnn = ops.RnnSeq(T, B, H, ld, gates, Wd[Dx:], bufs, specs[-1].output_attention, c0=dev(c0), h0=dev(h0), drop=drop)
     out = rnn.forward()
-    rt = tol(tensor_cores)
+    rt = tol(tensor_cores) * (1.0 if keep is None else 1.0 / min(keep))  # inverted dropout scales operand rounding errors
     close(out.transpose(0, 1), r['outputs'], rt, 'outputs')
     close(rnn.cT, r['final'][0], rt, 'final c')
     close(rnn.hT, r['final'][1], rt, 'final h')
@@ -390,6 +430,8 @@ def _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, tensor_cores):
     ops.gemm(xt.view(T * B, Dx), dZ2, gW[:Dx], ta=True, beta=1.0)
     dx = torch.empty(T, B, Dx, device='cuda')
     ops.gemm(dZ2, Wd[:Dx], dx.view(T * B, Dx), tb=True)
+    if drop is not None and drop.thr_in:
+        ops.dropout(dx, drop.rng, drop.stream + 3, drop.thr_in, out=dx)
     rg = 1e-1 if tensor_cores else 1e-4
     close(dx.transpose(0, 1), rb['dx'], rg, 'dx')
     close(gW, rb['dW'], rg, 'dW')
