@@ -27,6 +27,14 @@ class AvsrAttnMech(C.Structure):
     ]
 
 
+class AvsrSampling(C.Structure):
+    _fields_ = [
+        ('Wd', C.c_void_p), ('bd', C.c_void_p), ('embedding', C.c_void_p), ('Wx', C.c_void_p), ('bias', C.c_void_p),
+        ('used_ids', C.c_void_p), ('sample_ids', C.c_void_p), ('x', C.c_void_p),
+        ('V', C.c_int), ('E', C.c_int), ('stream', C.c_uint32), ('thr_p', C.c_uint32),
+    ]
+
+
 class AvsrRnnSeq(C.Structure):
     _fields_ = [
         ('T', C.c_int), ('B', C.c_int), ('H', C.c_int), ('n_mech', C.c_int), ('output_attention', C.c_int),
@@ -38,6 +46,7 @@ class AvsrRnnSeq(C.Structure):
         ('grad_scale', C.c_float),
         ('rng', C.c_void_p), ('drop_stream', C.c_uint32), ('thr_in', C.c_uint32), ('thr_state', C.c_uint32),
         ('thr_out', C.c_uint32), ('t_begin', C.c_int), ('t_end', C.c_int), ('stepwise', C.c_int),
+        ('samp', C.POINTER(AvsrSampling)),
     ]
 
 
@@ -69,6 +78,7 @@ PROTOTYPES = {
     'avsr_transpose01': (_I, [_P, _P, _P, _I, _I, _I]),
     'avsr_rnn_work_floats': (C.c_size_t, [_I, _I, _I, _I, _I, _I]),
     'avsr_struct_sizes': (_I, [C.POINTER(C.c_int)]),
+    'avsr_rnn_sampling_fused': (_I, [C.POINTER(AvsrRnnSeq)]),
     'avsr_rnn_seq_fwd': (_I, [_P, C.POINTER(AvsrRnnSeq)]),
     'avsr_rnn_seq_bwd': (_I, [_P, C.POINTER(AvsrRnnSeq)]),
     'avsr_normed_v_fwd': (_I, [_P, _P, _P, _I, _P]),

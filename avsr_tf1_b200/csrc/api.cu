@@ -18,6 +18,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r);
+int rnn_sampling_fused(const AvsrRnnSeq* r);
 int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r);
 size_t rnn_work_floats(int B, int H, int At, int maxHD, int maxA, int maxTm);
 // tcgen05 TF32 path (gemm_tc.cu); returns -1 when the shape is not eligible
@@ -115,6 +116,7 @@ int avsr_struct_sizes(int* out2) {
   out2[1] = (int)sizeof(AvsrRnnSeq);
   return 0;
 }
+int avsr_rnn_sampling_fused(const AvsrRnnSeq* r) { return rnn_sampling_fused(r); }
 int avsr_rnn_seq_fwd(avsr_stream_t s, const AvsrRnnSeq* r) { return rnn_seq_fwd((cudaStream_t)s, r); }
 int avsr_rnn_seq_bwd(avsr_stream_t s, const AvsrRnnSeq* r) { return rnn_seq_bwd((cudaStream_t)s, r); }
 

@@ -1111,6 +1111,7 @@ static int cluster_width() {
 }
 
 }  // namespace ap
+int cluster_width_ap() { return ap::cluster_width(); }
 
 int attn_persist4_launch_fwd(cudaStream_t st, int T, int B, int Tm, int scaled, const int* len, const int* mem_len,
                              float* gates, const float* Wp, const void* keys_h, const void* values_h, const float* g,
@@ -1127,6 +1128,20 @@ int attn_persist4d_launch_bwd(cudaStream_t st, const AvsrRnnSeq* r, const void* 
 
 // DropoutWrapper of the wrapped cell on: the two-product kernels of attn_persist4d.cu (no fold of the attention layer)
 static bool layer_dropout(const AvsrRnnSeq* r) { return r->rng && (r->thr_in | r->thr_state | r->thr_out); }
+// the two-product kernels also carry the in-kernel scheduled sampling (AvsrSampling)
+static bool unfused_fwd(const AvsrRnnSeq* r) { return layer_dropout(r) || r->samp != nullptr; }
+
+// shapes the persistent attention kernels of this file / attn_persist4*.cu cover
+static bool persist_shape_ok(const AvsrRnnSeq* r) {
+  if (r->n_mech != 1 || r->T <= 1) return false;
+  const AvsrAttnMech& m = r->mech[0];
+  return m.kind <= AVSR_ATTN_SCALED_LUONG && r->H == 256 && m.A == 256 && m.Dm == 256 && m.Tm <= 384;
+}
+int cluster_width_ap();
+int rnn_sampling_fused(const AvsrRnnSeq* r) {
+  return r && r->rng && tensor_cores_enabled() && persist_shape_ok(r) && r->output_attention && cluster_width_ap() == 4 &&
+         !getenv("AVSR_NO_ATTN_PERSIST") && !(r->t_begin || r->t_end || r->stepwise);
+}
 
 size_t attn_persist_work_floats(int B, int H, int Dm, int Tm) {
   // fused weights [(H+Dm),4H] + product scratch [H,4H] + fp16 keys / values
@@ -1141,7 +1156,7 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   const AvsrAttnMech& m = r->mech[0];
   if (m.kind > AVSR_ATTN_SCALED_LUONG) return -1;
   if (r->H != H || m.A != H || m.Dm != DM || m.Tm > MAX_TM) return -1;
-  if (layer_dropout(r) && (!r->output_attention || cluster_width() != 4)) return -1;
+  if (unfused_fwd(r) && (!r->output_attention || cluster_width() != 4)) return -1;
   const int T = r->T, B = r->B, At = m.A, SW = At + H;
   float* Wp = scratch;
   float* tmp = Wp + (size_t)(H + DM) * 4 * H;
@@ -1149,8 +1164,8 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   __half* values_h = keys_h + (size_t)m.Tm * B * H;
   // step 0: att_{-1} = 0, so only h_0 Wh enters (exact AttentionWrapper zero-state semantics)
   AVSR_TRY(gemm(st, 0, 0, B, 4 * H, H, r->S + At, SW, r->Wrec + (size_t)At * 4 * H, 4 * H, r->gates, 4 * H, 1.0f, nullptr));
-  if (layer_dropout(r)) {
-    // DropoutWrapper on: no fused matrix; the kernel forms the attention vectors itself and writes `out` (attention
+  if (unfused_fwd(r)) {
+    // DropoutWrapper on (or scheduled sampling inside the recurrence): no fused matrix; the kernel forms the attention vectors itself and writes `out` (attention
     // vectors, zero past the length) and the state rows [a (.) m_in | hs]
     const long long nk = (long long)m.Tm * B * H, nv = (long long)m.Tm * B * DM;
     AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
@@ -1218,7 +1233,7 @@ int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch, bool 
   const AvsrAttnMech& m = r->mech[0];
   if (m.kind > AVSR_ATTN_SCALED_LUONG) return -1;
   if (r->H != H || m.A != H || m.Dm != DM || m.Tm > MAX_TM) return -1;
-  unfused = unfused || layer_dropout(r);
+  unfused = unfused || unfused_fwd(r);
   if (unfused && (!r->output_attention || cluster_width() != 4)) return -1;
   const int T = r->T, B = r->B, At = m.A, SW = At + H, HD = H + DM;
   const bool oa = r->output_attention != 0;

@@ -64,11 +64,30 @@ struct DParams {
   float* cT;             // [B,H] or null
   float* hT;             // [B,H] or null
   DropCfg d;
+  // SAMPLE instantiation: ScheduledEmbeddingTrainingHelper inside the kernel (AvsrSampling, include/avsr_b200.h)
+  const float* Wd;       // [AT, V]
+  const float* bd;       // [V]
+  const float* emb;      // [V, E]
+  const float* Wx;       // [E, 4H]
+  const float* bias;     // [4H]
+  int* used_ids;         // [T,B]
+  int* sample_ids;       // [T,B]
+  float* x;              // [T,B,E]
+  int V, E;
+  uint32_t ss_stream, thr_p;
 };
 
+constexpr int SAMP_VP = 32;                                 // padded alphabet (V <= 32)
+constexpr int SAMP_EMAX = 256;                              // E <= 256
+constexpr int SAMP_SMEM = NB * UPC * 4 + UPC * SAMP_VP * 4 + CL * NB * SAMP_VP * 4 + SAMP_EMAX * 4 + NB * 4;
 constexpr size_t DFWD_SMEM = (size_t)W_BYTES + 2 * OP_BYTES + Q_BYTES + 4 * NB * UPC * 4 + APART_FLOATS * 4 +
-                             NU * MAX_TM * 4 + NU * 8 * 4 + 64 + 1024;
+                             NU * MAX_TM * 4 + NU * 8 * 4 + 64 + SAMP_SMEM + 1024;
 
+// SAMPLE: scheduled sampling (decoder_unimodal.py:304-309) inside the recurrence.  Which (step, utterance) pairs
+// are replaced is a function of the generator alone, so every CTA of the cluster knows it; for those pairs the CTAs
+// reduce partial logits a_t Wd over their attention units through DSMEM, every CTA draws the same id (inverse CDF of
+// the fp32 softmax, as avsr_sched_sample) and forms the x-projection of the drawn embedding for its own gate rows.
+template <bool SAMPLE>
 __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(const DParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -80,10 +99,17 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
   const uint32_t sSc = sAp + APART_FLOATS * 4;       // [NU][MAX_TM] scores / alignments
   const uint32_t sRed = sSc + NU * MAX_TM * 4;       // [NU][8]
   const uint32_t sBar = sRed + NU * 8 * 4;           // [0] mma1 [1] mma2 [2,3] h_full[buf] [4] ctx_full [5] a_full
-  const uint32_t sTmem = sBar + 48;
+  const uint32_t sTmem = sBar + 56;                  // [6] logits_full (SAMPLE)
+  const uint32_t sSamp = sBar + 64;                  // SAMPLE: a_t [NB][UPC] | Wd slice [UPC][32] | partial logits [CL][NB][32] | x [256] | picks [NB]
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   float* act = reinterpret_cast<float*>(gen + (sAct - base));
   float* apart = reinterpret_cast<float*>(gen + (sAp - base));
+  float* sAf = reinterpret_cast<float*>(gen + (sSamp - base));
+  float* sWd = sAf + NB * UPC;
+  float* sLg = sWd + UPC * SAMP_VP;
+  float* sX = sLg + CL * NB * SAMP_VP;
+  int* sPick = reinterpret_cast<int*>(sX + SAMP_EMAX);
+  const uint32_t sLgAddr = sSamp + (NB * UPC + UPC * SAMP_VP) * 4, barL = sBar + 48;
   float* sc_all = reinterpret_cast<float*>(gen + (sSc - base));
   float* part_all = act;
   float* red_all = reinterpret_cast<float*>(gen + (sRed - base));
@@ -97,8 +123,14 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
   if (tid == 0) {
     mbar_init(barM1, THREADS / 32);  // one commit per issuing warp
     mbar_init(barM2, THREADS / 32);
-    for (int i = 2; i < 6; ++i) mbar_init(sBar + 8 * i, 1);
+    for (int i = 2; i < 7; ++i) mbar_init(sBar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if constexpr (SAMPLE) {  // output-layer rows of the CTA's attention units
+    for (int i = tid; i < UPC * SAMP_VP; i += THREADS) {
+      const int u = i / SAMP_VP, v = i % SAMP_VP;
+      sWd[i] = v < p.V ? p.Wd[(size_t)(UPC * rank + u) * p.V + v] : 0.0f;
+    }
   }
   // tensor memory (all 512 columns): [0, 128) accumulators (8 x 16 columns, shared by the two products);
   // [128, 256) Wa slice (paired layout); [256, 512) recurrent tile 1
@@ -251,6 +283,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
   const uint32_t att_bar_id = 2 + jl;          // named barrier of the 128 threads of this utterance
   const AttRole role = {p.keys, p.values, L, B, b_att, Tm, w4, gt, lane, gs, att_bar_id, sc, part, red};
 
+  uint32_t lphase = 0u;  // SAMPLE: completed phases of the logits barrier
   for (int t = 0; t < T; ++t) {
     float* grow = p.gates + ((size_t)t * B + b0) * 4 * H + g * H + unit_g;
     uint32_t r[8];
@@ -404,6 +437,14 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
         ap[b * UPC] = (__uint_as_float(r0[b]) + __uint_as_float(r1[b])) + (__uint_as_float(r2[b]) + __uint_as_float(r3[b]));
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    uint32_t selmask = 0u;  // SAMPLE: utterances of the cluster whose next input is drawn from this step's logits
+    if constexpr (SAMPLE) {
+      if (t + 1 < T) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+          if (b0 + b < B && avsr_rand_u32(seed, rstep, p.ss_stream, (uint32_t)t, (uint32_t)(b0 + b)) < p.thr_p) selmask |= 1u << b;
+      }
+    }
     if (comb) {
       float a[4];
       {
@@ -431,6 +472,77 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
         *reinterpret_cast<float4*>(p.out + row * AT + ucol) =
             live ? make_float4(a[0], a[1], a[2], a[3]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         *reinterpret_cast<float4*>(p.S + (row + B) * (AT + H) + ucol) = make_float4(ad[0], ad[1], ad[2], ad[3]);
+      }
+      if constexpr (SAMPLE) {
+        if (selmask) *reinterpret_cast<float4*>(&sAf[bq * UPC + 4 * uq]) = make_float4(a[0], a[1], a[2], a[3]);
+      }
+    }
+    if constexpr (SAMPLE) {
+      if (selmask) {  // uniform over the cluster
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // partial logits of the selected utterances over this CTA's attention units: warp = utterance, lane = class
+        if ((selmask >> warp) & 1u) {
+          float sacc = 0.0f;
+#pragma unroll 8
+          for (int u = 0; u < UPC; ++u) sacc = fmaf(sAf[warp * UPC + u], sWd[u * SAMP_VP + lane], sacc);
+          const uint32_t dstoff = sLgAddr + (uint32_t)(((int)rank * NB + warp) * SAMP_VP + lane) * 4;
+#pragma unroll
+          for (uint32_t dst = 0; dst < (uint32_t)CL; ++dst) st_async_f(mapa(dstoff, dst), mapa(barL, dst), sacc);
+        }
+        if (tid == 0) mbar_expect_tx(barL, (uint32_t)__popc(selmask) * SAMP_VP * 4 * CL);
+        mbar_wait(barL, lphase & 1);
+        ++lphase;
+        if (((selmask >> warp) & 1u) && lane == 0) {
+          // inverse CDF of the fp32 softmax, summed in class order (the arithmetic of sched_sample_kernel, misc.cu)
+          float z[SAMP_VP];
+          float mx = -INFINITY;
+          for (int v = 0; v < p.V; ++v) {
+            z[v] = p.bd[v] + ((sLg[(0 * NB + warp) * SAMP_VP + v] + sLg[(1 * NB + warp) * SAMP_VP + v]) +
+                              (sLg[(2 * NB + warp) * SAMP_VP + v] + sLg[(3 * NB + warp) * SAMP_VP + v]));
+            mx = fmaxf(mx, z[v]);
+          }
+          float total = 0.0f;
+          for (int v = 0; v < p.V; ++v) total += expf(z[v] - mx);
+          const float u01 = (float)(avsr_rand_u32(seed, rstep, p.ss_stream + 1u, (uint32_t)t, (uint32_t)(b0 + warp)) >> 8) * (1.0f / 16777216.0f);
+          const float target = u01 * total;
+          float cum = 0.0f;
+          int pick = p.V - 1;
+          for (int v = 0; v < p.V; ++v) {
+            cum += expf(z[v] - mx);
+            if (cum > target) {
+              pick = v;
+              break;
+            }
+          }
+          sPick[warp] = pick;
+          if (rank == 0) {
+            p.sample_ids[(size_t)t * B + b0 + warp] = pick;
+            p.used_ids[(size_t)(t + 1) * B + b0 + warp] = pick;
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // x-projection of the drawn embeddings for this thread's gate row (g, unit_g): replaces the prefetched one
+        const float* wxcol = p.Wx + g * H + unit_g;
+        const float bias_row = p.bias[g * H + unit_g];
+#pragma unroll 1
+        for (int bb = 0; bb < NB; ++bb) {
+          if (!((selmask >> bb) & 1u)) continue;
+          const int id = sPick[bb];
+          for (int e = tid; e < p.E; e += THREADS) {
+            const uint32_t lo = (uint32_t)(((size_t)(t + 1) * B + b0 + bb) * p.E + e);
+            const float xv = tf32_rn(p.emb[(size_t)id * p.E + e] * dfac(seed, rstep, p.d.stream + 3u, p.d.thr_in, p.d.inv_in, 0u, lo));
+            sX[e] = xv;
+            if (rank == 0) p.x[((size_t)(t + 1) * B + b0 + bb) * p.E + e] = xv;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          float acc = bias_row;
+#pragma unroll 8
+          for (int e = 0; e < p.E; ++e) acc = fmaf(sX[e], wxcol[(size_t)e * 4 * H], acc);
+#pragma unroll
+          for (int b = 0; b < NB; ++b)
+            if (b == bb) gx[b] = (t + 1 < len_a[b]) ? acc : 0.0f;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
       }
     }
     // recurrent product of step t+1 once every CTA's a_t slice has landed (hs_t landed before the attention).  After
@@ -943,7 +1055,18 @@ int attn_persist4d_launch_fwd(cudaStream_t st, const AvsrRnnSeq* r, const void* 
   p.g = m.g; p.c0 = r->c0; p.S = r->S; p.craw = r->craw; p.out = r->out; p.hc = m.hc; p.align = m.align;
   p.cT = r->cT; p.hT = r->hT;
   p.d = drop_cfg(r);
-  return ap4::launch_cluster(st, ap4::attn_lstm_persist4d_fwd_kernel, r->B, ap4::DFWD_SMEM, p, AVSR_K_ATTN_FWD);
+  p.Wd = p.bd = p.emb = p.Wx = p.bias = nullptr;
+  p.used_ids = p.sample_ids = nullptr; p.x = nullptr; p.V = p.E = 0; p.ss_stream = p.thr_p = 0u;
+  if (r->samp) {
+    const AvsrSampling& s = *r->samp;
+    AVSR_REQUIRE(r->rng != nullptr, "rnn: scheduled sampling needs the generator words (rng)");
+    AVSR_REQUIRE(s.V > 0 && s.V <= ap4::SAMP_VP && s.E > 0 && s.E <= ap4::SAMP_EMAX, "rnn: sampling alphabet / embedding too wide");
+    p.Wd = s.Wd; p.bd = s.bd; p.emb = s.embedding; p.Wx = s.Wx; p.bias = s.bias;
+    p.used_ids = s.used_ids; p.sample_ids = s.sample_ids; p.x = s.x; p.V = s.V; p.E = s.E;
+    p.ss_stream = s.stream; p.thr_p = s.thr_p;
+    return ap4::launch_cluster(st, ap4::attn_lstm_persist4d_fwd_kernel<true>, r->B, ap4::DFWD_SMEM, p, AVSR_K_ATTN_FWD);
+  }
+  return ap4::launch_cluster(st, ap4::attn_lstm_persist4d_fwd_kernel<false>, r->B, ap4::DFWD_SMEM, p, AVSR_K_ATTN_FWD);
 }
 
 int attn_persist4d_launch_bwd(cudaStream_t st, const AvsrRnnSeq* r, const void* keys_h, const void* values_h) {

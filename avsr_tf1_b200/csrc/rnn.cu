@@ -251,10 +251,15 @@ static int check_common(const AvsrRnnSeq* r, int* At_out, int* maxHD, int* maxA,
 int lstm_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r);   // lstm_persist.cu (tries the clusters of 4 first)
 int lstm_persist4_fwd(cudaStream_t st, const AvsrRnnSeq* r);  // lstm_persist4.cu (also under dropout)
 
+int rnn_sampling_fused(const AvsrRnnSeq* r);  // attn_persist.cu
+
 int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   int At, maxHD, maxA, maxTm;
   AVSR_TRY(check_common(r, &At, &maxHD, &maxA, &maxTm));
   const bool stepwise = stepwise_only(r);
+  AVSR_REQUIRE(!r->samp || rnn_sampling_fused(r),
+               "rnn: scheduled sampling inside the recurrence is not available for this layer (see avsr_rnn_sampling_fused); "
+               "advance in step ranges with avsr_sched_sample instead");
   if (r->n_mech == 0 && tensor_cores_enabled() && !stepwise) {  // persistent cluster kernel (tcgen05, weights resident)
     const int rc = has_dropout(r) ? lstm_persist4_fwd(st, r) : lstm_persist_fwd(st, r);
     if (rc >= 0) return rc;

@@ -142,11 +142,19 @@ class Seq2SeqUnimodalDecoder(object):
         The ids actually fed are kept for the embedding gradient; no gradient flows through the draws."""
         ctx, cell = self._ctx, self._cell
         V = self._vocab_size
-        used = torch.empty((T, B), dtype=torch.int32, device='cuda')
-        used[0].copy_(dec_in_ids[0])
+        used = dec_in_ids.clone()  # [T,B]; rows 1.. are overwritten where the helper draws
         self.sample_ids = torch.full((T, B), -1, dtype=torch.int32, device='cuda')
-        cell.begin_stepwise(T, B, labels_len, memories, init)
         table = ctx.w(self._embedding)
+        # the persistent kernel draws inside the recurrence when it covers this cell (one launch instead of ~11 per step)
+        out = cell.forward_sampled(table, dec_in_ids, labels_len, memories, init, ctx.p(self._Wd), ctx.p(self._bd),
+                                   self._ss_stream, self._ss_thr, used, self.sample_ids)
+        if out is not None:
+            O = cell.out_dim
+            ops.gemm(out.view(T * B, O), ctx.p(self._Wd), self._logits.view(T * B, V), bias=ctx.p(self._bd))
+            self._ids = used.reshape(-1)
+            self.decoder_input_ids = used
+            return out
+        cell.begin_stepwise(T, B, labels_len, memories, init)
         for t in range(T):
             x_t = ops.empty(B, self._E)
             ops.embedding_fwd(table, used[t], x_t)

@@ -298,6 +298,35 @@ class AttnLSTMOp:
         self.operand = out if (self.output_attention or self.drop is not None) else self.rnn.S[1:, :, self.At:]
         return out
 
+    def forward_sampled(self, table, true_ids, lens, memories, init, Wd, bd, ss_stream, ss_thr, used_ids, sample_ids):
+        """Whole-sequence forward with ScheduledEmbeddingTrainingHelper INSIDE the recurrent kernel (AvsrSampling in
+        include/avsr_b200.h): true_ids [T,B] are the teacher-forced decoder inputs, used_ids (pre-filled with them) /
+        sample_ids (pre-filled with -1) receive what the helper drew.  Returns the outputs, or None when this layer's
+        persistent kernel cannot do it (the caller then advances step by step: begin_stepwise / stepwise_step)."""
+        T, B = true_ids.shape
+        H, Dx, ctx = self.H, self.Dx, self.ctx
+        W, b = ctx.w(self.kernel), ctx.p(self.bias)
+        gates = ops.empty(T, B, 4 * H)
+        bufs = self.prepare_memories(memories)
+        c0, h0 = init if init is not None else (None, None)
+        rnn = ops.RnnSeq(T, B, H, lens, gates, W[Dx:], bufs, self.output_attention, c0=c0, h0=h0, drop=self.drop)
+        rnn.rng = ctx.rng
+        x = ops.empty(T, B, Dx)
+        rnn.sampling = ops.Sampling(Wd, bd, table, W[:Dx], b, used_ids, sample_ids, x, ss_stream, ss_thr)
+        if not rnn.sampling_fused():
+            return None
+        ops.embedding_fwd(table, true_ids.reshape(-1), x)
+        if self.drop is not None and self.drop.thr_in:
+            ops.dropout(x, self.drop.rng, self.drop.stream + 3, self.drop.thr_in, round_out=True, out=x)
+        elif ops.tensor_cores_enabled():
+            ops.round_tf32(x, x)
+        ops.gemm(x.view(T * B, Dx), W[:Dx], gates.view(T * B, 4 * H), bias=b)
+        self.x, self.bufs, self.rnn = x, bufs, rnn
+        out = rnn.forward()  # rows of x whose input was drawn are replaced by the kernel (operand of dWx in backward)
+        self.final = (rnn.cT, rnn.hT)
+        self.operand = out if (self.output_attention or self.drop is not None) else rnn.S[1:, :, self.At:]
+        return out
+
     def begin_stepwise(self, T, B, lens, memories, init=None):
         """Scheduled sampling (decoder_unimodal.py:304-309): the decoder inputs are only known step by step.  Sets up
         the whole-sequence buffers; `stepwise_step(t, x_t)` then advances one step and returns that step's output."""

@@ -8,7 +8,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ATTN_KINDS, AvsrAttnMech, AvsrRnnSeq, check
+from ._lib import AvsrSampling, ATTN_KINDS, AvsrAttnMech, AvsrRnnSeq, check
 
 
 def _stream() -> int:
@@ -360,6 +360,26 @@ class MechBuffers:
             setattr(m, k, _p(getattr(self, k)))
 
 
+class Sampling:
+    """ScheduledEmbeddingTrainingHelper inside the recurrence (AvsrSampling in include/avsr_b200.h): device tensors the
+    recurrent op reads / updates when it draws the decoder inputs itself."""
+
+    def __init__(self, Wd, bd, embedding, Wx, bias, used_ids, sample_ids, x, stream, thr_p):
+        self.Wd, self.bd, self.embedding, self.Wx, self.bias = Wd, bd, embedding, Wx, bias
+        self.used_ids, self.sample_ids, self.x = used_ids, sample_ids, x
+        self.V, self.E = int(embedding.shape[0]), int(embedding.shape[1])
+        self.stream, self.thr_p = int(stream), int(thr_p)
+        for t in (Wd, embedding, Wx, x):
+            _chk_f32(t)
+
+    def struct(self) -> AvsrSampling:
+        s = AvsrSampling()
+        for k in ('Wd', 'bd', 'embedding', 'Wx', 'bias', 'used_ids', 'sample_ids', 'x'):
+            setattr(s, k, _p(getattr(self, k)))
+        s.V, s.E, s.stream, s.thr_p = self.V, self.E, self.stream, self.thr_p
+        return s
+
+
 class RnnSeq:
     """One dynamic_rnn / dynamic_decode loop (see AvsrRnnSeq in include/avsr_b200.h)."""
 
@@ -368,6 +388,8 @@ class RnnSeq:
         self.T, self.B, self.H = T, B, H
         self.drop = drop  # DropState (layers.py) or None: DropoutWrapper masks applied inside the loop
         self.stepwise = False
+        self.sampling = None  # Sampling or None: scheduled sampling inside a whole-sequence forward
+        self.rng = None       # generator words when there is no DropState (sampling without dropout)
         self.lens, self.gates, self.Wrec, self.c0 = lens, gates, Wrec, c0
         self.mechs = list(mechs)
         self.oa = bool(output_attention) and len(self.mechs) > 0
@@ -415,7 +437,12 @@ class RnnSeq:
             d = self.drop
             r.rng, r.drop_stream = _p(d.rng), d.stream
             r.thr_in, r.thr_state, r.thr_out = d.thr_in, d.thr_state, d.thr_out
+        elif self.rng is not None:
+            r.rng = _p(self.rng)
         r.stepwise = int(self.stepwise)
+        if self.sampling is not None:
+            self._samp_struct = self.sampling.struct()  # kept alive for the duration of the call
+            r.samp = C.pointer(self._samp_struct)
         for k, v in bw.items():
             setattr(r, k, _p(v))
         return r
@@ -424,6 +451,10 @@ class RnnSeq:
         r = self._desc()
         check(_lib.load().avsr_rnn_seq_fwd(_stream(), C.byref(r)))
         return self.out
+
+    def sampling_fused(self) -> bool:
+        """True if a whole-sequence forward of this layer can draw scheduled samples inside the recurrence."""
+        return bool(_lib.load().avsr_rnn_sampling_fused(C.byref(self._desc())))
 
     def forward_range(self, t_begin, t_end):
         """Steps [t_begin, t_end) only (step-wise kernels): scheduled sampling interleaves its draws with the

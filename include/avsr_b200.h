@@ -134,6 +134,27 @@ typedef struct AvsrAttnMech {
   float* dhc;           /* [T,B,H+Dm] scratch: d[cell output | context] of every step */
 } AvsrAttnMech;
 
+/* ScheduledEmbeddingTrainingHelper (decoder_unimodal.py:304-309) inside a whole-sequence call: step t's output decides,
+ * per row with probability p, the decoder input of step t + 1 (an id drawn from Categorical(logits_t), logits_t =
+ * out_t Wd + bd).  The caller prepares the teacher-forced sequence as usual (x = dropped embeddings of true_ids, gates =
+ * x Wx + bias) and pre-fills used_ids = true_ids, sample_ids = -1; the recurrence replaces the rows that are drawn:
+ * used_ids[t+1,b], sample_ids[t,b], x[t+1,b,:] (the dropped embedding of the drawn id, mask of the whole-sequence
+ * avsr_dropout call on x: stream drop_stream + 3) and the x-projection it uses for that step.  Same generator streams
+ * and arithmetic as avsr_sched_sample.  No gradient flows through the draws. */
+typedef struct AvsrSampling {
+  const float* Wd;         /* output layer kernel [O, V] */
+  const float* bd;         /* [V] */
+  const float* embedding;  /* [V, E] */
+  const float* Wx;         /* x rows of the cell kernel [E, 4H] */
+  const float* bias;       /* cell bias [4H] */
+  int* used_ids;           /* [T,B] in/out */
+  int* sample_ids;         /* [T,B] in/out */
+  float* x;                /* [T,B,E] in/out */
+  int V, E;
+  uint32_t stream;         /* +0 Bernoulli select (hi = t, lo = b), +1 draw */
+  uint32_t thr_p;          /* p * 2^32 */
+} AvsrSampling;
+
 typedef struct AvsrRnnSeq {
   int T, B, H, n_mech, output_attention;
   const int* len;       /* [B] */
@@ -171,12 +192,18 @@ typedef struct AvsrRnnSeq {
    * is how ScheduledEmbeddingTrainingHelper (decoder_unimodal.py:304-309) interleaves sampling with the recurrence.
    * stepwise != 0 forces them for a whole-sequence call too (the backward of a ranged forward). */
   int t_begin, t_end, stepwise;
+  /* scheduled sampling inside a whole-sequence forward call, or NULL.  Only the persistent two-product kernels
+   * implement it: ask avsr_rnn_sampling_fused() first and advance in step ranges with avsr_sched_sample otherwise. */
+  const AvsrSampling* samp;
 } AvsrRnnSeq;
 
 /* At = sum of mechanism A; maxHD = max(H+Dm); maxA = max A; maxTm = max memory length (0,0,0,0 without attention) */
 size_t avsr_rnn_work_floats(int B, int H, int At, int maxHD, int maxA, int maxTm);
 /* sizeof(AvsrAttnMech), sizeof(AvsrRnnSeq) as compiled (bindings check their struct layout against it) */
 int avsr_struct_sizes(int* out2);
+/* 1 if avsr_rnn_seq_fwd(r) with r->samp set would draw the samples inside the recurrence (tensor-core mode, one Luong-family
+ * mechanism, H = A = Dm = 256, T > 1), else 0 */
+int avsr_rnn_sampling_fused(const AvsrRnnSeq* r);
 int avsr_rnn_seq_fwd(avsr_stream_t stream, const AvsrRnnSeq* r);
 int avsr_rnn_seq_bwd(avsr_stream_t stream, const AvsrRnnSeq* r);
 

@@ -305,6 +305,7 @@ def _spec64(s):
     (('scaled_luong',), 20, 9, 128, 256, (75,), (256,)),   # persistent cluster kernel (tf32 mode), 2 clusters
     (('luong',), 5, 14, 256, 256, (300,), (256,)),
     (('scaled_luong',), 250, 6, 128, 256, (75,), (256,)),  # > 240 utterances: 32-utterance slices, 16-warp CTAs
+    (('scaled_luong',), 8, 24, 80, 256, (96,), (256,)),    # more steps, memory = SMALL_TM rows (stress weights: errors grow with T)
 ])
 def test_attention_rnn_fwd_bwd(kinds, B, T, Dx, H, Tms, Dms, tensor_cores):
     _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, tensor_cores)
@@ -340,7 +341,7 @@ class _Drop:
 @pytest.mark.parametrize('kinds,B,T,Dx,H,Tms,Dms,keep', [
     (('scaled_luong',), 20, 9, 128, 256, (75,), (256,), (0.9, 0.9, 0.9)),     # 3 clusters, the last one half full
     (('luong',), 36, 14, 256, 256, (300,), (256,), (0.8, 0.9, 0.7)),          # long memory: shared-memory softmax path
-    (('scaled_luong',), 8, 70, 80, 256, (96,), (256,), (0.9, 0.85, 0.95)),    # many steps, memory = SMALL_TM
+    (('scaled_luong',), 8, 12, 80, 256, (96,), (256,), (0.9, 0.85, 0.95)),    # memory = SMALL_TM rows (stress weights: chaotic beyond ~12 steps, tools/drop_diag.py)
     (('scaled_luong',), 250, 6, 128, 256, (75,), (256,), (0.9, 0.9, 0.9)),    # 32 clusters
     (('luong',), 9, 7, 32, 256, (40,), (256,), (1.0, 0.8, 1.0)),              # only the state mask
     (('scaled_luong',), 9, 7, 32, 256, (40,), (256,), (0.8, 1.0, 1.0)),       # only the input mask

@@ -4,7 +4,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from avsr_tf1_b200 import ops
 B, H = 256, 256
-for (name, T, Dx, Tm) in [('cross-modal', 300, 256, 75), ('decoder', 41, 128, 300)]:
+
+
+class Drop:  # what ops.RnnSeq reads of a layers.DropState (keep 0.9 / 0.9 / 0.9: the reference default)
+    def __init__(self):
+        self.rng = torch.tensor([1234, 5], dtype=torch.int32, device='cuda')
+        self.stream = 8
+        self.thr_in = self.thr_state = self.thr_out = ops.keep_threshold(0.9)
+
+
+ops.kernel_timing(True)
+for (name, T, Dx, Tm, drop) in [('cross-modal', 300, 256, 75, None), ('decoder', 41, 128, 300, None),
+                                ('cross-modal+dropout', 300, 256, 75, Drop()), ('decoder+dropout', 41, 128, 300, Drop())]:
     A = Dm = 256
     x = ops.round_tf32(torch.randn(T, B, Dx, device='cuda'))
     W = ops.round_tf32(torch.randn(Dx + A + H, 4 * H, device='cuda') / (Dx + A + H) ** 0.5)
@@ -22,7 +33,7 @@ for (name, T, Dx, Tm) in [('cross-modal', 300, 256, 75), ('decoder', 41, 128, 30
     for rep in range(3):
         gates = gates0.clone()
         mb = ops.MechBuffers('scaled_luong', values, keys, mlen, Wl, g=g)
-        rnn = ops.RnnSeq(T, B, H, lens, gates, W[Dx:], [mb], True)
+        rnn = ops.RnnSeq(T, B, H, lens, gates, W[Dx:], [mb], True, drop=drop)
         mb.dkeys, mb.dvalues = torch.zeros_like(keys), torch.zeros_like(values)
         mb.dWl, mb.dg = torch.zeros_like(Wl), torch.zeros(1, device='cuda')
         gW = torch.zeros_like(W)
@@ -33,4 +44,7 @@ for (name, T, Dx, Tm) in [('cross-modal', 300, 256, 75), ('decoder', 41, 128, 30
         e0.record(); rnn.forward(); e1.record(); rnn.backward(dout, gW[Dx:]); e2.record()
         torch.cuda.synchronize()
         best = [min(best[0], e0.elapsed_time(e1) * 1e3), min(best[1], e1.elapsed_time(e2) * 1e3)]
-    print(f'{name:12s} T={T:3d} Tm={Tm:3d}: fwd {best[0]:8.1f} us ({best[0] / T:6.2f}/step)  bwd {best[1]:8.1f} us ({best[1] / T:6.2f}/step)', flush=True)
+    kt = ops.kernel_times()
+    ops.kernel_timing(True)
+    print(f'{name:20s} kernels only (3 reps): fwd {kt["attn_lstm_fwd"][0] / 3 * 1e3:8.1f} us  bwd {kt["attn_lstm_bwd"][0] / 3 * 1e3:8.1f} us')
+    print(f'{name:20s} T={T:3d} Tm={Tm:3d}: fwd {best[0]:8.1f} us ({best[0] / T:6.2f}/step)  bwd {best[1]:8.1f} us ({best[1] / T:6.2f}/step)', flush=True)
