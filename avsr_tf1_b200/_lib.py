@@ -76,6 +76,7 @@ PROTOTYPES = {
     'avsr_bn_bwd_apply': (_I, [_P, _P, _P, _L, _I, _P, _D, _P, _P, _P, _P, _P]),
     'avsr_reverse_sequence': (_I, [_P, _P, _P, _I, _I, _I, _P]),
     'avsr_transpose01': (_I, [_P, _P, _P, _I, _I, _I]),
+    'avsr_u8_to_f32': (_I, [_P, _P, _L, _F, _F, _P]),
     'avsr_rnn_work_floats': (C.c_size_t, [_I, _I, _I, _I, _I, _I]),
     'avsr_struct_sizes': (_I, [C.POINTER(C.c_int)]),
     'avsr_rnn_sampling_fused': (_I, [C.POINTER(AvsrRnnSeq)]),

@@ -255,6 +255,23 @@ __global__ void transpose01_kernel(const float* __restrict__ x, float* __restric
   y[i] = x[((long long)k * d1 + j) * F + f];
 }
 
+// lip-crop pixels as they are stored (uint8) -> the reference's float features (v - 128) / 128 (dataset_writer.py:537):
+// the crops cross PCIe as bytes and are expanded here (exact: k / 128 is a float).  16 pixels per thread.
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ x, long long n, float scale, float shift, float* __restrict__ y) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i + 16 <= n) {
+    const uint4 v = *reinterpret_cast<const uint4*>(x + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      *reinterpret_cast<float4*>(y + i + 4 * k) =
+          make_float4(((float)(w[k] & 255u) + shift) * scale, ((float)((w[k] >> 8) & 255u) + shift) * scale,
+                      ((float)((w[k] >> 16) & 255u) + shift) * scale, ((float)(w[k] >> 24) + shift) * scale);
+  } else {
+    for (long long j = i; j < n; ++j) y[j] = ((float)x[j] + shift) * scale;
+  }
+}
+
 __global__ void embedding_fwd_kernel(const float* __restrict__ table, int V, int E, const int* __restrict__ ids,
                                      long long n, float* __restrict__ out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -829,6 +846,13 @@ int avsr_transpose01(avsr_stream_t s, const float* x, float* y, int d0, int d1, 
   if (n <= 0) return 0;
   AVSR_REQUIRE(x != y, "transpose01 cannot run in place");
   AVSR_LAUNCH(transpose01_kernel, cdiv(n, 256), 256, 0, ST(s), x, y, d0, d1, F);
+  return 0;
+}
+
+int avsr_u8_to_f32(avsr_stream_t s, const uint8_t* x, long long n, float scale, float shift, float* y) {
+  if (n <= 0) return 0;
+  AVSR_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "u8_to_f32: buffers must be 16-byte aligned");
+  AVSR_LAUNCH(u8_to_f32_kernel, cdiv(cdiv(n, 16), 256), 256, 0, ST(s), x, n, scale, shift, y);
   return 0;
 }
 

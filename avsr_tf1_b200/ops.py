@@ -64,6 +64,15 @@ def round_tf32(src: torch.Tensor, dst: torch.Tensor = None) -> torch.Tensor:
     return dst
 
 
+def u8_to_f32(x: torch.Tensor, y: torch.Tensor = None, scale=1.0 / 128.0, shift=-128.0) -> torch.Tensor:
+    """Stored lip-crop pixels (uint8) -> the reference's float features (v - 128) / 128 (dataset_writer.py:537)."""
+    assert x.dtype == torch.uint8 and x.is_cuda and x.is_contiguous()
+    if y is None:
+        y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    check(_lib.load().avsr_u8_to_f32(_stream(), x.data_ptr(), x.numel(), float(scale), float(shift), y.data_ptr()))
+    return y
+
+
 def empty(*shape, dtype=torch.float32):
     return torch.empty(*shape, dtype=dtype, device='cuda')
 

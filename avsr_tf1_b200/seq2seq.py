@@ -260,7 +260,10 @@ class Seq2SeqModel(object):
         for key, d in (('video', video), ('audio', audio)):
             if d is None:
                 continue
-            x = self._as_tensor(d.inputs, torch.float32)
+            # lip crops may arrive as the stored pixels (uint8): they cross PCIe as bytes and become the reference's
+            # (v - 128) / 128 floats on the device (_prep)
+            raw_u8 = key == 'video' and torch.is_tensor(d.inputs) and d.inputs.dtype == torch.uint8
+            x = d.inputs if raw_u8 else self._as_tensor(d.inputs, torch.float32)
             if x.dim() > 3 and not (key == 'video' and self._cnn is not None):
                 x = x.reshape(x.shape[0], x.shape[1], -1)  # raw lip crops fed as flat features (`features`)
             src[key] = x
@@ -359,7 +362,7 @@ class Seq2SeqModel(object):
         b: Dict[str, object] = {}
         for key in ('video', 'audio'):
             if key in src:
-                b[key] = src[key]
+                b[key] = ops.u8_to_f32(src[key]) if src[key].dtype == torch.uint8 else src[key]
                 b[key + '_len'] = src[key + '_len']
         if 'aus' in src:
             b['aus'] = src['aus']

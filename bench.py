@@ -1,17 +1,22 @@
 #!/usr/bin/env python
-"""bench.py - headline benchmark: AV-Align training throughput (utterances/s).
+"""bench.py - headline benchmark: AV-Align training throughput (utterances/s) on the reference's DEFAULT graph.
 
-Workload (BASELINE.json configs[4], the configuration the metric is quoted on): AV-Align
-cross-modal fusion, 3x256 uni-LSTM video and audio encoders, 1x256 attention decoder,
-per-GPU batch 256, T_audio = 300 mel-80 frames, T_video = 75 lip crops of 36x36x3 (fed as
-flat 3888-d `features`, the only video entry the six hot-path files define; the ResNet
-front-end is SURVEY.md row f-3), 40-char targets + EOS.  One step = forward + backward +
-global-norm clip + Adam on one batch.
+Workload (BASELINE.json configs[4], the configuration the metric is quoted on): AV-Align cross-modal fusion, 3x256
+uni-LSTM video and audio encoders, 1x256 attention decoder, per-GPU batch 256, T_audio = 300 mel-80 frames, T_video =
+75 lip crops of 36x36x3 (fed as flat 3888-d `features`, the only video entry the six hot-path files define; the ResNet
+front-end is SURVEY.md row f-3), 40-char targets + EOS, with the reference's default randomness ON (avsr.py:51-56:
+DropoutWrapper keep 0.9 / 0.9 / 0.9 on every cell, scheduled sampling 0.1) - what run_audiovisual.py trains.  One step =
+forward + backward + global-norm clip + Adam on one batch.
 
   python bench.py --gpus N --steps K --warmup W          # our arm (one rank per GPU under torchrun)
-  python bench.py --impl reference ...                   # the CPU restatement of the TF1 graph (oracle)
+  python bench.py --impl reference ...                   # the CPU restatement of the TF1 graph (oracle), same graph
+  python bench.py --config 2 ...                         # another BASELINE.json configuration as the workload
+  python bench.py --graph parity ...                     # randomness off (the switches of the parity tests)
+  python bench.py --scaling strong --gpus N              # global batch fixed at the configuration's (256 / N per GPU)
 
-Prints ONE JSON line on rank 0.
+The default run also measures, as side keys of the same JSON line (N = 1): `parity_graph`, `configs` (BASELINE configs
+1-4 with their kernel-class times), `e2e_tfrecord`, `cpu_baseline`; at N > 1: `strong_scaling`.  Prints ONE JSON line on
+rank 0.
 """
 from __future__ import annotations
 
@@ -28,8 +33,17 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-METRIC = 'AV-Align train utterances/sec'
 UNIT = 'utterances/s'
+# BASELINE.json configs: (per-GPU batch at N = 1, label, uses video, uses audio)
+CONFIGS = {
+    1: dict(batch=2, what='audio-only LAS, 1x128 uni-LSTM encoder, 1x128 decoder (run_audio.py reduced; the CPU-runnable case)'),
+    2: dict(batch=64, what='audio-only LAS, 3x256 BiLSTM encoder + Bahdanau attention decoder, T_a=300'),
+    3: dict(batch=64, what='video-only lipreading, 3x256 LSTM over 36x36x3 lip crops (flat 3888-d features), T_v=75'),
+    4: dict(batch=128, what='WLAS dual-attention AV decoder, 3x256 encoder per modality'),
+    5: dict(batch=256, what='AV-Align cross-modal fusion, 3x256 encoders, T_a=300 / T_v=75'),
+}
+METRICS = {1: 'LAS (1x128) train utterances/sec', 2: 'LAS BiLSTM train utterances/sec', 3: 'lipreading train utterances/sec',
+           4: 'WLAS train utterances/sec', 5: 'AV-Align train utterances/sec'}
 
 
 def parse():
@@ -38,11 +52,16 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=256, help='per-GPU batch (weak scaling)')
+    ap.add_argument('--config', type=int, default=5, choices=sorted(CONFIGS), help='BASELINE.json configuration (1-5)')
+    ap.add_argument('--graph', default='default', choices=['default', 'parity'],
+                    help='default: the reference defaults (dropout 0.9 on every cell, scheduled sampling 0.1); '
+                         'parity: randomness off (SURVEY.md 8d parity switches)')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: per-GPU batch fixed; strong: global batch fixed (per-GPU batch = batch / N)')
+    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch at N = 1 (default: the configuration\'s)')
     ap.add_argument('--video-input', default='crops3888', choices=['crops3888', 'features128'])
-    ap.add_argument('--attention', default='scaled_luong', choices=['bahdanau', 'scaled_luong'],
-                    help='scorer of the cross-modal and decoder attention; scaled_luong is the reference default '
-                         '(avsr.py:50) used by its AV-Align script (run_audiovisual.py:55)')
+    ap.add_argument('--attention', default=None, choices=['bahdanau', 'scaled_luong'],
+                    help='scorer override; default: scaled_luong (avsr.py:50) except config 2 (Bahdanau, BASELINE.json)')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of one CUDA graph per step')
     ap.add_argument('--no-tensor-cores', action='store_true')
     ap.add_argument('--cpu-sample', type=int, default=16, help='utterances per CPU-baseline step')
@@ -50,83 +69,111 @@ def parse():
     ap.add_argument('--overlap', action='store_true', help='run the video and audio encoder branches on two streams')
     ap.add_argument('--skip-roofline', action='store_true')
     ap.add_argument('--skip-extras', action='store_true',
-                    help='skip the two side measurements: the reference-default training graph (dropout + scheduled '
-                         'sampling on) and the TFRecord-fed end-to-end loop')
+                    help='skip the side measurements (parity graph, configs 1-4, TFRecord-fed loop, strong scaling)')
     ap.add_argument('--tfrecord-utterances', type=int, default=1024)
     ap.add_argument('--cer-check-only', action='store_true', help=argparse.SUPPRESS)  # child process of the CER check
     return ap.parse_args()
 
 
-def workload(args, B, seed):
+def randomness(graph):
+    return dict(use_dropout=True, sampling_probability_outputs=0.1) if graph == 'default' else {}
+
+
+def workload(args, cfg, B, seed, graph):
+    """hparams + one synthetic batch (numpy) of BASELINE config `cfg`.  Lip crops are generated as PIXELS: the float
+    features are (v - 128) / 128 of uint8 values (dataset_writer.py:537), `video_u8` holds the bytes."""
     from tests.helpers import config_hparams, synthetic_batch
-    hp = config_hparams(5, attention_type=((args.attention,), (args.attention,)))
+    over = dict(randomness(graph))
+    att = args.attention or ('bahdanau' if cfg == 2 else 'scaled_luong')
+    over['attention_type'] = ((att,), (att,))
+    hp = config_hparams(cfg, **over)
     Fv = 3888 if args.video_input == 'crops3888' else 128
     batch = synthetic_batch(hp, B=B, Ta=300, Tv=75, Fa=80, Fv=Fv, L=40, ragged=False, seed=seed)
-    return hp, batch
+    if 'video' in batch and Fv == 3888:
+        u8 = np.clip(np.rint(batch['video'] * 128.0 + 128.0), 0, 255).astype(np.uint8)
+        batch['video'] = ((u8.astype(np.float32) - 128.0) / 128.0).astype(np.float32)
+        batch['video_u8'] = u8
+    return hp, batch, att
 
 
-def config_dict(args, N):
-    return {
-        'workload': 'AV-Align (BASELINE.json configs[4]): 3x256 uni-LSTM video+audio encoders, cross-modal '
-                    f'{args.attention} attention in the top audio layer, 1x256 {args.attention} attention decoder',
-        'per_gpu_batch': args.batch, 'global_batch': args.batch * N, 'T_audio': 300, 'audio_features': 80,
-        'T_video': 75, 'video_features': 3888 if args.video_input == 'crops3888' else 128,
-        'video_input': '36x36x3 lip crops as flat features' if args.video_input == 'crops3888'
-        else '128-d visual features', 'label_len': 41, 'parallelism': f'dp{N}',
-        'dropout': 'off', 'scheduled_sampling': 'off (the parity switches of SURVEY.md 8d, the graph the reference '
-                                                'arm / cpu_baseline runs too; the reference-default graph with '
-                                                'both ON is timed beside it: key reference_default_graph)',
+def config_dict(args, cfg, B, N, att, graph, scaling):
+    d = {
+        'workload': f'BASELINE.json configs[{cfg - 1}]: {CONFIGS[cfg]["what"]}; {att} attention',
+        'per_gpu_batch': B, 'global_batch': B * N, 'label_len': 41, 'parallelism': f'dp{N}', 'scaling': scaling,
+        'dropout': 'DropoutWrapper keep 0.9/0.9/0.9 on every cell (cells.py:46-54, avsr.py:51-54)' if graph == 'default' else 'off',
+        'scheduled_sampling': '0.1 (decoder_unimodal.py:304-309, avsr.py:56)' if graph == 'default' else 'off',
+        'graph': 'reference default (what run_audiovisual.py trains)' if graph == 'default'
+                 else 'parity switches of SURVEY.md 8d (randomness off)',
         'l2_flush': 'not needed: every step streams > 2 GB of activations through a 126 MB L2',
     }
+    if cfg != 3:
+        d.update(T_audio=300, audio_features=80)
+    if cfg >= 3:
+        d.update(T_video=75, video_features=3888 if args.video_input == 'crops3888' else 128,
+                 video_input='36x36x3 lip crops as flat features; uint8 pixels over PCIe in the e2e loop, expanded to '
+                             '(v-128)/128 on the device' if args.video_input == 'crops3888' else '128-d visual features')
+    return d
 
 
 # ------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle (CPU restatement of the TF1 graph) on host cores
 # ------------------------------------------------------------------------------------
-def run_oracle(args, steps, warmup, sample):
+def host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+        got = max([p['num_threads'] for p in threadpoolctl.threadpool_info()] + [1])
+    except Exception:
+        got = n
+    return int(got)
+
+
+def run_oracle(args, cfg, graph, steps, warmup, sample):
     from avsr_tf1_b200.seq2seq import Seq2SeqModel
     from oracle import avsr_oracle as O
     from tests.helpers import oracle_hparams, to_data_sequences
-    hp, batch = workload(args, sample, seed=0)
+    threads = host_threads()
+    hp, batch, _ = workload(args, cfg, sample, seed=0, graph=graph)
+    batch.pop('video_u8', None)
     model = Seq2SeqModel(to_data_sequences(batch), 'train', hp, seed=2001, device='cpu')
     P = model.store.to_numpy('p')
     names = model.store.names()
-    om = O.OracleModel(oracle_hparams(hp), P)
     m = {k: np.zeros_like(P[k]) for k in names}
     v = {k: np.zeros_like(P[k]) for k in names}
     times = []
     for s in range(warmup + steps):
         t0 = time.perf_counter()
+        model._global_step = s  # fresh masks / draws every step, as in training
+        om = O.OracleModel(oracle_hparams(hp, model if graph == 'default' else None), P)
         loss, G, _ = om.loss_and_grads(batch)
         Pt = {k: P[k] for k in names}
         O.clip_and_adam(Pt, G, m, v, s, hp.learning_rate, clip=hp.max_gradient_norm)
         P.update(Pt)
         times.append(time.perf_counter() - t0)
     t = float(np.mean(times[warmup:]))
-    try:
-        import threadpoolctl
-        threads = max([p['num_threads'] for p in threadpoolctl.threadpool_info()] + [1])
-    except Exception:
-        threads = os.cpu_count() or 1
-    return dict(value=sample / t, sec_per_step=t, cores=int(threads), sample=sample, loss=float(loss))
+    return dict(value=sample / t, sec_per_step=t, cores=threads, sample=sample, loss=float(loss))
 
 
 def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 12))
-    warmup = max(1, min(args.warmup, 2))
-    r = run_oracle(args, steps, warmup, args.cpu_sample)
+    cfg = args.config
+    sample = min(args.cpu_sample, (args.batch or CONFIGS[cfg]['batch']))
+    r = run_oracle(args, cfg, args.graph, args.steps, args.warmup, sample)
+    _, _, att = workload(args, cfg, 1, 0, args.graph)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': steps, 'warmup': warmup, 'ms_per_step': r['sec_per_step'] * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': config_dict(args, args.gpus),
+        'impl': 'reference', 'metric': METRICS[cfg], 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['sec_per_step'] * 1e3, 'higher_is_better': True,
+        'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': config_dict(args, cfg, args.batch or CONFIGS[cfg]['batch'], args.gpus, att, args.graph, args.scaling),
         'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
-                         'sample': f'{r["sample"]} utterances per step of the same workload (full sequence '
-                                   f'lengths), {steps} steps; NumPy/OpenBLAS restatement of the TF1 graph '
-                                   '(TensorFlow 1.13 cannot be installed here)'},
+                         'sample': f'{r["sample"]} utterances per step of the same workload and graph (full sequence '
+                                   f'lengths), {args.steps} steps; NumPy/OpenBLAS restatement of the TF1 graph '
+                                   '(TensorFlow 1.13 cannot be installed here); OMP_NUM_THREADS of the launcher overridden '
+                                   f'to {r["cores"]} threads'},
         'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -171,13 +218,19 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
+
 # ------------------------------------------------------------------------------------
-# roofline of the dominant kernel class: the LSTM gate GEMMs (tensor-pipe bound)
+# rooflines
 # ------------------------------------------------------------------------------------
-def gate_gemm_roofline(args, torch, ops):
-    """Times the big LSTM gate products of this workload in isolation with CUDA events on the launch
+def gate_gemm_roofline(args, torch, ops, B):
+    """Times the big LSTM gate products of the AV-Align workload in isolation with CUDA events on the launch
     stream (distinct operand buffers per launch, > L2 in total).  FLOP = 2*M*N*K per product."""
-    B = args.batch
     Fv = 3888 if args.video_input == 'crops3888' else 128
     H = 256
     shapes = []  # (ta, tb, M, N, K) forward x@Wx, dgrad dZ@Wx^T, wgrad x^T@dZ for every encoder layer
@@ -220,12 +273,9 @@ def gate_gemm_roofline(args, torch, ops):
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     torch.backends.cuda.matmul.allow_tf32 = old
+    del x, y
     tf32_peak = 2.0 * n ** 3 / best / 1e9
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
+    peaks = load_peaks()
     achieved = flops / ms / 1e9
     return {'bound': 'tensor', 'achieved': round(achieved, 2), 'peak': round(tf32_peak, 1), 'unit': 'TFLOP/s',
             'frac': round(achieved / tf32_peak, 4), 'traffic': None,
@@ -235,26 +285,11 @@ def gate_gemm_roofline(args, torch, ops):
             'gate_gemm_ms_per_step': round(ms, 3), 'per_shape': per}
 
 
-def persistent_kernel_rooflines(args, torch, ops, model, gate):
-    """The kernels that dominate the step, timed LIVE with CUDA events on their launching stream (in-library timers,
-    avsr_kernel_timing) over three eager replays of the same training step that was timed above as a CUDA graph.
-
-    Attention class (HBM): algorithmic bytes per (utterance, query step) = 4 Tm (A + Dm) + 4 (Tm + Dm + A)
-    (fp32 keys + values streamed once per step); the backward kernel sweeps both again.  Tensor class (8d-1): the
-    recurrent gate products 2 K 4H per (utterance, step), K = H for the plain layers, H + Dm for the attention layers,
-    forward and backward alike."""
-    B, H, A, Dm = args.batch, 256, 256, 256
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    f16_peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0)))
-    peak_src = 'MEASURED_PEAKS.json' if peaks else 'fallback of B200_PROFILING.md'
+def kernel_class_times(torch, ops, model, reps=3):
+    """The persistent kernels and the GEMM class, timed LIVE with CUDA events on their launching stream (in-library
+    timers, avsr_kernel_timing) over `reps` eager replays of the training step that was timed as a CUDA graph."""
     was_graph = model.use_cuda_graph
     model.use_cuda_graph = False
-    reps = 3
     model.train_step(fetch=False)
     torch.cuda.synchronize()
     ops.kernel_timing(True)
@@ -264,8 +299,26 @@ def persistent_kernel_rooflines(args, torch, ops, model, gate):
     kt = ops.kernel_times()
     ops.kernel_timing(False)
     model.use_cuda_graph = was_graph
-    ms = {k: v[0] / reps for k, v in kt.items()}
-    n = {k: v[1] // reps for k, v in kt.items()}
+    return ({k: v[0] / reps for k, v in kt.items()}, {k: v[1] // reps for k, v in kt.items()})
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch each of the cross-modal layer's forward and backward kernels
+# (ncu --set full, profiles/): the activations written for / read by the backward pass; the fp16 keys / values stay in L2
+MEASURED_DRAM_BYTES = {'parity': (1.921e9, 'profiles/r01_ncu_full_persist4.csv'),
+                       'default': (None, 'profiles/r02_ncu_full_persist4d.csv')}
+
+
+def attention_roofline(args, B, graph, ms, n, gate):
+    """Attention class (HBM): algorithmic bytes per (utterance, query step) = 4 Tm (A + Dm) + 4 (Tm + Dm + A)
+    (fp32 keys + values streamed once per step); the backward kernel sweeps both again.  Three readings of the same
+    time are given because the memories stay on chip (L2): streamed bytes (`frac`, the contract's definition), keys +
+    values once per utterance, and the DRAM bytes ncu measured.  Tensor class (8d-1): the recurrent gate products
+    2 K 4H per (utterance, step), K = H for the plain layers, H + Dm (+ the attention layer under dropout)."""
+    H, A, Dm = 256, 256, 256
+    peaks = load_peaks()
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    f16_peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 1590.0)))
+    peak_src = 'MEASURED_PEAKS.json' if peaks else 'fallback of B200_PROFILING.md'
 
     def att_bytes(Tm):
         return 4.0 * Tm * (A + Dm) + 4.0 * (Tm + Dm + A)
@@ -274,35 +327,45 @@ def persistent_kernel_rooflines(args, torch, ops, model, gate):
     once = sum(B * 4.0 * Tm * (A + Dm) for _, Tm in layers)              # keys + values read once per utterance
     t_att = ms['attn_lstm_fwd'] + ms['attn_lstm_bwd']
     ach = 2.0 * bytes_dir / (t_att * 1e-3) / 1e9 if t_att > 0 else 0.0
-    flop_attn = sum(B * T * 2.0 * (H + Dm) * 4 * H for T, _ in layers)   # per direction
+    ach_once = 2.0 * once / (t_att * 1e-3) / 1e9 if t_att > 0 else 0.0
+    dram, dram_src = MEASURED_DRAM_BYTES[graph]
+    k_att = (H + Dm + (H + Dm) * A / (4.0 * H)) if graph == 'default' else (H + Dm)  # + a_t = [ho|ctx] Wa under dropout
+    flop_attn = sum(B * T * 2.0 * k_att * 4 * H for T, _ in layers)      # per direction
     flop_lstm = B * (2 * 300 + 3 * 75) * 2.0 * H * 4 * H                 # audio layers 0-1 + three video layers
     t_rec = t_att + ms['lstm_fwd'] + ms['lstm_bwd']
     rec_tflops = 2.0 * (flop_attn + flop_lstm) / (t_rec * 1e-3) / 1e12 if t_rec > 0 else 0.0
+    steps_total = sum(T for T, _ in layers)
+    kname = 'ap4::attn_lstm_persist4d_{fwd,bwd}_kernel (two products per step: DropoutWrapper inside the AttentionWrapper)' \
+        if graph == 'default' else 'ap4::attn_lstm_persist4_{fwd,bwd}_kernel (attention layer folded into the recurrent matrix)'
     roof = {
         'bound': 'hbm', 'achieved': round(ach, 1), 'peak': hbm_peak, 'unit': 'GB/s',
         'frac': round(ach / hbm_peak, 4),
-        # dram__bytes_read.sum + dram__bytes_write.sum of the two launches of the cross-modal layer (forward 0.938 GB,
-        # backward 0.983 GB) in profiles/r01_ncu_full_persist4.csv: the activations written for / read by the backward
-        # pass.  The fp16 keys / values (19.7 MB per batch) stay in L2.
-        'traffic': 1.921e9,
-        'kernel': 'ap4::attn_lstm_persist4_{fwd,bwd}_kernel (cross-modal audio layer T=300/Tm=75 + decoder T=41/Tm=300)',
+        'traffic': dram,
+        'kernel': kname + ': cross-modal audio layer T=300/Tm=75 + decoder T=41/Tm=300',
+        'us_per_recurrent_step': {'fwd': round(ms['attn_lstm_fwd'] * 1e3 / steps_total, 3),
+                                  'bwd': round(ms['attn_lstm_bwd'] * 1e3 / steps_total, 3),
+                                  'note': 'summed kernel time / (300 + 41) steps: the layer is a latency chain '
+                                          '(exchange -> product -> gate math -> sweep -> product -> exchange)'},
         'ms_per_step': {'attn_lstm_fwd': round(ms['attn_lstm_fwd'], 4), 'attn_lstm_bwd': round(ms['attn_lstm_bwd'], 4)},
         'launches_per_step': n['attn_lstm_fwd'] + n['attn_lstm_bwd'],
         'algorithmic_bytes_per_step': int(2 * bytes_dir),
+        'frac_once_per_utterance': round(ach_once / hbm_peak, 5),
         'once_per_utterance_bytes_per_step': int(2 * once),
+        'frac_measured_dram': round(dram / (t_att * 1e-3) / 1e9 / hbm_peak, 4) if (dram and t_att > 0) else None,
+        'traffic_source': dram_src,
         'peak_source': f'hbm_gbs of {peak_src}',
-        'note': 'algorithmic bytes = keys + values streamed once per query step as fp32 (SURVEY.md 8d); the kernels read '
-                'fp16 copies (half of it) and the memories stay resident in the 126 MB L2, so the figure measures L2-fed '
-                'sweeps against the HBM peak: the layer is bound by the per-step latency chain exchange -> product -> '
-                'gate math -> sweep, not by DRAM (ncu: dram throughput 5 %, issue slots 37 %, tensor pipe 4 %)',
-        'timing': f'CUDA events around each launch on its stream, {reps} eager steps after the graph-timed loop',
+        'note': '`frac` follows the contract (SURVEY.md 8d: keys + values streamed once per query step as fp32) but the '
+                'kernels read fp16 copies that stay resident in the 126 MB L2, so it is an L2-fed figure against the HBM '
+                'peak; by DRAM bytes (frac_measured_dram) and by the once-per-utterance bound the kernel is far from the '
+                'HBM roof: it is latency bound (ncu: dram 5 %, issue slots 37 %, tensor pipe 3-4 %)',
+        'timing': 'CUDA events around each launch on its stream, 3 eager steps after the graph-timed loop',
     }
     tensor = {
         'bound': 'tensor', 'unit': 'TFLOP/s',
         'recurrent_products': {
             'achieved': round(rec_tflops, 2), 'peak': f16_peak, 'frac': round(rec_tflops / f16_peak, 5),
-            'kernels': 'lp4::lstm_persist4_{fwd,bwd}_kernel + ap4::attn_lstm_persist4_{fwd,bwd}_kernel (fp16 operands, '
-                       'fp32 accumulation in TMEM)',
+            'kernels': 'lp4::lstm_persist4_{fwd,bwd}_kernel + the attention-LSTM kernels above (fp16 operands, fp32 '
+                       'accumulation in TMEM)',
             'ms_per_step': {k: round(ms[k], 4) for k in ('lstm_fwd', 'lstm_bwd', 'attn_lstm_fwd', 'attn_lstm_bwd')},
             'flop_per_step': 2.0 * (flop_attn + flop_lstm),
             'peak_source': f'bf16 sustained of {peak_src}',
@@ -314,37 +377,62 @@ def persistent_kernel_rooflines(args, torch, ops, model, gate):
     return roof, tensor
 
 
-def default_graph_throughput(args, torch, ds_host, steps):
-    """The reference's DEFAULT training graph (avsr.py:49-56: DropoutWrapper keep 0.9 on input / state / output of
-    every cell, scheduled sampling 0.1) on the same workload.  Plain LSTM layers keep their persistent kernels (masks
-    regenerated in-kernel); the two attention layers run step-wise (a mask sits between the attention layer and the
-    recurrent matrix, so the folded recurrence of the persistent attention kernel does not apply)."""
+# ------------------------------------------------------------------------------------
+# one configuration, device-resident: inputs already in HBM, K graph replays between CUDA events
+# ------------------------------------------------------------------------------------
+def build_model(args, torch, cfg, B, graph, seed, pinned_u8=True):
     from avsr_tf1_b200.seq2seq import Seq2SeqModel
-    from tests.helpers import config_hparams
-    hp = config_hparams(5, attention_type=((args.attention,), (args.attention,)), use_dropout=True,
-                        sampling_probability_outputs=0.1)
-    model = Seq2SeqModel(ds_host, 'train', hp, seed=2001)
+    from tests.helpers import to_data_sequences
+    hp, batch, att = workload(args, cfg, B, seed=seed, graph=graph)
+    u8 = batch.pop('video_u8', None)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in batch.items()}
+    ds_float = to_data_sequences(pinned)
+    ds_host = ds_float
+    if u8 is not None and pinned_u8:  # the e2e loop ships the crops as stored pixels (a quarter of the bytes)
+        p8 = dict(pinned)
+        p8['video'] = torch.from_numpy(u8).pin_memory()
+        ds_host = to_data_sequences(p8)
+    model = Seq2SeqModel(ds_float, 'train', hp, seed=2001)
     model.use_cuda_graph = not args.no_graph
-    model.feed(ds_host)
-    for _ in range(3):
+    model.overlap_streams = bool(args.overlap)
+    return model, ds_host, att
+
+
+def timed_steps(torch, model, steps, warmup, barrier=None):
+    for _ in range(max(3, warmup)):
         model.train_step(fetch=False)
-    torch.cuda.synchronize()
+    (barrier or torch.cuda.synchronize)()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         model.train_step(fetch=False)
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    loss, gnorm = model.fetch_scalars()
-    return {'value': round(args.batch / (ms / 1e3), 2), 'unit': UNIT, 'ms_per_step': round(ms, 4), 'steps': steps,
-            'gpu_launches_per_step': int(model.launches_last_step), 'loss': round(float(loss), 6),
-            'config': 'same workload with use_dropout=True (keep 0.9/0.9/0.9 on every cell) and '
-                      'sampling_probability_outputs=0.1: the reference defaults; masks and draws from the '
-                      'counter-based generator (include/avsr_b200.h avsr_dropout / avsr_sched_sample)'}
+    (barrier or torch.cuda.synchronize)()
+    return e0.elapsed_time(e1)
 
 
-def tfrecord_e2e(args, torch, model, n_utt):
+def side_config(args, torch, ops, cfg, graph, steps):
+    """BASELINE config `cfg` at its own batch on one GPU: utterances/s + the kernel classes of its step."""
+    B = CONFIGS[cfg]['batch']
+    model, ds_host, att = build_model(args, torch, cfg, B, graph, seed=0)
+    model.feed(ds_host)
+    ms = timed_steps(torch, model, steps, 3) / steps
+    launches = int(model.launches_last_step)
+    loss, _ = model.fetch_scalars()
+    kms, kn = kernel_class_times(torch, ops, model, reps=2)
+    persistent = kms['attn_lstm_fwd'] + kms['attn_lstm_bwd'] + kms['lstm_fwd'] + kms['lstm_bwd']
+    out = {'value': round(B / (ms / 1e3), 2), 'unit': UNIT, 'ms_per_step': round(ms, 4), 'per_gpu_batch': B,
+           'gpu_launches_per_step': launches, 'loss': round(float(loss), 6), 'attention': att,
+           'workload': CONFIGS[cfg]['what'], 'graph': graph,
+           'kernel_ms_per_step': {k: round(v, 4) for k, v in kms.items()},
+           'kernel_launches_per_step': kn,
+           'persistent_kernel_share': round(persistent / ms, 3) if ms > 0 else None}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def tfrecord_e2e(args, torch, model, n_utt, B):
     """the same training step fed from synthetic TFRecords in the reference's schema (8d) through
     the native reader (include/avsr_io.h) - shuffle, bucket, padded batch into pinned memory on a prefetch thread -
     instead of one resident pinned batch."""
@@ -360,7 +448,7 @@ def tfrecord_e2e(args, torch, model, n_utt):
         t_write = time.perf_counter() - t0
         cores = max(1, min(16, (os.cpu_count() or 4) - 1))
         it = io_utils.make_iterator_from_two_records(
-            paths['video'], paths['audio'], paths['labels'], batch_size=args.batch,
+            paths['video'], paths['audio'], paths['labels'], batch_size=B,
             unit_dict=model._hparams.unit_dict, shuffle=True, bucket_width=45, num_cores=cores, prefetch=3)
         bytes_on_disk = sum(os.path.getsize(p) for p in paths.values())
 
@@ -416,7 +504,8 @@ def cer_check(args, torch, ops):
     from tests.helpers import cast_batch, config_hparams, oracle_hparams, synthetic_batch, to_data_sequences
     old = ops.set_tensor_cores(False)
     try:
-        hp = config_hparams(5, attention_type=((args.attention,), (args.attention,)), decoding_algorithm='greedy')
+        att = args.attention or 'scaled_luong'
+        hp = config_hparams(5, attention_type=((att,), (att,)), decoding_algorithm='greedy')
         hp.max_label_length = 12
         # (the configuration of tests/test_gpu_model.py::test_decoding_and_error_rates[5-greedy])
         batch = synthetic_batch(hp, B=3, Ta=30, Tv=10, L=6, ragged=True)
@@ -480,16 +569,11 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
     from avsr_tf1_b200 import ops
-    from avsr_tf1_b200.seq2seq import Seq2SeqModel
-    from tests.helpers import to_data_sequences
 
     ops.set_tensor_cores(not args.no_tensor_cores)
-    hp, batch = workload(args, args.batch, seed=rank)
-    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in batch.items()}
-    ds_host = to_data_sequences(pinned)
-    model = Seq2SeqModel(ds_host, 'train', hp, seed=2001)
-    model.use_cuda_graph = not args.no_graph
-    model.overlap_streams = bool(args.overlap)
+    cfg, graph = args.config, args.graph
+    B1 = args.batch or CONFIGS[cfg]['batch']           # per-GPU batch at N = 1
+    B = B1 if args.scaling == 'weak' else max(1, B1 // world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -504,28 +588,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    model, ds_host, att = build_model(args, torch, cfg, B, graph, seed=rank)
+
     # ---- device-resident timing: inputs already in HBM ------------------------------------
     model.feed(ds_host)
-    for _ in range(max(3, args.warmup)):
-        model.train_step(fetch=False)
-    barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        model.train_step(fetch=False)
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_total = max_over_ranks(timed_steps(torch, model, args.steps, args.warmup, barrier))
     launches = model.launches_last_step
     loss, gnorm = model.fetch_scalars()
 
     # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, every step ---------------
     # The H2D copy of step k+1's batch is issued (copy stream) right after step k is launched, so it overlaps
     # the compute of step k - the input-pipeline prefetch the reference gets from tf.data (io_utils.py:145).
-    # Every step still copies its full batch from pinned host memory and reads its loss back (the read of step k is
-    # waited for after step k+1 has been launched, so the host round trip is off the GPU's critical path).
+    # Every step still copies its full batch from pinned host memory (lip crops as the stored uint8 pixels, expanded
+    # to the reference's floats on the device) and reads its loss back (the read of step k is waited for after step
+    # k+1 has been launched, so the host round trip is off the GPU's critical path).
     for _ in range(2):
         model.train_step(ds_host, fetch=True)
     barrier()
@@ -552,6 +630,24 @@ def main():
     h2d = model.h2d_bytes
     d2h = int(model._loss_dev.numel() * 4)
 
+    # ---- N > 1: the other scaling mode beside the headline (global batch 256 at 1/2/4/8 GPUs) ----
+    other = None
+    if world > 1 and not args.skip_extras:
+        try:
+            Bo = max(1, B1 // world) if args.scaling == 'weak' else B1
+            del model
+            torch.cuda.empty_cache()
+            model, ds_o, _ = build_model(args, torch, cfg, Bo, graph, seed=rank)
+            model.feed(ds_o)
+            ms_o = max_over_ranks(timed_steps(torch, model, args.steps, args.warmup, barrier)) / args.steps
+            other = {'scaling': 'strong' if args.scaling == 'weak' else 'weak', 'per_gpu_batch': Bo,
+                     'global_batch': Bo * world, 'ms_per_step': round(ms_o, 4),
+                     'value': round(Bo * world / (ms_o / 1e3), 2), 'unit': UNIT,
+                     'note': 'device-timed like `value`; strong scaling of a latency-bound recurrence: the step time barely '
+                             'falls with the per-GPU batch (one wave of 8-utterance clusters either way)'}
+        except Exception as ex:
+            other = {'error': repr(ex)}
+
     def finish():
         # captured graphs hold NCCL work; tearing the process group down under them can hang, so leave hard
         sys.stdout.flush()
@@ -566,49 +662,66 @@ def main():
         return
 
     ms_step = ms_total / args.steps
-    value = args.batch * world / (ms_step / 1e3)
+    value = B * world / (ms_step / 1e3)
     e2e_step = e2e_ms / args.steps
     line = {
-        'metric': METRIC, 'value': round(value, 2), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'metric': METRICS[cfg], 'value': round(value, 2), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(3, args.warmup), 'ms_per_step': round(ms_step, 4), 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None,
+        'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'f32' if args.no_tensor_cores else 'f32 storage/accumulate, tf32 tensor-core products',
-        'data': 'synthetic', 'config': config_dict(args, world),
+        'data': 'synthetic', 'config': config_dict(args, cfg, B, world, att, graph, args.scaling),
         'clocks': sampler.summary(),
-        'e2e': {'value': round(args.batch * world / (e2e_step / 1e3), 2), 'unit': UNIT, 'ms_per_step': round(e2e_step, 4),
+        'e2e': {'value': round(B * world / (e2e_step / 1e3), 2), 'unit': UNIT, 'ms_per_step': round(e2e_step, 4),
                 'wall_ms_per_step': round(e2e_wall / args.steps, 4), 'h2d_bytes_per_step': int(h2d),
                 'd2h_bytes_per_step': d2h},
         'gpu_launches': int(launches * args.steps),
         'gpu_launches_per_step': int(launches),
-        'cuda_graph': bool(model.use_cuda_graph),
+        'cuda_graph': not args.no_graph,
         'loss': round(float(loss), 6), 'global_norm': round(float(gnorm), 6), 'n_params': int(model.n_params),
     }
+    if other is not None:
+        line['strong_scaling' if args.scaling == 'weak' else 'weak_scaling'] = other
     try:
-        if args.skip_roofline or world > 1:
+        if args.skip_roofline or world > 1 or cfg != 5:
             line['roofline'] = None
         else:
-            gate = gate_gemm_roofline(args, torch, ops)
-            line['roofline'], line['roofline_tensor'] = persistent_kernel_rooflines(args, torch, ops, model, gate)
+            gate = gate_gemm_roofline(args, torch, ops, B)
+            kms, kn = kernel_class_times(torch, ops, model)
+            line['roofline'], line['roofline_tensor'] = attention_roofline(args, B, graph, kms, kn, gate)
     except Exception as ex:  # keep the headline number even if the side measurement fails
         line['roofline'] = {'error': repr(ex)}
     if world == 1 and not args.skip_extras:
-        try:
-            line['reference_default_graph'] = default_graph_throughput(args, torch, ds_host, max(2, min(args.steps, 5)))
-        except Exception as ex:
-            line['reference_default_graph'] = {'error': repr(ex)}
-        try:
-            line['e2e_tfrecord'] = tfrecord_e2e(args, torch, model, args.tfrecord_utterances)
-        except Exception as ex:
-            line['e2e_tfrecord'] = {'error': repr(ex)}
+        if cfg == 5:
+            try:
+                line['e2e_tfrecord'] = tfrecord_e2e(args, torch, model, args.tfrecord_utterances, B)
+            except Exception as ex:
+                line['e2e_tfrecord'] = {'error': repr(ex)}
+        del model
+        torch.cuda.empty_cache()
+        side_steps = max(2, min(args.steps, 5))
+        if graph == 'default':  # the same workload with the randomness off: the graph the parity tests check
+            try:
+                line['parity_graph'] = side_config(args, torch, ops, cfg, 'parity', side_steps)
+            except Exception as ex:
+                line['parity_graph'] = {'error': repr(ex)}
+        line['configs'] = {}
+        for c in sorted(CONFIGS):  # the other BASELINE.json configurations, each at its own batch, same graph
+            if c == cfg:
+                continue
+            try:
+                line['configs'][str(c)] = side_config(args, torch, ops, c, graph, side_steps)
+            except Exception as ex:
+                line['configs'][str(c)] = {'error': repr(ex)}
     if world == 1 and not args.skip_cpu_baseline:
-        r = run_oracle(args, steps=3, warmup=1, sample=args.cpu_sample)
+        r = run_oracle(args, cfg, graph, steps=3, warmup=1, sample=min(args.cpu_sample, B))
         line['cpu_baseline'] = {
             'value': round(r['value'], 3), 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
-            'sample': f'{r["sample"]} utterances per step of the same workload at full sequence lengths, 3 timed '
+            'sample': f'{r["sample"]} utterances per step of the same workload and graph at full sequence lengths, 3 timed '
                       'steps (about 10 s of host work); NumPy/OpenBLAS restatement of the TF1 graph (oracle/)'}
         try:  # in a child process: nothing it does can cost the parent its JSON line
-            child = subprocess.run([sys.executable, os.path.abspath(__file__), '--cer-check-only', '--attention',
-                                    args.attention], capture_output=True, text=True, timeout=300)
+            child = subprocess.run([sys.executable, os.path.abspath(__file__), '--cer-check-only'] +
+                                   (['--attention', args.attention] if args.attention else []),
+                                   capture_output=True, text=True, timeout=300)
             out_lines = [ln for ln in child.stdout.strip().splitlines() if ln.startswith('{')]
             line['cpu_baseline']['cer_check'] = json.loads(out_lines[-1]) if out_lines else {
                 'error': 'exit %d: %s' % (child.returncode, child.stderr.strip()[-300:])}

@@ -97,6 +97,11 @@ int avsr_reverse_sequence(avsr_stream_t stream, const float* x, float* y, int T,
  * device tensors frame-major) */
 int avsr_transpose01(avsr_stream_t stream, const float* x, float* y, int d0, int d1, int F);
 
+/* lip crops as stored pixels: y[i] = (x[i] + shift) * scale.  dataset_writer.py:537 writes (v - 128) / 128 of uint8 pixels
+ * into the records; a host batch that keeps the bytes crosses PCIe at a quarter of the size and is expanded here (exact:
+ * every k / 128 is representable).  Buffers 16-byte aligned. */
+int avsr_u8_to_f32(avsr_stream_t stream, const uint8_t* x, long long n, float scale, float shift, float* y);
+
 /* ---- recurrent sequence op --------------------------------------------------
  * One call = one tf.nn.dynamic_rnn / seq2seq.dynamic_decode loop over an LSTMCell
  * (cells.py:14-18: gate order i,j,f,o, forget bias 1, cell_clip 1), optionally

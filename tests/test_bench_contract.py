@@ -1,48 +1,47 @@
-"""The JSON line bench.py printed on the B200 (committed under profiles/) carries every key of the measurement contract,
-for both arms, and the numbers are mutually consistent."""
+"""bench.py's measurement contract, exercised for real on the CPU arm (the GPU arm needs a B200): the reference arm
+of the smallest BASELINE configuration runs in a child process launched the way torchrun launches workers
+(OMP_NUM_THREADS=1) and must print ONE JSON line carrying the keys the driver reads, on the same graph and
+configuration names the product arm reports, using more than the one thread the launcher allowed."""
 import json
 import os
+import subprocess
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def load(name):
-    with open(os.path.join(ROOT, 'profiles', name)) as f:
-        return json.loads(f.read().strip().splitlines()[-1])
+def run_reference(*extra):
+    env = dict(os.environ, OMP_NUM_THREADS='1')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--config', '1',
+                          '--steps', '2', '--warmup', '1', '--cpu-sample', '2', *extra],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines  # exactly one JSON line
+    return json.loads(lines[0])
 
 
-def test_b200_arm_line():
-    l = load('r01_bench_v23_final.json')
-    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
-              'vs_baseline', 'dtype', 'data', 'config', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
-        assert k in l, k
-    assert l['metric'].startswith('AV-Align train utterances/sec') and l['unit'] == 'utterances/s'
-    assert l['n_gpus'] == 1 and l['warmup'] >= 3 and l['higher_is_better'] is True and l['scaling'] == 'weak'
-    assert l['vs_baseline'] is None and l['data'] == 'synthetic' and 'workload' in l['config']
-    assert 'model' not in l['config']
-    # value = utterances processed / device time
-    assert abs(l['value'] - l['config']['global_batch'] / (l['ms_per_step'] / 1e3)) <= 1e-3 * l['value']
-    e = l['e2e']
-    assert e['unit'] == l['unit'] and e['h2d_bytes_per_step'] > 3e8 and e['d2h_bytes_per_step'] > 0
-    assert 0.5 * l['value'] < e['value'] < l['value']  # end to end is measured, not copied
-    assert l['gpu_launches'] == l['gpu_launches_per_step'] * l['steps'] > 0
-    c = l['clocks']
-    assert c['sm_mhz'] > 0.9 * c['sm_max_mhz'] and not set(c['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown',
-                                                                           'sw_thermal_slowdown'}
-    r = l['roofline']
-    assert r['bound'] in ('hbm', 'tensor') and r['unit'] in ('GB/s', 'TFLOP/s')
-    assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-3 and r['traffic'] is not None
-    b = l['cpu_baseline']
-    assert b['kind'] in ('port', 'reference') and b['cores'] >= 1 and b['unit'] == l['unit'] and b['sample']
-    assert l['value'] > 1000 * b['value']
+def test_reference_arm_line_default_graph():
+    d = run_reference()
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+              'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['unit'] == 'utterances/s' and d['higher_is_better'] is True
+    assert d['steps'] == 2 and d['warmup'] == 1  # the arm runs the K / W it was given (no clamping)
+    assert d['value'] > 0 and abs(d['value'] - d['cpu_baseline']['value']) < 1e-9
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert d['cpu_baseline']['kind'] == 'port'
+    assert d['cpu_baseline']['cores'] == len(os.sched_getaffinity(0))  # the launcher's OMP_NUM_THREADS=1 is overridden
+    assert 'configs[0]' in d['config']['workload']
+    assert d['config']['dropout'].startswith('DropoutWrapper') and d['config']['scheduled_sampling'].startswith('0.1')
+    assert abs(d['ms_per_step'] * d['value'] / 1e3 - 2.0) < 1e-6  # 2 utterances per step
 
 
-def test_reference_arm_line():
-    l = load('r01_bench_v23_reference_arm.json')
-    assert l['impl'] == 'reference'
-    b200 = load('r01_bench_v23_final.json')
-    for k in ('metric', 'unit', 'higher_is_better'):
-        assert l[k] == b200[k]
-    assert l['config']['workload'] == b200['config']['workload']
-    assert l['e2e'] == {'value': l['value'], 'unit': l['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
-    assert l['cpu_baseline']['value'] == l['value'] and l['cpu_baseline']['kind'] == 'port'
+def test_reference_arm_parity_graph_and_nonzero_rank():
+    d = run_reference('--graph', 'parity')
+    assert d['config']['dropout'] == 'off' and d['config']['scheduled_sampling'] == 'off'
+    # under torchrun only rank 0 runs the CPU arm; the other ranks exit 0 without output
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--config', '1',
+                          '--gpus', '2'], capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == ''

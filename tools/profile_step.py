@@ -16,12 +16,14 @@ from tests.helpers import to_data_sequences  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--batch', type=int, default=256)
 ap.add_argument('--video-input', default='crops3888')
-ap.add_argument('--attention', default='scaled_luong')
+ap.add_argument('--attention', default=None)
+ap.add_argument('--graph', default='default', choices=['default', 'parity'])
 ap.add_argument('--no-tensor-cores', action='store_true')
 ap.add_argument('--graph', action='store_true')
 args = ap.parse_args()
 ops.set_tensor_cores(not args.no_tensor_cores)
-hp, batch = bench.workload(args, args.batch, seed=0)
+hp, batch, _ = bench.workload(args, 5, args.batch, seed=0, graph=args.graph)
+batch.pop('video_u8', None)
 ds = to_data_sequences(batch)
 model = Seq2SeqModel(ds, 'train', hp, seed=2001)
 model.use_cuda_graph = args.graph
