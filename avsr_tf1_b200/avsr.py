@@ -132,14 +132,19 @@ class AVSR(object):
         tm = self._train_model
         last_epoch = 0
         if try_restore_latest_checkpoint is True:
+            # avsr.py:241-249 swallows every restore error and trains from scratch; here only "there is no checkpoint"
+            # does that - a checkpoint that exists but cannot be loaded is an error, not a silent restart at epoch 0
+            latest_ckp = None
             try:
                 latest_ckp = latest_checkpoint(checkpoint_dir)
+            except Exception:
+                latest_ckp = None
+            if latest_ckp is None:
+                self._say('Could not restore from checkpoint, training from scratch!\n')
+            else:
                 last_epoch = int(latest_ckp.split('-')[-1])
                 tm.model.saver.restore(sess=None, save_path=latest_ckp)
                 self._say('Restoring checkpoint from epoch {}\n'.format(last_epoch))
-            except Exception:
-                last_epoch = 0
-                self._say('Could not restore from checkpoint, training from scratch!\n')
         self.last_error_rate = None
         with open(logfile if parallel.rank() == 0 else devnull, 'a') as f:
             for current_epoch in range(1, num_epochs):

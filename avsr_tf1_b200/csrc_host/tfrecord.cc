@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -25,15 +26,23 @@
 
 namespace {
 
+// Error text of the last failing call of THIS thread.  Worker threads of a call record into their own thread-local
+// buffer; the calling thread collects the first worker message under a mutex (collect_worker_error) so that
+// avsr_io_last_error never returns a stale message of an earlier call or a torn one.
 thread_local char g_err[512] = "";
-char g_err_shared[512] = "";
+std::mutex g_err_mutex;
 int fail(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
-  memcpy(g_err_shared, g_err, sizeof(g_err));
   return 1;
+}
+void clear_error() { g_err[0] = 0; }
+// called by a worker thread after a failing step: keeps the first message of the call in `first`
+void collect_worker_error(char (&first)[512]) {
+  std::lock_guard<std::mutex> lock(g_err_mutex);
+  if (!first[0]) memcpy(first, g_err, sizeof(g_err));
 }
 
 // ---- crc32c ---------------------------------------------------------------------------------------
@@ -339,11 +348,12 @@ struct AvsrIoWriter {
 
 extern "C" {
 
-const char* avsr_io_last_error(void) { return g_err[0] ? g_err : g_err_shared; }
+const char* avsr_io_last_error(void) { return g_err; }
 uint32_t avsr_io_crc32c(const void* data, size_t n) { return crc32c(data, n); }
 uint32_t avsr_io_masked_crc32c(const void* data, size_t n) { return mask_crc(crc32c(data, n)); }
 
 int avsr_io_open(const char* path, int verify_data, AvsrIoFile** out) {
+  clear_error();
   *out = nullptr;
   AvsrIoFile* f = new AvsrIoFile();
   f->fd = open(path, O_RDONLY);
@@ -452,6 +462,7 @@ int avsr_io_lengths(AvsrIoFile* f, long long* lengths) {
 }
 
 int avsr_io_filename(AvsrIoFile* f, long long idx, char* dst, int cap) {
+  clear_error();
   if (idx < 0 || idx >= f->info.n_records || cap <= 0) return fail("filename: record %lld out of range", idx);
   Example ex;
   Span feat, name;
@@ -504,17 +515,21 @@ static int fill_one_input(const AvsrIoFile* f, long long idx, int t_pad, float* 
 
 int avsr_io_fill_inputs(AvsrIoFile* f, const long long* idx, int n, int t_pad, float* dst, float* aus_dst,
                         int32_t* lens, int reverse, int n_threads) {
+  clear_error();
   if (f->info.kind == AVSR_IO_LABELS) return fail("fill_inputs on a label record");
   if (aus_dst && !f->info.has_aus) return fail("this record has no Action Units");
   for (int i = 0; i < n; ++i)
     if (idx[i] < 0 || idx[i] >= f->info.n_records) return fail("fill_inputs: record %lld out of range", idx[i]);
   const size_t feat = (size_t)f->info.feat;
   std::atomic<int> next(0), failed(0);
+  char first_error[512] = "";
   auto work = [&]() {
     for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
       if (fill_one_input(f, idx[i], t_pad, dst + (size_t)i * t_pad * feat,
-                         aus_dst ? aus_dst + (size_t)i * t_pad * 2 : nullptr, lens + i, reverse))
+                         aus_dst ? aus_dst + (size_t)i * t_pad * 2 : nullptr, lens + i, reverse)) {
         failed.store(1);
+        collect_worker_error(first_error);  // the message lives in the worker's thread-local buffer
+      }
     }
   };
   const int nt = std::max(1, std::min(n_threads, n));
@@ -525,11 +540,16 @@ int avsr_io_fill_inputs(AvsrIoFile* f, const long long* idx, int n, int t_pad, f
     for (int k = 0; k < nt; ++k) pool.emplace_back(work);
     for (auto& t : pool) t.join();
   }
-  return failed.load() ? 1 : 0;
+  if (failed.load()) {
+    memcpy(g_err, first_error, sizeof(g_err));  // into the CALLER's buffer, which avsr_io_last_error reads
+    return 1;
+  }
+  return 0;
 }
 
 int avsr_io_fill_labels(AvsrIoFile* f, const long long* idx, int n, int l_pad, int32_t eos, int32_t* dst,
                         int32_t* lens) {
+  clear_error();
   if (f->info.kind != AVSR_IO_LABELS) return fail("fill_labels on an input record");
   for (int i = 0; i < n; ++i) {
     if (idx[i] < 0 || idx[i] >= f->info.n_records) return fail("fill_labels: record %lld out of range", idx[i]);
@@ -560,6 +580,7 @@ int avsr_io_fill_labels(AvsrIoFile* f, const long long* idx, int n, int l_pad, i
 
 // ---- writer ------------------------------------------------------------------------------------------
 int avsr_io_writer_open(const char* path, AvsrIoWriter** out) {
+  clear_error();
   *out = nullptr;
   FILE* fp = fopen(path, "wb");
   if (!fp) return fail("cannot create %s", path);

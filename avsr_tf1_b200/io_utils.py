@@ -40,25 +40,49 @@ class OutOfRangeError(Exception):
 
 
 class _HostRing(object):
-    """Page-locked staging buffers, reused round-robin per shape (cudaHostAlloc of a 300 MB batch costs more than
-    decoding it).  A buffer is handed out again `depth` batches later: the consumer must have finished its
-    host-to-device copy by then (the training loop reads the loss back every step, which synchronises)."""
+    """Page-locked staging memory for the batches in flight: `depth` flat buffers per role (a role = one field of a
+    batch, e.g. the features of stream 0), handed out round-robin as views of the requested shape.  A buffer is as
+    large as the largest batch of its role seen so far (grown geometrically), so an epoch of bucketed batches with
+    hundreds of distinct padded lengths pins depth x roles buffers, not one set per shape (cudaHostAlloc of a 300 MB
+    batch costs more than decoding it, and pinned memory is never swapped).  A view is handed out again `depth` batches
+    later: the consumer must have finished its host-to-device copy by then (the training loop reads the loss back every
+    step, which synchronises)."""
 
     def __init__(self, pin, depth):
-        self._pin, self._depth, self._slots = pin, max(2, int(depth)), {}
+        self._pin, self._depth, self._rings = pin, max(2, int(depth)), {}
 
-    def get(self, shape, dtype):
+    def get(self, role, shape, dtype):
         import torch
-        key = (tuple(shape), dtype)
-        ring = self._slots.setdefault(key, [[], 0])
-        if len(ring[0]) < self._depth:
-            t = torch.empty(shape, dtype=dtype)
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        ring = self._rings.setdefault(role, [[None] * self._depth, 0])
+        i = ring[1]                       # slots are used in order 0, 1, ..., depth-1, 0, ...: reuse distance = depth
+        ring[1] = (i + 1) % self._depth
+        buf = ring[0][i]
+        if buf is None or buf.numel() < nbytes:
+            cap = nbytes if buf is None else max(nbytes, buf.numel() + buf.numel() // 2)
+            buf = torch.empty(max(cap, 16), dtype=torch.uint8)
             if self._pin and torch.cuda.is_available():
-                t = t.pin_memory()
-            ring[0].append(t)
-            return t
-        ring[1] = (ring[1] + 1) % self._depth
-        return ring[0][ring[1]]
+                buf = buf.pin_memory()
+            ring[0][i] = buf              # (a view of the replaced buffer that is still in use keeps it alive)
+        return buf[:nbytes].view(dtype).view(tuple(shape))
+
+    def pinned_bytes(self):
+        return sum(b.numel() for ring in self._rings.values() for b in ring[0] if b is not None)
+
+
+class _Shard(np.ndarray):
+    """This rank's slice of a global batch (an index array) that remembers the global batch: every rank pads its input
+    streams to the GLOBAL batch's longest sequence and reports the global batch size, so the all-reduced batch-norm
+    sums of the ranks are sums over identically shaped slices of one batch (N ranks == one rank with the whole batch,
+    also when the batch does not divide evenly)."""
+
+    def __new__(cls, idx, global_idx):
+        obj = np.asarray(idx, np.int64).view(cls)
+        obj.global_idx = np.asarray(global_idx, np.int64)
+        return obj
+
+    def __array_finalize__(self, obj):
+        self.global_idx = getattr(obj, 'global_idx', None)
 
 
 class RecordBatcher(object):
@@ -136,7 +160,7 @@ class RecordBatcher(object):
             if len(idx) < w:
                 continue
             lo, hi = shard_batch(len(idx), r, w)
-            out.append(idx[lo:hi])
+            out.append(_Shard(idx[lo:hi], idx))
         return out
 
     def _global_batches(self):
@@ -159,12 +183,15 @@ class RecordBatcher(object):
     def _assemble(self, idx):
         import torch
         n = len(idx)
+        gidx = getattr(idx, 'global_idx', None)
+        gidx = idx if gidx is None else gidx
+        idx = np.asarray(idx, np.int64)
         streams = []
         for k, f in enumerate(self._inputs):
-            t_pad = int(f.lengths[idx].max())
-            x = self._ring.get((n, t_pad, f.feat), torch.float32)
+            t_pad = int(f.lengths[gidx].max())
+            x = self._ring.get(('x', k), (n, t_pad, f.feat), torch.float32)
             lens = torch.empty(n, dtype=torch.int32)
-            aus = self._ring.get((n, t_pad, 2), torch.float32) if (k == 0 and f.has_aus) else None
+            aus = self._ring.get(('aus', k), (n, t_pad, 2), torch.float32) if (k == 0 and f.has_aus) else None
             f.fill_inputs(idx, t_pad, x, lens, aus_dst=aus, reverse=self.reverse_input and len(self._inputs) == 1,
                           n_threads=self.num_cores)
             if len(f.input_shape) == 3:
@@ -176,7 +203,7 @@ class RecordBatcher(object):
         lab_len = torch.empty(n, dtype=torch.int32)
         self._labels.fill_labels(idx, l_pad, self._eos, labels, lab_len)
         lab_names = np.array([self._labels.filename(i) for i in idx], dtype=object)
-        return streams, labels, lab_len, lab_names
+        return streams, labels, lab_len, lab_names, int(len(gidx))
 
     def _producer(self, batches, q, stop):
         try:
@@ -221,6 +248,7 @@ class RecordBatcher(object):
         if self._queue is not None:
             item = self._queue.get()
             if isinstance(item, BaseException):
+                self._current, self._exhausted = None, True  # the producer thread is gone: never block on its queue again
                 raise item
         else:
             idx = next(self._pending, None)
@@ -274,13 +302,16 @@ class RecordBatcher(object):
         """(video BatchedData | None, audio BatchedData | None) of the current batch - what avsr.py:566-570 hands to
         Seq2SeqModel (_parse_iterator / _parse_multimodal_iterator, avsr.py:573-626)."""
         from .tfrecord import KIND_VIDEO
-        streams, labels, lab_len, lab_names = self._cur()
+        streams, labels, lab_len, lab_names, global_b = self._cur()
+        # under data parallelism (no counterpart in the reference) the shard also names the size of its global batch
+        extra = {'global_batch_size': global_b} if self._shard is not None else {}
         out = [None, None]
         for f, (x, lens, names, aus) in zip(self._inputs, streams):
             slot = 0 if (f.kind == KIND_VIDEO or (len(streams) == 2 and f is self._inputs[0])) else 1
             out[slot] = BatchedData(iterator_initializer=self.iterator_initializer, inputs=x, inputs_length=lens,
                                     inputs_filenames=names, labels=labels, labels_length=lab_len,
-                                    labels_filenames=lab_names, payload={'aus': aus} if aus is not None else {})
+                                    labels_filenames=lab_names,
+                                    payload=dict({'aus': aus} if aus is not None else {}, **extra))
         return tuple(out)
 
 

@@ -21,6 +21,11 @@ class BuildContext:
         self.specs: List[ParamSpec] = []
         self.store = None
         self.world_size = 1
+        # global batch / this rank's batch: batch-norm statistics are all-reduced SUMS over the global batch, so their
+        # row count is rows_local * batch_scale.  Ranks may hold unequal shares of a global batch (a batch that does not
+        # divide evenly); Seq2SeqModel sets the exact ratio per batch when the iterator reports the global batch size,
+        # else it is world_size (equal shares).  All ranks must pad a stream to the same length (RecordBatcher does).
+        self.batch_scale = 1.0
         self.grad_scale = 1.0  # power of two ~ number of target tokens (set per step by Seq2SeqModel)
         self.allreduce = None  # callable(tensor) -> None (in-place sum), set by Seq2SeqModel under DP
         self.rng = None  # device int32[2] {seed, step}: counter-based generator of dropout / scheduled sampling
@@ -119,7 +124,7 @@ class BatchNormInput:
         count = float(T * B)
         if ctx.world_size > 1:  # exact large-batch statistics under data parallelism
             ctx.allreduce(sums)
-            count *= ctx.world_size
+            count *= ctx.batch_scale
         self.xhat = ops.empty(T, B, F) if keep_xhat else None
         self.invstd = ops.empty(F)
         self.count = count

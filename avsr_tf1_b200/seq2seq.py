@@ -78,7 +78,14 @@ class Saver(object):
             blob.update({'adam_m/' + k: v for k, v in st.to_numpy('m').items()})
             blob.update({'adam_v/' + k: v for k, v in st.to_numpy('v').items()})
         blob['global_step'] = np.asarray(self._model._global_step, np.int64)
-        np.savez(path + '.npz', **blob)
+        # written next to the target and renamed into place: a crash mid-save never leaves a truncated file as the
+        # newest checkpoint (tf.train.Saver writes to a temporary name too); the old one is removed only afterwards
+        tmp = path + '.tmp.npz'
+        with open(tmp, 'wb') as fh:
+            np.savez(fh, **blob)
+            fh.flush()
+            os.fsync(fh.fileno())
+        os.replace(tmp, path + '.npz')
         if path not in self._kept:
             self._kept.append(path)
         while self._max_to_keep and len(self._kept) > self._max_to_keep:
@@ -284,7 +291,12 @@ class Seq2SeqModel(object):
             meta['n_tokens'] = float(lab_len_host.sum())
             src['labels'] = self._as_tensor(ref.labels, torch.int32)
             src['labels_len'] = self._as_tensor(ll, torch.int32)
-        key = tuple((k, tuple(v.shape)) for k, v in sorted(src.items())) + (meta.get('T_dec', 0),)
+        # data parallelism: the iterator reports the size of the GLOBAL batch this shard was cut from (payload
+        # 'global_batch_size'); without it every rank is taken to hold an equal share
+        gb = (ref.payload or {}).get('global_batch_size') if ref.payload is not None else None
+        local_b = int(src[('audio' if audio is not None else 'video') + '_len'].shape[0])
+        meta['batch_scale'] = float(gb) / local_b if gb else float(self._ctx.world_size)
+        key = tuple((k, tuple(v.shape)) for k, v in sorted(src.items())) + (meta.get('T_dec', 0), meta['batch_scale'])
         meta['key'] = key
         meta['h2d_bytes'] = sum(v.numel() * v.element_size() for v in src.values() if not v.is_cuda)
         return src, meta
@@ -452,6 +464,7 @@ class Seq2SeqModel(object):
         """Forward + backward on the prepared batch.  Leaves the local gradient sums in store.grad and
         the cross-entropy SUM in _loss_dev[0] (normalised by the device scalar inv_denom)."""
         b = self._batch if self._batch is not None else self._prep()
+        self._ctx.batch_scale = self._meta.get('batch_scale', float(self._ctx.world_size))
         self.store.grad.zero_()
         self._loss_dev.zero_()
         if self._ctx.world_size > 1:

@@ -115,7 +115,7 @@ class _BatchNormRelu(object):
         count = float(x2.shape[0])
         if ctx.world_size > 1:
             ctx.allreduce(sums)
-            count *= ctx.world_size
+            count *= ctx.batch_scale  # rows of the GLOBAL batch (layers.BuildContext.batch_scale)
         self.xhat, self.invstd, self.count = torch.empty_like(x2), ops.empty(C), count
         ops.bn_apply_train(x2, sums, count, ctx.p(self.gamma), ctx.p(self.beta), BN_EPS, BN_MOMENTUM, y.view(-1, C),
                            self.xhat, self.invstd, ctx.p(self.mm), ctx.p(self.mv))

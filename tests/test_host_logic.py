@@ -181,3 +181,59 @@ def test_resnet_cnn_variable_table():
     assert 'CNN/res_block_0_first_bn/gamma' not in names and 'CNN/res_block_0_shortcut/kernel' not in names
     assert m.store.table['CNN/flatten/kernel'][1] == (5, 5, 64, 128)  # 36 -> 18 -> 9 -> 5, VALID over the rest
     assert m.store.table['CNN/res_block_2_shortcut/kernel'][1] == (1, 1, 16, 32)
+
+
+def test_host_ring_is_bounded_and_reuses_in_order():
+    """the staging ring keyed buffers by exact shape and never evicted (one set per padded length of a
+    bucketed epoch).  Now: `depth` flat buffers per role, grown geometrically, handed out in slot order 0, 1, ..."""
+    import torch
+    from avsr_tf1_b200.io_utils import _HostRing
+    ring = _HostRing(pin=False, depth=3)
+    first = [ring.get(('x', 0), (4, 10, 8), torch.float32) for _ in range(3)]
+    assert len({t.data_ptr() for t in first}) == 3
+    again = ring.get(('x', 0), (4, 10, 8), torch.float32)
+    assert again.data_ptr() == first[0].data_ptr()  # reuse distance = depth: the OLDEST slot comes back first
+    for t_pad in range(11, 200):                    # hundreds of distinct padded lengths ...
+        t = ring.get(('x', 0), (4, t_pad, 8), torch.float32)
+        assert t.shape == (4, t_pad, 8) and t.is_contiguous()
+    biggest = 4 * 199 * 8 * 4
+    assert ring.pinned_bytes() <= 3 * int(1.5 * biggest)  # ... still three buffers, each at most 1.5x the largest batch
+    a = ring.get(('aus', 0), (4, 7, 2), torch.float32)    # another role has its own ring
+    a.fill_(1.0)
+    assert float(a.sum()) == 4 * 7 * 2
+
+
+def test_record_iterator_stays_failed_after_a_producer_error(tmp_path):
+    """after the prefetch thread raised once, the next next() blocked forever on the dead thread's queue."""
+    from avsr_tf1_b200 import io_utils
+    from avsr_tf1_b200.synthetic import write_synthetic_records
+    paths = write_synthetic_records(str(tmp_path), n=6, Ta=8, Tv=4, Fa=3, hw=2, L=3)
+    from avsr_tf1_b200.hparams import create_unit_dict
+    it = io_utils.make_iterator_from_one_record(paths["audio"], paths["labels"], create_unit_dict(None), batch_size=2,
+                                                prefetch=1, pin_memory=False)
+
+    def boom(idx):
+        raise RuntimeError('decode failed')
+    it._assemble = boom
+    it.iterator_initializer()
+    with pytest.raises(RuntimeError):
+        it.next()
+    with pytest.raises(io_utils.OutOfRangeError):  # does not hang: the iterator is at its end until re-initialised
+        it.next()
+
+
+def test_checkpoint_is_written_atomically(tmp_path):
+    from avsr_tf1_b200.avsr import latest_checkpoint
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    hp = config_hparams(1)
+    batch = synthetic_batch(hp, B=2, Ta=6, L=3)
+    model = Seq2SeqModel(to_data_sequences(batch), 'train', hp, seed=1, device='cpu')
+    ckp = str(tmp_path / 'checkpoint.ckp')
+    model.saver.save(None, ckp, global_step=10)
+    # a crash during the NEXT save leaves only a temporary file behind: it is never taken for a checkpoint
+    open(ckp + '-20.tmp.npz', 'wb').write(b'truncated')
+    assert latest_checkpoint(str(tmp_path)) == ckp + '-10'
+    model.saver.save(None, ckp, global_step=20)
+    assert latest_checkpoint(str(tmp_path)) == ckp + '-20'
+    assert not (tmp_path / 'checkpoint.ckp-10.npz').exists()  # max_to_keep = 1, removed only after the rename
+    assert not (tmp_path / 'checkpoint.ckp-20.tmp.npz').exists()

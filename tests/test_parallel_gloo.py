@@ -101,7 +101,17 @@ def _shard_worker(rank, world, port, paths, out):
         # what a training step does between ranks: one collective per step must pair up on every rank
         t = torch.tensor([float(len(names))])
         parallel.allreduce_sum_(t)
-        steps.append((names, int(t.item())))
+        # input batch-norm statistics the way layers.BatchNormInput forms them under data parallelism: all-reduced
+        # [sum, sumsq] over this rank's rows (padding included), row count = padded length x GLOBAL batch size
+        audio = b.data_sequences()[1]
+        x = torch.as_tensor(audio.inputs, dtype=torch.float64)
+        n, t_pad, F = x.shape
+        sums = torch.cat([x.reshape(-1, F).sum(0), (x.reshape(-1, F) ** 2).sum(0)])
+        parallel.allreduce_sum_(sums)
+        count = t_pad * audio.payload['global_batch_size']
+        mean = (sums[:F] / count).numpy()
+        var = (sums[F:] / count).numpy() - mean * mean
+        steps.append((names, int(t.item()), t_pad, audio.payload['global_batch_size'], mean, var))
     parallel.barrier()
     out.put((rank, steps))
     dist.destroy_process_group()
@@ -124,10 +134,28 @@ def test_record_iterator_shards_pair_up_across_ranks(tmp_path):
         assert p.exitcode == 0
     s0, s1 = got[0], got[1]
     assert len(s0) == len(s1) > 0
-    seen = []
-    for (n0, tot0), (n1, tot1) in zip(s0, s1):
+    # the single-rank iterator over the same epoch: its batches are the global batches the two ranks share
+    from avsr_tf1_b200 import io_utils
+    from avsr_tf1_b200.hparams import create_unit_dict
+    whole = io_utils.make_iterator_from_two_records(
+        paths['video'], paths['audio'], paths['labels'], batch_size=6, unit_dict=create_unit_dict(None), shuffle=True,
+        bucket_width=3, seed=5, shuffle_buffer=8, prefetch=0, pin_memory=False)
+    ref = {}
+    for b in whole:
+        x = np.asarray(b.data_sequences()[1].inputs, np.float64)
+        key = frozenset(n.decode() for n in b.labels_filenames.tolist())
+        ref[key] = (x.shape[1], x.shape[0], x.reshape(-1, x.shape[2]).mean(0), x.reshape(-1, x.shape[2]).var(0))
+    seen, uneven = [], 0
+    for (n0, tot0, tp0, gb0, m0, v0), (n1, tot1, tp1, gb1, m1, v1) in zip(s0, s1):
         assert tot0 == tot1 == len(n0) + len(n1)      # the all-reduce saw both slices of the same global batch
         assert not set(n0) & set(n1) and abs(len(n0) - len(n1)) <= 1
+        uneven += len(n0) != len(n1)
+        # both ranks padded to the global batch's longest sequence and know its size: the all-reduced statistics are
+        # those of the one large batch, also when the batch does not divide evenly (count was T*B*world)
+        t_ref, b_ref, m_ref, v_ref = ref[frozenset(n0 + n1)]
+        assert tp0 == tp1 == t_ref and gb0 == gb1 == b_ref == len(n0) + len(n1)
+        assert np.allclose(m0, m_ref) and np.allclose(m1, m_ref) and np.allclose(v0, v_ref) and np.allclose(v1, v_ref)
         seen += n0 + n1
+    assert uneven > 0  # the epoch contains batches that do not divide evenly between the ranks
     assert len(seen) == len(set(seen))
     assert len(seen) >= 31 - 2 * 4  # only batches smaller than the world (at most one per bucket) are dropped
