@@ -1,0 +1,85 @@
+"""Data parallelism on real GPUs (NCCL): two ranks with B utterances each reproduce one rank with the 2B-utterance
+batch - loss, global gradient norm, input batch-norm moving statistics and the parameters after the step
+(reference semantics of one large batch: encoder.py:44-50 BN over the whole batch, seq2seq.py:165-171 loss
+denominator = all target tokens, seq2seq.py:246 clip by the GLOBAL norm).  Needs two visible GPUs (`gpurun --gpus 2`);
+skipped on a one-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import config_hparams, synthetic_batch, to_data_sequences
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _slice(batch, lo, hi):
+    return {k: v[lo:hi] for k, v in batch.items()}
+
+
+def _one_step(hp, ds, graph):
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    model = Seq2SeqModel(ds, 'train', hp, seed=2001)
+    model.use_cuda_graph = graph
+    out = [model.train_step(ds) for _ in range(2)]
+    st = model.store
+    return out, st.to_numpy('p'), {k: v.cpu().numpy() for k, v in st.state.items()}
+
+
+def _worker(rank, world, port, cfg, over, B, graph, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        hp = config_hparams(cfg, **over)
+        batch = synthetic_batch(hp, B=world * B, Ta=40, Tv=12, L=8, ragged=True)
+        batch['audio_len'][:] = np.maximum(batch['audio_len'], 1)
+        ds = to_data_sequences(_slice(batch, rank * B, (rank + 1) * B))
+        out, params, state = _one_step(hp, ds, graph)
+        if rank == 0:
+            ret.put((out, params, state))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
+@pytest.mark.parametrize('cfg,graph', [(5, False), (5, True), (2, False)])
+def test_two_ranks_equal_one_rank_with_the_whole_batch(cfg, graph):
+    import torch.multiprocessing as mp
+    B, over = 6, {}
+    ctx = mp.get_context('spawn')
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, cfg, over, B, graph, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out2, params2, state2 = ret.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    hp = config_hparams(cfg, **over)
+    batch = synthetic_batch(hp, B=2 * B, Ta=40, Tv=12, L=8, ragged=True)
+    batch['audio_len'][:] = np.maximum(batch['audio_len'], 1)
+    out1, params1, state1 = _one_step(hp, to_data_sequences(batch), False)
+    for (l2, g2), (l1, g1) in zip(out2, out1):
+        assert abs(l2 - l1) <= 2e-4 * abs(l1), (l2, l1)          # same loss of the same global batch
+        assert abs(g2 - g1) <= 2e-3 * g1, (g2, g1)                # same global norm (clip acts on it)
+    for k, v in state1.items():                                   # batch-norm moving statistics
+        assert np.allclose(state2[k], v, rtol=1e-4, atol=1e-6), k
+    lr_sum = sum(hp.learning_rate * (s + 1) / 750.0 for s in range(2))
+    for k, v in params1.items():                                  # Adam's first steps are sign-like: see test_gpu_model
+        diff = np.abs(params2[k] - v)
+        assert diff.max() <= 2.2 * lr_sum + 1e-6 * np.abs(v).max() + 1e-7, (k, diff.max())
+        assert (diff > 0.05 * lr_sum + 1e-6 * np.abs(v).max()).mean() < 3e-2, k

@@ -134,3 +134,104 @@ def test_generator_known_answers_and_uniformity():
     assert set(np.unique(fx)) == {0.0, 4294967296.0 / keep_threshold(0.9)}
     assert abs(fx.mean() - 1.0) < 0.02  # inverted dropout is unbiased
     assert np.all(spec.step_factor(2, 5, 4, 64, np.float64) == 1.0)  # output keep 1.0: no mask
+
+
+# ---- hand-computed known answers for the pieces no PyTorch primitive pins (cell_clip, the Bahdanau
+# scorers, one beam-search step) -------------------------------------------------------------------------------------
+def test_cell_clip_known_answer_and_zero_gradient_outside_the_range():
+    """cell_clip = 1.0 (cells.py:16): c = clip(f*c_prev + i*j, -1, 1) with saturated gates i = j = f = o = 1;
+    the gradient wrt c_prev is f inside the range and 0 where the clip is active."""
+    big = 40.0
+    W = np.zeros((2, 4))
+    b = np.array([big, big, big, big])            # i, j, f (+1 forget bias), o all saturate at 1 (tanh(40) = 1)
+    for c_prev, c_want in ((0.5, 1.0), (-0.5, 0.5), (-3.0, -1.0)):
+        h, c, cache = O.lstm_cell(np.zeros((1, 2)), np.array([[c_prev]]), W, b)
+        assert np.allclose(c, c_want) and np.allclose(h, np.tanh(c_want))
+        dxh, dc_prev, _, _ = O.lstm_cell_bwd(np.zeros((1, 1)), np.ones((1, 1)), cache, W)
+        inside = -1.0 <= c_prev + 1.0 <= 1.0
+        assert np.allclose(dc_prev, 1.0 if inside else 0.0), (c_prev, dc_prev)
+
+
+def _mech(kind, **kw):
+    mem = np.array([[[1.0, 0.0], [0.0, 1.0]]])  # B = 1, Tm = 2, Dm = 2; memory_layer = identity -> keys = memory
+    base = dict(kind=kind, memory=mem, mem_len=np.array([2]), Wm=np.eye(2), Wl=np.eye(4)[:, :2])
+    base.update(kw)
+    return O.AttnSpec(**base)
+
+
+def test_bahdanau_scores_known_answer():
+    """score_t = sum_u v_u tanh(keys_tu + (q Wq)_u) (attention.py:25-33)."""
+    from math import tanh
+    spec = _mech('bahdanau', Wq=np.eye(2), v=np.array([1.0, 2.0]))
+    _, keys, _ = O._prepare_memory(spec)
+    score, _ = O._score_fwd(spec, keys, np.array([[0.5, -0.5]]))
+    want = [1.0 * tanh(1.0 + 0.5) + 2.0 * tanh(0.0 - 0.5), 1.0 * tanh(0.0 + 0.5) + 2.0 * tanh(1.0 - 0.5)]
+    assert np.allclose(score, [want])
+
+
+def test_normed_bahdanau_scores_known_answer():
+    """v_hat = g v / |v|, bias inside the tanh (attention.py:34-42): v = (3, 4) -> |v| = 5."""
+    from math import tanh
+    spec = _mech('normed_bahdanau', Wq=np.eye(2), v=np.array([3.0, 4.0]), g=np.asarray(0.5), b=np.array([0.1, -0.2]))
+    _, keys, _ = O._prepare_memory(spec)
+    score, _ = O._score_fwd(spec, keys, np.array([[0.5, -0.5]]))
+    nv = (0.5 * 3.0 / 5.0, 0.5 * 4.0 / 5.0)
+    want = [nv[0] * tanh(1.0 + 0.5 + 0.1) + nv[1] * tanh(0.0 - 0.5 - 0.2),
+            nv[0] * tanh(0.0 + 0.5 + 0.1) + nv[1] * tanh(1.0 - 0.5 - 0.2)]
+    assert np.allclose(score, [want])
+
+
+def test_scaled_luong_and_memory_mask_known_answer():
+    """score = g keys.q (attention.py:64-72); rows past memory_sequence_length are zeroed BEFORE the key projection
+    and their scores masked to -inf, so a memory of length 1 puts all the weight on row 0."""
+    spec = _mech('scaled_luong', g=np.asarray(2.0))
+    _, keys, _ = O._prepare_memory(spec)
+    score, _ = O._score_fwd(spec, keys, np.array([[0.5, -0.25]]))
+    assert np.allclose(score, [[1.0, -0.5]])
+    short = _mech('luong', mem_len=np.array([1]))
+    values, keys, mask = O._prepare_memory(short)
+    assert np.array_equal(values[0, 1], [0.0, 0.0]) and np.array_equal(mask, [[1.0, 0.0]])
+    x = np.zeros((1, 1, 1))
+    W = np.zeros((1 + 2 + 2, 8))
+    r = O.attn_rnn_fwd(x, np.array([1]), W, np.zeros(8), [short])
+    assert np.allclose(r['alignments'][0][0, 0], [1.0, 0.0]) and np.allclose(r['contexts'][0][0, 0], [1.0, 0.0])
+
+
+def test_beam_search_step_known_answer():
+    """One BeamSearchDecoder step by hand (W = 2, V = 3, EOS = 2, length_penalty_weight = 0.6).
+    Step 1 from the initial state (log_probs = [0, -inf]): p = (0.5, 0.3, 0.2) on beam 0.  Candidates: word 0 with
+    score log 0.5 / ((5+1)/6)^0.6 = -0.693, word 1 with log 0.3 = -1.204, EOS (length stays 0) with
+    log 0.2 / (5/6)^0.6 = -1.795: the survivors are words 0 and 1, both from parent 0."""
+    eos, lpw = 2, 0.6
+    logits = np.log(np.array([[[0.5, 0.3, 0.2], [0.1, 0.1, 0.8]]]))
+    lp0 = np.array([[0.0, -np.inf]])
+    word, parent, score, lp, fin, ln = O.beam_search_step(logits, lp0, np.zeros((1, 2), bool), np.zeros((1, 2), np.int64),
+                                                           eos, lpw)
+    assert word.tolist() == [[0, 1]] and parent.tolist() == [[0, 0]]
+    assert np.allclose(score, [[np.log(0.5), np.log(0.3)]]) and np.allclose(lp, score)
+    assert fin.tolist() == [[False, False]] and ln.tolist() == [[1, 1]]
+    # Step 2: beam 0 (log p = log 0.5) sees p = (0.1, 0.1, 0.8); beam 1 (log 0.3) sees p = (0.6, 0.3, 0.1).
+    #   beam 0 + EOS : (log 0.5 + log 0.8) / (6/6)^0.6          = -0.9163  (EOS does not lengthen: length 1)
+    #   beam 1 + w0  : (log 0.3 + log 0.6) / (7/6)^0.6          = -1.5633
+    #   beam 0 + w0/1: (log 0.5 + log 0.1) / (7/6)^0.6          = -2.7311
+    logits2 = np.log(np.array([[[0.1, 0.1, 0.8], [0.6, 0.3, 0.1]]]))
+    word, parent, score, lp, fin, ln = O.beam_search_step(logits2, lp, fin, ln, eos, lpw)
+    assert word.tolist() == [[2, 0]] and parent.tolist() == [[0, 1]]
+    assert np.allclose(score, [[np.log(0.4), np.log(0.18) / (7.0 / 6.0) ** 0.6]])
+    assert np.allclose(lp, [[np.log(0.4), np.log(0.18)]])
+    # state lengths count the EOS of a beam that finishes now (TF: "beams that are now finished have their length
+    # increased by 1"), although the EOS candidate was SCORED with the un-lengthened hypothesis
+    assert fin.tolist() == [[True, False]] and ln.tolist() == [[2, 2]]
+    # Step 3: the finished beam may only be extended by EOS at zero cost and keeps its length
+    logits3 = np.log(np.array([[[0.98, 0.01, 0.01], [0.05, 0.05, 0.9]]]))
+    word, parent, score, lp, fin, ln = O.beam_search_step(logits3, lp, fin, ln, eos, lpw)
+    #   finished beam 0 + EOS: log 0.4 / (7/6)^0.6 = -0.835 (its length 2 now includes the EOS);
+    #   beam 1 + EOS: (log 0.18 + log 0.9) / (7/6)^0.6 = -1.659
+    assert word.tolist() == [[2, 2]] and parent.tolist() == [[0, 1]]
+    assert np.allclose(score, [[np.log(0.4) / (7.0 / 6.0) ** 0.6, np.log(0.162) / (7.0 / 6.0) ** 0.6]])
+    assert np.allclose(lp, [[np.log(0.4), np.log(0.162)]])
+    assert fin.tolist() == [[True, True]] and ln.tolist() == [[2, 3]]
+    # ties: equal scores keep the lowest flat index first (tf.nn.top_k)
+    tie = np.log(np.array([[[0.25, 0.25, 0.5], [0.25, 0.25, 0.5]]]))
+    word, parent, *_ = O.beam_search_step(tie, np.array([[0.0, 0.0]]), np.zeros((1, 2), bool), np.ones((1, 2), np.int64), eos, 0.0)
+    assert word.tolist() == [[2, 2]] and parent.tolist() == [[0, 1]]

@@ -19,14 +19,14 @@ ap.add_argument('--video-input', default='crops3888')
 ap.add_argument('--attention', default=None)
 ap.add_argument('--graph', default='default', choices=['default', 'parity'])
 ap.add_argument('--no-tensor-cores', action='store_true')
-ap.add_argument('--graph', action='store_true')
+ap.add_argument('--cuda-graph', action='store_true')
 args = ap.parse_args()
 ops.set_tensor_cores(not args.no_tensor_cores)
 hp, batch, _ = bench.workload(args, 5, args.batch, seed=0, graph=args.graph)
 batch.pop('video_u8', None)
 ds = to_data_sequences(batch)
 model = Seq2SeqModel(ds, 'train', hp, seed=2001)
-model.use_cuda_graph = args.graph
+model.use_cuda_graph = args.cuda_graph
 model.feed(ds)
 for _ in range(2):
     model.train_step(fetch=False)
