@@ -49,9 +49,15 @@ def _worker(rank, world, port, cfg, over, B, graph, ret):
         out, params, state = _one_step(hp, ds, graph)
         if rank == 0:
             ret.put((out, params, state))
+            ret.close()
+            ret.join_thread()  # flushed before the hard exit below
         dist.barrier()
+        torch.cuda.synchronize()
     finally:
-        dist.destroy_process_group()
+        # a captured CUDA graph holds NCCL work: tearing the process group down under it can hang until the NCCL
+        # watchdog fires (10 minutes), so the worker leaves hard once every rank has reached the barrier (bench.py
+        # does the same)
+        os._exit(0)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
@@ -62,13 +68,18 @@ def test_two_ranks_equal_one_rank_with_the_whole_batch(cfg, graph):
     ctx = mp.get_context('spawn')
     ret = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, cfg, over, B, graph, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, cfg, over, B, graph, ret), daemon=True) for r in range(2)]
     for p in procs:
         p.start()
-    out2, params2, state2 = ret.get(timeout=600)
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        out2, params2, state2 = ret.get(timeout=300)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0, p.exitcode
+    finally:
+        for p in procs:  # never leave a worker behind: pytest would wait for it at exit
+            if p.is_alive():
+                p.kill()
     hp = config_hparams(cfg, **over)
     batch = synthetic_batch(hp, B=2 * B, Ta=40, Tv=12, L=8, ragged=True)
     batch['audio_len'][:] = np.maximum(batch['audio_len'], 1)
