@@ -53,11 +53,13 @@ def _worker(rank, world, port, cfg, over, B, graph, ret):
             ret.join_thread()  # flushed before the hard exit below
         dist.barrier()
         torch.cuda.synchronize()
-    finally:
-        # a captured CUDA graph holds NCCL work: tearing the process group down under it can hang until the NCCL
-        # watchdog fires (10 minutes), so the worker leaves hard once every rank has reached the barrier (bench.py
-        # does the same)
-        os._exit(0)
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        os._exit(1)
+    # a captured CUDA graph holds NCCL work: tearing the process group down under it can hang until the NCCL watchdog
+    # fires (10 minutes), so the worker leaves hard once every rank has reached the barrier (bench.py does the same)
+    os._exit(0)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
@@ -72,7 +74,16 @@ def test_two_ranks_equal_one_rank_with_the_whole_batch(cfg, graph):
     for p in procs:
         p.start()
     try:
-        out2, params2, state2 = ret.get(timeout=300)
+        import queue as _q
+        got = None
+        for _ in range(300):  # a worker that died (exit code != 0) ends the wait at once
+            try:
+                got = ret.get(timeout=1)
+                break
+            except _q.Empty:
+                assert all(p.exitcode in (None, 0) for p in procs), [p.exitcode for p in procs]
+        assert got is not None, 'no result from rank 0 within 300 s'
+        out2, params2, state2 = got
         for p in procs:
             p.join(timeout=60)
             assert p.exitcode == 0, p.exitcode
