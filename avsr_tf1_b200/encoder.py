@@ -6,6 +6,8 @@ import collections
 
 import numpy as np
 
+import torch
+
 from . import ops
 from .attention import add_attention
 from .cells import build_rnn_layers
@@ -133,20 +135,31 @@ class Seq2SeqEncoder(object):
         ctx = self._ctx
         self._lens = inputs_len
         x = self._normalised_inputs(inputs, batch_major)
+
+        def backward_stack():
+            curb, curb_op = None, ops.reverse_sequence(x, inputs_len)
+            for op in self._bw:
+                curb = op.forward(curb_op, inputs_len)
+                curb_op = op.operand
+            return ops.reverse_sequence(curb, inputs_len)
+        # bidirectional_dynamic_rnn (encoder.py:110) = two independent deep stacks: side by side when they fit the GPU
+        side = ctx.fork(1) if (self._bw is not None and ctx.parallel_chains) else None
+        if side is not None:
+            with torch.cuda.stream(side):
+                outb = backward_stack()
         cur, cur_op = None, x
         for op in self._fw:
             cur = op.forward(cur_op, inputs_len)
             cur_op = op.operand
+        if side is not None:
+            ctx.join(1)
+        elif self._bw is not None:
+            outb = backward_stack()
         if self._bw is None:
             self._outputs = cur
             self._outputs_op = self._round_outputs(cur, self._fw[-1])
             self._final = self._fw[-1].final
         else:
-            curb, curb_op = None, ops.reverse_sequence(x, inputs_len)
-            for op in self._bw:
-                curb = op.forward(curb_op, inputs_len)
-                curb_op = op.operand
-            outb = ops.reverse_sequence(curb, inputs_len)
             T, B, H = cur.shape
             out = ops.empty(T, B, 2 * H)
             out[:, :, :H].copy_(cur)
@@ -223,10 +236,25 @@ class Seq2SeqEncoder(object):
             db = ops.reverse_sequence(doutputs[:, :, H:].contiguous(), self._lens)
             n = len(self._fw)
             need_dx = need_dx or self._layer0_drops_input()
-            for i in range(n - 1, -1, -1):
-                need = (i > 0) or need_dx
-                df = self._fw[i].backward(df, dsf if i == n - 1 else None, need_dx=need)
-                db = self._bw[i].backward(db, dsb if i == n - 1 else None, need_dx=need)
+
+            def stack_backward(stack, d, ds):
+                for i in range(n - 1, -1, -1):
+                    d = stack[i].backward(d, ds if i == n - 1 else None, need_dx=(i > 0) or need_dx)
+                return d
+            if ctx.parallel_chains:  # the two stacks are independent in the backward pass too
+                # `db` was allocated on THIS stream and is read by kernels of the side stream: it must stay referenced
+                # until the join, or the caching allocator hands its block to the forward stack's allocations while
+                # the side kernels still read it (the allocator only orders reuse within the allocating stream)
+                keep = db
+                with torch.cuda.stream(ctx.fork(1)):
+                    db_new = stack_backward(self._bw, db, dsb)
+                df = stack_backward(self._fw, df, dsf)
+                ctx.join(1)
+                db = db_new
+                del keep
+            else:
+                df = stack_backward(self._fw, df, dsf)
+                db = stack_backward(self._bw, db, dsb)
             dx = None
             if need_dx:
                 dxb = ops.reverse_sequence(db, self._lens)

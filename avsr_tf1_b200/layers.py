@@ -29,8 +29,23 @@ class BuildContext:
         self.grad_scale = 1.0  # power of two ~ number of target tokens (set per step by Seq2SeqModel)
         self.allreduce = None  # callable(tensor) -> None (in-place sum), set by Seq2SeqModel under DP
         self.rng = None  # device int32[2] {seed, step}: counter-based generator of dropout / scheduled sampling
+        # Independent recurrent chains (forward / backward stacks of a BiLSTM encoder, video / audio encoders) run side
+        # by side on two streams when two persistent kernels fit the GPU together: a cluster-of-4 kernel occupies
+        # 4 * ceil(B / 8) SMs, so up to 144 utterances two of them share the 148 SMs (Seq2SeqModel sets this per batch).
+        self.parallel_chains = False
+        self._side = {}
         self._streams = 0
         self.streams = {}  # cell name (variable prefix) -> first stream id: lets the oracle regenerate every mask
+
+    def fork(self, level=0):
+        """Side stream forked from the current one (also under graph capture); `level` keeps nested forks apart."""
+        if level not in self._side:
+            self._side[level] = torch.cuda.Stream()
+        self._side[level].wait_stream(torch.cuda.current_stream())
+        return self._side[level]
+
+    def join(self, level=0):
+        torch.cuda.current_stream().wait_stream(self._side[level])
 
     def new_stream(self, n=4):
         """Reserves n consecutive stream ids of the generator (one independent random sequence each)."""

@@ -150,6 +150,7 @@ class Seq2SeqModel(object):
         # cluster-of-4 kernels run 32 clusters on 128 SMs, two of them only time-slice the same SMs and the audio
         # branch (the critical path) loses: measured 13.6k utt/s overlapped vs 15.7k on one stream.
         self.overlap_streams = False
+        self.serial_chains = False  # True: never run independent recurrent chains side by side (debugging, A/B timing)
         self._graphs = {}
         self.use_cuda_graph = False  # opt-in: train_step replays one captured graph per batch shape
         self.launches_last_step = 0
@@ -390,6 +391,13 @@ class Seq2SeqModel(object):
         return b
 
     # ---- forward ---------------------------------------------------------------------
+    def _chains_fit(self, b):
+        """Two persistent recurrent kernels side by side: 2 * 4 * ceil(B / 8) <= 148 SMs (layers.BuildContext)."""
+        if not ops.tensor_cores_enabled() or self.serial_chains:
+            return False
+        B = int(b['labels'].shape[0]) if 'labels' in b else int(next(b[k] for k in ('audio', 'video') if k in b).shape[0])
+        return 8 * ((B + 7) // 8) <= 148
+
     def _fork(self):
         """Side stream forked from the current one (also under graph capture): the video encoder and the
         audio layers below the cross-modal attention are independent, and a persistent LSTM kernel with
@@ -422,8 +430,9 @@ class Seq2SeqModel(object):
 
     def _encode(self, b):
         enc = {}
+        self._ctx.parallel_chains = self._chains_fit(b)
         both = self._video_encoder is not None and self._audio_encoder is not None
-        overlap = both and self.overlap_streams
+        overlap = both and (self.overlap_streams or self._ctx.parallel_chains)
         if self._video_encoder is not None:
             if overlap:
                 with torch.cuda.stream(self._fork()):
@@ -465,6 +474,7 @@ class Seq2SeqModel(object):
         the cross-entropy SUM in _loss_dev[0] (normalised by the device scalar inv_denom)."""
         b = self._batch if self._batch is not None else self._prep()
         self._ctx.batch_scale = self._meta.get('batch_scale', float(self._ctx.world_size))
+        self._ctx.parallel_chains = self._chains_fit(b)
         self.store.grad.zero_()
         self._loss_dev.zero_()
         if self._ctx.world_size > 1:
@@ -484,7 +494,7 @@ class Seq2SeqModel(object):
             self._video_encoder.au_loss_forward(b['aus'], self._scal_dev[2:3], self._loss_dev[3:4])
             dvid_au = self._video_encoder.au_loss_backward(None)
         both = self._video_encoder is not None and self._audio_encoder is not None
-        overlap = both and self.overlap_streams
+        overlap = both and (self.overlap_streams or self._ctx.parallel_chains)
         if self._hparams.architecture == 'bimodal':
             if overlap:
                 with torch.cuda.stream(self._fork()):
