@@ -23,7 +23,7 @@ class AvsrAttnMech(C.Structure):
         ('align', C.c_void_p), ('hc', C.c_void_p), ('pq', C.c_void_p),
         ('dkeys', C.c_void_p), ('dvalues', C.c_void_p), ('dWl', C.c_void_p), ('dWq', C.c_void_p),
         ('dv', C.c_void_p), ('dg', C.c_void_p), ('dbias', C.c_void_p), ('dpq', C.c_void_p),
-        ('ds', C.c_void_p), ('dhc', C.c_void_p),
+        ('ds', C.c_void_p), ('dhc', C.c_void_p), ('values_op', C.c_void_p),
     ]
 
 

@@ -220,25 +220,36 @@ __device__ __forceinline__ void unpack_q(const uint4& qraw, float (&q)[8]) {
   const float2 a = unpack_h2(qraw.x), b = unpack_h2(qraw.y), c = unpack_h2(qraw.z), d = unpack_h2(qraw.w);
   q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y; q[4] = c.x; q[5] = c.y; q[6] = d.x; q[7] = d.y;
 }
+// score of one memory row against the query: Luong keys.q (attention.py:55-72) or Bahdanau sum_u v_u tanh(keys_u + pq_u)
+// (attention.py:25-42; q then holds the processed query plus the bias of the normed variant, v the effective v)
+template <bool BAHD>
+__device__ __forceinline__ float score8(const uint4& r, const float (&q)[8], const float (&v)[8]) {
+  if constexpr (!BAHD) {
+    return dot8(r, q);
+  } else {
+    const float2 a = unpack_h2(r.x), b = unpack_h2(r.y), c = unpack_h2(r.z), d = unpack_h2(r.w);
+    return ((v[0] * tanhf_acc(a.x + q[0]) + v[1] * tanhf_acc(a.y + q[1])) + (v[2] * tanhf_acc(b.x + q[2]) + v[3] * tanhf_acc(b.y + q[3]))) +
+           ((v[4] * tanhf_acc(c.x + q[4]) + v[5] * tanhf_acc(c.y + q[5])) + (v[6] * tanhf_acc(d.x + q[6]) + v[7] * tanhf_acc(d.y + q[7])));
+  }
+}
 // forward: scores (keys already in ra / rb) -> masked softmax -> alignments (shared memory and `arow` in HBM) ->
-// context.  On return warp w4 == 0 holds the context (tf32-rounded) in ctxv.
-__device__ __forceinline__ void att_fwd_core(const AttRole& a, const uint4& qraw, uint4 (&ra)[4], uint4 (&rb)[4],
-                                             float* __restrict__ arow, float (&ctxv)[8]) {
+// context.  On return warp w4 == 0 holds the context in ctxv (tf32-rounded unless RAW_CTX).
+template <bool BAHD = false, bool RAW_CTX = false>
+__device__ __forceinline__ void att_fwd_core(const AttRole& a, const float (&q)[8], const float (&v)[8], uint4 (&ra)[4],
+                                             uint4 (&rb)[4], float* __restrict__ arow, float (&ctxv)[8]) {
   const int lane = a.lane, w4 = a.w4, gt = a.gt, L = a.L;
   float* sc = a.sc;
   float* red = a.red;
-  float q[8];
-  unpack_q(qraw, q);
   // scores: rows tm = w4 + 4*i, one 9-shuffle reduction per batch of 8 rows
   const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
     float sacc[RIF];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sacc[j] = dot8(ra[j], q);
+    for (int j = 0; j < 4; ++j) sacc[j] = score8<BAHD>(ra[j], q, v);
 #pragma unroll
     for (int j = 0; j < 4; ++j) ra[j] = ld_row(a.keys, tm0 + 32 + 4 * j, L, a.B, a.b_att, lane);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sacc[4 + j] = dot8(rb[j], q);
+    for (int j = 0; j < 4; ++j) sacc[4 + j] = score8<BAHD>(rb[j], q, v);
 #pragma unroll
     for (int j = 0; j < 4; ++j) rb[j] = ld_row(a.keys, tm0 + 48 + 4 * j, L, a.B, a.b_att, lane);
     const float tot = warp_reduce8(sacc, lane);
@@ -289,9 +300,10 @@ __device__ __forceinline__ void att_fwd_core(const AttRole& a, const uint4& qraw
   att_bar(a.bar_id);
   if (w4 == 0) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      ctxv[e] = tf32_rn((a.part[8 * lane + e] + a.part[DM + 8 * lane + e]) +
-                        (a.part[2 * DM + 8 * lane + e] + a.part[3 * DM + 8 * lane + e]));
+    for (int e = 0; e < 8; ++e) {
+      const float c = (a.part[8 * lane + e] + a.part[DM + 8 * lane + e]) + (a.part[2 * DM + 8 * lane + e] + a.part[3 * DM + 8 * lane + e]);
+      ctxv[e] = RAW_CTX ? c : tf32_rn(c);
+    }
   }
 }
 

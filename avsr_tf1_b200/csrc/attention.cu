@@ -606,6 +606,58 @@ attn_bahdanau_post_kernel(int T, int B, int Tm, int A, const int* __restrict__ s
   }
 }
 
+// Contexts of all steps from the saved alignments: ctx[t,b,:] = sum_tm align[t,b,tm] values[tm,b,:] for t < len[b], else
+// 0; tf32-rounded (operand of the attention-layer weight gradient).  Used after the persistent Bahdanau kernels, which
+// keep the context half of the attention layer out of the recurrence (attn_persist4d.cu).  Block = (utterance, chunk
+// of CTX_TC steps): the alignments of the chunk sit in shared memory, a thread owns feature columns d, d + 256.
+constexpr int CTX_TC = 16;
+__global__ void attn_context_all_kernel(int T, int B, int Tm, int Dm, const int* __restrict__ seq_len,
+                                        const int* __restrict__ mem_len, const float* __restrict__ align,
+                                        const float* __restrict__ values, float* __restrict__ ctx, int ldc, int rnd) {
+  extern __shared__ float sa[];  // [CTX_TC][Tm]
+  const int b = blockIdx.x, t0 = blockIdx.y * CTX_TC;
+  const int n = min(CTX_TC, T - t0);
+  const int L = min(mem_len[b], Tm), len = seq_len[b];
+  for (int i = threadIdx.x; i < n * Tm; i += blockDim.x) {
+    const int t = i / Tm, tm = i - t * Tm;
+    sa[i] = (t0 + t < len && tm < L) ? align[((size_t)(t0 + t) * B + b) * Tm + tm] : 0.0f;
+  }
+  __syncthreads();
+  for (int d0 = threadIdx.x; d0 < Dm; d0 += 2 * blockDim.x) {
+    const int d1 = d0 + blockDim.x;
+    float acc0[CTX_TC], acc1[CTX_TC];
+#pragma unroll
+    for (int t = 0; t < CTX_TC; ++t) acc0[t] = acc1[t] = 0.0f;
+    for (int tm = 0; tm < L; ++tm) {
+      const float* vr = values + ((size_t)tm * B + b) * Dm;
+      const float v0 = vr[d0], v1 = d1 < Dm ? vr[d1] : 0.0f;
+#pragma unroll
+      for (int t = 0; t < CTX_TC; ++t) {
+        const float a = sa[t * Tm + tm];
+        acc0[t] = fmaf(a, v0, acc0[t]);
+        acc1[t] = fmaf(a, v1, acc1[t]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < CTX_TC; ++t)
+      if (t < n) {
+        float* o = ctx + ((size_t)(t0 + t) * B + b) * ldc;
+        o[d0] = maybe_tf32(acc0[t], rnd);
+        if (d1 < Dm) o[d1] = maybe_tf32(acc1[t], rnd);
+      }
+  }
+}
+
+int attn_context_all(cudaStream_t st, int T, int B, int Tm, int Dm, const int* seq_len, const int* mem_len,
+                     const float* align, const float* values, float* ctx, int ldc) {
+  if (T <= 0) return 0;
+  const size_t smem = (size_t)CTX_TC * Tm * sizeof(float);
+  AVSR_REQUIRE(smem <= 48 * 1024, "attn_context_all: memory of %d rows too long", Tm);
+  AVSR_LAUNCH(attn_context_all_kernel, dim3(B, cdiv(T, CTX_TC)), 256, smem, st, T, B, Tm, Dm, seq_len, mem_len, align,
+              values, ctx, ldc, tensor_cores_enabled());
+  return 0;
+}
+
 int attn_bahdanau_post(cudaStream_t st, int T, int B, int Tm, int A, const int* seq_len, const int* mem_len,
                        const float* ds, const float* pq, const float* keys, const float* v, const float* bias,
                        float* dkeys, float* dv, float* dbias) {

@@ -1135,8 +1135,12 @@ static bool unfused_fwd(const AvsrRnnSeq* r) { return layer_dropout(r) || r->sam
 static bool persist_shape_ok(const AvsrRnnSeq* r) {
   if (r->n_mech != 1 || r->T <= 1) return false;
   const AvsrAttnMech& m = r->mech[0];
-  return m.kind <= AVSR_ATTN_SCALED_LUONG && r->H == 256 && m.A == 256 && m.Dm == 256 && m.Tm <= 384;
+  if (m.kind >= AVSR_ATTN_BAHDANAU)  // Bahdanau family: two-product kernels, any memory depth (projected values)
+    return r->H == 256 && m.A == 256 && m.Tm <= 384 && !r->output_attention;
+  return r->H == 256 && m.A == 256 && m.Dm == 256 && m.Tm <= 384;
 }
+int attn_context_all(cudaStream_t st, int T, int B, int Tm, int Dm, const int* seq_len, const int* mem_len,
+                     const float* align, const float* values, float* ctx, int ldc);  // attention.cu
 int cluster_width_ap();
 int rnn_sampling_fused(const AvsrRnnSeq* r) {
   return r && r->rng && tensor_cores_enabled() && persist_shape_ok(r) && r->output_attention && cluster_width_ap() == 4 &&
@@ -1144,8 +1148,34 @@ int rnn_sampling_fused(const AvsrRnnSeq* r) {
 }
 
 size_t attn_persist_work_floats(int B, int H, int Dm, int Tm) {
-  // fused weights [(H+Dm),4H] + product scratch [H,4H] + fp16 keys / values
-  return (size_t)(H + Dm) * 4 * H + (size_t)H * 4 * H + ((size_t)Tm * B * (H + Dm) + 1) / 2 + 64;
+  // fused weights [(H+Dm),4H] + product scratch [H,4H] + fp16 keys / values + (Bahdanau family) the projected memory
+  // values PV = values Wl_c [Tm*B, H] in fp32 before their fp16 copy takes the place of the values
+  return (size_t)(H + Dm) * 4 * H + (size_t)H * 4 * H + ((size_t)Tm * B * (H + Dm) + 1) / 2 + 64 + (size_t)Tm * B * H;
+}
+static float* pv_scratch(float* scratch, int B, int H, int Dm, int Tm) {
+  return scratch + (size_t)(H + Dm) * 4 * H + (size_t)H * 4 * H + ((size_t)Tm * B * (H + Dm) + 1) / 2 + 64;
+}
+
+// Forward of a single-mechanism Bahdanau-family layer (any memory depth) on the two-product kernels
+static int bahdanau_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
+  using namespace ap;
+  const AvsrAttnMech& m = r->mech[0];
+  const int T = r->T, B = r->B, At = m.A, SW = At + H, HD = H + m.Dm;
+  float* tmp = scratch + (size_t)HD * 4 * H;
+  __half* keys_h = reinterpret_cast<__half*>(tmp + (size_t)H * 4 * H);
+  __half* pv_h = keys_h + (size_t)m.Tm * B * H;
+  float* pv = pv_scratch(scratch, B, H, m.Dm, m.Tm);
+  // step 0: att_{-1} = 0, so only h_0 Wh enters
+  AVSR_TRY(gemm(st, 0, 0, B, 4 * H, H, r->S + At, SW, r->Wrec + (size_t)At * 4 * H, 4 * H, r->gates, 4 * H, 1.0f, nullptr));
+  // PV = values Wl_c: the context half of the attention layer, once per batch
+  AVSR_TRY(gemm(st, 0, 0, m.Tm * B, At, m.Dm, m.values_op ? m.values_op : m.values, m.Dm, m.Wl + (size_t)H * At, At, pv, At,
+                0.0f, nullptr));
+  const long long nk = (long long)m.Tm * B * H;
+  AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
+  AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, pv, pv_h, nk);
+  AVSR_TRY(attn_persist4d_launch_fwd(st, r, keys_h, pv_h));
+  // the true contexts of every step (parity probe; operand of the attention-layer weight gradient)
+  return attn_context_all(st, T, B, m.Tm, m.Dm, r->len, m.mem_len, m.align, m.values, m.hc + H, HD);
 }
 
 // Forward of a single-mechanism Luong-family attention layer with the persistent kernel.  Returns -1 when
@@ -1154,7 +1184,10 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   using namespace ap;
   if (r->n_mech != 1 || r->T <= 0) return -1;
   const AvsrAttnMech& m = r->mech[0];
-  if (m.kind > AVSR_ATTN_SCALED_LUONG) return -1;
+  if (m.kind > AVSR_ATTN_SCALED_LUONG) {
+    if (!persist_shape_ok(r) || cluster_width() != 4 || getenv("AVSR_NO_BAHDANAU_PERSIST")) return -1;
+    return bahdanau_persist_fwd(st, r, scratch);
+  }
   if (r->H != H || m.A != H || m.Dm != DM || m.Tm > MAX_TM) return -1;
   if (unfused_fwd(r) && (!r->output_attention || cluster_width() != 4)) return -1;
   const int T = r->T, B = r->B, At = m.A, SW = At + H;

@@ -280,7 +280,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_fwd_kernel(cons
     if (live_q) {
       // query: lane holds dims 8*lane .. 8*lane+7 (one swizzled 16-byte chunk of the operand row)
       const uint4 qraw = *reinterpret_cast<const uint4*>(gen + (sOp - base) + nb * OP_BYTES + sw128h_off(NP, bl_att, 8 * lane));
-      att_fwd_core(role, qraw, ra, rb, p.align + ((size_t)t * B + b_att) * Tm, ctxv);
+      float q[8];
+      const float vnone[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+      unpack_q(qraw, q);
+      att_fwd_core(role, q, vnone, ra, rb, p.align + ((size_t)t * B + b_att) * Tm, ctxv);
     }
     if (w4 == 0) {
       // ctx_t of this utterance: HBM (tf32-rounded fp32, for the backward pass) + all-gather (fp16 operand)

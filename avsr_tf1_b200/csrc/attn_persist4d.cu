@@ -64,6 +64,13 @@ struct DParams {
   float* cT;             // [B,H] or null
   float* hT;             // [B,H] or null
   DropCfg d;
+  // BAHD instantiation (Bahdanau family, attention.py:25-42): query layer, effective v, bias (normed) or null, the
+  // processed queries kept for the backward pass; `values` then holds the PROJECTED memory values Wl_c (see below) and
+  // `out` [T,B,H] receives the cell output ho (the wrapper returns the cell output for this family)
+  const float* Wq;       // [H, AT]
+  const float* v;        // [AT]
+  const float* batt;     // [AT] or null
+  float* pq;             // [T,B,AT]
   // SAMPLE instantiation: ScheduledEmbeddingTrainingHelper inside the kernel (AvsrSampling, include/avsr_b200.h)
   const float* Wd;       // [AT, V]
   const float* bd;       // [V]
@@ -80,14 +87,24 @@ struct DParams {
 constexpr int SAMP_VP = 32;                                 // padded alphabet (V <= 32)
 constexpr int SAMP_EMAX = 256;                              // E <= 256
 constexpr int SAMP_SMEM = NB * UPC * 4 + UPC * SAMP_VP * 4 + CL * NB * SAMP_VP * 4 + SAMP_EMAX * 4 + NB * 4;
+constexpr int BAHD_SMEM = NU * AT * 4 + NB * UPC * 4;         // processed queries of the CTA's utterances | projected contexts
 constexpr size_t DFWD_SMEM = (size_t)W_BYTES + 2 * OP_BYTES + Q_BYTES + 4 * NB * UPC * 4 + APART_FLOATS * 4 +
-                             NU * MAX_TM * 4 + NU * 8 * 4 + 64 + SAMP_SMEM + 1024;
+                             NU * MAX_TM * 4 + NU * 8 * 4 + 96 + SAMP_SMEM + BAHD_SMEM + 1024;
 
 // SAMPLE: scheduled sampling (decoder_unimodal.py:304-309) inside the recurrence.  Which (step, utterance) pairs
 // are replaced is a function of the generator alone, so every CTA of the cluster knows it; for those pairs the CTAs
 // reduce partial logits a_t Wd over their attention units through DSMEM, every CTA draws the same id (inverse CDF of
 // the fp32 softmax, as avsr_sched_sample) and forms the x-projection of the drawn embedding for its own gate rows.
-template <bool SAMPLE>
+//
+// BAHD: the Bahdanau scorers.  Two more things enter the step: the processed query pq_t = ho_t Wq and
+// score = sum_u v_u tanh(keys_u + pq_u).  The query layer shares the attention product: the A operand in tensor memory
+// holds the CTA's 64 rows of Wl_h^T in lanes 0..63 and its 64 rows of Wq^T in lanes 64..127, both multiply ho (K = 256),
+// issued as soon as ho_t has been gathered; the pq slices are exchanged (all-to-all) to the owners of the utterances
+// before the sweep.  The context half of the attention layer is taken out of the recurrence: the host projects the
+// memory once per batch, PV = values Wl_c (any memory depth Dm), the sweep forms ctx' = sum_t a_t PV_t (256-d) and
+// a_t = ho_t Wl_h + ctx'_t.  The true contexts (parity probe, operand of dWl) are formed after the loop from the saved
+// alignments (attn_context_all).
+template <bool SAMPLE, bool BAHD>
 __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(const DParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -99,8 +116,11 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
   const uint32_t sSc = sAp + APART_FLOATS * 4;       // [NU][MAX_TM] scores / alignments
   const uint32_t sRed = sSc + NU * MAX_TM * 4;       // [NU][8]
   const uint32_t sBar = sRed + NU * 8 * 4;           // [0] mma1 [1] mma2 [2,3] h_full[buf] [4] ctx_full [5] a_full
-  const uint32_t sTmem = sBar + 56;                  // [6] logits_full (SAMPLE)
-  const uint32_t sSamp = sBar + 64;                  // SAMPLE: a_t [NB][UPC] | Wd slice [UPC][32] | partial logits [CL][NB][32] | x [256] | picks [NB]
+  const uint32_t sTmem = sBar + 64;                  // [6] logits_full (SAMPLE) [7] pq_full (BAHD)
+  const uint32_t sSamp = sBar + 80;                  // SAMPLE: a_t [NB][UPC] | Wd slice [UPC][32] | partial logits [CL][NB][32] | x [256] | picks [NB]
+  const uint32_t sPqA = sSamp + SAMP_SMEM;           // BAHD: pq of the CTA's utterances [NU][AT]
+  const uint32_t sCxA = sPqA + NU * AT * 4;          // BAHD: projected contexts of the CTA's attention units [NB][UPC]
+  const uint32_t barPq = sBar + 56;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   float* act = reinterpret_cast<float*>(gen + (sAct - base));
   float* apart = reinterpret_cast<float*>(gen + (sAp - base));
@@ -109,6 +129,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
   float* sLg = sWd + UPC * SAMP_VP;
   float* sX = sLg + CL * NB * SAMP_VP;
   int* sPick = reinterpret_cast<int*>(sX + SAMP_EMAX);
+  float* sPq = reinterpret_cast<float*>(gen + (sPqA - base));
+  float* sCx = reinterpret_cast<float*>(gen + (sCxA - base));
   const uint32_t sLgAddr = sSamp + (NB * UPC + UPC * SAMP_VP) * 4, barL = sBar + 48;
   float* sc_all = reinterpret_cast<float*>(gen + (sSc - base));
   float* part_all = act;
@@ -123,7 +145,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
   if (tid == 0) {
     mbar_init(barM1, THREADS / 32);  // one commit per issuing warp
     mbar_init(barM2, THREADS / 32);
-    for (int i = 2; i < 7; ++i) mbar_init(sBar + 8 * i, 1);
+    for (int i = 2; i < 8; ++i) mbar_init(sBar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if constexpr (SAMPLE) {  // output-layer rows of the CTA's attention units
@@ -170,8 +192,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     }
     // Wa slice: lane l = 32 q + lane: part = l >> 6 (0: rows multiplying ho, 1: rows multiplying ctx), attention unit
     // 64*rank + (l & 63); column c holds K elements 2c, 2c+1 of that part; warp w fills columns 64*(w >> 2) .. +63
+    // (BAHD: lanes 64..127 hold the CTA's rows of Wq^T instead - both halves multiply ho)
     const int l = 32 * q + lane;
-    const float* wcol = p.Wa + (size_t)((l >> 6) * H) * AT + UPC * rank + (l & 63);
+    const float* wcol = (BAHD && l >= 64) ? p.Wq + UPC * rank + (l & 63)
+                                          : p.Wa + (size_t)((l >> 6) * H) * AT + UPC * rank + (l & 63);
 #pragma unroll 1
     for (int c0 = 0; c0 < 64; c0 += 32) {
       uint32_t r[32];
@@ -284,8 +308,39 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
   const AttRole role = {p.keys, p.values, L, B, b_att, Tm, w4, gt, lane, gs, att_bar_id, sc, part, red};
 
   uint32_t lphase = 0u;  // SAMPLE: completed phases of the logits barrier
+  float v8[8], b8[8];    // BAHD: effective v and bias of the lane's 8 attention units
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    v8[e] = BAHD ? p.v[8 * lane + e] : 0.0f;
+    b8[e] = (BAHD && p.batt) ? p.batt[8 * lane + e] : 0.0f;
+  }
+  // the attention product's accumulators -> partial planes [K group][part]: warp (grp, q) sums accumulators 4 grp .. +3
+  // of lane quarter q; part 0 = lanes 0..63, part 1 = lanes 64..127 (Luong: the ctx rows, B columns 8..15; BAHD: Wq^T)
+  auto att_epilogue = [&]() {
+    const int grp = warp >> 2, q = warp & 3;
+    const uint32_t a0 = tmem_base + ((uint32_t)(32 * q) << 16) + (4 * grp) * NP + ((!BAHD && q >= 2) ? 8 : 0);
+    uint32_t r0[8], r1[8], r2[8], r3[8];
+    tmem_ld8(a0, r0);
+    tmem_ld8(a0 + NP, r1);
+    tmem_ld8(a0 + 2 * NP, r2);
+    tmem_ld8(a0 + 3 * NP, r3);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    float* ap = apart + ((grp * 2 + (q >> 1)) * NB) * UPC + 32 * (q & 1) + lane;
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      ap[b * UPC] = (__uint_as_float(r0[b]) + __uint_as_float(r1[b])) + (__uint_as_float(r2[b]) + __uint_as_float(r3[b]));
+  };
   for (int t = 0; t < T; ++t) {
     float* grow = p.gates + ((size_t)t * B + b0) * 4 * H + g * H + unit_g;
+    uint32_t selmask = 0u;  // SAMPLE: utterances of the cluster whose next input is drawn from this step's logits
+    if constexpr (SAMPLE) {
+      if (t + 1 < T) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+          if (b0 + b < B && avsr_rand_u32(seed, rstep, p.ss_stream, (uint32_t)t, (uint32_t)(b0 + b)) < p.thr_p) selmask |= 1u << b;
+      }
+    }
     uint32_t r[8];
     if (t > 0) {
       mbar_wait(barM1, (t - 1) & 1);
@@ -368,6 +423,16 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
       *reinterpret_cast<float4*>(p.craw + row * H + u0) = make_float4(cr[0], cr[1], cr[2], cr[3]);
       *reinterpret_cast<float4*>(p.S + (row + B) * (AT + H) + AT + u0) = make_float4(hs[0], hs[1], hs[2], hs[3]);
       *reinterpret_cast<float4*>(p.hc + row * (H + DM) + u0) = make_float4(ho[0], ho[1], ho[2], ho[3]);
+      if constexpr (BAHD)  // the wrapper emits the cell output for the Bahdanau family (zero past the length)
+        *reinterpret_cast<float4*>(p.out + row * H + u0) =
+            t < len_c ? make_float4(ho[0], ho[1], ho[2], ho[3]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    if constexpr (SAMPLE && BAHD) {  // the output layer reads the emitted h
+      if (comb && selmask) {
+        const bool live = t < len_c;
+        *reinterpret_cast<float4*>(&sAf[bq * UPC + 4 * uq]) =
+            live ? make_float4(ho[0], ho[1], ho[2], ho[3]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
     }
     if (t + 1 < T) {
       const float* gnext = grow + (size_t)B * 4 * H;
@@ -381,15 +446,60 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     if (tid == 0) mbar_expect_tx(hbar_n, 2 * NB * H * 2);
     mbar_wait(hbar_n, (t >> 1) & 1);  // every CTA's hs_t / ho_t slices have landed
 
+    if constexpr (BAHD) {
+      // [ho Wl_h | ho Wq] for the CTA's units as soon as ho_t is there; the pq slices go to the owners of the utterances
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      issue_att();
+      mbar_wait(barM2, t & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      att_epilogue();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (comb) {
+        const float4 p1 = *reinterpret_cast<const float4*>(&apart[(1 * NB + bq) * UPC + 4 * uq]);
+        const float4 p3 = *reinterpret_cast<const float4*>(&apart[(3 * NB + bq) * UPC + 4 * uq]);
+        const uint32_t dst = (uint32_t)(bq / NU);
+        st_async_v4f(mapa(sPqA + (uint32_t)(((bq % NU) * AT + UPC * (int)rank + 4 * uq) * 4), dst), mapa(barPq, dst),
+                     p1.x + p3.x, p1.y + p3.y, p1.z + p3.z, p1.w + p3.w);
+      }
+      if (tid == 0) mbar_expect_tx(barPq, NU * AT * 4);
+      mbar_wait(barPq, t & 1);
+    }
     float ctxv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) ctxv[e] = 0.0f;
     if (live_q) {
-      // query: lane holds dims 8*lane .. 8*lane+7 (one swizzled 16-byte chunk of the operand row)
-      const uint4 qraw = *reinterpret_cast<const uint4*>(gen + (sQ - base) + sw128h_off(NP, bl_att, 8 * lane));
-      att_fwd_core(role, qraw, ra, rb, p.align + ((size_t)t * B + b_att) * Tm, ctxv);
+      float q[8];
+      if constexpr (BAHD) {
+        const float4 q0 = *reinterpret_cast<const float4*>(&sPq[jl * AT + 8 * lane]);
+        const float4 q1 = *reinterpret_cast<const float4*>(&sPq[jl * AT + 8 * lane + 4]);
+        if (w4 == 0) {  // kept for the backward pass (without the bias)
+          float* dst = p.pq + ((size_t)t * B + b_att) * AT + 8 * lane;
+          *reinterpret_cast<float4*>(dst) = q0;
+          *reinterpret_cast<float4*>(dst + 4) = q1;
+        }
+        q[0] = q0.x + b8[0]; q[1] = q0.y + b8[1]; q[2] = q0.z + b8[2]; q[3] = q0.w + b8[3];
+        q[4] = q1.x + b8[4]; q[5] = q1.y + b8[5]; q[6] = q1.z + b8[6]; q[7] = q1.w + b8[7];
+      } else {
+        // query: lane holds dims 8*lane .. 8*lane+7 (one swizzled 16-byte chunk of the operand row)
+        const uint4 qraw = *reinterpret_cast<const uint4*>(gen + (sQ - base) + sw128h_off(NP, bl_att, 8 * lane));
+        unpack_q(qraw, q);
+      }
+      att_fwd_core<BAHD, BAHD>(role, q, v8, ra, rb, p.align + ((size_t)t * B + b_att) * Tm, ctxv);
     }
-    if (w4 == 0) {
+    if (BAHD && w4 == 0) {
+      // projected context ctx' = sum_t a_t PV_t: slices to the owners of the attention units (fp32)
+      if (b_att < B && !live_q) {
+        float* arow = p.align + ((size_t)t * B + b_att) * Tm;
+        for (int tm = lane; tm < Tm; tm += 32) arow[tm] = 0.0f;
+      }
+      const uint32_t dst = (uint32_t)(lane >> 3);
+      const uint32_t a0 = mapa(sCxA + (uint32_t)((bl_att * UPC + ((8 * lane) & (UPC - 1))) * 4), dst);
+      const uint32_t bar = mapa(barCtx, dst);
+      st_async_v4f(a0, bar, ctxv[0], ctxv[1], ctxv[2], ctxv[3]);
+      st_async_v4f(a0 + 16, bar, ctxv[4], ctxv[5], ctxv[6], ctxv[7]);
+    }
+    if (!BAHD && w4 == 0) {
       // ctx_t of this utterance: HBM (tf32-rounded fp32, for the backward pass) + all-gather (fp16, rows 8..15 of sQ)
       if (b_att < B) {
         float* dst = p.hc + ((size_t)t * B + b_att) * (H + DM) + H + 8 * lane;
@@ -412,46 +522,27 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     for (int e = 0; e < 4; ++e) fi[e] = f_in[e];
     drop_factors(t + 1);
     // ---------------- a_t = [ho | ctx] Wa for the CTA's 64 attention units ----------------
-    if (tid == 0) mbar_expect_tx(barCtx, NB * DM * 2);
+    if (tid == 0) mbar_expect_tx(barCtx, BAHD ? NB * UPC * 4 : NB * DM * 2);
     mbar_wait(barCtx, t & 1);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    issue_att();
-    mbar_wait(barM2, t & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
-      // warp (grp, q): accumulators 4 grp .. 4 grp + 3 of lane quarter q; quarters 0, 1 (ho rows) take columns 0..7,
-      // quarters 2, 3 (ctx rows) columns 8..15
-      const int grp = warp >> 2, q = warp & 3;
-      const uint32_t a0 = tmem_base + ((uint32_t)(32 * q) << 16) + (4 * grp) * NP + (q >= 2 ? 8 : 0);
-      uint32_t r0[8], r1[8], r2[8], r3[8];
-      tmem_ld8(a0, r0);
-      tmem_ld8(a0 + NP, r1);
-      tmem_ld8(a0 + 2 * NP, r2);
-      tmem_ld8(a0 + 3 * NP, r3);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      float* ap = apart + ((grp * 2 + (q >> 1)) * NB) * UPC + 32 * (q & 1) + lane;
-#pragma unroll
-      for (int b = 0; b < NB; ++b)
-        ap[b * UPC] = (__uint_as_float(r0[b]) + __uint_as_float(r1[b])) + (__uint_as_float(r2[b]) + __uint_as_float(r3[b]));
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    uint32_t selmask = 0u;  // SAMPLE: utterances of the cluster whose next input is drawn from this step's logits
-    if constexpr (SAMPLE) {
-      if (t + 1 < T) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-          if (b0 + b < B && avsr_rand_u32(seed, rstep, p.ss_stream, (uint32_t)t, (uint32_t)(b0 + b)) < p.thr_p) selmask |= 1u << b;
-      }
+    if constexpr (!BAHD) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      issue_att();
+      mbar_wait(barM2, t & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      att_epilogue();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if (comb) {
       float a[4];
       {
         const float4 p0 = *reinterpret_cast<const float4*>(&apart[(0 * NB + bq) * UPC + 4 * uq]);
-        const float4 p1 = *reinterpret_cast<const float4*>(&apart[(1 * NB + bq) * UPC + 4 * uq]);
         const float4 p2 = *reinterpret_cast<const float4*>(&apart[(2 * NB + bq) * UPC + 4 * uq]);
-        const float4 p3 = *reinterpret_cast<const float4*>(&apart[(3 * NB + bq) * UPC + 4 * uq]);
+        // Luong: planes 1, 3 hold the ctx half of the product; BAHD: the projected context arrived through sCx
+        const float4 p1 = BAHD ? *reinterpret_cast<const float4*>(&sCx[bq * UPC + 4 * uq])
+                               : *reinterpret_cast<const float4*>(&apart[(1 * NB + bq) * UPC + 4 * uq]);
+        const float4 p3 = BAHD ? make_float4(0.0f, 0.0f, 0.0f, 0.0f)
+                               : *reinterpret_cast<const float4*>(&apart[(3 * NB + bq) * UPC + 4 * uq]);
         a[0] = (p0.x + p1.x) + (p2.x + p3.x); a[1] = (p0.y + p1.y) + (p2.y + p3.y);
         a[2] = (p0.z + p1.z) + (p2.z + p3.z); a[3] = (p0.w + p1.w) + (p2.w + p3.w);
       }
@@ -469,11 +560,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
       if (b0 + bq < B) {
         const size_t row = (size_t)t * B + b0 + bq;
         const bool live = t < len_c;
-        *reinterpret_cast<float4*>(p.out + row * AT + ucol) =
-            live ? make_float4(a[0], a[1], a[2], a[3]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if constexpr (!BAHD)
+          *reinterpret_cast<float4*>(p.out + row * AT + ucol) =
+              live ? make_float4(a[0], a[1], a[2], a[3]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         *reinterpret_cast<float4*>(p.S + (row + B) * (AT + H) + ucol) = make_float4(ad[0], ad[1], ad[2], ad[3]);
       }
-      if constexpr (SAMPLE) {
+      if constexpr (SAMPLE && !BAHD) {
         if (selmask) *reinterpret_cast<float4*>(&sAf[bq * UPC + 4 * uq]) = make_float4(a[0], a[1], a[2], a[3]);
       }
     }
@@ -1046,8 +1138,17 @@ static ap4::DropCfg drop_cfg(const AvsrRnnSeq* r) {
   return d;
 }
 
+template <bool BAHD>
+static int launch_fwd_variant(cudaStream_t st, const AvsrRnnSeq* r, const ap4::DParams& p) {
+  if (r->samp)
+    return ap4::launch_cluster(st, ap4::attn_lstm_persist4d_fwd_kernel<true, BAHD>, r->B, ap4::DFWD_SMEM, p, AVSR_K_ATTN_FWD);
+  return ap4::launch_cluster(st, ap4::attn_lstm_persist4d_fwd_kernel<false, BAHD>, r->B, ap4::DFWD_SMEM, p, AVSR_K_ATTN_FWD);
+}
+
+// values_h: fp16 memory values (Luong family) or the fp16 PROJECTED values PV = values Wl_c (Bahdanau family)
 int attn_persist4d_launch_fwd(cudaStream_t st, const AvsrRnnSeq* r, const void* keys_h, const void* values_h) {
   const AvsrAttnMech& m = r->mech[0];
+  const bool bahd = m.kind >= AVSR_ATTN_BAHDANAU;
   ap4::DParams p;
   p.T = r->T; p.B = r->B; p.Tm = m.Tm; p.scaled = m.kind == AVSR_ATTN_SCALED_LUONG;
   p.len = r->len; p.mem_len = m.mem_len; p.gates = r->gates; p.Wrec = r->Wrec; p.Wa = m.Wl;
@@ -1055,6 +1156,8 @@ int attn_persist4d_launch_fwd(cudaStream_t st, const AvsrRnnSeq* r, const void* 
   p.g = m.g; p.c0 = r->c0; p.S = r->S; p.craw = r->craw; p.out = r->out; p.hc = m.hc; p.align = m.align;
   p.cT = r->cT; p.hT = r->hT;
   p.d = drop_cfg(r);
+  p.Wq = m.Wq; p.v = m.v; p.batt = m.bias; p.pq = m.pq;
+  if (bahd) AVSR_REQUIRE(m.Wq && m.v && m.pq, "rnn: Bahdanau mechanism without query layer / v / pq buffer");
   p.Wd = p.bd = p.emb = p.Wx = p.bias = nullptr;
   p.used_ids = p.sample_ids = nullptr; p.x = nullptr; p.V = p.E = 0; p.ss_stream = p.thr_p = 0u;
   if (r->samp) {
@@ -1064,9 +1167,8 @@ int attn_persist4d_launch_fwd(cudaStream_t st, const AvsrRnnSeq* r, const void* 
     p.Wd = s.Wd; p.bd = s.bd; p.emb = s.embedding; p.Wx = s.Wx; p.bias = s.bias;
     p.used_ids = s.used_ids; p.sample_ids = s.sample_ids; p.x = s.x; p.V = s.V; p.E = s.E;
     p.ss_stream = s.stream; p.thr_p = s.thr_p;
-    return ap4::launch_cluster(st, ap4::attn_lstm_persist4d_fwd_kernel<true>, r->B, ap4::DFWD_SMEM, p, AVSR_K_ATTN_FWD);
   }
-  return ap4::launch_cluster(st, ap4::attn_lstm_persist4d_fwd_kernel<false>, r->B, ap4::DFWD_SMEM, p, AVSR_K_ATTN_FWD);
+  return bahd ? launch_fwd_variant<true>(st, r, p) : launch_fwd_variant<false>(st, r, p);
 }
 
 int attn_persist4d_launch_bwd(cudaStream_t st, const AvsrRnnSeq* r, const void* keys_h, const void* values_h) {

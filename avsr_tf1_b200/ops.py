@@ -360,12 +360,13 @@ class MechBuffers:
         self.align = self.hc = self.pq = None
         self.dkeys = self.dvalues = self.dWl = self.dWq = self.dv = self.dg = self.dbias = self.dpq = None
         self.ds = self.dhc = None
+        self.values_op = None  # tf32-rounded copy of the memory (operand of tensor-core products), or None = values
 
     def fill(self, m: AvsrAttnMech):
         m.kind = ATTN_KINDS[self.kind]
         m.Tm, m.Dm, m.A = self.Tm, self.Dm, self.A
         for k in ('values', 'keys', 'mem_len', 'Wl', 'Wq', 'v', 'g', 'bias', 'align', 'hc', 'pq', 'dkeys', 'dvalues',
-                  'dWl', 'dWq', 'dv', 'dg', 'dbias', 'dpq', 'ds', 'dhc'):
+                  'dWl', 'dWq', 'dv', 'dg', 'dbias', 'dpq', 'ds', 'dhc', 'values_op'):
             setattr(m, k, _p(getattr(self, k)))
 
 

@@ -137,6 +137,8 @@ typedef struct AvsrAttnMech {
   float* dpq;           /* [T,B,A] scratch */
   float* ds;            /* [T,B,Tm] scratch: d(score) of every step (dkeys is formed after the loop) */
   float* dhc;           /* [T,B,H+Dm] scratch: d[cell output | context] of every step */
+  const float* values_op; /* [Tm,B,Dm] the memory as the operand of a tensor-core product (tf32-rounded copy) or NULL =
+                             values; read by the persistent Bahdanau kernels' projection PV = values Wl_c */
 } AvsrAttnMech;
 
 /* ScheduledEmbeddingTrainingHelper (decoder_unimodal.py:304-309) inside a whole-sequence call: step t's output decides,
