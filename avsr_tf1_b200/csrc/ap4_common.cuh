@@ -312,12 +312,30 @@ __device__ __forceinline__ void att_fwd_core(const AttRole& a, const float (&q)[
 // d(score) (ds_keep, same rows) stay in registers; the caller writes ds / d(attention_g) off the critical path.
 // Otherwise alignments come from a_s (shared memory, loaded by the caller) and this function writes `dsrow` (HBM) and
 // accumulates d(attention_g).  On return warp w4 == 0 holds dq (already scaled by g) in dqv.
-template <bool SMALL>
+// BAHD: the second sweep forms the gradient wrt the PROCESSED query instead: dpq_u += ds[tm] v_u (1 - th^2),
+// th = tanh(keys[tm]_u + q_u) recomputed (q = pq + bias, v the effective v); `values` is then whatever the first sweep
+// multiplies with dctx_s (the projected values and d(attention vector) in attn_persist4d.cu).
+template <bool BAHD>
+__device__ __forceinline__ void key_axpy8(float w, const uint4& r, const float (&q)[8], const float (&v)[8], float (&acc)[8]) {
+  if constexpr (!BAHD) {
+    axpy8(w, r, acc);
+  } else {
+    const float2 a = unpack_h2(r.x), b = unpack_h2(r.y), c = unpack_h2(r.z), d = unpack_h2(r.w);
+    const float k[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float th = tanhf_acc(k[e] + q[e]);
+      acc[e] = fmaf(w * v[e], 1.0f - th * th, acc[e]);
+    }
+  }
+}
+template <bool SMALL, bool BAHD = false>
 __device__ __forceinline__ void att_bwd_core(const AttRole& a, const float* __restrict__ dctx_s, uint4 (&ra)[4],
                                              uint4 (&rb)[4], const float (&al)[SMALL ? SMALL_B : 1],
                                              float (&ds_keep)[SMALL ? SMALL_B : 1], const float* __restrict__ a_s,
                                              float* __restrict__ ds_s, float* __restrict__ dsrow, bool scaled,
-                                             float* __restrict__ dg, float (&dqv)[8]) {
+                                             float* __restrict__ dg, float (&dqv)[8], const float (&q8)[8],
+                                             const float (&v8)[8]) {
   constexpr int MAXB = SMALL ? SMALL_B : 1;
   const int lane = a.lane, w4 = a.w4, gt = a.gt, L = a.L;
   float* red = a.red;
@@ -367,11 +385,11 @@ __device__ __forceinline__ void att_bwd_core(const AttRole& a, const float* __re
 #pragma unroll
       for (int j = 0; j < RIF; ++j) d[j] = __shfl_sync(0xffffffffu, da[i], reduce8_src(j));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) axpy8(d[j], ra[j], dqv);
+      for (int j = 0; j < 4; ++j) key_axpy8<BAHD>(d[j], ra[j], q8, v8, dqv);
 #pragma unroll
       for (int j = 0; j < 4; ++j) ra[j] = ld_row(a.keys, tm0 + 32 + 4 * j, L, a.B, a.b_att, lane);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) axpy8(d[4 + j], rb[j], dqv);
+      for (int j = 0; j < 4; ++j) key_axpy8<BAHD>(d[4 + j], rb[j], q8, v8, dqv);
 #pragma unroll
       for (int j = 0; j < 4; ++j) rb[j] = ld_row(a.keys, tm0 + 48 + 4 * j, L, a.B, a.b_att, lane);
     }
@@ -424,11 +442,11 @@ __device__ __forceinline__ void att_bwd_core(const AttRole& a, const float* __re
 #pragma unroll
       for (int j = 0; j < RIF; ++j) d[j] = tm0 + 4 * j < L ? ds_s[tm0 + 4 * j] : 0.0f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) axpy8(d[j], ra[j], dqv);
+      for (int j = 0; j < 4; ++j) key_axpy8<BAHD>(d[j], ra[j], q8, v8, dqv);
 #pragma unroll
       for (int j = 0; j < 4; ++j) ra[j] = ld_row(a.keys, tm0 + 32 + 4 * j, L, a.B, a.b_att, lane);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) axpy8(d[4 + j], rb[j], dqv);
+      for (int j = 0; j < 4; ++j) key_axpy8<BAHD>(d[4 + j], rb[j], q8, v8, dqv);
 #pragma unroll
       for (int j = 0; j < 4; ++j) rb[j] = ld_row(a.keys, tm0 + 48 + 4 * j, L, a.B, a.b_att, lane);
     }

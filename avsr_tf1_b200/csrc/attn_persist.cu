@@ -1143,8 +1143,11 @@ int attn_context_all(cudaStream_t st, int T, int B, int Tm, int Dm, const int* s
                      const float* align, const float* values, float* ctx, int ldc);  // attention.cu
 int cluster_width_ap();
 int rnn_sampling_fused(const AvsrRnnSeq* r) {
-  return r && r->rng && tensor_cores_enabled() && persist_shape_ok(r) && r->output_attention && cluster_width_ap() == 4 &&
-         !getenv("AVSR_NO_ATTN_PERSIST") && !(r->t_begin || r->t_end || r->stepwise);
+  if (!(r && r->rng && tensor_cores_enabled() && persist_shape_ok(r) && cluster_width_ap() == 4 &&
+        !getenv("AVSR_NO_ATTN_PERSIST") && !(r->t_begin || r->t_end || r->stepwise)))
+    return 0;
+  // Luong family: the wrapper emits the attention vector; Bahdanau family (persist_shape_ok): the cell output
+  return r->mech[0].kind >= AVSR_ATTN_BAHDANAU ? !getenv("AVSR_NO_BAHDANAU_PERSIST") : r->output_attention != 0;
 }
 
 size_t attn_persist_work_floats(int B, int H, int Dm, int Tm) {
@@ -1260,11 +1263,52 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
 int attn_outer(cudaStream_t st, int T, int B, int Tm, int C, const int* seq_len, const float* w, const float* x,
                int ldx, const float* scale, float* out);  // attention.cu
 
+int attn_persist4d_launch_bahd_bwd(cudaStream_t st, const AvsrRnnSeq* r, const void* keys_h, const void* pv_h);  // attn_persist4d.cu
+int attn_bahdanau_post(cudaStream_t st, int T, int B, int Tm, int A, const int* seq_len, const int* mem_len,
+                       const float* ds, const float* pq, const float* keys, const float* v, const float* bias,
+                       float* dkeys, float* dv, float* dbias);  // attention.cu
+
+// Backward of a single-mechanism Bahdanau-family layer on the two-product kernels.  Needs only the saved activations
+// (gates, craw, S, hc, pq, align): the fp16 keys and the projected values are rebuilt here.
+static int bahdanau_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
+  using namespace ap;
+  const AvsrAttnMech& m = r->mech[0];
+  const int T = r->T, B = r->B, At = m.A, SW = At + H, HD = H + m.Dm;
+  AVSR_REQUIRE(m.dpq && m.ds && m.dhc && r->dA, "rnn bwd: Bahdanau scratch (dpq / ds / dhc / dA) missing");
+  float* tmp = scratch + (size_t)HD * 4 * H;
+  __half* keys_h = reinterpret_cast<__half*>(tmp + (size_t)H * 4 * H);
+  __half* pv_h = keys_h + (size_t)m.Tm * B * H;
+  float* pv = pv_scratch(scratch, B, H, m.Dm, m.Tm);
+  AVSR_TRY(gemm(st, 0, 0, m.Tm * B, At, m.Dm, m.values_op ? m.values_op : m.values, m.Dm, m.Wl + (size_t)H * At, At, pv, At,
+                0.0f, nullptr));
+  const long long nk = (long long)m.Tm * B * H;
+  AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
+  AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, pv, pv_h, nk);
+  // rows of finished steps stay zero: dWq sums over all of them
+  AVSR_CHECK_CUDA(cudaMemsetAsync(m.dpq, 0, (size_t)T * B * At * sizeof(float), st));
+  AVSR_TRY(attn_persist4d_launch_bahd_bwd(st, r, keys_h, pv_h));
+  if (r->dh0)  // dh_0 += dz_0 Wh^T (the kernel stops before the product of step 0)
+    AVSR_TRY(gemm(st, 0, 1, B, H, 4 * H, r->dZ, 4 * H, r->Wrec + (size_t)At * 4 * H, 4 * H, r->dh0, H, 1.0f, nullptr));
+  // parameter gradients and per-utterance accumulations, all batched
+  AVSR_TRY(gemm(st, 1, 0, SW, 4 * H, T * B, r->S, SW, r->dZ, 4 * H, r->dWrec, 4 * H, 1.0f, nullptr));
+  AVSR_TRY(gemm(st, 1, 0, HD, At, T * B, m.hc, HD, r->dA, At, m.dWl, At, 1.0f, nullptr));
+  // dctx_t = da_t Wl_c^T for every step -> dvalues (through the contexts)
+  AVSR_TRY(gemm(st, 0, 1, T * B, m.Dm, At, r->dA, At, m.Wl + (size_t)H * At, At, m.dhc + H, HD, 0.0f, nullptr));
+  AVSR_TRY(attn_outer(st, T, B, m.Tm, m.Dm, r->len, m.align, m.dhc + H, HD, nullptr, m.dvalues));
+  AVSR_TRY(gemm(st, 1, 0, H, At, T * B, m.hc, HD, m.dpq, At, m.dWq, At, 1.0f, nullptr));
+  return attn_bahdanau_post(st, T, B, m.Tm, At, r->len, m.mem_len, m.ds, m.pq, m.keys, m.v, m.bias, m.dkeys, m.dv, m.dbias);
+}
+
 int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch, bool unfused) {
   using namespace ap;
   if (r->n_mech != 1 || r->T <= 1) return -1;
   const AvsrAttnMech& m = r->mech[0];
-  if (m.kind > AVSR_ATTN_SCALED_LUONG) return -1;
+  if (m.kind > AVSR_ATTN_SCALED_LUONG) {
+    if (!persist_shape_ok(r) || cluster_width() != 4 || getenv("AVSR_NO_BAHDANAU_PERSIST") ||
+        getenv("AVSR_NO_BAHDANAU_PERSIST_BWD"))
+      return -1;
+    return bahdanau_persist_bwd(st, r, scratch);
+  }
   if (r->H != H || m.A != H || m.Dm != DM || m.Tm > MAX_TM) return -1;
   unfused = unfused || unfused_fwd(r);
   if (unfused && (!r->output_attention || cluster_width() != 4)) return -1;

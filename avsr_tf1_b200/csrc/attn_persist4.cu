@@ -508,6 +508,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
   float* red = red_all + jl * 8;
   const uint32_t att_bar_id = 2 + jl;
   const AttRole role = {p.keys, p.values, L, B, b_att, Tm, w4, gt, lane, gs, att_bar_id, nullptr, part, red};
+  const float vzero8[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   // reduce-scatter role after the product: warps 0-3 forward tiles 0, 1 (h rows), warps 4-7 tiles 2, 3 (ctx dims)
   const int q = warp & 3;
 
@@ -582,7 +583,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4_bwd_kernel(cons
 #pragma unroll
     for (int i = 0; i < MAXB; ++i) ds_keep[i] = 0.0f;
     if (live_q)
-      att_bwd_core<SMALL>(role, dctx_s, ra, rb, al, ds_keep, a_s, ds_s, p.ds + ((size_t)t * B + b_att) * Tm, p.scaled != 0, p.dg, dqv);
+      att_bwd_core<SMALL>(role, dctx_s, ra, rb, al, ds_keep, a_s, ds_s, p.ds + ((size_t)t * B + b_att) * Tm, p.scaled != 0, p.dg, dqv,
+                          vzero8, vzero8);
     AP4B_STAMP(3);
     if (w4 == 0) {
       // dq dims 8*lane .. +7 belong to the CTA owning units (8*lane)/64

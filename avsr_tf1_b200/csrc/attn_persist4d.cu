@@ -59,7 +59,8 @@ struct DParams {
   float* S;              // [(T+1),B,AT+H]; S[0] by the caller; rows 1.. = [a (.) m_in | hs], tf32-rounded
   float* craw;           // [T,B,H]
   float* out;            // [T,B,AT] attention vectors (tf32-rounded), zero past the length
-  float* hc;             // [T,B,H+DM]  [ho | ctx], tf32-rounded
+  float* hc;             // [T,B,ldhc]  [ho | ctx], tf32-rounded (BAHD: only the ho columns; ldhc = H + memory depth)
+  int ldhc;
   float* align;          // [T,B,Tm]
   float* cT;             // [B,H] or null
   float* hT;             // [B,H] or null
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
       const int u0 = UPC * rank + 4 * uq;
       *reinterpret_cast<float4*>(p.craw + row * H + u0) = make_float4(cr[0], cr[1], cr[2], cr[3]);
       *reinterpret_cast<float4*>(p.S + (row + B) * (AT + H) + AT + u0) = make_float4(hs[0], hs[1], hs[2], hs[3]);
-      *reinterpret_cast<float4*>(p.hc + row * (H + DM) + u0) = make_float4(ho[0], ho[1], ho[2], ho[3]);
+      *reinterpret_cast<float4*>(p.hc + row * p.ldhc + u0) = make_float4(ho[0], ho[1], ho[2], ho[3]);
       if constexpr (BAHD)  // the wrapper emits the cell output for the Bahdanau family (zero past the length)
         *reinterpret_cast<float4*>(p.out + row * H + u0) =
             t < len_c ? make_float4(ho[0], ho[1], ho[2], ho[3]) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     if (!BAHD && w4 == 0) {
       // ctx_t of this utterance: HBM (tf32-rounded fp32, for the backward pass) + all-gather (fp16, rows 8..15 of sQ)
       if (b_att < B) {
-        float* dst = p.hc + ((size_t)t * B + b_att) * (H + DM) + H + 8 * lane;
+        float* dst = p.hc + ((size_t)t * B + b_att) * p.ldhc + H + 8 * lane;
         *reinterpret_cast<float4*>(dst) = make_float4(ctxv[0], ctxv[1], ctxv[2], ctxv[3]);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(ctxv[4], ctxv[5], ctxv[6], ctxv[7]);
         if (!live_q) {
@@ -856,6 +857,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bwd_kernel(con
   float* red = red_all + jl * 8;
   const uint32_t att_bar_id = 2 + jl;
   const AttRole role = {p.keys, p.values, L, B, b_att, Tm, w4, gt, lane, gs, att_bar_id, nullptr, part, red};
+  const float vzero8[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   // product-issue / reduce-scatter roles
   const int q = warp & 3;
   const int mt_i = warp >> 1, hj_i = warp & 1;
@@ -998,7 +1000,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bwd_kernel(con
 #pragma unroll
     for (int i = 0; i < MAXB; ++i) ds_keep[i] = 0.0f;
     if (live_q)
-      att_bwd_core<SMALL>(role, dctx_s, ra, rb, al, ds_keep, a_s, ds_s, p.ds + ((size_t)t * B + b_att) * Tm, p.scaled != 0, p.dg, dqv);
+      att_bwd_core<SMALL>(role, dctx_s, ra, rb, al, ds_keep, a_s, ds_s, p.ds + ((size_t)t * B + b_att) * Tm, p.scaled != 0, p.dg, dqv,
+                          vzero8, vzero8);
     if (w4 == 0) {
       // dq dims 8*lane .. +7 belong to the CTA owning units (8*lane)/64
       const uint32_t dst = (uint32_t)(lane >> 3);
@@ -1124,6 +1127,462 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bwd_kernel(con
   cluster_sync_all();
 }
 
+
+// =====================================================================================================
+// backward, Bahdanau family (see the BAHD notes at the forward kernel).  Per step t (descending):
+//   da_t   = dSa_t (.) m_in(t+1)                                 (kept for dWl; sent to the owners of the utterances)
+//   d(align) = PV . da_t -> softmax backward -> ds -> dpq_u = sum_tm ds[tm] v_u (1 - tanh^2(keys[tm]_u + pq_u + b_u))
+//   d ho   = da_t Wl_h^T + dpq_t Wq^T                            (ONE product: K = [64 attention units | 64 query units] of
+//                                                                  the CTA, the dpq half issued when the sweeps are done)
+//   dh_t   = (d ho + dout_t) (.) m_out(t) + dSh_t (.) m_state(t) -> gate gradients -> dS_{t-1} = dz_t [Wl_att ; Wh]^T
+// =====================================================================================================
+struct DBahdBwdParams {
+  int T, B, Tm;
+  float grad_scale, inv_grad_scale;
+  const int* len;
+  const int* mem_len;
+  const float* gates;    // [T,B,4H] activations
+  const float* craw;     // [T,B,H]
+  const float* c0;       // [B,H] or null
+  const float* Wrec;     // [(AT+H),4H]
+  const float* Wa;       // attention_layer kernel [(H+Dm),AT] (only its first H rows enter the recurrence)
+  const float* Wq;       // [H,AT]
+  const float* v;        // [AT] effective v
+  const float* batt;     // [AT] or null
+  const __half* keys;    // [Tm,B,AT]
+  const __half* pv;      // [Tm,B,AT] projected values
+  const float* pq;       // [T,B,AT] processed queries of the forward pass
+  const float* align;    // [T,B,Tm]
+  const float* dout;     // [T,B,H] gradient wrt the emitted cell output, or null
+  const float* dcT;      // [B,H] or null
+  const float* dhT;      // [B,H] or null
+  float* dZ;             // [T,B,4H]
+  float* ds;             // [T,B,Tm]
+  float* dpq;            // [T,B,AT]
+  float* dA;             // [T,B,AT]
+  float* dc0;            // [B,H] or null
+  float* dh0;            // [B,H] or null
+  float* dbias;          // [4H] or null
+  DropCfg d;
+};
+constexpr size_t DBAHD_BWD_SMEM = (size_t)2 * BW_TILE_BYTES + BW_DZ_BYTES + 2 * BW_DA_BYTES + 3 * REDH_FLOATS * 4 +
+                                  NU * 4 * DM * 4 + DQ_FLOATS * 4 + NU * AT * 4 + 2 * NU * MAX_TM * 4 + NU * 8 * 4 + 96 + 1024;
+
+template <bool SMALL>
+__global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bahd_bwd_kernel(const DBahdBwdParams p) {
+  constexpr int MAXB = SMALL ? SMALL_B : 1;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW = base;                                  // tiles 0, 1 (attention rows) of Wrec^T
+  const uint32_t sDz = sW + 2 * BW_TILE_BYTES;
+  const uint32_t sDa = sDz + BW_DZ_BYTES;                    // B operand, da half of product 2
+  const uint32_t sDp = sDa + BW_DA_BYTES;                    // B operand, dpq half of product 2
+  const uint32_t sRedA = sDp + BW_DA_BYTES;                  // partial dSa of the CTA's attention units
+  const uint32_t sRedH = sRedA + REDH_FLOATS * 4;            // partial dSh of the CTA's hidden units
+  const uint32_t sRedH2 = sRedH + REDH_FLOATS * 4;           // partial d ho of the CTA's hidden units
+  const uint32_t sPart = sRedH2 + REDH_FLOATS * 4;           // [NU][4][DM] per-warp partial dpq
+  const uint32_t sDq = sPart + NU * 4 * DM * 4;              // dpq of the CTA's query units [src][utt][u]
+  const uint32_t sDaU = sDq + DQ_FLOATS * 4;                 // da of the CTA's utterances [NU][AT]
+  const uint32_t sSc = sDaU + NU * AT * 4;                   // [NU][MAX_TM] alignments (long memories only)
+  const uint32_t sDs = sSc + NU * MAX_TM * 4;                // [NU][MAX_TM] d(align) / ds (long memories only)
+  const uint32_t sRed = sDs + NU * MAX_TM * 4;               // [NU][8]
+  const uint32_t sBar = sRed + NU * 8 * 4;
+  const uint32_t sTmem = sBar + 72;
+  const uint32_t barMma = sBar, barMma2 = sBar + 8, barDz = sBar + 16, barRedA = sBar + 24, barRedH = sBar + 32,
+                 barRedH2 = sBar + 40, barDaU = sBar + 48, barDq = sBar + 56;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  float* redA = reinterpret_cast<float*>(gen + (sRedA - base));
+  float* redH = reinterpret_cast<float*>(gen + (sRedH - base));
+  float* redH2 = reinterpret_cast<float*>(gen + (sRedH2 - base));
+  float* dqb = reinterpret_cast<float*>(gen + (sDq - base));
+  float* dau_all = reinterpret_cast<float*>(gen + (sDaU - base));
+  float* part_all = reinterpret_cast<float*>(gen + (sPart - base));
+  float* red_all = reinterpret_cast<float*>(gen + (sRed - base));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int b0 = cluster_id_x() * NB;
+  const int T = p.T, B = p.B, Tm = p.Tm;
+
+  if (tid == 0) {
+    mbar_init(barMma, THREADS / 32);   // one commit per issuing warp
+    mbar_init(barMma2, THREADS / 32);
+    mbar_init(barDz, THREADS);
+    mbar_init(barRedA, 1);
+    mbar_init(barRedH, 1);
+    mbar_init(barRedH2, 1);
+    mbar_init(barDaU, 1);
+    mbar_init(barDq, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // tensor memory (all 512 columns): [0, 128) accumulators of both products; [128, 256) the two 128-row tiles (ho dims) of
+  // [Wl_h^T | Wq^T] restricted to the CTA's 64 attention / query units (K = 128: 64 columns each); [256, 512) tiles 2, 3
+  // (h rows) of Wrec^T
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // A[n][k = g*64 + u] = Wrec[n][g*H + 64*rank + u]; rows n < 256 (attention) -> shared memory (tile n >> 7)
+  for (int seg = warp; seg < 256 * 8; seg += THREADS / 32) {
+    const int n = seg >> 3, g = (seg >> 1) & 3, u = 32 * (seg & 1) + lane;
+    const float w = p.Wrec[(size_t)n * 4 * H + g * H + UPC * rank + u];
+    *reinterpret_cast<__half*>(gen + (sW - base) + (n >> 7) * BW_TILE_BYTES + sw128h_off(128, n & 127, g * 64 + u)) =
+        __float2half_rn(w);
+  }
+  for (int i = tid; i < (BW_DZ_BYTES + 2 * BW_DA_BYTES) / 4; i += THREADS) reinterpret_cast<uint32_t*>(gen + (sDz - base))[i] = 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
+  const uint32_t tB2 = tmem_base + 128, tA = tmem_base + 256;
+  {
+    // rows n = 256 + 128*tt + 32*q + lane (h rows) -> tensor memory tile tt; column c holds k = 2c, 2c+1 (adjacent units)
+    const int q = warp & 3, tt = warp >> 2;
+    const float* row = p.Wrec + (size_t)(256 + 128 * tt + 32 * q + lane) * 4 * H + UPC * rank;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t r[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = 2 * (c0 + c), g = k >> 6, u = k & 63;
+        const float2 w = *reinterpret_cast<const float2*>(row + g * H + u);
+        r[c] = pack_h2(w.x, w.y);
+      }
+      tmem_st32(tA + 128 * tt + c0 + ((uint32_t)(32 * q) << 16), r);
+    }
+    // [Wl_h^T | Wq^T]: row n = 128*tt + 32*q + lane (ho dim), K = the CTA's 64 attention units, then its 64 query units
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+      const float* wrow = (i == 0 ? p.Wa : p.Wq) + (size_t)(128 * tt + 32 * q + lane) * AT + UPC * rank;
+      uint32_t r[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float2 w = *reinterpret_cast<const float2*>(wrow + 2 * c);
+        r[c] = pack_h2(w.x, w.y);
+      }
+      tmem_st32(tB2 + 64 * tt + 32 * i + ((uint32_t)(32 * q) << 16), r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  cluster_sync_all();
+
+  const uint64_t dWt = make_desc_k128(sW), dDz = make_desc_k128(sDz), dDa = make_desc_k128(sDa), dDp = make_desc_k128(sDp);
+  // gate-gradient role: thread = (local unit ul - hidden, attention and query -, utterances 2*(warp >> 1) + j)
+  constexpr int PB = 2;
+  const int ul = 32 * (warp & 1) + lane;
+  const int unit = UPC * rank + ul;
+  float dc[PB], dh_carry[PB];
+  int len_t[PB];
+#pragma unroll
+  for (int j = 0; j < PB; ++j) {
+    const int b = b0 + (warp >> 1) * PB + j;
+    len_t[j] = (b < B) ? p.len[b] : 0;
+    dc[j] = (b < B && p.dcT) ? p.dcT[(size_t)b * H + unit] : 0.0f;
+    dh_carry[j] = (b < B && p.dhT) ? p.dhT[(size_t)b * H + unit] : 0.0f;
+  }
+  const uint32_t seed = p.d.rng ? p.d.rng[0] : 0u, rstep = p.d.rng ? p.d.rng[1] : 0u;
+  float gi[PB], gj[PB], gf[PB], go[PB], crw[PB], cpv[PB], dov[PB];
+#pragma unroll
+  for (int j = 0; j < PB; ++j) gi[j] = gj[j] = gf[j] = go[j] = crw[j] = cpv[j] = dov[j] = 0.0f;
+  auto load_step = [&](int t) {
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int b = b0 + (warp >> 1) * PB + j;
+      if (t >= 0 && t < len_t[j]) {
+        const float* g = p.gates + ((size_t)t * B + b) * 4 * H + unit;
+        gi[j] = g[0]; gj[j] = g[H]; gf[j] = g[2 * H]; go[j] = g[3 * H];
+        const size_t o = ((size_t)t * B + b) * H + unit;
+        crw[j] = p.craw[o];
+        cpv[j] = t > 0 ? p.craw[o - (size_t)B * H] : (p.c0 ? p.c0[(size_t)b * H + unit] : 0.0f);
+        dov[j] = p.dout ? p.dout[o] : 0.0f;  // wrt the emitted cell output
+      }
+    }
+  };
+  // attention role
+  const int jl = warp >> 2, w4 = warp & 3, gt = tid & 127;
+  const int bl_att = NU * (int)rank + jl;
+  const int b_att = b0 + bl_att;
+  const int len_q = (b_att < B) ? p.len[b_att] : 0;
+  const int L = (b_att < B) ? min(p.mem_len[b_att], Tm) : 0;
+  float* dau_s = dau_all + jl * AT;
+  float* a_s = reinterpret_cast<float*>(gen + (sSc - base)) + jl * MAX_TM;
+  float* ds_s = reinterpret_cast<float*>(gen + (sDs - base)) + jl * MAX_TM;
+  float* part = part_all + jl * 4 * DM;
+  float* red = red_all + jl * 8;
+  const uint32_t att_bar_id = 2 + jl;
+  const AttRole role = {p.keys, p.pv, L, B, b_att, Tm, w4, gt, lane, 1.0f, att_bar_id, nullptr, part, red};
+  float v8[8], b8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    v8[e] = p.v[8 * lane + e];
+    b8[e] = p.batt ? p.batt[8 * lane + e] : 0.0f;
+  }
+  // product roles: product 2: warp (mt_b, ks_b) issues K step ks_b of both halves of tile mt_b and reduce-scatters the tile's
+  // lane quarter q; product 1: warp (mt_i, hj_i) as in the Luong kernel
+  const int q = warp & 3;
+  const int mt_b = warp >> 2, ks_b = warp & 3;
+  const uint32_t acc_b = tmem_base + warp * NP;
+  const int mt_i = warp >> 1, hj_i = warp & 1;
+  const uint32_t acc_i = tmem_base + (2 * mt_i + hj_i) * NP;
+
+  float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  load_step(T - 1);
+  for (int it = 0; it < T; ++it) {
+    const int t = T - 1 - it;
+    const bool live_q = t < len_q;
+    uint4 ra[4], rb[4];
+    float al[MAXB], q8[8];
+    const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) al[i] = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) q8[e] = 0.0f;
+    if (live_q) {
+      att_prefetch(role, p.pv, ra, rb);
+      const float* pqr = p.pq + ((size_t)t * B + b_att) * AT + 8 * lane;
+      const float4 q0 = *reinterpret_cast<const float4*>(pqr), q1 = *reinterpret_cast<const float4*>(pqr + 4);
+      q8[0] = q0.x + b8[0]; q8[1] = q0.y + b8[1]; q8[2] = q0.z + b8[2]; q8[3] = q0.w + b8[3];
+      q8[4] = q1.x + b8[4]; q8[5] = q1.y + b8[5]; q8[6] = q1.z + b8[6]; q8[7] = q1.w + b8[7];
+      if constexpr (SMALL) {
+#pragma unroll
+        for (int i = 0; i < MAXB; ++i) {
+          const int tm = w4 + 32 * i + 4 * jrow;
+          if (tm < L) al[i] = p.align[((size_t)t * B + b_att) * Tm + tm];
+        }
+      } else {
+        for (int tm = gt; tm < Tm; tm += 128) a_s[tm] = p.align[((size_t)t * B + b_att) * Tm + tm];
+      }
+    }
+    float f_in[PB], f_st[PB], f_o[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const uint32_t idx = (uint32_t)(b0 + (warp >> 1) * PB + j) * (uint32_t)H + (uint32_t)unit;  // H == AT
+      f_in[j] = dfac(seed, rstep, p.d.stream, p.d.thr_in, p.d.inv_in, (uint32_t)(t + 1), idx);
+      f_st[j] = dfac(seed, rstep, p.d.stream + 1u, p.d.thr_state, p.d.inv_state, (uint32_t)t, idx);
+      f_o[j] = dfac(seed, rstep, p.d.stream + 2u, p.d.thr_out, p.d.inv_out, (uint32_t)t, idx);
+    }
+    // ---- (A) dS_t pushed during the previous iteration -> da_t (operand of product 2; to the utterances' owners) -----
+    float dh_in[PB], sa[PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      dh_in[j] = dh_carry[j];
+      sa[j] = 0.0f;
+    }
+    if (it > 0) {
+      if (tid == 0) {
+        mbar_expect_tx(barRedA, REDH_FLOATS * 4);
+        mbar_expect_tx(barRedH, REDH_FLOATS * 4);
+      }
+      mbar_wait(barRedA, (it - 1) & 1);
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int bl = (warp >> 1) * PB + j;
+#pragma unroll
+        for (int src = 0; src < CL; ++src) sa[j] += redA[(src * NB + bl) * UPC + ul];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int bl = (warp >> 1) * PB + j;
+      const float da = (t < len_t[j]) ? tf32_rn(sa[j] * f_in[j]) : 0.0f;
+      if (b0 + bl < B) p.dA[((size_t)t * B + b0 + bl) * AT + unit] = da;
+      *reinterpret_cast<__half*>(gen + (sDa - base) + sw128h_off(NP, bl, ul)) = __float2half_rn(da * p.grad_scale);
+      const uint32_t dst = (uint32_t)(bl / NU);
+      st_async_f(mapa(sDaU + (uint32_t)(((bl % NU) * AT + unit) * 4), dst), mapa(barDaU, dst), da);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- (B) product 2, da half: d ho partial from the CTA's 64 attention units (the dpq half follows the sweeps) -----
+    if (lane == 0) umma_ts(acc_b, tB2 + 64 * mt_b + ks_b * 8, desc_at(dDa, ks_b * 32), IDESC, 0u);
+    __syncwarp();
+    if (it > 0) {
+      mbar_wait(barRedH, (it - 1) & 1);
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        const int bl = (warp >> 1) * PB + j;
+#pragma unroll
+        for (int src = 0; src < CL; ++src) dh_in[j] += redH[(src * NB + bl) * UPC + ul];
+      }
+    }
+    // ---- (E) attention backward of the CTA's utterances: da of all 256 attention units has been gathered ------------
+    if (tid == 0) mbar_expect_tx(barDaU, NU * AT * 4);
+    mbar_wait(barDaU, it & 1);
+    float dqv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dqv[e] = 0.0f;
+    float ds_keep[MAXB];
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) ds_keep[i] = 0.0f;
+    if (live_q)
+      att_bwd_core<SMALL, true>(role, dau_s, ra, rb, al, ds_keep, a_s, ds_s, p.ds + ((size_t)t * B + b_att) * Tm, false, nullptr,
+                                dqv, q8, v8);
+    if (w4 == 0) {
+      if (live_q) {  // dpq of this step: kept for dWq and the post-loop dkeys / dv pass
+        float* dst = p.dpq + ((size_t)t * B + b_att) * AT + 8 * lane;
+        *reinterpret_cast<float4*>(dst) = make_float4(dqv[0], dqv[1], dqv[2], dqv[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(dqv[4], dqv[5], dqv[6], dqv[7]);
+      }
+      // dpq dims 8*lane .. +7 belong to the CTA owning query units (8*lane)/64
+      const uint32_t dst = (uint32_t)(lane >> 3);
+      const uint32_t a0 = mapa(sDq + (uint32_t)(((rank * NU + jl) * UPC + ((8 * lane) & (UPC - 1))) * 4), dst);
+      const uint32_t bar = mapa(barDq, dst);
+      st_async_v4f(a0, bar, dqv[0], dqv[1], dqv[2], dqv[3]);
+      st_async_v4f(a0 + 16, bar, dqv[4], dqv[5], dqv[6], dqv[7]);
+    }
+    // ---- (F') dpq of this CTA's query units -> second half of product 2 -> d ho partials to the owners ---------------
+    if (tid == 0) mbar_expect_tx(barDq, DQ_FLOATS * 4);
+    mbar_wait(barDq, it & 1);
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int bl = (warp >> 1) * PB + j;
+      *reinterpret_cast<__half*>(gen + (sDp - base) + sw128h_off(NP, bl, ul)) = __float2half_rn(dqb[bl * UPC + ul] * p.grad_scale);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (lane == 0) {
+      umma_ts(acc_b, tB2 + 64 * mt_b + 32 + ks_b * 8, desc_at(dDp, ks_b * 32), IDESC, 1u);
+      umma_commit(barMma2);
+    }
+    __syncwarp();
+    mbar_wait(barMma2, it & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      // warp (mt_b, q): rows 128*mt_b + 32*q + lane of d ho, summed over the four K-step accumulators of the tile
+      uint32_t r0[8], r1[8], r2[8], r3[8];
+      const uint32_t a0 = tmem_base + ((uint32_t)(32 * q) << 16) + (4 * mt_b) * NP;
+      tmem_ld8(a0, r0);
+      tmem_ld8(a0 + NP, r1);
+      tmem_ld8(a0 + 2 * NP, r2);
+      tmem_ld8(a0 + 3 * NP, r3);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const uint32_t dst = (uint32_t)(2 * mt_b + (q >> 1));
+      const uint32_t d0 = mapa(sRedH2 + (uint32_t)((rank * NB) * UPC + 32 * (q & 1) + lane) * 4, dst);
+      const uint32_t bar = mapa(barRedH2, dst);
+#pragma unroll
+      for (int c = 0; c < NB; ++c)
+        st_async_f(d0 + c * UPC * 4, bar,
+                   ((__uint_as_float(r0[c]) + __uint_as_float(r1[c])) + (__uint_as_float(r2[c]) + __uint_as_float(r3[c]))) * p.inv_grad_scale);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    // ---- (F) d ho of this CTA's units -> gate gradients --------------------------------------------------------------
+    if (tid == 0) mbar_expect_tx(barRedH2, REDH_FLOATS * 4);
+    mbar_wait(barRedH2, it & 1);
+    float dz[4][PB];
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int bl = (warp >> 1) * PB + j;
+      if (t < len_t[j]) {
+        float dho = dov[j];
+#pragma unroll
+        for (int src = 0; src < CL; ++src) dho += redH2[(src * NB + bl) * UPC + ul];
+        const float dh = dh_in[j] * f_st[j] + dho * f_o[j];
+        const float c = fminf(fmaxf(crw[j], -1.0f), 1.0f);
+        const float tc = tanhf_acc(c);
+        const float cp = t > 0 ? fminf(fmaxf(cpv[j], -1.0f), 1.0f) : cpv[j];
+        const float dct = dc[j] + dh * go[j] * (1.0f - tc * tc);
+        const float dcr = (crw[j] >= -1.0f && crw[j] <= 1.0f) ? dct : 0.0f;
+        dz[0][j] = dcr * gj[j] * gi[j] * (1.0f - gi[j]);
+        dz[1][j] = dcr * gi[j] * (1.0f - gj[j] * gj[j]);
+        dz[2][j] = dcr * cp * gf[j] * (1.0f - gf[j]);
+        dz[3][j] = dh * tc * go[j] * (1.0f - go[j]);
+        dc[j] = dcr * gf[j];
+        dh_carry[j] = 0.0f;
+      } else {
+        dz[0][j] = dz[1][j] = dz[2][j] = dz[3][j] = 0.0f;
+        dh_carry[j] = dh_in[j];
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<__half*>(gen + (sDz - base) + sw128h_off(NP, bl, g * 64 + ul)) = __float2half_rn(dz[g][j] * p.grad_scale);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    mbar_arrive(barDz);
+    {
+      mbar_wait(barDz, it & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int kb = 2 * hj_i + kk;
+            const uint64_t db = desc_at(dDz, kb * (NP * 128) + k4 * 32);
+            if (mt_i < 2)
+              umma_ss(acc_i, desc_at(dWt, mt_i * BW_TILE_BYTES + kb * (128 * 128) + k4 * 32), db, IDESC, (kk | k4) ? 1u : 0u);
+            else
+              umma_ts(acc_i, tA + (mt_i - 2) * 128 + (kb * 4 + k4) * 8, db, IDESC, (kk | k4) ? 1u : 0u);
+          }
+        umma_commit(barMma);
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+      const int b = b0 + (warp >> 1) * PB + j;
+      if (b < B) {
+        float* o = p.dZ + ((size_t)t * B + b) * 4 * H + unit;
+        o[0] = tf32_rn(dz[0][j]); o[H] = tf32_rn(dz[1][j]); o[2 * H] = tf32_rn(dz[2][j]); o[3 * H] = tf32_rn(dz[3][j]);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) bsum[g] += tf32_rn(dz[g][j]);
+      }
+    }
+    load_step(t - 1);
+    if constexpr (SMALL) {
+      if (live_q) att_bwd_small_tail(role, p.ds + ((size_t)t * B + b_att) * Tm, al, ds_keep, false, nullptr);
+    }
+    // ---- (G) partial dS_{t-1} -> owners of the attention / hidden units -------------------------------------------
+    mbar_wait(barMma, it & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (it + 1 < T) {
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int mt = 2 * (warp >> 2) + mi;  // tiles 0, 1: attention units; 2, 3: hidden units
+        uint32_t r[8], r1[8];
+        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (2 * mt) * NP, r);
+        tmem_ld8(tmem_base + ((uint32_t)(32 * q) << 16) + (2 * mt + 1) * NP, r1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < NB; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(r1[c]));
+        const uint32_t dst = (uint32_t)(2 * (mt & 1) + (q >> 1));
+        const uint32_t buf = mt < 2 ? sRedA : sRedH;
+        const uint32_t a0 = mapa(buf + (uint32_t)((rank * NB) * UPC + 32 * (q & 1) + lane) * 4, dst);
+        const uint32_t bar = mapa(mt < 2 ? barRedA : barRedH, dst);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) st_async_f(a0 + c * UPC * 4, bar, __uint_as_float(r[c]) * p.inv_grad_scale);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+#pragma unroll
+  for (int j = 0; j < PB; ++j) {
+    const int b = b0 + (warp >> 1) * PB + j;
+    if (b < B) {
+      if (p.dh0) p.dh0[(size_t)b * H + unit] = dh_carry[j];
+      if (p.dc0) p.dc0[(size_t)b * H + unit] = dc[j];
+    }
+  }
+  if (p.dbias) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) atomicAdd(p.dbias + g * H + unit, bsum[g]);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  cluster_sync_all();
+}
+
 }  // namespace ap4
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1153,7 +1612,8 @@ int attn_persist4d_launch_fwd(cudaStream_t st, const AvsrRnnSeq* r, const void* 
   p.T = r->T; p.B = r->B; p.Tm = m.Tm; p.scaled = m.kind == AVSR_ATTN_SCALED_LUONG;
   p.len = r->len; p.mem_len = m.mem_len; p.gates = r->gates; p.Wrec = r->Wrec; p.Wa = m.Wl;
   p.keys = reinterpret_cast<const __half*>(keys_h); p.values = reinterpret_cast<const __half*>(values_h);
-  p.g = m.g; p.c0 = r->c0; p.S = r->S; p.craw = r->craw; p.out = r->out; p.hc = m.hc; p.align = m.align;
+  p.g = m.g; p.c0 = r->c0; p.S = r->S; p.craw = r->craw; p.out = r->out; p.hc = m.hc; p.ldhc = r->H + m.Dm;
+  p.align = m.align;
   p.cT = r->cT; p.hT = r->hT;
   p.d = drop_cfg(r);
   p.Wq = m.Wq; p.v = m.v; p.batt = m.bias; p.pq = m.pq;
@@ -1186,6 +1646,25 @@ int attn_persist4d_launch_bwd(cudaStream_t st, const AvsrRnnSeq* r, const void* 
   return m.Tm <= ap4::SMALL_TM
              ? ap4::launch_cluster(st, ap4::attn_lstm_persist4d_bwd_kernel<true>, r->B, ap4::DBWD_SMEM, p, AVSR_K_ATTN_BWD)
              : ap4::launch_cluster(st, ap4::attn_lstm_persist4d_bwd_kernel<false>, r->B, ap4::DBWD_SMEM, p, AVSR_K_ATTN_BWD);
+}
+
+// keys_h / pv_h: fp16 keys and projected values (see attn_persist4d_launch_fwd)
+int attn_persist4d_launch_bahd_bwd(cudaStream_t st, const AvsrRnnSeq* r, const void* keys_h, const void* pv_h) {
+  const AvsrAttnMech& m = r->mech[0];
+  ap4::DBahdBwdParams p;
+  p.T = r->T; p.B = r->B; p.Tm = m.Tm;
+  p.grad_scale = r->grad_scale > 0.0f ? r->grad_scale : 1.0f;
+  p.inv_grad_scale = 1.0f / p.grad_scale;
+  p.len = r->len; p.mem_len = m.mem_len; p.gates = r->gates; p.craw = r->craw; p.c0 = r->c0;
+  p.Wrec = r->Wrec; p.Wa = m.Wl; p.Wq = m.Wq; p.v = m.v; p.batt = m.bias;
+  p.keys = reinterpret_cast<const __half*>(keys_h); p.pv = reinterpret_cast<const __half*>(pv_h);
+  p.pq = m.pq; p.align = m.align; p.dout = r->dout; p.dcT = r->dcT; p.dhT = r->dhT;
+  p.dZ = r->dZ; p.ds = m.ds; p.dpq = m.dpq; p.dA = r->dA; p.dc0 = r->dc0; p.dh0 = r->dh0; p.dbias = r->dbias;
+  p.d = drop_cfg(r);
+  AVSR_REQUIRE(m.Wq && m.v && m.pq && m.dpq && m.ds && r->dA, "rnn bwd: Bahdanau mechanism buffers missing");
+  return m.Tm <= ap4::SMALL_TM
+             ? ap4::launch_cluster(st, ap4::attn_lstm_persist4d_bahd_bwd_kernel<true>, r->B, ap4::DBAHD_BWD_SMEM, p, AVSR_K_ATTN_BWD)
+             : ap4::launch_cluster(st, ap4::attn_lstm_persist4d_bahd_bwd_kernel<false>, r->B, ap4::DBAHD_BWD_SMEM, p, AVSR_K_ATTN_BWD);
 }
 
 }  // namespace avsr

@@ -363,6 +363,9 @@ class MechBuffers:
         self.values_op = None  # tf32-rounded copy of the memory (operand of tensor-core products), or None = values
 
     def fill(self, m: AvsrAttnMech):
+        if self.values_op is not None and not self.values_op.is_contiguous():
+            # e.g. the h columns of a layer's state rows: the library reads a dense [Tm*B, Dm] operand
+            self.values_op = self.values_op.contiguous()
         m.kind = ATTN_KINDS[self.kind]
         m.Tm, m.Dm, m.A = self.Tm, self.Dm, self.A
         for k in ('values', 'keys', 'mem_len', 'Wl', 'Wq', 'v', 'g', 'bias', 'align', 'hc', 'pq', 'dkeys', 'dvalues',
