@@ -347,7 +347,7 @@ class _Drop:
     (('scaled_luong',), 9, 7, 32, 256, (40,), (256,), (0.8, 1.0, 1.0)),       # only the input mask
     # Bahdanau family on the two-product kernels: query layer inside the attention product, tanh sweeps, projected values
     (('bahdanau',), 20, 9, 128, 256, (75,), (256,), (0.9, 0.9, 0.9)),          # registers-resident alignments (SMALL)
-    (('bahdanau',), 36, 12, 128, 256, (300,), (512,), (0.9, 0.85, 0.8)),       # BiLSTM memory (Dm = 512), long memory
+    (('bahdanau',), 36, 8, 128, 256, (300,), (512,), (0.9, 0.9, 0.85)),       # BiLSTM memory (Dm = 512), long memory
     (('normed_bahdanau',), 9, 8, 80, 256, (96,), (512,), (1.0, 1.0, 1.0)),     # no dropout: same kernels, bias + g v/|v|
     (('bahdanau',), 250, 5, 128, 256, (40,), (128,), (0.9, 0.9, 0.9)),         # 32 clusters, narrow memory (Dm = 128)
 ])
