@@ -1142,7 +1142,11 @@ static bool persist_shape_ok(const AvsrRnnSeq* r) {
 int attn_context_all(cudaStream_t st, int T, int B, int Tm, int Dm, const int* seq_len, const int* mem_len,
                      const float* align, const float* values, float* ctx, int ldc);  // attention.cu
 int cluster_width_ap();
+static bool wlas_shape_ok(const AvsrRnnSeq* r);
 int rnn_sampling_fused(const AvsrRnnSeq* r) {
+  if (r && r->rng && tensor_cores_enabled() && r->n_mech == 2 && !(r->t_begin || r->t_end || r->stepwise) &&
+      !getenv("AVSR_NO_ATTN_PERSIST"))
+    return wlas_shape_ok(r);  // dual-attention decoder: cluster-of-8 kernels (attn_persist8w.cu)
   if (!(r && r->rng && tensor_cores_enabled() && persist_shape_ok(r) && cluster_width_ap() == 4 &&
         !getenv("AVSR_NO_ATTN_PERSIST") && !(r->t_begin || r->t_end || r->stepwise)))
     return 0;
@@ -1297,6 +1301,94 @@ static int bahdanau_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scr
   AVSR_TRY(attn_outer(st, T, B, m.Tm, m.Dm, r->len, m.align, m.dhc + H, HD, nullptr, m.dvalues));
   AVSR_TRY(gemm(st, 1, 0, H, At, T * B, m.hc, HD, m.dpq, At, m.dWq, At, 1.0f, nullptr));
   return attn_bahdanau_post(st, T, B, m.Tm, At, r->len, m.mem_len, m.ds, m.pq, m.keys, m.v, m.bias, m.dkeys, m.dv, m.dbias);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Dual-attention decoder (WLAS, decoder_bimodal.py:179-277) on the cluster-of-8 kernels of attn_persist8w.cu: two
+// Luong-family mechanisms, H = A = 256, any memory depth (the values are projected through the context half of each
+// attention layer once per batch), DropoutWrapper and in-kernel scheduled sampling included.
+// ---------------------------------------------------------------------------------------------------------------------
+int wlas_persist8_launch_fwd(cudaStream_t st, const AvsrRnnSeq* r, const void* const* keys_h, const void* const* pv_h);  // attn_persist8w.cu
+int wlas_persist8_launch_bwd(cudaStream_t st, const AvsrRnnSeq* r, const void* const* keys_h, const void* const* pv_h);  // attn_persist8w.cu
+
+static bool wlas_shape_ok(const AvsrRnnSeq* r) {
+  if (r->n_mech != 2 || r->T <= 1 || r->H != ap::H || !r->output_attention) return false;
+  for (int k = 0; k < 2; ++k) {
+    const AvsrAttnMech& m = r->mech[k];
+    if (m.kind > AVSR_ATTN_SCALED_LUONG || m.A != ap::H || m.Tm > ap::MAX_TM) return false;
+  }
+  return !getenv("AVSR_NO_WLAS_PERSIST");
+}
+// fp16 keys | fp16 projected values | fp32 projected values, per mechanism
+size_t wlas_persist_work_floats(int B, int H, int Tm) { return 2 * ((size_t)2 * Tm * B * H + 64); }
+struct WlasScratch {
+  const void* keys_h[2];
+  const void* pv_h[2];
+};
+// (re)builds the fp16 memories in `scratch`: forward and backward both call it, so the backward depends on nothing but
+// the saved activations
+static int wlas_prepare(cudaStream_t st, const AvsrRnnSeq* r, float* scratch, WlasScratch* ws) {
+  using namespace ap;
+  const int B = r->B;
+  float* o = scratch;
+  for (int k = 0; k < 2; ++k) {
+    const AvsrAttnMech& m = r->mech[k];
+    const long long nk = (long long)m.Tm * B * H;
+    __half* keys_h = reinterpret_cast<__half*>(o);
+    __half* pv_h = keys_h + nk;
+    float* pv = o + nk + 32;
+    o = pv + nk + 32;
+    // PV_k = values_k Wl_c,k: the context half of the attention layer, once per batch
+    AVSR_TRY(gemm(st, 0, 0, m.Tm * B, H, m.Dm, m.values_op ? m.values_op : m.values, m.Dm, m.Wl + (size_t)H * H, H, pv, H, 0.0f,
+                  nullptr));
+    AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
+    AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, pv, pv_h, nk);
+    ws->keys_h[k] = keys_h;
+    ws->pv_h[k] = pv_h;
+  }
+  return 0;
+}
+
+int wlas_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
+  using namespace ap;
+  if (!wlas_shape_ok(r)) return -1;
+  const int T = r->T, B = r->B, At = 2 * H, SW = At + H;
+  WlasScratch ws;
+  AVSR_TRY(wlas_prepare(st, r, scratch, &ws));
+  // step 0: att_{-1} = 0, so only h_0 Wh enters
+  AVSR_TRY(gemm(st, 0, 0, B, 4 * H, H, r->S + At, SW, r->Wrec + (size_t)At * 4 * H, 4 * H, r->gates, 4 * H, 1.0f, nullptr));
+  AVSR_TRY(wlas_persist8_launch_fwd(st, r, ws.keys_h, ws.pv_h));
+  // the true contexts of every step (parity probe; operand of the attention-layer weight gradients)
+  for (int k = 0; k < 2; ++k) {
+    const AvsrAttnMech& m = r->mech[k];
+    AVSR_TRY(attn_context_all(st, T, B, m.Tm, m.Dm, r->len, m.mem_len, m.align, m.values, m.hc + H, H + m.Dm));
+  }
+  return 0;
+}
+
+int wlas_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
+  using namespace ap;
+  if (!wlas_shape_ok(r)) return -1;
+  const int T = r->T, B = r->B, At = 2 * H, SW = At + H;
+  WlasScratch ws;
+  AVSR_TRY(wlas_prepare(st, r, scratch, &ws));
+  AVSR_TRY(wlas_persist8_launch_bwd(st, r, ws.keys_h, ws.pv_h));
+  if (r->dh0)  // dh_0 += dz_0 Wh^T (the kernel stops before the product of step 0)
+    AVSR_TRY(gemm(st, 0, 1, B, H, 4 * H, r->dZ, 4 * H, r->Wrec + (size_t)At * 4 * H, 4 * H, r->dh0, H, 1.0f, nullptr));
+  // parameter gradients and per-utterance accumulations, all batched
+  AVSR_TRY(gemm(st, 1, 0, SW, 4 * H, T * B, r->S, SW, r->dZ, 4 * H, r->dWrec, 4 * H, 1.0f, nullptr));
+  for (int k = 0; k < 2; ++k) {
+    const AvsrAttnMech& m = r->mech[k];
+    const int HD = H + m.Dm;
+    AVSR_REQUIRE(m.dhc && m.ds, "rnn bwd: mechanism scratch ds / dhc missing");
+    const float* dAk = r->dA + (size_t)k * H;
+    AVSR_TRY(gemm(st, 1, 0, HD, H, T * B, m.hc, HD, dAk, At, m.dWl, H, 1.0f, nullptr));
+    // dctx_t = da_t Wl_c^T for every step -> dvalues (through the contexts)
+    AVSR_TRY(gemm(st, 0, 1, T * B, m.Dm, H, dAk, At, m.Wl + (size_t)H * H, H, m.dhc + H, HD, 0.0f, nullptr));
+    AVSR_TRY(attn_outer(st, T, B, m.Tm, m.Dm, r->len, m.align, m.dhc + H, HD, nullptr, m.dvalues));
+    AVSR_TRY(attn_outer(st, T, B, m.Tm, H, r->len, m.ds, m.hc, HD, m.kind == AVSR_ATTN_SCALED_LUONG ? m.g : nullptr, m.dkeys));
+  }
+  return 0;
 }
 
 int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch, bool unfused) {

@@ -203,6 +203,9 @@ int attn_bahdanau_post(cudaStream_t st, int T, int B, int Tm, int A, const int* 
 // host orchestration
 // --------------------------------------------------------------------------- //
 size_t attn_persist_work_floats(int B, int H, int Dm, int Tm);                 // attn_persist.cu
+size_t wlas_persist_work_floats(int B, int H, int Tm);                         // attn_persist.cu
+int wlas_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch);    // attn_persist.cu (dual attention, clusters of 8)
+int wlas_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch);    // attn_persist.cu
 int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch);    // attn_persist.cu
 int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch, bool unfused);  // attn_persist.cu
 
@@ -219,7 +222,12 @@ static WorkLayout work_layout(int B, int H, int At, int maxHD, int maxA, int max
   w.dcbuf = take((size_t)2 * B * H);
   w.dHC = take((size_t)2 * B * maxHD);
   w.dq = take((size_t)2 * B * (maxA > H ? maxA : H));
-  w.persist = take(maxTm > 0 ? attn_persist_work_floats(B, H, maxHD - H, maxTm) : 0);
+  size_t pw = maxTm > 0 ? attn_persist_work_floats(B, H, maxHD - H, maxTm) : 0;
+  if (maxTm > 0 && maxA > 0 && At >= 2 * maxA) {  // two mechanisms: the dual-attention kernels keep both memories in fp16
+    const size_t ww = wlas_persist_work_floats(B, H, maxTm);
+    pw = pw > ww ? pw : ww;
+  }
+  w.persist = take(pw);
   w.total = o;
   return w;
 }
@@ -270,6 +278,11 @@ int rnn_seq_fwd(cudaStream_t st, const AvsrRnnSeq* r) {
   if (r->n_mech == 1 && rnd && T > 1 && !stepwise && !getenv("AVSR_NO_ATTN_PERSIST")) {  // T == 1: step-wise decoding (carried attention)
     // persistent cluster kernel for the Luong-family attention layer (AV-Align top layer, LAS decoder)
     const int rc = attn_persist_fwd(st, r, r->work + wl.persist);  // also writes `out` when it is the attention
+    if (rc >= 0) return rc;
+  }
+  if (r->n_mech == 2 && rnd && T > 1 && !stepwise && !getenv("AVSR_NO_ATTN_PERSIST")) {
+    // dual-attention (WLAS) decoder: persistent cluster-of-8 kernel
+    const int rc = wlas_persist_fwd(st, r, r->work + wl.persist);
     if (rc >= 0) return rc;
   }
   float* rec = r->work + wl.rec;
@@ -355,6 +368,11 @@ int rnn_seq_bwd(cudaStream_t st, const AvsrRnnSeq* r) {
     // forward left (fused matrix).
     AVSR_REQUIRE(r->mech[0].ds && r->mech[0].dhc, "rnn bwd: mechanism scratch ds / dhc missing");
     const int rc = attn_persist_bwd(st, r, r->work + wl.persist, r->stepwise != 0);
+    if (rc >= 0) return rc;
+  }
+  if (r->n_mech == 2 && rnd && T > 1 && !getenv("AVSR_NO_ATTN_PERSIST")) {
+    // (also after a step-wise forward: the kernel needs nothing but the saved activations)
+    const int rc = wlas_persist_bwd(st, r, r->work + wl.persist);
     if (rc >= 0) return rc;
   }
   float* dS[2] = {r->work + wl.dS, r->work + wl.dS + (size_t)B * SW};

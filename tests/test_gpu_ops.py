@@ -30,6 +30,23 @@ def close(got, want, rtol, what=''):
     return err
 
 
+def close_grad(got, want, rtol, what=''):
+    """Gradients through cell_clip (cells.py:14-18, cell_clip = 1): d clip / dc jumps from 1 to 0 at |c| = 1, so a raw cell
+    state within the operand rounding of the boundary legitimately flips an entry of the gradient.  The bulk must meet
+    `rtol` (relative L2 error and every element but at most 1e-4 of them); a flipped entry is bounded by the tensor's scale."""
+    g = got.detach().cpu().numpy().astype(np.float64) if torch.is_tensor(got) else np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    assert g.shape == want.shape, (what, g.shape, want.shape)
+    assert np.isfinite(g).all(), what + ': non-finite values'
+    scale = max(1e-30, np.abs(want).max())
+    err = np.abs(g - want) / scale
+    rel_l2 = np.linalg.norm(g - want) / max(1e-30, np.linalg.norm(want))
+    frac = float((err > rtol).mean())
+    assert rel_l2 <= rtol, f'{what}: relative L2 error {rel_l2:.3e} > {rtol:.1e}'
+    assert frac <= 1e-4 and err.max() <= 1.0, f'{what}: {frac:.2e} of the entries beyond {rtol:.1e}, max {err.max():.3e}'
+    return err.max()
+
+
 @pytest.fixture(params=[False, True], ids=['fp32', 'tf32'])
 def tensor_cores(request):
     ops = ops_mod()
@@ -350,6 +367,11 @@ class _Drop:
     (('bahdanau',), 36, 8, 128, 256, (300,), (512,), (0.9, 0.9, 0.85)),       # BiLSTM memory (Dm = 512), long memory
     (('normed_bahdanau',), 9, 8, 80, 256, (96,), (512,), (1.0, 1.0, 1.0)),     # no dropout: same kernels, bias + g v/|v|
     (('bahdanau',), 250, 5, 128, 256, (40,), (128,), (0.9, 0.9, 0.9)),         # 32 clusters, narrow memory (Dm = 128)
+    # dual attention (WLAS, decoder_bimodal.py:179-277) on the cluster-of-8 kernels of attn_persist8w.cu
+    (('scaled_luong', 'scaled_luong'), 20, 9, 128, 256, (75, 300), (256, 256), (0.9, 0.9, 0.9)),  # 2 clusters, the second a quarter full
+    (('luong', 'scaled_luong'), 40, 8, 128, 256, (40, 96), (512, 128), (0.8, 0.9, 0.85)),       # other memory depths
+    (('scaled_luong', 'scaled_luong'), 130, 5, 128, 256, (75, 300), (256, 256), (1.0, 1.0, 1.0)),  # 9 clusters, no dropout
+    (('scaled_luong', 'luong'), 3, 12, 80, 256, (20, 33), (256, 256), (1.0, 0.9, 1.0)),          # one partial cluster
 ])
 def test_attention_rnn_dropout_persistent(kinds, B, T, Dx, H, Tms, Dms, keep):
     """AttentionWrapper(DropoutWrapper(LSTMCell)) - the reference's default training graph (cells.py:46-54) - on the
@@ -441,8 +463,8 @@ def _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, tensor_cores, keep=None):
     rg = 1e-1 if tensor_cores else 1e-4
     close(dx.transpose(0, 1), rb['dx'], rg, 'dx')
     close(gW, rb['dW'], rg, 'dW')
-    close(rnn.dc0, rb['dinit'][0], rg, 'dc0')
-    close(rnn.dh0, rb['dinit'][1], rg, 'dh0')
+    (close_grad if tensor_cores and B * H > 20000 else close)(rnn.dc0, rb['dinit'][0], rg, 'dc0')
+    (close_grad if tensor_cores and B * H > 20000 else close)(rnn.dh0, rb['dinit'][1], rg, 'dh0')
     for k, (s, mb) in enumerate(zip(specs, bufs)):
         Tm, Dm = mb.Tm, mb.Dm
         mg = rb['mech'][k]
