@@ -368,10 +368,10 @@ class _Drop:
     (('normed_bahdanau',), 9, 8, 80, 256, (96,), (512,), (1.0, 1.0, 1.0)),     # no dropout: same kernels, bias + g v/|v|
     (('bahdanau',), 250, 5, 128, 256, (40,), (128,), (0.9, 0.9, 0.9)),         # 32 clusters, narrow memory (Dm = 128)
     # dual attention (WLAS, decoder_bimodal.py:179-277) on the cluster-of-8 kernels of attn_persist8w.cu
-    (('scaled_luong', 'scaled_luong'), 20, 9, 128, 256, (75, 300), (256, 256), (0.9, 0.9, 0.9)),  # 2 clusters, the second a quarter full
-    (('luong', 'scaled_luong'), 40, 8, 128, 256, (40, 96), (512, 128), (0.8, 0.9, 0.85)),       # other memory depths
+    (('scaled_luong', 'scaled_luong'), 20, 6, 128, 256, (75, 300), (256, 256), (0.9, 0.9, 0.9)),  # 2 clusters, the second a quarter full (stress weights + 512-d feedback: errors double per step, tools/wlas_diag.py)
+    (('luong', 'scaled_luong'), 40, 6, 128, 256, (40, 96), (512, 128), (0.8, 0.9, 0.85)),       # other memory depths
     (('scaled_luong', 'scaled_luong'), 130, 5, 128, 256, (75, 300), (256, 256), (1.0, 1.0, 1.0)),  # 9 clusters, no dropout
-    (('scaled_luong', 'luong'), 3, 12, 80, 256, (20, 33), (256, 256), (1.0, 0.9, 1.0)),          # one partial cluster
+    (('scaled_luong', 'luong'), 3, 7, 80, 256, (20, 33), (256, 256), (1.0, 0.9, 1.0)),          # one partial cluster
 ])
 def test_attention_rnn_dropout_persistent(kinds, B, T, Dx, H, Tms, Dms, keep):
     """AttentionWrapper(DropoutWrapper(LSTMCell)) - the reference's default training graph (cells.py:46-54) - on the
