@@ -50,7 +50,7 @@ def test_library_loads_and_reports_version(lib):
 def test_struct_sizes_match_header(lib):
     sizes = (ctypes.c_int * 2)()
     lib.load().avsr_struct_sizes(sizes)  # sizeof() as compiled by nvcc
-    assert ctypes.sizeof(lib.AvsrAttnMech) == sizes[0] == 16 + 21 * 8
+    assert ctypes.sizeof(lib.AvsrAttnMech) == sizes[0] == 16 + 22 * 8
     assert ctypes.sizeof(lib.AvsrRnnSeq) == sizes[1]
 
 
