@@ -267,6 +267,32 @@ def conv2d_wgrad(x, dy, kh, kw, stride, padding, dW):
                                         Wo, Co, dW.data_ptr()))
 
 
+def conv2d_tc_supported(Ci, Co, kh, kw, stride):
+    return bool(_lib.load().avsr_conv2d_tc_supported(int(Ci), int(Co), int(kh), int(kw), int(stride)))
+
+
+def conv2d_tc(x, wmat, bias, kh, kw, stride, pad_top, pad_left, Ho, Wo, in_dilation=1, residual=None, stats=None, out=None):
+    """Tensor-core NHWC convolution (avsr_conv2d_tc): x [N,H,W,Ci], wmat [kh*kw*Ci, Co] -> [N,Ho,Wo,Co]; explicit padding /
+    output size so that the same call serves as the input gradient (in_dilation = 2: zero-stuffed x)."""
+    _chk_f32(x, wmat, bias, residual, stats)
+    N, H, W, Ci = x.shape
+    Co = wmat.shape[1]
+    y = empty(N, Ho, Wo, Co) if out is None else out
+    check(_lib.load().avsr_conv2d_tc(_stream(), x.data_ptr(), N, H, W, Ci, wmat.data_ptr(), _p(bias), kh, kw, stride, pad_top,
+                                     pad_left, Ho, Wo, Co, in_dilation, _p(residual), _p(stats), y.data_ptr()))
+    return y
+
+
+def conv2d_wgrad_tc(x, dy, kh, kw, stride, padding, dW):
+    """dW [kh*kw*Ci, Co] += patches(x)^T dy on tensor cores (avsr_conv2d_wgrad_tc)."""
+    _chk_f32(x, dy, dW)
+    N, H, W, Ci = x.shape
+    Ho, Wo, pt, pl = conv_geometry(H, W, kh, kw, stride, padding)
+    Co = dy.shape[-1]
+    check(_lib.load().avsr_conv2d_wgrad_tc(_stream(), x.data_ptr(), dy.data_ptr(), N, H, W, Ci, kh, kw, stride, pt, pl, Ho,
+                                           Wo, Co, dW.data_ptr()))
+
+
 def relu_fwd(x, out=None):
     y = torch.empty_like(x) if out is None else out
     check(_lib.load().avsr_relu_fwd(_stream(), x.data_ptr(), x.numel(), y.data_ptr()))

@@ -41,10 +41,32 @@ class _Conv(object):
         return (self.cout in (8, 16) and self.kh * self.kw * self.cin * self.cout <= 2304
                 and not os.environ.get('AVSR_CNN_IM2COL'))
 
-    def forward(self, x):
-        """x [N,H,W,Cin] -> [N,Ho,Wo,Cout] (exact fp32 out; the operand copy of x is made by im2col)."""
+    @property
+    def tensor_core(self):
+        """Tensor-core mode: implicit-GEMM kernels of csrc/conv_mma.cu (forward, both input gradients, weight gradient)."""
+        return (ops.tensor_cores_enabled() and self.padding == 'SAME' and not os.environ.get('AVSR_CNN_NO_TC')
+                and ops.conv2d_tc_supported(self.cin, self.cout, self.kh, self.kw, self.stride))
+
+    def forward(self, x, residual=None, stats=None):
+        """x [N,H,W,Cin] -> [N,Ho,Wo,Cout] (exact fp32 out; the operand copy of x is made by im2col).
+        residual: added to the output (residual_block's tf.add); stats [2 Cout]: += (sum, sum of squares) of the output
+        per channel, for the batch norm that follows - both fused into the tensor-core kernel, separate passes otherwise."""
         ctx = self.ctx
         self._x = x
+        if self.tensor_core:
+            N, H, W, _ = x.shape
+            Ho, Wo, pt, pl = ops.conv_geometry(H, W, self.kh, self.kw, self.stride, self.padding)
+            return ops.conv2d_tc(x, ctx.p(self.kernel).view(-1, self.cout), ctx.p(self.bias), self.kh, self.kw, self.stride,
+                                 pt, pl, Ho, Wo, residual=residual, stats=stats)
+        y = self._forward_plain(x)
+        if residual is not None:
+            ops.axpy(1.0, residual, y)
+        if stats is not None:
+            ops.bn_stats(y.view(-1, self.cout), stats)
+        return y
+
+    def _forward_plain(self, x):
+        ctx = self.ctx
         if self.direct:
             return ops.conv2d_direct(x, ctx.p(self.kernel).view(-1, self.cout), ctx.p(self.bias), self.kh, self.kw,
                                      self.stride, self.padding)
@@ -61,6 +83,25 @@ class _Conv(object):
 
     def backward(self, dy, need_dx=True):
         ctx = self.ctx
+        if self.tensor_core:
+            dyc = dy.contiguous()
+            x = self._x
+            self._x = None
+            N, H, W, _ = x.shape
+            Ho, Wo, pt, pl = ops.conv_geometry(H, W, self.kh, self.kw, self.stride, self.padding)
+            ops.conv2d_wgrad_tc(x, dyc, self.kh, self.kw, self.stride, self.padding, ctx.g(self.kernel).view(-1, self.cout))
+            ops.colsum(dyc.view(-1, self.cout), ctx.g(self.bias))
+            if not need_dx:
+                return None
+            if ops.conv2d_tc_supported(self.cout, self.cin, self.kh, self.kw, 1):
+                # gradient wrt the input = stride-1 convolution of dy (zero-stuffed for a stride-2 layer) with the kernel
+                # flipped in space and transposed in channels, padding k - 1 - pad
+                wt = ctx.p(self.kernel).flip(0, 1).permute(0, 1, 3, 2).contiguous().view(-1, self.cin)
+                return ops.conv2d_tc(dyc, wt, None, self.kh, self.kw, 1, self.kh - 1 - pt, self.kw - 1 - pl, H, W,
+                                     in_dilation=self.stride)
+            dcols = ops.empty(dyc.numel() // self.cout, self.kh * self.kw * self.cin)
+            ops.gemm(dyc.view(-1, self.cout), ctx.p(self.kernel).view(-1, self.cout), dcols, tb=True)
+            return ops.col2im(dcols, (N, H, W, self.cin, self.kh, self.kw, self.stride, pt, pl, Ho, Wo))
         if self.direct:
             dyc = dy.contiguous()
             ops.conv2d_wgrad(self._x, dyc, self.kh, self.kw, self.stride, self.padding,

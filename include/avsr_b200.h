@@ -279,6 +279,20 @@ int avsr_conv2d_direct(avsr_stream_t stream, const float* x, int N, int H, int W
                        float* y);
 int avsr_conv2d_wgrad(avsr_stream_t stream, const float* x, const float* dy, int N, int H, int W, int Ci, int kh, int kw,
                       int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, float* dW);
+/* The same convolutions on tensor cores (csrc/conv_mma.cu: implicit GEMM on mma.sync TF32, whole frames staged once in
+ * shared memory, no im2col buffer) for Ci <= 64, Co in {8, 16, 32 k}, square kernels of 1 or 3, stride 1 or 2
+ * (avsr_conv2d_tc_supported).  y = conv(x, w) (+ bias) (+ residual: the `tf.add` of residual_block video.py:92);
+ * stats [2 Co] += per-channel (sum, sum of squares) of y: the statistics pass of the batch_norm_relu that follows
+ * (video.py:4-15), fused into the producer.  in_dilation = 2: x is read zero-stuffed (pixel (i, j) at (2 i, 2 j)) - with the
+ * kernel flipped / transposed and pad = k - 1 - pad_fwd this is the input gradient of a stride-2 convolution (replaces
+ * avsr_gemm + avsr_col2im); with in_dilation = 1 it is that of a stride-1 convolution.  Operands tf32-rounded while staged. */
+int avsr_conv2d_tc_supported(int Ci, int Co, int kh, int kw, int stride);
+int avsr_conv2d_tc(avsr_stream_t stream, const float* x, int N, int H, int W, int Ci, const float* w, const float* bias,
+                   int kh, int kw, int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, int in_dilation,
+                   const float* residual, float* stats, float* y);
+/* dW[kh*kw*Ci, Co] += x-patches^T dy on tensor cores (M = kh*kw*Ci, N = Co, K = pixels) */
+int avsr_conv2d_wgrad_tc(avsr_stream_t stream, const float* x, const float* dy, int N, int H, int W, int Ci, int kh, int kw,
+                         int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, float* dW);
 int avsr_relu_fwd(avsr_stream_t stream, const float* x, long long n, float* y);               /* in place allowed */
 int avsr_relu_bwd(avsr_stream_t stream, const float* y, const float* dy, long long n, float* dx); /* dx = dy [y > 0] */
 

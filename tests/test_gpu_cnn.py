@@ -139,3 +139,48 @@ def test_model_with_cnn_front_end(cfg, over, tensor_cores):
     ev = Seq2SeqModel(ds, 'evaluate', hp_eval, share_params_with=model)
     ids = ev.predict(ds)
     assert ids.shape[0] == 3
+
+
+@pytest.mark.parametrize('N,H,Ci,Co,k,stride', [
+    (5, 36, 3, 8, 3, 1), (3, 36, 8, 8, 3, 1), (4, 36, 8, 16, 1, 2), (4, 36, 8, 16, 3, 2), (7, 18, 16, 16, 3, 1),
+    (5, 18, 16, 32, 1, 2), (5, 18, 16, 32, 3, 2), (9, 9, 32, 32, 3, 1), (9, 9, 32, 64, 1, 2), (9, 9, 32, 64, 3, 2),
+    (37, 5, 64, 64, 3, 1), (2, 12, 4, 8, 3, 2), (300, 9, 32, 32, 3, 1),
+])
+def test_tensor_core_convolutions_against_torch(N, H, Ci, Co, k, stride):
+    """csrc/conv_mma.cu against torch.nn.functional.conv2d (fp32 reference of the same op, TF's SAME padding applied by hand)
+    and its autograd: forward with bias + residual + fused BN statistics, the input gradient (stride 1: flipped kernel;
+    stride 2: zero-stuffed dy) and the weight gradient, on every layer shape of the reference's front-end.  Operands are
+    tf32-rounded by the kernels: 2e-3 of the tensor's scale."""
+    import torch.nn.functional as F
+    from avsr_tf1_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(N * 1000 + H * 10 + Ci + Co + k + stride)
+    x = torch.randn(N, H, H, Ci, device='cuda', generator=g)
+    w = torch.randn(k, k, Ci, Co, device='cuda', generator=g) / (k * k * Ci) ** 0.5
+    b = torch.randn(Co, device='cuda', generator=g)
+    Ho, Wo, pt, pl = ops.conv_geometry(H, H, k, k, stride, 'SAME')
+    _, _, pb = ops.same_padding(H, k, stride)
+    res = torch.randn(N, Ho, Wo, Co, device='cuda', generator=g)
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+        wr = w.permute(3, 2, 0, 1).clone().requires_grad_(True)
+        yr = F.conv2d(F.pad(xr, (pl, pb, pt, pb)), wr, b, stride=stride)
+        dy = torch.randn(N, Ho, Wo, Co, device='cuda', generator=g)
+        yr.backward(dy.permute(0, 3, 1, 2))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    y_ref = yr.detach().permute(0, 2, 3, 1) + res
+    stats = torch.zeros(2 * Co, device='cuda')
+    y = ops.conv2d_tc(x, w.reshape(-1, Co), b, k, k, stride, pt, pl, Ho, Wo, residual=res, stats=stats)
+    close(y, y_ref.cpu().numpy(), 2e-3, 'conv forward')
+    y2 = y_ref.reshape(-1, Co).double()
+    close(stats[:Co], y2.sum(0).cpu().numpy(), 2e-3, 'sum of y')
+    close(stats[Co:], (y2 * y2).sum(0).cpu().numpy(), 2e-3, 'sum of y^2')
+    dW = torch.zeros(k * k * Ci, Co, device='cuda')
+    ops.conv2d_wgrad_tc(x, dy, k, k, stride, 'SAME', dW)
+    close(dW, wr.grad.permute(2, 3, 1, 0).reshape(-1, Co).cpu().numpy(), 2e-3, 'weight gradient')
+    if Ci % 8 == 0:
+        wt = w.flip(0, 1).permute(0, 1, 3, 2).contiguous().view(-1, Ci)
+        dx = ops.conv2d_tc(dy, wt, None, k, k, 1, k - 1 - pt, k - 1 - pl, H, H, in_dilation=stride)
+        close(dx, xr.grad.permute(0, 2, 3, 1).cpu().numpy(), 2e-3, 'input gradient')
