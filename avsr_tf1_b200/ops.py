@@ -271,26 +271,56 @@ def conv2d_tc_supported(Ci, Co, kh, kw, stride):
     return bool(_lib.load().avsr_conv2d_tc_supported(int(Ci), int(Co), int(kh), int(kw), int(stride)))
 
 
-def conv2d_tc(x, wmat, bias, kh, kw, stride, pad_top, pad_left, Ho, Wo, in_dilation=1, residual=None, stats=None, out=None):
+def conv2d_tc(x, wmat, bias, kh, kw, stride, pad_top, pad_left, Ho, Wo, in_dilation=1, in_bn=None, residual=None, res_bn=None,
+              mask_u=None, mask_bn=None, stats=None, out=None):
     """Tensor-core NHWC convolution (avsr_conv2d_tc): x [N,H,W,Ci], wmat [kh*kw*Ci, Co] -> [N,Ho,Wo,Co]; explicit padding /
-    output size so that the same call serves as the input gradient (in_dilation = 2: zero-stuffed x)."""
-    _chk_f32(x, wmat, bias, residual, stats)
+    output size so that the same call serves as the input gradient (in_dilation = 2: zero-stuffed x).  in_bn / res_bn /
+    mask_u + mask_bn / stats: the batch_norm_relu layers around the convolution, fused (see include/avsr_b200.h)."""
+    _chk_f32(x, wmat, bias, residual, stats, in_bn, res_bn, mask_u, mask_bn)
     N, H, W, Ci = x.shape
     Co = wmat.shape[1]
     y = empty(N, Ho, Wo, Co) if out is None else out
     check(_lib.load().avsr_conv2d_tc(_stream(), x.data_ptr(), N, H, W, Ci, wmat.data_ptr(), _p(bias), kh, kw, stride, pad_top,
-                                     pad_left, Ho, Wo, Co, in_dilation, _p(residual), _p(stats), y.data_ptr()))
+                                     pad_left, Ho, Wo, Co, in_dilation, _p(in_bn), _p(residual), _p(res_bn), _p(mask_u),
+                                     _p(mask_bn), _p(stats), y.data_ptr()))
     return y
 
 
-def conv2d_wgrad_tc(x, dy, kh, kw, stride, padding, dW):
-    """dW [kh*kw*Ci, Co] += patches(x)^T dy on tensor cores (avsr_conv2d_wgrad_tc)."""
-    _chk_f32(x, dy, dW)
+def conv2d_wgrad_tc(x, dy, kh, kw, stride, padding, dW, in_bn=None):
+    """dW [kh*kw*Ci, Co] += patches(x')^T dy on tensor cores (avsr_conv2d_wgrad_tc); x' = relu(x scale + shift) with in_bn."""
+    _chk_f32(x, dy, dW, in_bn)
     N, H, W, Ci = x.shape
     Ho, Wo, pt, pl = conv_geometry(H, W, kh, kw, stride, padding)
     Co = dy.shape[-1]
-    check(_lib.load().avsr_conv2d_wgrad_tc(_stream(), x.data_ptr(), dy.data_ptr(), N, H, W, Ci, kh, kw, stride, pt, pl, Ho,
-                                           Wo, Co, dW.data_ptr()))
+    check(_lib.load().avsr_conv2d_wgrad_tc(_stream(), x.data_ptr(), _p(in_bn), dy.data_ptr(), N, H, W, Ci, kh, kw, stride, pt,
+                                           pl, Ho, Wo, Co, dW.data_ptr()))
+
+
+def bn_finalize(sums, count, gamma, beta, eps, momentum, moving_mean, moving_var):
+    """coef [4C] = (scale, shift, invstd, -mean invstd) of a batch_norm_relu from fused (sum, sum of squares) statistics."""
+    C = gamma.numel()
+    coef = empty(4 * C)
+    check(_lib.load().avsr_bn_finalize(_stream(), sums.data_ptr(), float(count), gamma.data_ptr(), beta.data_ptr(), eps,
+                                       momentum, C, _p(moving_mean), _p(moving_var), coef.data_ptr()))
+    return coef
+
+
+def bn_coef_eval(gamma, beta, moving_mean, moving_var, eps):
+    C = gamma.numel()
+    coef = empty(4 * C)
+    check(_lib.load().avsr_bn_coef_eval(_stream(), gamma.data_ptr(), beta.data_ptr(), moving_mean.data_ptr(),
+                                        moving_var.data_ptr(), eps, C, coef.data_ptr()))
+    return coef
+
+
+def bn_relu_bwd_apply(d, u, coef, sums2, count, residual=None, out=None):
+    """du of a batch_norm_relu from the ReLU-masked gradient d, the saved BN input u and sums2 = (sum d, sum d xhat)."""
+    _chk_f32(d, u, coef, sums2, residual)
+    C = d.shape[-1]
+    du = torch.empty_like(d) if out is None else out
+    check(_lib.load().avsr_bn_relu_bwd_apply(_stream(), d.data_ptr(), u.data_ptr(), coef.data_ptr(), sums2.data_ptr(),
+                                             float(count), _p(residual), d.numel() // C, C, du.data_ptr()))
+    return du
 
 
 def relu_fwd(x, out=None):

@@ -10,9 +10,14 @@ The narrow convolutions (8 / 16 output channels at 36x36 and 18x18: nearly all p
 (avsr_conv2d_direct, avsr_conv2d_wgrad; exact fp32); the 32- / 64-channel ones are avsr_im2col + avsr_gemm (bias in the
 product's epilogue), their gradients avsr_gemm + avsr_colsum + avsr_col2im.  BN is the same stats / apply pair as the
 input normalisation (rows = N*H*W; eps 1e-5, momentum 0.98; all-reduced sums under data parallelism).  im2col buffers
-are not kept: the backward pass rebuilds them from the saved layer inputs.  This is the functional version of the row
-(parity against the oracle); fusing BN statistics / BN-ReLU into the convolutions and tcgen05 implicit GEMMs for the
-wide layers are the next step.
+are not kept: the backward pass rebuilds them from the saved layer inputs.  That is the exact-fp32 path (parity against the oracle at 1e-3).
+
+In tensor-core mode (the default) every convolution runs on the implicit-GEMM `mma.sync` TF32 kernels of csrc/conv_mma.cu
+(forward, both input gradients, weight gradient: no im2col / col2im buffers) and the batch_norm_relu layers never
+materialise: a convolution accumulates the statistics of the batch norm that follows in its epilogue, its consumers apply
+the BN-ReLU while they stage their input, the ReLU mask and the statistics pass of the BN backward ride in the epilogue of
+the convolution that forms the incoming gradient, and the residual `tf.add`s are epilogue adds
+(`ResNetCNN._forward_fused / _backward_fused`).
 
 `2dconv_cnn` / `3dconv_cnn` (video.py:108-140, 198-221) are not built (no reference script selects them)."""
 from __future__ import annotations
@@ -64,6 +69,29 @@ class _Conv(object):
         if stats is not None:
             ops.bn_stats(y.view(-1, self.cout), stats)
         return y
+
+    # --- building blocks of the fused tensor-core path (ResNetCNN._forward_fused / _backward_fused) ---
+    def conv_tc(self, x, **kw):
+        H, W = x.shape[1], x.shape[2]
+        Ho, Wo, pt, pl = ops.conv_geometry(H, W, self.kh, self.kw, self.stride, self.padding)
+        return ops.conv2d_tc(x, self.ctx.p(self.kernel).view(-1, self.cout), self.ctx.p(self.bias), self.kh, self.kw,
+                             self.stride, pt, pl, Ho, Wo, **kw)
+
+    def wgrad_tc(self, x, dy, in_bn=None):
+        """kernel and bias gradients from the layer input x (read through in_bn) and dy."""
+        ctx = self.ctx
+        ops.conv2d_wgrad_tc(x, dy, self.kh, self.kw, self.stride, self.padding, ctx.g(self.kernel).view(-1, self.cout),
+                            in_bn=in_bn)
+        ops.colsum(dy.view(-1, self.cout), ctx.g(self.bias))
+
+    def dgrad_tc(self, dy, in_hw, **kw):
+        """gradient wrt the layer input [N, in_hw, in_hw, cin]: stride-1 convolution of dy (zero-stuffed for a stride-2
+        layer) with the kernel flipped in space and transposed in channels, padding k - 1 - pad."""
+        H, W = in_hw
+        _, _, pt, pl = ops.conv_geometry(H, W, self.kh, self.kw, self.stride, self.padding)
+        wt = self.ctx.p(self.kernel).flip(0, 1).permute(0, 1, 3, 2).contiguous().view(-1, self.cin)
+        return ops.conv2d_tc(dy, wt, None, self.kh, self.kw, 1, self.kh - 1 - pt, self.kw - 1 - pl, H, W,
+                             in_dilation=self.stride, **kw)
 
     def _forward_plain(self, x):
         ctx = self.ctx
@@ -143,6 +171,34 @@ class _BatchNormRelu(object):
         self.mm = ctx.declare(name + '/moving_mean', (C,), 'zeros', trainable=False)
         self.mv = ctx.declare(name + '/moving_variance', (C,), 'ones', trainable=False)
 
+    # --- fused path: the layer never materialises; the convolutions around it apply these coefficients ---
+    def coef(self, stats, rows, train):
+        """[4C] (scale, shift, invstd, -mean invstd) from the statistics the producing convolution accumulated (training;
+        updates the moving statistics) or from the moving statistics (inference)."""
+        ctx = self.ctx
+        if not train:
+            return ops.bn_coef_eval(ctx.p(self.gamma), ctx.p(self.beta), ctx.p(self.mm), ctx.p(self.mv), BN_EPS)
+        count = float(rows)
+        if ctx.world_size > 1:
+            ctx.allreduce(stats)
+            count *= ctx.batch_scale  # rows of the GLOBAL batch (layers.BuildContext.batch_scale)
+        self.count = count
+        return ops.bn_finalize(stats, count, ctx.p(self.gamma), ctx.p(self.beta), BN_EPS, BN_MOMENTUM, ctx.p(self.mm),
+                               ctx.p(self.mv))
+
+    def backward_fused(self, d, u, coef, sums2, residual=None):
+        """d: gradient wrt the layer output already masked by its ReLU, sums2 = (sum d, sum d xhat) (both from the epilogue of
+        the convolution that produced d); u: the layer's input.  Returns the gradient wrt u (+ residual), in place of d."""
+        ctx, C = self.ctx, self.C
+        local = sums2
+        if ctx.world_size > 1:
+            local = sums2.clone()
+            ctx.allreduce(sums2)
+        du = ops.bn_relu_bwd_apply(d, u, coef, sums2, self.count, residual=residual, out=d)
+        ops.axpy(1.0, local[C:], ctx.g(self.gamma))
+        ops.axpy(1.0, local[:C], ctx.g(self.beta))
+        return du
+
     def forward(self, x, train):
         ctx, C = self.ctx, self.C
         x2 = x.reshape(-1, C)
@@ -215,8 +271,96 @@ class ResNetCNN(object):
             out += [blk[k] for k in ('shortcut', 'conv1', 'conv2') if k in blk]
         return out + [self.flatten]
 
+    def _fused_ok(self):
+        """Tensor-core mode and every layer shape covered by csrc/conv_mma.cu: the fused path (no BN / ReLU / add passes)."""
+        if os.environ.get('AVSR_CNN_NO_FUSE'):
+            return False
+        convs = self._convs()[:-1]
+        if not all(c.tensor_core for c in convs):
+            return False
+        if not all(ops.conv2d_tc_supported(c.cout, c.cin, c.kh, c.kw, 1) for c in convs[1:]):  # input gradients
+            return False
+        return all(1024 % c.cout == 0 for c in convs)
+
+    def _forward_fused(self, frames, train):
+        """Every convolution writes its raw output once and accumulates the statistics of the batch norm that follows; the
+        BN-ReLU itself is applied by the consumers while they stage their input (csrc/conv_mma.cu)."""
+        st = (lambda C: ops.zeros(2 * C)) if train else (lambda C: None)
+        rows = lambda t: t.numel() // t.shape[-1]
+        sv = []
+        blk = self.blocks[0]
+        s0 = st(self.layer0.cout)
+        y0 = self.layer0.conv_tc(frames, stats=s0)
+        c0 = self.layer0_bn.coef(s0, rows(y0), train)
+        s1 = st(blk['conv1'].cout)
+        y1 = blk['conv1'].conv_tc(y0, in_bn=c0, stats=s1)
+        c1 = blk['second_bn'].coef(s1, rows(y1), train)
+        sn = st(blk['conv2'].cout) if len(self.blocks) > 1 else None
+        o = blk['conv2'].conv_tc(y1, in_bn=c1, residual=y0, res_bn=c0, stats=sn)  # + shortcut = relu(bn(y0))
+        sv.append((frames, y0, c0, y1, c1))
+        for k in range(1, len(self.blocks)):
+            blk = self.blocks[k]
+            cf = blk['first_bn'].coef(sn, rows(o), train)
+            sc = blk['shortcut'].conv_tc(o)  # projection of the RAW block input
+            s2 = st(blk['conv1'].cout)
+            y = blk['conv1'].conv_tc(o, in_bn=cf, stats=s2)
+            c2 = blk['second_bn'].coef(s2, rows(y), train)
+            sn = st(blk['conv2'].cout) if k + 1 < len(self.blocks) else None
+            o_new = blk['conv2'].conv_tc(y, in_bn=c2, residual=sc, stats=sn)
+            sv.append((o, cf, y, c2))
+            o = o_new
+        N = frames.shape[0]
+        fl = self.flatten  # VALID convolution over the whole remaining image = a dense product on the flattened pixels
+        cols = ops.round_tf32(o.reshape(N, -1))
+        y = ops.empty(N, self.out_dim)
+        ops.gemm(cols, self.ctx.w(fl.kernel).view(-1, self.out_dim), y, bias=self.ctx.p(fl.bias))
+        self._feat = ops.relu_fwd(y, out=y)
+        self._saved = (sv, cols, tuple(o.shape)) if train else None
+        return self._feat
+
+    def _backward_fused(self, dfeat):
+        ctx = self.ctx
+        sv, cols, oshape = self._saved
+        fl = self.flatten
+        d = ops.relu_bwd(self._feat, dfeat.reshape(self._feat.shape).contiguous())
+        d = ops.round_tf32(d)
+        ops.gemm(cols, d, ctx.g(fl.kernel).view(-1, self.out_dim), ta=True, beta=1.0)
+        ops.colsum(d, ctx.g(fl.bias))
+        d_o = ops.empty(*oshape)
+        ops.gemm(d, ctx.w(fl.kernel).view(-1, self.out_dim), d_o.view(oshape[0], -1), tb=True)
+        for k in range(len(self.blocks) - 1, 0, -1):
+            blk = self.blocks[k]
+            o_in, cf, y, c2 = sv[k]
+            hw_y, hw_in = (y.shape[1], y.shape[2]), (o_in.shape[1], o_in.shape[2])
+            blk['conv2'].wgrad_tc(y, d_o, in_bn=c2)
+            s2 = ops.zeros(2 * y.shape[-1])
+            dm = blk['conv2'].dgrad_tc(d_o, hw_y, mask_u=y, mask_bn=c2, stats=s2)
+            du = blk['second_bn'].backward_fused(dm, y, c2, s2)
+            blk['conv1'].wgrad_tc(o_in, du, in_bn=cf)
+            s1 = ops.zeros(2 * o_in.shape[-1])
+            d1 = blk['conv1'].dgrad_tc(du, hw_in, mask_u=o_in, mask_bn=cf, stats=s1)
+            blk['shortcut'].wgrad_tc(o_in, d_o)
+            d_sc = blk['shortcut'].dgrad_tc(d_o, hw_in)
+            d_o = blk['first_bn'].backward_fused(d1, o_in, cf, s1, residual=d_sc)
+        blk = self.blocks[0]
+        frames, y0, c0, y1, c1 = sv[0]
+        hw = (y0.shape[1], y0.shape[2])
+        blk['conv2'].wgrad_tc(y1, d_o, in_bn=c1)
+        s1 = ops.zeros(2 * y1.shape[-1])
+        dm = blk['conv2'].dgrad_tc(d_o, hw, mask_u=y1, mask_bn=c1, stats=s1)
+        du1 = blk['second_bn'].backward_fused(dm, y1, c1, s1)
+        blk['conv1'].wgrad_tc(y0, du1, in_bn=c0)
+        s0 = ops.zeros(2 * y0.shape[-1])
+        dm0 = blk['conv1'].dgrad_tc(du1, hw, residual=d_o, mask_u=y0, mask_bn=c0, stats=s0)  # + the shortcut's gradient
+        du0 = self.layer0_bn.backward_fused(dm0, y0, c0, s0)
+        self.layer0.wgrad_tc(frames, du0)
+        self._feat = self._saved = None
+
     def forward(self, frames, train):
         """frames [N,H,W,C] device tensor -> features [N, cnn_dense_units]."""
+        self._fused = self._fused_ok()
+        if self._fused:
+            return self._forward_fused(frames, train)
         flow = self.layer0_bn.forward(self.layer0.forward(frames), train)
         for blk in self.blocks:
             shortcut = flow
@@ -233,6 +377,8 @@ class ResNetCNN(object):
 
     def backward(self, dfeat):
         """Accumulates the gradients of every CNN variable (nothing upstream of the frames is trained)."""
+        if self._fused:
+            return self._backward_fused(dfeat)
         d = ops.relu_bwd(self._feat, dfeat.reshape(self._feat.shape).contiguous())
         d = self.flatten.backward(d)
         for k in range(len(self.blocks) - 1, -1, -1):

@@ -281,18 +281,37 @@ int avsr_conv2d_wgrad(avsr_stream_t stream, const float* x, const float* dy, int
                       int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, float* dW);
 /* The same convolutions on tensor cores (csrc/conv_mma.cu: implicit GEMM on mma.sync TF32, whole frames staged once in
  * shared memory, no im2col buffer) for Ci <= 64, Co in {8, 16, 32 k}, square kernels of 1 or 3, stride 1 or 2
- * (avsr_conv2d_tc_supported).  y = conv(x, w) (+ bias) (+ residual: the `tf.add` of residual_block video.py:92);
- * stats [2 Co] += per-channel (sum, sum of squares) of y: the statistics pass of the batch_norm_relu that follows
- * (video.py:4-15), fused into the producer.  in_dilation = 2: x is read zero-stuffed (pixel (i, j) at (2 i, 2 j)) - with the
- * kernel flipped / transposed and pad = k - 1 - pad_fwd this is the input gradient of a stride-2 convolution (replaces
- * avsr_gemm + avsr_col2im); with in_dilation = 1 it is that of a stride-1 convolution.  Operands tf32-rounded while staged. */
+ * (avsr_conv2d_tc_supported).  y = conv(x', w) (+ bias) (+ residual'), where the batch_norm_relu layers around the
+ * convolution (video.py:4-15, 57-92) never materialise:
+ *   in_bn  [2 Ci] (scale, shift) or NULL: x' = relu(x * scale + shift), applied while the frames are staged;
+ *   residual (+ res_bn [2 Co]) or NULL: the `tf.add` of residual_block video.py:92, of the raw tensor or of its BN-ReLU;
+ *   stats [2 Co] or NULL: += per-channel (sum, sum of squares) of y: the statistics pass of the NEXT batch_norm_relu;
+ *   mask_u [N,Ho,Wo,Co] + mask_bn [4 Co] (scale, shift, a, b) or NULL: this call is an input gradient and the tensor it
+ *     differentiates was z = relu(u * scale + shift): the result is masked by z > 0 (= d) and stats += (sum d,
+ *     sum d * xhat), xhat = u * a + b - relu_bwd and the statistics pass of the BN backward, fused into the producer.
+ * in_dilation = 2: x is read zero-stuffed (pixel (i, j) at (2 i, 2 j)) - with the kernel flipped / transposed and
+ * pad = k - 1 - pad_fwd this is the input gradient of a stride-2 convolution (replaces avsr_gemm + avsr_col2im); with
+ * in_dilation = 1 it is that of a stride-1 convolution.  Operands are tf32-rounded while staged. */
 int avsr_conv2d_tc_supported(int Ci, int Co, int kh, int kw, int stride);
 int avsr_conv2d_tc(avsr_stream_t stream, const float* x, int N, int H, int W, int Ci, const float* w, const float* bias,
                    int kh, int kw, int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, int in_dilation,
-                   const float* residual, float* stats, float* y);
-/* dW[kh*kw*Ci, Co] += x-patches^T dy on tensor cores (M = kh*kw*Ci, N = Co, K = pixels) */
-int avsr_conv2d_wgrad_tc(avsr_stream_t stream, const float* x, const float* dy, int N, int H, int W, int Ci, int kh, int kw,
-                         int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, float* dW);
+                   const float* in_bn, const float* residual, const float* res_bn, const float* mask_u,
+                   const float* mask_bn, float* stats, float* y);
+/* dW[kh*kw*Ci, Co] += x'-patches^T dy on tensor cores (M = kh*kw*Ci, N = Co, K = pixels); in_bn as above */
+int avsr_conv2d_wgrad_tc(avsr_stream_t stream, const float* x, const float* in_bn, const float* dy, int N, int H, int W,
+                         int Ci, int kh, int kw, int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, float* dW);
+/* per-channel coefficients of a batch_norm_relu from the fused statistics: coef [4 C] = (scale = gamma invstd, shift =
+ * beta - mean scale, a = invstd, b = -mean invstd); updates the moving statistics (momentum as tf.layers: m = m mom +
+ * batch (1 - mom), biased variance).  avsr_bn_coef_eval: the same from the moving statistics (inference). */
+int avsr_bn_finalize(avsr_stream_t stream, const float* sums, double count, const float* gamma, const float* beta,
+                     float eps, float momentum, int C, float* moving_mean, float* moving_var, float* coef);
+int avsr_bn_coef_eval(avsr_stream_t stream, const float* gamma, const float* beta, const float* moving_mean,
+                      const float* moving_var, float eps, int C, float* coef);
+/* du = gamma invstd (d - sum_d / n - xhat sum_dxhat / n) (+ residual): the apply pass of the batch_norm_relu backward from
+ * the masked gradient d and sums2 = (sum d, sum d xhat) that avsr_conv2d_tc(mask_u, mask_bn) produced; xhat recomputed from
+ * the saved BN input u */
+int avsr_bn_relu_bwd_apply(avsr_stream_t stream, const float* d, const float* u, const float* coef, const float* sums2,
+                           double count, const float* residual, long long rows, int C, float* du);
 int avsr_relu_fwd(avsr_stream_t stream, const float* x, long long n, float* y);               /* in place allowed */
 int avsr_relu_bwd(avsr_stream_t stream, const float* y, const float* dy, long long n, float* dx); /* dx = dy [y > 0] */
 

@@ -184,3 +184,63 @@ def test_tensor_core_convolutions_against_torch(N, H, Ci, Co, k, stride):
         wt = w.flip(0, 1).permute(0, 1, 3, 2).contiguous().view(-1, Ci)
         dx = ops.conv2d_tc(dy, wt, None, k, k, 1, k - 1 - pt, k - 1 - pl, H, H, in_dilation=stride)
         close(dx, xr.grad.permute(0, 2, 3, 1).cpu().numpy(), 2e-3, 'input gradient')
+
+
+@pytest.mark.parametrize('N,H,C', [(6, 36, 8), (10, 18, 16), (40, 9, 32)])
+def test_fused_batch_norm_relu_block_against_torch(N, H, C):
+    """conv -> batch_norm_relu -> conv + shortcut (res_block_0 of video.py:57-92 with skip_bn) with the BN-ReLU fused into
+    the convolutions around it (statistics in the producer's epilogue, apply in the consumer's loads, ReLU mask and backward
+    statistics in the epilogue of the input-gradient convolution) against torch autograd in fp32.  The torch chain starts
+    from the first convolution's output as the kernel produced it (that convolution is checked on its own above), so both
+    sides normalise - and cut at zero - the same numbers; what remains is the tf32 rounding of the operands."""
+    import torch.nn.functional as F
+    from avsr_tf1_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(N + H + C)
+    rnd = lambda *s: torch.randn(*s, device='cuda', generator=g)
+    x, wa, wb = rnd(N, H, H, C), rnd(3, 3, C, C) / (9 * C) ** 0.5, rnd(3, 3, C, C) / (9 * C) ** 0.5
+    ba, bb, gamma, beta, wout = 0.1 * rnd(C), 0.1 * rnd(C), 1 + 0.2 * rnd(C), 0.2 * rnd(C), rnd(N, H, H, C)
+    eps = 1e-5
+    count = N * H * H
+    s0 = torch.zeros(2 * C, device='cuda')
+    y0k = ops.conv2d_tc(x, wa.reshape(-1, C), ba, 3, 3, 1, 1, 1, H, H, stats=s0)
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y0, wbr, bbr, gr, br = [t.clone().requires_grad_(True) for t in (y0k, wb, bb, gamma, beta)]
+        conv = lambda t, w, b: F.conv2d(t.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, padding=1).permute(0, 2, 3, 1)
+        mean, var = y0.mean((0, 1, 2)), y0.var((0, 1, 2), unbiased=False)
+        z = torch.relu((y0 - mean) / torch.sqrt(var + eps) * gr + br)
+        o = conv(z, wbr, bbr) + z
+        (o * wout).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+
+    def l2(got, want, what, tol=3e-3):
+        err = float(torch.linalg.norm(got.double() - want.double()) / (torch.linalg.norm(want.double()) + 1e-30))
+        assert np.isfinite(err) and err <= tol, f'{what}: relative L2 error {err:.3e}'
+
+    l2(s0[:C] / count, mean.detach(), 'fused mean', 1e-4)
+    l2(s0[C:] / count - (s0[:C] / count) ** 2, var.detach(), 'fused variance', 1e-4)
+    mm, mv = torch.zeros(C, device='cuda'), torch.ones(C, device='cuda')
+    c0 = ops.bn_finalize(s0, count, gamma, beta, eps, 0.98, mm, mv)
+    l2(mm, 0.02 * mean.detach(), 'moving mean', 1e-4)
+    l2(mv, 0.98 + 0.02 * var.detach(), 'moving variance', 1e-4)
+    ok = ops.conv2d_tc(y0k, wb.reshape(-1, C), bb, 3, 3, 1, 1, 1, H, H, in_bn=c0, residual=y0k, res_bn=c0)
+    l2(ok, o.detach(), 'block output')
+    dWb = torch.zeros(9 * C, C, device='cuda')
+    ops.conv2d_wgrad_tc(y0k, wout, 3, 3, 1, 'SAME', dWb, in_bn=c0)
+    l2(dWb, wbr.grad.reshape(-1, C), 'dW of the second convolution')
+    s2 = torch.zeros(2 * C, device='cuda')
+    flipT = lambda w: w.flip(0, 1).permute(0, 1, 3, 2).contiguous().view(-1, C)
+    dm = ops.conv2d_tc(wout, flipT(wb), None, 3, 3, 1, 1, 1, H, H, residual=wout, mask_u=y0k, mask_bn=c0, stats=s2)
+    l2(s2[:C], br.grad, 'dbeta')
+    l2(s2[C:], gr.grad, 'dgamma')
+    du0 = ops.bn_relu_bwd_apply(dm, y0k, c0, s2, count)
+    l2(du0, y0.grad, 'gradient wrt the batch norm input')
+    res = rnd(N, H, H, C)
+    du1 = ops.bn_relu_bwd_apply(dm, y0k, c0, s2, count, residual=res)
+    l2(du1, y0.grad + res, 'gradient wrt the batch norm input + residual')
+    # inference coefficients from the moving statistics
+    ce = ops.bn_coef_eval(gamma, beta, mm, mv, eps)
+    ze = ops.conv2d_tc(y0k, torch.eye(C, device='cuda').reshape(1, 1, C, C).reshape(-1, C), None, 1, 1, 1, 0, 0, H, H, in_bn=ce)
+    l2(ze, torch.relu((y0k - mm) / torch.sqrt(mv + eps) * gamma + beta), 'inference-mode BN-ReLU through a 1x1 identity')
