@@ -100,7 +100,7 @@ PROTOTYPES = {
     'avsr_conv2d_wgrad': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'avsr_conv2d_tc_supported': (_I, [_I, _I, _I, _I, _I]),
     'avsr_conv2d_tc': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
-    'avsr_conv2d_wgrad_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'avsr_conv2d_wgrad_tc': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     'avsr_bn_finalize': (_I, [_P, _P, _D, _P, _P, _F, _F, _I, _P, _P, _P]),
     'avsr_bn_coef_eval': (_I, [_P, _P, _P, _P, _P, _F, _I, _P]),
     'avsr_bn_relu_bwd_apply': (_I, [_P, _P, _P, _P, _P, _D, _P, _L, _I, _P]),

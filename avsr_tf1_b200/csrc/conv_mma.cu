@@ -291,6 +291,7 @@ struct WgradP {
   const float* x;   // [N, H, W, Cin]
   const float* dy;  // [N, Ho, Wo, cout_total]
   float* dW;        // [KS*KS*Cin, cout_total] +=
+  float* dbias;     // [cout_total] += column sums of dy (the bias gradient), or null
   const float* in_bn;  // [2*Cin] or null: x is read as relu(x * scale + shift) (see ConvP)
   int N, H, W, Cin, Ho, Wo, pt, pl, Hp, Wp, F, PS, cout_total;
   int PK;           // pixels of a full group rounded up to 8
@@ -332,6 +333,7 @@ __global__ void __launch_bounds__(THREADS) conv_mma_wgrad_kernel(const WgradP p)
     offA[i] = (ca >> 2) * PS + ((ta / KS) * Wp + (ta % KS)) * 4 + (ca & 3);
     offB[i] = (cb >> 2) * PS + ((tb / KS) * Wp + (tb % KS)) * 4 + (cb & 3);
   }
+  float4 bsum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   const int hwo = p.Ho * p.Wo;
   const int ngroups = (p.N + p.F - 1) / p.F;
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
@@ -341,13 +343,15 @@ __global__ void __launch_bounds__(THREADS) conv_mma_wgrad_kernel(const WgradP p)
     load_frames<CINP>(sX, p.x, f0, nf, p.H, p.W, p.Cin, 1, p.pt, p.pl, p.Hp, Wp, PS, p.in_bn, p.mg);
     const int pvalid = nf * hwo;
     const int pk = (pvalid + 7) & ~7;
-    {  // dy of the group: [pixel][this CTA's NT*8 channels], rows past the last pixel zero
+    {  // dy of the group: [pixel][this CTA's NT*8 channels], rows past the last pixel zero; a thread always meets the
+       // same 4 channels (THREADS % C4 == 0), so the bias gradient is summed on the way
       constexpr int C4 = NT * 2;
       const float* src = p.dy + (size_t)f0 * hwo * p.cout_total + n0;
       for (int i = tid; i < pk * C4; i += THREADS) {
         const int pix = i / C4, c4 = i - pix * C4;
         float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (pix < pvalid) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)pix * p.cout_total) + c4);
+        bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
         v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);
         *reinterpret_cast<float4*>(sDy + pix * DS + c4 * 4) = v;
       }
@@ -377,6 +381,20 @@ __global__ void __launch_bounds__(THREADS) conv_mma_wgrad_kernel(const WgradP p)
           for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[i][nt], a0, a1, a2, a3, b0[nt], b1[nt]);
         }
       }
+    }
+  }
+  if (p.dbias) {  // threads tid, tid + C4, ... hold partial sums of the same 4 channels: lanes first, then one atomic per warp
+    constexpr int C4 = NT * 2;
+#pragma unroll
+    for (int o = C4; o < 32; o <<= 1) {
+      bsum.x += __shfl_xor_sync(0xffffffffu, bsum.x, o);
+      bsum.y += __shfl_xor_sync(0xffffffffu, bsum.y, o);
+      bsum.z += __shfl_xor_sync(0xffffffffu, bsum.z, o);
+      bsum.w += __shfl_xor_sync(0xffffffffu, bsum.w, o);
+    }
+    if (lane < C4) {
+      float* dst = p.dbias + n0 + lane * 4;
+      atomicAdd(dst, bsum.x); atomicAdd(dst + 1, bsum.y); atomicAdd(dst + 2, bsum.z); atomicAdd(dst + 3, bsum.w);
     }
   }
   // D rows gid (acc 0, 1) and gid + 8 (acc 2, 3), columns 2 tig, 2 tig + 1
@@ -633,7 +651,7 @@ extern "C" int avsr_conv2d_tc(avsr_stream_t stream, const float* x, int N, int H
 
 extern "C" int avsr_conv2d_wgrad_tc(avsr_stream_t stream, const float* x, const float* in_bn, const float* dy, int N, int H, int W,
                                     int Ci, int kh, int kw, int stride, int pad_top, int pad_left, int Ho, int Wo, int Co,
-                                    float* dW) {
+                                    float* dW, float* dbias) {
   AVSR_REQUIRE(avsr_conv2d_tc_supported(Ci, Co, kh, kw, stride), "conv2d_wgrad_tc: unsupported shape Ci=%d Co=%d k=%dx%d stride=%d",
                Ci, Co, kh, kw, stride);
   if (N <= 0) return 0;
@@ -642,7 +660,7 @@ extern "C" int avsr_conv2d_wgrad_tc(avsr_stream_t stream, const float* x, const 
                "conv2d_wgrad_tc: frame does not fit shared memory (H=%d W=%d Ci=%d)", H, W, Ci);
   cv::WgradP p;
   p.mg = q.mg;
-  p.x = x; p.dy = dy; p.dW = dW; p.in_bn = in_bn;
+  p.x = x; p.dy = dy; p.dW = dW; p.dbias = dbias; p.in_bn = in_bn;
   p.N = N; p.H = H; p.W = W; p.Cin = Ci; p.Ho = Ho; p.Wo = Wo; p.pt = pad_top; p.pl = pad_left;
   p.Hp = q.Hp; p.Wp = q.Wp; p.F = q.F; p.PS = q.PS; p.cout_total = Co; p.PK = q.PK;
   const int rc = cv::dispatch_wgrad((cudaStream_t)stream, p, q, kh, stride);

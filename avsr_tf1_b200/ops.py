@@ -286,14 +286,14 @@ def conv2d_tc(x, wmat, bias, kh, kw, stride, pad_top, pad_left, Ho, Wo, in_dilat
     return y
 
 
-def conv2d_wgrad_tc(x, dy, kh, kw, stride, padding, dW, in_bn=None):
+def conv2d_wgrad_tc(x, dy, kh, kw, stride, padding, dW, in_bn=None, dbias=None):
     """dW [kh*kw*Ci, Co] += patches(x')^T dy on tensor cores (avsr_conv2d_wgrad_tc); x' = relu(x scale + shift) with in_bn."""
-    _chk_f32(x, dy, dW, in_bn)
+    _chk_f32(x, dy, dW, in_bn, dbias)
     N, H, W, Ci = x.shape
     Ho, Wo, pt, pl = conv_geometry(H, W, kh, kw, stride, padding)
     Co = dy.shape[-1]
     check(_lib.load().avsr_conv2d_wgrad_tc(_stream(), x.data_ptr(), _p(in_bn), dy.data_ptr(), N, H, W, Ci, kh, kw, stride, pt,
-                                           pl, Ho, Wo, Co, dW.data_ptr()))
+                                           pl, Ho, Wo, Co, dW.data_ptr(), _p(dbias)))
 
 
 def bn_finalize(sums, count, gamma, beta, eps, momentum, moving_mean, moving_var):

@@ -81,8 +81,7 @@ class _Conv(object):
         """kernel and bias gradients from the layer input x (read through in_bn) and dy."""
         ctx = self.ctx
         ops.conv2d_wgrad_tc(x, dy, self.kh, self.kw, self.stride, self.padding, ctx.g(self.kernel).view(-1, self.cout),
-                            in_bn=in_bn)
-        ops.colsum(dy.view(-1, self.cout), ctx.g(self.bias))
+                            in_bn=in_bn, dbias=ctx.g(self.bias))
 
     def dgrad_tc(self, dy, in_hw, **kw):
         """gradient wrt the layer input [N, in_hw, in_hw, cin]: stride-1 convolution of dy (zero-stuffed for a stride-2

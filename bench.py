@@ -432,6 +432,57 @@ def side_config(args, torch, ops, cfg, graph, steps):
     return out
 
 
+def cnn_front_end_config(args, torch, ops, cfg, graph, steps):
+    """The same workload with the reference's visual front-end in the step (video_processing='resnet_cnn', what
+    run_audiovisual.py:34-58 / run_video.py select; video.py:143-195): lip crops [B, 75, 36, 36, 3] -> 13 convolutions +
+    batch_norm_relu per frame -> 128-d features -> video LSTM, trained jointly.  Reports the whole step and
+    the front-end's own forward + backward time."""
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    from tests.helpers import config_hparams, synthetic_batch, to_data_sequences, to_image_sequences
+    B = CONFIGS[cfg]['batch']
+    over = dict(randomness(graph))
+    att = args.attention or ('bahdanau' if cfg == 2 else 'scaled_luong')
+    over['attention_type'] = ((att,), (att,))
+    hp = config_hparams(cfg, video_processing='resnet_cnn', **over)
+    batch = to_image_sequences(synthetic_batch(hp, B=B, Ta=300, Tv=75, Fa=80, Fv=128, L=40, ragged=False, seed=0), hw=36)
+    ds = to_data_sequences({k: torch.from_numpy(v).pin_memory() for k, v in batch.items()})
+    model = Seq2SeqModel(ds, 'train', hp, seed=2001)
+    model.use_cuda_graph = not args.no_graph
+    model.feed(ds)
+    ms = timed_steps(torch, model, steps, 3) / steps
+    launches = int(model.launches_last_step)
+    loss, _ = model.fetch_scalars()
+    # the front-end alone, eager, CUDA events around its forward and backward
+    cnn = getattr(model, '_cnn', None)
+    fe = None
+    if cnn is not None:
+        N = B * 75
+        frames = torch.rand(N, 36, 36, 3, device='cuda') * 2 - 1
+        d = torch.randn(N, cnn.out_dim, device='cuda') * 1e-3
+        for _ in range(2):
+            cnn.forward(frames, True)
+            cnn.backward(d)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        torch.cuda.synchronize()
+        e[0].record()
+        cnn.forward(frames, True)
+        e[1].record()
+        cnn.backward(d)
+        e[2].record()
+        torch.cuda.synchronize()
+        fw, bw = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+        fe = {'forward_ms': round(fw, 3), 'backward_ms': round(bw, 3), 'frames': N,
+              'forward_tflops': round(11.47e6 * N / fw / 1e9, 2),
+              'kernels': 'cv::conv_mma_{fwd,wgrad}_kernel (implicit-GEMM mma.sync TF32, BN-ReLU fused), csrc/conv_mma.cu'}
+    out = {'value': round(B / (ms / 1e3), 2), 'unit': UNIT, 'ms_per_step': round(ms, 4), 'per_gpu_batch': B,
+           'gpu_launches_per_step': launches, 'loss': round(float(loss), 6), 'graph': graph,
+           'video_input': '36x36x3 lip crops -> resnet_cnn (8, 16, 32, 64 filters, 128 units) inside the training step',
+           'front_end': fe}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def tfrecord_e2e(args, torch, model, n_utt, B):
     """the same training step fed from synthetic TFRecords in the reference's schema (8d) through
     the native reader (include/avsr_io.h) - shuffle, bucket, padded batch into pinned memory on a prefetch thread -
@@ -704,6 +755,11 @@ def main():
                 line['parity_graph'] = side_config(args, torch, ops, cfg, 'parity', side_steps)
             except Exception as ex:
                 line['parity_graph'] = {'error': repr(ex)}
+        if cfg >= 3:  # the visual front-end inside the step (what run_video.py / run_audiovisual.py train)
+            try:
+                line['with_resnet_cnn'] = cnn_front_end_config(args, torch, ops, cfg, graph, side_steps)
+            except Exception as ex:
+                line['with_resnet_cnn'] = {'error': repr(ex)}
         line['configs'] = {}
         for c in sorted(CONFIGS):  # the other BASELINE.json configurations, each at its own batch, same graph
             if c == cfg:

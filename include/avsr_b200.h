@@ -297,9 +297,11 @@ int avsr_conv2d_tc(avsr_stream_t stream, const float* x, int N, int H, int W, in
                    int kh, int kw, int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, int in_dilation,
                    const float* in_bn, const float* residual, const float* res_bn, const float* mask_u,
                    const float* mask_bn, float* stats, float* y);
-/* dW[kh*kw*Ci, Co] += x'-patches^T dy on tensor cores (M = kh*kw*Ci, N = Co, K = pixels); in_bn as above */
+/* dW[kh*kw*Ci, Co] += x'-patches^T dy on tensor cores (M = kh*kw*Ci, N = Co, K = pixels); in_bn as above;
+ * dbias [Co] += column sums of dy (the bias gradient, summed while dy is staged) or NULL */
 int avsr_conv2d_wgrad_tc(avsr_stream_t stream, const float* x, const float* in_bn, const float* dy, int N, int H, int W,
-                         int Ci, int kh, int kw, int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, float* dW);
+                         int Ci, int kh, int kw, int stride, int pad_top, int pad_left, int Ho, int Wo, int Co, float* dW,
+                         float* dbias);
 /* per-channel coefficients of a batch_norm_relu from the fused statistics: coef [4 C] = (scale = gamma invstd, shift =
  * beta - mean scale, a = invstd, b = -mean invstd); updates the moving statistics (momentum as tf.layers: m = m mom +
  * batch (1 - mom), biased variance).  avsr_bn_coef_eval: the same from the moving statistics (inference). */

@@ -177,9 +177,10 @@ def test_tensor_core_convolutions_against_torch(N, H, Ci, Co, k, stride):
     y2 = y_ref.reshape(-1, Co).double()
     close(stats[:Co], y2.sum(0).cpu().numpy(), 2e-3, 'sum of y')
     close(stats[Co:], (y2 * y2).sum(0).cpu().numpy(), 2e-3, 'sum of y^2')
-    dW = torch.zeros(k * k * Ci, Co, device='cuda')
-    ops.conv2d_wgrad_tc(x, dy, k, k, stride, 'SAME', dW)
+    dW, db = torch.zeros(k * k * Ci, Co, device='cuda'), torch.zeros(Co, device='cuda')
+    ops.conv2d_wgrad_tc(x, dy, k, k, stride, 'SAME', dW, dbias=db)
     close(dW, wr.grad.permute(2, 3, 1, 0).reshape(-1, Co).cpu().numpy(), 2e-3, 'weight gradient')
+    close(db, dy.double().sum((0, 1, 2)).cpu().numpy(), 1e-4, 'bias gradient')
     if Ci % 8 == 0:
         wt = w.flip(0, 1).permute(0, 1, 3, 2).contiguous().view(-1, Ci)
         dx = ops.conv2d_tc(dy, wt, None, k, k, 1, k - 1 - pt, k - 1 - pl, H, H, in_dilation=stride)
