@@ -106,6 +106,8 @@ PROTOTYPES = {
     'avsr_bn_relu_bwd_apply': (_I, [_P, _P, _P, _P, _P, _D, _P, _L, _I, _P]),
     'avsr_relu_fwd': (_I, [_P, _P, _L, _P]),
     'avsr_relu_bwd': (_I, [_P, _P, _P, _L, _P]),
+    'avsr_selu_fwd': (_I, [_P, _P, _L, _P]),
+    'avsr_selu_bwd': (_I, [_P, _P, _P, _L, _P]),
     'avsr_greedy_pick': (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     'avsr_beam_step': (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     'avsr_gather_rows': (_I, [_P, _P, _P, _L, _I, _P]),

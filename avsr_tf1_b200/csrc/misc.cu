@@ -507,6 +507,24 @@ __global__ void relu_bwd_kernel(const float* __restrict__ y, const float* __rest
     dx[i] = y[i] > 0.0f ? dy[i] : 0.0f;
 }
 
+// tf.nn.selu of the optional dense stack in front of an encoder (encoder.py:148-171): y = s * (x > 0 ? x : a * (e^x - 1));
+// backward from the saved y: dy/dx = s for y > 0, else y + s a
+#define AVSR_SELU_SCALE 1.0507009873554804934193349852946f
+#define AVSR_SELU_ALPHA 1.6732632423543772848170429916717f
+__global__ void selu_fwd_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    y[i] = AVSR_SELU_SCALE * (v > 0.0f ? v : AVSR_SELU_ALPHA * expm1f(v));
+  }
+}
+__global__ void selu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, long long n,
+                                float* __restrict__ dx) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = y[i];
+    dx[i] = dy[i] * (v > 0.0f ? AVSR_SELU_SCALE : v + AVSR_SELU_SCALE * AVSR_SELU_ALPHA);
+  }
+}
+
 // ---- direct convolutions for the narrow layers of the front-end (8 / 16 output channels: almost all of its pixels) ---
 // One thread per output pixel, all CO output channels in registers, the kernel [kh*kw*Ci][CO] in shared memory (broadcast
 // reads); NHWC input read straight from global memory (the 3x3 neighbourhoods of adjacent threads overlap in L1).  No
@@ -1013,6 +1031,18 @@ int avsr_relu_fwd(avsr_stream_t s, const float* x, long long n, float* y) {
 int avsr_relu_bwd(avsr_stream_t s, const float* y, const float* dy, long long n, float* dx) {
   if (n <= 0) return 0;
   AVSR_LAUNCH(relu_bwd_kernel, grid_for(n), 256, 0, ST(s), y, dy, n, dx);
+  return 0;
+}
+
+int avsr_selu_fwd(avsr_stream_t s, const float* x, long long n, float* y) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(selu_fwd_kernel, grid_for(n), 256, 0, ST(s), x, n, y);
+  return 0;
+}
+
+int avsr_selu_bwd(avsr_stream_t s, const float* y, const float* dy, long long n, float* dx) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(selu_bwd_kernel, grid_for(n), 256, 0, ST(s), y, dy, n, dx);
   return 0;
 }
 

@@ -34,6 +34,63 @@ def _layer_prefixes(scope, n_layers, sub=''):
     return [pre + f'multi_rnn_cell/cell_{k}/lstm_cell' for k in range(n_layers)]
 
 
+class InputDenseStack(object):
+    """_maybe_add_dense_layers (encoder.py:148-171): Dense(units, activation=tf.nn.selu, use_bias=False,
+    kernel_initializer=variance_scaling_initializer(), kernel_regularizer=l2(1e-4)) for every entry of
+    `input_dense_layers`, between the input normalisation and the first recurrent layer.  tf.layers names them dense,
+    dense_1, ... inside `<scope>/Encoder` (they are called at encoder.py:64, before the state projections of a
+    bidirectional encoder get their names)."""
+    L2_SCALE = 1e-4
+
+    def __init__(self, ctx: BuildContext, scope, in_dim, units):
+        self.ctx = ctx
+        self.kernels, d = [], int(in_dim)
+        for i, u in enumerate(units):
+            name = f'{scope}/Encoder/dense' + ('' if i == 0 else f'_{i}') + '/kernel'
+            self.kernels.append(ctx.declare(name, (d, int(u)), 'lstm_kernel'))  # (variance_scaling_initializer(), as the cells)
+            d = int(u)
+        self.out_dim = d
+
+    def forward(self, x):
+        """x [T,B,F] product operand -> [T,B,units[-1]] product operand."""
+        ctx = self.ctx
+        self._saved = []
+        for k in self.kernels:
+            T, B, F = x.shape
+            W = ctx.w(k)
+            y = ops.empty(T, B, W.shape[1])
+            ops.gemm(x.reshape(T * B, F), W, y.view(T * B, -1))
+            ops.selu_fwd(y, out=y)
+            self._saved.append((x, y))
+            x = ops.round_tf32(y) if ops.tensor_cores_enabled() else y
+        return x
+
+    def backward(self, d):
+        """d: gradient wrt the stack's output; accumulates the kernel gradients, returns the gradient wrt its input."""
+        ctx = self.ctx
+        for k, (x, y) in zip(reversed(self.kernels), reversed(self._saved)):
+            T, B, F = x.shape
+            dz = ops.selu_bwd(y, d.contiguous())
+            if ops.tensor_cores_enabled():
+                ops.round_tf32(dz, dz)
+            dz2 = dz.view(T * B, -1)
+            ops.gemm(x.reshape(T * B, F), dz2, ctx.g(k), ta=True, beta=1.0)
+            d = ops.empty(T, B, F)
+            ops.gemm(dz2, ctx.w(k), d.view(T * B, F), tb=True)
+        self._saved = None
+        return d
+
+    def add_l2(self, loss_sumsq, unit_scale):
+        """kernel_regularizer: gradient += 1e-4 w; loss_sumsq[0] += (1e-4 / unit_scale) sum w^2 (the caller's slot is later
+        multiplied by unit_scale / 2).  Only called when the reference adds REGULARIZATION_LOSSES (seq2seq.py:180-184)."""
+        ctx = self.ctx
+        for k in self.kernels:
+            ops.axpy(self.L2_SCALE, ctx.p(k).reshape(-1), ctx.g(k).reshape(-1))
+            tmp = ops.zeros(1)
+            ops.sumsq(ctx.p(k).reshape(-1), tmp)
+            ops.axpy(self.L2_SCALE / unit_scale, tmp, loss_sumsq)
+
+
 class Seq2SeqEncoder(object):
     """Input BatchNorm -> stacked uni/bi-directional LSTM (encoder.py:14-196).
 
@@ -52,9 +109,12 @@ class Seq2SeqEncoder(object):
         self._regress_aus = bool(kwargs.get('regress_aus', False)) and mode == 'train'
         if hparams.instance_normalisation:
             raise NotImplementedError('instance_normalisation is off in every reference config')
-        if hparams.input_dense_layers[0] > 0:
-            raise NotImplementedError('input_dense_layers is off in every reference config (avsr.py:38)')
         self._bn = BatchNormInput(ctx, scope, self._F) if hparams.batch_normalisation is True else None
+        self._dense = None  # _maybe_add_dense_layers (encoder.py:148-171); default (0,) = identity (avsr.py:38)
+        self._rnn_in = self._F
+        if hparams.input_dense_layers[0] > 0:
+            self._dense = InputDenseStack(ctx, scope, self._F, hparams.input_dense_layers)
+            self._rnn_in = self._dense.out_dim
         self.input_gradient = False  # True: keep what the gradient wrt the raw features needs (backward(need_dx=True))
         self._init_encoder()
         if self._regress_aus:
@@ -75,7 +135,7 @@ class Seq2SeqEncoder(object):
                 residual_connections=hp.residual_encoder if not sub else False,
                 highway_connections=hp.highway_encoder if not sub else False,
                 weight_sharing=hp.encoder_weight_sharing if not sub else False))
-            ops_, in_dim = [], self._F
+            ops_, in_dim = [], self._rnn_in
             for prefix, cell in zip(_layer_prefixes(scope, L, sub), cells):
                 ops_.append(LSTMLayerOp(ctx, prefix, in_dim, cell.num_units, drop=ctx.drop_state(cell, prefix)))
                 in_dim = cell.num_units
@@ -93,9 +153,10 @@ class Seq2SeqEncoder(object):
             self._fw, self._bw = stack('fw'), stack('bw')
             dec = hp.decoder_units_per_layer[0]
             self._proj = []
-            for i in range(2 * L):  # encoder.py:124-141: dense, dense_1, ... (c then h per layer)
+            nd = len(self._dense.kernels) if self._dense is not None else 0  # the input dense stack is named first
+            for i in range(nd, nd + 2 * L):  # encoder.py:124-141: dense, dense_1, ... (c then h per layer)
                 name = f'{scope}/Encoder/dense' + ('' if i == 0 else f'_{i}') + '/kernel'
-                self._proj.append(ctx.declare(name, (2 * units[i // 2], dec), 'glorot'))
+                self._proj.append(ctx.declare(name, (2 * units[(i - nd) // 2], dec), 'glorot'))
             self.output_dim = 2 * units[-1]
         else:
             raise Exception('Allowed encoder types: `unidirectional`, `bidirectional`')
@@ -111,17 +172,23 @@ class Seq2SeqEncoder(object):
         if self._bn is not None:
             # tf32-rounded in tensor-core mode; xhat is only stored if the gradient wrt the raw features is wanted
             # (or if layer 0 drops its input: then dgamma / dbeta need the gradient wrt the normalised features)
-            return self._bn.forward(inputs, train, batch_major=batch_major,
-                                    keep_xhat=self.input_gradient or self._layer0_drops_input())
-        if batch_major:
-            inputs = ops.transpose01(inputs)
-        return ops.round_tf32(inputs) if ops.tensor_cores_enabled() else inputs
+            x = self._bn.forward(inputs, train, batch_major=batch_major,
+                                 keep_xhat=self.input_gradient or self._layer0_drops_input())
+        else:
+            if batch_major:
+                inputs = ops.transpose01(inputs)
+            x = ops.round_tf32(inputs) if ops.tensor_cores_enabled() else inputs
+        return self._dense.forward(x) if self._dense is not None else x
 
     def _layer0_ops(self):
         first = [self._fw[0]] if self._fw else [self._top]  # (an AV-Align encoder of one layer: the attention cell)
         return first + ([self._bw[0]] if self._bw is not None else [])
 
     def _layer0_drops_input(self):
+        """True when the gradient wrt the normalised features has to be formed explicitly (dgamma / dbeta cannot be read
+        off the layer-0 weight gradient): layer 0 drops its input, or a dense stack sits between the two."""
+        if self._mode == 'train' and self._dense is not None:
+            return True
         return self._mode == 'train' and any(op.drop is not None and op.drop.thr_in for op in self._layer0_ops())
 
     def _round_outputs(self, out, op):
@@ -266,6 +333,8 @@ class Seq2SeqEncoder(object):
         """Gradients of the input normalisation.  Its output only feeds the layer-0 gate product(s), so dgamma / dbeta
         follow from the layer-0 weight gradients (BatchNormInput.backward_from_layer0) and the [T*B,F] gradient wrt the
         normalised features is only formed when the caller asks for the gradient wrt the raw features."""
+        if self._dense is not None and dx is not None:
+            dx = self._dense.backward(dx)
         if self._bn is None:
             return dx
         if self._layer0_drops_input() and not self.input_gradient:
@@ -298,7 +367,7 @@ class AttentiveEncoder(Seq2SeqEncoder):
         cells = maybe_list(build_rnn_layers(
             cell_type=hp.cell_type, num_units_per_layer=units, use_dropout=hp.use_dropout,
             dropout_probability=hp.audio_encoder_dropout_probability, mode=self._mode, as_list=True))
-        self._fw, in_dim = [], self._F
+        self._fw, in_dim = [], self._rnn_in
         for k in range(L - 1):
             prefix = f'{scope}/Encoder/multi_rnn_cell/cell_{k}/lstm_cell'
             self._fw.append(LSTMLayerOp(ctx, prefix, in_dim, cells[k].num_units, drop=ctx.drop_state(cells[k], prefix)))

@@ -323,6 +323,18 @@ def bn_relu_bwd_apply(d, u, coef, sums2, count, residual=None, out=None):
     return du
 
 
+def selu_fwd(x, out=None):
+    y = torch.empty_like(x) if out is None else out
+    check(_lib.load().avsr_selu_fwd(_stream(), x.data_ptr(), x.numel(), y.data_ptr()))
+    return y
+
+
+def selu_bwd(y, dy, out=None):
+    dx = torch.empty_like(dy) if out is None else out
+    check(_lib.load().avsr_selu_bwd(_stream(), y.data_ptr(), dy.data_ptr(), dy.numel(), dx.data_ptr()))
+    return dx
+
+
 def relu_fwd(x, out=None):
     y = torch.empty_like(x) if out is None else out
     check(_lib.load().avsr_relu_fwd(_stream(), x.data_ptr(), x.numel(), y.data_ptr()))

@@ -558,6 +558,9 @@ class Seq2SeqModel(object):
                 ops.sumsq(st.p(n), self._loss_dev[1:2])
         if self._cnn is not None:  # conv kernel_regularizer (video.py:27), summed into the loss by seq2seq.py:180-184
             self._cnn.add_l2(self._loss_dev[4:5])
+            for enc in (self._video_encoder, self._audio_encoder):  # ... together with the rest of REGULARIZATION_LOSSES
+                if enc is not None and getattr(enc, '_dense', None) is not None:
+                    enc._dense.add_l2(self._loss_dev[4:5], 1e-3)
         ops.sumsq(st.grad, self._loss_dev[2:3])
 
     def apply_gradients(self):

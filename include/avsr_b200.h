@@ -316,6 +316,10 @@ int avsr_bn_relu_bwd_apply(avsr_stream_t stream, const float* d, const float* u,
                            double count, const float* residual, long long rows, int C, float* du);
 int avsr_relu_fwd(avsr_stream_t stream, const float* x, long long n, float* y);               /* in place allowed */
 int avsr_relu_bwd(avsr_stream_t stream, const float* y, const float* dy, long long n, float* dx); /* dx = dy [y > 0] */
+/* tf.nn.selu of the optional dense stack in front of an encoder (encoder.py:148-171, Dense(units, activation=selu,
+ * use_bias=False)): y = 1.0507 (x > 0 ? x : 1.6733 (e^x - 1)); backward from the saved y.  In place allowed. */
+int avsr_selu_fwd(avsr_stream_t stream, const float* x, long long n, float* y);
+int avsr_selu_bwd(avsr_stream_t stream, const float* y, const float* dy, long long n, float* dx);
 
 /* ---- optimiser (seq2seq.py:175-178, 195-257) --------------------------------- */
 /* out[0] += sum x^2 */

@@ -51,6 +51,8 @@ CASES = [
     (4, dict(attention_type=(('bahdanau',), ('bahdanau',)))),
     (5, dict(attention_type=(('bahdanau',), ('bahdanau',)))),
     (5, dict(attention_type=(('luong',), ('normed_bahdanau',)), batch_normalisation=False)),
+    # input_dense_layers (encoder.py:148-171): selu Dense stack in front of the encoders
+    (2, dict(input_dense_layers=(96, 64))), (5, dict(input_dense_layers=(64,))),
 ]
 
 

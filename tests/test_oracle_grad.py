@@ -32,6 +32,10 @@ CASES += [
     # resnet_cnn front-end on 8x8x3 crops (8 -> 4 -> 2 -> 1), through the encoders and the decoder
     (3, dict(video_processing='resnet_cnn', cnn_filters=(2, 3, 4, 5), cnn_dense_units=6)),
     (5, dict(DROP, video_processing='resnet_cnn', cnn_filters=(2, 3, 4, 5), cnn_dense_units=6, regress_aus=True)),
+    # input_dense_layers (encoder.py:148-171): selu Dense stack between the input normalisation and the first layer -
+    # uni / bidirectional (the state projections are named after it) / AV-Align, and with a CNN (its L2 term joins the loss)
+    (1, dict(input_dense_layers=(5, 4))), (2, dict(input_dense_layers=(5,))), (5, dict(DROP, input_dense_layers=(4, 5))),
+    (4, dict(input_dense_layers=(5,), video_processing='resnet_cnn', cnn_filters=(2, 3, 4, 5), cnn_dense_units=6)),
 ]
 
 
