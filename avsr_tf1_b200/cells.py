@@ -30,11 +30,23 @@ def build_rnn_layers(cell_type, num_units_per_layer, use_dropout, dropout_probab
                      residual_connections=False, highway_connections=False, weight_sharing=False, as_list=False):
     """Same signature and return convention as cells.py:61-102: one cell for a single
     layer, else the stack (a list stands in for MultiRNNCell)."""
-    if residual_connections or highway_connections or weight_sharing:
-        raise NotImplementedError('residual / highway / weight-sharing encoders are off in every reference '
-                                  'config (avsr.py:41-48) and not implemented on the B200 path')
-    cell_list = [_build_single_cell(cell_type, units, use_dropout, mode, dropout_probability, dtype)
-                 for units in num_units_per_layer]
+    if highway_connections:
+        raise NotImplementedError('highway encoders (tf.contrib.rnn.HighwayWrapper) are off in every reference '
+                                  'config (avsr.py:42) and not implemented on the B200 path')
+    cell_list = []
+    for layer, units in enumerate(num_units_per_layer):
+        if layer > 1 and weight_sharing is True:
+            # cells.py:77-78: the SAME cell object is used again: layers 2.. run with the variables of layer 1 (the cell
+            # is already built when MultiRNNCell calls it under `cell_2`); every position still draws its own masks
+            cell = LSTMCellSpec(units, cell_list[-1].use_dropout, cell_list[-1].dropout_probability)
+            cell.share_with = 1
+            cell.residual = cell_list[-1].residual
+        else:
+            cell = _build_single_cell(cell_type, units, use_dropout, mode, dropout_probability, dtype)
+            cell.share_with = None
+            # cells.py:91-92: ResidualWrapper(cell) for layer > 0: output = cell output + (un-dropped) layer input
+            cell.residual = bool(residual_connections is True and layer > 0)
+        cell_list.append(cell)
     if len(cell_list) == 1:
         return cell_list[0]
     return cell_list

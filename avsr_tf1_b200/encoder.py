@@ -137,7 +137,12 @@ class Seq2SeqEncoder(object):
                 weight_sharing=hp.encoder_weight_sharing if not sub else False))
             ops_, in_dim = [], self._rnn_in
             for prefix, cell in zip(_layer_prefixes(scope, L, sub), cells):
-                ops_.append(LSTMLayerOp(ctx, prefix, in_dim, cell.num_units, drop=ctx.drop_state(cell, prefix)))
+                share = ops_[cell.share_with] if getattr(cell, 'share_with', None) is not None else None
+                op = LSTMLayerOp(ctx, prefix, in_dim, cell.num_units, drop=ctx.drop_state(cell, prefix), share=share)
+                op.residual = bool(getattr(cell, 'residual', False))
+                if op.residual and in_dim != cell.num_units:
+                    raise ValueError('residual connections need layers of equal width (ResidualWrapper adds input and output)')
+                ops_.append(op)
                 in_dim = cell.num_units
             return ops_
 
@@ -216,15 +221,19 @@ class Seq2SeqEncoder(object):
                 outb = backward_stack()
         cur, cur_op = None, x
         for op in self._fw:
-            cur = op.forward(cur_op, inputs_len)
-            cur_op = op.operand
+            out = op.forward(cur_op, inputs_len)
+            if getattr(op, 'residual', False):  # ResidualWrapper (cells.py:91-92): + the layer's (un-dropped) input
+                cur = out + cur
+                cur_op = ops.round_tf32(cur) if ops.tensor_cores_enabled() else cur
+            else:
+                cur, cur_op = out, op.operand
         if side is not None:
             ctx.join(1)
         elif self._bw is not None:
             outb = backward_stack()
         if self._bw is None:
             self._outputs = cur
-            self._outputs_op = self._round_outputs(cur, self._fw[-1])
+            self._outputs_op = cur_op if getattr(self._fw[-1], 'residual', False) else self._round_outputs(cur, self._fw[-1])
             self._final = self._fw[-1].final
         else:
             T, B, H = cur.shape
@@ -282,7 +291,10 @@ class Seq2SeqEncoder(object):
             need_dx = need_dx or self._layer0_drops_input()
             for i in range(n - 1, -1, -1):
                 need = (i > 0) or need_dx
-                d = self._fw[i].backward(d, dfinal_state if i == n - 1 else None, need_dx=need)
+                dn = self._fw[i].backward(d, dfinal_state if i == n - 1 else None, need_dx=need)
+                if getattr(self._fw[i], 'residual', False) and dn is not None:
+                    ops.axpy(1.0, d, dn)  # the shortcut around the cell
+                d = dn
             dx = d
         else:
             T, B, H2 = self._outputs.shape

@@ -188,9 +188,15 @@ class BatchNormInput:
 class LSTMLayerOp:
     """One LSTMCell layer under dynamic_rnn (cells.py:14-18, encoder.py:80)."""
 
-    def __init__(self, ctx: BuildContext, prefix: str, in_dim: int, H: int, drop: 'DropState' = None):
+    def __init__(self, ctx: BuildContext, prefix: str, in_dim: int, H: int, drop: 'DropState' = None,
+                 share: 'LSTMLayerOp' = None):
         self.ctx, self.I, self.H = ctx, in_dim, H
         self.drop = drop
+        if share is not None:  # encoder_weight_sharing (cells.py:77-78): this position runs with another layer's variables
+            if (share.I, share.H) != (in_dim, H):
+                raise ValueError('weight sharing needs layers of equal shape')
+            self.kernel, self.bias = share.kernel, share.bias
+            return
         self.kernel = ctx.declare(prefix + '/kernel', (in_dim + H, 4 * H), 'lstm_kernel')
         self.bias = ctx.declare(prefix + '/bias', (4 * H,), 'zeros')
 

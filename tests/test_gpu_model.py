@@ -53,6 +53,8 @@ CASES = [
     (5, dict(attention_type=(('luong',), ('normed_bahdanau',)), batch_normalisation=False)),
     # input_dense_layers (encoder.py:148-171): selu Dense stack in front of the encoders
     (2, dict(input_dense_layers=(96, 64))), (5, dict(input_dense_layers=(64,))),
+    # ResidualWrapper on encoder layers > 0, layers 2.. sharing the cell of layer 1 (cells.py:77-92)
+    (3, dict(residual_encoder=True)), (4, dict(residual_encoder=True, encoder_weight_sharing=True)),
 ]
 
 

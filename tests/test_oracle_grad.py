@@ -36,6 +36,9 @@ CASES += [
     # uni / bidirectional (the state projections are named after it) / AV-Align, and with a CNN (its L2 term joins the loss)
     (1, dict(input_dense_layers=(5, 4))), (2, dict(input_dense_layers=(5,))), (5, dict(DROP, input_dense_layers=(4, 5))),
     (4, dict(input_dense_layers=(5,), video_processing='resnet_cnn', cnn_filters=(2, 3, 4, 5), cnn_dense_units=6)),
+    # ResidualWrapper on encoder layers > 0 and the shared cell of layers 2.. (cells.py:77-92)
+    (3, dict(DROP, residual_encoder=True)), (4, dict(residual_encoder=True, encoder_weight_sharing=True)),
+    (3, dict(encoder_weight_sharing=True)),
 ]
 
 
