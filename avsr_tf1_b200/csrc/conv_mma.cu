@@ -534,6 +534,7 @@ static bool make_plan(int N, int H, int W, int Ci, int Ho, int Wo, int Co, int K
   q.Wp = max(ls * (W - 1) + 1 + pl, S * (Wo - 1) + KS);
   const int ws = q.nt == 1 ? 8 : q.nt * 8 + 8;
   // two CTAs per SM when a group of >= 8 m16 tiles (128 pixels) fits 100 KB; one CTA with up to 200 KB otherwise
+  // (measured: three CTAs of one frame each are slower than two CTAs of two frames for the narrow layers)
   const size_t limit = 200 * 1024;
   size_t budget = 100 * 1024;
   const int mt = (KS * KS * q.cinp + 15) / 16;

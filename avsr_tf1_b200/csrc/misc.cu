@@ -303,10 +303,13 @@ __global__ void embedding_bwd_kernel(const float* __restrict__ dout, const int* 
   }
 }
 
-// one warp per (t,b) row
+// one warp per (t,b) row.  smoothing > 0: the reference's label-smoothing path (seq2seq.py:147-155 -> devel.py:54-61):
+// the targets become (1 - eps) onehot + eps / V AND the loss turns into the UNMASKED mean over all T x B positions - the
+// smoothed loss function returns a reduced scalar, which sequence_loss multiplies by the weights and divides by their sum
+// again.  Rows past the label length hold imputed zero logits: they add log V to the sum and carry no gradient.
 __global__ void seq_loss_kernel(const float* __restrict__ logits, int T, int B, int V, const int* __restrict__ labels,
                                 int ldl, const int* __restrict__ labels_len, const float* __restrict__ inv_denom_dev,
-                                float* __restrict__ loss_sum, float* __restrict__ dlogits) {
+                                float smoothing, float* __restrict__ loss_sum, float* __restrict__ dlogits) {
   const float inv_denom = inv_denom_dev[0];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= T * B) return;
@@ -315,21 +318,27 @@ __global__ void seq_loss_kernel(const float* __restrict__ logits, int T, int B, 
   float* dz = dlogits + (size_t)warp * V;
   if (t >= labels_len[b]) {
     for (int v = lane; v < V; v += 32) dz[v] = 0.0f;
+    if (smoothing > 0.0f && lane == 0) atomicAdd(loss_sum, logf((float)V));
     return;
   }
   float mx = -INFINITY;
   for (int v = lane; v < V; v += 32) mx = fmaxf(mx, z[v]);
   mx = warp_max(mx);
-  float s = 0.0f;
-  for (int v = lane; v < V; v += 32) s += expf(z[v] - mx);
+  float s = 0.0f, zs = 0.0f;
+  for (int v = lane; v < V; v += 32) {
+    s += expf(z[v] - mx);
+    zs += z[v];
+  }
   s = warp_sum(s);
+  zs = warp_sum(zs);
   const float lse = logf(s) + mx;
   const int y = labels[(size_t)b * ldl + t];
+  const float on = 1.0f - smoothing, off = smoothing / (float)V;
   for (int v = lane; v < V; v += 32) {
     float p = expf(z[v] - lse);
-    dz[v] = (p - (v == y ? 1.0f : 0.0f)) * inv_denom;
+    dz[v] = (p - (v == y ? on : 0.0f) - off) * inv_denom;
   }
-  if (lane == 0) atomicAdd(loss_sum, lse - z[y]);
+  if (lane == 0) atomicAdd(loss_sum, lse - on * z[y] - off * zs);
 }
 
 // Action-Unit head: one thread per (t, b, k)
@@ -888,10 +897,10 @@ int avsr_embedding_bwd(avsr_stream_t s, const float* dout, const int* ids, long 
 }
 
 int avsr_seq_loss(avsr_stream_t s, const float* logits, int T, int B, int V, const int* labels, int ldl,
-                  const int* labels_len, const float* inv_denom, float* loss_sum, float* dlogits) {
+                  const int* labels_len, const float* inv_denom, float label_smoothing, float* loss_sum, float* dlogits) {
   if (T * B <= 0) return 0;
   AVSR_LAUNCH(seq_loss_kernel, cdiv((long long)T * B * 32, 256), 256, 0, ST(s), logits, T, B, V, labels, ldl,
-              labels_len, inv_denom, loss_sum, dlogits);
+              labels_len, inv_denom, label_smoothing, loss_sum, dlogits);
   return 0;
 }
 

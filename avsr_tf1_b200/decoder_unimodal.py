@@ -133,7 +133,8 @@ class Seq2SeqUnimodalDecoder(object):
                      bias=ctx.p(self._bd))
         self._out = out
         self._dlogits = torch.empty_like(self._logits)
-        ops.seq_loss(self._logits, labels, labels_len, inv_denom, loss_sum, self._dlogits)
+        ops.seq_loss(self._logits, labels, labels_len, inv_denom, loss_sum, self._dlogits,
+                     label_smoothing=float(self._hparams.label_smoothing))
         return self._logits
 
     def _forward_train_sampled(self, memories, init, dec_in_ids, labels_len, T, B):

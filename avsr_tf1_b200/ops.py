@@ -180,12 +180,14 @@ def _dev_scalar(x):
     return torch.tensor([float(x)], dtype=torch.float32, device='cuda')
 
 
-def seq_loss(logits, labels, labels_len, inv_denom, loss_sum, dlogits):
-    """inv_denom: device scalar tensor (or a float, copied to the device)."""
+def seq_loss(logits, labels, labels_len, inv_denom, loss_sum, dlogits, label_smoothing=0.0):
+    """inv_denom: device scalar tensor (or a float, copied to the device).  label_smoothing > 0: the reference's smoothed,
+    UNMASKED mean (include/avsr_b200.h); inv_denom is then 1 / (T*B)."""
     T, B, V = logits.shape
     inv = _dev_scalar(inv_denom)
     check(_lib.load().avsr_seq_loss(_stream(), logits.data_ptr(), T, B, V, labels.data_ptr(), labels.stride(0),
-                                    labels_len.data_ptr(), inv.data_ptr(), loss_sum.data_ptr(), dlogits.data_ptr()))
+                                    labels_len.data_ptr(), inv.data_ptr(), float(label_smoothing), loss_sum.data_ptr(),
+                                    dlogits.data_ptr()))
 
 
 def au_loss(z, aus, lens, scale_dev, loss_sum, dz):

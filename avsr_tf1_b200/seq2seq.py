@@ -237,8 +237,6 @@ class Seq2SeqModel(object):
         if hp.loss_fun is not None:
             raise ValueError('Unknown loss function {}'.format(hp.loss_fun)) if hp.loss_fun not in (
                 'focal_loss', 'mc_loss') else NotImplementedError('devel.py losses are self-described untested')
-        if hp.label_smoothing > 0.0:
-            raise NotImplementedError('label smoothing is off in every reference config')
         if hp.optimiser not in ops.OPTIMISERS:  # Adam, Nadam, AdamW, Momentum (seq2seq.py:195-219)
             raise Exception('Unsupported optimiser, try Adam')
         self._l2_names = [n for n in self.store.names() if 'lstm_' in n and 'bias' not in n]  # seq2seq.py:283-290
@@ -290,6 +288,7 @@ class Seq2SeqModel(object):
             lab_len_host = ll.cpu().numpy() if torch.is_tensor(ll) else np.asarray(ll)
             meta['T_dec'] = int(lab_len_host.max())
             meta['n_tokens'] = float(lab_len_host.sum())
+            meta['n_positions'] = float(len(lab_len_host) * int(lab_len_host.max()))
             src['labels'] = self._as_tensor(ref.labels, torch.int32)
             src['labels_len'] = self._as_tensor(ll, torch.int32)
         # data parallelism: the iterator reports the size of the GLOBAL batch this shard was cut from (payload
@@ -481,6 +480,8 @@ class Seq2SeqModel(object):
             # exact large-batch loss denominator (seq2seq.sequence_loss, seq2seq.py:165-171): the token count of the
             # GLOBAL batch, summed over ranks on the device inside the step (no host round trip, graph-capturable)
             tok = b['labels_len'].sum(dtype=torch.float32).reshape(1)
+            if self._hparams.label_smoothing > 0.0:  # the smoothed loss is the unmasked mean over all positions
+                tok = torch.full((1,), float(b['labels_len'].shape[0] * b['T_dec']), dtype=torch.float32, device=tok.device)
             self._ctx.allreduce(tok)
             torch.reciprocal(tok + 1e-12, out=self._scal_dev[0:1])
         self._loss_dev[5:6].copy_(self._scal_dev[0:1])
@@ -585,6 +586,10 @@ class Seq2SeqModel(object):
         # power-of-two operand scale of the backward kernels.
         n_tok = self._meta['n_tokens'] * ctx.world_size
         self._inv_denom = 1.0 / (n_tok + 1e-12)  # seq2seq.sequence_loss
+        if self._hparams.label_smoothing > 0.0:
+            # seq2seq.py:147-155: smoothed_cross_entropy (devel.py:54-61) returns a reduced scalar - the mean over ALL
+            # B x T positions, padding included - which sequence_loss multiplies by the weights and divides by their sum
+            self._inv_denom = 1.0 / (self._meta['n_positions'] * ctx.world_size)
         self._ctx.grad_scale = float(2 ** int(math.floor(math.log2(max(n_tok, 1.0)))))
         lr = self._lr_now()
         self.current_lr = lr

@@ -257,7 +257,8 @@ def gate_gemm_roofline(args, torch, ops, B):
         f = 2.0 * M * N * K
         flops += f
         ms += t
-        per.append({'shape': [int(ta), int(tb), M, N, K], 'ms': round(t, 4), 'tflops': round(f / t / 1e9, 2)})
+        per.append({'shape': [int(ta), int(tb), M, N, K], 'ms': round(t, 4), 'tflops': round(f / t / 1e9, 2),
+                    'bytes': 4.0 * (M * K + K * N + M * N)})
         del a, b, c
     # TF32 cuBLAS peak, measured the way MEASURED_PEAKS.json measures bf16 (denominator only, not on the path)
     n = 8192
@@ -277,11 +278,25 @@ def gate_gemm_roofline(args, torch, ops, B):
     tf32_peak = 2.0 * n ** 3 / best / 1e9
     peaks = load_peaks()
     achieved = flops / ms / 1e9
+    # every product against ITS roof: the K = 256 / 80 shapes are bound by writing the fp32 x-projection (the [T B, 4H]
+    # output is 4x the input), not by the tensor pipe - time at the roof = max(flop / tensor peak, bytes / HBM peak)
+    hbm = float(peaks.get('hbm_gbs', 6650.0))
+    roof_ms = 0.0
+    for e in per:
+        ta_, tb_, M_, N_, K_ = e['shape']
+        t_tensor = 2.0 * M_ * N_ * K_ / (tf32_peak * 1e9)
+        t_hbm = e.pop('bytes') / (hbm * 1e6)
+        e['bound'] = 'tensor' if t_tensor >= t_hbm else 'hbm'
+        e['frac_of_roof'] = round(max(t_tensor, t_hbm) / e['ms'], 3)
+        roof_ms += max(t_tensor, t_hbm)
     return {'bound': 'tensor', 'achieved': round(achieved, 2), 'peak': round(tf32_peak, 1), 'unit': 'TFLOP/s',
             'frac': round(achieved / tf32_peak, 4), 'traffic': None,
             'kernel': 'LSTM gate GEMMs (x@Wx, dZ@Wx^T, x^T@dZ of the six encoder layers), timed in isolation',
             'peak_source': 'TF32 torch.matmul 8192^3 measured in this run (operands are fp32/TF32, BASELINE.md '
                            'section 2); bf16 peak of MEASURED_PEAKS.json = %s' % peaks.get('bf16_tflops'),
+            'frac_of_roofline': round(roof_ms / ms, 4),
+            'frac_of_roofline_note': 'sum over the products of max(flop / TF32 peak, compulsory bytes / HBM peak) over the '
+                                     'measured time: 12 of the 18 products are HBM-bound (fp32 gate pre-activations out)',
             'gate_gemm_ms_per_step': round(ms, 3), 'per_shape': per}
 
 

@@ -248,9 +248,13 @@ int avsr_embedding_bwd(avsr_stream_t stream, const float* dout, const int* ids, 
 /* ---- seq2seq.sequence_loss with sequence_mask weights (seq2seq.py:142-171) ---
  * logits [T,B,V] (rows past labels_len are treated as zero logits, impute_finished);
  * labels [B,ldl] EOS-terminated.  loss_sum[0] += sum xent*w; dlogits = (softmax-onehot)*w*inv_denom.
- * inv_denom_dev / lr_t_dev are DEVICE scalars so a captured CUDA graph can be replayed with new values. */
+ * inv_denom_dev / lr_t_dev are DEVICE scalars so a captured CUDA graph can be replayed with new values.
+ * label_smoothing > 0 (seq2seq.py:147-155, devel.py:54-61): targets (1 - eps) onehot + eps / V and - as the reference's
+ * smoothed loss function hands sequence_loss a reduced scalar - the UNMASKED mean over all T*B positions: rows past the
+ * label length (imputed zero logits) add log V to loss_sum and get no gradient; the caller passes 1 / (T*B) as inv_denom. */
 int avsr_seq_loss(avsr_stream_t stream, const float* logits, int T, int B, int V, const int* labels, int ldl,
-                  const int* labels_len, const float* inv_denom_dev, float* loss_sum, float* dlogits);
+                  const int* labels_len, const float* inv_denom_dev, float label_smoothing, float* loss_sum,
+                  float* dlogits);
 
 /* ---- Action-Unit regression head of the video encoder (encoder.py:173-189, seq2seq.py:188-190) -------------------
  * z [T,B,2] = encoder outputs @ video/dense/kernel + bias (pre-sigmoid); aus [B,T,2] as the reader delivers them

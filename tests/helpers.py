@@ -52,7 +52,7 @@ def oracle_hparams(hp, model=None):
                     streams=model.random_streams)
     rand.update(regress_aus=bool(hp.regress_aus), au_loss_weight=hp.kwargs.get('au_loss_weight', 10.0),
                 input_dense_layers=tuple(hp.input_dense_layers), residual_encoder=bool(hp.residual_encoder),
-                encoder_weight_sharing=bool(hp.encoder_weight_sharing),
+                encoder_weight_sharing=bool(hp.encoder_weight_sharing), label_smoothing=float(hp.label_smoothing),
                 video_processing=hp.video_processing, cnn_filters=tuple(hp.kwargs.get('cnn_filters', (8, 16, 32, 64))))
     return OracleHParams(
         **rand,

@@ -39,6 +39,7 @@ CASES += [
     # ResidualWrapper on encoder layers > 0 and the shared cell of layers 2.. (cells.py:77-92)
     (3, dict(DROP, residual_encoder=True)), (4, dict(residual_encoder=True, encoder_weight_sharing=True)),
     (3, dict(encoder_weight_sharing=True)),
+    (1, dict(label_smoothing=0.1)), (5, dict(DROP, label_smoothing=0.2)),  # seq2seq.py:147-155
 ]
 
 
