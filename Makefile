@@ -1,4 +1,4 @@
-# Builds the C-ABI library (sm_100a only) and the oracle's C twin.
+# Builds the C-ABI library (sm_100a only) and the host-side record reader.
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr

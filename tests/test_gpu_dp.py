@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.helpers import config_hparams, synthetic_batch, to_data_sequences
+from tests.helpers import config_hparams, synthetic_batch, to_data_sequences, to_image_sequences
 
 pytestmark = pytest.mark.gpu
 
@@ -25,6 +25,15 @@ def _free_port():
 
 def _slice(batch, lo, hi):
     return {k: v[lo:hi] for k, v in batch.items()}
+
+
+def _batch(hp, n):
+    batch = synthetic_batch(hp, B=n, Ta=40, Tv=12, L=8, ragged=True)
+    if 'audio_len' in batch:
+        batch['audio_len'][:] = np.maximum(batch['audio_len'], 1)
+    if hp.video_processing == 'resnet_cnn':  # lip crops: the front-end's fused batch norms all-reduce their statistics
+        to_image_sequences(batch, hw=12)
+    return batch
 
 
 def _one_step(hp, ds, graph):
@@ -43,8 +52,7 @@ def _worker(rank, world, port, cfg, over, B, graph, ret):
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
         hp = config_hparams(cfg, **over)
-        batch = synthetic_batch(hp, B=world * B, Ta=40, Tv=12, L=8, ragged=True)
-        batch['audio_len'][:] = np.maximum(batch['audio_len'], 1)
+        batch = _batch(hp, world * B)
         ds = to_data_sequences(_slice(batch, rank * B, (rank + 1) * B))
         out, params, state = _one_step(hp, ds, graph)
         if rank == 0:
@@ -63,10 +71,11 @@ def _worker(rank, world, port, cfg, over, B, graph, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
-@pytest.mark.parametrize('cfg,graph', [(5, False), (5, True), (2, False)])
-def test_two_ranks_equal_one_rank_with_the_whole_batch(cfg, graph):
+@pytest.mark.parametrize('cfg,graph,over', [(5, False, {}), (5, True, {}), (2, False, {}), (4, False, {}),
+                                            (3, False, dict(video_processing='resnet_cnn'))])
+def test_two_ranks_equal_one_rank_with_the_whole_batch(cfg, graph, over):
     import torch.multiprocessing as mp
-    B, over = 6, {}
+    B = 6
     ctx = mp.get_context('spawn')
     ret = ctx.Queue()
     port = _free_port()
@@ -92,9 +101,7 @@ def test_two_ranks_equal_one_rank_with_the_whole_batch(cfg, graph):
             if p.is_alive():
                 p.kill()
     hp = config_hparams(cfg, **over)
-    batch = synthetic_batch(hp, B=2 * B, Ta=40, Tv=12, L=8, ragged=True)
-    batch['audio_len'][:] = np.maximum(batch['audio_len'], 1)
-    out1, params1, state1 = _one_step(hp, to_data_sequences(batch), False)
+    out1, params1, state1 = _one_step(hp, to_data_sequences(_batch(hp, 2 * B)), False)
     for (l2, g2), (l1, g1) in zip(out2, out1):
         assert abs(l2 - l1) <= 2e-4 * abs(l1), (l2, l1)          # same loss of the same global batch
         assert abs(g2 - g1) <= 2e-3 * g1, (g2, g1)                # same global norm (clip acts on it)
