@@ -392,6 +392,41 @@ def attention_roofline(args, B, graph, ms, n, gate):
     return roof, tensor
 
 
+# attention layers of every BASELINE configuration: (query steps, [(memory rows, memory depth)], units)
+ATT_LAYERS = {
+    1: [(41, [(300, 128)], 128)],                       # LAS 1x128: decoder over the audio memory
+    2: [(41, [(300, 512)], 256)],                       # BiLSTM memory (2 x 256)
+    3: [(41, [(75, 256)], 256)],
+    4: [(41, [(75, 256), (300, 256)], 256)],            # WLAS: video + audio mechanisms
+    5: [(300, [(75, 256)], 256), (41, [(300, 256)], 256)],
+}
+
+
+def config_roofline(cfg, B, kms, kn):
+    """The roofline object of SURVEY.md 8d-2 for one configuration's attention layers (same definition as the headline's):
+    algorithmic bytes = 4 Tm (A + Dm) + 4 (Tm + Dm + A) per (utterance, query step, mechanism), both directions, over the
+    persistent attention-LSTM kernels' measured time."""
+    peaks = load_peaks()
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    t_att = kms['attn_lstm_fwd'] + kms['attn_lstm_bwd']
+    if t_att <= 0:
+        return {'bound': 'hbm', 'achieved': None, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': None, 'traffic': None,
+                'note': 'no persistent attention kernel ran: this shape (H = 128) takes the per-step launch path'}
+    by, once, steps = 0.0, 0.0, 0
+    for T, mems, A in ATT_LAYERS[cfg]:
+        steps += T
+        for Tm, Dm in mems:
+            by += B * T * (4.0 * Tm * (A + Dm) + 4.0 * (Tm + Dm + A))
+            once += B * 4.0 * Tm * (A + Dm)
+    ach = 2.0 * by / (t_att * 1e-3) / 1e9
+    return {'bound': 'hbm', 'achieved': round(ach, 1), 'peak': hbm_peak, 'unit': 'GB/s', 'frac': round(ach / hbm_peak, 4),
+            'traffic': None, 'frac_once_per_utterance': round(2.0 * once / (t_att * 1e-3) / 1e9 / hbm_peak, 5),
+            'us_per_recurrent_step': {'fwd': round(kms['attn_lstm_fwd'] * 1e3 / steps, 3),
+                                      'bwd': round(kms['attn_lstm_bwd'] * 1e3 / steps, 3)},
+            'launches_per_step': kn['attn_lstm_fwd'] + kn['attn_lstm_bwd'],
+            'note': 'L2-fed figure against the HBM peak, as the headline roofline: the fp16 memories stay in the 126 MB L2'}
+
+
 # ------------------------------------------------------------------------------------
 # one configuration, device-resident: inputs already in HBM, K graph replays between CUDA events
 # ------------------------------------------------------------------------------------
@@ -441,7 +476,8 @@ def side_config(args, torch, ops, cfg, graph, steps):
            'workload': CONFIGS[cfg]['what'], 'graph': graph,
            'kernel_ms_per_step': {k: round(v, 4) for k, v in kms.items()},
            'kernel_launches_per_step': kn,
-           'persistent_kernel_share': round(persistent / ms, 3) if ms > 0 else None}
+           'persistent_kernel_share': round(persistent / ms, 3) if ms > 0 else None,
+           'roofline': config_roofline(cfg, B, kms, kn)}
     del model
     torch.cuda.empty_cache()
     return out
@@ -748,8 +784,12 @@ def main():
     if other is not None:
         line['strong_scaling' if args.scaling == 'weak' else 'weak_scaling'] = other
     try:
-        if args.skip_roofline or world > 1 or cfg != 5:
+        if args.skip_roofline or world > 1:
             line['roofline'] = None
+        elif cfg != 5:  # --config 1..4 as the headline: the same object as in the `configs` side key of the default run
+            kms, kn = kernel_class_times(torch, ops, model)
+            line['roofline'] = config_roofline(cfg, B, kms, kn)
+            line['kernel_ms_per_step'] = {k: round(v, 4) for k, v in kms.items()}
         else:
             gate = gate_gemm_roofline(args, torch, ops, B)
             kms, kn = kernel_class_times(torch, ops, model)
