@@ -105,10 +105,20 @@ def test_two_ranks_equal_one_rank_with_the_whole_batch(cfg, graph, over):
     for (l2, g2), (l1, g1) in zip(out2, out1):
         assert abs(l2 - l1) <= 2e-4 * abs(l1), (l2, l1)          # same loss of the same global batch
         assert abs(g2 - g1) <= 2e-3 * g1, (g2, g1)                # same global norm (clip acts on it)
-    for k, v in state1.items():                                   # batch-norm moving statistics
-        assert np.allclose(state2[k], v, rtol=1e-4, atol=1e-6), k
+    # batch-norm moving statistics.  Behind the front-end the features reach the input normalisation through 13 tf32
+    # convolutions whose fp32 statistics are summed by atomics in a different order on 2 x 6 and on 12 utterances
+    cnn = over.get('video_processing') == 'resnet_cnn'
+    for k, v in state1.items():
+        assert np.allclose(state2[k], v, rtol=1e-3 if cnn else 1e-4, atol=2e-5 if cnn else 1e-6), \
+            (k, float(np.abs(state2[k] - v).max()), float(np.abs(v).max()))
     lr_sum = sum(hp.learning_rate * (s + 1) / 750.0 for s in range(2))
     for k, v in params1.items():                                  # Adam's first steps are sign-like: see test_gpu_model
+        if k.endswith(('moving_mean', 'moving_variance')):        # not trained: the moving statistics of the front-end
+            assert np.allclose(params2[k], v, rtol=1e-3 if cnn else 1e-4, atol=2e-5 if cnn else 1e-6), \
+                (k, float(np.abs(params2[k] - v).max()), float(np.abs(v).max()))
+            continue
         diff = np.abs(params2[k] - v)
         assert diff.max() <= 2.2 * lr_sum + 1e-6 * np.abs(v).max() + 1e-7, (k, diff.max())
-        assert (diff > 0.05 * lr_sum + 1e-6 * np.abs(v).max()).mean() < 3e-2, k
+        # (a sign-like first Adam step flips where a gradient entry is rounding noise: a few percent of a large tensor, one
+        # or two entries of a 16-entry batch-norm gamma)
+        assert (diff > 0.05 * lr_sum + 1e-6 * np.abs(v).max()).mean() < max(3e-2, 2.5 / diff.size), k
