@@ -101,7 +101,8 @@ def test_loss_states_contexts_and_gradients(cfg, over, tensor_cores):
         err = np.abs(got - g_ref).max() / scale
         l2 = np.linalg.norm(got - g_ref) / max(np.linalg.norm(g_ref), 1e-30)
         tol = gtol
-        if tensor_cores and ('/Encoder/dense' in name or name.endswith('attention_g')):
+        under_dense = 'input_dense_layers' in over and ('/Encoder/dense' in name or '/batch_normalization/' in name)
+        if tensor_cores and (under_dense or name.endswith('attention_g')):
             # what sits UNDER the first recurrent layer inherits the noise of the gradient wrt that layer's input (dZ Wx^T sums
             # 1024 gate columns that largely cancel: a few percent in tensor-core mode on these 4-utterance batches), and
             # attention_g is one scalar formed by a cancelling sum whose size is at the 1e-3 floor of `scale`: the tensor as
