@@ -192,8 +192,8 @@ class Seq2SeqEncoder(object):
     def _layer0_drops_input(self):
         """True when the gradient wrt the normalised features has to be formed explicitly (dgamma / dbeta cannot be read
         off the layer-0 weight gradient): layer 0 drops its input, or a dense stack sits between the two."""
-        if self._mode == 'train' and self._dense is not None:
-            return True
+        if self._mode == 'train' and (self._dense is not None or getattr(self, 'explicit_bn_backward', False)):
+            return True  # (explicit_bn_backward: set by Seq2SeqModel._guard_bn_shortcut when a gamma came close to zero)
         return self._mode == 'train' and any(op.drop is not None and op.drop.thr_in for op in self._layer0_ops())
 
     def _round_outputs(self, out, op):

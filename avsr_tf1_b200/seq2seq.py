@@ -675,6 +675,8 @@ class Seq2SeqModel(object):
         elif self._pending is not None:
             self._consume_prefetch()
         self._set_step_scalars()
+        if self._global_step % self.BN_GAMMA_CHECK_EVERY == 0:
+            self._guard_bn_shortcut()
         if self.use_cuda_graph:
             key = self._meta['key']
             g, n = self._graphs.get(key) or self._capture(key)
@@ -688,6 +690,27 @@ class Seq2SeqModel(object):
         if fetch:
             return self.fetch_scalars()
         return None
+
+    BN_GAMMA_CHECK_EVERY = 64
+    BN_GAMMA_FLOOR = 0.05
+
+    def _guard_bn_shortcut(self):
+        """The input normalisation's dgamma is read off the layer-0 weight gradient divided by gamma (avsr_bn_input_grads)
+        when nothing sits between the two.  A gamma that training has driven towards zero amplifies the tf32 rounding of
+        that weight gradient into a spurious dgamma (and through the global norm into every clipped gradient), so every
+        BN_GAMMA_CHECK_EVERY steps the smallest |gamma| is read back (one 4-byte D2H copy) and an encoder that fell under
+        the floor switches - for good - to the explicit path (gradient wrt the normalised features, stored xhat).  The
+        captured graphs are dropped so that the new path is what replays."""
+        changed = False
+        for enc in (self._video_encoder, self._audio_encoder):
+            bn = getattr(enc, '_bn', None) if enc is not None else None
+            if bn is None or getattr(enc, 'explicit_bn_backward', False) or enc._layer0_drops_input():
+                continue
+            if float(self.store.p(bn.gamma).abs().min().item()) < self.BN_GAMMA_FLOOR:
+                enc.explicit_bn_backward = True
+                changed = True
+        if changed:
+            self._graphs.clear()
 
     def train_op(self):
         return self.train_step()

@@ -95,3 +95,39 @@ def test_decoding_stops_at_max_label_length():
         ids = model.predict(ds)
         assert ids.shape == (3, 12), ids.shape
         assert (ids != 29).all()
+
+
+def test_small_input_bn_gamma_switches_to_the_explicit_gradient_path():
+    """dgamma of the input normalisation is normally read off the layer-0 weight gradient DIVIDED by gamma
+    (avsr_bn_input_grads); a gamma near zero would amplify the tf32 rounding of that gradient.  Seq2SeqModel checks the
+    smallest |gamma| every BN_GAMMA_CHECK_EVERY steps and moves the encoder to the explicit path; the gradient of the tiny
+    gamma must then agree with the oracle like every other entry."""
+    import torch
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    hp = config_hparams(5)
+    batch = synthetic_batch(hp, B=4, Ta=30, Tv=10, L=6, ragged=True)
+    ds = to_data_sequences(batch)
+    model = Seq2SeqModel(ds, 'train', hp, seed=2001)
+    g = model.store.p('audio/batch_normalization/gamma')
+    g[3] = 1e-6
+    g[7] = -2e-3
+    model.store.sync_tf32()
+    assert not getattr(model._audio_encoder, 'explicit_bn_backward', False)
+    model.feed(ds)
+    model._set_step_scalars()
+    model._guard_bn_shortcut()
+    assert model._audio_encoder.explicit_bn_backward and not getattr(model._video_encoder, 'explicit_bn_backward', False)
+    P = {k: v.astype(np.float64) for k, v in model.store.to_numpy('p').items()}
+    loss_ref, G_ref, _ = O.OracleModel(oracle_hparams(hp), P).loss_and_grads(cast_batch(batch, np.float64))
+    model.forward_backward()
+    model.finish_gradients()
+    loss, gnorm = model.fetch_scalars()
+    check(loss, gnorm, loss_ref, G_ref)
+    got = model.store.to_numpy('g')['audio/batch_normalization/gamma'].astype(np.float64)
+    ref = G_ref['audio/batch_normalization/gamma']
+    assert np.abs(got - ref).max() <= 2e-2 * np.abs(ref).max(), (got[[3, 7]], ref[[3, 7]])
+    # and training goes on (graphs are re-captured on the new path)
+    model.use_cuda_graph = True
+    for _ in range(3):
+        l, _ = model.train_step(ds)
+        assert np.isfinite(l)
