@@ -328,24 +328,6 @@ def test_attention_rnn_fwd_bwd(kinds, B, T, Dx, H, Tms, Dms, tensor_cores):
     _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, tensor_cores)
 
 
-@pytest.mark.parametrize('kinds,B,T,Dx,H,Tms,Dms,slice_width', [
-    (('scaled_luong',), 40, 9, 128, 256, (75,), (256,), 32),   # two clusters, the second one a quarter full
-    (('luong',), 33, 12, 256, 256, (300,), (256,), 32),
-    (('scaled_luong',), 20, 9, 128, 256, (75,), (256,), 16),
-])
-def test_attention_rnn_cluster8(kinds, B, T, Dx, H, Tms, Dms, slice_width, monkeypatch):
-    """The cluster-of-8 persistent attention-LSTM kernels (attn_persist.cu; the default is the cluster-of-4 pair of
-    attn_persist4.cu), in both slice widths: 16 utterances per cluster and the 32-utterance, 16-warp variant."""
-    monkeypatch.setenv('AVSR_AP_CLUSTER', '8')
-    monkeypatch.setenv('AVSR_AP_SLICE', str(slice_width))
-    ops = ops_mod()
-    old = ops.set_tensor_cores(True)
-    try:
-        _run_attention_rnn(kinds, B, T, Dx, H, Tms, Dms, True)
-    finally:
-        ops.set_tensor_cores(old)
-
-
 class _Drop:
     """What ops.RnnSeq reads of a layers.DropState."""
 
