@@ -35,6 +35,8 @@ def run_once(hp, ds, tc, seed=2001, step_word=7):
         loss, gnorm = model.fetch_scalars()
         probes = {}
         for key, enc in (('video', model._video_encoder), ('audio', model._audio_encoder)):
+            if enc is None:
+                continue
             d = enc.get_data()
             probes[key + '/outputs'] = d.outputs.clone()
             probes[key + '/final_c'] = d.final_state[0].clone()
@@ -43,12 +45,14 @@ def run_once(hp, ds, tc, seed=2001, step_word=7):
         # the per-step kernels compute it; nothing reads them): compare the valid steps
         def valid(lens, T):
             return (torch.arange(T, device='cuda')[:, None] < lens.cuda()[None, :]).float()[:, :, None]
-        Ha = model._audio_encoder._num_units_per_layer[-1]
-        ctx_a = model._audio_encoder.attention_contexts[:, :, Ha:]
-        probes['audio/xmodal_contexts'] = ctx_a * valid(model._in['audio_len'], ctx_a.shape[0])
+        if hasattr(model._audio_encoder, 'attention_contexts'):  # AV-Align
+            Ha = model._audio_encoder._num_units_per_layer[-1]
+            ctx_a = model._audio_encoder.attention_contexts[:, :, Ha:]
+            probes['audio/xmodal_contexts'] = ctx_a * valid(model._in['audio_len'], ctx_a.shape[0])
         H = model._decoder._H
-        ctx_d = model._decoder._cell.bufs[0].hc[:, :, H:]
-        probes['decoder/contexts'] = ctx_d * valid(model._in['labels_len'], ctx_d.shape[0])
+        for k, mb in enumerate(model._decoder._cell.bufs):  # (two mechanisms for the WLAS decoder)
+            ctx_d = mb.hc[:, :, H:]
+            probes['decoder/contexts' + ('_%d' % k if k else '')] = ctx_d * valid(model._in['labels_len'], ctx_d.shape[0])
         probes['decoder/logits'] = model._decoder._logits.clone()
         grads = {k: torch.from_numpy(v) for k, v in model.store.to_numpy('g').items()}
         launches = None
@@ -72,6 +76,29 @@ def test_bench_shape_tensor_core_mode_tracks_exact_fp32(graph):
     for k in px:
         worst[k] = scaled_err(pt[k], px[k])
     print('bench-shape scaled errors (tensor-core vs exact fp32):', {k: '%.2e' % v for k, v in worst.items()})
+    for k, v in worst.items():
+        assert v <= 1e-3, f'{k}: scaled error {v:.3e}'
+    assert abs(gn_t - gn_x) <= 5e-3 * gn_x, (gn_t, gn_x)
+    gmax = max(float(g.abs().max()) for g in gx.values())
+    for k in gx:
+        scale = max(float(gx[k].abs().max()), 1e-3 * gmax)
+        err = float((gt[k].double() - gx[k].double()).abs().max()) / scale
+        assert err <= 1.5e-2, f'{k}: gradient scaled error {err:.3e}'
+
+
+@pytest.mark.parametrize('cfg,B', [(4, 128), (2, 64)])
+def test_bench_shapes_of_the_other_configurations(cfg, B):
+    """BASELINE configs 4 (WLAS: the dual-attention cluster-of-8 kernels, 8 clusters x 16 utterances) and 2 (BiLSTM +
+    Bahdanau: the two-product Bahdanau kernels over a 512-deep memory) at the batch and lengths bench.py times, reference
+    default graph (every DropoutWrapper on): tensor-core mode against the exact-fp32 mode, same bars as above."""
+    hp = config_hparams(cfg, use_dropout=True)
+    batch = synthetic_batch(hp, B=B, Ta=300, Tv=75, Fa=80, Fv=128, L=40, ragged=False)
+    ds = to_data_sequences(batch)
+    loss_x, gn_x, px, gx, _ = run_once(hp, ds, tc=False)
+    loss_t, gn_t, pt, gt, _ = run_once(hp, ds, tc=True)
+    assert abs(loss_t - loss_x) <= 1e-3 * abs(loss_x), (loss_t, loss_x)
+    worst = {k: scaled_err(pt[k], px[k]) for k in px}
+    print('config %d bench-shape scaled errors (tensor-core vs exact fp32):' % cfg, {k: '%.2e' % v for k, v in worst.items()})
     for k, v in worst.items():
         assert v <= 1e-3, f'{k}: scaled error {v:.3e}'
     assert abs(gn_t - gn_x) <= 5e-3 * gn_x, (gn_t, gn_x)
