@@ -30,9 +30,19 @@ constexpr int H = 256;
 constexpr int DM = 256;
 constexpr int MAX_TM = 384;
 
-__global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+// fp16 copy of a memory (keys / values / projected values): 8 elements per thread (two 16-byte loads, one 16-byte store);
+// every caller's count is a multiple of 256 (rows of H or DM floats, 16-byte aligned work buffers)
+__global__ void to_half_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n8) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = __float2half_rn(src[i]);
+  if (i >= n8) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+  const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+  const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+  uint4 o;
+  o.x = *reinterpret_cast<const uint32_t*>(&h0); o.y = *reinterpret_cast<const uint32_t*>(&h1);
+  o.z = *reinterpret_cast<const uint32_t*>(&h2); o.w = *reinterpret_cast<const uint32_t*>(&h3);
+  reinterpret_cast<uint4*>(dst)[i] = o;
 }
 
 // all steps at once: rows = T*Bt, step of a row = row / Bt
@@ -123,8 +133,8 @@ static int bahdanau_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scr
   AVSR_TRY(gemm(st, 0, 0, m.Tm * B, At, m.Dm, m.values_op ? m.values_op : m.values, m.Dm, m.Wl + (size_t)H * At, At, pv, At,
                 0.0f, nullptr));
   const long long nk = (long long)m.Tm * B * H;
-  AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
-  AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, pv, pv_h, nk);
+  AVSR_LAUNCH(to_half_kernel, cdiv(nk / 8, 256), 256, 0, st, m.keys, keys_h, nk / 8);
+  AVSR_LAUNCH(to_half_kernel, cdiv(nk / 8, 256), 256, 0, st, pv, pv_h, nk / 8);
   AVSR_TRY(attn_persist4d_launch_fwd(st, r, keys_h, pv_h));
   // the true contexts of every step (parity probe; operand of the attention-layer weight gradient)
   return attn_context_all(st, T, B, m.Tm, m.Dm, r->len, m.mem_len, m.align, m.values, m.hc + H, HD);
@@ -153,8 +163,8 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
     // DropoutWrapper on (or scheduled sampling inside the recurrence): no fused matrix; the kernel forms the attention vectors itself and writes `out` (attention
     // vectors, zero past the length) and the state rows [a (.) m_in | hs]
     const long long nk = (long long)m.Tm * B * H, nv = (long long)m.Tm * B * DM;
-    AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
-    AVSR_LAUNCH(to_half_kernel, cdiv(nv, 256), 256, 0, st, m.values, values_h, nv);
+    AVSR_LAUNCH(to_half_kernel, cdiv(nk / 8, 256), 256, 0, st, m.keys, keys_h, nk / 8);
+    AVSR_LAUNCH(to_half_kernel, cdiv(nv / 8, 256), 256, 0, st, m.values, values_h, nv / 8);
     return attn_persist4d_launch_fwd(st, r, keys_h, values_h);
   }
   // fused recurrent matrix W' = [Wh + Wl_h Wa ; Wl_c Wa]
@@ -164,8 +174,8 @@ int attn_persist_fwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch) {
   AVSR_TRY(gemm(st, 0, 0, DM, 4 * H, At, m.Wl + (size_t)H * m.A, m.A, r->Wrec, 4 * H, Wp + (size_t)H * 4 * H, 4 * H, 0.0f,
                 nullptr));
   const long long nk = (long long)m.Tm * B * H, nv = (long long)m.Tm * B * DM;
-  AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
-  AVSR_LAUNCH(to_half_kernel, cdiv(nv, 256), 256, 0, st, m.values, values_h, nv);
+  AVSR_LAUNCH(to_half_kernel, cdiv(nk / 8, 256), 256, 0, st, m.keys, keys_h, nk / 8);
+  AVSR_LAUNCH(to_half_kernel, cdiv(nv / 8, 256), 256, 0, st, m.values, values_h, nv / 8);
   AVSR_TRY(attn_persist4_launch_fwd(st, T, B, m.Tm, m.kind == AVSR_ATTN_SCALED_LUONG, r->len, m.mem_len, r->gates, Wp, keys_h,
                                     values_h, m.g, r->c0, r->S, SW, At, r->craw, r->out, m.hc, m.align, r->cT, r->hT));
   // attention vectors of all steps in one product: S[1:, :, :At] = [h | ctx] Wl (tf32-rounded operand rows)
@@ -201,8 +211,8 @@ static int bahdanau_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scr
   AVSR_TRY(gemm(st, 0, 0, m.Tm * B, At, m.Dm, m.values_op ? m.values_op : m.values, m.Dm, m.Wl + (size_t)H * At, At, pv, At,
                 0.0f, nullptr));
   const long long nk = (long long)m.Tm * B * H;
-  AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
-  AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, pv, pv_h, nk);
+  AVSR_LAUNCH(to_half_kernel, cdiv(nk / 8, 256), 256, 0, st, m.keys, keys_h, nk / 8);
+  AVSR_LAUNCH(to_half_kernel, cdiv(nk / 8, 256), 256, 0, st, pv, pv_h, nk / 8);
   // rows of finished steps stay zero: dWq sums over all of them
   AVSR_CHECK_CUDA(cudaMemsetAsync(m.dpq, 0, (size_t)T * B * At * sizeof(float), st));
   AVSR_TRY(attn_persist4d_launch_bahd_bwd(st, r, keys_h, pv_h));
@@ -256,8 +266,8 @@ static int wlas_prepare(cudaStream_t st, const AvsrRnnSeq* r, float* scratch, Wl
     // PV_k = values_k Wl_c,k: the context half of the attention layer, once per batch
     AVSR_TRY(gemm(st, 0, 0, m.Tm * B, H, m.Dm, m.values_op ? m.values_op : m.values, m.Dm, m.Wl + (size_t)H * H, H, pv, H, 0.0f,
                   nullptr));
-    AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
-    AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, pv, pv_h, nk);
+    AVSR_LAUNCH(to_half_kernel, cdiv(nk / 8, 256), 256, 0, st, m.keys, keys_h, nk / 8);
+    AVSR_LAUNCH(to_half_kernel, cdiv(nk / 8, 256), 256, 0, st, pv, pv_h, nk / 8);
     ws->keys_h[k] = keys_h;
     ws->pv_h[k] = pv_h;
   }
@@ -330,8 +340,8 @@ int attn_persist_bwd(cudaStream_t st, const AvsrRnnSeq* r, float* scratch, bool 
     // backward does not depend on which forward path ran (a ranged step-wise forward leaves the same activations)
     AVSR_REQUIRE(r->dA != nullptr, "rnn bwd: dA scratch missing");
     const long long nk = (long long)m.Tm * B * H, nv = (long long)m.Tm * B * DM;
-    AVSR_LAUNCH(to_half_kernel, cdiv(nk, 256), 256, 0, st, m.keys, keys_h, nk);
-    AVSR_LAUNCH(to_half_kernel, cdiv(nv, 256), 256, 0, st, m.values, values_h, nv);
+    AVSR_LAUNCH(to_half_kernel, cdiv(nk / 8, 256), 256, 0, st, m.keys, keys_h, nk / 8);
+    AVSR_LAUNCH(to_half_kernel, cdiv(nv / 8, 256), 256, 0, st, m.values, values_h, nv / 8);
     AVSR_CHECK_CUDA(cudaMemsetAsync(m.dhc, 0, (size_t)T * B * HD * sizeof(float), st));
     AVSR_TRY(attn_persist4d_launch_bwd(st, r, keys_h, values_h));
     if (r->dh0)  // dh_0 += dz_0 Wh^T (the kernel stops before the product of step 0)

@@ -640,6 +640,23 @@ __global__ void dropout_kernel(const float* __restrict__ x, long long n, long lo
   }
 }
 
+// four elements per thread (16-byte accesses): n, first and both pointers are multiples of 4 elements
+__global__ void dropout_v4_kernel(const float4* __restrict__ x, long long n4, long long first,
+                                  const uint32_t* __restrict__ rng, uint32_t stream_id, uint32_t thr, float inv_keep,
+                                  int rnd, float4* __restrict__ y) {
+  const uint32_t seed = rng[0], step = rng[1];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    const uint32_t lo = (uint32_t)(first + 4 * i);
+    float4 o;
+    o.x = maybe_tf32(v.x * (avsr_rand_u32(seed, step, stream_id, 0u, lo) < thr ? inv_keep : 0.0f), rnd);
+    o.y = maybe_tf32(v.y * (avsr_rand_u32(seed, step, stream_id, 0u, lo + 1u) < thr ? inv_keep : 0.0f), rnd);
+    o.z = maybe_tf32(v.z * (avsr_rand_u32(seed, step, stream_id, 0u, lo + 2u) < thr ? inv_keep : 0.0f), rnd);
+    o.w = maybe_tf32(v.w * (avsr_rand_u32(seed, step, stream_id, 0u, lo + 3u) < thr ? inv_keep : 0.0f), rnd);
+    y[i] = o;
+  }
+}
+
 // one thread per row: V is the output alphabet (31)
 __global__ void sched_sample_kernel(const float* __restrict__ logits, int B, int V, const uint32_t* __restrict__ rng,
                                     uint32_t stream_id, int t, uint32_t thr_p, const int* __restrict__ true_next,
@@ -965,6 +982,13 @@ int avsr_dropout(avsr_stream_t s, const float* x, long long n, long long first, 
   AVSR_REQUIRE(rng != nullptr && thr != 0u, "dropout: needs the rng words and a non-zero keep threshold");
   AVSR_REQUIRE(n >= 0 && first >= 0 && first + n <= (1ll << 32), "dropout: element indices must stay below 2^32");
   if (n == 0) return 0;
+  if (((n | first) & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    int grid4 = cdiv(n / 4, 256);
+    if (grid4 > 148 * 8) grid4 = 148 * 8;
+    AVSR_LAUNCH(dropout_v4_kernel, grid4, 256, 0, ST(s), reinterpret_cast<const float4*>(x), n / 4, first, rng, stream_id,
+                thr, inv_keep_of(thr), round_out && tensor_cores_enabled(), reinterpret_cast<float4*>(y));
+    return 0;
+  }
   int grid = cdiv(n, 256);
   if (grid > 148 * 16) grid = 148 * 16;
   AVSR_LAUNCH(dropout_kernel, grid, 256, 0, ST(s), x, n, first, rng, stream_id, thr, inv_keep_of(thr),

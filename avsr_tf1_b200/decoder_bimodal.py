@@ -12,22 +12,32 @@ class Seq2SeqBimodalDecoder(Seq2SeqUnimodalDecoder):
     LENGTH_PENALTY = 0.5  # decoder_bimodal.py:366
 
     def __init__(self, video_depth, audio_depth, video_state_depth, audio_state_depth, mode, hparams, ctx=None):
+        """video_depth / audio_depth None: that stream is missing (decoder_bimodal.py:127-142) - its state is a zero
+        tuple of width *_state_depth in the shared projection and it gets no attention mechanism (:179-225)."""
         self._state_depths = (int(video_state_depth), int(audio_state_depth))
-        super(Seq2SeqBimodalDecoder, self).__init__([video_depth, audio_depth], mode, hparams, ctx=ctx)
+        self._present = tuple(k for k, d in enumerate((video_depth, audio_depth)) if d is not None)
+        if not self._present:
+            raise Exception('labels are None')
+        depths = [d for d in (video_depth, audio_depth) if d is not None]
+        super(Seq2SeqBimodalDecoder, self).__init__(depths, mode, hparams, ctx=ctx)
 
     def _attention_types(self):
         at = self._hparams.attention_type
         # decoder_bimodal.py:196-223: video mechanisms use attention_type[0], audio attention_type[1]
-        return [at[0][0], at[1][0]]
+        return [at[k][0] for k in self._present]
 
     def _mem_layer_names(self):
-        return ['Decoder/memory_layer/kernel', 'Decoder/memory_layer_1/kernel']
+        return ['Decoder/memory_layer/kernel', 'Decoder/memory_layer_1/kernel'][:len(self._present)]
 
     def _extra_decls(self):
         self._Wp = self._ctx.declare('Decoder/state_projection/kernel', (sum(self._state_depths), self._H), 'glorot')
 
     def _initial_state_fwd(self, encoder_states):
         ctx = self._ctx
+        if len(self._present) == 1:  # zero state for the missing stream
+            (c1, h1), = encoder_states
+            z = ops.zeros(c1.shape[0], self._state_depths[1 - self._present[0]])
+            encoder_states = [(c1, h1), (z, z)] if self._present[0] == 0 else [(z, z), (c1, h1)]
         (cv, hv), (ca, ha) = encoder_states
         B, Hv = cv.shape
         Ha = ca.shape[1]
@@ -49,5 +59,6 @@ class Seq2SeqBimodalDecoder(Seq2SeqUnimodalDecoder):
         dcc, dch = ops.empty(B, Hv + Ha), ops.empty(B, Hv + Ha)
         ops.gemm(dc0, ctx.w(self._Wp), dcc, tb=True)
         ops.gemm(dh0, ctx.w(self._Wp), dch, tb=True)
-        return [(dcc[:, :Hv].contiguous(), dch[:, :Hv].contiguous()),
+        both = [(dcc[:, :Hv].contiguous(), dch[:, :Hv].contiguous()),
                 (dcc[:, Hv:].contiguous(), dch[:, Hv:].contiguous())]
+        return [both[k] for k in self._present]

@@ -221,7 +221,19 @@ class Seq2SeqModel(object):
             self._decoder = Seq2SeqUnimodalDecoder([enc.output_dim], mode=self._mode, hparams=hp, ctx=ctx)
         elif hp.architecture == 'bimodal':
             if self._video_encoder is None or self._audio_encoder is None:
-                raise NotImplementedError('bimodal decoder with a missing modality (decoder_bimodal.py:127-142)')
+                # one stream only (decoder_bimodal.py:127-142, 179-225): the missing stream enters the shared state
+                # projection as a zero state shaped like the FIRST layer's state of the present encoder
+                # (`final_state[0].c`) and gets no attention mechanism
+                key = 'audio' if self._video_encoder is None else 'video'
+                enc = self._audio_encoder if key == 'audio' else self._video_encoder
+                zero_depth = enc._num_units_per_layer[0]
+                if hp.encoder_type == 'bidirectional':
+                    zero_depth = self._state_depth(enc)
+                depths = (self._state_depth(enc), zero_depth) if key == 'video' else (zero_depth, self._state_depth(enc))
+                self._decoder = Seq2SeqBimodalDecoder(
+                    enc.output_dim if key == 'video' else None, enc.output_dim if key == 'audio' else None,
+                    depths[0], depths[1], mode=self._mode, hparams=hp, ctx=ctx)
+                return
             self._decoder = Seq2SeqBimodalDecoder(
                 self._video_encoder.output_dim, self._audio_encoder.output_dim,
                 self._state_depth(self._video_encoder), self._state_depth(self._audio_encoder), mode=self._mode,
@@ -452,7 +464,7 @@ class Seq2SeqModel(object):
         return enc
 
     def _decoder_inputs(self, b, enc):
-        if self._hparams.architecture == 'bimodal':
+        if self._hparams.architecture == 'bimodal' and len(enc) == 2:
             mems = [(enc['video'].outputs, b['video_len'], enc['video'].outputs_operand),
                     (enc['audio'].outputs, b['audio_len'], enc['audio'].outputs_operand)]
             states = [enc['video'].final_state, enc['audio'].final_state]
@@ -496,7 +508,7 @@ class Seq2SeqModel(object):
             dvid_au = self._video_encoder.au_loss_backward(None)
         both = self._video_encoder is not None and self._audio_encoder is not None
         overlap = both and (self.overlap_streams or self._ctx.parallel_chains)
-        if self._hparams.architecture == 'bimodal':
+        if self._hparams.architecture == 'bimodal' and both:
             if overlap:
                 with torch.cuda.stream(self._fork()):
                     self._video_backward(self._plus(dmem[0], dvid_au), dstates[0])

@@ -156,6 +156,33 @@ def run_oracle(args, cfg, graph, steps, warmup, sample):
     return dict(value=sample / t, sec_per_step=t, cores=threads, sample=sample, loss=float(loss))
 
 
+def train_flop_per_utterance(cfg, Fv):
+    """2 M N K of every matrix product of one forward pass per utterance (gate products, memory layers, attention
+    layers, score / context sweeps, output layer), times 3 for training."""
+    H = 128 if cfg == 1 else 256
+    Ta, Tv, L, E, V = 300, 75, 41, 128, 31
+    f = 0.0
+    def lstm(T, I, n=1):
+        return n * T * 2.0 * (I + H) * 4 * H
+    def attn(Tq, mems, x):  # AttentionWrapper layer: cell over [x, attention, h]; per memory: memory layer, scores + contexts, attention layer
+        f = Tq * 2.0 * (x + len(mems) * H + H) * 4 * H
+        for Tm, Dm in mems:
+            f += Tm * 2.0 * Dm * H + Tq * (2.0 * Tm * H + 2.0 * Tm * Dm) + Tq * 2.0 * (H + Dm) * H
+        return f
+    if cfg == 1:
+        f = lstm(Ta, 80) + attn(L, [(Ta, H)], E)
+    elif cfg == 2:
+        f = 2 * (lstm(Ta, 80) + lstm(Ta, H, 2)) + attn(L, [(Ta, 2 * H)], E)
+    elif cfg == 3:
+        f = lstm(Tv, Fv) + lstm(Tv, H, 2) + attn(L, [(Tv, H)], E)
+    elif cfg == 4:
+        f = lstm(Tv, Fv) + lstm(Tv, H, 2) + lstm(Ta, 80) + lstm(Ta, H, 2) + attn(L, [(Tv, H), (Ta, H)], E)
+    else:
+        f = lstm(Tv, Fv) + lstm(Tv, H, 2) + lstm(Ta, 80) + lstm(Ta, H) + attn(Ta, [(Tv, H)], H) + attn(L, [(Ta, H)], E)
+    f += L * 2.0 * H * V
+    return 3.0 * f
+
+
 def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -176,6 +203,9 @@ def reference_arm(args):
                                    f'to {r["cores"]} threads'},
         'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
+    fl = train_flop_per_utterance(cfg, 3888 if args.video_input == 'crops3888' else 128)
+    line['cpu_baseline']['gflops'] = round(r['value'] * fl / 1e9, 1)
+    line['cpu_baseline']['gflop_per_utterance'] = round(fl / 1e9, 2)
     print(json.dumps(line), flush=True)
 
 
@@ -829,6 +859,19 @@ def main():
             'value': round(r['value'], 3), 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
             'sample': f'{r["sample"]} utterances per step of the same workload and graph at full sequence lengths, 3 timed '
                       'steps (about 10 s of host work); NumPy/OpenBLAS restatement of the TF1 graph (oracle/)'}
+        # matrix-product FLOP of one training step per utterance (forward x 3: forward, input gradient, weight gradient)
+        # -> the rate the CPU arm sustains, so its distance from the host's own roof can be judged
+        fl = train_flop_per_utterance(cfg, 3888 if args.video_input == 'crops3888' else 128)
+        line['cpu_baseline']['gflops'] = round(r['value'] * fl / 1e9, 1)
+        line['cpu_baseline']['gflop_per_utterance'] = round(fl / 1e9, 2)
+        if cfg != 1:  # BASELINE.json configs[0]: the reference's own CPU-runnable case, at its own batch of 2
+            try:
+                r1 = run_oracle(args, 1, graph, steps=3, warmup=1, sample=CONFIGS[1]['batch'])
+                line['cpu_baseline']['config_1'] = {
+                    'value': round(r1['value'], 3), 'unit': UNIT, 'cores': r1['cores'], 'ms_per_step': round(r1['sec_per_step'] * 1e3, 1),
+                    'sample': 'configs[0] exactly: audio-only LAS 1x128, batch 2, Ta = 300 x 80, 41 label steps, 3 timed steps'}
+            except Exception as ex:
+                line['cpu_baseline']['config_1'] = {'error': repr(ex)}
         try:  # in a child process: nothing it does can cost the parent its JSON line
             child = subprocess.run([sys.executable, os.path.abspath(__file__), '--cer-check-only'] +
                                    (['--attention', args.attention] if args.attention else []),

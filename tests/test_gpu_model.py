@@ -56,6 +56,8 @@ CASES = [
     # ResidualWrapper on encoder layers > 0, layers 2.. sharing the cell of layer 1 (cells.py:77-92)
     (3, dict(residual_encoder=True)), (4, dict(residual_encoder=True, encoder_weight_sharing=True)),
     (1, dict(label_smoothing=0.1)),  # seq2seq.py:147-155: smoothed targets, unmasked mean
+    # bimodal decoder with one stream missing (decoder_bimodal.py:127-142): zero state in the shared projection
+    (4, dict(video_processing=None)), (4, dict(audio_processing=None, attention_type=(('bahdanau',), ('luong',)))),
 ]
 
 
@@ -215,7 +217,7 @@ def test_padding_invariance_full_size():
 
 
 @pytest.mark.parametrize('cfg,algo', [(1, 'greedy'), (5, 'greedy'), (1, 'beam_search'), (4, 'beam_search'),
-                                      (5, 'beam_search')])
+                                      (5, 'beam_search'), (-4, 'greedy'), (-4, 'beam_search')])
 def test_decoding_and_error_rates(cfg, algo):
     """ids from greedy / beam search equal the oracle's; CER / WER computed from them are
     bit-identical (integer Levenshtein, avsr/utils.py)."""
@@ -223,7 +225,8 @@ def test_decoding_and_error_rates(cfg, algo):
     from avsr_tf1_b200.seq2seq import Seq2SeqModel
     old = ops.set_tensor_cores(False)  # exact fp32 so arg-max / top-k decisions are reproducible
     try:
-        hp = config_hparams(cfg, decoding_algorithm=algo, beam_width=4 if algo == 'beam_search' else 10)
+        over = dict(video_processing=None) if cfg < 0 else {}  # -4: the bimodal decoder with the video stream missing
+        hp = config_hparams(abs(cfg), decoding_algorithm=algo, beam_width=4 if algo == 'beam_search' else 10, **over)
         hp.max_label_length = 12
         batch = synthetic_batch(hp, B=3, Ta=30, Tv=10, L=6, ragged=True)
         ds = to_data_sequences(batch)

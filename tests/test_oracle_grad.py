@@ -40,6 +40,9 @@ CASES += [
     (3, dict(DROP, residual_encoder=True)), (4, dict(residual_encoder=True, encoder_weight_sharing=True)),
     (3, dict(encoder_weight_sharing=True)),
     (1, dict(label_smoothing=0.1)), (5, dict(DROP, label_smoothing=0.2)),  # seq2seq.py:147-155
+    # bimodal decoder with one stream missing (decoder_bimodal.py:127-142): zero state in the shared projection
+    (4, dict(video_processing=None)), (4, dict(DROP, audio_processing=None)),
+    (4, dict(audio_processing=None, encoder_units_per_layer=((5, 6, 6), (6, 6, 6)))),
 ]
 
 
