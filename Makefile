@@ -25,3 +25,11 @@ $(LIB): $(OBJ)
 
 clean:
 	rm -f $(OBJ) $(LIB) $(IOLIB)
+
+# trace variant of the library (tools/ap4d_trace.py): the two-product attention kernel stamps clock64 at its
+# synchronisation points.  Never loaded by the product (AVSR_B200_LIB points the tool at it).
+TRACELIB := avsr_tf1_b200/lib/libavsr_b200_trace.so
+trace: $(TRACELIB)
+$(TRACELIB): $(OBJ)
+	$(NVCC) $(NVFLAGS) -DAP4D_TRACE -c avsr_tf1_b200/csrc/attn_persist4d.cu -o avsr_tf1_b200/csrc/attn_persist4d.trace.o
+	$(NVCC) $(ARCH) -shared -o $@ $(filter-out avsr_tf1_b200/csrc/attn_persist4d.o,$(OBJ)) avsr_tf1_b200/csrc/attn_persist4d.trace.o

@@ -108,6 +108,8 @@ PROTOTYPES = {
     'avsr_relu_bwd': (_I, [_P, _P, _P, _L, _P]),
     'avsr_selu_fwd': (_I, [_P, _P, _L, _P]),
     'avsr_selu_bwd': (_I, [_P, _P, _P, _L, _P]),
+    'avsr_highway_fwd': (_I, [_P, _P, _P, _P, _L, _P, _P]),
+    'avsr_highway_bwd': (_I, [_P, _P, _P, _P, _P, _L, _P, _P, _P]),
     'avsr_greedy_pick': (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     'avsr_beam_step': (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     'avsr_gather_rows': (_I, [_P, _P, _P, _L, _I, _P]),

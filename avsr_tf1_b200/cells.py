@@ -30,9 +30,6 @@ def build_rnn_layers(cell_type, num_units_per_layer, use_dropout, dropout_probab
                      residual_connections=False, highway_connections=False, weight_sharing=False, as_list=False):
     """Same signature and return convention as cells.py:61-102: one cell for a single
     layer, else the stack (a list stands in for MultiRNNCell)."""
-    if highway_connections:
-        raise NotImplementedError('highway encoders (tf.contrib.rnn.HighwayWrapper) are off in every reference '
-                                  'config (avsr.py:42) and not implemented on the B200 path')
     cell_list = []
     for layer, units in enumerate(num_units_per_layer):
         if layer > 1 and weight_sharing is True:
@@ -41,11 +38,14 @@ def build_rnn_layers(cell_type, num_units_per_layer, use_dropout, dropout_probab
             cell = LSTMCellSpec(units, cell_list[-1].use_dropout, cell_list[-1].dropout_probability)
             cell.share_with = 1
             cell.residual = cell_list[-1].residual
+            cell.highway = cell_list[-1].highway  # (the wrapper object is shared, its carry variables are per position)
         else:
             cell = _build_single_cell(cell_type, units, use_dropout, mode, dropout_probability, dtype)
             cell.share_with = None
-            # cells.py:91-92: ResidualWrapper(cell) for layer > 0: output = cell output + (un-dropped) layer input
-            cell.residual = bool(residual_connections is True and layer > 0)
+            # cells.py:89-92: HighwayWrapper(cell) for layer > 0 (carry = sigmoid(x Wc + bc), output = x * carry + cell
+            # output * (1 - carry)), else ResidualWrapper(cell): output = cell output + (un-dropped) layer input
+            cell.highway = bool(highway_connections is True and layer > 0)
+            cell.residual = bool(residual_connections is True and layer > 0 and not cell.highway)
         cell_list.append(cell)
     if len(cell_list) == 1:
         return cell_list[0]

@@ -119,6 +119,22 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
+// One lane of a converged warp (elect.sync): together with provably warp-uniform operands (warp index / tensor-memory
+// base passed through __shfl_sync, see warp_uniform) ptxas keeps the descriptors in uniform registers and emits the
+// tcgen05.mma directly - with `lane == 0` and per-thread operands every MMA sat in an ELECT / 4 x R2UR / branch loop
+// (~290 clocks per instruction, measured with tools/ap4d_trace.py).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0u;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -232,6 +248,18 @@ __device__ __forceinline__ float score8(const uint4& r, const float (&q)[8], con
            ((v[4] * tanhf_acc(c.x + q[4]) + v[5] * tanhf_acc(c.y + q[5])) + (v[6] * tanhf_acc(d.x + q[6]) + v[7] * tanhf_acc(d.y + q[7])));
   }
 }
+// (step-latency trace of tools/ap4d_trace.py: stamps of thread 0 / CTA 0 inside the attention core, -DAP4D_TRACE only)
+#ifdef AP4D_TRACE
+__device__ int g_att_trace_row = -1;                 // set by the kernel at the top of a traced step, -1 otherwise
+__device__ unsigned long long g_att_trace[16 * 8];
+#define ATT_STAMP(k)                                                                                   \
+  do {                                                                                                 \
+    if (threadIdx.x == 0 && blockIdx.x == 0 && g_att_trace_row >= 0)                                   \
+      g_att_trace[g_att_trace_row * 8 + (k)] = (unsigned long long)clock64();                          \
+  } while (0)
+#else
+#define ATT_STAMP(k) do { } while (0)
+#endif
 // forward: scores (keys already in ra / rb) -> masked softmax -> alignments (shared memory and `arow` in HBM) ->
 // context.  On return warp w4 == 0 holds the context in ctxv (tf32-rounded unless RAW_CTX).
 template <bool BAHD = false, bool RAW_CTX = false>
@@ -242,6 +270,7 @@ __device__ __forceinline__ void att_fwd_core(const AttRole& a, const float (&q)[
   float* red = a.red;
   // scores: rows tm = w4 + 4*i, one 9-shuffle reduction per batch of 8 rows
   const int jrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  ATT_STAMP(0);
   for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
     float sacc[RIF];
 #pragma unroll
@@ -256,14 +285,17 @@ __device__ __forceinline__ void att_fwd_core(const AttRole& a, const float (&q)[
     if ((lane & 3) == 0 && tm0 + 4 * jrow < L) sc[tm0 + 4 * jrow] = a.gs * tot;
   }
   // first batch of the values: in flight during the softmax
+  ATT_STAMP(1);
   att_prefetch(a, a.values, ra, rb);
   att_bar(a.bar_id);
+  ATT_STAMP(2);
   // masked softmax over the L scores (128 threads)
   float mx = -INFINITY;
   for (int tm = gt; tm < L; tm += 128) mx = fmaxf(mx, sc[tm]);
   mx = warp_max(mx);
   if (lane == 0) red[w4] = mx;
   att_bar(a.bar_id);
+  ATT_STAMP(3);
   mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
   float sum = 0.0f;
   for (int tm = gt; tm < L; tm += 128) {
@@ -274,6 +306,7 @@ __device__ __forceinline__ void att_fwd_core(const AttRole& a, const float (&q)[
   sum = warp_sum(sum);
   if (lane == 0) red[4 + w4] = sum;
   att_bar(a.bar_id);
+  ATT_STAMP(4);
   const float inv = L > 0 ? 1.0f / ((red[4] + red[5]) + (red[6] + red[7])) : 0.0f;
   for (int tm = gt; tm < a.Tm; tm += 128) {
     const float al = tm < L ? sc[tm] * inv : 0.0f;
@@ -281,6 +314,7 @@ __device__ __forceinline__ void att_fwd_core(const AttRole& a, const float (&q)[
     arow[tm] = al;
   }
   att_bar(a.bar_id);
+  ATT_STAMP(5);
   // context: rows tm = w4 + 4*i, lane accumulates dims 8*lane .. +7
   for (int tm0 = w4; tm0 < L; tm0 += 4 * RIF) {
     float al[RIF];
@@ -295,6 +329,7 @@ __device__ __forceinline__ void att_fwd_core(const AttRole& a, const float (&q)[
 #pragma unroll
     for (int j = 0; j < 4; ++j) rb[j] = ld_row(a.values, tm0 + 48 + 4 * j, L, a.B, a.b_att, lane);
   }
+  ATT_STAMP(6);
 #pragma unroll
   for (int e = 0; e < 8; ++e) a.part[w4 * DM + 8 * lane + e] = ctxv[e];
   att_bar(a.bar_id);
@@ -305,6 +340,7 @@ __device__ __forceinline__ void att_fwd_core(const AttRole& a, const float (&q)[
       ctxv[e] = RAW_CTX ? c : tf32_rn(c);
     }
   }
+  ATT_STAMP(7);
 }
 
 // backward of the same: d(align) = values . dctx (values already in ra / rb), softmax backward, dq = g * ds^T keys.

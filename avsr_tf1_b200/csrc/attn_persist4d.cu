@@ -41,6 +41,20 @@ __device__ __forceinline__ float dfac(uint32_t seed, uint32_t step, uint32_t str
   return (thr == 0u || avsr_rand_u32(seed, step, stream, hi, lo) < thr) ? inv : 0.0f;
 }
 
+// Step-latency trace (tools/ap4d_trace.py; compiled in only with -DAP4D_TRACE: a separate library, never the product):
+// thread 0 of CTA 0 stamps clock64 at the synchronisation points of steps TR_T0 .. TR_T0 + TR_NT - 1.
+#ifdef AP4D_TRACE
+constexpr int TR_T0 = 100, TR_NT = 16, TR_NP = 12;
+__device__ unsigned long long g_ap4d_trace[TR_NT * TR_NP];
+#define AP4D_STAMP(k)                                                                         \
+  do {                                                                                        \
+    if (tid == 0 && blockIdx.x == 0 && t >= TR_T0 && t < TR_T0 + TR_NT)                       \
+      g_ap4d_trace[(t - TR_T0) * TR_NP + (k)] = (unsigned long long)clock64();                \
+  } while (0)
+#else
+#define AP4D_STAMP(k) do { } while (0)
+#endif
+
 // =====================================================================================================
 // forward
 // =====================================================================================================
@@ -219,12 +233,16 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
   // product-issue role (lane 0 of EVERY warp; a tcgen05.mma costs ~80 clocks of its issuing thread).  Recurrent product:
   // warp (m, j) issues K blocks j (attention half) and 4 + j (h half) of tile m into accumulator 4 m + j.  Attention
   // product: warp w issues K steps 2 w, 2 w + 1 (of 16) into accumulator w.
-  const int jq = warp & 3;
-  const uint32_t acc1 = tmem_base + (4 * m + jq) * NP, acc2 = tmem_base + warp * NP;
+  // (every operand of the issue is derived from warp-uniform values, the issuing lane is elected: see elect_one)
+  const int warp_u = (int)warp_uniform((uint32_t)warp);
+  const uint32_t tmem_u = warp_uniform(tmem_base);
+  const int jq = warp_u & 3, m_u = warp_u >> 2;
+  const uint32_t acc1 = tmem_u + (4 * m_u + jq) * NP, acc2 = tmem_u + warp_u * NP;
+  const uint32_t tWa_u = tmem_u + 128, tW1_u = tmem_u + 256;
   const uint64_t dW0 = make_desc_k128(sW), dQ = make_desc_k128(sQ);
   const uint64_t dOp[2] = {make_desc_k128(sOp), make_desc_k128(sOp + OP_BYTES)};
   auto issue_rec = [&](uint32_t nbuf) {
-    if (lane == 0) {
+    if (elect_one()) {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int kb = 4 * half + jq;
@@ -232,8 +250,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
         for (int k4 = 0; k4 < 4; ++k4) {
           const uint64_t db = desc_at(dOp[nbuf], kb * (NP * 128) + k4 * 32);
           const uint32_t acc = (half | k4) ? 1u : 0u;
-          if (m == 0) umma_ss(acc1, desc_at(dW0, kb * (128 * 128) + k4 * 32), db, IDESC, acc);
-          else umma_ts(acc1, tW1 + (kb * 4 + k4) * 8, db, IDESC, acc);
+          if (m_u == 0) umma_ss(acc1, desc_at(dW0, kb * (128 * 128) + k4 * 32), db, IDESC, acc);
+          else umma_ts(acc1, tW1_u + (kb * 4 + k4) * 8, db, IDESC, acc);
         }
       }
       umma_commit(barM1);
@@ -241,11 +259,11 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     __syncwarp();
   };
   auto issue_att = [&]() {
-    if (lane == 0) {
+    if (elect_one()) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int s = 2 * warp + i;  // K step of 16: K block s >> 2, 32-byte slice s & 3
-        umma_ts(acc2, tWa + s * 8, desc_at(dQ, (s >> 2) * (NP * 128) + (s & 3) * 32), IDESC, i ? 1u : 0u);
+        const int s = 2 * warp_u + i;  // K step of 16: K block s >> 2, 32-byte slice s & 3
+        umma_ts(acc2, tWa_u + s * 8, desc_at(dQ, (s >> 2) * (NP * 128) + (s & 3) * 32), IDESC, i ? 1u : 0u);
       }
       umma_commit(barM2);
     }
@@ -333,6 +351,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
       ap[b * UPC] = (__uint_as_float(r0[b]) + __uint_as_float(r1[b])) + (__uint_as_float(r2[b]) + __uint_as_float(r3[b]));
   };
   for (int t = 0; t < T; ++t) {
+#ifdef AP4D_TRACE
+    if (tid == 0 && blockIdx.x == 0) g_att_trace_row = (t >= TR_T0 && t < TR_T0 + TR_NT) ? t - TR_T0 : -1;
+#endif
+    AP4D_STAMP(0);
     float* grow = p.gates + ((size_t)t * B + b0) * 4 * H + g * H + unit_g;
     uint32_t selmask = 0u;  // SAMPLE: utterances of the cluster whose next input is drawn from this step's logits
     if constexpr (SAMPLE) {
@@ -345,6 +367,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     uint32_t r[8];
     if (t > 0) {
       mbar_wait(barM1, (t - 1) & 1);
+      AP4D_STAMP(1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t r1[8], r2[8], r3[8];
       tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 0) * NP, r);
@@ -371,6 +394,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
       act[(g * NB + b) * UPC + 32 * m + lane] = a;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    AP4D_STAMP(2);
     const uint32_t nb = (t + 1) & 1;
     const uint32_t hbar_n = sBar + 16 + 8 * nb;
     float hs[4], ho[4], cr[4];
@@ -414,6 +438,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
         st_async_v2(mapa(dO, dst), bar, o01, o23);
       }
     }
+    AP4D_STAMP(3);
     // HBM side of this step + x-projection of the next (overlaps the all-gather)
 #pragma unroll
     for (int b = 0; b < NB; ++b)
@@ -445,7 +470,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     uint4 ra[4], rb[4];
     if (live_q) att_prefetch(role, p.keys, ra, rb);
     if (tid == 0) mbar_expect_tx(hbar_n, 2 * NB * H * 2);
+    AP4D_STAMP(4);
     mbar_wait(hbar_n, (t >> 1) & 1);  // every CTA's hs_t / ho_t slices have landed
+    AP4D_STAMP(5);
 
     if constexpr (BAHD) {
       // [ho Wl_h | ho Wq] for the CTA's units as soon as ho_t is there; the pq slices go to the owners of the utterances
@@ -488,6 +515,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
       }
       att_fwd_core<BAHD, BAHD>(role, q, v8, ra, rb, p.align + ((size_t)t * B + b_att) * Tm, ctxv);
     }
+    AP4D_STAMP(6);
     if (BAHD && w4 == 0) {
       // projected context ctx' = sum_t a_t PV_t: slices to the owners of the attention units (fp32)
       if (b_att < B && !live_q) {
@@ -525,15 +553,18 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     // ---------------- a_t = [ho | ctx] Wa for the CTA's 64 attention units ----------------
     if (tid == 0) mbar_expect_tx(barCtx, BAHD ? NB * UPC * 4 : NB * DM * 2);
     mbar_wait(barCtx, t & 1);
+    AP4D_STAMP(7);
     if constexpr (!BAHD) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       issue_att();
       mbar_wait(barM2, t & 1);
+      AP4D_STAMP(8);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       att_epilogue();
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    AP4D_STAMP(9);
     if (comb) {
       float a[4];
       {
@@ -642,11 +673,13 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     // the last step the wait only drains the all-gather: no st.async may be in flight towards a CTA that exits.
     if (tid == 0) mbar_expect_tx(barA, NB * AT * 2);
     mbar_wait(barA, t & 1);
+    AP4D_STAMP(10);
     if (t + 1 < T) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       issue_rec(nb);
     }
+    AP4D_STAMP(11);
   }
   if (comb && b0 + bq < B) {
     const size_t o = (size_t)(b0 + bq) * H + UPC * rank + 4 * uq;
@@ -1668,3 +1701,20 @@ int attn_persist4d_launch_bahd_bwd(cudaStream_t st, const AvsrRnnSeq* r, const v
 }
 
 }  // namespace avsr
+
+#ifdef AP4D_TRACE
+// debug accessor of the trace library (tools/ap4d_trace.py): clock64 stamps [TR_NT][TR_NP] of the last forward launch
+extern "C" int avsr_debug_ap4d_trace(unsigned long long* out, int n) {
+  const int total = avsr::ap4::TR_NT * avsr::ap4::TR_NP;
+  if (n < total) return -1;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpyFromSymbol(out, avsr::ap4::g_ap4d_trace, sizeof(unsigned long long) * total) != cudaSuccess) return -3;
+  return total;
+}
+extern "C" int avsr_debug_att_trace(unsigned long long* out, int n) {
+  if (n < 16 * 8) return -1;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpyFromSymbol(out, avsr::ap4::g_att_trace, sizeof(unsigned long long) * 16 * 8) != cudaSuccess) return -3;
+  return 16 * 8;
+}
+#endif

@@ -101,6 +101,22 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc)
       : "memory");
 }
+// One lane of a converged warp (elect.sync).  With the issuing lane elected and every operand derived from provably
+// warp-uniform values (warp index / tensor-memory base passed through __shfl_sync) ptxas keeps the descriptors in uniform
+// registers and emits the tcgen05.mma back to back; with `lane == 0` and per-thread operands every MMA sat in an
+// ELECT / 4 x R2UR / branch loop of ~290 clocks (tools/ap4d_trace.py).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0u;
+}
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -236,15 +252,18 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_fwd_kernel(const Fwd
   // more than the 128 x 16 x 16 product takes, and the 16 K steps of a tile sit on the critical path of the step.  So
   // EVERY warp issues: lane 0 of warp (m, j) issues the K quarter j (= K block j, four steps) of tile m into its own
   // accumulator columns, and the gate math adds the four partial accumulators of its tile.
-  const int jq = warp & 3;
-  const uint32_t acc_col = tmem_base + (4 * m + jq) * NP;
+  const int warp_u = (int)warp_uniform((uint32_t)warp);  // (uniform operands + elected lane: see elect_one)
+  const uint32_t tmem_u = warp_uniform(tmem_base);
+  const int jq = warp_u & 3, m_u = warp_u >> 2;
+  const uint32_t acc_col = tmem_u + (4 * m_u + jq) * NP;
+  const uint32_t tW_u = tmem_u + 256, mbar_mu = sBar + 8 * m_u;
   const uint64_t dOp[2] = {make_desc_k128(sOp), make_desc_k128(sOp + OP_BYTES)};
   auto issue_quarter = [&](uint32_t nbuf) {
-    if (lane == 0) {
+    if (elect_one()) {
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4)
-        umma_ts(acc_col, tW + 128 * m + (jq * 4 + k4) * 8, desc_at(dOp[nbuf], jq * (NP * 128) + k4 * 32), IDESC, k4 ? 1u : 0u);
-      umma_commit(mbar_m);
+        umma_ts(acc_col, tW_u + 128 * m_u + (jq * 4 + k4) * 8, desc_at(dOp[nbuf], jq * (NP * 128) + k4 * 32), IDESC, k4 ? 1u : 0u);
+      umma_commit(mbar_mu);
     }
     __syncwarp();
   };
@@ -484,6 +503,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
   const uint32_t tA = tmem_base + 256;
+  const int warp_u = (int)warp_uniform((uint32_t)warp);  // (uniform operands + elected lane: see elect_one)
+  const uint32_t tmem_u = warp_uniform(tmem_base), tA_u = tmem_u + 256;
   {
     const int q = warp & 3, tt = warp >> 2;
     const float* row = p.Wrec + (size_t)(128 * tt + 32 * q + lane) * 4 * H + UPC * rank;
@@ -619,14 +640,14 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_persist4_bwd_kernel(const Bwd
       // partial dh (256 rows) x NB from this CTA's 256 gate columns, once every warp's dz is in shared memory.  Every
       // warp issues (see the forward kernel): lane 0 of warp (mt, j) the K quarter j (gate j) of the 128-row tile mt
       // into its own accumulator columns; the reduce-scatter below adds the four partial accumulators.
-      const int mt = warp >> 2, jq = warp & 3;
+      const int mt = warp_u >> 2, jq = warp_u & 3;
       mbar_wait(sBar + 8, it & 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4)
-          umma_ts(tmem_base + (4 * mt + jq) * NP, tA + 128 * mt + (jq * 4 + k4) * 8, desc_at(dDz, jq * (NP * 128) + k4 * 32), IDESC,
+          umma_ts(tmem_u + (4 * mt + jq) * NP, tA_u + 128 * mt + (jq * 4 + k4) * 8, desc_at(dDz, jq * (NP * 128) + k4 * 32), IDESC,
                   k4 ? 1u : 0u);
         umma_commit(sBar);
       }

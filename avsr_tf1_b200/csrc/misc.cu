@@ -534,6 +534,31 @@ __global__ void selu_bwd_kernel(const float* __restrict__ y, const float* __rest
   }
 }
 
+// tf.contrib.rnn.HighwayWrapper around an encoder layer (cells.py:89-90; coupled gates, carry bias 1):
+//   carry = sigmoid(x Wc + bc) (`pre` = the product), y = x * carry + out * (1 - carry)
+// backward: dx (direct part only: the carry product's share is a GEMM on dpre), dout, dpre
+__global__ void highway_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pre,
+                                   const float* __restrict__ out, long long n, int rnd, float* __restrict__ y,
+                                   float* __restrict__ y_op) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float c = 1.0f / (1.0f + expf(-pre[i]));
+    const float v = x[i] * c + out[i] * (1.0f - c);
+    y[i] = v;
+    if (y_op) y_op[i] = maybe_tf32(v, rnd);
+  }
+}
+__global__ void highway_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                   const float* __restrict__ pre, const float* __restrict__ out, long long n, int rnd,
+                                   float* __restrict__ dx, float* __restrict__ dout, float* __restrict__ dpre) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float c = 1.0f / (1.0f + expf(-pre[i]));
+    const float d = dy[i];
+    dx[i] = d * c;
+    dout[i] = d * (1.0f - c);
+    dpre[i] = maybe_tf32(d * (x[i] - out[i]) * c * (1.0f - c), rnd);
+  }
+}
+
 // ---- direct convolutions for the narrow layers of the front-end (8 / 16 output channels: almost all of its pixels) ---
 // One thread per output pixel, all CO output channels in registers, the kernel [kh*kw*Ci][CO] in shared memory (broadcast
 // reads); NHWC input read straight from global memory (the 3x3 neighbourhoods of adjacent threads overlap in L1).  No
@@ -1076,6 +1101,20 @@ int avsr_selu_fwd(avsr_stream_t s, const float* x, long long n, float* y) {
 int avsr_selu_bwd(avsr_stream_t s, const float* y, const float* dy, long long n, float* dx) {
   if (n <= 0) return 0;
   AVSR_LAUNCH(selu_bwd_kernel, grid_for(n), 256, 0, ST(s), y, dy, n, dx);
+  return 0;
+}
+
+int avsr_highway_fwd(avsr_stream_t s, const float* x, const float* pre, const float* out, long long n, float* y,
+                     float* y_op) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(highway_fwd_kernel, grid_for(n), 256, 0, ST(s), x, pre, out, n, tensor_cores_enabled(), y, y_op);
+  return 0;
+}
+
+int avsr_highway_bwd(avsr_stream_t s, const float* dy, const float* x, const float* pre, const float* out, long long n,
+                     float* dx, float* dout, float* dpre) {
+  if (n <= 0) return 0;
+  AVSR_LAUNCH(highway_bwd_kernel, grid_for(n), 256, 0, ST(s), dy, x, pre, out, n, tensor_cores_enabled(), dx, dout, dpre);
   return 0;
 }
 

@@ -70,9 +70,22 @@ class Seq2SeqUnimodalDecoder(object):
     def _init_embedding(self):
         hp, ctx = self._hparams, self._ctx
         if hp.embedding_size <= 0:
-            raise NotImplementedError('one-hot decoder inputs (embedding_size <= 0) are not built')
+            # decoder_unimodal.py:75-76: one-hot inputs - the "embedding matrix" is the constant tf.eye(vocab_size): no
+            # variable, nothing to train or to save
+            self._E = self._vocab_size
+            self._embedding = None
+            self._eye = None
+            return
         self._E = hp.embedding_size
         self._embedding = ctx.declare('embeddings/embedding_matrix', (self._vocab_size, self._E), 'embedding')
+
+    def _table(self):
+        """The lookup table as a product operand: the trained embedding matrix, or the identity for one-hot inputs."""
+        if self._embedding is not None:
+            return self._ctx.w(self._embedding)
+        if self._eye is None:
+            self._eye = torch.eye(self._vocab_size, dtype=torch.float32, device='cuda')
+        return self._eye
 
     def _attention_types(self):
         return [self._hparams.attention_type[1][0]]
@@ -84,8 +97,6 @@ class Seq2SeqUnimodalDecoder(object):
         hp, ctx = self._hparams, self._ctx
         if len(hp.decoder_units_per_layer) != 1:
             raise NotImplementedError('multi-layer decoders are not used by any reference config')
-        if hp.enable_attention is not True:
-            raise NotImplementedError('enable_attention=False is not used by any reference config')
         if hp.decoding_algorithm not in ('greedy', 'beam_search'):
             raise Exception('The only supported algorithms are `greedy` and `beam_search`')
         cell = build_rnn_layers(cell_type=hp.cell_type, num_units_per_layer=hp.decoder_units_per_layer,
@@ -93,10 +104,17 @@ class Seq2SeqUnimodalDecoder(object):
                                 mode=self._mode)
         self._H = cell.num_units
         self._extra_decls()
-        self._cell = add_attention(cell, attention_types=self._attention_types(),
-                                   num_units=hp.decoder_units_per_layer[-1], memory_depths=self._mem_depths, ctx=ctx,
-                                   wrap_prefix='Decoder/decoder/attention_wrapper',
-                                   mem_layer_names=self._mem_layer_names(), in_dim=self._E)
+        if hp.enable_attention is True:
+            self._cell = add_attention(cell, attention_types=self._attention_types(),
+                                       num_units=hp.decoder_units_per_layer[-1], memory_depths=self._mem_depths, ctx=ctx,
+                                       wrap_prefix='Decoder/decoder/attention_wrapper',
+                                       mem_layer_names=self._mem_layer_names(), in_dim=self._E)
+        else:
+            # decoder_unimodal.py:319-327 / decoder_bimodal.py:261-263: the bare (dropout-wrapped) cell under BasicDecoder,
+            # started from the decoder initial state; the encoder outputs are not attended to (`Decoder/decoder/lstm_cell`)
+            from .layers import AttnLSTMOp
+            self._cell = AttnLSTMOp(ctx, 'Decoder/decoder', self._E, cell.num_units, [],
+                                    drop=ctx.drop_state(cell, 'Decoder/decoder'))
         self._Wd = ctx.declare('Decoder/decoder/my_dense/kernel', (self._cell.out_dim, self._vocab_size), 'glorot')
         self._bd = ctx.declare('Decoder/decoder/my_dense/bias', (self._vocab_size,), 'zeros')
 
@@ -120,6 +138,9 @@ class Seq2SeqUnimodalDecoder(object):
         ctx = self._ctx
         B = labels.shape[0]
         init = self._initial_state_fwd(encoder_states)
+        self._n_mem = len(memories)
+        if not self._cell.mechs:
+            memories = []
         O = self._cell.out_dim
         self._logits = ops.empty(T, B, self._vocab_size)
         if self._ss_thr:
@@ -127,7 +148,7 @@ class Seq2SeqUnimodalDecoder(object):
         else:
             self._ids = dec_in_ids.reshape(-1)
             x = ops.empty(T, B, self._E)
-            ops.embedding_fwd(ctx.w(self._embedding), self._ids, x)
+            ops.embedding_fwd(self._table(), self._ids, x)
             out = self._cell.forward(x, labels_len, memories=memories, init=init)
             ops.gemm(out.view(T * B, O), ctx.p(self._Wd), self._logits.view(T * B, self._vocab_size),
                      bias=ctx.p(self._bd))
@@ -145,7 +166,7 @@ class Seq2SeqUnimodalDecoder(object):
         V = self._vocab_size
         used = dec_in_ids.clone()  # [T,B]; rows 1.. are overwritten where the helper draws
         self.sample_ids = torch.full((T, B), -1, dtype=torch.int32, device='cuda')
-        table = ctx.w(self._embedding)
+        table = self._table()
         # the persistent kernel draws inside the recurrence when it covers this cell (one launch instead of ~11 per step)
         out = cell.forward_sampled(table, dec_in_ids, labels_len, memories, init, ctx.p(self._Wd), ctx.p(self._bd),
                                    self._ss_stream, self._ss_thr, used, self.sample_ids)
@@ -179,7 +200,10 @@ class Seq2SeqUnimodalDecoder(object):
         dout = ops.empty(T, B, O)
         ops.gemm(dl2, ctx.p(self._Wd), dout.view(T * B, O), tb=True)
         dx, dmem, dinit = self._cell.backward(dout, None, need_dx=True, want_init_grad=True)
-        ops.embedding_bwd(dx.view(T * B, self._E), self._ids, ctx.g(self._embedding))
+        if self._embedding is not None:
+            ops.embedding_bwd(dx.view(T * B, self._E), self._ids, ctx.g(self._embedding))
+        if not self._cell.mechs:  # nothing attends to the encoder outputs
+            dmem = [None] * self._n_mem
         return dmem, self._initial_state_bwd(dinit)
 
     # ---- inference -------------------------------------------------------------
@@ -194,16 +218,18 @@ class Seq2SeqUnimodalDecoder(object):
         ctx, hp = self._ctx, self._hparams
         B = memories[0][0].shape[1]
         init = self._initial_state_fwd(encoder_states)
+        if not self._cell.mechs:
+            memories = []
         bufs = self._cell.prepare_memories(memories)
         state = self._cell.initial_state(B, init)
         ids = torch.full((B,), self._GO_ID, dtype=torch.int32, device='cuda')
         finished = torch.zeros(B, dtype=torch.int32, device='cuda')
         active = torch.ones(B, dtype=torch.int32, device='cuda')
         samples = []
-        history = [[] for _ in bufs] if hp.write_attention_alignment else None
+        history = [[] for _ in bufs] if (hp.write_attention_alignment and bufs) else None
         for _ in range(hp.max_label_length):
             x = ops.empty(1, B, self._E)
-            ops.embedding_fwd(ctx.w(self._embedding), ids, x)
+            ops.embedding_fwd(self._table(), ids, x)
             torch.sub(1, finished, out=active)  # finished rows carry their state (impute_finished)
             out, state = self._cell.step(x, active, bufs, state)
             if history is not None:  # alignment_history (attention.py:178)
@@ -236,6 +262,8 @@ class Seq2SeqUnimodalDecoder(object):
         W = hp.beam_width
         B = memories[0][0].shape[1]
         init = self._initial_state_fwd(encoder_states)
+        if not self._cell.mechs:
+            memories = []
         tiled = [(m[0].repeat_interleave(W, dim=1).contiguous(), m[1].repeat_interleave(W).contiguous(),
                   m[2].repeat_interleave(W, dim=1).contiguous() if len(m) > 2 and m[2] is not None else None)
                  for m in memories]  # seq2seq.tile_batch (attention.py:101-106)
@@ -252,7 +280,7 @@ class Seq2SeqUnimodalDecoder(object):
         words, parents, scores = [], [], []
         for _ in range(hp.max_label_length):
             x = ops.empty(1, B * W, self._E)
-            ops.embedding_fwd(ctx.w(self._embedding), ids, x)
+            ops.embedding_fwd(self._table(), ids, x)
             out, (c, S) = self._cell.step(x, active, bufs, (c, S))
             logits = self._logits_step(out)
             word = torch.empty((B, W), dtype=torch.int32, device='cuda')

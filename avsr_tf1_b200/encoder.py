@@ -140,8 +140,17 @@ class Seq2SeqEncoder(object):
                 share = ops_[cell.share_with] if getattr(cell, 'share_with', None) is not None else None
                 op = LSTMLayerOp(ctx, prefix, in_dim, cell.num_units, drop=ctx.drop_state(cell, prefix), share=share)
                 op.residual = bool(getattr(cell, 'residual', False))
+                op.highway = None
                 if op.residual and in_dim != cell.num_units:
                     raise ValueError('residual connections need layers of equal width (ResidualWrapper adds input and output)')
+                if getattr(cell, 'highway', False):
+                    # tf.contrib.rnn.HighwayWrapper (cells.py:89-90): `carry_w` [in, in] (default glorot initialiser) and
+                    # `carry_b` (constant 1) live in the position's own scope (`.../cell_k/`), also when the cell is shared
+                    if in_dim != cell.num_units:
+                        raise ValueError('highway connections need layers of equal width (HighwayWrapper mixes input and output)')
+                    scope_k = prefix.rsplit('/', 1)[0]
+                    op.highway = (ctx.declare(scope_k + '/carry_w', (in_dim, in_dim), 'glorot'),
+                                  ctx.declare(scope_k + '/carry_b', (in_dim,), 'const:1.0'))
                 ops_.append(op)
                 in_dim = cell.num_units
             return ops_
@@ -222,7 +231,13 @@ class Seq2SeqEncoder(object):
         cur, cur_op = None, x
         for op in self._fw:
             out = op.forward(cur_op, inputs_len)
-            if getattr(op, 'residual', False):  # ResidualWrapper (cells.py:91-92): + the layer's (un-dropped) input
+            if getattr(op, 'highway', None):  # HighwayWrapper (cells.py:89-90) around the (dropout-wrapped) cell
+                T_, B_, D_ = cur.shape
+                pre = ops.empty(T_, B_, D_)
+                ops.gemm(cur_op.reshape(T_ * B_, D_), ctx.w(op.highway[0]), pre.view(T_ * B_, D_), bias=ctx.p(op.highway[1]))
+                op.hw_saved = (cur, cur_op, pre, out)
+                cur, cur_op = ops.highway_fwd(cur, pre, out)
+            elif getattr(op, 'residual', False):  # ResidualWrapper (cells.py:91-92): + the layer's (un-dropped) input
                 cur = out + cur
                 cur_op = ops.round_tf32(cur) if ops.tensor_cores_enabled() else cur
             else:
@@ -233,7 +248,8 @@ class Seq2SeqEncoder(object):
             outb = backward_stack()
         if self._bw is None:
             self._outputs = cur
-            self._outputs_op = cur_op if getattr(self._fw[-1], 'residual', False) else self._round_outputs(cur, self._fw[-1])
+            wrapped = getattr(self._fw[-1], 'residual', False) or getattr(self._fw[-1], 'highway', None)
+            self._outputs_op = cur_op if wrapped else self._round_outputs(cur, self._fw[-1])
             self._final = self._fw[-1].final
         else:
             T, B, H = cur.shape
@@ -291,8 +307,22 @@ class Seq2SeqEncoder(object):
             need_dx = need_dx or self._layer0_drops_input()
             for i in range(n - 1, -1, -1):
                 need = (i > 0) or need_dx
-                dn = self._fw[i].backward(d, dfinal_state if i == n - 1 else None, need_dx=need)
-                if getattr(self._fw[i], 'residual', False) and dn is not None:
+                op = self._fw[i]
+                if getattr(op, 'highway', None):
+                    x_in, x_op, pre, out = op.hw_saved
+                    op.hw_saved = None
+                    T_, B_, D_ = x_in.shape
+                    dx_carry, dcell, dpre = ops.highway_bwd(d, x_in, pre, out)
+                    dpre2 = dpre.view(T_ * B_, D_)
+                    ops.gemm(x_op.reshape(T_ * B_, D_), dpre2, ctx.g(op.highway[0]), ta=True, beta=1.0)
+                    ops.colsum(dpre2, ctx.g(op.highway[1]))
+                    dn = op.backward(dcell, dfinal_state if i == n - 1 else None, need_dx=True)
+                    ops.gemm(dpre2, ctx.w(op.highway[0]), dn.view(T_ * B_, D_), tb=True, beta=1.0)
+                    ops.axpy(1.0, dx_carry, dn)
+                    d = dn
+                    continue
+                dn = op.backward(d, dfinal_state if i == n - 1 else None, need_dx=need)
+                if getattr(op, 'residual', False) and dn is not None:
                     ops.axpy(1.0, d, dn)  # the shortcut around the cell
                 d = dn
             dx = d

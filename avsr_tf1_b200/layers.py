@@ -275,7 +275,9 @@ class AttnLSTMOp:
         self.At = sum(m.A for m in self.mechs)
         self.kernel = ctx.declare(wrap_prefix + '/lstm_cell/kernel', (in_dim + self.At + H, 4 * H), 'lstm_kernel')
         self.bias = ctx.declare(wrap_prefix + '/lstm_cell/bias', (4 * H,), 'zeros')
-        self.output_attention = self.mechs[-1].output_attention  # flag of the last mechanism created
+        # flag of the last mechanism created; no mechanisms (enable_attention=False: the bare cell under BasicDecoder,
+        # decoder_unimodal.py:319-327 - `wrap_prefix` is then the decoder scope itself): the cell output
+        self.output_attention = self.mechs[-1].output_attention if self.mechs else False
         self.out_dim = self.At if self.output_attention else H
 
     def prepare_memories(self, memories: Sequence[Tuple[torch.Tensor, torch.Tensor]]):

@@ -337,6 +337,23 @@ def selu_bwd(y, dy, out=None):
     return dx
 
 
+def highway_fwd(x, pre, out, want_operand=True):
+    """HighwayWrapper (cells.py:89-90): y = x * sigmoid(pre) + out * (1 - sigmoid(pre)); returns (y, operand copy of y)."""
+    y = torch.empty_like(x)
+    y_op = torch.empty_like(x) if want_operand else None
+    check(_lib.load().avsr_highway_fwd(_stream(), x.data_ptr(), pre.data_ptr(), out.data_ptr(), x.numel(), y.data_ptr(),
+                                       _p(y_op)))
+    return y, y_op
+
+
+def highway_bwd(dy, x, pre, out):
+    """Returns (dx through the carried input, dout, dpre)."""
+    dx, dout, dpre = torch.empty_like(dy), torch.empty_like(dy), torch.empty_like(dy)
+    check(_lib.load().avsr_highway_bwd(_stream(), dy.data_ptr(), x.data_ptr(), pre.data_ptr(), out.data_ptr(), dy.numel(),
+                                       dx.data_ptr(), dout.data_ptr(), dpre.data_ptr()))
+    return dx, dout, dpre
+
+
 def relu_fwd(x, out=None):
     y = torch.empty_like(x) if out is None else out
     check(_lib.load().avsr_relu_fwd(_stream(), x.data_ptr(), x.numel(), y.data_ptr()))

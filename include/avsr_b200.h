@@ -325,6 +325,15 @@ int avsr_relu_bwd(avsr_stream_t stream, const float* y, const float* dy, long lo
 int avsr_selu_fwd(avsr_stream_t stream, const float* x, long long n, float* y);
 int avsr_selu_bwd(avsr_stream_t stream, const float* y, const float* dy, long long n, float* dx);
 
+/* tf.contrib.rnn.HighwayWrapper around encoder layers > 0 (cells.py:89-90: `highway_encoder`; coupled gates):
+ * carry = sigmoid(pre) with pre = x Wc + bc formed by avsr_gemm, y = x * carry + out * (1 - carry); y_op (or NULL) receives
+ * the product-operand copy of y (tf32-rounded in tensor-core mode).  Backward: dx = dy * carry (the share through the
+ * carry product is dpre Wc^T, a GEMM), dout = dy * (1 - carry), dpre = dy (x - out) carry (1 - carry) (operand-rounded). */
+int avsr_highway_fwd(avsr_stream_t stream, const float* x, const float* pre, const float* out, long long n, float* y,
+                     float* y_op);
+int avsr_highway_bwd(avsr_stream_t stream, const float* dy, const float* x, const float* pre, const float* out,
+                     long long n, float* dx, float* dout, float* dpre);
+
 /* ---- optimiser (seq2seq.py:175-178, 195-257) --------------------------------- */
 /* out[0] += sum x^2 */
 int avsr_sumsq(avsr_stream_t stream, const float* x, long long n, float* out);

@@ -174,8 +174,8 @@ def test_two_hundred_steps_tensor_core_training_tracks_exact_fp32():
           norm 5e-3, gradient direction cosine >= 0.9995; the trajectory itself is not reproducible - fp32 atomics order - and
           the smallest cosine of a run has been seen between 0.99988 and 0.99995) - this is what the 1.5e-2 per-tensor gradient tolerance of the
           tensor-core tests has to guarantee;
-      (b) the independent tensor-core run learns the same thing: same final loss level (within 25 %: the two runs are
-          different chaotic trajectories) and step-by-step agreement over the first 10 steps."""
+      (b) the independent tensor-core run learns the same thing: same final loss level (within the band two chaotic
+          trajectories oscillate in) and step-by-step agreement over the first 10 steps."""
     from avsr_tf1_b200 import ops
     from avsr_tf1_b200.seq2seq import Seq2SeqModel
     hp = config_hparams(5, learning_rate=1e-3)
@@ -222,5 +222,7 @@ def test_two_hundred_steps_tensor_core_training_tracks_exact_fp32():
     assert worst['loss'] <= 1e-3 and worst['gnorm'] <= 5e-3 and worst['cos'] >= 0.9995, worst
     # independent runs drift apart (the loss oscillates between 0.24 and 0.35 at lr 1e-3 on four memorised batches):
     # same level, not the same value
-    assert abs(t[-20:].mean() - x[-20:].mean()) <= 0.25 * x[-20:].mean()
+    # (the last-20-step means of two such runs have been seen anywhere in 0.24 .. 0.36: a factor 1.6 bounds the band)
+    lo, hi = sorted([float(t[-20:].mean()), float(x[-20:].mean())])
+    assert hi <= 1.6 * lo and hi < 0.15 * x[:4].mean()
     assert np.abs(t[:10] - x[:10]).max() <= 1e-3 * x[:10].max()  # before the runs drift apart they agree step by step

@@ -86,6 +86,7 @@ CASES = [
     (1, dict(attention_type=(('bahdanau',), ('bahdanau',)))),
     (5, dict(attention_type=(('bahdanau',), ('normed_bahdanau',)))),
     (5, dict(batch_normalisation=False)),
+    (3, dict(highway_encoder=True)),  # HighwayWrapper around the dropout-wrapped cells (cells.py:89-90)
 ]
 
 
@@ -120,7 +121,9 @@ def test_dropout_masks_change_with_the_step_and_not_in_evaluate_mode():
 
 
 @pytest.mark.parametrize('cfg,over', [(1, {}), (4, {}), (5, {}),
-                                      (5, dict(attention_type=(('bahdanau',), ('bahdanau',))))])
+                                      (5, dict(attention_type=(('bahdanau',), ('bahdanau',)))),
+                                      (5, dict(embedding_size=0)),  # one-hot decoder inputs (decoder_unimodal.py:75-76)
+                                      (1, dict(enable_attention=False))])  # the bare decoder cell (decoder_unimodal.py:319-327)
 def test_scheduled_sampling(cfg, over, tensor_cores):
     """p = 0.5 so that about half of the decoder inputs are draws.  Which (step, row) pairs are replaced is an integer
     decision and must agree exactly; the drawn ids agree unless the uniform lands within rounding of a CDF step, so

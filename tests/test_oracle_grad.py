@@ -43,11 +43,19 @@ CASES += [
     # bimodal decoder with one stream missing (decoder_bimodal.py:127-142): zero state in the shared projection
     (4, dict(video_processing=None)), (4, dict(DROP, audio_processing=None)),
     (4, dict(audio_processing=None, encoder_units_per_layer=((5, 6, 6), (6, 6, 6)))),
+    # HighwayWrapper on encoder layers > 0 (cells.py:89-90), alone, over the residual flag, with the shared cell
+    (3, dict(DROP, highway_encoder=True)), (4, dict(highway_encoder=True, residual_encoder=True)),
+    (3, dict(highway_encoder=True, encoder_weight_sharing=True)),
+    # enable_attention=False (decoder_unimodal.py:319-327): the bare decoder cell started from the encoder state
+    (1, dict(enable_attention=False)), (4, dict(DROP, enable_attention=False, sampling_probability_outputs=0.5)),
+    (5, dict(enable_attention=False)),
+    # one-hot decoder inputs (decoder_unimodal.py:75-76: embedding_size <= 0 -> tf.eye)
+    (1, dict(embedding_size=0)), (5, dict(DROP, embedding_size=-1, sampling_probability_outputs=0.5)),
 ]
 
 
 def tiny_model(cfg, over, seed=7):
-    hp = config_hparams(cfg, units=6, embedding_size=5, **over)
+    hp = config_hparams(cfg, units=6, **dict(dict(embedding_size=5), **over))
     batch = synthetic_batch(hp, B=3, Ta=7, Tv=5, Fa=4, Fv=3, L=4, ragged=True, seed=seed)
     if hp.regress_aus:
         add_aus(batch)

@@ -14,8 +14,12 @@ class Drop:  # what ops.RnnSeq reads of a layers.DropState (keep 0.9 / 0.9 / 0.9
 
 
 ops.kernel_timing(True)
-for (name, T, Dx, Tm, drop) in [('cross-modal', 300, 256, 75, None), ('decoder', 41, 128, 300, None),
-                                ('cross-modal+dropout', 300, 256, 75, Drop()), ('decoder+dropout', 41, 128, 300, Drop())]:
+CASES = [('cross-modal', 300, 256, 75, None), ('decoder', 41, 128, 300, None),
+         ('cross-modal+dropout', 300, 256, 75, Drop()), ('decoder+dropout', 41, 128, 300, Drop())]
+if len(sys.argv) > 1 and sys.argv[1] == 'sweep':  # memory-length sweep: what of a step is the memory sweeps, what the chain
+    CASES = [('xmodal+dropout Tm=%d' % tm, 300, 256, tm, Drop()) for tm in (4, 20, 40, 75, 150, 300)]
+    CASES += [('xmodal Tm=%d' % tm, 300, 256, tm, None) for tm in (4, 75)]
+for (name, T, Dx, Tm, drop) in CASES:
     A = Dm = 256
     x = ops.round_tf32(torch.randn(T, B, Dx, device='cuda'))
     W = ops.round_tf32(torch.randn(Dx + A + H, 4 * H, device='cuda') / (Dx + A + H) ** 0.5)
