@@ -262,9 +262,16 @@ __device__ unsigned long long g_att_trace[16 * 8];
 #endif
 // forward: scores (keys already in ra / rb) -> masked softmax -> alignments (shared memory and `arow` in HBM) ->
 // context.  On return warp w4 == 0 holds the context in ctxv (tf32-rounded unless RAW_CTX).
-template <bool BAHD = false, bool RAW_CTX = false>
+// `hook()` is called once per batch of the two sweeps, right after the next batch's loads have been requested: the caller
+// may use these (load-latency bound) moments for warp-uniform side work - the two-product kernel feeds its slow SS
+// products to the tensor pipe there, two at a time (attn_persist4d.cu; one at a time from twice as many call sites
+// measured slower).
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+template <bool BAHD = false, bool RAW_CTX = false, class Hook = NoHook>
 __device__ __forceinline__ void att_fwd_core(const AttRole& a, const float (&q)[8], const float (&v)[8], uint4 (&ra)[4],
-                                             uint4 (&rb)[4], float* __restrict__ arow, float (&ctxv)[8]) {
+                                             uint4 (&rb)[4], float* __restrict__ arow, float (&ctxv)[8], Hook hook = Hook()) {
   const int lane = a.lane, w4 = a.w4, gt = a.gt, L = a.L;
   float* sc = a.sc;
   float* red = a.red;
@@ -281,6 +288,7 @@ __device__ __forceinline__ void att_fwd_core(const AttRole& a, const float (&q)[
     for (int j = 0; j < 4; ++j) sacc[4 + j] = score8<BAHD>(rb[j], q, v);
 #pragma unroll
     for (int j = 0; j < 4; ++j) rb[j] = ld_row(a.keys, tm0 + 48 + 4 * j, L, a.B, a.b_att, lane);
+    hook();
     const float tot = warp_reduce8(sacc, lane);
     if ((lane & 3) == 0 && tm0 + 4 * jrow < L) sc[tm0 + 4 * jrow] = a.gs * tot;
   }
@@ -328,6 +336,7 @@ __device__ __forceinline__ void att_fwd_core(const AttRole& a, const float (&q)[
     for (int j = 0; j < 4; ++j) axpy8(al[4 + j], rb[j], ctxv);
 #pragma unroll
     for (int j = 0; j < 4; ++j) rb[j] = ld_row(a.values, tm0 + 48 + 4 * j, L, a.B, a.b_att, lane);
+    hook();
   }
   ATT_STAMP(6);
 #pragma unroll

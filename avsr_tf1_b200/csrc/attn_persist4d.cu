@@ -12,14 +12,18 @@
 //
 // Same cluster geometry as attn_persist4.cu (4 CTAs x 8 utterances; a CTA owns 64 hidden units = 256 gate rows, 64
 // attention units and the attention of 2 utterances).  Per CTA:
-//   * recurrent matrix [Wl_att ; Wh] restricted to its gate rows: tile 0 (128 x 512 fp16) in shared memory, tile 1 in
-//     tensor memory (columns 256..511), as before;
+//   * recurrent matrix [Wl_att ; Wh] restricted to its gate rows, split BY K, not by tile: the h half (K = 256) of both
+//     128-row tiles in shared memory (SS products, ~68 clocks per 128 x 16 x 16 MMA: the A operand is read from shared
+//     memory), the attention half of both tiles in tensor memory (columns 256..511; TS products, 8 clocks).  The slow h
+//     half of step t+1 is issued as soon as hs_t has been gathered and runs behind the attention sweeps; only the fast
+//     attention half sits on the critical path after the a_t all-gather (profiles/r02_ap4d_step_trace.txt: the product
+//     went from 1.2 us to 0.2 us of the step);
 //   * its 64 x 512 slice of Wa in tensor memory columns 128..255 as ONE 128-row A operand with K = 256: lanes 0..63
 //     hold the rows that multiply ho, lanes 64..127 the rows that multiply ctx; the B operand has ho in rows 0..7 and
 //     ctx in rows 8..15, so D[u][b] (lanes 0..63, columns 0..7) + D[64+u][8+b] is a_t - half the MMAs of a K = 512
 //     product and exactly the tensor memory that was left;
-//   * 128 accumulator columns shared by both products (they never overlap in time: the recurrent product of step t+1
-//     can only start when a_t has been all-gathered).
+//   * 128 accumulator columns: four accumulators (tile x K parity) for the recurrent product, four for the attention
+//     product (the early h half of step t+1 is in flight while the attention product of step t runs).
 // Exchanges per step (DSMEM st.async + mbarrier complete_tx, all-gathers over the 4 CTAs): {hs_t, ho_t}, ctx_t, a_t.
 // Masks come from the counter-based generator (common.cuh avsr_rand_u32), computed one step ahead of their use.
 #include "ap4_common.cuh"
@@ -123,7 +127,7 @@ template <bool SAMPLE, bool BAHD>
 __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(const DParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sW = base;                          // recurrent tile 0: gate rows of the CTA's units 0..31
+  const uint32_t sW = base;                          // h half (K = 256) of the recurrent matrix, both 128-row tiles
   const uint32_t sOp = sW + W_BYTES;                 // two operand buffers [a (.) m_in | hs], NP rows (rows >= NB zero)
   const uint32_t sQ = sOp + 2 * OP_BYTES;            // [rows 0..7 ho | rows 8..15 ctx] x 256
   const uint32_t sAct = sQ + Q_BYTES;                // [4][NB][UPC] floats; also [NU][4][DM] partial contexts
@@ -158,8 +162,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
   const int T = p.T, B = p.B, Tm = p.Tm;
 
   if (tid == 0) {
-    mbar_init(barM1, THREADS / 32);  // one commit per issuing warp
-    mbar_init(barM2, THREADS / 32);
+    mbar_init(barM1, THREADS / 64);  // one commit per issuing warp: four warps issue each product
+    mbar_init(barM2, THREADS / 64);
     for (int i = 2; i < 8; ++i) mbar_init(sBar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -169,17 +173,17 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
       sWd[i] = v < p.V ? p.Wd[(size_t)(UPC * rank + u) * p.V + v] : 0.0f;
     }
   }
-  // tensor memory (all 512 columns): [0, 128) accumulators (8 x 16 columns, shared by the two products);
-  // [128, 256) Wa slice (paired layout); [256, 512) recurrent tile 1
+  // tensor memory (all 512 columns): [0, 64) accumulators of the recurrent product, [64, 128) of the attention product;
+  // [128, 256) Wa slice (paired layout); [256, 512) attention half of the recurrent matrix (tile m at 256 + 128 m)
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sTmem) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // recurrent tile 0 -> shared memory as fp16: row r = gate*32 + u  <->  Wrec[k][gate*H + 64*rank + u], u < 32
-  for (int seg = warp; seg < KTOT * 4; seg += THREADS / 32) {
-    const int k = seg >> 2, g = seg & 3;
-    const float w = p.Wrec[(size_t)k * 4 * H + g * H + UPC * rank + lane];
-    *reinterpret_cast<__half*>(gen + (sW - base) + sw128h_off(128, g * 32 + lane, k)) = __float2half_rn(w);
+  // h half -> shared memory as fp16: tile mm, row r = gate*32 + u  <->  Wrec[AT + k][gate*H + 64*rank + 32*mm + u], k < H
+  for (int seg = warp; seg < H * 8; seg += THREADS / 32) {
+    const int k = seg >> 3, g = (seg >> 1) & 3, mm = seg & 1;
+    const float w = p.Wrec[(size_t)(AT + k) * 4 * H + g * H + UPC * rank + 32 * mm + lane];
+    *reinterpret_cast<__half*>(gen + (sW - base) + mm * (W_BYTES / 2) + sw128h_off(128, g * 32 + lane, k)) = __float2half_rn(w);
   }
   // operand buffers start as zeros (the padding rows stay zero; no product reads them before they are filled)
   for (int i = tid; i < (2 * OP_BYTES + Q_BYTES) / 4; i += THREADS) reinterpret_cast<uint32_t*>(gen + (sOp - base))[i] = 0u;
@@ -191,16 +195,16 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(sTmem));
   const uint32_t tWa = tmem_base + 128, tW1 = tmem_base + 256;
   {
-    // recurrent tile 1 -> tensor memory: lane r = gate*32 + u <-> unit 32 + u; column c holds K elements 2c, 2c+1.
-    // warp w fills lane quarter (w & 3) = gate, columns 128*(w >> 2) .. +127
+    // attention half -> tensor memory: tile hh at columns 128 hh .. +127; lane r = gate*32 + u <-> unit 32 hh + u; column c
+    // holds K elements 2c, 2c+1 (k < AT).  warp w fills lane quarter (w & 3) = gate of tile w >> 2
     const int q = warp & 3, hh = warp >> 2;
-    const float* col = p.Wrec + q * H + UPC * rank + 32 + lane;
+    const float* col = p.Wrec + q * H + UPC * rank + 32 * hh + lane;
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 32) {
       uint32_t r[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
-        const int k = 2 * (128 * hh + c0 + c);
+        const int k = 2 * (c0 + c);
         r[c] = pack_h2(col[(size_t)k * 4 * H], col[(size_t)(k + 1) * 4 * H]);
       }
       tmem_st32(tW1 + 128 * hh + c0 + ((uint32_t)(32 * q) << 16), r);
@@ -230,44 +234,74 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
 
   // gate-math role: warp <-> (gate g, tile m): the gate rows of units 32*m + lane for all NB utterances
   const int g = warp & 3, m = warp >> 2;
-  // product-issue role (lane 0 of EVERY warp; a tcgen05.mma costs ~80 clocks of its issuing thread).  Recurrent product:
-  // warp (m, j) issues K blocks j (attention half) and 4 + j (h half) of tile m into accumulator 4 m + j.  Attention
-  // product: warp w issues K steps 2 w, 2 w + 1 (of 16) into accumulator w.
-  // (every operand of the issue is derived from warp-uniform values, the issuing lane is elected: see elect_one)
+  // product-issue roles (one elected lane, warp-uniform operands: see elect_one).  Warps with (w & 3) < 2 issue the
+  // recurrent product: warp (m, j) the K blocks j, j + 2 of each half of tile m into accumulator 2 m + j - first the h
+  // half (SS, from shared memory) as soon as hs_t is gathered, later the attention half (TS) and the commit.  Warps with
+  // (w & 3) >= 2 issue the attention product: four K steps (of 16) each into accumulators 4 .. 7.
   const int warp_u = (int)warp_uniform((uint32_t)warp);
   const uint32_t tmem_u = warp_uniform(tmem_base);
   const int jq = warp_u & 3, m_u = warp_u >> 2;
-  const uint32_t acc1 = tmem_u + (4 * m_u + jq) * NP, acc2 = tmem_u + warp_u * NP;
-  const uint32_t tWa_u = tmem_u + 128, tW1_u = tmem_u + 256;
-  const uint64_t dW0 = make_desc_k128(sW), dQ = make_desc_k128(sQ);
+  const int ia = 2 * m_u + (jq & 1);  // index of the warp within its issue group (0..3)
+  const uint32_t acc1 = tmem_u + ia * NP, acc2 = tmem_u + (4 + ia) * NP;
+  const uint32_t tWa_u = tmem_u + 128, tW1_u = tmem_u + 256 + 128 * m_u;
+  const uint64_t dWh = make_desc_k128(sW + m_u * (W_BYTES / 2)), dQ = make_desc_k128(sQ);
   const uint64_t dOp[2] = {make_desc_k128(sOp), make_desc_k128(sOp + OP_BYTES)};
-  auto issue_rec = [&](uint32_t nbuf) {
-    if (elect_one()) {
+  // h half of step t+1 (operand K blocks 4 .. 7; starts the accumulation): eight SS products per issuing warp.  The tensor
+  // pipe takes ~68 clocks for each and queues only a few, so issuing them in one go blocks the warp (and with it its
+  // attention group) for ~1 100 clocks: they are fed two at a time from inside the sweeps, where the warp waits for its
+  // loads anyway (att_fwd_core's hook), and the rest is flushed after the sweeps.
+  int h_next = 8;           // next product of the h half (8 = nothing to issue); warp-uniform
+  uint32_t h_buf = 0u;
+  auto issue_rec_h2 = [&]() {
+    if (h_next < 8) {       // (only ever < 8 in the issuing warps)
+      if (elect_one()) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int kb = 4 * half + jq;
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const uint64_t db = desc_at(dOp[nbuf], kb * (NP * 128) + k4 * 32);
-          const uint32_t acc = (half | k4) ? 1u : 0u;
-          if (m_u == 0) umma_ss(acc1, desc_at(dW0, kb * (128 * 128) + k4 * 32), db, IDESC, acc);
-          else umma_ts(acc1, tW1_u + (kb * 4 + k4) * 8, db, IDESC, acc);
+        for (int e = 0; e < 2; ++e) {
+          const int i = h_next + e, kb = jq + 2 * (i >> 2), k4 = i & 3;
+          umma_ss(acc1, desc_at(dWh, kb * (128 * 128) + k4 * 32), desc_at(dOp[h_buf], (4 + kb) * (NP * 128) + k4 * 32), IDESC,
+                  i ? 1u : 0u);
         }
       }
-      umma_commit(barM1);
+      __syncwarp();
+      h_next += 2;
     }
-    __syncwarp();
+  };
+  auto rec_h_begin = [&](uint32_t nbuf) {
+    if (jq < 2) {
+      h_next = 0;
+      h_buf = nbuf;
+    }
+  };
+  auto rec_h_flush = [&]() {
+    while (h_next < 8) issue_rec_h2();
+  };
+  auto issue_rec_a = [&](uint32_t nbuf) {  // attention half (operand K blocks 0 .. 3) on top, then the commit
+    if (jq < 2) {
+      if (elect_one()) {
+#pragma unroll
+        for (int i2 = 0; i2 < 2; ++i2) {
+          const int kb = jq + 2 * i2;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4)
+            umma_ts(acc1, tW1_u + (kb * 4 + k4) * 8, desc_at(dOp[nbuf], kb * (NP * 128) + k4 * 32), IDESC, 1u);
+        }
+        umma_commit(barM1);
+      }
+      __syncwarp();
+    }
   };
   auto issue_att = [&]() {
-    if (elect_one()) {
+    if (jq >= 2) {
+      if (elect_one()) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int s = 2 * warp_u + i;  // K step of 16: K block s >> 2, 32-byte slice s & 3
-        umma_ts(acc2, tWa_u + s * 8, desc_at(dQ, (s >> 2) * (NP * 128) + (s & 3) * 32), IDESC, i ? 1u : 0u);
+        for (int i2 = 0; i2 < 4; ++i2) {
+          const int s4 = 4 * ia + i2;  // K step of 16: K block s4 >> 2, 32-byte slice s4 & 3
+          umma_ts(acc2, tWa_u + s4 * 8, desc_at(dQ, (s4 >> 2) * (NP * 128) + (s4 & 3) * 32), IDESC, i2 ? 1u : 0u);
+        }
+        umma_commit(barM2);
       }
-      umma_commit(barM2);
+      __syncwarp();
     }
-    __syncwarp();
   };
   const int unit_g = UPC * rank + 32 * m + lane;
   // combine role (threads 0..127): utterance bq, units (hidden and attention) 4*uq .. 4*uq+3 of the CTA
@@ -333,22 +367,19 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     v8[e] = BAHD ? p.v[8 * lane + e] : 0.0f;
     b8[e] = (BAHD && p.batt) ? p.batt[8 * lane + e] : 0.0f;
   }
-  // the attention product's accumulators -> partial planes [K group][part]: warp (grp, q) sums accumulators 4 grp .. +3
+  // the attention product's accumulators -> partial planes [K group][part]: warp (grp, q) sums accumulators 4 + 2 grp, + 1
   // of lane quarter q; part 0 = lanes 0..63, part 1 = lanes 64..127 (Luong: the ctx rows, B columns 8..15; BAHD: Wq^T)
   auto att_epilogue = [&]() {
     const int grp = warp >> 2, q = warp & 3;
-    const uint32_t a0 = tmem_base + ((uint32_t)(32 * q) << 16) + (4 * grp) * NP + ((!BAHD && q >= 2) ? 8 : 0);
-    uint32_t r0[8], r1[8], r2[8], r3[8];
+    const uint32_t a0 = tmem_base + ((uint32_t)(32 * q) << 16) + (4 + 2 * grp) * NP + ((!BAHD && q >= 2) ? 8 : 0);
+    uint32_t r0[8], r1[8];
     tmem_ld8(a0, r0);
     tmem_ld8(a0 + NP, r1);
-    tmem_ld8(a0 + 2 * NP, r2);
-    tmem_ld8(a0 + 3 * NP, r3);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     float* ap = apart + ((grp * 2 + (q >> 1)) * NB) * UPC + 32 * (q & 1) + lane;
 #pragma unroll
-    for (int b = 0; b < NB; ++b)
-      ap[b * UPC] = (__uint_as_float(r0[b]) + __uint_as_float(r1[b])) + (__uint_as_float(r2[b]) + __uint_as_float(r3[b]));
+    for (int b = 0; b < NB; ++b) ap[b * UPC] = __uint_as_float(r0[b]) + __uint_as_float(r1[b]);
   };
   for (int t = 0; t < T; ++t) {
 #ifdef AP4D_TRACE
@@ -369,16 +400,13 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
       mbar_wait(barM1, (t - 1) & 1);
       AP4D_STAMP(1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t r1[8], r2[8], r3[8];
-      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 0) * NP, r);
-      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 1) * NP, r1);
-      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 2) * NP, r2);
-      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (4 * m + 3) * NP, r3);
+      uint32_t r1[8];
+      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (2 * m + 0) * NP, r);
+      tmem_ld8(tmem_base + ((uint32_t)(32 * g) << 16) + (2 * m + 1) * NP, r1);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int b = 0; b < 8; ++b)
-        r[b] = __float_as_uint((__uint_as_float(r[b]) + __uint_as_float(r1[b])) + (__uint_as_float(r2[b]) + __uint_as_float(r3[b])));
+      for (int b = 0; b < 8; ++b) r[b] = __float_as_uint(__uint_as_float(r[b]) + __uint_as_float(r1[b]));
     } else {
 #pragma unroll
       for (int b = 0; b < 8; ++b) r[b] = 0u;  // att_{-1} = 0; h_0 Wh is already in the x-projection
@@ -473,14 +501,17 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     AP4D_STAMP(4);
     mbar_wait(hbar_n, (t >> 1) & 1);  // every CTA's hs_t / ho_t slices have landed
     AP4D_STAMP(5);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // h half of the recurrent product of step t+1: behind the sweeps (BAHD: behind the query product, which the sweeps wait for)
+    if (!BAHD && t + 1 < T) rec_h_begin(nb);
 
     if constexpr (BAHD) {
       // [ho Wl_h | ho Wq] for the CTA's units as soon as ho_t is there; the pq slices go to the owners of the utterances
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       issue_att();
       mbar_wait(barM2, t & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (t + 1 < T) rec_h_begin(nb);
       att_epilogue();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (comb) {
@@ -513,8 +544,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
         const uint4 qraw = *reinterpret_cast<const uint4*>(gen + (sQ - base) + sw128h_off(NP, bl_att, 8 * lane));
         unpack_q(qraw, q);
       }
-      att_fwd_core<BAHD, BAHD>(role, q, v8, ra, rb, p.align + ((size_t)t * B + b_att) * Tm, ctxv);
+      att_fwd_core<BAHD, BAHD>(role, q, v8, ra, rb, p.align + ((size_t)t * B + b_att) * Tm, ctxv, issue_rec_h2);
     }
+    rec_h_flush();
     AP4D_STAMP(6);
     if (BAHD && w4 == 0) {
       // projected context ctx' = sum_t a_t PV_t: slices to the owners of the attention units (fp32)
@@ -677,7 +709,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
     if (t + 1 < T) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      issue_rec(nb);
+      issue_rec_a(nb);
     }
     AP4D_STAMP(11);
   }
