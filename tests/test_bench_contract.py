@@ -45,3 +45,29 @@ def test_reference_arm_parity_graph_and_nonzero_rank():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--config', '1',
                           '--gpus', '2'], capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ''
+
+
+def test_roofline_arithmetic_matches_survey_8d():
+    """The algorithmic bytes / FLOP that `roofline` divides by are SURVEY.md 8d's per-unit figures times the units of one
+    step (no GPU needed: the kernel times are given)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Args:
+        video_input = 'crops3888'
+    ms = {'attn_lstm_fwd': 3.0, 'attn_lstm_bwd': 3.0, 'lstm_fwd': 2.0, 'lstm_bwd': 1.0, 'gemm': 2.5}
+    n = {'attn_lstm_fwd': 2, 'attn_lstm_bwd': 2, 'lstm_fwd': 5, 'lstm_bwd': 5, 'gemm': 39}
+    gate = {'frac': 0.5, 'achieved': 350.0, 'peak': 700.0}
+    roof, tensor = bench.attention_roofline(Args(), 256, 'default', ms, n, gate)
+    # 4 Tm (A + Dm) + 4 (Tm + Dm + A) bytes per (utterance, query step): 155 948 B at Tm = 75, 617 648 B at Tm = 300
+    per_dir = 256 * (300 * 155948 + 41 * 617648)
+    assert roof['algorithmic_bytes_per_step'] == 2 * per_dir
+    assert roof['once_per_utterance_bytes_per_step'] == 2 * 256 * 4 * (75 + 300) * 512
+    assert abs(roof['achieved'] - 2 * per_dir / 6e-3 / 1e9) < 1e-3 * roof['achieved']
+    assert abs(roof['frac'] - roof['achieved'] / roof['peak']) < 1e-3
+    assert roof['bound'] == 'hbm' and roof['unit'] == 'GB/s'
+    # matrix-product FLOP of a training step per utterance: dominated by 3 x 2 (I + H) 4H per (layer, step)
+    f5 = bench.train_flop_per_utterance(5, 3888)
+    lower = 3 * 2 * 4 * 256 * (75 * (3888 + 256) + 2 * 75 * 512 + 300 * (80 + 256) + 300 * 512 + 300 * 768 + 41 * (128 + 512))
+    assert lower <= f5 <= 1.1 * lower
+    assert bench.train_flop_per_utterance(1, 128) < 0.1 * f5
