@@ -648,32 +648,35 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
         if (tid == 0) mbar_expect_tx(barL, (uint32_t)__popc(selmask) * SAMP_VP * 4 * CL);
         mbar_wait(barL, lphase & 1);
         ++lphase;
-        if (((selmask >> warp) & 1u) && lane == 0) {
-          // inverse CDF of the fp32 softmax, summed in class order (the arithmetic of sched_sample_kernel, misc.cu)
-          float z[SAMP_VP];
-          float mx = -INFINITY;
-          for (int v = 0; v < p.V; ++v) {
-            z[v] = p.bd[v] + ((sLg[(0 * NB + warp) * SAMP_VP + v] + sLg[(1 * NB + warp) * SAMP_VP + v]) +
-                              (sLg[(2 * NB + warp) * SAMP_VP + v] + sLg[(3 * NB + warp) * SAMP_VP + v]));
-            mx = fmaxf(mx, z[v]);
-          }
-          float total = 0.0f;
-          for (int v = 0; v < p.V; ++v) total += expf(z[v] - mx);
-          const float u01 = (float)(avsr_rand_u32(seed, rstep, p.ss_stream + 1u, (uint32_t)t, (uint32_t)(b0 + warp)) >> 8) * (1.0f / 16777216.0f);
-          const float target = u01 * total;
-          float cum = 0.0f;
-          int pick = p.V - 1;
-          for (int v = 0; v < p.V; ++v) {
-            cum += expf(z[v] - mx);
-            if (cum > target) {
-              pick = v;
-              break;
+        if ((selmask >> warp) & 1u) {
+          // inverse CDF of the fp32 softmax, summed in class order (the arithmetic of sched_sample_kernel, misc.cu): lane v
+          // forms exp(z_v - max) of its class, lane 0 adds them in class order (same values, same order; sX is free here)
+          const float zv = lane < p.V ? p.bd[lane] + ((sLg[(0 * NB + warp) * SAMP_VP + lane] + sLg[(1 * NB + warp) * SAMP_VP + lane]) +
+                                                      (sLg[(2 * NB + warp) * SAMP_VP + lane] + sLg[(3 * NB + warp) * SAMP_VP + lane]))
+                                      : -INFINITY;
+          const float mx = warp_max(zv);
+          float* sE = sX + warp * SAMP_VP;
+          sE[lane] = lane < p.V ? expf(zv - mx) : 0.0f;
+          __syncwarp();
+          if (lane == 0) {
+            float total = 0.0f;
+            for (int v = 0; v < p.V; ++v) total += sE[v];
+            const float u01 = (float)(avsr_rand_u32(seed, rstep, p.ss_stream + 1u, (uint32_t)t, (uint32_t)(b0 + warp)) >> 8) * (1.0f / 16777216.0f);
+            const float target = u01 * total;
+            float cum = 0.0f;
+            int pick = p.V - 1;
+            for (int v = 0; v < p.V; ++v) {
+              cum += sE[v];
+              if (cum > target) {
+                pick = v;
+                break;
+              }
             }
-          }
-          sPick[warp] = pick;
-          if (rank == 0) {
-            p.sample_ids[(size_t)t * B + b0 + warp] = pick;
-            p.used_ids[(size_t)(t + 1) * B + b0 + warp] = pick;
+            sPick[warp] = pick;
+            if (rank == 0) {
+              p.sample_ids[(size_t)t * B + b0 + warp] = pick;
+              p.used_ids[(size_t)(t + 1) * B + b0 + warp] = pick;
+            }
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -691,9 +694,17 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_fwd_kernel(con
             if (rank == 0) p.x[((size_t)(t + 1) * B + b0 + bb) * p.E + e] = xv;
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
+          // (16 weight loads in flight per thread: the column walk is 4 KB-strided L2 traffic; same summation order)
           float acc = bias_row;
-#pragma unroll 8
-          for (int e = 0; e < p.E; ++e) acc = fmaf(sX[e], wxcol[(size_t)e * 4 * H], acc);
+          int e0 = 0;
+          for (; e0 + 16 <= p.E; e0 += 16) {
+            float wv[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) wv[k] = __ldg(wxcol + (size_t)(e0 + k) * 4 * H);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc = fmaf(sX[e0 + k], wv[k], acc);
+          }
+          for (; e0 < p.E; ++e0) acc = fmaf(sX[e0], wxcol[(size_t)e0 * 4 * H], acc);
 #pragma unroll
           for (int b = 0; b < NB; ++b)
             if (b == bb) gx[b] = (t + 1 < len_a[b]) ? acc : 0.0f;

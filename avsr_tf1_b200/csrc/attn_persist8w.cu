@@ -538,9 +538,17 @@ __global__ void __launch_bounds__(THREADS, 1) wlas_persist8_fwd_kernel(const WFw
             if (rank == 0) p.x[((size_t)(t + 1) * B + b0 + bb) * p.E + e] = xv;
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
+          // (16 weight loads in flight per thread: the column walk is 4 KB-strided L2 traffic; same summation order)
           float acc = bias_row;
-#pragma unroll 8
-          for (int e = 0; e < p.E; ++e) acc = fmaf(sX[e], wxcol[(size_t)e * 4 * H], acc);
+          int e0 = 0;
+          for (; e0 + 16 <= p.E; e0 += 16) {
+            float wv[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) wv[k] = __ldg(wxcol + (size_t)(e0 + k) * 4 * H);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc = fmaf(sX[e0 + k], wv[k], acc);
+          }
+          for (; e0 < p.E; ++e0) acc = fmaf(sX[e0], wxcol[(size_t)e0 * 4 * H], acc);
           if ((bb >> 3) == hf) {
 #pragma unroll
             for (int b = 0; b < 8; ++b)
