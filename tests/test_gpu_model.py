@@ -226,7 +226,7 @@ def test_padding_invariance_full_size():
 
 @pytest.mark.parametrize('cfg,algo', [(1, 'greedy'), (5, 'greedy'), (1, 'beam_search'), (4, 'beam_search'),
                                       (5, 'beam_search'), (-4, 'greedy'), (-4, 'beam_search'),
-                                      (-1, 'greedy'), (-1, 'beam_search')])
+                                      (-1, 'greedy'), (-1, 'beam_search'), (-3, 'greedy')])
 def test_decoding_and_error_rates(cfg, algo):
     """ids from greedy / beam search equal the oracle's; CER / WER computed from them are
     bit-identical (integer Levenshtein, avsr/utils.py)."""
@@ -235,7 +235,9 @@ def test_decoding_and_error_rates(cfg, algo):
     old = ops.set_tensor_cores(False)  # exact fp32 so arg-max / top-k decisions are reproducible
     try:
         # -4: the bimodal decoder with the video stream missing; -1: the decoder without attention
-        over = dict(video_processing=None) if cfg == -4 else dict(enable_attention=False) if cfg == -1 else {}
+        # -3: highway encoder + one-hot decoder inputs
+        over = dict(video_processing=None) if cfg == -4 else dict(enable_attention=False) if cfg == -1 else \
+            dict(highway_encoder=True, embedding_size=0) if cfg == -3 else {}
         hp = config_hparams(abs(cfg), decoding_algorithm=algo, beam_width=4 if algo == 'beam_search' else 10, **over)
         hp.max_label_length = 12
         batch = synthetic_batch(hp, B=3, Ta=30, Tv=10, L=6, ragged=True)
