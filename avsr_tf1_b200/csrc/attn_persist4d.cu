@@ -934,10 +934,13 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bwd_kernel(con
   const uint32_t att_bar_id = 2 + jl;
   const AttRole role = {p.keys, p.values, L, B, b_att, Tm, w4, gt, lane, gs, att_bar_id, nullptr, part, red};
   const float vzero8[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-  // product-issue / reduce-scatter roles
+  // product-issue / reduce-scatter roles (issue: elected lane, warp-uniform operands - see elect_one)
   const int q = warp & 3;
-  const int mt_i = warp >> 1, hj_i = warp & 1;
-  const uint32_t acc_i = tmem_base + (2 * mt_i + hj_i) * NP;
+  const int warp_u = (int)warp_uniform((uint32_t)warp);
+  const uint32_t tmem_u = warp_uniform(tmem_base);
+  const int mt_i = warp_u >> 1, hj_i = warp_u & 1;
+  const uint32_t acc_i = tmem_u + (2 * mt_i + hj_i) * NP;
+  const uint32_t tWaT_u = tmem_u + 128, tA_u = tmem_u + 256;
 
   float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // bias gradient of this thread's unit
   load_step(T - 1);
@@ -1003,11 +1006,11 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bwd_kernel(con
     asm volatile("bar.sync 1, 256;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- (B) product 2: d[ho | ctx] partial from the CTA's 64 attention units ------------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         const int s4 = 2 * hj_i + kk;  // K step of 16 attention units
-        umma_ts(acc_i, tWaT + 32 * mt_i + s4 * 8, desc_at(dDa, s4 * 32), IDESC, kk ? 1u : 0u);
+        umma_ts(acc_i, tWaT_u + 32 * mt_i + s4 * 8, desc_at(dDa, s4 * 32), IDESC, kk ? 1u : 0u);
       }
       umma_commit(barMma2);
     }
@@ -1130,7 +1133,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bwd_kernel(con
       mbar_wait(barDz, it & 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
@@ -1140,7 +1143,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bwd_kernel(con
             if (mt_i < 2)
               umma_ss(acc_i, desc_at(dWt, mt_i * BW_TILE_BYTES + kb * (128 * 128) + k4 * 32), db, IDESC, (kk | k4) ? 1u : 0u);
             else
-              umma_ts(acc_i, tA + (mt_i - 2) * 128 + (kb * 4 + k4) * 8, db, IDESC, (kk | k4) ? 1u : 0u);
+              umma_ts(acc_i, tA_u + (mt_i - 2) * 128 + (kb * 4 + k4) * 8, db, IDESC, (kk | k4) ? 1u : 0u);
           }
         umma_commit(barMma);
       }
