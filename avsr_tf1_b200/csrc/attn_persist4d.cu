@@ -1403,11 +1403,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bahd_bwd_kerne
   }
   // product roles: product 2: warp (mt_b, ks_b) issues K step ks_b of both halves of tile mt_b and reduce-scatters the tile's
   // lane quarter q; product 1: warp (mt_i, hj_i) as in the Luong kernel
+  // (issue: elected lane, warp-uniform operands - see elect_one)
   const int q = warp & 3;
-  const int mt_b = warp >> 2, ks_b = warp & 3;
-  const uint32_t acc_b = tmem_base + warp * NP;
-  const int mt_i = warp >> 1, hj_i = warp & 1;
-  const uint32_t acc_i = tmem_base + (2 * mt_i + hj_i) * NP;
+  const int warp_u = (int)warp_uniform((uint32_t)warp);
+  const uint32_t tmem_u = warp_uniform(tmem_base);
+  const int mt_b = warp_u >> 2, ks_b = warp_u & 3;
+  const uint32_t acc_b = tmem_u + warp_u * NP;
+  const int mt_i = warp_u >> 1, hj_i = warp_u & 1;
+  const uint32_t acc_i = tmem_u + (2 * mt_i + hj_i) * NP;
+  const uint32_t tB2_u = tmem_u + 128, tA_u = tmem_u + 256;
 
   float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   load_step(T - 1);
@@ -1479,7 +1483,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bahd_bwd_kerne
     asm volatile("bar.sync 1, 256;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- (B) product 2, da half: d ho partial from the CTA's 64 attention units (the dpq half follows the sweeps) -----
-    if (lane == 0) umma_ts(acc_b, tB2 + 64 * mt_b + ks_b * 8, desc_at(dDa, ks_b * 32), IDESC, 0u);
+    if (elect_one()) umma_ts(acc_b, tB2_u + 64 * mt_b + ks_b * 8, desc_at(dDa, ks_b * 32), IDESC, 0u);
     __syncwarp();
     if (it > 0) {
       mbar_wait(barRedH, (it - 1) & 1);
@@ -1527,8 +1531,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bahd_bwd_kerne
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("bar.sync 1, 256;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (lane == 0) {
-      umma_ts(acc_b, tB2 + 64 * mt_b + 32 + ks_b * 8, desc_at(dDp, ks_b * 32), IDESC, 1u);
+    if (elect_one()) {
+      umma_ts(acc_b, tB2_u + 64 * mt_b + 32 + ks_b * 8, desc_at(dDp, ks_b * 32), IDESC, 1u);
       umma_commit(barMma2);
     }
     __syncwarp();
@@ -1590,7 +1594,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bahd_bwd_kerne
       mbar_wait(barDz, it & 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
@@ -1600,7 +1604,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_lstm_persist4d_bahd_bwd_kerne
             if (mt_i < 2)
               umma_ss(acc_i, desc_at(dWt, mt_i * BW_TILE_BYTES + kb * (128 * 128) + k4 * 32), db, IDESC, (kk | k4) ? 1u : 0u);
             else
-              umma_ts(acc_i, tA + (mt_i - 2) * 128 + (kb * 4 + k4) * 8, db, IDESC, (kk | k4) ? 1u : 0u);
+              umma_ts(acc_i, tA_u + (mt_i - 2) * 128 + (kb * 4 + k4) * 8, db, IDESC, (kk | k4) ? 1u : 0u);
           }
         umma_commit(barMma);
       }

@@ -189,25 +189,29 @@ __global__ void __launch_bounds__(THREADS, 1) wlas_persist8_fwd_kernel(const WFw
   // gate-math role: gate g = lane quarter, unit = lane, utterances 8*hf .. 8*hf+7
   const int g = warp & 3, hf = warp >> 2;
   const int unit_g = UP8 * rank + lane;
-  const uint32_t acc_w = tmem_base + warp * NP;  // every warp issues into its own accumulator
+  // (issue: elected lane, warp-uniform operands - ap4_common.cuh elect_one)
+  const int warp_u = (int)ap4::warp_uniform((uint32_t)warp);
+  const uint32_t tmem_u = ap4::warp_uniform(tmem_base);
+  const uint32_t acc_w = tmem_u + warp_u * NP;  // every warp issues into its own accumulator
+  const uint32_t tW_u = tmem_u + 128;
   const uint64_t dWa = make_desc_k128(sWa), dQ = make_desc_k128(sQ);
   const uint64_t dOp[2] = {make_desc_k128(sOp), make_desc_k128(sOp + OP8_BYTES)};
   auto issue_rec = [&](uint32_t nbuf) {  // K steps 6 w .. 6 w + 5 of 48
-    if (lane == 0) {
+    if (ap4::elect_one()) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        const int ks = 6 * warp + i;
-        umma_ts(acc_w, tW + ks * 8, desc_at(dOp[nbuf], (ks >> 2) * (NB8 * 128) + (ks & 3) * 32), IDESC, i ? 1u : 0u);
+        const int ks = 6 * warp_u + i;
+        umma_ts(acc_w, tW_u + ks * 8, desc_at(dOp[nbuf], (ks >> 2) * (NB8 * 128) + (ks & 3) * 32), IDESC, i ? 1u : 0u);
       }
       umma_commit(barM1);
     }
     __syncwarp();
   };
   auto issue_att = [&]() {  // K steps 2 w, 2 w + 1 of 16
-    if (lane == 0) {
+    if (ap4::elect_one()) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const int ks = 2 * warp + i;
+        const int ks = 2 * warp_u + i;
         umma_ss(acc_w, desc_at(dWa, (ks >> 2) * (128 * 128) + (ks & 3) * 32), desc_at(dQ, (ks >> 2) * (NB8 * 128) + (ks & 3) * 32),
                 IDESC, i ? 1u : 0u);
       }
@@ -769,6 +773,8 @@ __global__ void __launch_bounds__(THREADS, 1) wlas_persist8_bwd_kernel(const WBw
   const AttRole role1 = {p.keys[1], p.pv[1], L1, B, b_att, p.Tm[1], w4, gt, lane, p.scaled[1] ? p.g[1][0] : 1.0f, att_bar_id, nullptr, part, red};
   const float vzero8[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   const int q = warp & 3, hf = warp >> 2;
+  const int warp_u = (int)ap4::warp_uniform((uint32_t)warp);  // (issue: elected lane, warp-uniform operands)
+  const uint32_t tmem_u = ap4::warp_uniform(tmem_base), tA_u = tmem_u + 128;
 
   float bsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   load_step(T - 1);
@@ -835,8 +841,9 @@ __global__ void __launch_bounds__(THREADS, 1) wlas_persist8_bwd_kernel(const WBw
     asm volatile("bar.sync 1, 256;" ::: "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // ---- (B) product 2: d ho partial from the CTA's 64 attention units; warp (tile hf, K step q) ----------------------
-    if (lane == 0) {
-      umma_ss(tmem_base + warp * NP, desc_at(dWt, hf * (128 * 128) + q * 32), desc_at(dDa, q * 32), IDESC, 0u);
+    if (ap4::elect_one()) {
+      umma_ss(tmem_u + warp_u * NP, desc_at(dWt, (warp_u >> 2) * (128 * 128) + (warp_u & 3) * 32), desc_at(dDa, (warp_u & 3) * 32),
+              IDESC, 0u);
       umma_commit(barMma2);
     }
     __syncwarp();
@@ -942,14 +949,16 @@ __global__ void __launch_bounds__(THREADS, 1) wlas_persist8_bwd_kernel(const WBw
       mbar_wait(barDz, it & 1);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0 && warp < 6) {
+      if (warp_u < 6) {
+        if (ap4::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_ts(tmem_base + warp * NP, tA + 64 * warp + ks * 8, desc_at(dDz, (ks >> 2) * (NB8 * 128) + (ks & 3) * 32), IDESC,
-                  ks ? 1u : 0u);
-        umma_commit(barMma);
+          for (int ks = 0; ks < 8; ++ks)
+            umma_ts(tmem_u + warp_u * NP, tA_u + 64 * warp_u + ks * 8, desc_at(dDz, (ks >> 2) * (NB8 * 128) + (ks & 3) * 32), IDESC,
+                    ks ? 1u : 0u);
+          umma_commit(barMma);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
 #pragma unroll
     for (int j = 0; j < PB; ++j) {
