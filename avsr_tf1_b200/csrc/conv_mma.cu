@@ -80,7 +80,7 @@ __device__ __forceinline__ void load_frames(float* sX, const float* __restrict__
     const int c4n = Cin >> 2;
     const int total = nf * hw * c4n;
     const float4* src = reinterpret_cast<const float4*>(x + (size_t)f0 * hw * Cin);
-    constexpr int U = 4;  // loads in flight per thread
+    constexpr int U = 8;  // loads in flight per thread (HBM latency x bandwidth needs ~32 KB per CTA in flight)
     for (int i0 = tid; i0 < total; i0 += U * THREADS) {
       float4 v[U];
 #pragma unroll
