@@ -256,9 +256,10 @@ class Seq2SeqUnimodalDecoder(object):
         """BeamSearchDecoder(beam_width, length_penalty_weight) + gather_tree
         (decoder_unimodal.py:222-271).  Returns beam 0 ids [B, T]."""
         ctx, hp = self._ctx, self._hparams
-        if hp.write_attention_alignment:
-            raise NotImplementedError('alignment images are produced by greedy decoding here: the reference reads '
-                                      'cell_state.alignment_history[0] of the beam-search state, which is not a history')
+        # Alignment images under beam search: the reference's own branch (decoder_unimodal.py:277-280) subscripts the
+        # TensorArray `cell_state.alignment_history` of a state that BeamSearchDecoder never reorders and cannot run in
+        # TF 1.13.  Provided here as what that branch is after: the alignments of the WINNING hypothesis, traced back along
+        # the beam parents like its ids (gather_tree), in the layout of the greedy images [B, Tm, T, 1].
         W = hp.beam_width
         B = memories[0][0].shape[1]
         init = self._initial_state_fwd(encoder_states)
@@ -278,10 +279,14 @@ class Seq2SeqUnimodalDecoder(object):
         active = torch.ones(B * W, dtype=torch.int32, device='cuda')
         base = (torch.arange(B, device='cuda', dtype=torch.int32) * W).view(B, 1)
         words, parents, scores = [], [], []
+        history = [[] for _ in bufs] if (hp.write_attention_alignment and bufs) else None
         for _ in range(hp.max_label_length):
             x = ops.empty(1, B * W, self._E)
             ops.embedding_fwd(self._table(), ids, x)
             out, (c, S) = self._cell.step(x, active, bufs, (c, S))
+            if history is not None:  # alignments of every live hypothesis at this step, by beam slot BEFORE the re-ranking
+                for k, mb in enumerate(bufs):
+                    history[k].append(mb.align[0].clone())
             logits = self._logits_step(out)
             word = torch.empty((B, W), dtype=torch.int32, device='cuda')
             parent = torch.empty((B, W), dtype=torch.int32, device='cuda')
@@ -309,6 +314,22 @@ class Seq2SeqUnimodalDecoder(object):
             scores=torch.stack(scores, 0).cpu().numpy().transpose(1, 0, 2),
             predicted_ids=step_ids.transpose(1, 0, 2).astype(np.int32),
             parent_ids=parent_ids.transpose(1, 0, 2).astype(np.int32))
+        if history is not None:
+            al = []
+            for h in history:
+                A = torch.stack(h, 0).cpu().numpy()           # [T, B*W, Tm]
+                T_, Tm = A.shape[0], A.shape[2]
+                A = A.reshape(T_, B, W, Tm)
+                out_al = np.zeros((B, Tm, T_, 1), A.dtype)
+                for b in range(B):
+                    ml = int(min(max_len[b], T_))
+                    slot = 0                                   # winning hypothesis = beam 0 after the last re-ranking
+                    for lvl in range(ml - 1, -1, -1):
+                        slot = int(parent_ids[lvl, b, slot])   # the slot it occupied when step lvl ran
+                        out_al[b, :, lvl, 0] = A[lvl, b, slot]
+                al.append(out_al)
+            self.attention_alignment = al[0] if len(al) == 1 else al
+            self.attention_summary = 1.0 - al[0] if len(al) == 1 else [1.0 - a for a in al]
         return self.inference_predicted_ids
 
     def get_predictions(self):

@@ -306,3 +306,52 @@ def test_other_optimisers(optimiser, tensor_cores):
     if optimiser == 'AdamW':  # the decay is visible: a bias-free kernel shrinks by about 3 * weight_decay
         k = 'Decoder/decoder/my_dense/kernel'
         assert abs(np.abs(got[k]).sum() / np.abs(P0[k]).sum() - (1 - 3e-2)) < 5e-3
+
+
+@pytest.mark.parametrize('cfg', [1, 4, 5])
+def test_alignment_images_under_beam_search(cfg):
+    """write_attention_alignment with beam search: the alignments of the winning hypothesis, traced back along the beam
+    parents (the reference's own branch, decoder_unimodal.py:277-280, cannot run in TF 1.13).  Pinned by teacher forcing:
+    feeding the winning ids to the training graph (no dropout, no sampling) walks the same prefixes, so its alignments
+    must equal the traced ones step for step."""
+    from avsr_tf1_b200 import ops
+    from avsr_tf1_b200.seq2seq import Seq2SeqModel
+    old = ops.set_tensor_cores(False)
+    try:
+        # (no input batch norm: the training graph normalises with batch statistics, inference with the moving ones)
+        hp = config_hparams(cfg, decoding_algorithm='beam_search', beam_width=4, write_attention_alignment=True,
+                            batch_normalisation=False)
+        hp.max_label_length = 10
+        batch = synthetic_batch(hp, B=3, Ta=30, Tv=10, L=6, ragged=True)
+        ds = to_data_sequences(batch)
+        train = Seq2SeqModel(ds, 'train', hp, seed=2001)
+        train.train_step(ds)
+        beam = Seq2SeqModel(ds, 'evaluate', hp, share_params_with=train)
+        ids = beam.predict(ds)
+        al = beam._decoder.attention_alignment
+        al = al if isinstance(al, list) else [al]
+        eos = {v: k for k, v in hp.unit_dict.items()}['EOS']
+        steps = []
+        for row in ids:  # steps up to and including the first EOS (gather_tree pads with EOS afterwards)
+            hit = np.nonzero(row == eos)[0]
+            steps.append(int(hit[0]) + 1 if hit.size else len(row))
+        L = max(steps)
+        forced = dict(batch)
+        forced['labels'] = np.zeros((3, L), np.int32)
+        for b in range(3):
+            forced['labels'][b, :steps[b]] = ids[b, :steps[b]]
+        forced['labels_len'] = np.asarray(steps, np.int32)
+        train.feed(to_data_sequences(forced))
+        train._set_step_scalars()
+        train.forward_backward()
+        assert len(al) == len(train._decoder._cell.bufs)
+        for a_b, mb in zip(al, train._decoder._cell.bufs):
+            ref = mb.align.cpu().numpy()  # [T, B, Tm]
+            assert a_b.ndim == 4 and a_b.shape[0] == 3 and a_b.shape[3] == 1 and a_b.shape[1] == ref.shape[2]
+            for b in range(3):
+                n = min(steps[b], a_b.shape[2])
+                assert n > 0
+                np.testing.assert_allclose(a_b[b, :, :n, 0].sum(axis=0), 1.0, atol=1e-4)
+                np.testing.assert_allclose(a_b[b, :, :n, 0], ref[:n, b, :].T, atol=2e-5)
+    finally:
+        ops.set_tensor_cores(old)
