@@ -11,7 +11,7 @@ import torch
 from . import ops
 from .attention import add_attention
 from .cells import build_rnn_layers
-from .layers import BatchNormInput, BuildContext, LSTMLayerOp
+from .layers import BatchNormInput, BuildContext, InstanceNormInput, LSTMLayerOp
 
 
 class EncoderData(collections.namedtuple("EncoderData", ("outputs", "final_state", "outputs_operand"))):
@@ -107,9 +107,8 @@ class Seq2SeqEncoder(object):
         self._F = int(feature_dim if feature_dim is not None else np.prod(tuple(data.inputs.shape[2:])))
         # Action-Unit regression head (encoder.py:28-29, 173-189): train mode only
         self._regress_aus = bool(kwargs.get('regress_aus', False)) and mode == 'train'
-        if hparams.instance_normalisation:
-            raise NotImplementedError('instance_normalisation is off in every reference config')
         self._bn = BatchNormInput(ctx, scope, self._F) if hparams.batch_normalisation is True else None
+        self._inorm = InstanceNormInput(ctx, scope, self._F) if hparams.instance_normalisation is True else None
         self._dense = None  # _maybe_add_dense_layers (encoder.py:148-171); default (0,) = identity (avsr.py:38)
         self._rnn_in = self._F
         if hparams.input_dense_layers[0] > 0:
@@ -191,7 +190,9 @@ class Seq2SeqEncoder(object):
         else:
             if batch_major:
                 inputs = ops.transpose01(inputs)
-            x = ops.round_tf32(inputs) if ops.tensor_cores_enabled() else inputs
+            x = inputs if self._inorm is not None else (ops.round_tf32(inputs) if ops.tensor_cores_enabled() else inputs)
+        if self._inorm is not None:  # instance_norm on the (batch-normalised) features (encoder.py:51-55)
+            x = self._inorm.forward(x)
         return self._dense.forward(x) if self._dense is not None else x
 
     def _layer0_ops(self):
@@ -200,8 +201,10 @@ class Seq2SeqEncoder(object):
 
     def _layer0_drops_input(self):
         """True when the gradient wrt the normalised features has to be formed explicitly (dgamma / dbeta cannot be read
-        off the layer-0 weight gradient): layer 0 drops its input, or a dense stack sits between the two."""
-        if self._mode == 'train' and (self._dense is not None or getattr(self, 'explicit_bn_backward', False)):
+        off the layer-0 weight gradient): layer 0 drops its input, or a dense stack / the instance normalisation sits between
+        the two."""
+        if self._mode == 'train' and (self._dense is not None or self._inorm is not None or
+                                      getattr(self, 'explicit_bn_backward', False)):
             return True  # (explicit_bn_backward: set by Seq2SeqModel._guard_bn_shortcut when a gamma came close to zero)
         return self._mode == 'train' and any(op.drop is not None and op.drop.thr_in for op in self._layer0_ops())
 
@@ -377,6 +380,8 @@ class Seq2SeqEncoder(object):
         normalised features is only formed when the caller asks for the gradient wrt the raw features."""
         if self._dense is not None and dx is not None:
             dx = self._dense.backward(dx)
+        if self._inorm is not None and dx is not None:
+            dx = self._inorm.backward(dx)
         if self._bn is None:
             return dx
         if self._layer0_drops_input() and not self.input_gradient:

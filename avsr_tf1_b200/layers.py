@@ -185,6 +185,48 @@ class BatchNormInput:
         return dx
 
 
+class InstanceNormInput:
+    """tf.contrib.layers.instance_norm(inputs) on the [B,T,F] features (encoder.py:51-55; TF 1.13 defaults: center, scale,
+    epsilon 1e-6): moments over the time axis of every (utterance, feature), padded frames included; gamma / beta per
+    feature.  Frame-major [T,B,F] is a [T, B*F] matrix whose COLUMN statistics are exactly these moments, so the batch-norm
+    kernels serve it with gamma / beta tiled over the utterances (no moving statistics: the same in training and inference;
+    nothing to exchange under data parallelism)."""
+    EPS = 1e-6
+
+    def __init__(self, ctx: BuildContext, scope: str, F: int):
+        self.ctx, self.F = ctx, F
+        self.beta = ctx.declare(f'{scope}/InstanceNorm/beta', (F,), 'zeros')
+        self.gamma = ctx.declare(f'{scope}/InstanceNorm/gamma', (F,), 'ones')
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x [T,B,F] frame-major -> normalised features, a product operand (tf32-rounded in tensor-core mode)."""
+        ctx = self.ctx
+        T, B, F = x.shape
+        x2 = x.contiguous().view(T, B * F)
+        sums = ops.zeros(2 * B * F)
+        ops.bn_stats(x2, sums)
+        self.gamma_t = ctx.p(self.gamma).repeat(B)
+        beta_t = ctx.p(self.beta).repeat(B)
+        y = ops.empty(T, B, F)
+        self.xhat, self.invstd = ops.empty(T, B * F), ops.empty(B * F)
+        ops.bn_apply_train(x2, sums, float(T), self.gamma_t, beta_t, self.EPS, 0.0, y.view(T, B * F), self.xhat, self.invstd,
+                           None, None)
+        return y
+
+    def backward(self, dy: torch.Tensor) -> torch.Tensor:
+        ctx = self.ctx
+        T, B, F = dy.shape
+        dy2 = dy.contiguous().view(T, B * F)
+        sums2 = ops.zeros(2 * B * F)
+        ops.bn_bwd_stats(dy2, self.xhat, sums2)
+        ops.axpy(1.0, sums2[B * F:].view(B, F).sum(0), ctx.g(self.gamma))
+        ops.axpy(1.0, sums2[:B * F].view(B, F).sum(0), ctx.g(self.beta))
+        dx = ops.empty(T, B, F)
+        ops.bn_bwd_apply(dy2, self.xhat, sums2, float(T), self.gamma_t, self.invstd, dx.view(T, B * F), None, None)
+        self.xhat = None
+        return dx
+
+
 class LSTMLayerOp:
     """One LSTMCell layer under dynamic_rnn (cells.py:14-18, encoder.py:80)."""
 

@@ -63,6 +63,8 @@ CASES = [
     (3, dict(highway_encoder=True)), (4, dict(highway_encoder=True, encoder_weight_sharing=True)),
     # enable_attention=False (decoder_unimodal.py:319-327): the bare decoder cell started from the encoder state
     (1, dict(enable_attention=False)), (4, dict(enable_attention=False)), (5, dict(enable_attention=False)),
+    # instance_norm on the (batch-normalised) inputs (encoder.py:51-55)
+    (1, dict(instance_normalisation=True)), (5, dict(instance_normalisation=True, batch_normalisation=False)),
 ]
 
 
@@ -102,6 +104,8 @@ def test_loss_states_contexts_and_gradients(cfg, over, tensor_cores):
     assert abs(gnorm - gn_ref) <= 5e-3 * gn_ref, (gnorm, gn_ref)
     gmax = max(np.abs(g).max() for g in G_ref.values())
     gtol = 1.5e-2 if tensor_cores else 1e-3  # gradients pass through ~2x as many tf32 products as the states
+    if tensor_cores and over.get('instance_normalisation'):
+        gtol = 2e-2  # (features normalised per utterance over 40 frames: the layer-0 weight gradient of config 1 sits at 1.6e-2)
     for name, g_ref in G_ref.items():
         scale = max(np.abs(g_ref).max(), 1e-3 * gmax)
         got = G[name].astype(np.float64)

@@ -49,6 +49,9 @@ CASES += [
     # enable_attention=False (decoder_unimodal.py:319-327): the bare decoder cell started from the encoder state
     (1, dict(enable_attention=False)), (4, dict(DROP, enable_attention=False, sampling_probability_outputs=0.5)),
     (5, dict(enable_attention=False)),
+    # instance_norm on the (batch-normalised) inputs (encoder.py:51-55)
+    (1, dict(instance_normalisation=True)), (5, dict(DROP, instance_normalisation=True, batch_normalisation=False)),
+    (2, dict(instance_normalisation=True, input_dense_layers=(5,))),
     # one-hot decoder inputs (decoder_unimodal.py:75-76: embedding_size <= 0 -> tf.eye)
     (1, dict(embedding_size=0)), (5, dict(DROP, embedding_size=-1, sampling_probability_outputs=0.5)),
 ]
