@@ -89,6 +89,7 @@ PROTOTYPES = {
     'avsr_embedding_fwd': (_I, [_P, _P, _I, _I, _P, _L, _P]),
     'avsr_embedding_bwd': (_I, [_P, _P, _P, _L, _I, _I, _P]),
     'avsr_seq_loss': (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _F, _P, _P]),
+    'avsr_seq_loss_devel': (_I, [_P, _P, _I, _I, _I, _P, _I, _P, _P, _I, _F, _P, _P]),
     'avsr_au_loss': (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     'avsr_sumsq': (_I, [_P, _P, _L, _P]),
     'avsr_axpy': (_I, [_P, _F, _P, _P, _L]),

@@ -341,6 +341,71 @@ __global__ void seq_loss_kernel(const float* __restrict__ logits, int T, int B, 
   if (lane == 0) atomicAdd(loss_sum, lse - on * z[y] - off * zs);
 }
 
+// devel.py losses as `softmax_loss_function` of sequence_loss (seq2seq.py:156-163; devel.py:12-52, "not tested thoroughly"
+// by its authors): per token, with p = clip(softmax(z), 1e-7, 1 - 1e-7) and y the label,
+//   mc_loss    = - log p_y - sum_{k != y} log(1 - p_k)
+//   focal_loss = - (1 - p_y)^g log p_y - sum_{k != y} p_k^g log(1 - p_k)          (g = 2)
+// masked and normalised like the cross-entropy (weights = sequence_mask, / token count).  Gradient: dL/dp through the
+// clip (zero where it clipped) and the softmax Jacobian.  One warp per (t, b) row.
+__global__ void seq_loss_devel_kernel(const float* __restrict__ logits, int T, int B, int V, const int* __restrict__ labels,
+                                      int ldl, const int* __restrict__ labels_len, const float* __restrict__ inv_denom_dev,
+                                      int kind, float gamma, float* __restrict__ loss_sum, float* __restrict__ dlogits) {
+  const float inv_denom = inv_denom_dev[0];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= T * B) return;
+  const int t = warp / B, b = warp - t * B;
+  const float* z = logits + (size_t)warp * V;
+  float* dz = dlogits + (size_t)warp * V;
+  if (t >= labels_len[b]) {
+    for (int v = lane; v < V; v += 32) dz[v] = 0.0f;
+    return;
+  }
+  float mx = -INFINITY;
+  for (int v = lane; v < V; v += 32) mx = fmaxf(mx, z[v]);
+  mx = warp_max(mx);
+  float se = 0.0f;
+  for (int v = lane; v < V; v += 32) se += expf(z[v] - mx);
+  se = warp_sum(se);
+  const float lse = logf(se) + mx;
+  const int y = labels[(size_t)b * ldl + t];
+  float loss = 0.0f, dot = 0.0f;
+  for (int v = lane; v < V; v += 32) {
+    const float sv = expf(z[v] - lse);
+    const float p = fminf(fmaxf(sv, 1e-7f), 1.0f - 1e-7f);
+    const bool inside = sv >= 1e-7f && sv <= 1.0f - 1e-7f;
+    float L, g;
+    if (kind == 1) {  // mc_loss
+      if (v == y) { L = -logf(p); g = -1.0f / p; }
+      else { L = -logf(1.0f - p); g = 1.0f / (1.0f - p); }
+    } else {          // focal_loss
+      if (v == y) {
+        const float q = 1.0f - p, qg = powf(q, gamma);
+        L = -qg * logf(p);
+        g = gamma * powf(q, gamma - 1.0f) * logf(p) - qg / p;
+      } else {
+        const float pg = powf(p, gamma);
+        L = -pg * logf(1.0f - p);
+        g = -gamma * powf(p, gamma - 1.0f) * logf(1.0f - p) + pg / (1.0f - p);
+      }
+    }
+    loss += L;
+    dot += inside ? sv * g : 0.0f;
+  }
+  loss = warp_sum(loss);
+  dot = warp_sum(dot);
+  for (int v = lane; v < V; v += 32) {  // (recomputed: V <= a few dozen classes)
+    const float sv = expf(z[v] - lse);
+    const float p = fminf(fmaxf(sv, 1e-7f), 1.0f - 1e-7f);
+    const bool inside = sv >= 1e-7f && sv <= 1.0f - 1e-7f;
+    float g;
+    if (kind == 1) g = v == y ? -1.0f / p : 1.0f / (1.0f - p);
+    else if (v == y) g = gamma * powf(1.0f - p, gamma - 1.0f) * logf(p) - powf(1.0f - p, gamma) / p;
+    else g = -gamma * powf(p, gamma - 1.0f) * logf(1.0f - p) + powf(p, gamma) / (1.0f - p);
+    dz[v] = sv * ((inside ? g : 0.0f) - dot) * inv_denom;
+  }
+  if (lane == 0) atomicAdd(loss_sum, loss);
+}
+
 // Action-Unit head: one thread per (t, b, k)
 __global__ void au_loss_kernel(const float* __restrict__ z, int T, int B, const float* __restrict__ aus,
                                const int* __restrict__ len, const float* __restrict__ scale_dev,
@@ -943,6 +1008,16 @@ int avsr_seq_loss(avsr_stream_t s, const float* logits, int T, int B, int V, con
   if (T * B <= 0) return 0;
   AVSR_LAUNCH(seq_loss_kernel, cdiv((long long)T * B * 32, 256), 256, 0, ST(s), logits, T, B, V, labels, ldl,
               labels_len, inv_denom, label_smoothing, loss_sum, dlogits);
+  return 0;
+}
+
+int avsr_seq_loss_devel(avsr_stream_t s, const float* logits, int T, int B, int V, const int* labels, int ldl,
+                        const int* labels_len, const float* inv_denom, int kind, float gamma, float* loss_sum,
+                        float* dlogits) {
+  AVSR_REQUIRE(kind == 1 || kind == 2, "seq_loss_devel: kind must be 1 (mc_loss) or 2 (focal_loss)");
+  if (T * B <= 0) return 0;
+  AVSR_LAUNCH(seq_loss_devel_kernel, cdiv((long long)T * B * 32, 256), 256, 0, ST(s), logits, T, B, V, labels, ldl,
+              labels_len, inv_denom, kind, gamma, loss_sum, dlogits);
   return 0;
 }
 

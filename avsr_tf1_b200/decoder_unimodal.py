@@ -154,8 +154,11 @@ class Seq2SeqUnimodalDecoder(object):
                      bias=ctx.p(self._bd))
         self._out = out
         self._dlogits = torch.empty_like(self._logits)
-        ops.seq_loss(self._logits, labels, labels_len, inv_denom, loss_sum, self._dlogits,
-                     label_smoothing=float(self._hparams.label_smoothing))
+        if self._hparams.loss_fun is not None:  # devel.py focal_loss / mc_loss (seq2seq.py:156-163)
+            ops.seq_loss_devel(self._logits, labels, labels_len, inv_denom, loss_sum, self._dlogits, self._hparams.loss_fun)
+        else:
+            ops.seq_loss(self._logits, labels, labels_len, inv_denom, loss_sum, self._dlogits,
+                         label_smoothing=float(self._hparams.label_smoothing))
         return self._logits
 
     def _forward_train_sampled(self, memories, init, dec_in_ids, labels_len, T, B):

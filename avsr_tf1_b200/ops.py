@@ -190,6 +190,18 @@ def seq_loss(logits, labels, labels_len, inv_denom, loss_sum, dlogits, label_smo
                                     dlogits.data_ptr()))
 
 
+LOSS_FUNS = {'mc_loss': 1, 'focal_loss': 2}
+
+
+def seq_loss_devel(logits, labels, labels_len, inv_denom, loss_sum, dlogits, loss_fun, gamma=2.0):
+    """devel.py's mc_loss / focal_loss under sequence_loss (include/avsr_b200.h avsr_seq_loss_devel)."""
+    T, B, V = logits.shape
+    inv = _dev_scalar(inv_denom)
+    check(_lib.load().avsr_seq_loss_devel(_stream(), logits.data_ptr(), T, B, V, labels.data_ptr(), labels.stride(0),
+                                          labels_len.data_ptr(), inv.data_ptr(), LOSS_FUNS[loss_fun], float(gamma),
+                                          loss_sum.data_ptr(), dlogits.data_ptr()))
+
+
 def au_loss(z, aus, lens, scale_dev, loss_sum, dz):
     """Action-Unit head loss (include/avsr_b200.h avsr_au_loss): z [T,B,2], aus [B,T,2]."""
     T, B, _ = z.shape

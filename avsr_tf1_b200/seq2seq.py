@@ -246,9 +246,8 @@ class Seq2SeqModel(object):
 
     def _init_optimiser(self):
         hp = self._hparams
-        if hp.loss_fun is not None:
-            raise ValueError('Unknown loss function {}'.format(hp.loss_fun)) if hp.loss_fun not in (
-                'focal_loss', 'mc_loss') else NotImplementedError('devel.py losses are self-described untested')
+        if hp.loss_fun is not None and hp.loss_fun not in ops.LOSS_FUNS:  # focal_loss / mc_loss (seq2seq.py:156-163)
+            raise ValueError('Unknown loss function {}'.format(hp.loss_fun))
         if hp.optimiser not in ops.OPTIMISERS:  # Adam, Nadam, AdamW, Momentum (seq2seq.py:195-219)
             raise Exception('Unsupported optimiser, try Adam')
         self._l2_names = [n for n in self.store.names() if 'lstm_' in n and 'bias' not in n]  # seq2seq.py:283-290

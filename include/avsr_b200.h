@@ -256,6 +256,13 @@ int avsr_seq_loss(avsr_stream_t stream, const float* logits, int T, int B, int V
                   const int* labels_len, const float* inv_denom_dev, float label_smoothing, float* loss_sum,
                   float* dlogits);
 
+/* devel.py's per-token losses as `softmax_loss_function` of seq2seq.sequence_loss (seq2seq.py:156-163, devel.py:12-52):
+ * kind 1 = mc_loss, 2 = focal_loss (gamma, 2.0 in the reference), on p = clip(softmax(logits), 1e-7, 1 - 1e-7); masked by
+ * the label lengths and scaled by inv_denom like avsr_seq_loss; dlogits receives the gradient. */
+int avsr_seq_loss_devel(avsr_stream_t stream, const float* logits, int T, int B, int V, const int* labels, int ldl,
+                        const int* labels_len, const float* inv_denom, int kind, float gamma, float* loss_sum,
+                        float* dlogits);
+
 /* ---- Action-Unit regression head of the video encoder (encoder.py:173-189, seq2seq.py:188-190) -------------------
  * z [T,B,2] = encoder outputs @ video/dense/kernel + bias (pre-sigmoid); aus [B,T,2] as the reader delivers them
  * (batch-major payload, io_utils.py:45-46).  tf.losses.mean_squared_error(sigmoid(z), clip(aus,0,3)/3, weights =

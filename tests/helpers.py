@@ -53,7 +53,7 @@ def oracle_hparams(hp, model=None):
     rand.update(regress_aus=bool(hp.regress_aus), au_loss_weight=hp.kwargs.get('au_loss_weight', 10.0),
                 input_dense_layers=tuple(hp.input_dense_layers), residual_encoder=bool(hp.residual_encoder),
                 highway_encoder=bool(hp.highway_encoder), enable_attention=hp.enable_attention is True,
-                instance_normalisation=bool(hp.instance_normalisation),
+                instance_normalisation=bool(hp.instance_normalisation), loss_fun=hp.loss_fun,
                 encoder_weight_sharing=bool(hp.encoder_weight_sharing), label_smoothing=float(hp.label_smoothing),
                 video_processing=hp.video_processing, cnn_filters=tuple(hp.kwargs.get('cnn_filters', (8, 16, 32, 64))))
     return OracleHParams(

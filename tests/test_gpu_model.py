@@ -65,6 +65,7 @@ CASES = [
     (1, dict(enable_attention=False)), (4, dict(enable_attention=False)), (5, dict(enable_attention=False)),
     # instance_norm on the (batch-normalised) inputs (encoder.py:51-55)
     (1, dict(instance_normalisation=True)), (5, dict(instance_normalisation=True, batch_normalisation=False)),
+    (1, dict(loss_fun='mc_loss')), (5, dict(loss_fun='focal_loss')),  # devel.py losses under sequence_loss (seq2seq.py:156-163)
 ]
 
 

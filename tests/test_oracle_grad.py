@@ -52,6 +52,8 @@ CASES += [
     # instance_norm on the (batch-normalised) inputs (encoder.py:51-55)
     (1, dict(instance_normalisation=True)), (5, dict(DROP, instance_normalisation=True, batch_normalisation=False)),
     (2, dict(instance_normalisation=True, input_dense_layers=(5,))),
+    # devel.py losses under sequence_loss (seq2seq.py:156-163)
+    (1, dict(loss_fun='mc_loss')), (5, dict(DROP, loss_fun='focal_loss')),
     # one-hot decoder inputs (decoder_unimodal.py:75-76: embedding_size <= 0 -> tf.eye)
     (1, dict(embedding_size=0)), (5, dict(DROP, embedding_size=-1, sampling_probability_outputs=0.5)),
 ]
