@@ -237,3 +237,35 @@ def test_checkpoint_is_written_atomically(tmp_path):
     assert latest_checkpoint(str(tmp_path)) == ckp + '-20'
     assert not (tmp_path / 'checkpoint.ckp-10.npz').exists()  # max_to_keep = 1, removed only after the rename
     assert not (tmp_path / 'checkpoint.ckp-20.tmp.npz').exists()
+
+
+def test_variable_tables_of_the_round_2_options():
+    """Names / shapes the non-default options add or remove (TF scopes of the reference graph)."""
+    def table(cfg, **over):
+        _, m = build(cfg, **over)
+        return {n: tuple(m.store.p(n).shape) for n in m.store.names()}
+    # HighwayWrapper: carry variables in the position's own scope, per position even with the shared cell (cells.py:77-92)
+    t = table(3, highway_encoder=True, encoder_weight_sharing=True)
+    for k in (1, 2):
+        assert t[f'video/Encoder/multi_rnn_cell/cell_{k}/carry_w'] == (256, 256)
+        assert t[f'video/Encoder/multi_rnn_cell/cell_{k}/carry_b'] == (256,)
+    assert 'video/Encoder/multi_rnn_cell/cell_0/carry_w' not in t
+    assert 'video/Encoder/multi_rnn_cell/cell_2/lstm_cell/kernel' not in t  # layers 2.. run with the cell of layer 1
+    # enable_attention=False: the bare cell lives in the decoder scope; no mechanism, no memory layer
+    t = table(1, enable_attention=False)
+    assert t['Decoder/decoder/lstm_cell/kernel'] == (128 + 128, 4 * 128)
+    assert not any('attention' in n or 'memory_layer' in n for n in t)
+    # one-hot decoder inputs: tf.eye is a constant, the cell input is the alphabet
+    t = table(1, embedding_size=0)
+    assert 'embeddings/embedding_matrix' not in t
+    assert t['Decoder/decoder/attention_wrapper/lstm_cell/kernel'] == (31 + 128 + 128, 4 * 128)
+    # instance_norm after the batch norm
+    t = table(5, instance_normalisation=True)
+    assert t['audio/InstanceNorm/gamma'] == (80,) and t['video/InstanceNorm/beta'] == (128,)
+    assert t['audio/batch_normalization/gamma'] == (80,)
+    # bimodal decoder with the video stream missing: one mechanism, zero state of the FIRST layer's width in the projection
+    t = table(4, video_processing=None)
+    assert t['Decoder/state_projection/kernel'] == (256 + 256, 256)
+    assert 'Decoder/memory_layer_1/kernel' not in t and t['Decoder/memory_layer/kernel'] == (256, 256)
+    assert t['Decoder/decoder/attention_wrapper/lstm_cell/kernel'] == (128 + 256 + 256, 4 * 256)
+    assert not any(n.startswith('video/') for n in t)
