@@ -491,7 +491,7 @@ class Seq2SeqModel(object):
             # exact large-batch loss denominator (seq2seq.sequence_loss, seq2seq.py:165-171): the token count of the
             # GLOBAL batch, summed over ranks on the device inside the step (no host round trip, graph-capturable)
             tok = b['labels_len'].sum(dtype=torch.float32).reshape(1)
-            if self._hparams.label_smoothing > 0.0:  # the smoothed loss is the unmasked mean over all positions
+            if self._hparams.label_smoothing > 0.0 and self._hparams.loss_fun is None:  # smoothed loss: unmasked mean
                 tok = torch.full((1,), float(b['labels_len'].shape[0] * b['T_dec']), dtype=torch.float32, device=tok.device)
             self._ctx.allreduce(tok)
             torch.reciprocal(tok + 1e-12, out=self._scal_dev[0:1])
@@ -597,7 +597,7 @@ class Seq2SeqModel(object):
         # power-of-two operand scale of the backward kernels.
         n_tok = self._meta['n_tokens'] * ctx.world_size
         self._inv_denom = 1.0 / (n_tok + 1e-12)  # seq2seq.sequence_loss
-        if self._hparams.label_smoothing > 0.0:
+        if self._hparams.label_smoothing > 0.0 and self._hparams.loss_fun is None:  # (loss_fun takes precedence, seq2seq.py:147-163)
             # seq2seq.py:147-155: smoothed_cross_entropy (devel.py:54-61) returns a reduced scalar - the mean over ALL
             # B x T positions, padding included - which sequence_loss multiplies by the weights and divides by their sum
             self._inv_denom = 1.0 / (self._meta['n_positions'] * ctx.world_size)
