@@ -237,8 +237,10 @@ class Seq2SeqEncoder(object):
             if getattr(op, 'highway', None):  # HighwayWrapper (cells.py:89-90) around the (dropout-wrapped) cell
                 T_, B_, D_ = cur.shape
                 pre = ops.empty(T_, B_, D_)
-                ops.gemm(cur_op.reshape(T_ * B_, D_), ctx.w(op.highway[0]), pre.view(T_ * B_, D_), bias=ctx.p(op.highway[1]))
-                op.hw_saved = (cur, cur_op, pre, out)
+                # (the carry product's operand: rounded here - under dropout a layer hands back its exact outputs)
+                x_op = ops.round_tf32(cur) if ops.tensor_cores_enabled() else cur
+                ops.gemm(x_op.reshape(T_ * B_, D_), ctx.w(op.highway[0]), pre.view(T_ * B_, D_), bias=ctx.p(op.highway[1]))
+                op.hw_saved = (cur, x_op, pre, out)
                 cur, cur_op = ops.highway_fwd(cur, pre, out)
             elif getattr(op, 'residual', False):  # ResidualWrapper (cells.py:91-92): + the layer's (un-dropped) input
                 cur = out + cur
