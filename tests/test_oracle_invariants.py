@@ -235,3 +235,46 @@ def test_beam_search_step_known_answer():
     tie = np.log(np.array([[[0.25, 0.25, 0.5], [0.25, 0.25, 0.5]]]))
     word, parent, *_ = O.beam_search_step(tie, np.array([[0.0, 0.0]]), np.zeros((1, 2), bool), np.ones((1, 2), np.int64), eos, 0.0)
     assert word.tolist() == [[2, 2]] and parent.tolist() == [[0, 1]]
+
+
+def test_devel_losses_known_answers():
+    """devel.py:12-52 on uniform logits over 3 classes (p = 1/3 each), label 0, worked by hand:
+    mc_loss = -ln(1/3) - 2 ln(2/3); focal_loss (gamma 2) = -(2/3)^2 ln(1/3) - 2 (1/3)^2 ln(2/3)."""
+    z = np.zeros((1, 1, 3))
+    y = np.zeros((1, 1), np.int64)
+    lens = np.array([1])
+    mc, dmc = O.sequence_loss_fwd_bwd(z, y, lens, loss_fun='mc_loss')
+    fo, dfo = O.sequence_loss_fwd_bwd(z, y, lens, loss_fun='focal_loss')
+    # (sequence_loss divides by token count + 1e-12)
+    assert abs(mc - (-np.log(1 / 3) - 2 * np.log(2 / 3))) < 1e-10
+    assert abs(fo - (-(2 / 3) ** 2 * np.log(1 / 3) - 2 * (1 / 3) ** 2 * np.log(2 / 3))) < 1e-10
+    # softmax Jacobian at the uniform point: dz_j = p (g_j - mean(g)), g = dL/dp; rows of a softmax gradient sum to zero
+    g = np.array([-3.0, 1.5, 1.5])  # mc_loss: -1/p for the label, 1/(1-p) otherwise
+    np.testing.assert_allclose(dmc[0, 0], (g - g.mean()) / 3, atol=1e-10)
+    assert abs(dfo.sum()) < 1e-12 and dfo[0, 0, 0] < 0 < dfo[0, 0, 1]
+    # past the label length nothing contributes
+    z2 = np.zeros((1, 2, 3))
+    mc2, d2 = O.sequence_loss_fwd_bwd(z2, np.zeros((1, 2), np.int64), lens, loss_fun='mc_loss')
+    assert abs(mc2 - mc) < 1e-10 and np.all(d2[0, 1] == 0.0)
+
+
+def test_highway_and_instance_norm_known_answers():
+    """HighwayWrapper (cells.py:89-90; zero carry kernel, carry bias 1 -> carry = sigmoid(1) everywhere) around a cell
+    whose weights are zero (h = o tanh(c) = 0): the output is the carried input alone.  instance_norm: a feature that
+    runs 0, 1, 2 along time normalises to -sqrt(1.5), 0, sqrt(1.5) (variance 2/3, epsilon 1e-6)."""
+    B, T, H = 1, 3, 2
+    x = np.array([[[1.0, -2.0], [0.5, 0.25], [3.0, 0.0]]])
+    zero_layer = (np.zeros((2 * H, 4 * H)), np.zeros(4 * H))
+    out, _, _ = O.stacked_lstm_fwd(x, np.array([T]), [zero_layer, zero_layer],
+                                   highway=[None, (np.zeros((H, H)), np.ones(H))])
+    # layer 0 emits zeros, so layer 1 carries zeros: feed x straight into the wrapped layer instead
+    out1, _, _ = O.stacked_lstm_fwd(x, np.array([T]), [zero_layer], highway=[(np.zeros((H, H)), np.ones(H))])
+    carry = 1.0 / (1.0 + np.exp(-1.0))
+    np.testing.assert_allclose(out, 0.0, atol=1e-15)
+    np.testing.assert_allclose(out1, x * carry, atol=1e-12)
+    hp = O.OracleHParams(batch_normalisation=False, instance_normalisation=True)
+    P = {'audio/InstanceNorm/gamma': np.array([2.0]), 'audio/InstanceNorm/beta': np.array([0.5])}
+    om = O.OracleModel(hp, P)
+    y = om._bn('audio', np.array([[[0.0], [1.0], [2.0]]]), True, {})
+    ref = np.array([-1.0, 0.0, 1.0]) / np.sqrt(2.0 / 3.0 + 1e-6) * 2.0 + 0.5
+    np.testing.assert_allclose(y[0, :, 0], ref, atol=1e-12)
